@@ -1,0 +1,131 @@
+/* unidom_b200 -- C ABI of the B200-native DaXBench simulator step.
+ *
+ * Drop-in boundary: these entry points are what an
+ * XLA-FFI / ctypes / cgo binding for the reference's
+ *   SimpleMPMSimulator.step_jax   (DaXBench/daxbench/core/engine/mpm_simulator.py:61-63, 413-429)
+ *   ClothSimulator.step_jax       (DaXBench/daxbench/core/engine/cloth_simulator.py:68-70, 163-180)
+ * binds, at `step` granularity (one call = all `conf.steps` MPM substeps or
+ * all 50 cloth substeps of one sub-action, batched over num_envs).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name says host;
+ *   - float = IEEE binary32, int32 indices, row-major arrays in the reference's
+ *     own leaf shapes (the pytree order of MPMState / PrimitiveState / ClothState);
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*):
+ *     it never synchronises, never allocates and never throws;
+ *   - `workspace` is caller-owned scratch of at least *_workspace_bytes() bytes,
+ *     256-byte aligned; contents are undefined between calls except where a
+ *     bwd call documents that it consumes what the matching fwd call left;
+ *   - return value: 0 = enqueued, <0 = UD_E_* (nothing was enqueued).
+ */
+#ifndef UNIDOM_B200_H
+#define UNIDOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UD_MAX_PRIM 4
+
+#define UD_OK 0
+#define UD_E_INVALID (-1)   /* bad shape / parameter / null pointer   */
+#define UD_E_WORKSPACE (-2) /* workspace too small or misaligned      */
+#define UD_E_CUDA (-3)      /* a launch failed (cudaGetLastError)     */
+
+#define UD_SDF_BOX 0        /* core/engine/primitives/box.py:6-18       */
+#define UD_SDF_CONTAINER 1  /* core/engine/primitives/container.py:8-16 */
+
+#define UD_P2G_ATOMIC 0        /* vector RED per touched cell (fast, order-nondeterministic)   */
+#define UD_P2G_DETERMINISTIC 1 /* sorted per-cell gather (bit-reproducible run to run)         */
+
+/* Scalars of the reference's per-task DefaultConf (e.g. envs/shape_elasto_plastic.py:23-54).
+ * Doubles are the Python floats of the conf; the library folds derived constants in
+ * double and rounds to float exactly where the reference's expressions do. */
+typedef struct ud_mpm_params {
+  int32_t num_envs;          /* B: batch_size (mpm_simulator.py:34)                      */
+  int32_t n_particles;       /* n per env (mpm_simulator.py:154)                         */
+  int32_t steps;             /* S = conf.steps: substeps per step and rows of the tables */
+  int32_t res[3];            /* conf.res                                                 */
+  int32_t n_grid;            /* conf.n_grid (upper wall test uses this, :312)            */
+  double dt, dx, inv_dx;     /* conf.dt, conf.dx, conf.inv_dx                            */
+  double p_mass, p_vol;      /* conf.p_mass, conf.p_vol                                  */
+  double gravity[3];         /* conf.gravity                                             */
+  int32_t n_primitive;       /* conf.n_primitive, <= UD_MAX_PRIM                         */
+  int32_t sdf_kind;          /* UD_SDF_* (the reference's global set_sdf, primitives.py:26) */
+  int32_t use_position_control; /* mpm_simulator.py:289                                  */
+  int32_t p2g_mode;          /* UD_P2G_*                                                 */
+} ud_mpm_params;
+
+/* Float leaves of one PrimitiveState (primitives.py:9-23), batched on axis 0. */
+typedef struct ud_primitive {
+  float* size;          /* [B,3]   */
+  float* friction;      /* [B]     */
+  float* softness;      /* [B]  (the int leaf 666 as float; never differentiated) */
+  float* position;      /* [B,S,3] */
+  float* rotation;      /* [B,S,4] */
+  float* v;             /* [B,S,3] */
+  float* w;             /* [B,S,3] */
+  float* action_buffer; /* [B,6]   */
+  float* action_scale;  /* [B,6]   */
+} ud_primitive;
+
+/* Float leaves of MPMState (mpm_simulator.py:13-24), batched on axis 0.
+ * cur_step / key are pass-through in the step and stay on the host side. */
+typedef struct ud_mpm_state {
+  float* x;        /* [B,n,3]   */
+  float* v;        /* [B,n,3]   */
+  float* C;        /* [B,n,3,3] */
+  float* F;        /* [B,n,3,3] */
+  float* J;        /* [B,n]     */
+  float* friction; /* [B] (leaf shape (B,1)) */
+  float* mu;       /* [B]       */
+  float* lamda;    /* [B]       */
+  ud_primitive prim[UD_MAX_PRIM];
+} ud_mpm_state;
+
+const char* ud_version(void);
+/* Name of the last failing check of the calling thread (for error messages). */
+const char* ud_last_error(void);
+
+/* Bytes of workspace for one fwd call / for a fwd(save=1)+bwd pair. */
+size_t ud_mpm_fwd_workspace_bytes(const ud_mpm_params* p);
+size_t ud_mpm_bwd_workspace_bytes(const ud_mpm_params* p);
+
+/* Replaces vmap(jit(step)) (mpm_simulator.py:61-63,413-429): norm_grad_state fwd
+ * (nan_to_num), action clip, set_action, S x substep, copy_frame.
+ * material [n] int32 and h [n] float are SimpleMPMSimulator.material / .h
+ * (mpm_simulator.py:112-122), shared by all envs.  action is [B, 6*n_primitive].
+ * `out` must not alias `in`. */
+int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material,
+                    const float* h, const float* action, ud_mpm_state* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* Reverse-mode of the same step (replaces substep_wrapper's VJP :332-363, copy_frame,
+ * set_action, action clip, norm_grad_state/norm_grad bwd :389-408).  Recomputes the S
+ * substeps from `in` (checkpoint = the step input) inside `workspace`, then reverses.
+ * `gout` holds the cotangents of the step output leaves (carry + ys already summed),
+ * `gin` receives the cotangents of the input leaves, `gaction` [B, 6*n_primitive].
+ * Null pointers inside gout mean "zero cotangent"; null pointers inside gin mean
+ * "not wanted". */
+int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material,
+                    const float* h, const float* action, const ud_mpm_state* gout,
+                    ud_mpm_state* gin, float* gaction, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* The per-frame binning the step uses, exposed for the bit-exactness check:
+ * base = int32(x*inv_dx - 0.5) (mpm_simulator.py:233, no FMA contraction),
+ * key  = 4x4x4-block-major cell key, perm = stable argsort(key) per env.
+ * out_base [B,n,3], out_key [B,n], out_perm [B,n] (int32). */
+int ud_mpm_sort_bins(const ud_mpm_params* p, const float* x, int32_t* out_base, int32_t* out_key,
+                     int32_t* out_perm, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of keys per env used by ud_mpm_sort_bins (for sizing host-side checks). */
+int32_t ud_mpm_num_keys(const ud_mpm_params* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIDOM_B200_H */

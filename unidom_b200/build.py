@@ -1,0 +1,76 @@
+"""Build libunidom_b200.so in-tree with nvcc for sm_100a (no torch types, pure C ABI).
+
+Usage: python -m unidom_b200.build [--force]
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libunidom_b200.so")
+STAMP = os.path.join(HERE, "csrc", ".build_stamp")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+# (source, extra flags).  The grid/cell units carry fp32 finite-difference normals: no FMA contraction.
+UNITS = [
+    ("abi.cu", []),
+    ("mpm_particles.cu", []),
+    ("mpm_grid.cu", ["--fmad=false"]),
+    ("cloth.cu", []),
+]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _digest():
+    h = hashlib.sha256()
+    for root, _, files in sorted(os.walk(CSRC)):
+        for f in sorted(files):
+            if f.endswith((".cu", ".cuh", ".h")):
+                h.update(f.encode())
+                h.update(open(os.path.join(root, f), "rb").read())
+    h.update(open(os.path.join(HERE, "..", "include", "unidom_b200.h"), "rb").read())
+    h.update(repr((ARCH, COMMON, UNITS)).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    digest = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read() == digest:
+        return LIB
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    for src, extra in UNITS:
+        path = os.path.join(CSRC, src)
+        if not os.path.exists(path):
+            continue
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", path, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        if verbose or pr.returncode:
+            print(" ".join(cmd))
+            print(out)
+        if pr.returncode:
+            raise RuntimeError("nvcc failed for " + cmd[-3])
+    cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"]
+    subprocess.check_call(cmd)
+    open(STAMP, "w").write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

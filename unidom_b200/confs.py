@@ -1,0 +1,88 @@
+"""Scene configurations: the scalar fields of the reference's per-task DefaultConf classes.
+
+Each class cites the reference conf it restates; `synthetic_*` helpers build the scaled-up scenes
+BASELINE.json names.  Host-side only (no arithmetic of the hot path here).
+"""
+from dataclasses import dataclass, field
+from typing import Tuple
+
+from . import _lib
+
+
+@dataclass
+class MPMConf:
+    n_grid: int = 64
+    res: Tuple[int, int, int] = (32, 32, 32)
+    dt: float = 1e-4
+    steps: int = 16
+    E: float = 100.0
+    nu: float = 0.1
+    ground_friction: float = 0.1
+    gravity: Tuple[float, float, float] = (0.0, -9.8, 0.0)
+    n_primitive: int = 1
+    sdf_kind: int = _lib.UD_SDF_BOX
+    use_position_control: bool = False
+    p_rho: float = 1.0
+    seed: int = 1
+    task: str = ""
+
+    @property
+    def dx(self):
+        return 1 / self.n_grid
+
+    @property
+    def inv_dx(self):
+        return float(self.n_grid)
+
+    @property
+    def p_vol(self):
+        return (self.dx * 0.5) ** 2
+
+    @property
+    def p_mass(self):
+        return self.p_vol * self.p_rho
+
+
+def shape_elasto_plastic_conf():
+    """envs/shape_elasto_plastic.py:23-54 ("push_plasticine", BASELINE config 2)."""
+    n_grid = 96
+    return MPMConf(n_grid=n_grid, res=(n_grid // 2, n_grid // 3, n_grid // 2), dt=2e-4, steps=16, E=2, nu=0.2,
+                   ground_friction=2, n_primitive=1, sdf_kind=_lib.UD_SDF_BOX, task="shape_elasto_plastic")
+
+
+def shape_rope_conf():
+    """envs/shape_rope_env.py:26-62."""
+    n_grid = 128
+    dt = 0.5e-4
+    return MPMConf(n_grid=n_grid, res=(n_grid // 2, 6, n_grid // 2), dt=dt, steps=int(0.2 / 30 / dt), E=100, nu=0.1,
+                   ground_friction=0.9, n_primitive=1, sdf_kind=_lib.UD_SDF_BOX, task="shape_rope")
+
+
+def whip_rope_conf():
+    """envs/whip_rope_env.py:27-73."""
+    n_grid = 64
+    dt = 1e-4
+    return MPMConf(n_grid=n_grid, res=(n_grid // 2,) * 3, dt=dt, steps=int(0.007 / 1 / dt), E=100, nu=0.1,
+                   ground_friction=0.1, n_primitive=1, sdf_kind=_lib.UD_SDF_BOX, use_position_control=True,
+                   task="whip_rope")
+
+
+def pour_water_conf(res=None):
+    """envs/pour_water_env.py:28-60."""
+    n_grid = 80
+    dt = 3e-4
+    return MPMConf(n_grid=n_grid, res=res or (n_grid // 3, n_grid // 4, n_grid // 3), dt=dt,
+                   steps=int(0.007 / 1 / dt), E=0.00005, nu=0.4999, ground_friction=0.1, n_primitive=2,
+                   sdf_kind=_lib.UD_SDF_CONTAINER, task="pour_water")
+
+
+def build_shape_elasto_plastic(sim, density=3.0):
+    """reset() of envs/shape_elasto_plastic.py:139-157.  density=3.9 gives the 50 625-particle
+    synthetic scale-up of BASELINE config 2."""
+    from .mpm_simulator import create_primitive
+    conf = sim.conf
+    state = sim.add_box(conf=conf, state=None, hardness=1.0, size=[0.2, 0.06, 0.12], init_pos=[0.5, 0.07, 0.5],
+                        z_rotation_angle=0, material=2, density=density)
+    state.primitives.append(create_primitive(conf, friction=0.1, softness=666, color=[0.5, 0.5, 0.5],
+                                             size=[0.015, 0.06, 0.015], init_pos=[0.5, 0.01, 0.45]))
+    return sim.reset_jax(state)

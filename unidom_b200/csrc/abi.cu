@@ -1,0 +1,197 @@
+// C ABI of unidom_b200 (see include/unidom_b200.h): validation, constant folding, workspace carving
+// and the per-step launch sequences.  Nothing here synchronises or allocates.
+#include <stdio.h>
+#include <string.h>
+
+#include "mpm_internal.h"
+
+namespace ud {
+
+static thread_local const char* g_last_error = "";
+static int fail(int code, const char* what) {
+  g_last_error = what;
+  return code;
+}
+
+bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k) {
+  if (!p) return false;
+  if (p->num_envs < 1 || p->n_particles < 1 || p->steps < 1) return false;
+  if (p->res[0] < 1 || p->res[1] < 1 || p->res[2] < 1 || p->n_grid < 1) return false;
+  if (p->n_primitive < 0 || p->n_primitive > UD_MAX_PRIM) return false;
+  if (p->sdf_kind != UD_SDF_BOX && p->sdf_kind != UD_SDF_CONTAINER) return false;
+  if (!(p->dt > 0) || !(p->dx > 0) || !(p->inv_dx > 0) || !(p->p_mass > 0) || !(p->p_vol > 0)) return false;
+  long long N = (long long)p->num_envs * p->n_particles;
+  long long G = (long long)p->res[0] * p->res[1] * p->res[2];
+  if (N > 0x7fffffffLL / 32 || G > 0x7fffffffLL / 4) return false;
+  memset(k, 0, sizeof(*k));
+  k->B = p->num_envs;
+  k->n = p->n_particles;
+  k->S = p->steps;
+  k->N = (int)N;
+  k->G = (int)G;
+  k->rx = p->res[0];
+  k->ry = p->res[1];
+  k->rz = p->res[2];
+  k->n_grid = p->n_grid;
+  k->nbx = (k->rx + 3) / 4;
+  k->nby = (k->ry + 3) / 4;
+  k->nbz = (k->rz + 3) / 4;
+  k->NK = k->nbx * k->nby * k->nbz * 64;
+  k->dt = (float)p->dt;
+  k->dx = (float)p->dx;
+  k->inv_dx = (float)p->inv_dx;
+  k->p_mass = (float)p->p_mass;
+  k->c_stress_mul = (float)(-p->dt * p->p_vol * 4);  // mpm_simulator.py:267, folded in double like Python
+  k->c_stress_div = (float)(p->dx * p->dx);
+  for (int i = 0; i < 3; ++i) k->gdt[i] = (float)p->dt * (float)p->gravity[i];  // :285, f32*f32
+  k->sig_lo = (float)(1 - 2.5e-2 * 10);
+  k->sig_hi = (float)(1 + 4.5e-3 * 100);
+  k->n_prim = p->n_primitive;
+  k->sdf_kind = p->sdf_kind;
+  k->pos_control = p->use_position_control ? 1 : 0;
+  k->p2g_mode = p->p2g_mode;
+  return true;
+}
+
+static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Carves `base` (may be null: size query only).  Returns total bytes.
+size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, MpmWs* ws) {
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t bytes) {
+    void* r = b ? (void*)(b + off) : nullptr;
+    off += al(bytes);
+    return r;
+  };
+  const size_t N = k.N, BG = (size_t)k.B * k.G, P = k.n_prim > 0 ? k.n_prim : 1, S = k.S;
+  MpmWs w;
+  memset(&w, 0, sizeof(w));
+  w.keys = (int32_t*)take(4 * N);
+  w.tmp_idx = (int32_t*)take(4 * N);
+  w.perm = (int32_t*)take(4 * N);
+  w.cell_start = (int32_t*)take(4 * (size_t)k.B * (k.NK + 1));
+  w.cursor = (int32_t*)take(4 * (size_t)k.B * k.NK);
+  w.mat_s = (int32_t*)take(4 * N);
+  w.h_s = (float*)take(4 * N);
+  w.fk_pos = (float*)take(4 * (size_t)k.B * P * (S + 1) * 3);
+  w.fk_rot = (float*)take(4 * (size_t)k.B * P * (S + 1) * 4);
+  w.fk_vw = (float*)take(4 * (size_t)k.B * P * 6);
+  w.fk_act = (float*)take(4 * (size_t)k.B * P * 6);
+  w.jrows = (float*)take(4 * (size_t)k.B * S * 9);
+  if (!bwd) {
+    w.ps = (float*)take(4 * (size_t)PS_NCOMP * N);
+    w.grid_raw = (float4*)take(16 * BG);
+    w.grid_out = w.grid_raw;
+  } else {
+    w.ps = (float*)take(4 * (size_t)PS_NCOMP * N * (S + 1));
+    w.grid_raw = (float4*)take(16 * BG * S);
+    w.grid_out = (float4*)take(16 * BG * S);
+    w.gs = (float*)take(4 * (size_t)PS_NCOMP * N);
+    w.ggrid = (float4*)take(16 * BG);
+    w.g_fk_pos = (float*)take(4 * (size_t)k.B * P * (S + 1) * 3);
+    w.g_fk_rot = (float*)take(4 * (size_t)k.B * P * (S + 1) * 4);
+    w.g_fk_v = (float*)take(4 * (size_t)k.B * P * S * 3);
+    w.g_scal = (float*)take(4 * (size_t)k.B * GS_STRIDE);
+    w.g_prim_in = (float*)take(4 * (size_t)k.B * P * 16);
+    w.g_act = (float*)take(4 * (size_t)k.B * P * 6);
+    w.norm2 = (float*)take(4 * (size_t)k.B * 2);
+  }
+  w.bytes = off;
+  if (ws) *ws = w;
+  return off;
+}
+
+static bool state_ok(const MpmConst& k, const ud_mpm_state* s) {
+  if (!s || !s->x || !s->v || !s->C || !s->F || !s->J || !s->friction || !s->mu || !s->lamda) return false;
+  for (int q = 0; q < k.n_prim; ++q) {
+    const ud_primitive& p = s->prim[q];
+    if (!p.size || !p.friction || !p.softness || !p.position || !p.rotation || !p.v || !p.w ||
+        !p.action_buffer || !p.action_scale)
+      return false;
+  }
+  return true;
+}
+
+}  // namespace ud
+
+using namespace ud;
+
+extern "C" {
+
+const char* ud_version(void) { return "unidom_b200 0.1 (sm_100a)"; }
+const char* ud_last_error(void) { return g_last_error; }
+
+size_t ud_mpm_fwd_workspace_bytes(const ud_mpm_params* p) {
+  MpmConst k;
+  if (!mpm_fold_constants(p, &k)) return 0;
+  return mpm_carve(p, k, false, nullptr, nullptr);
+}
+size_t ud_mpm_bwd_workspace_bytes(const ud_mpm_params* p) {
+  MpmConst k;
+  if (!mpm_fold_constants(p, &k)) return 0;
+  return mpm_carve(p, k, true, nullptr, nullptr);
+}
+int32_t ud_mpm_num_keys(const ud_mpm_params* p) {
+  MpmConst k;
+  if (!mpm_fold_constants(p, &k)) return 0;
+  return k.NK;
+}
+
+int ud_mpm_sort_bins(const ud_mpm_params* p, const float* x, int32_t* out_base, int32_t* out_key,
+                     int32_t* out_perm, void* workspace, size_t workspace_bytes, void* stream) {
+  MpmConst k;
+  if (!mpm_fold_constants(p, &k)) return fail(UD_E_INVALID, "ud_mpm_sort_bins: invalid params");
+  if (!x || !out_base || !out_key || !out_perm) return fail(UD_E_INVALID, "ud_mpm_sort_bins: null pointer");
+  MpmWs ws;
+  size_t need = mpm_carve(p, k, false, workspace, &ws);
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
+    return fail(UD_E_WORKSPACE, "ud_mpm_sort_bins: workspace too small or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_sort(k, x, ws, out_base, st);
+  cudaMemcpyAsync(out_key, ws.keys, 4 * (size_t)k.N, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(out_perm, ws.perm, 4 * (size_t)k.N, cudaMemcpyDeviceToDevice, st);
+  if (cudaGetLastError() != cudaSuccess) return fail(UD_E_CUDA, "ud_mpm_sort_bins: launch failed");
+  return UD_OK;
+}
+
+int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material, const float* h,
+                    const float* action, ud_mpm_state* out, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  MpmConst k;
+  if (!mpm_fold_constants(p, &k)) return fail(UD_E_INVALID, "ud_mpm_step_fwd: invalid params");
+  if (!state_ok(k, in) || !state_ok(k, out) || !material || !h || (k.n_prim > 0 && !action))
+    return fail(UD_E_INVALID, "ud_mpm_step_fwd: null pointer");
+  MpmWs ws;
+  size_t need = mpm_carve(p, k, false, workspace, &ws);
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
+    return fail(UD_E_WORKSPACE, "ud_mpm_step_fwd: workspace too small or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  launch_sort(k, in->x, ws, nullptr, st);
+  launch_gather_state(k, in, material, h, ws, ws.ps, st);
+  launch_fk_fwd(k, in, action, out, ws, st);
+  cudaMemsetAsync(ws.jrows, 0, 4 * (size_t)k.B * k.S * 9, st);
+  for (int f = 0; f < k.S; ++f) {
+    cudaMemsetAsync(ws.grid_raw, 0, 16 * (size_t)k.B * k.G, st);
+    launch_p2g(k, ws.ps, ws.ps, ws.grid_raw, in->mu, in->lamda, ws, st);
+    launch_grid_fwd(k, ws.grid_raw, ws.grid_raw, f, in, ws, st);
+    launch_g2p(k, ws.ps, ws.ps, ws.grid_raw, f, ws, st);
+  }
+  launch_unsort_state(k, ws.ps, in->J, ws, out, st);
+  cudaMemcpyAsync(out->friction, in->friction, 4 * (size_t)k.B, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(out->mu, in->mu, 4 * (size_t)k.B, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(out->lamda, in->lamda, 4 * (size_t)k.B, cudaMemcpyDeviceToDevice, st);
+  if (cudaGetLastError() != cudaSuccess) return fail(UD_E_CUDA, "ud_mpm_step_fwd: launch failed");
+  return UD_OK;
+}
+
+int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material, const float* h,
+                    const float* action, const ud_mpm_state* gout, ud_mpm_state* gin, float* gaction,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  (void)p; (void)in; (void)material; (void)h; (void)action; (void)gout; (void)gin; (void)gaction;
+  (void)workspace; (void)workspace_bytes; (void)stream;
+  return fail(UD_E_INVALID, "ud_mpm_step_bwd: not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+// Shared device helpers for the unidom_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define UD_DEV __host__ __device__ __forceinline__
+
+namespace ud {
+
+// nan_to_num with JAX defaults (nan -> 0, +-inf -> +-FLT_MAX); mpm_simulator.py:377-381
+UD_DEV float nan_to_num(float a) {
+  if (a != a) return 0.f;
+  if (isinf(a)) return a > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+  return a;
+}
+
+struct Mat3 {
+  float m[9];  // row-major
+  UD_DEV float& operator()(int r, int c) { return m[r * 3 + c]; }
+  UD_DEV float operator()(int r, int c) const { return m[r * 3 + c]; }
+};
+
+UD_DEV Mat3 mat_mul(const Mat3& a, const Mat3& b) {
+  Mat3 r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r(i, j) = a(i, 0) * b(0, j) + a(i, 1) * b(1, j) + a(i, 2) * b(2, j);
+  return r;
+}
+// a * b^T
+UD_DEV Mat3 mat_mul_nt(const Mat3& a, const Mat3& b) {
+  Mat3 r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r(i, j) = a(i, 0) * b(j, 0) + a(i, 1) * b(j, 1) + a(i, 2) * b(j, 2);
+  return r;
+}
+// a^T * b
+UD_DEV Mat3 mat_mul_tn(const Mat3& a, const Mat3& b) {
+  Mat3 r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r(i, j) = a(0, i) * b(0, j) + a(1, i) * b(1, j) + a(2, i) * b(2, j);
+  return r;
+}
+UD_DEV Mat3 mat_zero() {
+  Mat3 r;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r.m[i] = 0.f;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 SVD  A = U diag(s) V^T,  s descending >= 0  (replaces jnp.linalg.svd, svd_safe_batch.py:51).
+// One-sided (Hestenes) Jacobi: rotate column pairs of B = A V until orthogonal.  Fixed sweep count,
+// branch-free rotations, all in registers.  Only the sign-invariant combinations U V^T, s and
+// U diag(clip s) V^T are consumed downstream (mpm_simulator.py:253-265).
+// Vt returned is V^T (the reference's "V"/"Vh").
+// ---------------------------------------------------------------------------------------------
+UD_DEV void jacobi_pair(float* bp, float* bq, float* vp, float* vq) {
+  float alpha = bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2];
+  float beta = bq[0] * bq[0] + bq[1] * bq[1] + bq[2] * bq[2];
+  float gamma = bp[0] * bq[0] + bp[1] * bq[1] + bp[2] * bq[2];
+  // rotation that zeroes gamma; identity when the pair is already orthogonal to rounding
+  bool act = fabsf(gamma) > 1e-9f * sqrtf(alpha * beta) && fabsf(gamma) > 1e-37f;
+  float zeta = (beta - alpha) / (2.f * (act ? gamma : 1.f));
+  float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+  float c = 1.f / sqrtf(1.f + t * t);
+  float s = c * t;
+  c = act ? c : 1.f;
+  s = act ? s : 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float x = bp[i], y = bq[i];
+    bp[i] = c * x - s * y;
+    bq[i] = s * x + c * y;
+    x = vp[i];
+    y = vq[i];
+    vp[i] = c * x - s * y;
+    vq[i] = s * x + c * y;
+  }
+}
+
+UD_DEV void swap3(float* a, float* b) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float t = a[i];
+    a[i] = b[i];
+    b[i] = t;
+  }
+}
+
+UD_DEV void svd3(const Mat3& A, Mat3& U, float s[3], Mat3& Vt) {
+  // columns of B and V kept as separate arrays
+  float b0[3] = {A(0, 0), A(1, 0), A(2, 0)}, b1[3] = {A(0, 1), A(1, 1), A(2, 1)},
+        b2[3] = {A(0, 2), A(1, 2), A(2, 2)};
+  float v0[3] = {1.f, 0.f, 0.f}, v1[3] = {0.f, 1.f, 0.f}, v2[3] = {0.f, 0.f, 1.f};
+#pragma unroll 1
+  for (int sweep = 0; sweep < 5; ++sweep) {
+    jacobi_pair(b0, b1, v0, v1);
+    jacobi_pair(b0, b2, v0, v2);
+    jacobi_pair(b1, b2, v1, v2);
+  }
+  float n0 = b0[0] * b0[0] + b0[1] * b0[1] + b0[2] * b0[2];
+  float n1 = b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2];
+  float n2 = b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2];
+  // sort descending (3-element network)
+  if (n0 < n1) { swap3(b0, b1); swap3(v0, v1); float t = n0; n0 = n1; n1 = t; }
+  if (n0 < n2) { swap3(b0, b2); swap3(v0, v2); float t = n0; n0 = n2; n2 = t; }
+  if (n1 < n2) { swap3(b1, b2); swap3(v1, v2); float t = n1; n1 = n2; n2 = t; }
+  s[0] = sqrtf(n0);
+  s[1] = sqrtf(n1);
+  s[2] = sqrtf(n2);
+  float u0[3], u1[3], u2[3];
+  float i0 = s[0] > 0.f ? 1.f / s[0] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u0[i] = s[0] > 0.f ? b0[i] * i0 : (i == 0 ? 1.f : 0.f);
+  if (s[1] > 1e-20f * s[0] && s[1] > 0.f) {
+    float i1 = 1.f / s[1];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) u1[i] = b1[i] * i1;
+  } else {  // any unit vector orthogonal to u0
+    float ax = fabsf(u0[0]), ay = fabsf(u0[1]), az = fabsf(u0[2]);
+    float e[3] = {0.f, 0.f, 0.f};
+    if (ax <= ay && ax <= az) e[0] = 1.f; else if (ay <= az) e[1] = 1.f; else e[2] = 1.f;
+    float d = e[0] * u0[0] + e[1] * u0[1] + e[2] * u0[2];
+    float w[3] = {e[0] - d * u0[0], e[1] - d * u0[1], e[2] - d * u0[2]};
+    float inv = 1.f / sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) u1[i] = w[i] * inv;
+  }
+  if (s[2] > 1e-20f * s[0] && s[2] > 0.f) {
+    float i2 = 1.f / s[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) u2[i] = b2[i] * i2;
+  } else {
+    u2[0] = u0[1] * u1[2] - u0[2] * u1[1];
+    u2[1] = u0[2] * u1[0] - u0[0] * u1[2];
+    u2[2] = u0[0] * u1[1] - u0[1] * u1[0];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    U(i, 0) = u0[i];
+    U(i, 1) = u1[i];
+    U(i, 2) = u2[i];
+    Vt(0, i) = v0[i];
+    Vt(1, i) = v1[i];
+    Vt(2, i) = v2[i];
+  }
+}
+
+// Reference VJP of the SVD, svd_safe_batch.py:65-102, real square case:
+//   dA = U diag(dS) Vt + U((J+J^T) o S_col) Vt + (U o S_col)(K+K^T) Vt
+//   Fij = safe_inv(s_j^2 - s_i^2), zero diagonal; J = F o (U^T dU); K = F o (Vt dVt^T)
+// (the L and projector terms vanish identically for real 3x3 input).
+UD_DEV float safe_inv(float x) { return x / (x * x + 1e-12f); }
+
+UD_DEV Mat3 svd3_bwd(const Mat3& U, const float s[3], const Mat3& Vt, const Mat3& dU, const float dS[3],
+                     const Mat3& dVt) {
+  float s2[3] = {s[0] * s[0], s[1] * s[1], s[2] * s[2]};
+  Mat3 UtdU = mat_mul_tn(U, dU);
+  Mat3 VdV = mat_mul_nt(Vt, dVt);
+  Mat3 M;  // diag(dS) + (J+J^T) o S_col + S_row-scaled (K+K^T)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (i == j) {
+        M(i, j) = dS[i];
+      } else {
+        float Fij = safe_inv(s2[j] - s2[i]);
+        float Fji = safe_inv(s2[i] - s2[j]);
+        float Jsym = Fij * UtdU(i, j) + Fji * UtdU(j, i);
+        float Ksym = Fij * VdV(i, j) + Fji * VdV(j, i);
+        // (J+J^T)*S broadcasts S over the last axis (column j); (U*S) scales column i of U,
+        // i.e. row i of (K+K^T).
+        M(i, j) = Jsym * s[j] + s[i] * Ksym;
+      }
+    }
+  return mat_mul(mat_mul(U, M), Vt);
+}
+
+}  // namespace ud

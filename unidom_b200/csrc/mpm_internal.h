@@ -1,0 +1,84 @@
+// Internal (non-ABI) declarations shared by the MPM translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/unidom_b200.h"
+#include "mpm_particle.cuh"
+
+namespace ud {
+
+// Sorted particle state is structure-of-arrays: component c of particle g lives at base[c*N + g].
+//   0..2 x, 3..5 v, 6..14 C (row-major), 15..23 F (row-major)
+constexpr int PS_X = 0, PS_V = 3, PS_C = 6, PS_F = 15, PS_NCOMP = 24;
+// per-env scalar cotangent accumulators (bwd)
+//   0 friction, 1 mu, 2 lamda, then per primitive q: 3+4q .. : size(3), friction(1)
+constexpr int GS_FRICTION = 0, GS_MU = 1, GS_LAMDA = 2, GS_PRIM = 3, GS_PRIM_STRIDE = 4;
+constexpr int GS_STRIDE = GS_PRIM + GS_PRIM_STRIDE * UD_MAX_PRIM;
+
+struct MpmWs {
+  // binning
+  int32_t* keys;        // [N]
+  int32_t* tmp_idx;     // [N]
+  int32_t* perm;        // [N] sorted slot -> original particle index (per env)
+  int32_t* cell_start;  // [B*(NK+1)]
+  int32_t* cursor;      // [B*NK]
+  int32_t* mat_s;       // [N] material in sorted order
+  float* h_s;           // [N] hardness in sorted order
+  // state
+  float* ps;            // fwd: [24*N]; bwd: [(S+1)*24*N] start-of-substep states
+  float4* grid_raw;     // fwd: [B*G]; bwd: [S*B*G] scattered (p,m)
+  float4* grid_out;     // fwd: == grid_raw; bwd: [S*B*G] updated velocities
+  float* fk_pos;        // [B*P*(S+1)*3] (row S = clamp copy of row S-1)
+  float* fk_rot;        // [B*P*(S+1)*4]
+  float* fk_vw;         // [B*P*6] per-substep (v,w) row
+  float* fk_act;        // [B*P*6] clipped action
+  float* jrows;         // [B*S*9] rows i<3 of C' of original particles 0..2 (J update, :327)
+  // adjoint
+  float* gs;            // [24*N] cotangent SoA (sorted order)
+  float4* ggrid;        // [B*G]
+  float* g_fk_pos;      // [B*P*(S+1)*3]
+  float* g_fk_rot;      // [B*P*(S+1)*4]
+  float* g_fk_v;        // [B*P*S*3] (position-control rows)
+  float* g_scal;        // [B*GS_STRIDE]
+  float* g_prim_in;     // [B*P*16]: gpos0(3) grot0(4) gscale(6) pad(3)
+  float* g_act;         // [B*P*6] cotangent of the (unclipped) action
+  float* norm2;         // [B*2] (state norm^2, action norm^2)
+  size_t bytes;
+};
+
+// Host helpers (abi.cu)
+bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k);
+size_t mpm_carve(const ud_mpm_params* p, const MpmConst& k, bool bwd, void* base, MpmWs* ws);
+
+// Launchers implemented in mpm_particles.cu
+void launch_sort(const MpmConst& k, const float* x_aos, const MpmWs& ws, int32_t* out_base, cudaStream_t st);
+void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
+                         const MpmWs& ws, float* ps_slot, cudaStream_t st);
+void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
+                const float* la_s, const MpmWs& ws, cudaStream_t st);
+void launch_g2p(const MpmConst& k, const float* ps_in, float* ps_out, const float4* grid, int substep,
+                const MpmWs& ws, cudaStream_t st);
+void launch_unsort_state(const MpmConst& k, const float* ps_slot, const float* J_in, const MpmWs& ws,
+                         ud_mpm_state* out, cudaStream_t st);
+void launch_gather_cot(const MpmConst& k, const ud_mpm_state* gout, const MpmWs& ws, cudaStream_t st);
+void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
+                    cudaStream_t st);
+void launch_p2g_bwd(const MpmConst& k, const float* ps_in, const float* mu_s, const float* la_s,
+                    const MpmWs& ws, cudaStream_t st);
+void launch_finish_bwd(const MpmConst& k, const ud_mpm_state* in, const ud_mpm_state* gout,
+                       ud_mpm_state* gin, const float* action, float* gaction, const MpmWs& ws,
+                       cudaStream_t st);
+
+// Launchers implemented in mpm_grid.cu (compiled with --fmad=false)
+void launch_fk_fwd(const MpmConst& k, const ud_mpm_state* in, const float* action, ud_mpm_state* out,
+                   const MpmWs& ws, cudaStream_t st);
+void launch_grid_fwd(const MpmConst& k, const float4* grid_in, float4* grid_out, int substep,
+                     const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st);
+void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,
+                     const MpmWs& ws, cudaStream_t st);
+void launch_fk_bwd(const MpmConst& k, const ud_mpm_state* in, const float* action,
+                   const ud_mpm_state* gout, const MpmWs& ws, cudaStream_t st);
+
+}  // namespace ud
