@@ -65,7 +65,8 @@ def test_step_forward_parity(built_lib, material, n_prim, pos_control):
     conf = _conf(steps=8, n_primitive=n_prim, use_position_control=pos_control)
     B = 2
     sim = _sim(conf, B)
-    st = util.mini_plasticine(sim, B, seed=material, material=material)
+    kw = dict(v_scale=0.05, c_scale=1.0, f_scale=0.02, ylow=0.045) if material == 0 else {}  # liquid branch is centred on ylow
+    st = util.mini_plasticine(sim, B, seed=material, material=material, **kw)
     act = _actions(B, n_prim).to(st.x.device)
     out, _ = sim.step_jax(st, act)
     ref = _oracle_step(conf, sim, st, act)
@@ -103,3 +104,78 @@ def test_multi_step_episode_parity(built_lib):
     assert util.rel_err(s_gpu.x, s_ref.x) < 1e-4
     assert util.rel_err(s_gpu.F, s_ref.F) < 1e-4
     assert util.rel_err(s_gpu.v, s_ref.v) < 2e-3   # velocities: see DESIGN.md (noise floor printed above)
+
+
+def _leaf_list(state, n_prim):
+    leaves = {k: getattr(state, k) for k in ("x", "v", "C", "F", "friction", "mu", "lamda")}
+    for q in range(n_prim):
+        for k in ("size", "friction", "position", "rotation", "action_scale"):
+            leaves[f"p{q}.{k}"] = getattr(state.primitives[q], k)
+    return leaves
+
+
+def _run_grad(step_fn, state, action, cot, n_prim, to_dev):
+    """L = sum(out_leaf * cot_leaf); returns d L / d (input leaves, action)."""
+    leaves = _leaf_list(state, n_prim)
+    req = {k: v.detach().clone().requires_grad_(True) for k, v in leaves.items()}
+    prims = []
+    for q, p in enumerate(state.primitives):
+        if q < n_prim:
+            p = p._replace(**{k.split(".")[1]: req[k] for k in req if k.startswith(f"p{q}.")})
+        prims.append(p)
+    st = state._replace(primitives=prims, **{k: req[k] for k in ("x", "v", "C", "F", "friction", "mu", "lamda")})
+    a = action.detach().clone().requires_grad_(True)
+    out = step_fn(st, a)
+    L = 0
+    for k in ("x", "v", "C", "F"):
+        L = L + (getattr(out, k) * to_dev(cot[k])).sum()
+    for q in range(n_prim):
+        for k in ("position", "rotation"):
+            L = L + (getattr(out.primitives[q], k) * to_dev(cot[f"p{q}.{k}"])).sum()
+    names = list(req.keys())
+    grads = torch.autograd.grad(L, [req[k] for k in names] + [a], allow_unused=True)
+    res = {k: (g if g is not None else torch.zeros_like(req[k])) for k, g in zip(names, grads[:-1])}
+    res["action"] = grads[-1]
+    return res
+
+
+@pytest.mark.parametrize("material,n_prim,pos_control,cot_scale",
+                         [(2, 1, False, 1e-3), (1, 2, False, 1e-3), (0, 1, False, 1e-3), (1, 1, True, 1e-3),
+                          (2, 1, False, 10.0)])
+def test_step_backward_parity(built_lib, material, n_prim, pos_control, cot_scale):
+    """Adjoint of one step (4 substeps) against torch autograd of the oracle.  cot_scale=1e-3 keeps
+    the per-env gradient norm < 1 (norm_grad is a pass-through), 10.0 exercises the renormalisation."""
+    conf = _conf(steps=4, n_primitive=n_prim, use_position_control=pos_control)
+    B = 2
+    sim = _sim(conf, B)
+    kw = dict(v_scale=0.05, c_scale=1.0, f_scale=0.02, ylow=0.045) if material == 0 else {}
+    st = util.mini_plasticine(sim, B, seed=10 + material, material=material, **kw)
+    dev = st.x.device
+    act = (_actions(B, n_prim, seed=4) * 0.8).to(dev)
+    g = torch.Generator().manual_seed(7)
+    S = conf.steps
+    n = st.x.shape[1]
+    cot = {"x": torch.randn((B, n, 3), generator=g), "v": torch.randn((B, n, 3), generator=g) * 0.1,
+           "C": torch.randn((B, n, 3, 3), generator=g) * 1e-3, "F": torch.randn((B, n, 3, 3), generator=g) * 0.1}
+    for q in range(n_prim):
+        cot[f"p{q}.position"] = torch.randn((B, S, 3), generator=g)
+        cot[f"p{q}.rotation"] = torch.randn((B, S, 4), generator=g)
+    cot = {k: v * cot_scale for k, v in cot.items()}
+
+    got = _run_grad(lambda s, a: sim.step_jax(s, a)[0], st, act, cot, n_prim, lambda t: t.to(dev))
+
+    osim = omp.Simulator(util.oracle_conf(conf), sim.material.clone(), sim.h.clone())
+    ost = util.to_oracle_state(st)
+    ref = _run_grad(lambda s, a: omp.step_batch(osim, s, a), ost, act.cpu(), cot, n_prim, lambda t: t)
+    osim64 = omp.Simulator(util.oracle_conf(conf), sim.material.clone(), sim.h.clone(), torch.float64)
+    ref64 = _run_grad(lambda s, a: omp.step_batch(osim64, s, a), util.to_oracle_state(st, torch.float64),
+                      act.cpu().double(), {k: v.double() for k, v in cot.items()}, n_prim, lambda t: t)
+    worst = 0.0
+    for k in ref:
+        e = util.rel_err(got[k], ref[k])
+        fl = util.rel_err(ref[k], ref64[k])
+        cs = util.cosine(got[k], ref[k]) if float(ref[k].abs().max()) > 0 else 1.0
+        print(f"grad {k:18s} rel {e:.3e} cos {cs:.6f}  | oracle32-vs-64 rel {fl:.3e}  max|ref| {float(ref[k].abs().max()):.3e}")
+        if float(ref[k].abs().max()) > 1e-12:
+            assert cs >= 0.999, (k, cs)
+            assert e < max(1e-3, 20 * fl), (k, e, fl)

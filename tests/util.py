@@ -35,7 +35,7 @@ def cosine(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-300))
 
 
-def mini_plasticine(sim, B, seed=0, density=1.0, v_scale=0.3, material=2, ylow=0.02):
+def mini_plasticine(sim, B, seed=0, density=1.0, v_scale=0.3, material=2, ylow=0.02, c_scale=2.0, f_scale=0.05):
     """A small block near the ground with a box primitive cutting its edge, random velocities,
     slightly non-identity F and non-zero C so that every term of the substep is exercised."""
     from unidom_b200.mpm_simulator import create_primitive
@@ -54,7 +54,7 @@ def mini_plasticine(sim, B, seed=0, density=1.0, v_scale=0.3, material=2, ylow=0
     n = st.x.shape[1]
     dev = st.x.device
     v = (torch.randn((B, n, 3), generator=g) * v_scale).to(dev)
-    Cm = (torch.randn((B, n, 3, 3), generator=g) * 2.0).to(dev)
-    F = (torch.eye(3)[None, None] + 0.05 * torch.randn((B, n, 3, 3), generator=g)).to(dev)
+    Cm = (torch.randn((B, n, 3, 3), generator=g) * c_scale).to(dev)
+    F = (torch.eye(3)[None, None] + f_scale * torch.randn((B, n, 3, 3), generator=g)).to(dev)
     x = st.x + (torch.randn((B, n, 3), generator=g) * 1e-3).to(dev)
     return st._replace(x=x, v=v, C=Cm, F=F)

@@ -189,9 +189,49 @@ int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
 int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material, const float* h,
                     const float* action, const ud_mpm_state* gout, ud_mpm_state* gin, float* gaction,
                     void* workspace, size_t workspace_bytes, void* stream) {
-  (void)p; (void)in; (void)material; (void)h; (void)action; (void)gout; (void)gin; (void)gaction;
-  (void)workspace; (void)workspace_bytes; (void)stream;
-  return fail(UD_E_INVALID, "ud_mpm_step_bwd: not built yet");
+  MpmConst k;
+  if (!mpm_fold_constants(p, &k)) return fail(UD_E_INVALID, "ud_mpm_step_bwd: invalid params");
+  if (!state_ok(k, in) || !gout || !gin || !material || !h || (k.n_prim > 0 && !action))
+    return fail(UD_E_INVALID, "ud_mpm_step_bwd: null pointer");
+  MpmWs ws;
+  size_t need = mpm_carve(p, k, true, workspace, &ws);
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
+    return fail(UD_E_WORKSPACE, "ud_mpm_step_bwd: workspace too small or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t slot = (size_t)PS_NCOMP * k.N, BG = (size_t)k.B * k.G;
+  const size_t P = k.n_prim > 0 ? k.n_prim : 1;
+
+  // ---- recompute pass: checkpoint = the step input; every substep's start state and grids are kept
+  launch_sort(k, in->x, ws, nullptr, st);
+  launch_gather_state(k, in, material, h, ws, ws.ps, st);
+  launch_fk_fwd(k, in, action, nullptr, ws, st);
+  cudaMemsetAsync(ws.grid_raw, 0, 16 * BG * k.S, st);
+  for (int f = 0; f < k.S; ++f) {
+    const float* s_in = ws.ps + slot * f;
+    float* s_out = ws.ps + slot * (f + 1);
+    launch_p2g(k, s_in, s_out, ws.grid_raw + BG * f, in->mu, in->lamda, ws, st);
+    launch_grid_fwd(k, ws.grid_raw + BG * f, ws.grid_out + BG * f, f, in, ws, st);
+    launch_g2p(k, s_in, s_out, ws.grid_out + BG * f, f, ws, st);
+  }
+  // ---- reverse pass
+  launch_gather_cot(k, gout, ws, st);
+  cudaMemsetAsync(ws.g_fk_pos, 0, 4 * (size_t)k.B * P * (k.S + 1) * 3, st);
+  cudaMemsetAsync(ws.g_fk_rot, 0, 4 * (size_t)k.B * P * (k.S + 1) * 4, st);
+  cudaMemsetAsync(ws.g_fk_v, 0, 4 * (size_t)k.B * P * k.S * 3, st);
+  cudaMemsetAsync(ws.g_scal, 0, 4 * (size_t)k.B * GS_STRIDE, st);
+  cudaMemsetAsync(ws.g_prim_in, 0, 4 * (size_t)k.B * P * 16, st);
+  cudaMemsetAsync(ws.g_act, 0, 4 * (size_t)k.B * P * 6, st);
+  for (int f = k.S - 1; f >= 0; --f) {
+    const float* s_in = ws.ps + slot * f;
+    cudaMemsetAsync(ws.ggrid, 0, 16 * BG, st);
+    launch_g2p_bwd(k, s_in, ws.grid_out + BG * f, ws, st);
+    launch_grid_bwd(k, ws.grid_raw + BG * f, f, in, ws, st);
+    launch_p2g_bwd(k, s_in, in->mu, in->lamda, ws, st);
+  }
+  launch_fk_bwd(k, in, action, gout, ws, st);
+  launch_finish_bwd(k, in, gout, gin, action, gaction, ws, st);
+  if (cudaGetLastError() != cudaSuccess) return fail(UD_E_CUDA, "ud_mpm_step_bwd: launch failed");
+  return UD_OK;
 }
 
 }  // extern "C"

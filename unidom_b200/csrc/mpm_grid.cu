@@ -169,4 +169,216 @@ void launch_grid_fwd(const MpmConst& k, const float4* grid_in, float4* grid_out,
                                                               ws.fk_rot, ws.fk_vw);
 }
 
+// ================================================================================================
+// Adjoint of the grid update.  One thread per cell with mass and a non-zero incoming cotangent:
+// forward-mode tangents of cell_update in chunks of ND inputs, contracted with the cotangent of the
+// updated velocity.  Inputs (in order): p(3), m, state.friction, then PRIM_NIN scalars per primitive.
+// Per-cell results (g_momentum, g_mass) overwrite ggrid; the rest is warp-reduced and accumulated
+// into the per-env scalar / primitive-table cotangents.
+// ================================================================================================
+constexpr int ND = 8;
+typedef Dual<ND> DualN;
+
+UD_DEV DualN seed(float v, int idx, int chunk) {
+  DualN r;
+  r.v = v;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) r.d[i] = (idx == chunk * ND + i) ? 1.f : 0.f;
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  return v;
+}
+
+__global__ void __launch_bounds__(128)
+k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__ ggrid, int f,
+           ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
+           const float* __restrict__ fk_vw, float* __restrict__ g_fk_pos, float* __restrict__ g_fk_rot,
+           float* __restrict__ g_fk_v, float* __restrict__ g_scal) {
+  int env = blockIdx.y;
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = c < k.G;
+  size_t idx = (size_t)env * k.G + (live ? c : 0);
+  float4 g = grid_raw[idx];
+  float4 gv = ggrid[idx];
+  bool work = live && g.w > 0.f && (gv.x != 0.f || gv.y != 0.f || gv.z != 0.f);
+  if (live && !work) ggrid[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!__any_sync(0xffffffffu, work)) return;  // warp-uniform exit (no barriers below)
+  const int n_in = 5 + PRIM_NIN * k.n_prim;
+  const int n_chunk = (n_in + ND - 1) / ND;
+  int ck = c % k.rz, cj = (c / k.rz) % k.ry, ci = c / (k.rz * k.ry);
+  PrimIn<float> pf[UD_MAX_PRIM];
+  for (int q = 0; q < k.n_prim; ++q) load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pf[q]);
+  float sfric = in.friction[env];
+  float gp[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int ch = 0; ch < n_chunk; ++ch) {
+    float gin[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) gin[i] = 0.f;
+    if (work) {
+      DualN p[3] = {seed(g.x, 0, ch), seed(g.y, 1, ch), seed(g.z, 2, ch)};
+      DualN m = seed(g.w, 3, ch), sf = seed(sfric, 4, ch);
+      PrimIn<DualN> pr[UD_MAX_PRIM];
+      for (int q = 0; q < k.n_prim; ++q) {
+        int b0 = 5 + PRIM_NIN * q;
+        for (int j = 0; j < 3; ++j) pr[q].pos_f[j] = seed(pf[q].pos_f[j], b0 + j, ch);
+        for (int j = 0; j < 4; ++j) pr[q].rot_f[j] = seed(pf[q].rot_f[j], b0 + 3 + j, ch);
+        for (int j = 0; j < 3; ++j) pr[q].pos_f1[j] = seed(pf[q].pos_f1[j], b0 + 7 + j, ch);
+        for (int j = 0; j < 4; ++j) pr[q].rot_f1[j] = seed(pf[q].rot_f1[j], b0 + 10 + j, ch);
+        for (int j = 0; j < 3; ++j) pr[q].size[j] = seed(pf[q].size[j], b0 + 14 + j, ch);
+        pr[q].friction = seed(pf[q].friction, b0 + 17, ch);
+        for (int j = 0; j < 3; ++j) pr[q].v_f[j] = seed(pf[q].v_f[j], b0 + 18 + j, ch);
+        pr[q].softness = pf[q].softness;
+      }
+      DualN v[3];
+      cell_update<DualN>(k, ci, cj, ck, p, m, sf, pr, v);
+#pragma unroll
+      for (int i = 0; i < ND; ++i) gin[i] = gv.x * v[0].d[i] + gv.y * v[1].d[i] + gv.z * v[2].d[i];
+    }
+    // distribute: inputs 0..3 are per cell, the rest reduce over the env
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      int id = ch * ND + i;
+      if (i < 4 && ch == 0) {  // ids 0..3 live in chunk 0 (ND >= 4)
+        gp[i] = gin[i];
+        continue;
+      }
+      if (id >= n_in) continue;
+      float tot = warp_sum(gin[i]);
+      if ((threadIdx.x & 31) != 0 || tot == 0.f) continue;
+      if (id == 4) {
+        atomicAdd(&g_scal[env * GS_STRIDE + GS_FRICTION], tot);
+        continue;
+      }
+      int q = (id - 5) / PRIM_NIN, j = (id - 5) % PRIM_NIN;
+      size_t t = (size_t)env * k.n_prim + q;
+      float* tp = g_fk_pos + t * (k.S + 1) * 3;
+      float* tr = g_fk_rot + t * (k.S + 1) * 4;
+      if (j < 3) atomicAdd(&tp[f * 3 + j], tot);
+      else if (j < 7) atomicAdd(&tr[f * 4 + (j - 3)], tot);
+      else if (j < 10) atomicAdd(&tp[(f + 1) * 3 + (j - 7)], tot);
+      else if (j < 14) atomicAdd(&tr[(f + 1) * 4 + (j - 10)], tot);
+      else if (j < 17) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + (j - 14)], tot);
+      else if (j < 18) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + 3], tot);
+      else atomicAdd(&g_fk_v[(t * k.S + f) * 3 + (j - 18)], tot);
+    }
+  }
+  if (work) ggrid[idx] = make_float4(gp[0], gp[1], gp[2], gp[3]);
+}
+
+void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,
+                     const MpmWs& ws, cudaStream_t st) {
+  dim3 grid(cdiv(k.G, 128), k.B);
+  k_grid_bwd<<<grid, 128, 0, st>>>(k, grid_raw, ws.ggrid, substep, *in, ws.fk_pos, ws.fk_rot, ws.fk_vw,
+                                   ws.g_fk_pos, ws.g_fk_rot, ws.g_fk_v, ws.g_scal);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reverse of the primitive prologue: copy_frame^T, FK chain^T (position clip masks, quaternion
+// products), set_action^T, action clip mask.  One thread per (env, primitive).
+// Writes g_prim_in = {g position[0] (3), g rotation[0] (4), g action_scale (6)} and g_act (6).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fk_bwd(MpmConst k, ud_mpm_state in, const float* __restrict__ action, ud_mpm_state gout,
+                         const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
+                         const float* __restrict__ fk_vw, const float* __restrict__ fk_act,
+                         float* __restrict__ g_fk_pos, float* __restrict__ g_fk_rot,
+                         const float* __restrict__ g_fk_v, float* __restrict__ g_prim_in,
+                         float* __restrict__ g_act) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= k.B * k.n_prim) return;
+  int env = t / k.n_prim, q = t % k.n_prim;
+  const int S = k.S;
+  const ud_primitive& go = gout.prim[q];
+  const float* tp = fk_pos + (size_t)t * (S + 1) * 3;
+  const float* tr = fk_rot + (size_t)t * (S + 1) * 4;
+  float* gtp = g_fk_pos + (size_t)t * (S + 1) * 3;
+  float* gtr = g_fk_rot + (size_t)t * (S + 1) * 4;
+  float vw[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) vw[j] = fk_vw[(size_t)t * 6 + j];
+  // row S is the clamped alias of row S-1
+  for (int j = 0; j < 3; ++j) gtp[(S - 1) * 3 + j] += gtp[S * 3 + j];
+  for (int j = 0; j < 4; ++j) gtr[(S - 1) * 4 + j] += gtr[S * 4 + j];
+  // output tables: row 0 = internal row S-1 (copy_frame), rows >= 1 = internal rows
+  float gvw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int f = 0; f < S; ++f) {
+    int dst = f == 0 ? S - 1 : f;
+    if (go.position)
+      for (int j = 0; j < 3; ++j) gtp[dst * 3 + j] += go.position[((size_t)env * S + f) * 3 + j];
+    if (go.rotation)
+      for (int j = 0; j < 4; ++j) gtr[dst * 4 + j] += go.rotation[((size_t)env * S + f) * 4 + j];
+    for (int j = 0; j < 3; ++j) {
+      if (go.v) gvw[j] += go.v[((size_t)env * S + f) * 3 + j];
+      if (go.w) gvw[3 + j] += go.w[((size_t)env * S + f) * 3 + j];
+      gvw[j] += g_fk_v[((size_t)t * S + f) * 3 + j];
+    }
+  }
+  float dq[4];
+  w2quat(vw + 3, dq);
+  float gdq[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int f = S - 2; f >= 0; --f) {
+    // pos[f+1] = clip(pos[f] + v, -2, 2)
+    for (int j = 0; j < 3; ++j) {
+      float u = tp[f * 3 + j] + vw[j];
+      float gnext = (u >= -2.f && u <= 2.f) ? gtp[(f + 1) * 3 + j] : 0.f;
+      gtp[f * 3 + j] += gnext;
+      gvw[j] += gnext;
+    }
+    // rot[f+1] = qmul(dq, rot[f]) : Jacobian by forward mode over the 8 inputs
+    Dual<8> dqd[4], rd[4], out[4];
+    for (int j = 0; j < 4; ++j) {
+      dqd[j].v = dq[j];
+      rd[j].v = tr[f * 4 + j];
+      for (int i = 0; i < 8; ++i) {
+        dqd[j].d[i] = (i == j) ? 1.f : 0.f;
+        rd[j].d[i] = (i == 4 + j) ? 1.f : 0.f;
+      }
+    }
+    qmul(dqd, rd, out);
+    for (int i = 0; i < 4; ++i) {
+      float a = 0.f, b = 0.f;
+      for (int o = 0; o < 4; ++o) {
+        a += gtr[(f + 1) * 4 + o] * out[o].d[i];
+        b += gtr[(f + 1) * 4 + o] * out[o].d[4 + i];
+      }
+      gdq[i] += a;
+      gtr[f * 4 + i] += b;
+    }
+  }
+  {  // dq = w2quat(w row)
+    Dual<3> wd[3], out[4];
+    for (int j = 0; j < 3; ++j) {
+      wd[j].v = vw[3 + j];
+      for (int i = 0; i < 3; ++i) wd[j].d[i] = (i == j) ? 1.f : 0.f;
+    }
+    w2quat(wd, out);
+    for (int i = 0; i < 3; ++i)
+      for (int o = 0; o < 4; ++o) gvw[3 + i] += gdq[o] * out[o].d[i];
+  }
+  float* pi = g_prim_in + (size_t)t * 16;
+  for (int j = 0; j < 3; ++j) pi[j] = gtp[j];
+  for (int j = 0; j < 4; ++j) pi[3 + j] = gtr[j];
+  const ud_primitive& pin = in.prim[q];
+  for (int j = 0; j < 6; ++j) {
+    float a = fk_act[(size_t)t * 6 + j];
+    float scale = pin.action_scale[env * 6 + j];
+    float ga = gvw[j] * scale / (float)S + (go.action_buffer ? go.action_buffer[env * 6 + j] : 0.f);
+    pi[7 + j] = gvw[j] * a / (float)S + (go.action_scale ? go.action_scale[env * 6 + j] : 0.f);
+    float raw = action[(size_t)env * 6 * k.n_prim + 6 * q + j];
+    g_act[(size_t)t * 6 + j] = (raw >= -1.f && raw <= 1.f) ? ga : 0.f;
+  }
+  for (int j = 13; j < 16; ++j) pi[j] = 0.f;
+}
+
+void launch_fk_bwd(const MpmConst& k, const ud_mpm_state* in, const float* action,
+                   const ud_mpm_state* gout, const MpmWs& ws, cudaStream_t st) {
+  int n = k.B * k.n_prim;
+  if (n == 0) return;
+  k_fk_bwd<<<cdiv(n, 64), 64, 0, st>>>(k, *in, action, *gout, ws.fk_pos, ws.fk_rot, ws.fk_vw, ws.fk_act,
+                                       ws.g_fk_pos, ws.g_fk_rot, ws.g_fk_v, ws.g_prim_in, ws.g_act);
+}
+
 }  // namespace ud

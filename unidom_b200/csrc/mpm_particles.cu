@@ -7,6 +7,14 @@ namespace ud {
 #define UD_BLOCK 128
 
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+static inline dim3 pgrid(const MpmConst& k, int block) { return dim3(cdiv(k.n, block), k.B); }
+
+// particle index of this thread: blockIdx.y = env, blockIdx.x*blockDim.x + threadIdx.x = slot in env
+#define UD_PARTICLE_INDEX(k, env, g)                         \
+  int env = blockIdx.y;                                      \
+  int slot_ = blockIdx.x * blockDim.x + threadIdx.x;         \
+  bool live_ = slot_ < (k).n;                                \
+  int g = env * (k).n + (live_ ? slot_ : 0);
 
 // ------------------------------------------------------------------------------------------------
 // Binning: key = 4x4x4-block-major cell key of base = int32(x*inv_dx - 0.5) (mpm_simulator.py:233),
@@ -22,9 +30,8 @@ UD_DEV int cell_key(const MpmConst& k, const int base[3]) {
 
 __global__ void k_keys(MpmConst k, const float* __restrict__ x_aos, int32_t* __restrict__ keys,
                        int32_t* __restrict__ count, int32_t* __restrict__ out_base) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= k.N) return;
-  int env = g / k.n;
+  UD_PARTICLE_INDEX(k, env, g);
+  if (!live_) return;
   float x[3] = {nan_to_num(x_aos[3 * g]), nan_to_num(x_aos[3 * g + 1]), nan_to_num(x_aos[3 * g + 2])};
   Stencil st;
   make_stencil(x, k.inv_dx, st);
@@ -66,9 +73,8 @@ __global__ void k_scan(MpmConst k, int32_t* __restrict__ cell_start) {
 
 __global__ void k_place(MpmConst k, const int32_t* __restrict__ keys, const int32_t* __restrict__ cell_start,
                         int32_t* __restrict__ cursor, int32_t* __restrict__ tmp_idx) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= k.N) return;
-  int env = g / k.n;
+  UD_PARTICLE_INDEX(k, env, g);
+  if (!live_) return;
   int key = keys[g];
   int slot = cell_start[(size_t)env * (k.NK + 1) + key] + atomicAdd(&cursor[(size_t)env * k.NK + key], 1);
   tmp_idx[(size_t)env * k.n + slot] = g - env * k.n;
@@ -76,9 +82,8 @@ __global__ void k_place(MpmConst k, const int32_t* __restrict__ keys, const int3
 
 __global__ void k_rank(MpmConst k, const int32_t* __restrict__ keys, const int32_t* __restrict__ cell_start,
                        const int32_t* __restrict__ tmp_idx, int32_t* __restrict__ perm) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= k.N) return;
-  int env = g / k.n;
+  UD_PARTICLE_INDEX(k, env, g);
+  if (!live_) return;
   int p = tmp_idx[g];
   int key = keys[env * k.n + p];
   const int32_t* cs = cell_start + (size_t)env * (k.NK + 1);
@@ -92,10 +97,10 @@ __global__ void k_rank(MpmConst k, const int32_t* __restrict__ keys, const int32
 void launch_sort(const MpmConst& k, const float* x_aos, const MpmWs& ws, int32_t* out_base, cudaStream_t st) {
   cudaMemsetAsync(ws.cell_start, 0, sizeof(int32_t) * (size_t)k.B * (k.NK + 1), st);
   cudaMemsetAsync(ws.cursor, 0, sizeof(int32_t) * (size_t)k.B * k.NK, st);
-  k_keys<<<cdiv(k.N, 256), 256, 0, st>>>(k, x_aos, ws.keys, ws.cell_start, out_base);
+  k_keys<<<pgrid(k, 256), 256, 0, st>>>(k, x_aos, ws.keys, ws.cell_start, out_base);
   k_scan<<<k.B, 1024, 0, st>>>(k, ws.cell_start);
-  k_place<<<cdiv(k.N, 256), 256, 0, st>>>(k, ws.keys, ws.cell_start, ws.cursor, ws.tmp_idx);
-  k_rank<<<cdiv(k.N, 256), 256, 0, st>>>(k, ws.keys, ws.cell_start, ws.tmp_idx, ws.perm);
+  k_place<<<pgrid(k, 256), 256, 0, st>>>(k, ws.keys, ws.cell_start, ws.cursor, ws.tmp_idx);
+  k_rank<<<pgrid(k, 256), 256, 0, st>>>(k, ws.keys, ws.cell_start, ws.tmp_idx, ws.perm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -107,9 +112,8 @@ __global__ void k_gather_state(MpmConst k, const float* __restrict__ x, const fl
                                const int32_t* __restrict__ material, const float* __restrict__ h,
                                const int32_t* __restrict__ perm, float* __restrict__ ps,
                                int32_t* __restrict__ mat_s, float* __restrict__ h_s) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= k.N) return;
-  int env = g / k.n;
+  UD_PARTICLE_INDEX(k, env, g);
+  if (!live_) return;
   int p = perm[g];
   size_t o = (size_t)env * k.n + p;
   const size_t N = k.N;
@@ -127,7 +131,7 @@ __global__ void k_gather_state(MpmConst k, const float* __restrict__ x, const fl
 
 void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
                          const MpmWs& ws, float* ps_slot, cudaStream_t st) {
-  k_gather_state<<<cdiv(k.N, 256), 256, 0, st>>>(k, in->x, in->v, in->C, in->F, material, h, ws.perm, ps_slot,
+  k_gather_state<<<pgrid(k, 256), 256, 0, st>>>(k, in->x, in->v, in->C, in->F, material, h, ws.perm, ps_slot,
                                                   ws.mat_s, ws.h_s);
 }
 
@@ -136,7 +140,7 @@ void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_
 // {momentum, mass} (p2g_micro, :178-194) as ONE 16-byte vector reduction per node
 // (red.global.add.v4.f32 -> REDG.E.ADD.F32x4).  Out-of-range nodes are dropped (JAX scatter rule).
 // ------------------------------------------------------------------------------------------------
-UD_DEV void load_particle(const float* __restrict__ ps, size_t N, int g, float x[3], float v[3], Mat3& C,
+UD_DEV void load_particle(const float* ps, size_t N, int g, float x[3], float v[3], Mat3& C,
                           Mat3& F) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) x[c] = ps[(PS_X + c) * N + g];
@@ -149,13 +153,12 @@ UD_DEV void load_particle(const float* __restrict__ ps, size_t N, int g, float x
 }
 
 __global__ void __launch_bounds__(UD_BLOCK)
-k_p2g(MpmConst k, const float* __restrict__ ps_in, float* __restrict__ ps_out, float4* __restrict__ grid,
+k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
       const float* __restrict__ h_s) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= k.N) return;
+  UD_PARTICLE_INDEX(k, env, g);
+  if (!live_) return;
   const size_t N = k.N;
-  int env = g / k.n;
   float x[3], v[3];
   Mat3 C, F;
   load_particle(ps_in, N, g, x, v, C, F);
@@ -195,7 +198,7 @@ k_p2g(MpmConst k, const float* __restrict__ ps_in, float* __restrict__ ps_out, f
 
 void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
                 const float* la_s, const MpmWs& ws, cudaStream_t st) {
-  k_p2g<<<cdiv(k.N, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s);
+  k_p2g<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -203,12 +206,11 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
 // Rows of C' of original particles 0..2 are kept for the J update quirk (:327).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(UD_BLOCK)
-k_g2p(MpmConst k, const float* __restrict__ ps_in, float* __restrict__ ps_out, const float4* __restrict__ grid,
+k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ grid,
       const int32_t* __restrict__ perm, float* __restrict__ jrows, int substep) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= k.N) return;
+  UD_PARTICLE_INDEX(k, env, g);
+  if (!live_) return;
   const size_t N = k.N;
-  int env = g / k.n;
   float x[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) x[c] = ps_in[(PS_X + c) * N + g];
@@ -262,7 +264,7 @@ k_g2p(MpmConst k, const float* __restrict__ ps_in, float* __restrict__ ps_out, c
 
 void launch_g2p(const MpmConst& k, const float* ps_in, float* ps_out, const float4* grid, int substep,
                 const MpmWs& ws, cudaStream_t st) {
-  k_g2p<<<cdiv(k.N, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, ws.perm, ws.jrows, substep);
+  k_g2p<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, ws.perm, ws.jrows, substep);
 }
 
 // sorted SoA -> AoS outputs; J' = J * prod_f (1 + dt * trace-quirk_f), sequentially as the reference
@@ -270,10 +272,9 @@ __global__ void k_unsort_state(MpmConst k, const float* __restrict__ ps, const f
                                const int32_t* __restrict__ perm, const float* __restrict__ jrows,
                                float* __restrict__ x, float* __restrict__ v, float* __restrict__ C,
                                float* __restrict__ F, float* __restrict__ J) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= k.N) return;
+  UD_PARTICLE_INDEX(k, env, g);
+  if (!live_) return;
   const size_t N = k.N;
-  int env = g / k.n;
   int p = perm[g];
   size_t o = (size_t)env * k.n + p;
 #pragma unroll
@@ -302,8 +303,353 @@ __global__ void k_unsort_state(MpmConst k, const float* __restrict__ ps, const f
 
 void launch_unsort_state(const MpmConst& k, const float* ps_slot, const float* J_in, const MpmWs& ws,
                          ud_mpm_state* out, cudaStream_t st) {
-  k_unsort_state<<<cdiv(k.N, 256), 256, 0, st>>>(k, ps_slot, J_in, ws.perm, ws.jrows, out->x, out->v, out->C,
+  k_unsort_state<<<pgrid(k, 256), 256, 0, st>>>(k, ps_slot, J_in, ws.perm, ws.jrows, out->x, out->v, out->C,
                                                   out->F, out->J);
+}
+
+// ================================================================================================
+// Adjoint.  Cotangents live in ws.gs in the same sorted SoA layout as the state.  Per substep, in
+// reverse order:  k_g2p_bwd (scatter of the grid-velocity cotangent = G2P^T + advection^T),
+// k_grid_bwd (mpm_grid.cu), k_p2g_bwd (gather = P2G^T, then constitutive / SVD / F-update reverse).
+// ================================================================================================
+__global__ void k_gather_cot(MpmConst k, const float* __restrict__ gx, const float* __restrict__ gv,
+                             const float* __restrict__ gC, const float* __restrict__ gF,
+                             const int32_t* __restrict__ perm, float* __restrict__ gs) {
+  UD_PARTICLE_INDEX(k, env, g);
+  if (!live_) return;
+  int p = perm[g];
+  size_t o = (size_t)env * k.n + p;
+  const size_t N = k.N;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) gs[(PS_X + c) * N + g] = gx ? gx[3 * o + c] : 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) gs[(PS_V + c) * N + g] = gv ? gv[3 * o + c] : 0.f;
+#pragma unroll
+  for (int c = 0; c < 9; ++c) gs[(PS_C + c) * N + g] = gC ? gC[9 * o + c] : 0.f;
+#pragma unroll
+  for (int c = 0; c < 9; ++c) gs[(PS_F + c) * N + g] = gF ? gF[9 * o + c] : 0.f;
+}
+
+void launch_gather_cot(const MpmConst& k, const ud_mpm_state* gout, const MpmWs& ws, cudaStream_t st) {
+  k_gather_cot<<<pgrid(k, 256), 256, 0, st>>>(k, gout->x, gout->v, gout->C, gout->F, ws.perm, ws.gs);
+}
+
+// G2P^T: v' = sum wt g ; C' = sum 4 inv_dx wt g (x) d ; x' = x + dt v'   (d = off - fx)
+// Scatters the cotangent of the updated grid velocity (clamped index = transpose of the clamping
+// gather) and leaves the partial position cotangent gx' + inv_dx * gfx in gs.X.
+__global__ void __launch_bounds__(UD_BLOCK)
+k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict__ grid_out,
+          float* __restrict__ gs, float4* __restrict__ ggrid) {
+  UD_PARTICLE_INDEX(k, env, g);
+  if (!live_) return;
+  const size_t N = k.N;
+  float x[3], gxo[3], gvt[3];
+  Mat3 gC;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) x[c] = ps_in[(PS_X + c) * N + g];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) gxo[c] = gs[(PS_X + c) * N + g];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) gvt[c] = gs[(PS_V + c) * N + g] + k.dt * gxo[c];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) gC.m[c] = gs[(PS_C + c) * N + g];
+  Stencil st;
+  make_stencil(x, k.inv_dx, st);
+  const float4* genv = grid_out + (size_t)env * k.G;
+  float4* ggenv = ggrid + (size_t)env * k.G;
+  float gw[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  float gfx[3] = {0.f, 0.f, 0.f};
+  const float c4 = 4.f * k.inv_dx;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    int ix = idx_gather(st.base[0] + a, k.rx);
+    float d0 = (float)a - st.fx[0];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      int iy = idx_gather(st.base[1] + b, k.ry);
+      float d1 = (float)b - st.fx[1];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        int iz = idx_gather(st.base[2] + c, k.rz);
+        float d2 = (float)c - st.fx[2];
+        float wt = st.w[a][0] * st.w[b][1] * st.w[c][2];
+        int cell = (ix * k.ry + iy) * k.rz + iz;
+        float4 gv = __ldg(&genv[cell]);
+        // r_i = gv'_i + 4 inv_dx (gC' d)_i
+        float r0 = gvt[0] + c4 * (gC(0, 0) * d0 + gC(0, 1) * d1 + gC(0, 2) * d2);
+        float r1 = gvt[1] + c4 * (gC(1, 0) * d0 + gC(1, 1) * d1 + gC(1, 2) * d2);
+        float r2 = gvt[2] + c4 * (gC(2, 0) * d0 + gC(2, 1) * d1 + gC(2, 2) * d2);
+        atomicAdd(&ggenv[cell], make_float4(wt * r0, wt * r1, wt * r2, 0.f));
+        float gwt = gv.x * r0 + gv.y * r1 + gv.z * r2;
+        // gd_j = 4 inv_dx wt sum_i g_i gC'_ij ; fx enters d with a minus sign
+        float cw = c4 * wt;
+        gfx[0] -= cw * (gv.x * gC(0, 0) + gv.y * gC(1, 0) + gv.z * gC(2, 0));
+        gfx[1] -= cw * (gv.x * gC(0, 1) + gv.y * gC(1, 1) + gv.z * gC(2, 1));
+        gfx[2] -= cw * (gv.x * gC(0, 2) + gv.y * gC(1, 2) + gv.z * gC(2, 2));
+        gw[a][0] += gwt * st.w[b][1] * st.w[c][2];
+        gw[b][1] += gwt * st.w[a][0] * st.w[c][2];
+        gw[c][2] += gwt * st.w[a][0] * st.w[b][1];
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    gfx[d] += gw[0][d] * st.dw[0][d] + gw[1][d] * st.dw[1][d] + gw[2][d] * st.dw[2][d];
+    gs[(PS_X + d) * N + g] = gxo[d] + k.inv_dx * gfx[d];
+  }
+}
+
+void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
+                    cudaStream_t st) {
+  k_g2p_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
+}
+
+// P2G^T (gather of the cotangents of scattered momentum/mass; dropped nodes contribute nothing),
+// then the reverse of stress / plasticity / SVD / F update.  Writes the cotangents of the substep's
+// input x, v, C, F in place and reduces d/d(state.mu), d/d(state.lamda) per env.
+__global__ void __launch_bounds__(UD_BLOCK)
+k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict__ ggrid,
+          float* __restrict__ gs, const float* __restrict__ mu_s, const float* __restrict__ la_s,
+          const int32_t* __restrict__ mat_s, const float* __restrict__ h_s, float* __restrict__ g_scal) {
+  UD_PARTICLE_INDEX(k, env, g);
+  const size_t N = k.N;
+  float gmu = 0.f, gla = 0.f;
+  if (live_) {
+    float x[3], v[3];
+    Mat3 C, F;
+    load_particle(ps_in, N, g, x, v, C, F);
+    Stencil st;
+    make_stencil(x, k.inv_dx, st);
+    Consti o;
+    constitutive_fwd(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+    const float4* ggenv = ggrid + (size_t)env * k.G;
+    float mv[3] = {k.p_mass * v[0], k.p_mass * v[1], k.p_mass * v[2]};
+    float gv[3] = {0.f, 0.f, 0.f}, gfx[3] = {0.f, 0.f, 0.f};
+    float gw[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    Mat3 gA = mat_zero();
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      int ix = idx_scatter(st.base[0] + a, k.rx);
+      float d0 = ((float)a - st.fx[0]) * k.dx;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        int iy = idx_scatter(st.base[1] + b, k.ry);
+        float d1 = ((float)b - st.fx[1]) * k.dx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          int iz = idx_scatter(st.base[2] + c, k.rz);
+          if ((ix | iy | iz) < 0) continue;
+          float d2 = ((float)c - st.fx[2]) * k.dx;
+          float wt = st.w[a][0] * st.w[b][1] * st.w[c][2];
+          float4 gp = __ldg(&ggenv[(ix * k.ry + iy) * k.rz + iz]);  // (g_momentum, g_mass)
+          float gpv[3] = {gp.x, gp.y, gp.z};
+          float dd[3] = {d0, d1, d2};
+          float gwt = k.p_mass * gp.w;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            gv[i] += wt * k.p_mass * gpv[i];
+            float Ad = o.affine(i, 0) * d0 + o.affine(i, 1) * d1 + o.affine(i, 2) * d2;
+            gwt += gpv[i] * (mv[i] + Ad);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) gA(i, j) += wt * gpv[i] * dd[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            gfx[j] -= k.dx * wt * (o.affine(0, j) * gpv[0] + o.affine(1, j) * gpv[1] + o.affine(2, j) * gpv[2]);
+          gw[a][0] += gwt * st.w[b][1] * st.w[c][2];
+          gw[b][1] += gwt * st.w[a][0] * st.w[c][2];
+          gw[c][2] += gwt * st.w[a][0] * st.w[b][1];
+        }
+      }
+    }
+    Mat3 gF2out, gC, gF;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) gF2out.m[c] = gs[(PS_F + c) * N + g];
+    constitutive_bwd(k, C, F, o, gA, gF2out, gC, gF, gmu, gla);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      gfx[d] += gw[0][d] * st.dw[0][d] + gw[1][d] * st.dw[1][d] + gw[2][d] * st.dw[2][d];
+      gs[(PS_X + d) * N + g] += k.inv_dx * gfx[d];
+      gs[(PS_V + d) * N + g] = gv[d];
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) gs[(PS_C + c) * N + g] = gC.m[c];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) gs[(PS_F + c) * N + g] = gF.m[c];
+  }
+  // block reduction of the per-env scalars
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    gmu += __shfl_down_sync(0xffffffffu, gmu, off);
+    gla += __shfl_down_sync(0xffffffffu, gla, off);
+  }
+  __shared__ float smu[UD_BLOCK / 32], sla[UD_BLOCK / 32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    smu[wid] = gmu;
+    sla[wid] = gla;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < UD_BLOCK / 32; ++i) {
+      a += smu[i];
+      b += sla[i];
+    }
+    atomicAdd(&g_scal[env * GS_STRIDE + GS_MU], a);
+    atomicAdd(&g_scal[env * GS_STRIDE + GS_LAMDA], b);
+  }
+}
+
+void launch_p2g_bwd(const MpmConst& k, const float* ps_in, const float* mu_s, const float* la_s,
+                    const MpmWs& ws, cudaStream_t st) {
+  k_p2g_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ws.ggrid, ws.gs, mu_s, la_s, ws.mat_s, ws.h_s,
+                                                     ws.g_scal);
+}
+
+// ------------------------------------------------------------------------------------------------
+// norm_grad_state / norm_grad backward (mpm_simulator.py:389-408): nan_to_num every cotangent leaf,
+// per-env global L2 norm over ALL leaves of the state, divide when the norm is >= 1.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_norm_particles(MpmConst k, float* __restrict__ gs, float* __restrict__ norm2) {
+  UD_PARTICLE_INDEX(k, env, g);
+  const size_t N = k.N;
+  float acc = 0.f;
+  if (live_) {
+    for (int c = 0; c < PS_NCOMP; ++c) {
+      float t = nan_to_num(gs[c * N + g]);
+      gs[c * N + g] = t;
+      acc += t * t;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  __shared__ float sh[8];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) a += sh[i];
+    atomicAdd(&norm2[env * 2], a);
+  }
+}
+
+// one thread per env: small leaves (per-env scalars, primitive leaves, action).  Adds pass-through
+// output cotangents, scrubs, accumulates the norms and stores the scrubbed values back.
+__global__ void k_norm_small(MpmConst k, ud_mpm_state gout, float* __restrict__ g_scal,
+                             float* __restrict__ g_prim_in, float* __restrict__ g_act,
+                             float* __restrict__ norm2) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= k.B) return;
+  float acc = 0.f, acc_a = 0.f;
+  float* sc = g_scal + env * GS_STRIDE;
+  sc[GS_FRICTION] = nan_to_num(sc[GS_FRICTION] + (gout.friction ? gout.friction[env] : 0.f));
+  sc[GS_MU] = nan_to_num(sc[GS_MU] + (gout.mu ? gout.mu[env] : 0.f));
+  sc[GS_LAMDA] = nan_to_num(sc[GS_LAMDA] + (gout.lamda ? gout.lamda[env] : 0.f));
+  acc += sc[GS_FRICTION] * sc[GS_FRICTION] + sc[GS_MU] * sc[GS_MU] + sc[GS_LAMDA] * sc[GS_LAMDA];
+  for (int q = 0; q < k.n_prim; ++q) {
+    float* ps = sc + GS_PRIM + q * GS_PRIM_STRIDE;
+    const ud_primitive& go = gout.prim[q];
+    for (int j = 0; j < 3; ++j) {
+      ps[j] = nan_to_num(ps[j] + (go.size ? go.size[env * 3 + j] : 0.f));
+      acc += ps[j] * ps[j];
+    }
+    ps[3] = nan_to_num(ps[3] + (go.friction ? go.friction[env] : 0.f));
+    acc += ps[3] * ps[3];
+    float* pi = g_prim_in + ((size_t)env * k.n_prim + q) * 16;
+    for (int j = 0; j < 13; ++j) {  // gpos0(3) grot0(4) gscale(6), pass-through already folded in
+      pi[j] = nan_to_num(pi[j]);
+      acc += pi[j] * pi[j];
+    }
+    float* ga = g_act + ((size_t)env * k.n_prim + q) * 6;
+    for (int j = 0; j < 6; ++j) {
+      ga[j] = nan_to_num(ga[j]);
+      acc_a += ga[j] * ga[j];
+    }
+  }
+  atomicAdd(&norm2[env * 2], acc);
+  norm2[env * 2 + 1] = acc_a;
+}
+
+UD_DEV float norm_div(float g, float n2) {
+  float nrm = sqrtf(n2);
+  return nrm < 1.0f ? g : g / nrm;
+}
+
+__global__ void k_unsort_cot(MpmConst k, const float* __restrict__ gs, const int32_t* __restrict__ perm,
+                             const float* __restrict__ norm2, float* __restrict__ gx, float* __restrict__ gv,
+                             float* __restrict__ gC, float* __restrict__ gF, float* __restrict__ gJ) {
+  UD_PARTICLE_INDEX(k, env, g);
+  if (!live_) return;
+  const size_t N = k.N;
+  int p = perm[g];
+  size_t o = (size_t)env * k.n + p;
+  float n2 = norm2[env * 2];
+  if (gx)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gx[3 * o + c] = norm_div(gs[(PS_X + c) * N + g], n2);
+  if (gv)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gv[3 * o + c] = norm_div(gs[(PS_V + c) * N + g], n2);
+  if (gC)
+#pragma unroll
+    for (int c = 0; c < 9; ++c) gC[9 * o + c] = norm_div(gs[(PS_C + c) * N + g], n2);
+  if (gF)
+#pragma unroll
+    for (int c = 0; c < 9; ++c) gF[9 * o + c] = norm_div(gs[(PS_F + c) * N + g], n2);
+  if (gJ) gJ[o] = 0.f;  // the cotangent of J is dropped by substep_bwd_loss (:343-350)
+}
+
+__global__ void k_write_small(MpmConst k, ud_mpm_state gin, float* __restrict__ gaction,
+                              const float* __restrict__ g_scal, const float* __restrict__ g_prim_in,
+                              const float* __restrict__ g_act, const float* __restrict__ norm2) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= k.B) return;
+  float n2 = norm2[env * 2], n2a = norm2[env * 2 + 1];
+  const float* sc = g_scal + env * GS_STRIDE;
+  if (gin.friction) gin.friction[env] = norm_div(sc[GS_FRICTION], n2);
+  if (gin.mu) gin.mu[env] = norm_div(sc[GS_MU], n2);
+  if (gin.lamda) gin.lamda[env] = norm_div(sc[GS_LAMDA], n2);
+  const int S = k.S;
+  for (int q = 0; q < k.n_prim; ++q) {
+    const float* ps = sc + GS_PRIM + q * GS_PRIM_STRIDE;
+    const float* pi = g_prim_in + ((size_t)env * k.n_prim + q) * 16;
+    const ud_primitive& gi = gin.prim[q];
+    if (gi.size)
+      for (int j = 0; j < 3; ++j) gi.size[env * 3 + j] = norm_div(ps[j], n2);
+    if (gi.friction) gi.friction[env] = norm_div(ps[3], n2);
+    // only row 0 of the input tables reaches the output (rows >= 1 and v, w, action_buffer are
+    // overwritten by FK / set_action)
+    for (int f = 0; f < S; ++f) {
+      for (int j = 0; j < 3; ++j) {
+        if (gi.position) gi.position[((size_t)env * S + f) * 3 + j] = f == 0 ? norm_div(pi[j], n2) : 0.f;
+        if (gi.v) gi.v[((size_t)env * S + f) * 3 + j] = 0.f;
+        if (gi.w) gi.w[((size_t)env * S + f) * 3 + j] = 0.f;
+      }
+      for (int j = 0; j < 4; ++j)
+        if (gi.rotation) gi.rotation[((size_t)env * S + f) * 4 + j] = f == 0 ? norm_div(pi[3 + j], n2) : 0.f;
+    }
+    for (int j = 0; j < 6; ++j) {
+      if (gi.action_scale) gi.action_scale[env * 6 + j] = norm_div(pi[7 + j], n2);
+      if (gi.action_buffer) gi.action_buffer[env * 6 + j] = 0.f;
+      if (gaction) gaction[(size_t)env * 6 * k.n_prim + 6 * q + j] =
+          norm_div(g_act[((size_t)env * k.n_prim + q) * 6 + j], n2a);
+    }
+  }
+}
+
+void launch_finish_bwd(const MpmConst& k, const ud_mpm_state* in, const ud_mpm_state* gout,
+                       ud_mpm_state* gin, const float* action, float* gaction, const MpmWs& ws,
+                       cudaStream_t st) {
+  (void)in;
+  (void)action;
+  cudaMemsetAsync(ws.norm2, 0, 4 * (size_t)k.B * 2, st);
+  k_norm_particles<<<pgrid(k, 256), 256, 0, st>>>(k, ws.gs, ws.norm2);
+  k_norm_small<<<cdiv(k.B, 64), 64, 0, st>>>(k, *gout, ws.g_scal, ws.g_prim_in, ws.g_act, ws.norm2);
+  k_unsort_cot<<<pgrid(k, 256), 256, 0, st>>>(k, ws.gs, ws.perm, ws.norm2, gin->x, gin->v, gin->C, gin->F,
+                                              gin->J);
+  k_write_small<<<cdiv(k.B, 64), 64, 0, st>>>(k, *gin, gaction, ws.g_scal, ws.g_prim_in, ws.g_act, ws.norm2);
 }
 
 }  // namespace ud
