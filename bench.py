@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the DaXBench simulator step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE configs[1] "push_plasticine" = the reference's
+envs/shape_elasto_plastic.py scene scaled to 50 625 particles/env (add_box density 3.9),
+num_envs = 32 per GPU, S = 16 substeps per step, forward + backward (adjoint with
+recompute) of one `SimpleMPMSimulator.step_jax` call = one "step".
+
+metric  = particle-substeps/s, forward+backward:  envs * particles * substeps / time.
+value   = inputs resident in HBM, CUDA events around exactly K steps, max over ranks.
+e2e     = same metric through the public API with HOST (pinned) buffers: H2D of the step inputs,
+          fwd+bwd, D2H of the new state and all gradients inside the timed region.
+roofline= dominant kernel class: algorithmic bytes per launch / mean launch time (CUDA events on
+          the launching stream, measured live) against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline = the CPU oracle (torch restatement of the reference; JAX is not installable here)
+          timed on the host cores on a bounded sample of the same scene.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# algorithmic bytes per particle per launch of each kernel class:
+ALG_BYTES = {"p2g": 132, "g2p": 72, "g2p_bwd": 84, "p2g_bwd": 240}
+ALG_BYTES_FWD, ALG_BYTES_FWDBWD = 200, 700          # SURVEY.md section 8(d) contract figures
+
+DENSITY, ENVS_PER_GPU = 3.9, 32
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_scene(sim, density):
+    """shape_elasto_plastic reset (envs/shape_elasto_plastic.py:139-157) already shifted to the
+    focus point the env's pre_step uses (mpm_env.py:99-114): centroid at res/2 cells."""
+    from unidom_b200.mpm_simulator import create_primitive
+    conf = sim.conf
+    state = sim.add_box(conf=conf, state=None, hardness=1.0, size=[0.2, 0.06, 0.12], init_pos=[0.25, 0.07, 0.25],
+                        z_rotation_angle=0, material=2, density=density)
+    state.primitives.append(create_primitive(conf, friction=0.1, softness=666, color=[0.5, 0.5, 0.5],
+                                             size=[0.015, 0.06, 0.015], init_pos=[0.25, 0.01, 0.20]))
+    return sim.reset_jax(state)
+
+
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_cotangents(state, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    B, n = state.x.shape[:2]
+    dev = state.x.device
+    return {"x": (torch.randn((B, n, 3), generator=g) * 1e-3).to(dev),
+            "v": (torch.randn((B, n, 3), generator=g) * 1e-4).to(dev)}
+
+
+def fwd_bwd(sim, state, action, cot):
+    """One step through the public API: forward (S substeps) + adjoint w.r.t. state and action."""
+    leaves = {k: getattr(state, k).detach().requires_grad_(True) for k in ("x", "v", "C", "F")}
+    a = action.detach().requires_grad_(True)
+    out, _ = sim.step_jax(state._replace(**leaves), a)
+    loss = (out.x * cot["x"]).sum() + (out.v * cot["v"]).sum()
+    grads = torch.autograd.grad(loss, list(leaves.values()) + [a])
+    return out, grads, loss
+
+
+def detach_state(s):
+    from unidom_b200.mpm_simulator import PrimitiveState
+    prims = [PrimitiveState(*[t.detach() for t in p]) for p in s.primitives]
+    vals = {k: getattr(s, k).detach() for k in s._fields if k != "primitives"}
+    return s._replace(primitives=prims, **vals)
+
+
+def cpu_oracle_rate(conf, n_envs, density, substeps, repeat, threads):
+    """particle-substeps/s (fwd+bwd) of the CPU oracle on a bounded sample of the same scene."""
+    import numpy as np
+    from oracle import mpm as omp, primitives as oP
+    torch.set_num_threads(threads)
+    oconf = omp.MPMConf(n_grid=conf.n_grid, res=tuple(conf.res), dt=conf.dt, steps=substeps, E=conf.E, nu=conf.nu,
+                        ground_friction=conf.ground_friction, gravity=tuple(conf.gravity),
+                        n_primitive=conf.n_primitive, sdf_kind=conf.sdf_kind)
+    x = omp.add_box(oconf, [0.2, 0.06, 0.12], [0.25, 0.07, 0.25], density=density)
+    n = x.shape[0]
+    prim = oP.create_primitive(substeps, 0.1, 666.0, [0.5] * 3, [0.015, 0.06, 0.015], [0.25, 0.01, 0.20])
+    sim = omp.Simulator(oconf, torch.full((n,), 2, dtype=torch.int32), torch.ones(n))
+    st = omp.reset_state(oconf, x, [prim], n_envs)
+    act = torch.tensor([[0.003, 0.0, 0.004, 0.0, 0.0, 0.0]]).repeat(n_envs, 1)
+    g = torch.Generator().manual_seed(0)
+    cx = torch.randn((n_envs, n, 3), generator=g) * 1e-3
+    best = None
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        xs = st.x.clone().requires_grad_(True)
+        a = act.clone().requires_grad_(True)
+        out = omp.step_batch(sim, st._replace(x=xs), a)
+        ((out.x * cx).sum()).backward()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_envs * n * substeps / best, n, best
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path.  The reference itself (JAX) cannot
+    be installed in this image (no jax/jaxlib wheel, no network), so this times the oracle PORT
+    (oracle/, a torch-CPU restatement of the same arithmetic) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from unidom_b200 import confs
+    conf = confs.shape_elasto_plastic_conf()
+    threads = os.cpu_count() or 1
+    sub = 2
+    for _ in range(max(args.warmup, 0)):
+        cpu_oracle_rate(conf, 1, 1.5, sub, 1, threads)     # short warm-up on a lighter sample
+    rates, secs = [], []
+    for _ in range(args.steps):
+        r, n, dt = cpu_oracle_rate(conf, 1, DENSITY, sub, 1, threads)
+        rates.append(r)
+        secs.append(dt)
+    total = sum(secs)
+    value = len(secs) * n * sub / total
+    line = {
+        "impl": "reference", "metric": "particle-substeps/s fwd+bwd", "value": value, "unit": "particle-substeps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(secs),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(n), "sample": f"1 env x {n} particles x {sub} substeps fwd+bwd per step"},
+        "cpu_baseline": {"value": value, "unit": "particle-substeps/s", "cores": threads, "kind": "port",
+                         "sample": f"1 env x {n} particles x {sub} substeps fwd+bwd, torch-CPU oracle"},
+        "e2e": {"value": value, "unit": "particle-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(n):
+    return (f"push_plasticine = shape_elasto_plastic MLS-MPM fwd+bwd, {n} particles/env, "
+            f"num_envs={ENVS_PER_GPU}/GPU, res=(48,32,48), 16 substeps/step")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--density", type=float, default=DENSITY)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--p2g-mode", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from unidom_b200 import _lib, confs
+    from unidom_b200.mpm_simulator import SimpleMPMSimulator
+    L = _lib.lib()
+    conf = confs.shape_elasto_plastic_conf()
+    sim = SimpleMPMSimulator(conf, args.envs, device=dev, p2g_mode=args.p2g_mode)
+    state = build_scene(sim, args.density)
+    B, n = state.x.shape[:2]
+    S = conf.steps
+    g = torch.Generator().manual_seed(1234 + rank)
+    action = (torch.tensor([0.003, 0.0, 0.004, 0.0, 0.0, 0.0]) + 5e-4 * torch.randn((B, 6), generator=g)).to(dev)
+    action[:, 3:] = 0
+    cot = make_cotangents(state, 99 + rank)
+    units_per_step = B * n * S
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident timing (value)
+    for _ in range(max(args.warmup, 3)):
+        out, grads, _ = fwd_bwd(sim, state, action, cot)
+        state = detach_state(out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    L.ud_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out, grads, _ = fwd_bwd(sim, state, action, cot)
+        state = detach_state(out)
+    e1.record()
+    barrier()
+    launches = int(L.ud_launch_count(0))
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * units_per_step * args.steps / (ms * 1e-3)
+
+    # ---------------- forward-only rate (reported next to the headline)
+    with torch.no_grad():
+        for _ in range(2):
+            sim.step_jax(state, action)
+        torch.cuda.synchronize(dev)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        s2 = state
+        for _ in range(args.steps):
+            s2, _ = sim.step_jax(s2, action)
+        f1.record()
+        torch.cuda.synchronize(dev)
+    fwd_value = world * units_per_step * args.steps / (f0.elapsed_time(f1) * 1e-3)
+
+    # ---------------- per-kernel-class timing (roofline), live CUDA events on the launch stream
+    L.ud_timing_enable(1)
+    nprof = min(args.steps, 5)
+    for _ in range(nprof):
+        out, grads, _ = fwd_bwd(sim, state, action, cot)
+        state = detach_state(out)
+    torch.cuda.synchronize(dev)
+    ncls = L.ud_timing_num_classes()
+    msb = (C.c_double * ncls)()
+    cnt = (C.c_int64 * ncls)()
+    L.ud_timing_collect(msb, cnt, ncls)
+    L.ud_timing_enable(0)
+    L.ud_timing_class_name.restype = C.c_char_p
+    classes = {L.ud_timing_class_name(i).decode(): (msb[i], cnt[i]) for i in range(ncls) if cnt[i] > 0}
+    tot_ms = sum(v[0] for v in classes.values())
+    peak, peak_src = peaks()
+    kern = {}
+    for name, (m, c) in classes.items():
+        avg_ms = m / c
+        ent = {"share": m / tot_ms, "avg_ms": avg_ms, "launches_per_step": c / nprof}
+        if name in ALG_BYTES:
+            ent["gbs"] = ALG_BYTES[name] * B * n / (avg_ms * 1e-3) / 1e9
+        kern[name] = ent
+    dom = max((k for k in kern if k in ALG_BYTES), key=lambda k: kern[k]["share"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": kern[dom]["share"],
+                "algorithmic_bytes_per_launch": ALG_BYTES[dom] * B * n,
+                "step_frac_fwdbwd": (value / world) * ALG_BYTES_FWDBWD / 1e9 / peak,
+                "step_frac_fwd": (fwd_value / world) * ALG_BYTES_FWD / 1e9 / peak}
+
+    # ---------------- end-to-end with host buffers (pinned), copies inside the timed region
+    names = ("x", "v", "C", "F", "J")
+    host_in = {k: getattr(state, k).detach().cpu().pin_memory() for k in names}
+    host_act = action.detach().cpu().pin_memory()
+    host_out = {k: torch.empty_like(host_in[k]).pin_memory() for k in names}
+    host_g = {k: torch.empty_like(host_in[k]).pin_memory() for k in ("x", "v", "C", "F")}
+    host_ga = torch.empty_like(host_act).pin_memory()
+    h2d = sum(t.numel() * 4 for t in host_in.values()) + host_act.numel() * 4
+    d2h = sum(t.numel() * 4 for t in host_out.values()) + sum(t.numel() * 4 for t in host_g.values()) \
+        + host_ga.numel() * 4
+
+    def e2e_step():
+        st = state._replace(**{k: host_in[k].to(dev, non_blocking=True) for k in names})
+        a = host_act.to(dev, non_blocking=True)
+        o, gr, _ = fwd_bwd(sim, st, a, cot)
+        for k in names:
+            host_out[k].copy_(getattr(o, k).detach(), non_blocking=True)
+        for k, t in zip(("x", "v", "C", "F"), gr[:4]):
+            host_g[k].copy_(t, non_blocking=True)
+        host_ga.copy_(gr[4], non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    g0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    g1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    e2e_ms = max(g0.elapsed_time(g1), wall_ms)
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * units_per_step * args.steps / (e2e_ms * 1e-3)
+
+    # ---------------- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, n_cpu, secs = cpu_oracle_rate(conf, 1, args.density, 2, 2, threads)
+        cpu = {"value": rate, "unit": "particle-substeps/s", "cores": threads, "kind": "port",
+               "sample": f"1 env x {n_cpu} particles x 2 substeps fwd+bwd (best of 2, {secs:.1f} s each), "
+                         "torch-CPU oracle restating the reference (JAX not installable in this image)"}
+
+    if rank == 0:
+        line = {
+            "metric": "particle-substeps/s fwd+bwd", "value": value, "unit": "particle-substeps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(n), "envs_per_gpu": B, "particles_per_env": n, "substeps": S,
+                       "l2": f"inputs larger than L2 (state+checkpoints {B * n * 96 * (S + 1) / 1e9:.2f} GB per step)",
+                       "p2g_mode": "atomic" if args.p2g_mode == 0 else "deterministic",
+                       "collective": "none in the step (envs are independent; APG's policy-gradient all-reduce "
+                                     "is outside this path)"},
+            "forward_only": {"value": fwd_value, "unit": "particle-substeps/s"},
+            "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "kernels": {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()}
+                        for k, v in kern.items()},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

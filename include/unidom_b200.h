@@ -125,6 +125,17 @@ int ud_mpm_sort_bins(const ud_mpm_params* p, const float* x, int32_t* out_base, 
 /* Number of keys per env used by ud_mpm_sort_bins (for sizing host-side checks). */
 int32_t ud_mpm_num_keys(const ud_mpm_params* p);
 
+/* ---- instrumentation (bench.py): launch counting and per-kernel-class CUDA-event timing ------
+ * ud_launch_count: kernels + memsets enqueued by this library since the last reset (host counter).
+ * ud_timing_enable(1): subsequent calls bracket every kernel class with cudaEvents on the call's
+ * stream; ud_timing_collect synchronises those events and returns, per class, the summed device
+ * milliseconds and number of launches since the last collect.  Class names: ud_timing_class_name. */
+uint64_t ud_launch_count(int reset);
+void ud_timing_enable(int on);
+int ud_timing_num_classes(void);
+const char* ud_timing_class_name(int cls);
+int ud_timing_collect(double* ms_by_class, int64_t* launches_by_class, int n_classes);
+
 #ifdef __cplusplus
 }
 #endif

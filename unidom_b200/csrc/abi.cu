@@ -3,9 +3,40 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "mpm_internal.h"
 
 namespace ud {
+
+// ---- instrumentation ---------------------------------------------------------------------------
+static std::atomic<uint64_t> g_launches{0};
+static bool g_timing = false;
+struct TimingRec { int cls; int n; cudaEvent_t a, b; };
+static std::vector<TimingRec> g_recs;      // in flight since the last collect
+static std::vector<cudaEvent_t> g_pool;    // recycled events
+static std::mutex g_tmu;
+
+static cudaEvent_t ev_get() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+KScope::KScope(int cls_, cudaStream_t st_, int n) : cls(cls_), st(st_), slot(-1) {
+  g_launches += (uint64_t)n;
+  if (!g_timing) return;
+  std::lock_guard<std::mutex> lk(g_tmu);
+  TimingRec r; r.cls = cls; r.n = n; r.a = ev_get(); r.b = ev_get();
+  cudaEventRecord(r.a, st);
+  slot = (int)g_recs.size();
+  g_recs.push_back(r);
+}
+KScope::~KScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_tmu);
+  cudaEventRecord(g_recs[slot].b, st);
+}
 
 static thread_local const char* g_last_error = "";
 static int fail(int code, const char* what) {
@@ -51,6 +82,11 @@ bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k) {
   k->pos_control = p->use_position_control ? 1 : 0;
   k->p2g_mode = p->p2g_mode;
   return true;
+}
+
+static inline void zero_async(void* p, size_t bytes, cudaStream_t st) {
+  KScope ks(KC_MEMSET, st);
+  cudaMemsetAsync(p, 0, bytes, st);
 }
 
 static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -120,6 +156,35 @@ using namespace ud;
 extern "C" {
 
 const char* ud_version(void) { return "unidom_b200 0.1 (sm_100a)"; }
+
+uint64_t ud_launch_count(int reset) {
+  uint64_t v = g_launches.load();
+  if (reset) g_launches = 0;
+  return v;
+}
+void ud_timing_enable(int on) { g_timing = on != 0; }
+int ud_timing_num_classes(void) { return KC_COUNT; }
+const char* ud_timing_class_name(int cls) {
+  static const char* names[KC_COUNT] = {"sort", "gather", "fk", "p2g", "grid", "g2p", "unsort", "g2p_bwd",
+                                        "grid_bwd", "p2g_bwd", "finish_bwd", "memset", "cloth_fwd", "cloth_bwd"};
+  return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "";
+}
+int ud_timing_collect(double* ms_by_class, int64_t* launches_by_class, int n_classes) {
+  if (!ms_by_class || !launches_by_class || n_classes < KC_COUNT) return UD_E_INVALID;
+  std::lock_guard<std::mutex> lk(g_tmu);
+  for (int i = 0; i < n_classes; ++i) { ms_by_class[i] = 0; launches_by_class[i] = 0; }
+  for (auto& r : g_recs) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    ms_by_class[r.cls] += ms;
+    launches_by_class[r.cls] += r.n;
+    g_pool.push_back(r.a);
+    g_pool.push_back(r.b);
+  }
+  g_recs.clear();
+  return UD_OK;
+}
 const char* ud_last_error(void) { return g_last_error; }
 
 size_t ud_mpm_fwd_workspace_bytes(const ud_mpm_params* p) {
@@ -171,9 +236,9 @@ int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   launch_sort(k, in->x, ws, nullptr, st);
   launch_gather_state(k, in, material, h, ws, ws.ps, st);
   launch_fk_fwd(k, in, action, out, ws, st);
-  cudaMemsetAsync(ws.jrows, 0, 4 * (size_t)k.B * k.S * 9, st);
+  zero_async(ws.jrows, 4 * (size_t)k.B * k.S * 9, st);
   for (int f = 0; f < k.S; ++f) {
-    cudaMemsetAsync(ws.grid_raw, 0, 16 * (size_t)k.B * k.G, st);
+    zero_async(ws.grid_raw, 16 * (size_t)k.B * k.G, st);
     launch_p2g(k, ws.ps, ws.ps, ws.grid_raw, in->mu, in->lamda, ws, st);
     launch_grid_fwd(k, ws.grid_raw, ws.grid_raw, f, in, ws, st);
     launch_g2p(k, ws.ps, ws.ps, ws.grid_raw, f, ws, st);
@@ -205,7 +270,7 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   launch_sort(k, in->x, ws, nullptr, st);
   launch_gather_state(k, in, material, h, ws, ws.ps, st);
   launch_fk_fwd(k, in, action, nullptr, ws, st);
-  cudaMemsetAsync(ws.grid_raw, 0, 16 * BG * k.S, st);
+  zero_async(ws.grid_raw, 16 * BG * k.S, st);
   for (int f = 0; f < k.S; ++f) {
     const float* s_in = ws.ps + slot * f;
     float* s_out = ws.ps + slot * (f + 1);
@@ -215,15 +280,15 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   }
   // ---- reverse pass
   launch_gather_cot(k, gout, ws, st);
-  cudaMemsetAsync(ws.g_fk_pos, 0, 4 * (size_t)k.B * P * (k.S + 1) * 3, st);
-  cudaMemsetAsync(ws.g_fk_rot, 0, 4 * (size_t)k.B * P * (k.S + 1) * 4, st);
-  cudaMemsetAsync(ws.g_fk_v, 0, 4 * (size_t)k.B * P * k.S * 3, st);
-  cudaMemsetAsync(ws.g_scal, 0, 4 * (size_t)k.B * GS_STRIDE, st);
-  cudaMemsetAsync(ws.g_prim_in, 0, 4 * (size_t)k.B * P * 16, st);
-  cudaMemsetAsync(ws.g_act, 0, 4 * (size_t)k.B * P * 6, st);
+  zero_async(ws.g_fk_pos, 4 * (size_t)k.B * P * (k.S + 1) * 3, st);
+  zero_async(ws.g_fk_rot, 4 * (size_t)k.B * P * (k.S + 1) * 4, st);
+  zero_async(ws.g_fk_v, 4 * (size_t)k.B * P * k.S * 3, st);
+  zero_async(ws.g_scal, 4 * (size_t)k.B * GS_STRIDE, st);
+  zero_async(ws.g_prim_in, 4 * (size_t)k.B * P * 16, st);
+  zero_async(ws.g_act, 4 * (size_t)k.B * P * 6, st);
   for (int f = k.S - 1; f >= 0; --f) {
     const float* s_in = ws.ps + slot * f;
-    cudaMemsetAsync(ws.ggrid, 0, 16 * BG, st);
+    zero_async(ws.ggrid, 16 * BG, st);
     launch_g2p_bwd(k, s_in, ws.grid_out + BG * f, ws, st);
     launch_grid_bwd(k, ws.grid_raw + BG * f, f, in, ws, st);
     launch_p2g_bwd(k, s_in, in->mu, in->lamda, ws, st);

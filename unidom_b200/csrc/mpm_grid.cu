@@ -111,6 +111,7 @@ void launch_fk_fwd(const MpmConst& k, const ud_mpm_state* in, const float* actio
                    const MpmWs& ws, cudaStream_t st) {
   int n = k.B * k.n_prim;
   if (n == 0) return;
+  KScope ks_(KC_FK, st);
   k_fk_fwd<<<cdiv(n, 64), 64, 0, st>>>(k, *in, action, out ? *out : *in, ws.fk_pos, ws.fk_rot, ws.fk_vw,
                                        ws.fk_act, out != nullptr);
 }
@@ -165,6 +166,7 @@ k_grid_fwd(MpmConst k, const float4* grid_in, float4* grid_out, int f,
 
 void launch_grid_fwd(const MpmConst& k, const float4* grid_in, float4* grid_out, int substep,
                      const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st) {
+  KScope ks_(KC_GRID, st);
   k_grid_fwd<<<cdiv((long long)k.B * k.G, 128), 128, 0, st>>>(k, grid_in, grid_out, substep, *in, ws.fk_pos,
                                                               ws.fk_rot, ws.fk_vw);
 }
@@ -272,6 +274,7 @@ k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__
 void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,
                      const MpmWs& ws, cudaStream_t st) {
   dim3 grid(cdiv(k.G, 128), k.B);
+  KScope ks_(KC_GRID_BWD, st);
   k_grid_bwd<<<grid, 128, 0, st>>>(k, grid_raw, ws.ggrid, substep, *in, ws.fk_pos, ws.fk_rot, ws.fk_vw,
                                    ws.g_fk_pos, ws.g_fk_rot, ws.g_fk_v, ws.g_scal);
 }
@@ -377,6 +380,7 @@ void launch_fk_bwd(const MpmConst& k, const ud_mpm_state* in, const float* actio
                    const ud_mpm_state* gout, const MpmWs& ws, cudaStream_t st) {
   int n = k.B * k.n_prim;
   if (n == 0) return;
+  KScope ks_(KC_FK, st);
   k_fk_bwd<<<cdiv(n, 64), 64, 0, st>>>(k, *in, action, *gout, ws.fk_pos, ws.fk_rot, ws.fk_vw, ws.fk_act,
                                        ws.g_fk_pos, ws.g_fk_rot, ws.g_fk_v, ws.g_prim_in, ws.g_act);
 }

@@ -95,6 +95,7 @@ __global__ void k_rank(MpmConst k, const int32_t* __restrict__ keys, const int32
 }
 
 void launch_sort(const MpmConst& k, const float* x_aos, const MpmWs& ws, int32_t* out_base, cudaStream_t st) {
+  KScope ks_(KC_SORT, st, 6);
   cudaMemsetAsync(ws.cell_start, 0, sizeof(int32_t) * (size_t)k.B * (k.NK + 1), st);
   cudaMemsetAsync(ws.cursor, 0, sizeof(int32_t) * (size_t)k.B * k.NK, st);
   k_keys<<<pgrid(k, 256), 256, 0, st>>>(k, x_aos, ws.keys, ws.cell_start, out_base);
@@ -131,6 +132,7 @@ __global__ void k_gather_state(MpmConst k, const float* __restrict__ x, const fl
 
 void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
                          const MpmWs& ws, float* ps_slot, cudaStream_t st) {
+  KScope ks_(KC_GATHER, st);
   k_gather_state<<<pgrid(k, 256), 256, 0, st>>>(k, in->x, in->v, in->C, in->F, material, h, ws.perm, ps_slot,
                                                   ws.mat_s, ws.h_s);
 }
@@ -198,6 +200,7 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
 
 void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
                 const float* la_s, const MpmWs& ws, cudaStream_t st) {
+  KScope ks_(KC_P2G, st);
   k_p2g<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s);
 }
 
@@ -264,6 +267,7 @@ k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ 
 
 void launch_g2p(const MpmConst& k, const float* ps_in, float* ps_out, const float4* grid, int substep,
                 const MpmWs& ws, cudaStream_t st) {
+  KScope ks_(KC_G2P, st);
   k_g2p<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, ws.perm, ws.jrows, substep);
 }
 
@@ -303,6 +307,7 @@ __global__ void k_unsort_state(MpmConst k, const float* __restrict__ ps, const f
 
 void launch_unsort_state(const MpmConst& k, const float* ps_slot, const float* J_in, const MpmWs& ws,
                          ud_mpm_state* out, cudaStream_t st) {
+  KScope ks_(KC_UNSORT, st);
   k_unsort_state<<<pgrid(k, 256), 256, 0, st>>>(k, ps_slot, J_in, ws.perm, ws.jrows, out->x, out->v, out->C,
                                                   out->F, out->J);
 }
@@ -331,6 +336,7 @@ __global__ void k_gather_cot(MpmConst k, const float* __restrict__ gx, const flo
 }
 
 void launch_gather_cot(const MpmConst& k, const ud_mpm_state* gout, const MpmWs& ws, cudaStream_t st) {
+  KScope ks_(KC_GATHER, st);
   k_gather_cot<<<pgrid(k, 256), 256, 0, st>>>(k, gout->x, gout->v, gout->C, gout->F, ws.perm, ws.gs);
 }
 
@@ -401,6 +407,7 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
 
 void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
                     cudaStream_t st) {
+  KScope ks_(KC_G2P_BWD, st);
   k_g2p_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
 }
 
@@ -503,6 +510,7 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
 
 void launch_p2g_bwd(const MpmConst& k, const float* ps_in, const float* mu_s, const float* la_s,
                     const MpmWs& ws, cudaStream_t st) {
+  KScope ks_(KC_P2G_BWD, st);
   k_p2g_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ws.ggrid, ws.gs, mu_s, la_s, ws.mat_s, ws.h_s,
                                                      ws.g_scal);
 }
@@ -642,6 +650,7 @@ __global__ void k_write_small(MpmConst k, ud_mpm_state gin, float* __restrict__ 
 void launch_finish_bwd(const MpmConst& k, const ud_mpm_state* in, const ud_mpm_state* gout,
                        ud_mpm_state* gin, const float* action, float* gaction, const MpmWs& ws,
                        cudaStream_t st) {
+  KScope ks_(KC_FINISH_BWD, st, 5);
   (void)in;
   (void)action;
   cudaMemsetAsync(ws.norm2, 0, 4 * (size_t)k.B * 2, st);
