@@ -251,17 +251,21 @@ UD_DEV void position_control_cell(int kind, float dt, const float gpos[3], const
 }
 
 // mpm_simulator.py:283-313 for one cell with m > 0.  p = scattered momentum, m = scattered mass.
-template <class T>
+// `prim_of(q, pr)` fills primitive q and returns false when the primitive is to be skipped (the
+// adjoint skips primitives whose influence on this cell is below 1e-12; the forward never skips).
+template <class T, class PF>
 UD_DEV void cell_update(const MpmConst& k, int ci, int cj, int ck, const T p[3], const T& m, const T& sfric,
-                        const PrimIn<T>* prims, T v[3]) {
+                        PF prim_of, T v[3]) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) v[i] = p[i] / m + k.gdt[i];
   const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
   for (int q = 0; q < k.n_prim; ++q) {
+    PrimIn<T> pr;
+    if (!prim_of(q, pr)) continue;
     if (k.pos_control)
-      position_control_cell(k.sdf_kind, k.dt, gpos, prims[q], v);
+      position_control_cell(k.sdf_kind, k.dt, gpos, pr, v);
     else
-      collide_cell(k.sdf_kind, k.dt, gpos, prims[q], v);
+      collide_cell(k.sdf_kind, k.dt, gpos, pr, v);
   }
   // ground friction (:297-307)
   const float ie[3] = {(float)ci * 1e-30f, (float)cj * 1e-30f, (float)ck * 1e-30f};
@@ -282,6 +286,19 @@ UD_DEV void cell_update(const MpmConst& k, int ci, int cj, int ck, const T p[3],
     bool cond = (cidx[d] < 3 && s_val(v[d]) < 0.f) || (cidx[d] > k.n_grid - 3 && s_val(v[d]) > 0.f);
     if (cond) v[d] = s_const(v[d], 0.f);
   }
+}
+
+// Does primitive `pr` act on the cell at gpos?  collide: influence = min(exp(-dist*softness),1) >= 1e-12
+// (below that every derivative w.r.t. the primitive is < 1e-12 relative and d v_out / d v_in = I);
+// position control: the mask itself.
+UD_DEV bool prim_active(const MpmConst& k, const float gpos[3], const PrimIn<float>& pr) {
+  float iq[4], rel[3], gp[3];
+  inv_quat(pr.rot_f, iq);
+  for (int i = 0; i < 3; ++i) rel[i] = gpos[i] - pr.pos_f[i];
+  qrot(iq, rel, gp);
+  float dist = sdf_local(k.sdf_kind, pr.size, gp);
+  if (k.pos_control) return dist < pr.size[0] * 1.5f;
+  return fminf(expf(-dist * pr.softness), 1.f) >= 1e-12f;
 }
 
 }  // namespace ud

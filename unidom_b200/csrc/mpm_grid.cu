@@ -157,10 +157,12 @@ k_grid_fwd(MpmConst k, const float4* grid_in, float4* grid_out, int f,
   int env = (int)(idx / k.G);
   int c = (int)(idx - (size_t)env * k.G);
   int ck = c % k.rz, cj = (c / k.rz) % k.ry, ci = c / (k.rz * k.ry);
-  PrimIn<float> prims[UD_MAX_PRIM];
-  for (int q = 0; q < k.n_prim; ++q) load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, prims[q]);
   float p[3] = {g.x, g.y, g.z}, v[3];
-  cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prims, v);
+  auto prim_of = [&](int q, PrimIn<float>& pr) {
+    load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
+    return true;
+  };
+  cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
   grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
 }
 
@@ -172,27 +174,38 @@ void launch_grid_fwd(const MpmConst& k, const float4* grid_in, float4* grid_out,
 }
 
 // ================================================================================================
-// Adjoint of the grid update.  One thread per cell with mass and a non-zero incoming cotangent:
-// forward-mode tangents of cell_update in chunks of ND inputs, contracted with the cotangent of the
-// updated velocity.  Inputs (in order): p(3), m, state.friction, then PRIM_NIN scalars per primitive.
-// Per-cell results (g_momentum, g_mass) overwrite ggrid; the rest is warp-reduced and accumulated
-// into the per-env scalar / primitive-table cotangents.
+// Adjoint of the grid update.  One thread per cell with mass and a non-zero incoming cotangent.
+// Forward-mode tangents of cell_update, contracted with the cotangent of the updated velocity:
+//   pass A  (Dual<5>): inputs p(3), m, state.friction          -> per-cell (g_momentum, g_mass)
+//   pass Pq (Dual<7> x 3): the PRIM_NIN = 21 inputs of primitive q, only where q acts on the cell
+// Primitive / friction cotangents are warp-reduced and accumulated per env.
 // ================================================================================================
-constexpr int ND = 8;
-typedef Dual<ND> DualN;
-
-UD_DEV DualN seed(float v, int idx, int chunk) {
-  DualN r;
-  r.v = v;
-#pragma unroll
-  for (int i = 0; i < ND; ++i) r.d[i] = (idx == chunk * ND + i) ? 1.f : 0.f;
-  return r;
-}
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
   return v;
+}
+
+template <int N>
+UD_DEV Dual<N> seed(float v, int idx, int first) {
+  Dual<N> r;
+  r.v = v;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = (idx == first + i) ? 1.f : 0.f;
+  return r;
+}
+
+// promote a float primitive to duals; inputs [first, first+N) of ITS OWN 21 scalars get unit tangents
+template <int N>
+UD_DEV void promote_prim(const PrimIn<float>& a, int first, PrimIn<Dual<N>>& o) {
+  for (int j = 0; j < 3; ++j) o.pos_f[j] = seed<N>(a.pos_f[j], j, first);
+  for (int j = 0; j < 4; ++j) o.rot_f[j] = seed<N>(a.rot_f[j], 3 + j, first);
+  for (int j = 0; j < 3; ++j) o.pos_f1[j] = seed<N>(a.pos_f1[j], 7 + j, first);
+  for (int j = 0; j < 4; ++j) o.rot_f1[j] = seed<N>(a.rot_f1[j], 10 + j, first);
+  for (int j = 0; j < 3; ++j) o.size[j] = seed<N>(a.size[j], 14 + j, first);
+  o.friction = seed<N>(a.friction, 17, first);
+  for (int j = 0; j < 3; ++j) o.v_f[j] = seed<N>(a.v_f[j], 18 + j, first);
+  o.softness = a.softness;
 }
 
 __global__ void __launch_bounds__(128)
@@ -208,67 +221,80 @@ k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__
   float4 gv = ggrid[idx];
   bool work = live && g.w > 0.f && (gv.x != 0.f || gv.y != 0.f || gv.z != 0.f);
   if (live && !work) ggrid[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!__any_sync(0xffffffffu, work)) return;  // warp-uniform exit (no barriers below)
-  const int n_in = 5 + PRIM_NIN * k.n_prim;
-  const int n_chunk = (n_in + ND - 1) / ND;
+  if (!__any_sync(0xffffffffu, work)) return;  // warp-uniform exit (no block barriers below)
   int ck = c % k.rz, cj = (c / k.rz) % k.ry, ci = c / (k.rz * k.ry);
-  PrimIn<float> pf[UD_MAX_PRIM];
-  for (int q = 0; q < k.n_prim; ++q) load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pf[q]);
-  float sfric = in.friction[env];
-  float gp[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int ch = 0; ch < n_chunk; ++ch) {
-    float gin[ND];
-#pragma unroll
-    for (int i = 0; i < ND; ++i) gin[i] = 0.f;
-    if (work) {
-      DualN p[3] = {seed(g.x, 0, ch), seed(g.y, 1, ch), seed(g.z, 2, ch)};
-      DualN m = seed(g.w, 3, ch), sf = seed(sfric, 4, ch);
-      PrimIn<DualN> pr[UD_MAX_PRIM];
-      for (int q = 0; q < k.n_prim; ++q) {
-        int b0 = 5 + PRIM_NIN * q;
-        for (int j = 0; j < 3; ++j) pr[q].pos_f[j] = seed(pf[q].pos_f[j], b0 + j, ch);
-        for (int j = 0; j < 4; ++j) pr[q].rot_f[j] = seed(pf[q].rot_f[j], b0 + 3 + j, ch);
-        for (int j = 0; j < 3; ++j) pr[q].pos_f1[j] = seed(pf[q].pos_f1[j], b0 + 7 + j, ch);
-        for (int j = 0; j < 4; ++j) pr[q].rot_f1[j] = seed(pf[q].rot_f1[j], b0 + 10 + j, ch);
-        for (int j = 0; j < 3; ++j) pr[q].size[j] = seed(pf[q].size[j], b0 + 14 + j, ch);
-        pr[q].friction = seed(pf[q].friction, b0 + 17, ch);
-        for (int j = 0; j < 3; ++j) pr[q].v_f[j] = seed(pf[q].v_f[j], b0 + 18 + j, ch);
-        pr[q].softness = pf[q].softness;
-      }
-      DualN v[3];
-      cell_update<DualN>(k, ci, cj, ck, p, m, sf, pr, v);
-#pragma unroll
-      for (int i = 0; i < ND; ++i) gin[i] = gv.x * v[0].d[i] + gv.y * v[1].d[i] + gv.z * v[2].d[i];
+  const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
+  const float sfric = in.friction[env];
+  unsigned act = 0;  // bit q: primitive q acts on this cell
+  if (work)
+    for (int q = 0; q < k.n_prim; ++q) {
+      PrimIn<float> pf;
+      load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pf);
+      if (prim_active(k, gpos, pf)) act |= 1u << q;
     }
-    // distribute: inputs 0..3 are per cell, the rest reduce over the env
+  // ---- pass A
+  {
+    typedef Dual<5> D5;
+    float gsf = 0.f;
+    if (work) {
+      D5 p[3] = {seed<5>(g.x, 0, 0), seed<5>(g.y, 1, 0), seed<5>(g.z, 2, 0)};
+      D5 m = seed<5>(g.w, 3, 0), sf = seed<5>(sfric, 4, 0), v[3];
+      auto prim_of = [&](int q, PrimIn<D5>& pr) {
+        if (!((act >> q) & 1u)) return false;
+        PrimIn<float> pf;
+        load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pf);
+        promote_prim<5>(pf, -100, pr);
+        return true;
+      };
+      cell_update<D5>(k, ci, cj, ck, p, m, sf, prim_of, v);
+      float r[5];
 #pragma unroll
-    for (int i = 0; i < ND; ++i) {
-      int id = ch * ND + i;
-      if (i < 4 && ch == 0) {  // ids 0..3 live in chunk 0 (ND >= 4)
-        gp[i] = gin[i];
-        continue;
+      for (int i = 0; i < 5; ++i) r[i] = gv.x * v[0].d[i] + gv.y * v[1].d[i] + gv.z * v[2].d[i];
+      ggrid[idx] = make_float4(r[0], r[1], r[2], r[3]);
+      gsf = r[4];
+    }
+    float tot = warp_sum(gsf);
+    if ((threadIdx.x & 31) == 0 && tot != 0.f) atomicAdd(&g_scal[env * GS_STRIDE + GS_FRICTION], tot);
+  }
+  // ---- primitive passes
+  typedef Dual<7> D7;
+  for (int q = 0; q < k.n_prim; ++q) {
+    bool mine = work && ((act >> q) & 1u);
+    if (!__any_sync(0xffffffffu, mine)) continue;
+    size_t t = (size_t)env * k.n_prim + q;
+    float* tp = g_fk_pos + t * (k.S + 1) * 3;
+    float* tr = g_fk_rot + t * (k.S + 1) * 4;
+    for (int ch = 0; ch < 3; ++ch) {
+      float r[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (mine) {
+        D7 p[3] = {seed<7>(g.x, -1, 0), seed<7>(g.y, -1, 0), seed<7>(g.z, -1, 0)};
+        D7 m = seed<7>(g.w, -1, 0), sf = seed<7>(sfric, -1, 0), v[3];
+        auto prim_of = [&](int qq, PrimIn<D7>& pr) {
+          if (!((act >> qq) & 1u)) return false;
+          PrimIn<float> pf;
+          load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, qq, f, pf);
+          promote_prim<7>(pf, qq == q ? ch * 7 : -100, pr);
+          return true;
+        };
+        cell_update<D7>(k, ci, cj, ck, p, m, sf, prim_of, v);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) r[i] = gv.x * v[0].d[i] + gv.y * v[1].d[i] + gv.z * v[2].d[i];
       }
-      if (id >= n_in) continue;
-      float tot = warp_sum(gin[i]);
-      if ((threadIdx.x & 31) != 0 || tot == 0.f) continue;
-      if (id == 4) {
-        atomicAdd(&g_scal[env * GS_STRIDE + GS_FRICTION], tot);
-        continue;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        float tot = warp_sum(r[i]);
+        if ((threadIdx.x & 31) != 0 || tot == 0.f) continue;
+        int j = ch * 7 + i;  // input index inside PrimIn
+        if (j < 3) atomicAdd(&tp[f * 3 + j], tot);
+        else if (j < 7) atomicAdd(&tr[f * 4 + (j - 3)], tot);
+        else if (j < 10) atomicAdd(&tp[(f + 1) * 3 + (j - 7)], tot);
+        else if (j < 14) atomicAdd(&tr[(f + 1) * 4 + (j - 10)], tot);
+        else if (j < 17) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + (j - 14)], tot);
+        else if (j < 18) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + 3], tot);
+        else atomicAdd(&g_fk_v[(t * k.S + f) * 3 + (j - 18)], tot);
       }
-      int q = (id - 5) / PRIM_NIN, j = (id - 5) % PRIM_NIN;
-      size_t t = (size_t)env * k.n_prim + q;
-      float* tp = g_fk_pos + t * (k.S + 1) * 3;
-      float* tr = g_fk_rot + t * (k.S + 1) * 4;
-      if (j < 3) atomicAdd(&tp[f * 3 + j], tot);
-      else if (j < 7) atomicAdd(&tr[f * 4 + (j - 3)], tot);
-      else if (j < 10) atomicAdd(&tp[(f + 1) * 3 + (j - 7)], tot);
-      else if (j < 14) atomicAdd(&tr[(f + 1) * 4 + (j - 10)], tot);
-      else if (j < 17) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + (j - 14)], tot);
-      else if (j < 18) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + 3], tot);
-      else atomicAdd(&g_fk_v[(t * k.S + f) * 3 + (j - 18)], tot);
     }
   }
-  if (work) ggrid[idx] = make_float4(gp[0], gp[1], gp[2], gp[3]);
 }
 
 void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,

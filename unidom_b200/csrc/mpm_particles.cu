@@ -138,6 +138,40 @@ void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Warp-level segmented reduction.  Lanes are consecutive particles of the per-frame sort, so lanes
+// that share a base cell form contiguous runs.  Every scattered value is first summed over its run
+// with 5 predicated shuffles and only the run head issues the global vector RED: ~59 particles per
+// cell collapse to one atomic per (run, node) instead of one per (particle, node).
+// ------------------------------------------------------------------------------------------------
+struct SegInfo {
+  unsigned pred;  // bit i: lane + 2^i is still inside this lane's run
+  bool head;
+};
+__device__ __forceinline__ SegInfo seg_info(int key) {
+  const unsigned lane = threadIdx.x & 31;
+  int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+  SegInfo s;
+  s.head = lane == 0 || kprev != key;
+  unsigned heads = __ballot_sync(0xffffffffu, s.head);
+  unsigned higher = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+  int run_end = higher ? (__ffs(higher) - 1) : 32;
+  s.pred = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+    if ((int)lane + (1 << i) < run_end) s.pred |= 1u << i;
+  return s;
+}
+__device__ __forceinline__ float seg_sum(float v, unsigned pred) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    float t = __shfl_down_sync(0xffffffffu, v, 1 << i);
+    if ((pred >> i) & 1u) v += t;
+  }
+  return v;
+}
+UD_DEV int base_key(const int base[3]) { return (base[0] * 2048 + base[1]) * 2048 + base[2]; }
+
+// ------------------------------------------------------------------------------------------------
 // P2G: F update + SVD + plasticity + stress (mpm_simulator.py:238-268), then the 27-node scatter of
 // {momentum, mass} (p2g_micro, :178-194) as ONE 16-byte vector reduction per node
 // (red.global.add.v4.f32 -> REDG.E.ADD.F32x4).  Out-of-range nodes are dropped (JAX scatter rule).
@@ -159,7 +193,6 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
       const float* __restrict__ h_s) {
   UD_PARTICLE_INDEX(k, env, g);
-  if (!live_) return;
   const size_t N = k.N;
   float x[3], v[3];
   Mat3 C, F;
@@ -168,8 +201,13 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
   make_stencil(x, k.inv_dx, st);
   Consti o;
   constitutive_fwd(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+  if (live_) {
 #pragma unroll
-  for (int c = 0; c < 9; ++c) ps_out[(PS_F + c) * N + g] = o.F2.m[c];
+    for (int c = 0; c < 9; ++c) ps_out[(PS_F + c) * N + g] = o.F2.m[c];
+  }
+  // dead lanes (past the env's last particle) get a unique key and contribute zeros
+  const SegInfo seg = seg_info(live_ ? base_key(st.base) : (int)(0x40000000u | threadIdx.x));
+  const float lw = live_ ? 1.f : 0.f;
   float4* genv = grid + (size_t)env * k.G;
   float mv[3] = {k.p_mass * v[0], k.p_mass * v[1], k.p_mass * v[2]};
 #pragma unroll
@@ -184,15 +222,18 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         int iz = idx_scatter(st.base[2] + c, k.rz);
-        if ((ix | iy | iz) < 0) continue;
         float dx2 = ((float)c - st.fx[2]) * k.dx;
-        float wt = wab * st.w[c][2];
+        float wt = wab * st.w[c][2] * lw;
         float4 val;
         val.x = wt * (mv[0] + (o.affine(0, 0) * dx0 + o.affine(0, 1) * dx1 + o.affine(0, 2) * dx2));
         val.y = wt * (mv[1] + (o.affine(1, 0) * dx0 + o.affine(1, 1) * dx1 + o.affine(1, 2) * dx2));
         val.z = wt * (mv[2] + (o.affine(2, 0) * dx0 + o.affine(2, 1) * dx1 + o.affine(2, 2) * dx2));
         val.w = wt * k.p_mass;
-        atomicAdd(&genv[(ix * k.ry + iy) * k.rz + iz], val);
+        val.x = seg_sum(val.x, seg.pred);
+        val.y = seg_sum(val.y, seg.pred);
+        val.z = seg_sum(val.z, seg.pred);
+        val.w = seg_sum(val.w, seg.pred);
+        if (seg.head && live_ && (ix | iy | iz) >= 0) atomicAdd(&genv[(ix * k.ry + iy) * k.rz + iz], val);
       }
     }
   }
@@ -347,7 +388,6 @@ __global__ void __launch_bounds__(UD_BLOCK)
 k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict__ grid_out,
           float* __restrict__ gs, float4* __restrict__ ggrid) {
   UD_PARTICLE_INDEX(k, env, g);
-  if (!live_) return;
   const size_t N = k.N;
   float x[3], gxo[3], gvt[3];
   Mat3 gC;
@@ -361,6 +401,8 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   for (int c = 0; c < 9; ++c) gC.m[c] = gs[(PS_C + c) * N + g];
   Stencil st;
   make_stencil(x, k.inv_dx, st);
+  const SegInfo seg = seg_info(live_ ? base_key(st.base) : (int)(0x40000000u | threadIdx.x));
+  const float lw = live_ ? 1.f : 0.f;
   const float4* genv = grid_out + (size_t)env * k.G;
   float4* ggenv = ggrid + (size_t)env * k.G;
   float gw[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
@@ -385,7 +427,9 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
         float r0 = gvt[0] + c4 * (gC(0, 0) * d0 + gC(0, 1) * d1 + gC(0, 2) * d2);
         float r1 = gvt[1] + c4 * (gC(1, 0) * d0 + gC(1, 1) * d1 + gC(1, 2) * d2);
         float r2 = gvt[2] + c4 * (gC(2, 0) * d0 + gC(2, 1) * d1 + gC(2, 2) * d2);
-        atomicAdd(&ggenv[cell], make_float4(wt * r0, wt * r1, wt * r2, 0.f));
+        float s0 = seg_sum(lw * wt * r0, seg.pred), s1 = seg_sum(lw * wt * r1, seg.pred),
+              s2 = seg_sum(lw * wt * r2, seg.pred);
+        if (seg.head && live_) atomicAdd(&ggenv[cell], make_float4(s0, s1, s2, 0.f));
         float gwt = gv.x * r0 + gv.y * r1 + gv.z * r2;
         // gd_j = 4 inv_dx wt sum_i g_i gC'_ij ; fx enters d with a minus sign
         float cw = c4 * wt;
@@ -398,6 +442,7 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
       }
     }
   }
+  if (!live_) return;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     gfx[d] += gw[0][d] * st.dw[0][d] + gw[1][d] * st.dw[1][d] + gw[2][d] * st.dw[2][d];
