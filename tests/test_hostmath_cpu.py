@@ -1,0 +1,138 @@
+"""CPU checks of the __host__ __device__ math headers (host build, tests/hostmath) against the oracle:
+3x3 SVD, constitutive model forward + hand-derived reverse, collider reverse vs forward-mode duals."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpm as omp
+from oracle import primitives as oP
+from oracle.svd import svd as osvd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hm():
+    src = os.path.join(HERE, "hostmath", "hostmath.cu")
+    lib = os.path.join(HERE, "hostmath", "libhostmath.so")
+    deps = [src] + [os.path.join(HERE, "..", "unidom_b200", "csrc", f) for f in ("common.cuh", "mpm_particle.cuh", "mpm_cell.cuh")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.check_call(["nvcc", "-x", "cu", "-std=c++17", "-O2", "--fmad=false", "--expt-relaxed-constexpr",
+                               "-Wno-deprecated-gpu-targets", "-shared", "-Xcompiler", "-fPIC", "-o", lib, src])
+    return C.CDLL(lib)
+
+
+def fp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_svd3_matches_lapack_invariants(hm):
+    rng = np.random.RandomState(0)
+    n = 4000
+    A = (np.eye(3)[None] + 0.3 * rng.randn(n, 3, 3)).astype(np.float32)
+    A[:50] = np.eye(3, dtype=np.float32)                       # degenerate: all singular values equal
+    A[50:100] *= np.float32(1e-3)
+    A[100:150, :, 2] = A[100:150, :, 1]                        # rank deficient
+    U = np.empty_like(A); Vt = np.empty_like(A); s = np.empty((n, 3), np.float32)
+    hm.hm_svd3(n, fp(A), fp(U), fp(s), fp(Vt))
+    s_ref = np.linalg.svd(A.astype(np.float64), compute_uv=False)
+    assert np.all(s[:, 0] >= s[:, 1]) and np.all(s[:, 1] >= s[:, 2]) and np.all(s >= 0)
+    assert np.abs(s - s_ref).max() < 2e-6 * max(1.0, s_ref.max())
+    rec = np.einsum("nij,nj,njk->nik", U.astype(np.float64), s.astype(np.float64), Vt.astype(np.float64))
+    assert np.abs(rec - A).max() < 5e-6
+    eye = np.eye(3)[None]
+    assert np.abs(np.einsum("nji,njk->nik", U, U) - eye).max() < 5e-6
+    assert np.abs(np.einsum("nij,nkj->nik", Vt, Vt) - eye).max() < 5e-6
+    # the polar rotation U Vt (what the stress uses) agrees with LAPACK's where it is well defined
+    Ur, sr, Vr = np.linalg.svd(A[150:].astype(np.float64))
+    R_ref = Ur @ Vr
+    R = U[150:].astype(np.float64) @ Vt[150:].astype(np.float64)
+    ok = sr[:, 2] > 0.05
+    assert np.abs(R - R_ref)[ok].max() < 2e-5
+
+
+@pytest.mark.parametrize("material", [0, 1, 2])
+def test_constitutive_forward_and_reverse_vs_oracle(hm, material):
+    rng = np.random.RandomState(1 + material)
+    n = 2000
+    conf = omp.MPMConf(n_grid=96, res=(48, 32, 48), dt=2e-4, steps=1, E=2.0, nu=0.2)
+    consts = np.array([conf.dt, conf.dx, conf.inv_dx, conf.p_mass, conf.p_vol], np.float64)
+    Cm = (rng.randn(n, 3, 3) * 3).astype(np.float32)
+    F = (np.eye(3)[None] + 0.25 * rng.randn(n, 3, 3)).astype(np.float32)   # spread sigmas across the clip range
+    h = rng.uniform(0.05, 6.0, n).astype(np.float32)
+    mat = np.full(n, material, np.int32)
+    gA = rng.randn(n, 3, 3).astype(np.float32)
+    gF2 = rng.randn(n, 3, 3).astype(np.float32) * 1e-3
+    mu_s, la_s = np.float32(0.83), np.float32(0.55)
+    outs = {k: np.empty((n, 3, 3), np.float32) for k in ("F2", "affine", "gC", "gF")}
+    gmu = np.empty(n, np.float32); gla = np.empty(n, np.float32)
+    hm.hm_constitutive(n, fp(consts), fp(Cm), fp(F), C.c_float(mu_s), C.c_float(la_s), fp(h), fp(mat), fp(gA), fp(gF2),
+                       fp(outs["F2"]), fp(outs["affine"]), fp(outs["gC"]), fp(outs["gF"]), fp(gmu), fp(gla))
+    # oracle in float64 (the reverse formula of the SVD is ill-conditioned in fp32 by construction)
+    dt64 = torch.float64
+    sim = omp.Simulator(conf, torch.from_numpy(mat), torch.from_numpy(h), dtype=dt64)
+    tC = torch.from_numpy(Cm).to(dt64).requires_grad_(True)
+    tF = torch.from_numpy(F).to(dt64).requires_grad_(True)
+    tmu = torch.tensor([float(mu_s)], dtype=dt64, requires_grad=True)
+    tla = torch.tensor([float(la_s)], dtype=dt64, requires_grad=True)
+    st = omp.MPMState(x=torch.zeros(n, 3, dtype=dt64), C=tC, F=tF, mu=tmu, lamda=tla)
+    F2, aff = sim.constitutive(st)
+    L = (aff * torch.from_numpy(gA).to(dt64)).sum() + (F2 * torch.from_numpy(gF2).to(dt64)).sum()
+    rC, rF, rmu, rla = torch.autograd.grad(L, [tC, tF, tmu, tla])
+
+    def rel(a, b):
+        b = b.detach().numpy()
+        return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+    assert rel(outs["F2"], F2) < 5e-6
+    assert rel(outs["affine"], aff) < 2e-5
+    assert rel(outs["gC"], rC) < 1e-4
+    assert rel(outs["gF"], rF) < 2e-3          # per-particle SVD-VJP conditioning (SURVEY hard part 3)
+    cosF = float((torch.from_numpy(outs["gF"]).double().flatten() @ rF.flatten()) /
+                 (np.linalg.norm(outs["gF"].astype(np.float64)) * rF.norm()))
+    assert cosF > 0.99999
+    assert abs(gmu.astype(np.float64).sum() - float(rmu)) < 1e-4 * (abs(float(rmu)) + 1e-6)
+    assert abs(gla.astype(np.float64).sum() - float(rla)) < 1e-4 * (abs(float(rla)) + 1e-6)
+
+
+@pytest.mark.parametrize("kind,pos_control", [(0, 0), (1, 0), (0, 1)])
+def test_collider_hand_reverse_matches_dual_jacobian(hm, kind, pos_control):
+    rng = np.random.RandomState(7 + kind)
+    dt = np.float32(2e-4)
+    worst = 0.0
+    n_flag = 0
+    for trial in range(400):
+        size = np.array([0.015, 0.06, 0.015], np.float32) if kind == 0 else np.array([0.09, 0.02, 0.008], np.float32)
+        pos = np.array([0.25, 0.03, 0.25], np.float32) + rng.randn(3).astype(np.float32) * 0.01
+        q = rng.randn(4).astype(np.float32) * 0.2 + np.array([1, 0, 0, 0], np.float32)
+        q /= np.linalg.norm(q)
+        q1 = q + rng.randn(4).astype(np.float32) * 0.01
+        q1 /= np.linalg.norm(q1)
+        pos1 = pos + rng.randn(3).astype(np.float32) * 1e-3
+        fric = np.float32(rng.uniform(0.1, 1.0))
+        vf = rng.randn(3).astype(np.float32) * 1e-3
+        prim = np.concatenate([pos, q, pos1, q1, size, [fric], vf]).astype(np.float32)
+        # cells in a shell around the primitive so that influence is O(1)
+        off = rng.randn(3).astype(np.float32)
+        off /= np.linalg.norm(off)
+        reach = (size.max() if kind == 0 else 0.09) + rng.uniform(-0.004, 0.006)
+        gpos = (pos + off * reach).astype(np.float32)
+        vin = rng.randn(3).astype(np.float32)
+        gout = rng.randn(3).astype(np.float32)
+        a = [np.empty(3, np.float32), np.empty(21, np.float32)]
+        b = [np.empty(3, np.float32), np.empty(21, np.float32)]
+        args = (pos_control, kind, C.c_float(dt), fp(gpos), fp(prim), C.c_float(666.0), fp(vin), fp(gout))
+        hm.hm_prim_vjp_dual(*args, fp(a[0]), fp(a[1]))
+        hm.hm_prim_vjp_hand(*args, fp(b[0]), fp(b[1]))
+        ref = np.concatenate(a); got = np.concatenate(b)
+        scale = np.abs(ref).max()
+        if scale > 1e-3:
+            n_flag += 1
+        worst = max(worst, np.abs(ref - got).max() / (scale + 1e-6))
+    assert n_flag > 50, "test cells never touch the collider"
+    # the fp32 dual reference itself carries ~1e-7/dt = 5e-4 of cancellation noise on d/d(cv)
+    # (1 - (1-infl) - infl != 0 in fp32); the hand reverse is exact there, hence the tolerance
+    assert worst < 1.5e-3, worst

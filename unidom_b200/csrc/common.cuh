@@ -61,18 +61,44 @@ UD_DEV Mat3 mat_zero() {
 // U diag(clip s) V^T are consumed downstream (mpm_simulator.py:253-265).
 // Vt returned is V^T (the reference's "V"/"Vh").
 // ---------------------------------------------------------------------------------------------
-UD_DEV void jacobi_pair(float* bp, float* bq, float* vp, float* vq) {
+// fast (approximate, <= 2 ulp) division / sqrt / rsqrt for the Jacobi rotations: the iteration is
+// self-correcting, only the final singular values and the U columns use IEEE sqrt / division.
+UD_DEV float fast_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+UD_DEV float fast_sqrt(float a) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+#else
+  return sqrtf(a);
+#endif
+}
+UD_DEV float fast_rsqrt(float a) {
+#ifdef __CUDA_ARCH__
+  return rsqrtf(a);
+#else
+  return 1.f / sqrtf(a);
+#endif
+}
+
+// One Hestenes rotation of the column pair (p,q); returns the pair's normalised off-diagonal
+// |b_p . b_q| / (|b_p| |b_q|) BEFORE the rotation (the orthogonality defect of U it removes).
+//   t = 2g / (tau + sign(tau) sqrt(tau^2 + 4 g^2)),  tau = |b_q|^2 - |b_p|^2,  g = b_p . b_q
+UD_DEV float jacobi_pair(float* bp, float* bq, float* vp, float* vq) {
   float alpha = bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2];
   float beta = bq[0] * bq[0] + bq[1] * bq[1] + bq[2] * bq[2];
-  float gamma = bp[0] * bq[0] + bp[1] * bq[1] + bp[2] * bq[2];
-  // rotation that zeroes gamma; identity when the pair is already orthogonal to rounding
-  bool act = fabsf(gamma) > 1e-9f * sqrtf(alpha * beta) && fabsf(gamma) > 1e-37f;
-  float zeta = (beta - alpha) / (2.f * (act ? gamma : 1.f));
-  float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-  float c = 1.f / sqrtf(1.f + t * t);
+  float g2 = 2.f * (bp[0] * bq[0] + bp[1] * bq[1] + bp[2] * bq[2]);
+  float tau = beta - alpha;
+  float den = tau + copysignf(fast_sqrt(tau * tau + g2 * g2), tau);
+  float t = den != 0.f ? fast_div(g2, den) : 0.f;
+  float c = fast_rsqrt(1.f + t * t);
   float s = c * t;
-  c = act ? c : 1.f;
-  s = act ? s : 0.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     float x = bp[i], y = bq[i];
@@ -83,6 +109,7 @@ UD_DEV void jacobi_pair(float* bp, float* bq, float* vp, float* vq) {
     vp[i] = c * x - s * y;
     vq[i] = s * x + c * y;
   }
+  return fabsf(g2) * fast_rsqrt(4.f * alpha * beta + 1e-37f);
 }
 
 UD_DEV void swap3(float* a, float* b) {
@@ -99,11 +126,14 @@ UD_DEV void svd3(const Mat3& A, Mat3& U, float s[3], Mat3& Vt) {
   float b0[3] = {A(0, 0), A(1, 0), A(2, 0)}, b1[3] = {A(0, 1), A(1, 1), A(2, 1)},
         b2[3] = {A(0, 2), A(1, 2), A(2, 2)};
   float v0[3] = {1.f, 0.f, 0.f}, v1[3] = {0.f, 1.f, 0.f}, v2[3] = {0.f, 0.f, 1.f};
+  // cyclic sweeps; quadratic convergence: once every normalised off-diagonal met in a sweep is
+  // < 2e-4 the defect left after that sweep is O(1e-8), below fp32 resolution
 #pragma unroll 1
-  for (int sweep = 0; sweep < 5; ++sweep) {
-    jacobi_pair(b0, b1, v0, v1);
-    jacobi_pair(b0, b2, v0, v2);
-    jacobi_pair(b1, b2, v1, v2);
+  for (int sweep = 0; sweep < 6; ++sweep) {
+    float t0 = jacobi_pair(b0, b1, v0, v1);
+    float t1 = jacobi_pair(b0, b2, v0, v2);
+    float t2 = jacobi_pair(b1, b2, v1, v2);
+    if (fmaxf(t0, fmaxf(t1, t2)) < 2e-4f) break;
   }
   float n0 = b0[0] * b0[0] + b0[1] * b0[1] + b0[2] * b0[2];
   float n1 = b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2];

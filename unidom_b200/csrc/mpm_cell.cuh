@@ -250,6 +250,29 @@ UD_DEV void position_control_cell(int kind, float dt, const float gpos[3], const
   for (int i = 0; i < 3; ++i) v[i] = s_sel(mask, pr.v_f[i] / dt, v[i]);
 }
 
+// ground friction (mpm_simulator.py:297-307) and boundary (:310-313) for one cell, in place
+template <class T>
+UD_DEV void cell_ground_boundary(const MpmConst& k, int ci, int cj, int ck, const T& sfric, T v[3]) {
+  const float ie[3] = {(float)ci * 1e-30f, (float)cj * 1e-30f, (float)ck * 1e-30f};
+  if (cj < 3 && s_val(v[1]) <= 0.f) {
+    T lin = v[1] + 1e-30f;
+    T vit[3] = {v[0] - ie[0], (v[1] - lin) - ie[1], v[2] - ie[2]};
+    T a[3] = {vit[0] + 1e-12f, vit[1] + 1e-12f, vit[2] + 1e-12f};
+    T lit = s_sqrt(dot3(a, a));
+    T sc = s_max_c(1.f + sfric * lin / lit, 0.f);
+    v[0] = sc * (vit[0] + ie[0]);
+    v[1] = s_const(v[1], 0.f);
+    v[2] = sc * (vit[2] + ie[2]);
+  }
+  // upper wall tests n_grid, not res
+  const int cidx[3] = {ci, cj, ck};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    bool cond = (cidx[d] < 3 && s_val(v[d]) < 0.f) || (cidx[d] > k.n_grid - 3 && s_val(v[d]) > 0.f);
+    if (cond) v[d] = s_const(v[d], 0.f);
+  }
+}
+
 // mpm_simulator.py:283-313 for one cell with m > 0.  p = scattered momentum, m = scattered mass.
 // `prim_of(q, pr)` fills primitive q and returns false when the primitive is to be skipped (the
 // adjoint skips primitives whose influence on this cell is below 1e-12; the forward never skips).
@@ -267,25 +290,7 @@ UD_DEV void cell_update(const MpmConst& k, int ci, int cj, int ck, const T p[3],
     else
       collide_cell(k.sdf_kind, k.dt, gpos, pr, v);
   }
-  // ground friction (:297-307)
-  const float ie[3] = {(float)ci * 1e-30f, (float)cj * 1e-30f, (float)ck * 1e-30f};
-  if (cj < 3 && s_val(v[1]) <= 0.f) {
-    T lin = v[1] + 1e-30f;
-    T vit[3] = {v[0] - ie[0], (v[1] - lin) - ie[1], v[2] - ie[2]};
-    T a[3] = {vit[0] + 1e-12f, vit[1] + 1e-12f, vit[2] + 1e-12f};
-    T lit = s_sqrt(dot3(a, a));
-    T sc = s_max_c(1.f + sfric * lin / lit, 0.f);
-    v[0] = sc * (vit[0] + ie[0]);
-    v[1] = s_const(v[1], 0.f);
-    v[2] = sc * (vit[2] + ie[2]);
-  }
-  // boundary (:310-313); upper wall tests n_grid, not res
-  const int cidx[3] = {ci, cj, ck};
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    bool cond = (cidx[d] < 3 && s_val(v[d]) < 0.f) || (cidx[d] > k.n_grid - 3 && s_val(v[d]) > 0.f);
-    if (cond) v[d] = s_const(v[d], 0.f);
-  }
+  cell_ground_boundary(k, ci, cj, ck, sfric, v);
 }
 
 // Does primitive `pr` act on the cell at gpos?  collide: influence = min(exp(-dist*softness),1) >= 1e-12
@@ -299,6 +304,246 @@ UD_DEV bool prim_active(const MpmConst& k, const float gpos[3], const PrimIn<flo
   float dist = sdf_local(k.sdf_kind, pr.size, gp);
   if (k.pos_control) return dist < pr.size[0] * 1.5f;
   return fminf(expf(-dist * pr.softness), 1.f) >= 1e-12f;
+}
+
+// ================================================================================================
+// Hand-written reverse mode of collide_cell / position_control_cell (float only).  Used by the grid
+// adjoint for cells a primitive acts on; checked against the Dual<N> Jacobian of the templates above
+// (tests/test_hostmath_cpu.py) and against torch autograd of the oracle (tests/test_mpm_gpu.py).
+// Conventions: every *_bwd ACCUMULATES into its output cotangents.
+// PrimGrad layout = the PRIM_NIN order: pos_f(3) rot_f(4) pos_f1(3) rot_f1(4) size(3) friction v_f(3).
+// ================================================================================================
+struct PrimGrad {
+  float g[PRIM_NIN];
+};
+
+UD_DEV void cross3f(const float a[3], const float b[3], float r[3]) {
+  r[0] = a[1] * b[2] - a[2] * b[1];
+  r[1] = a[2] * b[0] - a[0] * b[2];
+  r[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// out = v + 2 (r0 (q x v) + q x (q x v))
+UD_DEV void qrot_bwd(const float rot[4], const float v[3], const float gout[3], float grot[4], float gv[3]) {
+  const float q[3] = {rot[1], rot[2], rot[3]};
+  float uv[3];
+  cross3f(q, v, uv);
+  float guv[3], guuv[3], t[3];
+  for (int i = 0; i < 3; ++i) {
+    gv[i] += gout[i];
+    guv[i] = 2.f * rot[0] * gout[i];
+    guuv[i] = 2.f * gout[i];
+  }
+  grot[0] += 2.f * (gout[0] * uv[0] + gout[1] * uv[1] + gout[2] * uv[2]);
+  // uuv = q x uv : gq += uv x guuv ; guv += guuv x q
+  cross3f(uv, guuv, t);
+  for (int i = 0; i < 3; ++i) grot[1 + i] += t[i];
+  cross3f(guuv, q, t);
+  for (int i = 0; i < 3; ++i) guv[i] += t[i];
+  // uv = q x v : gq += v x guv ; gv += guv x q
+  cross3f(v, guv, t);
+  for (int i = 0; i < 3; ++i) grot[1 + i] += t[i];
+  cross3f(guv, q, t);
+  for (int i = 0; i < 3; ++i) gv[i] += t[i];
+}
+
+// iq = conj(rot) / (|rot| + 1e-12)
+UD_DEV void inv_quat_bwd(const float rot[4], const float giq[4], float grot[4]) {
+  float nr = sqrtf(rot[0] * rot[0] + rot[1] * rot[1] + rot[2] * rot[2] + rot[3] * rot[3]);
+  float n = nr + 1e-12f;
+  const float sg[4] = {1.f, -1.f, -1.f, -1.f};
+  float gn = 0.f;
+  for (int i = 0; i < 4; ++i) {
+    grot[i] += sg[i] * giq[i] / n;
+    gn -= giq[i] * (sg[i] * rot[i]) / (n * n);
+  }
+  for (int i = 0; i < 4; ++i) grot[i] += gn * rot[i] / nr;
+}
+
+UD_DEV float sgnf(float a) { return a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f); }
+
+UD_DEV void sdf_box_bwd(const float size[3], const float p[3], float g, float gsize[3], float gp[3]) {
+  float q[3], raw[3];
+  for (int i = 0; i < 3; ++i) {
+    raw[i] = fabsf(p[i]) - size[i];
+    q[i] = raw[i] >= 0.f ? raw[i] : 0.f;
+  }
+  float len = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + 1e-12f);
+  float gq[3] = {g * q[0] / len, g * q[1] / len, g * q[2] / len};
+  // "+ min(max(q), 0)": passes a gradient only when the selected q is exactly 0
+  int sel = q[1] > q[2] ? 1 : 2;
+  if (q[0] > q[sel]) sel = 0;
+  if (q[sel] <= 0.f) gq[sel] += g;
+  for (int i = 0; i < 3; ++i)
+    if (raw[i] >= 0.f) {
+      gp[i] += gq[i] * sgnf(p[i]);
+      gsize[i] -= gq[i];
+    }
+}
+
+UD_DEV void sdf_container_bwd(const float size[3], const float p[3], float g, float gsize[3], float gp[3]) {
+  const float r = size[0], h = size[1];
+  float w = sqrtf(r * r - h * h);
+  float q0 = sqrtf(p[0] * p[0] + p[2] * p[2] + 1e-12f), q1 = p[1];
+  float gq0 = 0.f, gq1 = 0.f, gw = 0.f, gr = 0.f, gh = 0.f, gt = -g;
+  if (h * q0 < w * q1) {
+    float a = q0 - w, b = q1 - h;
+    float L = sqrtf(a * a + b * b + 1e-12f);
+    gq0 = g * a / L;
+    gw = -gq0;
+    gq1 = g * b / L;
+    gh = -gq1;
+  } else {
+    float L = sqrtf(q0 * q0 + q1 * q1 + 1e-12f);
+    float sg = sgnf(L - r);
+    gr = -g * sg;
+    gq0 = g * sg * q0 / L;
+    gq1 = g * sg * q1 / L;
+  }
+  gr += gw * r / w;
+  gh -= gw * h / w;
+  gsize[0] += gr;
+  gsize[1] += gh;
+  gsize[2] += gt;
+  gp[0] += gq0 * p[0] / q0;
+  gp[2] += gq0 * p[2] / q0;
+  gp[1] += gq1;
+}
+
+UD_DEV void sdf_local_bwd(int kind, const float size[3], const float p[3], float g, float gsize[3], float gp[3]) {
+  if (g == 0.f) return;
+  if (kind == 0) sdf_box_bwd(size, p, g, gsize, gp);
+  else sdf_container_bwd(size, p, g, gsize, gp);
+}
+
+// Reverse of collide_cell: given v_in (the velocity BEFORE this primitive) and gout = cotangent of the
+// velocity after it, returns gv_in (overwritten) and accumulates the primitive's cotangents.
+UD_DEV void collide_cell_bwd(int kind, float dt, const float gpos[3], const PrimIn<float>& pr, const float vin[3],
+                             const float gout[3], float gvin[3], PrimGrad& pg) {
+  // ---- recompute the forward
+  float iq[4], rel[3], gp[3];
+  inv_quat(pr.rot_f, iq);
+  for (int i = 0; i < 3; ++i) rel[i] = gpos[i] - pr.pos_f[i];
+  qrot(iq, rel, gp);
+  float dist = sdf_local(kind, pr.size, gp);
+  float ex = expf((-dist) * pr.softness);
+  float infl = ex <= 1.f ? ex : 1.f;
+  const float d = 1.e-6f, cfd = 0.5f / d;
+  float nl[3];
+  for (int a = 0; a < 3; ++a) {
+    float inc[3] = {gp[0], gp[1], gp[2]}, dec[3] = {gp[0], gp[1], gp[2]};
+    inc[a] = inc[a] + d;
+    dec[a] = dec[a] + (-d);
+    nl[a] = cfd * (sdf_local(kind, pr.size, inc) - sdf_local(kind, pr.size, dec));
+  }
+  float nlen = sqrtf(nl[0] * nl[0] + nl[1] * nl[1] + nl[2] * nl[2] + 1e-12f);
+  float nn[3] = {nl[0] / nlen, nl[1] / nlen, nl[2] / nlen};
+  float D[3], np[3], cv[3], iv[3];
+  qrot(pr.rot_f, nn, D);
+  qrot(pr.rot_f1, gp, np);
+  for (int i = 0; i < 3; ++i) {
+    cv[i] = ((np[i] + pr.pos_f1[i]) - gpos[i]) / dt;
+    iv[i] = vin[i] - cv[i];
+  }
+  float nc = iv[0] * D[0] + iv[1] * D[1] + iv[2] * D[2];
+  float ncm = nc <= 0.f ? nc : 0.f;
+  float vt[3] = {iv[0] - ncm * D[0], iv[1] - ncm * D[1], iv[2] - ncm * D[2]};
+  float vt2 = vt[0] * vt[0] + vt[1] * vt[1] + vt[2] * vt[2];
+  float vtn = sqrtf(vt2 + 1e-12f);
+  float fr_raw = vtn + nc * pr.friction;
+  float fr = fr_raw >= 1e-12f ? fr_raw : 1e-12f;
+  bool flag = nc < 0.f && sqrtf(vt2) > 1e-12f;
+  // ---- reverse:  out = cv + iv (1 - infl) + vsel infl
+  // giv = gout (1 - infl) + ex,  gcv = gout - giv = gout infl - ex   (ex collects the vsel path; written
+  // this way the small-influence case does not cancel 1 - (1 - infl) in fp32)
+  float gcv[3], ex_[3], gvt[3], gD[3] = {0.f, 0.f, 0.f};
+  float ginfl = 0.f, gnc = 0.f, gfric = 0.f;
+  for (int i = 0; i < 3; ++i) {
+    float vsel = flag ? vt[i] / vtn * fr : vt[i];
+    ginfl += gout[i] * (vsel - iv[i]);
+  }
+  if (flag) {
+    // vsel_i = vt_i * s, s = fr / vtn
+    float sc = fr / vtn, gs = 0.f;
+    for (int i = 0; i < 3; ++i) {
+      float gvs = gout[i] * infl;
+      gvt[i] = gvs * sc;
+      gs += gvs * vt[i];
+    }
+    float gfr = gs / vtn;
+    float gvtn = -gs * fr / (vtn * vtn);
+    if (fr_raw >= 1e-12f) {
+      gvtn += gfr;
+      gnc += gfr * pr.friction;
+      gfric += gfr * nc;
+    }
+    for (int i = 0; i < 3; ++i) gvt[i] += gvtn * vt[i] / vtn;
+  } else {
+    for (int i = 0; i < 3; ++i) gvt[i] = gout[i] * infl;
+  }
+  // vt = iv - ncm D ; ncm = min(nc, 0) ; nc = iv . D
+  float gncm = 0.f;
+  for (int i = 0; i < 3; ++i) {
+    ex_[i] = gvt[i];
+    gncm -= gvt[i] * D[i];
+    gD[i] -= ncm * gvt[i];
+  }
+  if (nc <= 0.f) gnc += gncm;
+  for (int i = 0; i < 3; ++i) {
+    ex_[i] += gnc * D[i];
+    gD[i] += gnc * iv[i];
+  }
+  // iv = v - cv
+  for (int i = 0; i < 3; ++i) {
+    gvin[i] = gout[i] * (1.f - infl) + ex_[i];
+    gcv[i] = gout[i] * infl - ex_[i];
+  }
+  // cv = (np + pos_f1 - gpos) / dt ; np = qrot(rot_f1, gp)
+  float gnp[3], ggp[3] = {0.f, 0.f, 0.f};
+  for (int i = 0; i < 3; ++i) {
+    gnp[i] = gcv[i] / dt;
+    pg.g[7 + i] += gnp[i];
+  }
+  qrot_bwd(pr.rot_f1, gp, gnp, &pg.g[10], ggp);
+  // D = qrot(rot_f, nn) ; nn = nl / nlen
+  float gnn[3] = {0.f, 0.f, 0.f};
+  qrot_bwd(pr.rot_f, nn, gD, &pg.g[3], gnn);
+  float dotn = gnn[0] * nl[0] + gnn[1] * nl[1] + gnn[2] * nl[2];
+  float gsize[3] = {0.f, 0.f, 0.f};
+  for (int a = 0; a < 3; ++a) {
+    float gnl = gnn[a] / nlen - dotn * nl[a] / (nlen * nlen * nlen);
+    if (gnl != 0.f) {
+      float inc[3] = {gp[0], gp[1], gp[2]}, dec[3] = {gp[0], gp[1], gp[2]};
+      inc[a] = inc[a] + d;
+      dec[a] = dec[a] + (-d);
+      sdf_local_bwd(kind, pr.size, inc, cfd * gnl, gsize, ggp);
+      sdf_local_bwd(kind, pr.size, dec, -cfd * gnl, gsize, ggp);
+    }
+  }
+  // infl = min(exp(-dist softness), 1) ; dist = sdf(size, gp)
+  if (ex <= 1.f) sdf_local_bwd(kind, pr.size, gp, -pr.softness * infl * ginfl, gsize, ggp);
+  for (int i = 0; i < 3; ++i) pg.g[14 + i] += gsize[i];
+  pg.g[17] += gfric;
+  // gp = qrot(iq, rel) ; rel = gpos - pos_f ; iq = inv_quat(rot_f)
+  float giq[4] = {0.f, 0.f, 0.f, 0.f}, grel[3] = {0.f, 0.f, 0.f};
+  qrot_bwd(iq, rel, ggp, giq, grel);
+  for (int i = 0; i < 3; ++i) pg.g[i] -= grel[i];
+  inv_quat_bwd(pr.rot_f, giq, &pg.g[3]);
+}
+
+// Reverse of position_control_cell (the mask carries no gradient).
+UD_DEV void position_control_cell_bwd(int kind, float dt, const float gpos[3], const PrimIn<float>& pr,
+                                      const float gout[3], float gvin[3], PrimGrad& pg) {
+  float iq[4], rel[3], gp[3];
+  inv_quat(pr.rot_f, iq);
+  for (int i = 0; i < 3; ++i) rel[i] = gpos[i] - pr.pos_f[i];
+  qrot(iq, rel, gp);
+  float dist = sdf_local(kind, pr.size, gp);
+  bool mask = dist < pr.size[0] * 1.5f;
+  for (int i = 0; i < 3; ++i) {
+    gvin[i] = mask ? 0.f : gout[i];
+    if (mask) pg.g[18 + i] += gout[i] / dt;
+  }
 }
 
 }  // namespace ud

@@ -174,38 +174,19 @@ void launch_grid_fwd(const MpmConst& k, const float4* grid_in, float4* grid_out,
 }
 
 // ================================================================================================
-// Adjoint of the grid update.  One thread per cell with mass and a non-zero incoming cotangent.
-// Forward-mode tangents of cell_update, contracted with the cotangent of the updated velocity:
-//   pass A  (Dual<5>): inputs p(3), m, state.friction          -> per-cell (g_momentum, g_mass)
-//   pass Pq (Dual<7> x 3): the PRIM_NIN = 21 inputs of primitive q, only where q acts on the cell
-// Primitive / friction cotangents are warp-reduced and accumulated per env.
+// Adjoint of the grid update.  One thread per cell with mass and a non-zero incoming cotangent:
+// recompute the forward chain in float keeping the velocity that enters each primitive, then reverse:
+//   boundary + ground friction : forward-mode Dual<4> over (v, state.friction)  (tiny function)
+//   primitives, last to first  : hand-written reverse (collide_cell_bwd / position_control_cell_bwd),
+//                                only for primitives whose influence on the cell is >= 1e-12
+//   normalise                  : g_p = g_v / m ,  g_m = -g_v . p / m^2
+// Per-cell (g_momentum, g_mass) overwrite ggrid; primitive / friction cotangents are warp-reduced and
+// accumulated per env.
 // ================================================================================================
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
   return v;
-}
-
-template <int N>
-UD_DEV Dual<N> seed(float v, int idx, int first) {
-  Dual<N> r;
-  r.v = v;
-#pragma unroll
-  for (int i = 0; i < N; ++i) r.d[i] = (idx == first + i) ? 1.f : 0.f;
-  return r;
-}
-
-// promote a float primitive to duals; inputs [first, first+N) of ITS OWN 21 scalars get unit tangents
-template <int N>
-UD_DEV void promote_prim(const PrimIn<float>& a, int first, PrimIn<Dual<N>>& o) {
-  for (int j = 0; j < 3; ++j) o.pos_f[j] = seed<N>(a.pos_f[j], j, first);
-  for (int j = 0; j < 4; ++j) o.rot_f[j] = seed<N>(a.rot_f[j], 3 + j, first);
-  for (int j = 0; j < 3; ++j) o.pos_f1[j] = seed<N>(a.pos_f1[j], 7 + j, first);
-  for (int j = 0; j < 4; ++j) o.rot_f1[j] = seed<N>(a.rot_f1[j], 10 + j, first);
-  for (int j = 0; j < 3; ++j) o.size[j] = seed<N>(a.size[j], 14 + j, first);
-  o.friction = seed<N>(a.friction, 17, first);
-  for (int j = 0; j < 3; ++j) o.v_f[j] = seed<N>(a.v_f[j], 18 + j, first);
-  o.softness = a.softness;
 }
 
 __global__ void __launch_bounds__(128)
@@ -218,82 +199,98 @@ k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__
   bool live = c < k.G;
   size_t idx = (size_t)env * k.G + (live ? c : 0);
   float4 g = grid_raw[idx];
-  float4 gv = ggrid[idx];
-  bool work = live && g.w > 0.f && (gv.x != 0.f || gv.y != 0.f || gv.z != 0.f);
+  float4 gv4 = ggrid[idx];
+  bool work = live && g.w > 0.f && (gv4.x != 0.f || gv4.y != 0.f || gv4.z != 0.f);
   if (live && !work) ggrid[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!__any_sync(0xffffffffu, work)) return;  // warp-uniform exit (no block barriers below)
   int ck = c % k.rz, cj = (c / k.rz) % k.ry, ci = c / (k.rz * k.ry);
   const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
   const float sfric = in.friction[env];
-  unsigned act = 0;  // bit q: primitive q acts on this cell
-  if (work)
-    for (int q = 0; q < k.n_prim; ++q) {
+  // ---- forward recompute, remembering the velocity entering each primitive
+  float v[3] = {0.f, 0.f, 0.f}, vin[UD_MAX_PRIM][3];
+  unsigned act = 0;
+  if (work) {
+    v[0] = g.x / g.w + k.gdt[0];
+    v[1] = g.y / g.w + k.gdt[1];
+    v[2] = g.z / g.w + k.gdt[2];
+#pragma unroll
+    for (int q = 0; q < UD_MAX_PRIM; ++q) {
+      if (q >= k.n_prim) break;
       PrimIn<float> pf;
       load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pf);
-      if (prim_active(k, gpos, pf)) act |= 1u << q;
+      vin[q][0] = v[0];
+      vin[q][1] = v[1];
+      vin[q][2] = v[2];
+      if (!prim_active(k, gpos, pf)) continue;
+      act |= 1u << q;
+      if (k.pos_control) position_control_cell(k.sdf_kind, k.dt, gpos, pf, v);
+      else collide_cell(k.sdf_kind, k.dt, gpos, pf, v);
     }
-  // ---- pass A
+  }
+  // ---- reverse of ground friction + boundary
+  float gv[3] = {0.f, 0.f, 0.f}, gsf = 0.f;
+  if (work) {
+    typedef Dual<4> D4;
+    D4 dv[3], sf;
+    for (int i = 0; i < 3; ++i) {
+      dv[i].v = v[i];
+      for (int j = 0; j < 4; ++j) dv[i].d[j] = (i == j) ? 1.f : 0.f;
+    }
+    sf.v = sfric;
+    for (int j = 0; j < 4; ++j) sf.d[j] = (j == 3) ? 1.f : 0.f;
+    cell_ground_boundary<D4>(k, ci, cj, ck, sf, dv);
+    for (int j = 0; j < 3; ++j) gv[j] = gv4.x * dv[0].d[j] + gv4.y * dv[1].d[j] + gv4.z * dv[2].d[j];
+    gsf = gv4.x * dv[0].d[3] + gv4.y * dv[1].d[3] + gv4.z * dv[2].d[3];
+  }
   {
-    typedef Dual<5> D5;
-    float gsf = 0.f;
-    if (work) {
-      D5 p[3] = {seed<5>(g.x, 0, 0), seed<5>(g.y, 1, 0), seed<5>(g.z, 2, 0)};
-      D5 m = seed<5>(g.w, 3, 0), sf = seed<5>(sfric, 4, 0), v[3];
-      auto prim_of = [&](int q, PrimIn<D5>& pr) {
-        if (!((act >> q) & 1u)) return false;
-        PrimIn<float> pf;
-        load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pf);
-        promote_prim<5>(pf, -100, pr);
-        return true;
-      };
-      cell_update<D5>(k, ci, cj, ck, p, m, sf, prim_of, v);
-      float r[5];
-#pragma unroll
-      for (int i = 0; i < 5; ++i) r[i] = gv.x * v[0].d[i] + gv.y * v[1].d[i] + gv.z * v[2].d[i];
-      ggrid[idx] = make_float4(r[0], r[1], r[2], r[3]);
-      gsf = r[4];
-    }
     float tot = warp_sum(gsf);
     if ((threadIdx.x & 31) == 0 && tot != 0.f) atomicAdd(&g_scal[env * GS_STRIDE + GS_FRICTION], tot);
   }
-  // ---- primitive passes
-  typedef Dual<7> D7;
-  for (int q = 0; q < k.n_prim; ++q) {
+  // ---- reverse of the primitives, last to first
+  for (int q = k.n_prim - 1; q >= 0; --q) {
     bool mine = work && ((act >> q) & 1u);
     if (!__any_sync(0xffffffffu, mine)) continue;
+    PrimGrad pg;
+#pragma unroll
+    for (int i = 0; i < PRIM_NIN; ++i) pg.g[i] = 0.f;
+    if (mine) {
+      PrimIn<float> pf;
+      load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pf);
+      float vq[3] = {0.f, 0.f, 0.f}, gnew[3];
+#pragma unroll
+      for (int qq = 0; qq < UD_MAX_PRIM; ++qq)
+        if (qq == q) {
+          vq[0] = vin[qq][0];
+          vq[1] = vin[qq][1];
+          vq[2] = vin[qq][2];
+        }
+      if (k.pos_control) position_control_cell_bwd(k.sdf_kind, k.dt, gpos, pf, gv, gnew, pg);
+      else collide_cell_bwd(k.sdf_kind, k.dt, gpos, pf, vq, gv, gnew, pg);
+      gv[0] = gnew[0];
+      gv[1] = gnew[1];
+      gv[2] = gnew[2];
+    }
     size_t t = (size_t)env * k.n_prim + q;
     float* tp = g_fk_pos + t * (k.S + 1) * 3;
     float* tr = g_fk_rot + t * (k.S + 1) * 4;
-    for (int ch = 0; ch < 3; ++ch) {
-      float r[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (mine) {
-        D7 p[3] = {seed<7>(g.x, -1, 0), seed<7>(g.y, -1, 0), seed<7>(g.z, -1, 0)};
-        D7 m = seed<7>(g.w, -1, 0), sf = seed<7>(sfric, -1, 0), v[3];
-        auto prim_of = [&](int qq, PrimIn<D7>& pr) {
-          if (!((act >> qq) & 1u)) return false;
-          PrimIn<float> pf;
-          load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, qq, f, pf);
-          promote_prim<7>(pf, qq == q ? ch * 7 : -100, pr);
-          return true;
-        };
-        cell_update<D7>(k, ci, cj, ck, p, m, sf, prim_of, v);
 #pragma unroll
-        for (int i = 0; i < 7; ++i) r[i] = gv.x * v[0].d[i] + gv.y * v[1].d[i] + gv.z * v[2].d[i];
-      }
-#pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        float tot = warp_sum(r[i]);
-        if ((threadIdx.x & 31) != 0 || tot == 0.f) continue;
-        int j = ch * 7 + i;  // input index inside PrimIn
-        if (j < 3) atomicAdd(&tp[f * 3 + j], tot);
-        else if (j < 7) atomicAdd(&tr[f * 4 + (j - 3)], tot);
-        else if (j < 10) atomicAdd(&tp[(f + 1) * 3 + (j - 7)], tot);
-        else if (j < 14) atomicAdd(&tr[(f + 1) * 4 + (j - 10)], tot);
-        else if (j < 17) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + (j - 14)], tot);
-        else if (j < 18) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + 3], tot);
-        else atomicAdd(&g_fk_v[(t * k.S + f) * 3 + (j - 18)], tot);
-      }
+    for (int j = 0; j < PRIM_NIN; ++j) {
+      float tot = warp_sum(pg.g[j]);
+      if ((threadIdx.x & 31) != 0 || tot == 0.f) continue;
+      if (j < 3) atomicAdd(&tp[f * 3 + j], tot);
+      else if (j < 7) atomicAdd(&tr[f * 4 + (j - 3)], tot);
+      else if (j < 10) atomicAdd(&tp[(f + 1) * 3 + (j - 7)], tot);
+      else if (j < 14) atomicAdd(&tr[(f + 1) * 4 + (j - 10)], tot);
+      else if (j < 17) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + (j - 14)], tot);
+      else if (j < 18) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + 3], tot);
+      else atomicAdd(&g_fk_v[(t * k.S + f) * 3 + (j - 18)], tot);
     }
+  }
+  // ---- reverse of v = p / m + dt g
+  if (work) {
+    float im = 1.f / g.w;
+    float gm = -(gv[0] * g.x + gv[1] * g.y + gv[2] * g.z) * im * im;
+    ggrid[idx] = make_float4(gv[0] * im, gv[1] * im, gv[2] * im, gm);
   }
 }
 

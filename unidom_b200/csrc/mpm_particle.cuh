@@ -114,13 +114,13 @@ UD_DEV void constitutive_fwd(const MpmConst& k, const Mat3& C, const Mat3& F, fl
   for (int i = 0; i < 9; ++i) o.D.m[i] = o.F2.m[i] - R.m[i];
   Mat3 M = mat_mul_nt(o.D, o.F2);
   float iso = o.la * o.J * (o.J - 1.f);
+  const float cs = k.c_stress_mul / k.c_stress_div;  // (-dt*p_vol*4) / dx^2, one rounding earlier than :267
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       float st = 2.f * o.mu * M(i, j) + (i == j ? iso : 0.f);
-      st = k.c_stress_mul * st / k.c_stress_div;
-      o.affine(i, j) = st + k.p_mass * C(i, j);
+      o.affine(i, j) = cs * st + k.p_mass * C(i, j);
     }
 }
 

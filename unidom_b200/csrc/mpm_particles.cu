@@ -138,38 +138,72 @@ void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-level segmented reduction.  Lanes are consecutive particles of the per-frame sort, so lanes
-// that share a base cell form contiguous runs.  Every scattered value is first summed over its run
-// with 5 predicated shuffles and only the run head issues the global vector RED: ~59 particles per
-// cell collapse to one atomic per (run, node) instead of one per (particle, node).
+// Shared-memory staged scatter.  A CTA owns UD_BLOCK consecutive particles of the per-frame sort, so
+// particles that share a base cell form a few contiguous runs (~59 particles per cell in the
+// plasticine scene).  Phase 1: every particle stages its NV = 27*NC node values in shared memory
+// (value-major, +1 padded: conflict-free both ways).  Phase 2: thread t < NV owns one (node, comp)
+// and sums it over each run in particle order; one global RED per (run, node, comp) -- ~2.5 atomics
+// per particle instead of 27 vector atomics, and the summation order inside a CTA is fixed.
 // ------------------------------------------------------------------------------------------------
-struct SegInfo {
-  unsigned pred;  // bit i: lane + 2^i is still inside this lane's run
-  bool head;
+constexpr int STG_PAD = UD_BLOCK + 1;
+struct StageMeta {
+  int key[UD_BLOCK];
+  int base[UD_BLOCK][3];
+  int run_start[UD_BLOCK + 1];
+  int warp_heads[UD_BLOCK / 32];
+  int n_runs;
 };
-__device__ __forceinline__ SegInfo seg_info(int key) {
-  const unsigned lane = threadIdx.x & 31;
-  int kprev = __shfl_up_sync(0xffffffffu, key, 1);
-  SegInfo s;
-  s.head = lane == 0 || kprev != key;
-  unsigned heads = __ballot_sync(0xffffffffu, s.head);
-  unsigned higher = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
-  int run_end = higher ? (__ffs(higher) - 1) : 32;
-  s.pred = 0;
-#pragma unroll
-  for (int i = 0; i < 5; ++i)
-    if ((int)lane + (1 << i) < run_end) s.pred |= 1u << i;
-  return s;
-}
-__device__ __forceinline__ float seg_sum(float v, unsigned pred) {
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    float t = __shfl_down_sync(0xffffffffu, v, 1 << i);
-    if ((pred >> i) & 1u) v += t;
-  }
-  return v;
-}
+constexpr int DEAD_KEY = 0x40000000;
 UD_DEV int base_key(const int base[3]) { return (base[0] * 2048 + base[1]) * 2048 + base[2]; }
+
+// builds meta.run_start / n_runs from meta.key (call by all threads, after key/base are stored)
+__device__ __forceinline__ void stage_runs(StageMeta& m) {
+  __syncthreads();
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  bool head = t == 0 || m.key[t] != m.key[t - 1];
+  unsigned hb = __ballot_sync(0xffffffffu, head);
+  if (lane == 0) m.warp_heads[wid] = __popc(hb);
+  __syncthreads();
+  int before = __popc(hb & ((1u << lane) - 1u));
+  for (int w = 0; w < wid; ++w) before += m.warp_heads[w];
+  if (head) m.run_start[before] = t;
+  if (t == UD_BLOCK - 1) {
+    int total = before + (head ? 1 : 0);
+    m.n_runs = total;
+    m.run_start[total] = UD_BLOCK;
+  }
+  __syncthreads();
+}
+
+// phase 2: NC components per node; out points at the env's float4 grid
+template <int NC, bool CLAMP>
+__device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __restrict__ sv, const StageMeta& m,
+                                            float4* __restrict__ genv) {
+  const int t = threadIdx.x;
+  if (t >= 27 * NC) return;
+  const int j = t / NC, c = t - j * NC;
+  const int a = j / 9, b = (j / 3) % 3, cc = j % 3;
+  const float* col = sv + t * STG_PAD;
+  const int nr = m.n_runs;
+  for (int r = 0; r < nr; ++r) {
+    const int s0 = m.run_start[r], s1 = m.run_start[r + 1];
+    if (m.key[s0] & DEAD_KEY) continue;
+    float acc = 0.f;
+    for (int p = s0; p < s1; ++p) acc += col[p];
+    int ix, iy, iz;
+    if (CLAMP) {
+      ix = idx_gather(m.base[s0][0] + a, k.rx);
+      iy = idx_gather(m.base[s0][1] + b, k.ry);
+      iz = idx_gather(m.base[s0][2] + cc, k.rz);
+    } else {
+      ix = idx_scatter(m.base[s0][0] + a, k.rx);
+      iy = idx_scatter(m.base[s0][1] + b, k.ry);
+      iz = idx_scatter(m.base[s0][2] + cc, k.rz);
+      if ((ix | iy | iz) < 0) continue;
+    }
+    atomicAdd(reinterpret_cast<float*>(&genv[(ix * k.ry + iy) * k.rz + iz]) + c, acc);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // P2G: F update + SVD + plasticity + stress (mpm_simulator.py:238-268), then the 27-node scatter of
@@ -192,8 +226,12 @@ __global__ void __launch_bounds__(UD_BLOCK)
 k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
       const float* __restrict__ h_s) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sv = reinterpret_cast<float*>(smem_raw);                               // [108][STG_PAD]
+  StageMeta& meta = *reinterpret_cast<StageMeta*>(sv + 27 * 4 * STG_PAD);
   UD_PARTICLE_INDEX(k, env, g);
   const size_t N = k.N;
+  const int t = threadIdx.x;
   float x[3], v[3];
   Mat3 C, F;
   load_particle(ps_in, N, g, x, v, C, F);
@@ -205,44 +243,46 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
 #pragma unroll
     for (int c = 0; c < 9; ++c) ps_out[(PS_F + c) * N + g] = o.F2.m[c];
   }
-  // dead lanes (past the env's last particle) get a unique key and contribute zeros
-  const SegInfo seg = seg_info(live_ ? base_key(st.base) : (int)(0x40000000u | threadIdx.x));
+  meta.key[t] = live_ ? (base_key(st.base) & ~DEAD_KEY) : (DEAD_KEY | t);
+  meta.base[t][0] = st.base[0];
+  meta.base[t][1] = st.base[1];
+  meta.base[t][2] = st.base[2];
   const float lw = live_ ? 1.f : 0.f;
-  float4* genv = grid + (size_t)env * k.G;
   float mv[3] = {k.p_mass * v[0], k.p_mass * v[1], k.p_mass * v[2]};
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    int ix = idx_scatter(st.base[0] + a, k.rx);
     float dx0 = ((float)a - st.fx[0]) * k.dx;
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-      int iy = idx_scatter(st.base[1] + b, k.ry);
       float dx1 = ((float)b - st.fx[1]) * k.dx;
       float wab = st.w[a][0] * st.w[b][1];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        int iz = idx_scatter(st.base[2] + c, k.rz);
         float dx2 = ((float)c - st.fx[2]) * k.dx;
         float wt = wab * st.w[c][2] * lw;
-        float4 val;
-        val.x = wt * (mv[0] + (o.affine(0, 0) * dx0 + o.affine(0, 1) * dx1 + o.affine(0, 2) * dx2));
-        val.y = wt * (mv[1] + (o.affine(1, 0) * dx0 + o.affine(1, 1) * dx1 + o.affine(1, 2) * dx2));
-        val.z = wt * (mv[2] + (o.affine(2, 0) * dx0 + o.affine(2, 1) * dx1 + o.affine(2, 2) * dx2));
-        val.w = wt * k.p_mass;
-        val.x = seg_sum(val.x, seg.pred);
-        val.y = seg_sum(val.y, seg.pred);
-        val.z = seg_sum(val.z, seg.pred);
-        val.w = seg_sum(val.w, seg.pred);
-        if (seg.head && live_ && (ix | iy | iz) >= 0) atomicAdd(&genv[(ix * k.ry + iy) * k.rz + iz], val);
+        float* dst = sv + ((a * 9 + b * 3 + c) * 4) * STG_PAD + t;
+        dst[0] = wt * (mv[0] + (o.affine(0, 0) * dx0 + o.affine(0, 1) * dx1 + o.affine(0, 2) * dx2));
+        dst[STG_PAD] = wt * (mv[1] + (o.affine(1, 0) * dx0 + o.affine(1, 1) * dx1 + o.affine(1, 2) * dx2));
+        dst[2 * STG_PAD] = wt * (mv[2] + (o.affine(2, 0) * dx0 + o.affine(2, 1) * dx1 + o.affine(2, 2) * dx2));
+        dst[3 * STG_PAD] = wt * k.p_mass;
       }
     }
   }
+  stage_runs(meta);
+  stage_flush<4, false>(k, sv, meta, grid + (size_t)env * k.G);
 }
+
+constexpr size_t stage_smem_bytes(int nc) { return sizeof(float) * 27 * nc * STG_PAD + sizeof(StageMeta); }
 
 void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
                 const float* la_s, const MpmWs& ws, cudaStream_t st) {
   KScope ks_(KC_P2G, st);
-  k_p2g<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_p2g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4));
+    attr_set = true;
+  }
+  k_p2g<<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4), st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -278,18 +318,21 @@ k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ 
         float d2 = (float)c - st.fx[2];
         float wt = wab * st.w[c][2];
         float4 gv = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
-        nv[0] += wt * gv.x;
-        nv[1] += wt * gv.y;
-        nv[2] += wt * gv.z;
-        float w4 = 4.f * wt;
-        float gvv[3] = {gv.x, gv.y, gv.z};
+        float wg[3] = {wt * gv.x, wt * gv.y, wt * gv.z};
         float dd[3] = {d0, d1, d2};
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i) {
+          nv[i] += wg[i];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) nC(i, j) += w4 * (gvv[i] * dd[j]) * k.inv_dx;
+          for (int j = 0; j < 3; ++j) nC(i, j) += wg[i] * dd[j];
+        }
       }
     }
+  }
+  {  // C' = 4 inv_dx sum wt g (x) d   (the factor is applied once, after the 27-node sum)
+    const float c4 = 4.f * k.inv_dx;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) nC.m[c] *= c4;
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) ps_out[(PS_X + c) * N + g] = x[c] + k.dt * nv[c];
@@ -387,8 +430,12 @@ void launch_gather_cot(const MpmConst& k, const ud_mpm_state* gout, const MpmWs&
 __global__ void __launch_bounds__(UD_BLOCK)
 k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict__ grid_out,
           float* __restrict__ gs, float4* __restrict__ ggrid) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sv = reinterpret_cast<float*>(smem_raw);                               // [81][STG_PAD]
+  StageMeta& meta = *reinterpret_cast<StageMeta*>(sv + 27 * 3 * STG_PAD);
   UD_PARTICLE_INDEX(k, env, g);
   const size_t N = k.N;
+  const int t = threadIdx.x;
   float x[3], gxo[3], gvt[3];
   Mat3 gC;
 #pragma unroll
@@ -401,10 +448,12 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   for (int c = 0; c < 9; ++c) gC.m[c] = gs[(PS_C + c) * N + g];
   Stencil st;
   make_stencil(x, k.inv_dx, st);
-  const SegInfo seg = seg_info(live_ ? base_key(st.base) : (int)(0x40000000u | threadIdx.x));
+  meta.key[t] = live_ ? (base_key(st.base) & ~DEAD_KEY) : (DEAD_KEY | t);
+  meta.base[t][0] = st.base[0];
+  meta.base[t][1] = st.base[1];
+  meta.base[t][2] = st.base[2];
   const float lw = live_ ? 1.f : 0.f;
   const float4* genv = grid_out + (size_t)env * k.G;
-  float4* ggenv = ggrid + (size_t)env * k.G;
   float gw[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
   float gfx[3] = {0.f, 0.f, 0.f};
   const float c4 = 4.f * k.inv_dx;
@@ -427,9 +476,10 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
         float r0 = gvt[0] + c4 * (gC(0, 0) * d0 + gC(0, 1) * d1 + gC(0, 2) * d2);
         float r1 = gvt[1] + c4 * (gC(1, 0) * d0 + gC(1, 1) * d1 + gC(1, 2) * d2);
         float r2 = gvt[2] + c4 * (gC(2, 0) * d0 + gC(2, 1) * d1 + gC(2, 2) * d2);
-        float s0 = seg_sum(lw * wt * r0, seg.pred), s1 = seg_sum(lw * wt * r1, seg.pred),
-              s2 = seg_sum(lw * wt * r2, seg.pred);
-        if (seg.head && live_) atomicAdd(&ggenv[cell], make_float4(s0, s1, s2, 0.f));
+        float* dst = sv + ((a * 9 + b * 3 + c) * 3) * STG_PAD + t;
+        dst[0] = lw * wt * r0;
+        dst[STG_PAD] = lw * wt * r1;
+        dst[2 * STG_PAD] = lw * wt * r2;
         float gwt = gv.x * r0 + gv.y * r1 + gv.z * r2;
         // gd_j = 4 inv_dx wt sum_i g_i gC'_ij ; fx enters d with a minus sign
         float cw = c4 * wt;
@@ -442,18 +492,22 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
       }
     }
   }
-  if (!live_) return;
+  if (live_) {
 #pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    gfx[d] += gw[0][d] * st.dw[0][d] + gw[1][d] * st.dw[1][d] + gw[2][d] * st.dw[2][d];
-    gs[(PS_X + d) * N + g] = gxo[d] + k.inv_dx * gfx[d];
+    for (int d = 0; d < 3; ++d) {
+      gfx[d] += gw[0][d] * st.dw[0][d] + gw[1][d] * st.dw[1][d] + gw[2][d] * st.dw[2][d];
+      gs[(PS_X + d) * N + g] = gxo[d] + k.inv_dx * gfx[d];
+    }
   }
+  stage_runs(meta);
+  // transpose of the clamping gather: clamped target index
+  stage_flush<3, true>(k, sv, meta, ggrid + (size_t)env * k.G);
 }
 
 void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
                     cudaStream_t st) {
   KScope ks_(KC_G2P_BWD, st);
-  k_g2p_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
+  k_g2p_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(3), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
 }
 
 // P2G^T (gather of the cotangents of scattered momentum/mass; dropped nodes contribute nothing),
