@@ -125,6 +125,47 @@ int ud_mpm_sort_bins(const ud_mpm_params* p, const float* x, int32_t* out_base, 
 /* Number of keys per env used by ud_mpm_sort_bins (for sizing host-side checks). */
 int32_t ud_mpm_num_keys(const ud_mpm_params* p);
 
+/* ------------------------------------------------------------------------------------------------
+ * Mass-spring cloth (core/engine/cloth_simulator.py).  One call = robot_step (:163-180): the 8-vector
+ * sub-action is scaled, then `substeps` (50) x step (:257-337) run inside one launch.
+ * Topology is passed as two tables built on the host from the cloth mask (:48-66):
+ *   nbr [P,8] int32 : node index of the k-th link neighbour (links order of :48), or -1 when the
+ *                     link carries no force (neighbour outside the mask, or zero rest length)
+ *   L0  [P,8] float : rest length cell_size*|link| clipped to >= 1e-12 (:61-63)
+ * n_nodes <= 1024 (one thread per node, one CTA per environment).                                  */
+typedef struct ud_cloth_params {
+  int32_t num_envs;   /* B                                       */
+  int32_t n_nodes;    /* P = cloth_mask.sum()                    */
+  int32_t N;          /* conf.N (board size; informational)      */
+  int32_t substeps;   /* 50 in robot_step (:176)                 */
+  double dt, gravity, damping, max_v, small_num, cell_size;
+  double mask_sum;    /* divisor of norm_grad's backward (:192)  */
+  int32_t stiffness_is_float; /* 0: int leaf, no gradient (conf.stiffness=900); 1: float (GenDOM, apg_para) */
+} ud_cloth_params;
+
+/* Float leaves of ClothState (cloth_simulator.py:13-23), batched on axis 0. */
+typedef struct ud_cloth_state {
+  float* x;          /* [B,P,3] */
+  float* v;          /* [B,P,3] */
+  float* primitive0; /* [B,4] xyz + radius */
+  float* primitive1; /* [B,4] */
+  float* action0;    /* [B,4] dxyz + suction */
+  float* action1;    /* [B,4] */
+  float* stiffness;  /* [B] (as float) */
+  float* mu;         /* [B] */
+} ud_cloth_state;
+
+size_t ud_cloth_workspace_bytes(const ud_cloth_params* p);
+/* Replaces vmap(jit(robot_step_wrapper)) forward; action is [B,8]. */
+int ud_cloth_step_fwd(const ud_cloth_params* p, const ud_cloth_state* in, const int32_t* nbr, const float* L0,
+                      const float* action, ud_cloth_state* out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+/* Reverse mode of the same call (replaces the two custom_vjp levels :107-145, :228-255 and the 8
+ * norm_grad re-normalisations per substep): recomputes the substeps from `in`, then reverses. */
+int ud_cloth_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const int32_t* nbr, const float* L0,
+                      const float* action, const ud_cloth_state* gout, ud_cloth_state* gin, float* gaction,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- instrumentation (bench.py): launch counting and per-kernel-class CUDA-event timing ------
  * ud_launch_count: kernels + memsets enqueued by this library since the last reset (host counter).
  * ud_timing_enable(1): subsequent calls bracket every kernel class with cudaEvents on the call's

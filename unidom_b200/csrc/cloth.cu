@@ -1,0 +1,599 @@
+// Mass-spring cloth step (fwd + adjoint) for sm_100a.  One CTA per environment, one thread per cloth
+// node: positions/velocities live in registers, neighbour positions are exchanged through shared
+// memory, and all `substeps` (50) substeps of a sub-action run inside ONE launch -- the cloth state
+// (512 nodes x 24 B) never round-trips HBM between substeps.
+// Reference: DaXBench/daxbench/core/engine/cloth_simulator.py:163-180 (robot_step), :198-226 (grippers),
+// :257-337 (step), :182-196 (norm_grad, re-normalises the cotangent 8x per substep in the adjoint).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/unidom_b200.h"
+#include "mpm_internal.h"  // KScope instrumentation
+
+namespace ud {
+
+struct ClothK {
+  int B, P, S, threads;
+  float dt, g, gdt, damp, max_v, small_num, mask_sum;
+  int stiff_float;
+};
+
+static bool cloth_fold(const ud_cloth_params* p, ClothK* k) {
+  if (!p || p->num_envs < 1 || p->n_nodes < 1 || p->n_nodes > 1024 || p->substeps < 1) return false;
+  if (!(p->dt > 0) || !(p->mask_sum > 0)) return false;
+  k->B = p->num_envs;
+  k->P = p->n_nodes;
+  k->S = p->substeps;
+  k->threads = (p->n_nodes + 31) / 32 * 32;
+  k->dt = (float)p->dt;
+  k->g = (float)p->gravity;
+  k->gdt = (float)(p->gravity * p->dt);                 // jnp.array([0, gravity*dt, 0]) (:259)
+  k->damp = expf((float)(-p->damping * p->dt));         // jnp.exp(-damping*dt) in f32 (:309)
+  k->max_v = (float)p->max_v;
+  k->small_num = (float)p->small_num;
+  k->mask_sum = (float)p->mask_sum;
+  k->stiff_float = p->stiffness_is_float;
+  return true;
+}
+
+__device__ __forceinline__ float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
+__device__ __forceinline__ float nan0(float a) {
+  if (a != a) return 0.f;
+  if (isinf(a)) return a > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+  return a;
+}
+
+// block-wide sums of two values (all threads must call); result broadcast to every thread
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, off);
+    b += __shfl_down_sync(0xffffffffu, b, off);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();  // protect `red` from the previous use
+  if (lane == 0) {
+    red[wid] = a;
+    red[32 + wid] = b;
+  }
+  __syncthreads();
+  float sa = 0.f, sb = 0.f;
+  for (int w = 0; w < nw; ++w) {  // fixed order: deterministic
+    sa += red[w];
+    sb += red[32 + w];
+  }
+  a = sa;
+  b = sb;
+}
+
+struct Sub {  // forward intermediates of one substep for one node (kept for the reverse)
+  float vg[3];        // v after the gravity kick
+  float fr[3];        // spring force sum + gravity (before friction)
+  float f[3];         // force after friction
+  float muF, sV, sF;
+  bool fmask, dyn, stat, zero, nonz;
+  float v0[3];        // after damping, before grippers
+  bool m0, m1;        // gripper masks
+  float x1[3], v1[3]; // after gripper 0
+  float x2[3], v2[3]; // after gripper 1
+};
+
+// one forward substep for one node; xs = shared positions of all nodes (already synchronised)
+__device__ __forceinline__ void cloth_substep(const ClothK& k, const float* __restrict__ xs, const int nbr[8],
+                                              const float L0[8], float stiff, float mu, const float a0[4],
+                                              const float a1[4], const float ps0[4], const float ps1[4],
+                                              float x[3], float v[3], Sub& o) {
+  o.vg[0] = v[0];
+  o.vg[1] = v[1] - k.gdt;
+  o.vg[2] = v[2];
+  float fs[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (nbr[q] < 0) continue;
+    float r0 = xs[3 * nbr[q]] - x[0], r1 = xs[3 * nbr[q] + 1] - x[1], r2 = xs[3 * nbr[q] + 2] - x[2];
+    float cur = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 1e-12f));
+    float e = cur - L0[q];
+    fs[0] += stiff * r0 / cur * e / L0[q];
+    fs[1] += stiff * r1 / cur * e / L0[q];
+    fs[2] += stiff * r2 / cur * e / L0[q];
+  }
+  o.fr[0] = fs[0];
+  o.fr[1] = fs[1] - k.g;
+  o.fr[2] = fs[2];
+  // Coulomb ground friction (:281-306)
+  o.fmask = x[1] <= k.small_num;
+  o.muF = mu * fminf(o.fr[1], 0.f) * -1.f;
+  o.sV = sqrtf(o.vg[0] * o.vg[0] + o.vg[2] * o.vg[2] + k.small_num);
+  o.dyn = o.fmask && (o.sV > k.small_num);
+  float fx = o.fr[0], fz = o.fr[2];
+  if (o.dyn) {
+    fx = fx - o.muF * o.vg[0] / o.sV;
+    fz = fz - o.muF * o.vg[2] / o.sV;
+  }
+  o.stat = o.fmask && (o.sV <= k.small_num);
+  o.sF = sqrtf(fx * fx + fz * fz + k.small_num);
+  o.zero = o.stat && (o.muF > o.sF);
+  o.nonz = o.stat && (o.muF <= o.sF);
+  float xF = fx, yF = fz;
+  if (o.zero) {
+    fx = 0.f;
+    fz = 0.f;
+  }
+  if (o.nonz) {
+    float R = 1.f - o.muF / o.sF;
+    fx = R * xF;
+    fz = R * yF;
+  }
+  o.f[0] = fx;
+  o.f[1] = o.fr[1];
+  o.f[2] = fz;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o.v0[c] = (o.vg[c] + o.f[c] * k.dt) * k.damp;
+  // grippers (:198-226)
+  {
+    float d0 = x[0] - ps0[0], d1 = x[1] - ps0[1], d2 = x[2] - ps0[2];
+    o.m0 = sqrtf(d0 * d0 + d1 * d1 + d2 * d2) <= ps0[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o.v1[c] = o.m0 ? a0[3] * o.v0[c] : o.v0[c];
+      o.x1[c] = o.m0 ? x[c] + a0[c] * (1.f - a0[3]) : x[c];
+    }
+    d0 = o.x1[0] - ps1[0];
+    d1 = o.x1[1] - ps1[1];
+    d2 = o.x1[2] - ps1[2];
+    o.m1 = sqrtf(d0 * d0 + d1 * d1 + d2 * d2) <= ps1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o.v2[c] = o.m1 ? a1[3] * o.v1[c] : o.v1[c];
+      o.x2[c] = o.m1 ? o.x1[c] + a1[c] * (1.f - a1[3]) : o.x1[c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float vc = clipf(o.v2[c], -k.max_v, k.max_v);
+    v[c] = vc;
+    x[c] = clipf(o.x2[c], 0.f, 1.f) + k.dt * vc;
+  }
+}
+
+__device__ __forceinline__ void advance_gripper(const float a[4], float ps[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) ps[c] = clipf(ps[c] + (c < 3 ? a[c] : 0.f), 0.f, 1.f);
+}
+
+__device__ __forceinline__ void load_actions(const float* __restrict__ action, int env, float a0[4], float a1[4]) {
+  const float* a = action + (size_t)env * 8;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    a0[c] = clipf(a[c], -2.f, 2.f) / 50.f;       // :168
+    a1[c] = clipf(a[4 + c], -2.f, 2.f) / 50.f;   // :169
+  }
+  a0[3] = a[3];
+  a1[3] = a[7];
+}
+
+// save layout per (env, substep): [P*3 x][P*3 v][ps0 4][ps1 4]
+__device__ __forceinline__ size_t save_stride(const ClothK& k) { return (size_t)k.P * 6 + 8; }
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
+k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, const float* __restrict__ L0_t,
+            const float* __restrict__ action, ud_cloth_state out, float* __restrict__ save) {
+  extern __shared__ float xs[];  // [P*3]
+  const int env = blockIdx.x, t = threadIdx.x;
+  const bool live = t < k.P;
+  const int n = live ? t : 0;
+  const size_t o = (size_t)env * k.P + n;
+  float x[3], v[3], L0[8], a0[4], a1[4], ps0[4], ps1[4];
+  int nbr[8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    x[c] = in.x[3 * o + c];
+    v[c] = in.v[3 * o + c];
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    nbr[q] = live ? nbr_t[n * 8 + q] : -1;
+    L0[q] = L0_t[n * 8 + q];
+  }
+  load_actions(action, env, a0, a1);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    ps0[c] = in.primitive0[env * 4 + c];
+    ps1[c] = in.primitive1[env * 4 + c];
+  }
+  const float stiff = in.stiffness[env], mu = in.mu[env];
+  for (int s = 0; s < k.S; ++s) {
+    if (save) {
+      float* sv = save + ((size_t)env * k.S + s) * save_stride(k);
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          sv[3 * n + c] = x[c];
+          sv[(size_t)k.P * 3 + 3 * n + c] = v[c];
+        }
+      }
+      if (t == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          sv[(size_t)k.P * 6 + c] = ps0[c];
+          sv[(size_t)k.P * 6 + 4 + c] = ps1[c];
+        }
+      }
+    }
+    if (live) {
+      xs[3 * n] = x[0];
+      xs[3 * n + 1] = x[1];
+      xs[3 * n + 2] = x[2];
+    }
+    __syncthreads();
+    Sub sb;
+    cloth_substep(k, xs, nbr, L0, stiff, mu, a0, a1, ps0, ps1, x, v, sb);
+    advance_gripper(a0, ps0);
+    advance_gripper(a1, ps1);
+    __syncthreads();
+  }
+  if (!out.x) return;
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      out.x[3 * o + c] = x[c];
+      out.v[3 * o + c] = v[c];
+    }
+  }
+  if (t == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      out.primitive0[env * 4 + c] = ps0[c];
+      out.primitive1[env * 4 + c] = ps1[c];
+      out.action0[env * 4 + c] = a0[c];
+      out.action1[env * 4 + c] = a1[c];
+    }
+    out.stiffness[env] = stiff;
+    out.mu[env] = mu;
+  }
+}
+
+// norm_grad backward for a 4-vector that every thread holds identically (gripper state)
+__device__ __forceinline__ void norm_grad4(const ClothK& k, float g[4]) {
+  float n2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + g[3] * g[3];
+  float nrm = sqrtf(n2);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) g[c] = nan0(g[c] / nrm) / k.mask_sum;
+}
+
+// Adjoint of the 50-substep sub-action.  Expects `save` filled by k_cloth_fwd (recompute pass).
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
+k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, const float* __restrict__ L0_t,
+            const float* __restrict__ action, ud_cloth_state gout, ud_cloth_state gin,
+            float* __restrict__ gaction, const float* __restrict__ save) {
+  extern __shared__ float sm[];
+  float* xs = sm;                    // [P*3]
+  float* grel = sm + 3 * k.P;        // [P*8*3] cotangents of the spring vectors
+  float* red = grel + 24 * k.P;      // [64]
+  const int env = blockIdx.x, t = threadIdx.x;
+  const bool live = t < k.P;
+  const int n = live ? t : 0;
+  const size_t o = (size_t)env * k.P + n;
+  const int mirror[8] = {1, 0, 3, 2, 7, 6, 5, 4};  // link k of i  <->  link mirror[k] of its neighbour
+  float L0[8], a0[4], a1[4];
+  int nbr[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    nbr[q] = live ? nbr_t[n * 8 + q] : -1;
+    L0[q] = L0_t[n * 8 + q];
+  }
+  load_actions(action, env, a0, a1);
+  const float stiff = in.stiffness[env], mu = in.mu[env];
+  // incoming cotangents
+  float gx[3], gv[3], gps0[4], gps1[4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    gx[c] = (live && gout.x) ? gout.x[3 * o + c] : 0.f;
+    gv[c] = (live && gout.v) ? gout.v[3 * o + c] : 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    gps0[c] = gout.primitive0 ? gout.primitive0[env * 4 + c] : 0.f;
+    gps1[c] = gout.primitive1 ? gout.primitive1[env * 4 + c] : 0.f;
+  }
+  // per-thread partial sums (reduced at the end) and uniform parts of the action cotangents
+  float ga0p[4] = {0.f, 0.f, 0.f, 0.f}, ga1p[4] = {0.f, 0.f, 0.f, 0.f}, gstiffp = 0.f, gmup = 0.f;
+  float ga0u[4], ga1u[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    ga0u[c] = gout.action0 ? gout.action0[env * 4 + c] : 0.f;   // out.action0 = the scaled sub-action
+    ga1u[c] = gout.action1 ? gout.action1[env * 4 + c] : 0.f;
+  }
+  for (int s = k.S - 1; s >= 0; --s) {
+    const float* sv = save + ((size_t)env * k.S + s) * save_stride(k);
+    float x[3], v[3], ps0[4], ps1[4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      x[c] = sv[3 * n + c];
+      v[c] = sv[(size_t)k.P * 3 + 3 * n + c];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      ps0[c] = sv[(size_t)k.P * 6 + c];
+      ps1[c] = sv[(size_t)k.P * 6 + 4 + c];
+    }
+    const float xin[3] = {x[0], x[1], x[2]};
+    __syncthreads();
+    if (live) {
+      xs[3 * n] = x[0];
+      xs[3 * n + 1] = x[1];
+      xs[3 * n + 2] = x[2];
+    }
+    __syncthreads();
+    Sub f;
+    cloth_substep(k, xs, nbr, L0, stiff, mu, a0, a1, ps0, ps1, x, v, f);  // x,v now hold the outputs (unused)
+    // ---- (1) trailing norm_grads on x', v', ps0', ps1' (:331-334)
+    float nx = live ? gx[0] * gx[0] + gx[1] * gx[1] + gx[2] * gx[2] : 0.f;
+    float nv = live ? gv[0] * gv[0] + gv[1] * gv[1] + gv[2] * gv[2] : 0.f;
+    block_sum2(nx, nv, red);
+    nx = sqrtf(nx);
+    nv = sqrtf(nv);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      gx[c] = nan0(gx[c] / nx) / k.mask_sum;
+      gv[c] = nan0(gv[c] / nv) / k.mask_sum;
+    }
+    norm_grad4(k, gps0);
+    norm_grad4(k, gps1);
+    // ---- (2) x' = clip(x2,0,1) + dt clip(v2) ; v' = clip(v2, +-max_v)
+    float gx2[3], gv2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float gvc = gv[c] + k.dt * gx[c];
+      gv2[c] = (f.v2[c] >= -k.max_v && f.v2[c] <= k.max_v) ? gvc : 0.f;
+      gx2[c] = (f.x2[c] >= 0.f && f.x2[c] <= 1.f) ? gx[c] : 0.f;
+    }
+    // ---- (3) grippers advance: ps' = clip(ps + [a,0], 0, 1)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float u0 = ps0[c] + (c < 3 ? a0[c] : 0.f), u1 = ps1[c] + (c < 3 ? a1[c] : 0.f);
+      gps0[c] = (u0 >= 0.f && u0 <= 1.f) ? gps0[c] : 0.f;
+      gps1[c] = (u1 >= 0.f && u1 <= 1.f) ? gps1[c] : 0.f;
+      if (c < 3) {
+        ga0u[c] += gps0[c];
+        ga1u[c] += gps1[c];
+      }
+    }
+    // ---- (4) gripper 1: norm_grad(x2), norm_grad(v2), then the where()
+    nx = live ? gx2[0] * gx2[0] + gx2[1] * gx2[1] + gx2[2] * gx2[2] : 0.f;
+    nv = live ? gv2[0] * gv2[0] + gv2[1] * gv2[1] + gv2[2] * gv2[2] : 0.f;
+    block_sum2(nx, nv, red);
+    nx = sqrtf(nx);
+    nv = sqrtf(nv);
+    float gx1[3], gv1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float gxq = nan0(gx2[c] / nx) / k.mask_sum, gvq = nan0(gv2[c] / nv) / k.mask_sum;
+      gx1[c] = gxq;
+      if (f.m1 && live) {
+        gv1[c] = a1[3] * gvq;
+        ga1p[3] += gvq * f.v1[c] - gxq * a1[c];
+        ga1p[c] += gxq * (1.f - a1[3]);
+      } else {
+        gv1[c] = gvq;
+      }
+    }
+    // ---- (5) gripper 0
+    nx = live ? gx1[0] * gx1[0] + gx1[1] * gx1[1] + gx1[2] * gx1[2] : 0.f;
+    nv = live ? gv1[0] * gv1[0] + gv1[1] * gv1[1] + gv1[2] * gv1[2] : 0.f;
+    block_sum2(nx, nv, red);
+    nx = sqrtf(nx);
+    nv = sqrtf(nv);
+    float gxs[3], gv0[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float gxq = nan0(gx1[c] / nx) / k.mask_sum, gvq = nan0(gv1[c] / nv) / k.mask_sum;
+      gxs[c] = gxq;  // x passes through either branch of the where()
+      if (f.m0 && live) {
+        gv0[c] = a0[3] * gvq;
+        ga0p[3] += gvq * f.v0[c] - gxq * a0[c];
+        ga0p[c] += gxq * (1.f - a0[3]);
+      } else {
+        gv0[c] = gvq;
+      }
+    }
+    // ---- (6) v0 = (vg + f dt) damp
+    float gf[3], gvg[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      gvg[c] = gv0[c] * k.damp;
+      gf[c] = gv0[c] * k.damp * k.dt;
+    }
+    // ---- (7) friction reverse -> cotangent of the raw force fr, of vg (x,z) and of mu
+    float gfr[3] = {gf[0], gf[1], gf[2]};
+    float gmuF = 0.f;
+    {
+      // recompute the pre-static values
+      float fx1 = f.fr[0], fz1 = f.fr[2];
+      if (f.dyn) {
+        fx1 = fx1 - f.muF * f.vg[0] / f.sV;
+        fz1 = fz1 - f.muF * f.vg[2] / f.sV;
+      }
+      float gfx1 = gf[0], gfz1 = gf[2];
+      if (f.zero) {
+        gfx1 = 0.f;
+        gfz1 = 0.f;
+      }
+      if (f.nonz) {
+        // fx = R xF, fz = R yF, R = 1 - muF / sF, sF = sqrt(xF^2 + yF^2 + small)
+        float R = 1.f - f.muF / f.sF;
+        float gR = gf[0] * fx1 + gf[2] * fz1;
+        gmuF += -gR / f.sF;
+        float gsF = gR * f.muF / (f.sF * f.sF);
+        gfx1 = gf[0] * R + gsF * fx1 / f.sF;
+        gfz1 = gf[2] * R + gsF * fz1 / f.sF;
+      }
+      gfr[0] = gfx1;
+      gfr[2] = gfz1;
+      if (f.dyn) {
+        // fx1 = fr0 - muF vg0 / sV ; sV = sqrt(vg0^2 + vg2^2 + small)
+        gmuF += -(gfx1 * f.vg[0] + gfz1 * f.vg[2]) / f.sV;
+        float gsV = (gfx1 * f.vg[0] + gfz1 * f.vg[2]) * f.muF / (f.sV * f.sV);
+        gvg[0] += -gfx1 * f.muF / f.sV + gsV * f.vg[0] / f.sV;
+        gvg[2] += -gfz1 * f.muF / f.sV + gsV * f.vg[2] / f.sV;
+      }
+      // muF = -mu * min(fr1, 0)
+      if (live) gmup += gmuF * (-fminf(f.fr[1], 0.f));
+      if (f.fr[1] <= 0.f) gfr[1] += gmuF * (-mu);
+    }
+    // ---- (8) spring forces: f_c = (stiff/L0) rel_c (1 - L0/cur)
+    float gxi[3] = {gxs[0], gxs[1], gxs[2]};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+      if (nbr[q] >= 0 && live) {
+        float r0 = xs[3 * nbr[q]] - xin[0], r1 = xs[3 * nbr[q] + 1] - xin[1], r2 = xs[3 * nbr[q] + 2] - xin[2];
+        float sq = r0 * r0 + r1 * r1 + r2 * r2;
+        float cur = sqrtf(fmaxf(sq, 1e-12f));
+        float e = cur - L0[q];
+        float dot = gfr[0] * r0 + gfr[1] * r1 + gfr[2] * r2;
+        float sc = stiff / L0[q];
+        float a = sc * e / cur;                                   // d f_c / d rel_c (direct)
+        float b = sq >= 1e-12f ? sc * L0[q] * dot / (cur * cur * cur) : 0.f;  // through cur
+        g0 = a * gfr[0] + b * r0;
+        g1 = a * gfr[1] + b * r1;
+        g2 = a * gfr[2] + b * r2;
+        if (k.stiff_float) gstiffp += dot * e / (cur * L0[q]);
+        gxi[0] -= g0;
+        gxi[1] -= g1;
+        gxi[2] -= g2;
+      }
+      if (live) {
+        grel[(n * 8 + q) * 3] = g0;
+        grel[(n * 8 + q) * 3 + 1] = g1;
+        grel[(n * 8 + q) * 3 + 2] = g2;
+      }
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (nbr[q] < 0) continue;
+        const float* gr = grel + (nbr[q] * 8 + mirror[q]) * 3;  // the neighbour's spring towards me
+        gxi[0] += gr[0];
+        gxi[1] += gr[1];
+        gxi[2] += gr[2];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      gx[c] = gxi[c];
+      gv[c] = gvg[c];
+    }
+  }
+  // ---- outputs
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (gin.x) gin.x[3 * o + c] = gx[c];
+      if (gin.v) gin.v[3 * o + c] = gv[c];
+    }
+  }
+  // reduce the per-thread partials: (ga0p[0..3], ga1p[0..3], gstiffp, gmup)
+  float pr[10] = {ga0p[0], ga0p[1], ga0p[2], ga0p[3], ga1p[0], ga1p[1], ga1p[2], ga1p[3], gstiffp, gmup};
+  for (int i = 0; i < 10; i += 2) block_sum2(pr[i], pr[i + 1], red);
+  if (t == 0) {
+    float ga0[4], ga1[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      ga0[c] = ga0u[c] + pr[c];
+      ga1[c] = ga1u[c] + pr[4 + c];
+      if (gin.primitive0) gin.primitive0[env * 4 + c] = gps0[c];
+      if (gin.primitive1) gin.primitive1[env * 4 + c] = gps1[c];
+      if (gin.action0) gin.action0[env * 4 + c] = 0.f;  // overwritten by robot_step (:173)
+      if (gin.action1) gin.action1[env * 4 + c] = 0.f;
+    }
+    if (gin.stiffness) gin.stiffness[env] = pr[8] + (gout.stiffness ? gout.stiffness[env] : 0.f);
+    if (gin.mu) gin.mu[env] = pr[9] + (gout.mu ? gout.mu[env] : 0.f);
+    if (gaction) {
+      const float* a = action + (size_t)env * 8;
+      float* ga = gaction + (size_t)env * 8;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        ga[c] = (a[c] >= -2.f && a[c] <= 2.f) ? ga0[c] / 50.f : 0.f;
+        ga[4 + c] = (a[4 + c] >= -2.f && a[4 + c] <= 2.f) ? ga1[c] / 50.f : 0.f;
+      }
+      ga[3] = ga0[3];
+      ga[7] = ga1[3];
+    }
+  }
+}
+
+static bool cloth_state_ok(const ud_cloth_state* s) {
+  return s && s->x && s->v && s->primitive0 && s->primitive1 && s->action0 && s->action1 && s->stiffness && s->mu;
+}
+
+}  // namespace ud
+
+using namespace ud;
+
+extern "C" {
+
+size_t ud_cloth_workspace_bytes(const ud_cloth_params* p) {
+  ClothK k;
+  if (!cloth_fold(p, &k)) return 0;
+  return (((size_t)k.B * k.S * ((size_t)k.P * 6 + 8) * sizeof(float)) + 255) & ~(size_t)255;
+}
+
+int ud_cloth_step_fwd(const ud_cloth_params* p, const ud_cloth_state* in, const int32_t* nbr, const float* L0,
+                      const float* action, ud_cloth_state* out, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  ClothK k;
+  if (!cloth_fold(p, &k)) return UD_E_INVALID;
+  if (!cloth_state_ok(in) || !cloth_state_ok(out) || !nbr || !L0 || !action) return UD_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  KScope ks(KC_CLOTH_FWD, st);
+  if (k.threads <= 512)
+    k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, *out, nullptr);
+  else
+    k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, *out, nullptr);
+  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+}
+
+int ud_cloth_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const int32_t* nbr, const float* L0,
+                      const float* action, const ud_cloth_state* gout, ud_cloth_state* gin, float* gaction,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  ClothK k;
+  if (!cloth_fold(p, &k)) return UD_E_INVALID;
+  if (!cloth_state_ok(in) || !gout || !gin || !nbr || !L0 || !action) return UD_E_INVALID;
+  size_t need = ud_cloth_workspace_bytes(p);
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255)) return UD_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  ud_cloth_state none;
+  memset(&none, 0, sizeof(none));
+  size_t smem = sizeof(float) * ((size_t)27 * k.P + 64);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_cloth_bwd<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (27 * 512 + 64)));
+    cudaFuncSetAttribute(k_cloth_bwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (27 * 1024 + 64)));
+    attr = true;
+  }
+  {
+    KScope ks(KC_CLOTH_FWD, st);  // recompute pass: checkpoint = the sub-action input
+    if (k.threads <= 512)
+      k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, none, (float*)workspace);
+    else
+      k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, none, (float*)workspace);
+  }
+  {
+    KScope ks(KC_CLOTH_BWD, st);
+    if (k.threads <= 512)
+      k_cloth_bwd<512><<<k.B, k.threads, smem, st>>>(k, *in, nbr, L0, action, *gout, *gin, gaction, (const float*)workspace);
+    else
+      k_cloth_bwd<1024><<<k.B, k.threads, smem, st>>>(k, *in, nbr, L0, action, *gout, *gin, gaction, (const float*)workspace);
+  }
+  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+}
+
+}  // extern "C"
