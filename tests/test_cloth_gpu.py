@@ -9,11 +9,12 @@ from oracle import cloth as oc
 pytestmark = pytest.mark.gpu
 
 
-def _scene(B, seed, float_stiffness):
+def _scene(B, seed, float_stiffness, substeps=50):
     from unidom_b200.cloth_simulator import ClothSimulator
     conf = oc.ClothConf()
     mask = oc.fold_cloth_mask(conf)
     sim = ClothSimulator(conf, B, None, mask)
+    sim.SUBSTEPS = substeps
     st = sim.reset_jax()
     g = torch.Generator().manual_seed(seed)
     dev = st.x.device
@@ -40,26 +41,32 @@ def _to_oracle(st, dtype=torch.float32):
     return o._replace(stiffness=o.stiffness.to(dtype))
 
 
-@pytest.mark.parametrize("float_stiffness", [False, True])
-def test_cloth_forward_parity(built_lib, float_stiffness):
+@pytest.mark.parametrize("float_stiffness,substeps", [(False, 50), (True, 50), (True, 5)])
+def test_cloth_forward_parity(built_lib, float_stiffness, substeps):
+    """50 substeps = one reference sub-action (chaotic: compared against the oracle's own fp32-vs-fp64
+    floor, SURVEY hard part 2); 5 substeps = teacher-forced window with a tight tolerance."""
     B = 3
-    conf, mask, sim, st, act = _scene(B, 1, float_stiffness)
+    conf, mask, sim, st, act = _scene(B, 1, float_stiffness, substeps)
     out, _ = sim.step_jax(st, act)
     osim = oc.ClothSim(conf, mask)
     with torch.no_grad():
-        ref = oc.step_batch(osim, _to_oracle(st), act.cpu())
-        ref64 = oc.step_batch(oc.ClothSim(conf, mask, torch.float64), _to_oracle(st, torch.float64), act.cpu().double())
+        ref = oc.step_batch(osim, _to_oracle(st), act.cpu(), substeps)
+        ref64 = oc.step_batch(oc.ClothSim(conf, mask, torch.float64), _to_oracle(st, torch.float64),
+                              act.cpu().double(), substeps)
     for k in ("x", "v", "primitive0", "primitive1", "action0", "action1"):
         e = util.rel_err(getattr(out, k), getattr(ref, k))
         fl = util.rel_err(getattr(ref, k), getattr(ref64, k))
         print(f"cloth {k}: cuda-vs-oracle32 {e:.3e}  oracle32-vs-64 {fl:.3e}")
-        assert e < max(1e-4, 5 * fl), (k, e, fl)
+        assert e < (max(1e-4, 5 * fl) if substeps == 50 else max(2e-5, 3 * fl)), (k, e, fl)
 
 
-@pytest.mark.parametrize("float_stiffness", [False, True])
-def test_cloth_backward_parity(built_lib, float_stiffness):
+@pytest.mark.parametrize("float_stiffness,substeps", [(False, 50), (True, 50), (True, 3)])
+def test_cloth_backward_parity(built_lib, float_stiffness, substeps):
+    """The cloth cotangent is re-normalised 8x per substep (norm_grad) on chaotic dynamics, so over 50
+    substeps two correct fp32 implementations only agree to the oracle's fp32-vs-fp64 floor (printed);
+    the 3-substep window is the tight check of the adjoint formulas."""
     B = 2
-    conf, mask, sim, st, act = _scene(B, 2, float_stiffness)
+    conf, mask, sim, st, act = _scene(B, 2, float_stiffness, substeps)
     dev = st.x.device
     g = torch.Generator().manual_seed(3)
     cot = {"x": torch.randn(st.x.shape, generator=g), "v": torch.randn(st.v.shape, generator=g),
@@ -78,14 +85,74 @@ def test_cloth_backward_parity(built_lib, float_stiffness):
 
     got = run(lambda s, a: sim.step_jax(s, a)[0], st, act, lambda t: t.to(dev))
     osim = oc.ClothSim(conf, mask)
-    ref = run(lambda s, a: oc.step_batch(osim, s, a), _to_oracle(st), act.cpu(), lambda t: t)
+    ref = run(lambda s, a: oc.step_batch(osim, s, a, substeps), _to_oracle(st), act.cpu(), lambda t: t)
     osim64 = oc.ClothSim(conf, mask, torch.float64)
-    ref64 = run(lambda s, a: oc.step_batch(osim64, s, a), _to_oracle(st, torch.float64), act.cpu().double(), lambda t: t)
+    ref64 = run(lambda s, a: oc.step_batch(osim64, s, a, substeps), _to_oracle(st, torch.float64),
+                act.cpu().double(), lambda t: t)
+    pert = None
+    if substeps == 50:
+        # sensitivity floor: the oracle's own gradient after perturbing the input positions by 1e-6
+        # (relative) -- a few fp32 ulps decide on which substep a node touches the ground / leaves a clip
+        gp = torch.Generator().manual_seed(11)
+        ost = _to_oracle(st)
+        ost = ost._replace(x=ost.x * (1 + 1e-6 * torch.randn(ost.x.shape, generator=gp)))
+        pert = run(lambda s, a: oc.step_batch(osim, s, a, substeps), ost, act.cpu(), lambda t: t)
     for k in ref:
         e = util.rel_err(got[k], ref[k])
         fl = util.rel_err(ref[k], ref64[k])
-        cs = util.cosine(got[k], ref[k]) if float(ref[k].abs().max()) > 0 else 1.0
-        print(f"cloth grad {k:12s} rel {e:.3e} cos {cs:.6f} | oracle32-vs-64 {fl:.3e} max|ref| {float(ref[k].abs().max()):.3e}")
-        if float(ref[k].abs().max()) > 1e-20:
-            assert cs >= 0.999, (k, cs)
-            assert e < max(1e-3, 20 * fl), (k, e, fl)
+        big = float(ref[k].abs().max()) > 1e-20
+        cs = util.cosine(got[k], ref[k]) if big else 1.0
+        csf = util.cosine(ref[k], ref64[k]) if big else 1.0
+        line = (f"cloth[{substeps}] grad {k:12s} rel {e:.3e} cos {cs:.6f} | oracle32-vs-64 rel {fl:.3e} cos {csf:.6f} "
+                f"max|ref| {float(ref[k].abs().max()):.3e}")
+        if pert is not None and big:
+            fp_, csp = util.rel_err(pert[k], ref[k]), util.cosine(pert[k], ref[k])
+            line += f" | oracle32 under 1e-6 input perturbation rel {fp_:.3e} cos {csp:.6f}"
+            fl, csf = max(fl, fp_), min(csf, csp)
+        print("\n" + line)
+        if big:
+            if substeps == 50:
+                assert cs >= min(0.999, 1 - 3 * (1 - csf)), (k, cs, csf)
+                assert e < max(1e-3, 3 * fl), (k, e, fl)
+            else:
+                assert cs >= 0.99999 and e < 1e-3, (k, cs, e)
+
+
+@pytest.mark.parametrize("substeps", [1, 4])
+def test_cloth_adjoint_window_from_contact_state(built_lib, substeps):
+    """Teacher-forced adjoint windows starting from the oracle's state 44 substeps into a violent
+    sub-action (tests/golden/cloth_contact_state.pt: ground contacts, |v| clipped at max_v, closed
+    gripper): every discrete branch of the step is active, and the window is short enough that both
+    implementations take the same branches."""
+    import os
+    from unidom_b200.cloth_simulator import ClothSimulator, ClothState
+    d = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cloth_contact_state.pt"))
+    conf = oc.ClothConf()
+    mask = oc.fold_cloth_mask(conf)
+    st_o = oc.ClothState(*[d[k][None] for k in oc.ClothState._fields])
+    assert int((st_o.x[0, :, 1] <= 1e-8).sum()) >= 1 and float(st_o.v.abs().max()) >= 1.99
+    act = torch.cat([d["action0"][:3] * 50, d["action0"][3:], d["action1"][:3] * 50, d["action1"][3:]])[None]
+    sim = ClothSimulator(conf, 1, None, mask)
+    sim.SUBSTEPS = substeps
+    st = ClothState(*[t.cuda() for t in st_o])
+    g = torch.Generator().manual_seed(3)
+    cx, cv = torch.randn(st.x.shape, generator=g), torch.randn(st.x.shape, generator=g)
+
+    def run(step, state, action, dev):
+        x = state.x.detach().clone().requires_grad_(True)
+        v = state.v.detach().clone().requires_grad_(True)
+        mu = state.mu.detach().clone().requires_grad_(True)
+        a = action.detach().clone().requires_grad_(True)
+        out = step(state._replace(x=x, v=v, mu=mu), a)
+        L = (out.x * cx.to(dev)).sum() + (out.v * cv.to(dev)).sum()
+        return torch.autograd.grad(L, [x, v, mu, a]), out
+
+    got, o1 = run(lambda s, a: sim.step_jax(s, a)[0], st, act.cuda(), "cuda")
+    osim = oc.ClothSim(conf, mask)
+    ref, o2 = run(lambda s, a: oc.step_batch(osim, s, a, substeps), st_o, act, "cpu")
+    assert util.rel_err(o1.x, o2.x) < 1e-6 and util.rel_err(o1.v, o2.v) < 1e-4
+    for name, a, b in zip(("x", "v", "mu", "action"), got, ref):
+        cs = util.cosine(a, b)
+        e = util.rel_err(a, b)
+        print(f"cloth window[{substeps}] grad {name}: rel {e:.3e} cos {cs:.12f}")
+        assert cs > 0.9999999 and e < 1e-4, (name, cs, e)
