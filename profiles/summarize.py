@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Turn ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
+
+  python profiles/summarize.py launches gpurun_out/launches.csv            > profiles/rNN_launches.md
+  python profiles/summarize.py full gpurun_out/prof_k_p2g.ncu-rep [...]     > profiles/rNN_ncu_full.md
+
+`launches`: per-kernel totals/shares of an `ncu --metrics gpu__time_duration.sum` launch list
+(cold-cache, serialised: compare SHARES with bench.py's live CUDA-event shares, not absolutes).
+`full`: the counters DESIGN.md / north_star ask for, per captured launch of an `ncu --set full` report.
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum",
+    "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum", "smsp__inst_executed_op_global_red.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum", "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+]
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[h]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[h + 1:]:
+        if len(r) <= vi:
+            continue
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        name = r[ki].split("(")[0].split("<")[0]
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    print(f"source: {path}  ({sum(v[0] for v in agg.values())} launches, {tot / 1e6:.2f} ms total device time)\n")
+    print("| kernel | launches | total us | share | avg us |")
+    print("|---|---:|---:|---:|---:|")
+    for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{n}` | {c} | {t / 1e3:.1f} | {t / tot:.3f} | {t / c / 1e3:.1f} |")
+
+
+def full(paths):
+    for path in paths:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        hdr, units = rows[0], rows[1]
+        print(f"### {path}\n")
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            u = dict(zip(hdr, units))
+            print(f"launch `{d.get('Kernel Name', '?')}` grid {d.get('launch__grid_size')} x block {d.get('launch__block_size')}\n")
+            print("| metric | value | unit |")
+            print("|---|---:|---|")
+            for k in WANT:
+                if k in d:
+                    print(f"| {k} | {d[k]} | {u.get(k, '')} |")
+            print()
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2])
+    else:
+        full(sys.argv[2:])
