@@ -58,6 +58,17 @@ def fold_cloth_mask(conf):
 LINKS = [[-1, 0], [1, 0], [0, -1], [0, 1], [-1, -1], [1, -1], [-1, 1], [1, 1]]  # :48
 
 
+def jclip(x, lo=None, hi=None):
+    """jnp.clip = minimum(hi, maximum(lo, x)) (jax/_src/numpy/lax_numpy.py): at a tie with a bound the
+    cotangent is split evenly (lax.max/min JVP), where torch.clamp would pass all of it.  Cloth nodes rest
+    at y == 0 exactly after reset and the idle gripper sits at 1.0 exactly, so ties do occur."""
+    if lo is not None:
+        x = torch.maximum(x, torch.as_tensor(lo, dtype=x.dtype))
+    if hi is not None:
+        x = torch.minimum(x, torch.as_tensor(hi, dtype=x.dtype))
+    return x
+
+
 class ClothNormGrad(torch.autograd.Function):
     """norm_grad (cloth_simulator.py:182-196): identity forward; backward g/|g|, nan_to_num, /mask.sum()."""
 
@@ -123,7 +134,7 @@ class ClothSim:
         v = v - torch.tensor([0.0, c.gravity * c.dt, 0.0], dtype=dtype)
         x_grid = torch.zeros((self.N, self.N, 3), dtype=dtype).index_put((self.idx_i, self.idx_j), x)
         rel = x_grid[self.j_x, self.j_y] - x_grid[self.i_x, self.i_y]
-        cur = torch.clamp((rel ** 2).sum(-1), min=1e-12) ** 0.5
+        cur = jclip((rel ** 2).sum(-1), 1e-12) ** 0.5
         cur = cur.reshape(-1, 8, 1)
         force = state.stiffness * rel.reshape(-1, 8, 3) / cur * (cur - self.original_length) / self.original_length
         force = force * self.ori_len_is_not_0
@@ -132,7 +143,7 @@ class ClothSim:
         fx, fy, fz = force[:, 0], force[:, 1] - c.gravity, force[:, 2]
         # friction (:281-306)
         friction_mask = x[:, 1] <= c.small_num
-        muF = state.mu * torch.clamp(fy, max=0.0) * -1
+        muF = state.mu * jclip(fy, None, 0.0) * -1
         xV, yV = v[:, 0], v[:, 2]
         sV = torch.sqrt(xV ** 2 + yV ** 2 + c.small_num)
         dyn = (friction_mask & (sV > c.small_num)).to(dtype)
@@ -154,10 +165,10 @@ class ClothSim:
         # collision_func is the identity for all shipped tasks (cloth_env.py:239-243)
         x, v = self.primitive_collision(x, v, state.action0, state.primitive0)
         x, v = self.primitive_collision(x, v, state.action1, state.primitive1)
-        ps0 = torch.cat([state.primitive0[:3] + state.action0[:3], state.primitive0[3:]]).clamp(0, 1)
-        ps1 = torch.cat([state.primitive1[:3] + state.action1[:3], state.primitive1[3:]]).clamp(0, 1)
-        x = x.clamp(0, 1)
-        v = v.clamp(-c.max_v, c.max_v)
+        ps0 = jclip(torch.cat([state.primitive0[:3] + state.action0[:3], state.primitive0[3:]]), 0, 1)
+        ps1 = jclip(torch.cat([state.primitive1[:3] + state.action1[:3], state.primitive1[3:]]), 0, 1)
+        x = jclip(x, 0, 1)
+        v = jclip(v, -c.max_v, c.max_v)
         x = x + c.dt * v
         x, v = self.norm_grad(x), self.norm_grad(v)
         ps0, ps1 = self.norm_grad(ps0), self.norm_grad(ps1)
@@ -165,8 +176,8 @@ class ClothSim:
 
     def robot_step(self, state: ClothState, action: torch.Tensor, substeps: int = 50) -> ClothState:
         """:163-180 (50 substeps; the PRNG key split consumes no randomness and is carried as is)."""
-        action0 = torch.cat([action[:3].clamp(-2, 2) / 50.0, action[3:4]])
-        action1 = torch.cat([action[4:7].clamp(-2, 2) / 50.0, action[7:8]])
+        action0 = torch.cat([jclip(action[:3], -2, 2) / 50.0, action[3:4]])
+        action1 = torch.cat([jclip(action[4:7], -2, 2) / 50.0, action[7:8]])
         state = state._replace(action0=action0, action1=action1)
         for _ in range(substeps):
             state = self.step(state)

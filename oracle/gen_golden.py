@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ref_*.npz by running the UNMODIFIED reference sources.
+
+    python oracle/gen_golden.py            # in the build container (reference mounted at /root/reference)
+
+The reference (DaXBench) is Python + JAX; jax/jaxlib are not installable in this image.  This script puts
+`oracle/jaxshim` (a torch-backed stand-in for the jax / optax APIs the path uses) in front of sys.path and
+imports /root/reference/DaXBench/daxbench/core/engine/{mpm_simulator,cloth_simulator,svd_safe_batch}.py and
+primitives/{primitives,box,container}.py AS THEY ARE, then calls the reference's own
+`SimpleMPMSimulator.step_jax` / `ClothSimulator.step_jax` and `jax.grad` through the reference's own
+custom_vjp rules on small seeded scenes.  With a real JAX install (`--real-jax`) the same script runs
+against jax itself.
+
+TEST INFRASTRUCTURE ONLY.  The fixtures (inputs, outputs, cotangents, gradients, conf scalars) travel with
+the repo; /root/reference is never read at test time.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = os.environ.get("UNIDOM_REFERENCE", "/root/reference/DaXBench")
+
+STATE_F = ("x", "v", "C", "F", "J", "friction", "mu", "lamda")
+PRIM_F = ("size", "friction", "softness", "position", "rotation", "v", "w", "action_buffer", "action_scale")
+CLOTH_F = ("x", "v", "primitive0", "primitive1", "action0", "action1", "stiffness", "mu")
+
+
+def load_reference(real_jax):
+    if not real_jax:
+        sys.path.insert(0, os.path.join(HERE, "jaxshim"))
+    sys.path.insert(0, REF)
+    import jax  # noqa: F401
+    from daxbench.core.engine import cloth_simulator, mpm_simulator
+    from daxbench.core.engine.primitives import box, container, primitives
+    return mpm_simulator, cloth_simulator, primitives, box, container
+
+
+def npy(a):
+    return np.asarray(a)
+
+
+# --------------------------------------------------------------------------------------------- MPM
+class MPMConf:
+    """Scalar fields of the reference's per-task DefaultConf (envs/shape_elasto_plastic.py:23-54 etc.)."""
+
+    def __init__(self, jnp, key, n_grid, res, dt, steps, E, nu, ground_friction, n_primitive, gravity=(0, -9.8, 0)):
+        self.seed = 1
+        self.key = key
+        self.n_primitive = n_primitive
+        self.ground_friction = ground_friction
+        self.n_grid, self.steps, self.dt = n_grid, steps, dt
+        self.E, self.nu = E, nu
+        self.res = tuple(res)
+        self.dx, self.inv_dx = 1 / n_grid, float(n_grid)
+        self.p_vol, self.p_rho = (self.dx * 0.5) ** 2, 1
+        self.p_mass = self.p_vol * self.p_rho
+        self.gravity = jnp.array(list(gravity))
+
+
+def mpm_case(mods, name, material, n_prim, pos_control, sdf_kind, steps, seed, cot_scale, ylow=0.02, v_scale=0.3,
+             c_scale=2.0, f_scale=0.05, B=2, grads=True, zero_rot=False):
+    import jax
+    import jax.numpy as jnp
+    mpm, _, prim, box, container = mods
+    rng = np.random.RandomState(seed)
+    conf = MPMConf(jnp, jax.random.PRNGKey(0), n_grid=96, res=(48, 32, 48), dt=2e-4, steps=steps, E=2, nu=0.2,
+                   ground_friction=2, n_primitive=n_prim)
+    prim.set_sdf(box._sdf_batch if sdf_kind == 0 else container._sdf_batch)
+    sim = mpm.SimpleMPMSimulator(conf, B, use_position_control=pos_control)
+    sim.key_global = jax.random.PRNGKey(1)
+    # scene: the reference's own add_box lattice (material != 0) or seeded points (the liquid branch draws
+    # from jax.random, which the shim does not reproduce)
+    if material == 0:
+        size = np.array([0.1, 0.06, 0.08], np.float32)
+        n_pts = int(np.prod(size.astype(np.float64)) * conf.n_grid ** 3)
+        pts = (rng.uniform(size=(n_pts, 3)).astype(np.float32) * 2 - 1) * (np.float32(0.5) * size) \
+            + np.array([0.25, ylow, 0.25], np.float32)
+        state = sim.add_box_from_points(conf, None, jnp.array(pts), hardness=1.0, material=0)
+    else:
+        state = sim.add_box(conf=conf, state=None, hardness=1.0, size=[0.1, 0.06, 0.08], init_pos=[0.25, ylow, 0.25],
+                            z_rotation_angle=0, material=material, density=1)
+    prims = []
+    if sdf_kind == 0:
+        specs = [(0.9, [0.015, 0.06, 0.015], [0.25, 0.01, 0.205]), (0.5, [0.02, 0.03, 0.01], [0.29, 0.02, 0.27])]
+    else:  # bowls: size = (r, h, t)
+        specs = [(0.9, [0.06, 0.02, 0.004], [0.25, 0.06, 0.25]), (0.5, [0.04, 0.01, 0.004], [0.29, 0.05, 0.27])]
+    for q in range(n_prim):
+        fr, size, pos = specs[q]
+        p = prim.create_primitive(conf, friction=fr, softness=666, color=[0.5, 0.5, 0.5], size=size, init_pos=pos)
+        prims.append(p._replace(action_scale=p.action_scale * 0.012))
+    state = state._replace(primitives=prims)
+    state = sim.reset_jax(state)
+    n = state.x.shape[1]
+    f32 = np.float32
+    x = npy(state.x) + (rng.randn(B, n, 3) * 1e-3).astype(f32)
+    v = (rng.randn(B, n, 3) * v_scale).astype(f32)
+    Cm = (rng.randn(B, n, 3, 3) * c_scale).astype(f32)
+    F = (np.eye(3, dtype=f32)[None, None] + f_scale * rng.randn(B, n, 3, 3)).astype(f32)
+    state = state._replace(x=jnp.array(x), v=jnp.array(v), C=jnp.array(Cm), F=jnp.array(F))
+    action = rng.rand(B, 6 * n_prim).astype(f32) * 2.4 - 1.2          # some entries beyond the [-1, 1] clip
+    action.reshape(B, n_prim, 6)[:, :, 3:] *= 0.0 if zero_rot else 0.3
+    action = jnp.array(action)
+
+    out = {"material": npy(sim.material).astype(np.int32), "h": npy(sim.h).astype(np.float32), "action": npy(action),
+           "conf": np.array([conf.n_grid, *conf.res, conf.steps, n_prim, int(pos_control), sdf_kind], np.int64),
+           "conf_f": np.array([conf.dt, conf.E, conf.nu, conf.ground_friction, *npy(conf.gravity)], np.float64)}
+    for k in STATE_F:
+        out["in_" + k] = npy(getattr(state, k))
+    for q in range(n_prim):
+        for k in PRIM_F:
+            out[f"in_p{q}_{k}"] = npy(getattr(state.primitives[q], k)).astype(np.float32)
+
+    new_state, _ = sim.step_jax(state, action)
+    for k in STATE_F:
+        out["out_" + k] = npy(getattr(new_state, k))
+    for q in range(n_prim):
+        for k in PRIM_F:
+            out[f"out_p{q}_{k}"] = npy(getattr(new_state.primitives[q], k)).astype(np.float32)
+
+    if grads:
+        S = steps
+        cot = {"x": rng.randn(B, n, 3), "v": rng.randn(B, n, 3) * 0.1, "C": rng.randn(B, n, 3, 3) * 1e-3,
+               "F": rng.randn(B, n, 3, 3) * 0.1}
+        for q in range(n_prim):
+            cot[f"p{q}_position"] = rng.randn(B, S, 3)
+            cot[f"p{q}_rotation"] = rng.randn(B, S, 4)
+        cot = {k: (a * cot_scale).astype(f32) for k, a in cot.items()}
+        for k, a in cot.items():
+            out["cot_" + k] = a
+
+        def loss(inp):
+            st, act = inp
+            ns, _ = sim.step_jax(st, act)
+            L = 0.0
+            for k in ("x", "v", "C", "F"):
+                L = L + (getattr(ns, k) * jnp.array(cot[k])).sum()
+            for q in range(n_prim):
+                L = L + (ns.primitives[q].position * jnp.array(cot[f"p{q}_position"])).sum()
+                L = L + (ns.primitives[q].rotation * jnp.array(cot[f"p{q}_rotation"])).sum()
+            return L
+
+        g_state, g_action = jax.grad(loss, allow_int=True)((state, action))
+        out["g_action"] = npy(g_action)
+        for k in ("x", "v", "C", "F", "friction", "mu", "lamda"):
+            out["g_" + k] = npy(getattr(g_state, k))
+        for q in range(n_prim):
+            for k in ("size", "friction", "position", "rotation", "action_scale"):
+                out[f"g_p{q}_{k}"] = npy(getattr(g_state.primitives[q], k)).astype(np.float32)
+    path = os.path.join(GOLD, f"ref_mpm_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: n={n} B={B} S={steps}  max|out_x-in_x|={np.abs(out['out_x'] - out['in_x']).max():.3e}"
+          + (f"  |g_x|max={np.abs(out['g_x']).max():.3e} |g_action|max={np.abs(out['g_action']).max():.3e}" if grads else ""))
+
+
+# ------------------------------------------------------------------------------------------- cloth
+class ClothConf:
+    """envs/fold_cloth3_env.py:18-37."""
+    N = 80
+    cell_size = 1.0 / N
+    gravity = 0.5
+    stiffness = 900
+    damping = 2
+    dt = 2e-3
+    max_v = 2.
+    small_num = 1e-8
+    mu = 0.5
+    seed = 1
+    size = int(N / 5.0)
+    mem_saving_level = 2
+
+
+def fold_cloth_mask(conf):
+    """envs/fold_cloth3_env.py:51-56."""
+    import jax.numpy as jnp
+    N, size = conf.N, conf.size
+    cloth_mask = jnp.zeros((N, N))
+    cloth_mask = cloth_mask.at[size * 2:size * 3, size * 2:size * 4].set(1)
+    return cloth_mask
+
+
+def _closure_vars(fn):
+    return dict(zip(fn.__code__.co_freevars, [c.cell_contents for c in fn.__closure__]))
+
+
+def cloth_inner_step(sim):
+    """The reference's per-substep `step_wrapper` (cloth_simulator.py:228-255), fished out of the closures of
+    `sim.step_jax` (vmap -> robot_step_wrapper -> robot_step) without touching the source: robot_step hard-codes
+    50 substeps (:176), and 50 chaotic substeps are too long a window for tight parity."""
+    f = _closure_vars(sim.step_jax)["f"]                   # the function vmap wraps
+    robot_step = _closure_vars(f.fun)["robot_step"]
+    return _closure_vars(robot_step)["step_wrapper"]
+
+
+def cloth_case(mods, name, float_stiffness, seed, from_reset, B=2, n_calls=1, grads=True, window=0, contact=False):
+    import jax
+    import jax.numpy as jnp
+    _, cl, *_ = mods
+    rng = np.random.RandomState(seed)
+    conf = ClothConf()
+    mask = fold_cloth_mask(conf)
+    sim = cl.ClothSimulator(conf, B, lambda x, v, i, j: v, mask)      # identity collision (cloth_env.py:239-243)
+    st = sim.reset_jax()
+    f32 = np.float32
+    P = st.x.shape[1]
+    if not from_reset:
+        x = npy(st.x) + 0.002 * rng.randn(B, P, 3).astype(f32)
+        lift = (np.abs(x[..., 1]) * 3 + 0.01 * rng.rand(B, P)) * (rng.rand(B, P) > 0.5)
+        x[..., 1] = lift
+        v = 0.05 * rng.randn(B, P, 3).astype(f32)
+        p0 = np.concatenate([x[:, 100], np.full((B, 1), 0.02)], axis=1).astype(f32)
+        p1 = np.concatenate([x[:, 300] + 0.004, np.full((B, 1), 0.015)], axis=1).astype(f32)
+        st = st._replace(x=jnp.array(x.astype(f32)), v=jnp.array(v), primitive0=jnp.array(p0), primitive1=jnp.array(p1))
+    if float_stiffness:
+        st = st._replace(stiffness=jnp.array((900.0 + 300 * rng.rand(B)).astype(f32)))
+    st = st._replace(mu=jnp.array((0.3 + 0.4 * rng.rand(B)).astype(f32)))
+    acts = np.array([[0.3, 0.5, -0.2, 0.0, -0.1, 0.2, 0.4, 0.3], [2.6, -0.4, 0.1, 1.0, 0.0, 0.0, 0.0, 0.0],
+                     [0.0, 0.06, 0.0, 0.2, 0.5, 0.1, -3.0, 0.0]], f32)[:B]
+    if from_reset:   # grab a corner node and lift it (a pick-and-place approach phase, suction 1 then 0)
+        x0 = npy(st.x)
+        p0 = np.concatenate([x0[:, 0], np.full((B, 1), 0.01)], axis=1).astype(f32)
+        st = st._replace(primitive0=jnp.array(p0))
+        acts = np.array([[0.1, 0.6, 0.1, 0.0, 0, 0, 0, 1.0], [0.0, 0.8, -0.2, 0.0, 0, 0, 0, 1.0]], f32)[:B]
+    if contact:     # the oracle's state 44 substeps into a violent sub-action (ground contacts, |v| = max_v, closed gripper)
+        import torch
+        cs = torch.load(os.path.join(GOLD, "cloth_contact_state.pt"))
+        B = 1
+        st = st._replace(**{k: jnp.array(cs[k][None].numpy()) for k in ("x", "v", "primitive0", "primitive1", "mu")})
+        st = jax.tree_util.tree_map(lambda l: l[:1], st)
+        if float_stiffness:
+            st = st._replace(stiffness=jnp.array(cs["stiffness"][None].numpy().astype(f32)))
+        acts = np.concatenate([cs["action0"][:3].numpy() * 50, cs["action0"][3:].numpy(),
+                               cs["action1"][:3].numpy() * 50, cs["action1"][3:].numpy()]).astype(f32)[None]
+    action = jnp.array(acts)
+    out = {"action": npy(action), "mask": npy(mask).astype(np.int32), "n_calls": np.array(n_calls),
+           "window": np.array(window), "stiffness_is_float": np.array(int(float_stiffness))}
+    for k in CLOTH_F:
+        out["in_" + k] = npy(getattr(st, k))
+
+    inner = cloth_inner_step(sim) if window else None
+
+    def run_window_env(s, action):
+        # robot_step's prologue (cloth_simulator.py:168-169), then `window` substeps of the reference's step_wrapper
+        action0 = action.at[:3].set(action[:3].clip(-2, 2) / 50.)[:4]
+        action1 = action.at[4:7].set(action[4:7].clip(-2, 2) / 50.)[4:8]
+        s = s._replace(action0=action0, action1=action1)
+        for i in range(window):
+            s = inner(i, s)
+        return s
+
+    def run(s, a):
+        if window:
+            return jax.vmap(run_window_env)(s, a)
+        for _ in range(n_calls):
+            s, _ = sim.step_jax(s, a)
+        return s
+
+    ns = run(st, action)
+    for k in CLOTH_F:
+        out["out_" + k] = npy(getattr(ns, k))
+    if grads:
+        cot = {"x": rng.randn(B, P, 3).astype(f32), "v": rng.randn(B, P, 3).astype(f32),
+               "primitive0": rng.randn(B, 4).astype(f32), "primitive1": rng.randn(B, 4).astype(f32)}
+        for k, a in cot.items():
+            out["cot_" + k] = a
+
+        def loss(inp):
+            s, a = inp
+            o = run(s, a)
+            return sum((getattr(o, k) * jnp.array(cot[k])).sum() for k in cot)
+
+        gs, ga = jax.grad(loss, allow_int=True)((st, action))
+        out["g_action"] = npy(ga)
+        for k in ("x", "v", "primitive0", "primitive1", "mu") + (("stiffness",) if float_stiffness else ()):
+            out["g_" + k] = npy(getattr(gs, k))
+    path = os.path.join(GOLD, f"ref_cloth_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: P={P} B={B} calls={n_calls}  max|dx|={np.abs(out['out_x'] - out['in_x']).max():.3e}"
+          + (f"  |g_x|max={np.abs(out['g_x']).max():.3e} |g_action|max={np.abs(out['g_action']).max():.3e}" if grads else ""))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--real-jax", action="store_true")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    mods = load_reference(args.real_jax)
+    os.makedirs(GOLD, exist_ok=True)
+    cases = {
+        # name: (material, n_prim, pos_control, sdf_kind, steps, seed, cot_scale, kwargs)
+        "plastic_box": lambda: mpm_case(mods, "plastic_box", 2, 1, False, 0, 4, 11, 1e-3),
+        "elastic_2box": lambda: mpm_case(mods, "elastic_2box", 1, 2, False, 0, 4, 12, 1e-3),
+        "liquid_bowl": lambda: mpm_case(mods, "liquid_bowl", 0, 2, False, 1, 4, 13, 1e-3, ylow=0.045, v_scale=0.05,
+                                        c_scale=1.0, f_scale=0.02),
+        "elastic_poscontrol": lambda: mpm_case(mods, "elastic_poscontrol", 1, 1, True, 0, 4, 14, 1e-3),
+        "plastic_normgrad": lambda: mpm_case(mods, "plastic_normgrad", 2, 1, False, 0, 4, 15, 10.0),
+        "plastic_zero_rot": lambda: mpm_case(mods, "plastic_zero_rot", 2, 1, False, 0, 3, 17, 1e-3, zero_rot=True),
+        "plastic_fwd16": lambda: mpm_case(mods, "plastic_fwd16", 2, 1, False, 0, 16, 16, 1e-3, grads=False),
+        "cloth_lifted_int": lambda: cloth_case(mods, "lifted_int", False, 21, False),
+        "cloth_lifted_float": lambda: cloth_case(mods, "lifted_float", True, 22, False),
+        "cloth_reset_grab": lambda: cloth_case(mods, "reset_grab", True, 23, True),
+        "cloth_w1_reset": lambda: cloth_case(mods, "w1_reset", True, 24, True, window=1),
+        "cloth_w3_reset": lambda: cloth_case(mods, "w3_reset", False, 25, True, window=3),
+        "cloth_w5_lifted": lambda: cloth_case(mods, "w5_lifted", True, 26, False, window=5),
+        "cloth_w1_contact": lambda: cloth_case(mods, "w1_contact", True, 27, False, window=1, contact=True),
+        "cloth_w4_contact": lambda: cloth_case(mods, "w4_contact", False, 28, False, window=4, contact=True),
+    }
+    for name, fn in cases.items():
+        if args.only and args.only not in name:
+            continue
+        fn()
+
+
+if __name__ == "__main__":
+    main()

@@ -150,7 +150,7 @@ class Simulator:
         mu = torch.where(liquid, torch.zeros((), dtype=dtype), mu)
         la = torch.where(liquid, torch.ones((), dtype=dtype), la)
         U, sig, V = svd(F_)
-        sig_c = sig.clamp(1 - 2.5e-2 * 10, 1 + 4.5e-3 * 100)
+        sig_c = P.jclip(sig, 1 - 2.5e-2 * 10, 1 + 4.5e-3 * 100)
         sig = torch.where(plastic[:, None], sig_c, sig)
         J = sig.prod(-1)[:, None, None]
         sig_m = eye[None] * sig[..., None]
@@ -197,7 +197,7 @@ class Simulator:
         gi_eps = gi.to(dtype) * 1e-30
         vit = grid_v - lin[..., None] * normal.reshape(1, 1, 1, 3) - gi_eps
         lit = torch.sqrt(((vit + 1e-12) ** 2).sum(-1))
-        grid_v_ = torch.clamp(1.0 + state.friction * lin[..., None] / lit[..., None], min=0.0) * (vit + gi_eps)
+        grid_v_ = P.jclip(1.0 + state.friction * lin[..., None] / lit[..., None], 0.0) * (vit + gi_eps)
         grid_v_ = torch.cat([grid_v_[..., 0:1], torch.zeros_like(grid_v_[..., 1:2]), grid_v_[..., 2:3]], dim=-1)
         friction_mask = (gi[..., 1] < 3)
         fric_speed_mask = grid_v[..., 1] <= 0
@@ -244,7 +244,7 @@ class Simulator:
         """mpm_simulator.py:413-429 (returns the carry; the reference returns it twice)."""
         c = self.conf
         state, action = self._norm_grad_in(state, action)
-        action = action.clamp(-1, 1)
+        action = P.jclip(action, -1, 1)
         prims = [P.set_action(c.steps, action[i * 6:(i + 1) * 6], state.primitives[i])
                  for i in range(c.n_primitive)] + list(state.primitives[c.n_primitive:])
         state = state._replace(primitives=prims)

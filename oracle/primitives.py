@@ -54,6 +54,16 @@ def create_primitive(steps, friction, softness, color, size, init_pos, dtype=tor
     )
 
 
+def jclip(x, lo=None, hi=None):
+    """jnp.clip = minimum(hi, maximum(lo, x)): a tie with a bound passes HALF the cotangent (lax.max/min JVP);
+    torch.clamp would pass all of it."""
+    if lo is not None:
+        x = torch.maximum(x, torch.as_tensor(lo, dtype=x.dtype))
+    if hi is not None:
+        x = torch.minimum(x, torch.as_tensor(hi, dtype=x.dtype))
+    return x
+
+
 def length(x):
     """primitives.py:68-69: sqrt(x.x + 1e-12) over the last axis."""
     return torch.sqrt((x * x).sum(-1) + 1e-12)
@@ -67,12 +77,14 @@ def qmul(q, r):
     y = t[0, 2] + t[1, 3] + t[2, 0] - t[3, 1]
     z = t[0, 3] - t[1, 2] + t[2, 1] + t[3, 0]
     out = torch.stack([w, x, y, z])
-    return out / torch.clamp(torch.sqrt(out.dot(out)), min=1e-12)
+    return out / jclip(torch.sqrt(out.dot(out)), 1e-12)
 
 
 def w2quat(axis_angle):
     """primitives.py:84-92."""
-    w = torch.linalg.norm(axis_angle) + 1e-12
+    # jnp.linalg.norm = sqrt(sum(x*x)): NaN cotangent at exactly 0 (zero angular velocity), scrubbed later by
+    # norm_grad's nan_to_num -- torch.linalg.norm would return a finite subgradient instead
+    w = torch.sqrt((axis_angle * axis_angle).sum()) + 1e-12
     v = (axis_angle / w) * torch.sin(w / 2)
     return torch.cat([torch.cos(w / 2).reshape(1), v[:3]])
 
@@ -95,13 +107,13 @@ def inv_trans(pos, position, rotation):
 def sdf_box(size, p):
     """box.py:6-18."""
     q = torch.abs(p) - size.reshape(3)
-    qc = torch.clamp(q, min=0.0)
+    qc = jclip(q, 0.0)
     out = length(qc)
     # NOTE box.py:11 clips q in place *before* the max -- the "inside" term
     # uses the clipped q, so tmp is max(clipped q) clipped to <= 0, i.e. 0.
     tmp = torch.where(qc[..., 1] > qc[..., 2], qc[..., 1], qc[..., 2])
     tmp = torch.where(qc[..., 0] > tmp, qc[..., 0], tmp)
-    tmp = torch.clamp(tmp, max=0.0)
+    tmp = jclip(tmp, None, 0.0)
     return out + tmp
 
 
@@ -164,12 +176,12 @@ def collider_v(f, grid_pos, dt, state):
 def collide(f, grid_pos, v_out, dt, state, kind):
     """primitives.py:156-182.  grid_pos, v_out: (...,3)."""
     dist = sdf(f, grid_pos, state, kind)
-    influence = torch.clamp(torch.exp(-dist * state.softness), max=1.0)[..., None]
+    influence = jclip(torch.exp(-dist * state.softness), None, 1.0)[..., None]
     D = normal(f, grid_pos, state, kind)
     cv = collider_v(f, grid_pos, dt, state)
     input_v = v_out - cv
     normal_component = (input_v * D).sum(-1, keepdim=True)
-    grid_v_t = input_v - torch.clamp(normal_component, max=0.0) * D
+    grid_v_t = input_v - jclip(normal_component, None, 0.0) * D
     grid_v_t_norm = length(grid_v_t)[..., None]
     grid_v_t_friction = grid_v_t / grid_v_t_norm * torch.clamp(
         grid_v_t_norm + normal_component * state.friction, min=1e-12)
@@ -195,7 +207,7 @@ def forward_kinematics(f, state):
         position = torch.cat([position[:f + 1], new_p[None], position[f + 2:]], dim=0)
         new_r = qmul(w2quat(state.w[f]), state.rotation[f])
         rotation = torch.cat([rotation[:f + 1], new_r[None], rotation[f + 2:]], dim=0)
-    position = torch.clamp(position, -2, 2)
+    position = jclip(position, -2, 2)
     return state._replace(position=position, rotation=rotation)
 
 

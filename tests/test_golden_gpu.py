@@ -1,0 +1,103 @@
+"""GPU: the CUDA path (through the C ABI) against golden vectors produced by the UNMODIFIED reference sources
+run under oracle/jaxshim (oracle/gen_golden.py).  No oracle on this path: fixture in, kernels, fixture out."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+MPM_CASES = sorted(os.path.basename(p)[len("ref_mpm_"):-4] for p in glob.glob(os.path.join(util.GOLD, "ref_mpm_*.npz")))
+CLOTH_CASES = sorted(os.path.basename(p)[len("ref_cloth_"):-4] for p in glob.glob(os.path.join(util.GOLD, "ref_cloth_*.npz")))
+
+
+@pytest.mark.parametrize("name", MPM_CASES)
+def test_mpm_cuda_matches_reference_golden(built_lib, name):
+    from unidom_b200.mpm_simulator import SimpleMPMSimulator
+    conf, d = util.golden_mpm(name)
+    B = d["in_x"].shape[0]
+    sim = SimpleMPMSimulator(conf, B, use_position_control=conf.use_position_control)
+    st = util.golden_product_state(sim, conf, d)
+    dev = st.x.device
+    act = d["action"].to(dev)
+    has_grads = "g_x" in d
+    if has_grads:
+        got, out = util.golden_mpm_grads(lambda s, a: sim.step_jax(s, a)[0], st, act, d, conf.n_primitive,
+                                         lambda t: t.to(dev))
+    else:
+        out, _ = sim.step_jax(st, act)
+    bowl = conf.sdf_kind == 1
+    for k in ("x", "v", "C", "F", "J"):
+        e = util.rel_err(getattr(out, k), d["out_" + k])
+        print(f"{name} state {k}: cuda-vs-reference rel {e:.3e}")
+        assert e < (2e-3 if bowl else 1e-4), (k, e)      # north_star: state rtol 1e-4 (bowl: see test_oracle_golden)
+    for q in range(conf.n_primitive):
+        for k in ("position", "rotation", "v", "w", "action_buffer"):
+            e = util.rel_err(getattr(out.primitives[q], k), d[f"out_p{q}_{k}"])
+            assert e < 1e-5, (q, k, e)
+    if not has_grads:
+        return
+    for k, g in got.items():
+        ref = d["g_" + k]
+        if ("in_" + k) in d and not d["in_" + k].is_floating_point():
+            continue      # integer leaf in the reference: no gradient there
+        if float(ref.abs().max()) < 1e-20:
+            assert float(g.abs().max()) < 1e-10, k
+            continue
+        e, cs = util.rel_err(g, ref), util.cosine(g, ref)
+        print(f"{name} grad {k:16s}: rel {e:.3e} cos {cs:.8f} max|ref| {float(ref.abs().max()):.3e}")
+        assert cs >= 0.999, (k, cs)                       # north_star: gradients rtol 1e-3, cosine >= 0.999
+        assert e < (1e-2 if bowl else 3e-3), (k, e)
+
+
+@pytest.mark.parametrize("name", CLOTH_CASES)
+def test_cloth_cuda_matches_reference_golden(built_lib, name):
+    from oracle import cloth as oc      # conf + mask helpers only (host-side scene description)
+    from unidom_b200.cloth_simulator import ClothSimulator, ClothState
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in np.load(os.path.join(util.GOLD, f"ref_cloth_{name}.npz")).items()}
+    conf = oc.ClothConf()
+    mask = oc.fold_cloth_mask(conf)
+    B = d["in_x"].shape[0]
+    window = int(d["window"])
+    sim = ClothSimulator(conf, B, None, mask)
+    sim.SUBSTEPS = window if window else 50
+    z2 = torch.zeros((B, 2), dtype=torch.int32)
+    st = ClothState(x=d["in_x"], v=d["in_v"], primitive0=d["in_primitive0"], primitive1=d["in_primitive1"],
+                    action0=d["in_action0"], action1=d["in_action1"], key=z2, cur_step=z2[:, 0],
+                    stiffness=d["in_stiffness"], mu=d["in_mu"])
+    st = ClothState(*[t.cuda() for t in st])
+    names = ["x", "v", "primitive0", "primitive1", "mu"] + (["stiffness"] if int(d["stiffness_is_float"]) else [])
+    req = {k: getattr(st, k).detach().clone().requires_grad_(True) for k in names}
+    a = d["action"].cuda().requires_grad_(True)
+    s = st._replace(**req)
+    for _ in range(int(d["n_calls"])):
+        s, _ = sim.step_jax(s, a)
+    for k in ("x", "v", "primitive0", "primitive1", "action0", "action1"):
+        e = util.rel_err(getattr(s, k), d["out_" + k])
+        ea = float((getattr(s, k).detach().cpu() - d["out_" + k]).abs().max())
+        print(f"cloth {name} state {k}: cuda-vs-reference rel {e:.3e} abs {ea:.3e}")
+        # 5e-7 absolute floor: at rest the spring force k*(cur-L0)/L0 is rounding noise amplified by k = 900..1200
+        # (|dv| ~ 2e-7 per substep between any two fp32 evaluation orders)
+        assert e < ((1e-5 if window <= 3 else 2e-4) if window else 3e-2) or ea < 5e-7, (k, e, ea)
+    L = sum((getattr(s, k) * d["cot_" + k].cuda()).sum() for k in ("x", "v", "primitive0", "primitive1"))
+    gr = torch.autograd.grad(L, [req[k] for k in names] + [a], allow_unused=True)
+    for k, g in zip(names + ["action"], gr):
+        ref = d["g_" + k]
+        g = g if g is not None else torch.zeros_like(ref)
+        if float(ref.abs().max()) < 1e-20:
+            assert float(g.abs().max()) < 1e-10, k
+            continue
+        e, cs = util.rel_err(g, ref), util.cosine(g, ref)
+        print(f"cloth {name} grad {k:12s}: rel {e:.3e} cos {cs:.10f} max|ref| {float(ref.abs().max()):.3e}")
+        if window:
+            # from the reset state the in-plane velocities are that rounding noise divided by sV = 1e-4 in the
+            # friction term, which conditions the adjoint at ~1e-3 relative (oracle-vs-reference on identical
+            # torch op order: 4e-7)
+            rest = "reset" in name
+            assert cs > (0.99999 if window <= 3 else 0.999) and e < (1e-3 if (window <= 3 and not rest) else 1e-2), (k, e, cs)
+        else:
+            assert cs > 0.9, (k, e, cs)      # 50 chaotic substeps with 8 renormalisations each: see DESIGN.md

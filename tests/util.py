@@ -58,3 +58,86 @@ def mini_plasticine(sim, B, seed=0, density=1.0, v_scale=0.3, material=2, ylow=0
     F = (torch.eye(3)[None, None] + f_scale * torch.randn((B, n, 3, 3), generator=g)).to(dev)
     x = st.x + (torch.randn((B, n, 3), generator=g) * 1e-3).to(dev)
     return st._replace(x=x, v=v, C=Cm, F=F)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Golden fixtures produced by oracle/gen_golden.py (the unmodified reference sources under oracle/jaxshim)
+# ---------------------------------------------------------------------------------------------------
+import os
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STATE_F = ("x", "v", "C", "F", "J", "friction", "mu", "lamda")
+PRIM_F = ("size", "friction", "softness", "position", "rotation", "v", "w", "action_buffer", "action_scale")
+
+
+def golden_mpm(name):
+    """-> (conf for the product, dict of torch tensors) from tests/golden/ref_mpm_<name>.npz."""
+    from unidom_b200 import confs
+    d = {k: v for k, v in np.load(os.path.join(GOLD, f"ref_mpm_{name}.npz")).items()}
+    n_grid, rx, ry, rz, steps, n_prim, pos_control, sdf_kind = [int(v) for v in d["conf"]]
+    dt, E, nu, gf, g0, g1, g2 = [float(v) for v in d["conf_f"]]
+    conf = confs.MPMConf(n_grid=n_grid, res=(rx, ry, rz), dt=dt, steps=steps, E=E, nu=nu, ground_friction=gf,
+                         gravity=(g0, g1, g2), n_primitive=n_prim, sdf_kind=sdf_kind,
+                         use_position_control=bool(pos_control))
+    return conf, {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in d.items()}
+
+
+def golden_oracle_state(conf, d, prefix="in_", dtype=torch.float32):
+    """oracle MPMState (batched) from a golden dict."""
+    B = d[prefix + "x"].shape[0]
+    prims = []
+    for q in range(conf.n_primitive):
+        f = {k: d[f"{prefix}p{q}_{k}"].to(dtype) for k in PRIM_F}
+        prims.append(oP.PrimitiveState(
+            size=f["size"], dim=torch.full((B, 1), 3, dtype=torch.int32), friction=f["friction"], softness=f["softness"],
+            color=torch.full((B, 3), 0.5, dtype=dtype), position=f["position"], rotation=f["rotation"], v=f["v"], w=f["w"],
+            xyz_limit=torch.tensor([[0.0, 1.0]] * 3, dtype=dtype)[None].repeat(B, 1, 1), action_buffer=f["action_buffer"],
+            action_scale=f["action_scale"], min_dist=torch.zeros(B, dtype=torch.int32),
+            dist_norm=torch.zeros(B, dtype=torch.int32)))
+    vals = {k: d[prefix + k].to(dtype) for k in STATE_F}
+    return omp.MPMState(cur_step=torch.zeros(B, dtype=torch.int32), primitives=prims,
+                        key=torch.zeros((B, 2), dtype=torch.int32), **vals)
+
+
+def golden_product_state(sim, conf, d, device="cuda"):
+    """product MPMState on `device` from a golden dict; also sets sim.material / sim.h."""
+    from unidom_b200.mpm_simulator import MPMState, PrimitiveState
+    ost = golden_oracle_state(conf, d)
+    sim.material, sim.h = d["material"].to(torch.int32), d["h"].to(torch.float32)
+    sim.n_particles = ost.x.shape[1]
+    sim._material_dev = sim.material.to(device).contiguous()
+    sim._h_dev = sim.h.to(device).contiguous()
+    prims = [PrimitiveState(*[t.to(device) for t in p]) for p in ost.primitives]
+    vals = {k: getattr(ost, k).to(device) for k in ost._fields if k != "primitives"}
+    return MPMState(primitives=prims, **vals)
+
+
+MPM_GRAD_LEAVES = ("x", "v", "C", "F", "friction", "mu", "lamda")
+MPM_PRIM_GRAD_LEAVES = ("size", "friction", "position", "rotation", "action_scale")
+
+
+def golden_mpm_grads(step_fn, state, action, d, n_prim, to_dev):
+    """d L / d (input leaves, action) for L = sum(out_leaf * cot_leaf) with the golden cotangents."""
+    req = {k: getattr(state, k).detach().clone().requires_grad_(True) for k in MPM_GRAD_LEAVES}
+    prims = []
+    for q, p in enumerate(state.primitives):
+        if q < n_prim:
+            pr = {k: getattr(p, k).detach().clone().requires_grad_(True) for k in MPM_PRIM_GRAD_LEAVES}
+            req.update({f"p{q}_{k}": v for k, v in pr.items()})
+            p = p._replace(**pr)
+        prims.append(p)
+    st = state._replace(primitives=prims, **{k: req[k] for k in MPM_GRAD_LEAVES})
+    a = action.detach().clone().requires_grad_(True)
+    out = step_fn(st, a)
+    L = 0
+    for k in ("x", "v", "C", "F"):
+        L = L + (getattr(out, k) * to_dev(d["cot_" + k]).to(getattr(out, k).dtype)).sum()
+    for q in range(n_prim):
+        for k in ("position", "rotation"):
+            t = getattr(out.primitives[q], k)
+            L = L + (t * to_dev(d[f"cot_p{q}_{k}"]).to(t.dtype)).sum()
+    names = list(req.keys())
+    grads = torch.autograd.grad(L, [req[k] for k in names] + [a], allow_unused=True)
+    res = {k: (g if g is not None else torch.zeros_like(req[k])) for k, g in zip(names, grads[:-1])}
+    res["action"] = grads[-1]
+    return res, out

@@ -39,6 +39,12 @@ static bool cloth_fold(const ud_cloth_params* p, ClothK* k) {
 }
 
 __device__ __forceinline__ float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
+// d clip(a, lo, hi) / d a with jnp.clip's tie rule: clip = minimum(hi, maximum(lo, a)) and lax.max/min split the
+// cotangent evenly at a tie (a == lo or a == hi).  Nodes rest at y == 0 exactly after reset and the idle
+// gripper sits at 1.0 exactly, so ties are hit in practice.
+__device__ __forceinline__ float clip_grad(float a, float lo, float hi) {
+  return (a > lo && a < hi) ? 1.f : ((a == lo || a == hi) ? 0.5f : 0.f);
+}
 __device__ __forceinline__ float nan0(float a) {
   if (a != a) return 0.f;
   if (isinf(a)) return a > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
@@ -349,15 +355,15 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float gvc = gv[c] + k.dt * gx[c];
-      gv2[c] = (f.v2[c] >= -k.max_v && f.v2[c] <= k.max_v) ? gvc : 0.f;
-      gx2[c] = (f.x2[c] >= 0.f && f.x2[c] <= 1.f) ? gx[c] : 0.f;
+      gv2[c] = clip_grad(f.v2[c], -k.max_v, k.max_v) * gvc;
+      gx2[c] = clip_grad(f.x2[c], 0.f, 1.f) * gx[c];
     }
     // ---- (3) grippers advance: ps' = clip(ps + [a,0], 0, 1)
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float u0 = ps0[c] + (c < 3 ? a0[c] : 0.f), u1 = ps1[c] + (c < 3 ? a1[c] : 0.f);
-      gps0[c] = (u0 >= 0.f && u0 <= 1.f) ? gps0[c] : 0.f;
-      gps1[c] = (u1 >= 0.f && u1 <= 1.f) ? gps1[c] : 0.f;
+      gps0[c] = clip_grad(u0, 0.f, 1.f) * gps0[c];
+      gps1[c] = clip_grad(u1, 0.f, 1.f) * gps1[c];
       if (c < 3) {
         ga0u[c] += gps0[c];
         ga1u[c] += gps1[c];
@@ -443,7 +449,7 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
       }
       // muF = -mu * min(fr1, 0)
       if (live) gmup += gmuF * (-fminf(f.fr[1], 0.f));
-      if (f.fr[1] <= 0.f) gfr[1] += gmuF * (-mu);
+      gfr[1] += (f.fr[1] < 0.f ? 1.f : (f.fr[1] == 0.f ? 0.5f : 0.f)) * gmuF * (-mu);
     }
     // ---- (8) spring forces: f_c = (stiff/L0) rel_c (1 - L0/cur)
     float gxi[3] = {gxs[0], gxs[1], gxs[2]};
@@ -519,8 +525,8 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
       float* ga = gaction + (size_t)env * 8;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        ga[c] = (a[c] >= -2.f && a[c] <= 2.f) ? ga0[c] / 50.f : 0.f;
-        ga[4 + c] = (a[4 + c] >= -2.f && a[4 + c] <= 2.f) ? ga1[c] / 50.f : 0.f;
+        ga[c] = clip_grad(a[c], -2.f, 2.f) * (ga0[c] / 50.f);
+        ga[4 + c] = clip_grad(a[4 + c], -2.f, 2.f) * (ga1[c] / 50.f);
       }
       ga[3] = ga0[3];
       ga[7] = ga1[3];

@@ -32,6 +32,10 @@ template <class T> UD_DEV void w2quat(const T aa[3], T out[4]) {
 }
 
 UD_DEV float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
+// jnp.clip = minimum(hi, maximum(lo, a)); lax.max/min split the cotangent evenly at a tie
+UD_DEV float clip_grad(float a, float lo, float hi) {
+  return (a > lo && a < hi) ? 1.f : ((a == lo || a == hi) ? 0.5f : 0.f);
+}
 
 // ------------------------------------------------------------------------------------------------
 // step prologue for the primitives (mpm_simulator.py:419-423 + the FK of every substep, which only
@@ -349,7 +353,7 @@ __global__ void k_fk_bwd(MpmConst k, ud_mpm_state in, const float* __restrict__ 
     // pos[f+1] = clip(pos[f] + v, -2, 2)
     for (int j = 0; j < 3; ++j) {
       float u = tp[f * 3 + j] + vw[j];
-      float gnext = (u >= -2.f && u <= 2.f) ? gtp[(f + 1) * 3 + j] : 0.f;
+      float gnext = clip_grad(u, -2.f, 2.f) * gtp[(f + 1) * 3 + j];
       gtp[f * 3 + j] += gnext;
       gvw[j] += gnext;
     }
@@ -394,7 +398,7 @@ __global__ void k_fk_bwd(MpmConst k, ud_mpm_state in, const float* __restrict__ 
     float ga = gvw[j] * scale / (float)S + (go.action_buffer ? go.action_buffer[env * 6 + j] : 0.f);
     pi[7 + j] = gvw[j] * a / (float)S + (go.action_scale ? go.action_scale[env * 6 + j] : 0.f);
     float raw = action[(size_t)env * 6 * k.n_prim + 6 * q + j];
-    g_act[(size_t)t * 6 + j] = (raw >= -1.f && raw <= 1.f) ? ga : 0.f;
+    g_act[(size_t)t * 6 + j] = clip_grad(raw, -1.f, 1.f) * ga;
   }
   for (int j = 13; j < 16; ++j) pi[j] = 0.f;
 }

@@ -182,7 +182,9 @@ UD_DEV void constitutive_bwd(const MpmConst& k, const Mat3& C, const Mat3& F, co
   float gs[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
-    gs[i] = o.plastic ? ((o.s[i] >= k.sig_lo && o.s[i] <= k.sig_hi) ? gsc[i] : 0.f) : gsc[i];
+    gs[i] = o.plastic ? ((o.s[i] > k.sig_lo && o.s[i] < k.sig_hi) ? gsc[i]
+                         : ((o.s[i] == k.sig_lo || o.s[i] == k.sig_hi) ? 0.5f * gsc[i] : 0.f))   // jnp.clip tie rule
+                      : gsc[i];
   Mat3 dA = svd3_bwd(o.U, o.s, o.Vt, gU, gs, gVt);
 #pragma unroll
   for (int i = 0; i < 9; ++i) gF1.m[i] += dA.m[i];
