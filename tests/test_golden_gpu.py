@@ -88,8 +88,8 @@ def test_cloth_cuda_matches_reference_golden(built_lib, name):
     for k, g in zip(names + ["action"], gr):
         ref = d["g_" + k]
         g = g if g is not None else torch.zeros_like(ref)
-        if float(ref.abs().max()) < 1e-20:
-            assert float(g.abs().max()) < 1e-10, k
+        if float(ref.abs().max()) < 1e-10:     # exactly zero, or pure rounding noise (d/d stiffness at rest: cur - L0 ~ 0)
+            assert float(g.abs().max()) < 1e-9, k
             continue
         e, cs = util.rel_err(g, ref), util.cosine(g, ref)
         print(f"cloth {name} grad {k:12s}: rel {e:.3e} cos {cs:.10f} max|ref| {float(ref.abs().max()):.3e}")

@@ -123,6 +123,7 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
     w.ps = (float*)take(4 * (size_t)PS_NCOMP * N * (S + 1));
     w.grid_raw = (float4*)take(16 * BG * S);
     w.grid_out = (float4*)take(16 * BG * S);
+    w.svd_s = (float*)take(4 * (size_t)SV_NCOMP * N * S);
     w.gs = (float*)take(4 * (size_t)PS_NCOMP * N);
     w.ggrid = (float4*)take(16 * BG);
     w.g_fk_pos = (float*)take(4 * (size_t)k.B * P * (S + 1) * 3);
@@ -239,7 +240,7 @@ int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   zero_async(ws.jrows, 4 * (size_t)k.B * k.S * 9, st);
   for (int f = 0; f < k.S; ++f) {
     zero_async(ws.grid_raw, 16 * (size_t)k.B * k.G, st);
-    launch_p2g(k, ws.ps, ws.ps, ws.grid_raw, in->mu, in->lamda, ws, st);
+    launch_p2g(k, ws.ps, ws.ps, ws.grid_raw, in->mu, in->lamda, nullptr, ws, st);
     launch_grid_fwd(k, ws.grid_raw, ws.grid_raw, f, in, ws, st);
     launch_g2p(k, ws.ps, ws.ps, ws.grid_raw, f, ws, st);
   }
@@ -274,7 +275,7 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   for (int f = 0; f < k.S; ++f) {
     const float* s_in = ws.ps + slot * f;
     float* s_out = ws.ps + slot * (f + 1);
-    launch_p2g(k, s_in, s_out, ws.grid_raw + BG * f, in->mu, in->lamda, ws, st);
+    launch_p2g(k, s_in, s_out, ws.grid_raw + BG * f, in->mu, in->lamda, ws.svd_s + (size_t)SV_NCOMP * k.N * f, ws, st);
     launch_grid_fwd(k, ws.grid_raw + BG * f, ws.grid_out + BG * f, f, in, ws, st);
     launch_g2p(k, s_in, s_out, ws.grid_out + BG * f, f, ws, st);
   }
@@ -291,7 +292,7 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
     zero_async(ws.ggrid, 16 * BG, st);
     launch_g2p_bwd(k, s_in, ws.grid_out + BG * f, ws, st);
     launch_grid_bwd(k, ws.grid_raw + BG * f, f, in, ws, st);
-    launch_p2g_bwd(k, s_in, in->mu, in->lamda, ws, st);
+    launch_p2g_bwd(k, s_in, ws.svd_s + (size_t)SV_NCOMP * k.N * f, in->mu, in->lamda, ws, st);
   }
   launch_fk_bwd(k, in, action, gout, ws, st);
   launch_finish_bwd(k, in, gout, gin, action, gaction, ws, st);

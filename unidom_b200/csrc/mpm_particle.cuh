@@ -80,9 +80,9 @@ struct Consti {
   bool plastic, liquid;
 };
 
-// mpm_simulator.py:238-268
-UD_DEV void constitutive_fwd(const MpmConst& k, const Mat3& C, const Mat3& F, float mu_s, float la_s,
-                             float h, int material, Consti& o) {
+// mpm_simulator.py:238-245: F1 = (I + dt C) F and the per-particle Lame parameters
+UD_DEV void constitutive_pre(const MpmConst& k, const Mat3& C, const Mat3& F, float mu_s, float la_s, float h,
+                             int material, Consti& o) {
   o.liquid = material == 0;
   o.plastic = material == 2;
   Mat3 A;
@@ -95,7 +95,10 @@ UD_DEV void constitutive_fwd(const MpmConst& k, const Mat3& C, const Mat3& F, fl
   o.hc = fminf(fmaxf(h, 0.1f), 5.f);
   o.mu = o.liquid ? 0.f : mu_s * o.hc;
   o.la = o.liquid ? 1.f : la_s * o.hc;
-  svd3(o.F1, o.U, o.s, o.Vt);
+}
+
+// mpm_simulator.py:249-268 given the SVD (o.U, o.s, o.Vt) of o.F1: plastic clip, J, F2, stress, affine
+UD_DEV void constitutive_post(const MpmConst& k, const Mat3& C, Consti& o) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) o.sc[i] = o.plastic ? fminf(fmaxf(o.s[i], k.sig_lo), k.sig_hi) : o.s[i];
   o.J = o.sc[0] * o.sc[1] * o.sc[2];
@@ -122,6 +125,14 @@ UD_DEV void constitutive_fwd(const MpmConst& k, const Mat3& C, const Mat3& F, fl
       float st = 2.f * o.mu * M(i, j) + (i == j ? iso : 0.f);
       o.affine(i, j) = cs * st + k.p_mass * C(i, j);
     }
+}
+
+// mpm_simulator.py:238-268
+UD_DEV void constitutive_fwd(const MpmConst& k, const Mat3& C, const Mat3& F, float mu_s, float la_s,
+                             float h, int material, Consti& o) {
+  constitutive_pre(k, C, F, mu_s, la_s, h, material, o);
+  svd3(o.F1, o.U, o.s, o.Vt);
+  constitutive_post(k, C, o);
 }
 
 // Reverse of constitutive_fwd.  Inputs: cotangents of affine (gA) and of the output F (gF2out).

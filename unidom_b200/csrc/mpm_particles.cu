@@ -245,7 +245,7 @@ UD_DEV void load_particle(const float* ps, size_t N, int g, float x[3], float v[
 __global__ void __launch_bounds__(UD_BLOCK)
 k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
-      const float* __restrict__ h_s) {
+      const float* __restrict__ h_s, float* __restrict__ svd_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sv = reinterpret_cast<float*>(smem_raw);                               // [108][STG_PAD]
   StageMeta& meta = *reinterpret_cast<StageMeta*>(sv + 27 * 4 * STG_PAD);
@@ -262,6 +262,14 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
   if (live_) {
 #pragma unroll
     for (int c = 0; c < 9; ++c) ps_out[(PS_F + c) * N + g] = o.F2.m[c];
+    if (svd_out) {  // recompute pass of the adjoint: keep the SVD so that P2G^T does not redo it
+#pragma unroll
+      for (int c = 0; c < 9; ++c) svd_out[(SV_U + c) * N + g] = o.U.m[c];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) svd_out[(SV_S + c) * N + g] = o.s[c];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) svd_out[(SV_VT + c) * N + g] = o.Vt.m[c];
+    }
   }
   meta.key[t] = live_ ? (base_key(st.base) & ~DEAD_KEY) : (DEAD_KEY | t);
   meta.base[t][0] = st.base[0];
@@ -302,14 +310,15 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
 constexpr size_t stage_smem_bytes(int nc) { return sizeof(float) * 27 * nc * STG_PAD + sizeof(StageMeta); }
 
 void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
-                const float* la_s, const MpmWs& ws, cudaStream_t st) {
+                const float* la_s, float* svd_out, const MpmWs& ws, cudaStream_t st) {
   KScope ks_(KC_P2G, st);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_p2g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4));
     attr_set = true;
   }
-  k_p2g<<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4), st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s);
+  k_p2g<<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4), st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s,
+                                                                    svd_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -481,48 +490,59 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   meta.base[t][2] = st.base[2];
   const float lw = live_ ? 1.f : 0.f;
   const float4* genv = grid_out + (size_t)env * k.G;
-  float gw[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  float gfx[3] = {0.f, 0.f, 0.f};
   const float c4 = 4.f * k.inv_dx;
+  // r(a,b,c) = gv' + 4 inv_dx gC' (off - fx) = r0 + a K0 + b K1 + c K2   (K_j = 4 inv_dx * column j of gC')
+  float K[3][3], r0[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) K[j][i] = c4 * gC(i, j);
+    r0[i] = gvt[i] - (K[0][i] * st.fx[0] + K[1][i] * st.fx[1] + K[2][i] * st.fx[2]);
+  }
+  // accumulators: Wg = sum wt g ; the weight cotangent gwt = g . r is contracted hierarchically with (w, dw)
+  float Wg[3] = {0.f, 0.f, 0.f}, gfx[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    int ix = idx_gather(st.base[0] + a, k.rx);
-    float d0 = (float)a - st.fx[0];
+    const int ix = idx_gather(st.base[0] + a, k.rx);
+    const float wa = st.w[a][0] * lw;
+    float ra[3] = {r0[0] + (float)a * K[0][0], r0[1] + (float)a * K[0][1], r0[2] + (float)a * K[0][2]};
+    float P1 = 0.f, P2 = 0.f, Q1 = 0.f;  // sum_b (sum_c gwt w_c) w_b, ... dw_b, sum_b (sum_c gwt dw_c) w_b
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-      int iy = idx_gather(st.base[1] + b, k.ry);
-      float d1 = (float)b - st.fx[1];
+      const int iy = idx_gather(st.base[1] + b, k.ry);
+      const float wab = wa * st.w[b][1];
+      float rab[3] = {ra[0] + (float)b * K[1][0], ra[1] + (float)b * K[1][1], ra[2] + (float)b * K[1][2]};
+      float P = 0.f, Q = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        int iz = idx_gather(st.base[2] + c, k.rz);
-        float d2 = (float)c - st.fx[2];
-        float wt = st.w[a][0] * st.w[b][1] * st.w[c][2];
-        int cell = (ix * k.ry + iy) * k.rz + iz;
-        float4 gv = __ldg(&genv[cell]);
-        // r_i = gv'_i + 4 inv_dx (gC' d)_i
-        float r0 = gvt[0] + c4 * (gC(0, 0) * d0 + gC(0, 1) * d1 + gC(0, 2) * d2);
-        float r1 = gvt[1] + c4 * (gC(1, 0) * d0 + gC(1, 1) * d1 + gC(1, 2) * d2);
-        float r2 = gvt[2] + c4 * (gC(2, 0) * d0 + gC(2, 1) * d1 + gC(2, 2) * d2);
+        const int iz = idx_gather(st.base[2] + c, k.rz);
+        const float wt = wab * st.w[c][2];
+        const float4 gv = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
+        const float r[3] = {rab[0] + (float)c * K[2][0], rab[1] + (float)c * K[2][1], rab[2] + (float)c * K[2][2]};
         float* dst = sv + ((a * 9 + b * 3 + c) * 3) * STG_PAD + t;
-        dst[0] = lw * wt * r0;
-        dst[STG_PAD] = lw * wt * r1;
-        dst[2 * STG_PAD] = lw * wt * r2;
-        float gwt = gv.x * r0 + gv.y * r1 + gv.z * r2;
-        // gd_j = 4 inv_dx wt sum_i g_i gC'_ij ; fx enters d with a minus sign
-        float cw = c4 * wt;
-        gfx[0] -= cw * (gv.x * gC(0, 0) + gv.y * gC(1, 0) + gv.z * gC(2, 0));
-        gfx[1] -= cw * (gv.x * gC(0, 1) + gv.y * gC(1, 1) + gv.z * gC(2, 1));
-        gfx[2] -= cw * (gv.x * gC(0, 2) + gv.y * gC(1, 2) + gv.z * gC(2, 2));
-        gw[a][0] += gwt * st.w[b][1] * st.w[c][2];
-        gw[b][1] += gwt * st.w[a][0] * st.w[c][2];
-        gw[c][2] += gwt * st.w[a][0] * st.w[b][1];
+        dst[0] = wt * r[0];
+        dst[STG_PAD] = wt * r[1];
+        dst[2 * STG_PAD] = wt * r[2];
+        const float gwt = gv.x * r[0] + gv.y * r[1] + gv.z * r[2];
+        Wg[0] += wt * gv.x;
+        Wg[1] += wt * gv.y;
+        Wg[2] += wt * gv.z;
+        P += gwt * st.w[c][2];
+        Q += gwt * st.dw[c][2];
       }
+      P1 += P * st.w[b][1];
+      P2 += P * st.dw[b][1];
+      Q1 += Q * st.w[b][1];
     }
+    gfx[0] += P1 * st.dw[a][0];
+    gfx[1] += P2 * st.w[a][0];
+    gfx[2] += Q1 * st.w[a][0];
   }
   if (live_) {
+    // fx enters d = off - fx with a minus sign: gfx_j -= sum_n wt (K_j . g) = K_j . Wg
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      gfx[d] += gw[0][d] * st.dw[0][d] + gw[1][d] * st.dw[1][d] + gw[2][d] * st.dw[2][d];
+      gfx[d] -= K[d][0] * Wg[0] + K[d][1] * Wg[1] + K[d][2] * Wg[2];
       gs[(PS_X + d) * N + g] = gxo[d] + k.inv_dx * gfx[d];
     }
   }
@@ -540,10 +560,17 @@ void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_ou
 // P2G^T (gather of the cotangents of scattered momentum/mass; dropped nodes contribute nothing),
 // then the reverse of stress / plasticity / SVD / F update.  Writes the cotangents of the substep's
 // input x, v, C, F in place and reduces d/d(state.mu), d/d(state.lamda) per env.
+// The SVD of F1 is read back from the recompute pass (svd_in) instead of being recomputed.
+// Per node only q = wt*g_p, the weight cotangent gwt and a few running sums are formed; everything that
+// is linear in per-particle constants (affine, fx, p_mass) is applied once after the 27-node loop:
+//   gv = p_mass S            S = sum q            T_j = sum off_j q
+//   gA_ij = dx (T_ij - S_i fx_j)                  gfx(direct) = -dx A^T S
+//   gwt = p_mass g_m + g_p . (p_mass v + A dpos)  contracted hierarchically with (w, dw) over c, b, a
 __global__ void __launch_bounds__(UD_BLOCK)
-k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict__ ggrid,
-          float* __restrict__ gs, const float* __restrict__ mu_s, const float* __restrict__ la_s,
-          const int32_t* __restrict__ mat_s, const float* __restrict__ h_s, float* __restrict__ g_scal) {
+k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__ svd_in,
+          const float4* __restrict__ ggrid, float* __restrict__ gs, const float* __restrict__ mu_s,
+          const float* __restrict__ la_s, const int32_t* __restrict__ mat_s, const float* __restrict__ h_s,
+          float* __restrict__ g_scal) {
   UD_PARTICLE_INDEX(k, env, g);
   const size_t N = k.N;
   float gmu = 0.f, gla = 0.f;
@@ -554,56 +581,95 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
     Stencil st;
     make_stencil(x, k.inv_dx, st);
     Consti o;
-    constitutive_fwd(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+    constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+#pragma unroll
+    for (int c = 0; c < 9; ++c) o.U.m[c] = svd_in[(SV_U + c) * N + g];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o.s[c] = svd_in[(SV_S + c) * N + g];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) o.Vt.m[c] = svd_in[(SV_VT + c) * N + g];
+    constitutive_post(k, C, o);
     const float4* ggenv = ggrid + (size_t)env * k.G;
-    float mv[3] = {k.p_mass * v[0], k.p_mass * v[1], k.p_mass * v[2]};
-    float gv[3] = {0.f, 0.f, 0.f}, gfx[3] = {0.f, 0.f, 0.f};
-    float gw[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-    Mat3 gA = mat_zero();
+    // u(a,b,c) = p_mass v + A dpos = u0 + a Ax + b Ay + c Az,  A* = dx * columns of affine
+    float Ac[3][3], u0[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Ac[j][i] = k.dx * o.affine(i, j);
+      u0[i] = k.p_mass * v[i] - (Ac[0][i] * st.fx[0] + Ac[1][i] * st.fx[1] + Ac[2][i] * st.fx[2]);
+    }
+    float S[3] = {0.f, 0.f, 0.f}, TX[3] = {0.f, 0.f, 0.f}, TY[3] = {0.f, 0.f, 0.f}, TZ[3] = {0.f, 0.f, 0.f};
+    float gfx[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      int ix = idx_scatter(st.base[0] + a, k.rx);
-      float d0 = ((float)a - st.fx[0]) * k.dx;
+      const int ix = idx_scatter(st.base[0] + a, k.rx);
+      float ua[3] = {u0[0] + (float)a * Ac[0][0], u0[1] + (float)a * Ac[0][1], u0[2] + (float)a * Ac[0][2]};
+      float Sa[3] = {0.f, 0.f, 0.f}, Ya[3] = {0.f, 0.f, 0.f}, Za[3] = {0.f, 0.f, 0.f};
+      float P1 = 0.f, P2 = 0.f, Q1 = 0.f;
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
-        int iy = idx_scatter(st.base[1] + b, k.ry);
-        float d1 = ((float)b - st.fx[1]) * k.dx;
+        const int iy = idx_scatter(st.base[1] + b, k.ry);
+        const float wab = st.w[a][0] * st.w[b][1];
+        float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
+        float Sab[3] = {0.f, 0.f, 0.f}, Zab[3] = {0.f, 0.f, 0.f};
+        float P = 0.f, Q = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          int iz = idx_scatter(st.base[2] + c, k.rz);
-          if ((ix | iy | iz) < 0) continue;
-          float d2 = ((float)c - st.fx[2]) * k.dx;
-          float wt = st.w[a][0] * st.w[b][1] * st.w[c][2];
-          float4 gp = __ldg(&ggenv[(ix * k.ry + iy) * k.rz + iz]);  // (g_momentum, g_mass)
-          float gpv[3] = {gp.x, gp.y, gp.z};
-          float dd[3] = {d0, d1, d2};
-          float gwt = k.p_mass * gp.w;
+          const int iz = idx_scatter(st.base[2] + c, k.rz);
+          const bool ok = (ix | iy | iz) >= 0;
+          float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);  // (g_momentum, g_mass); dropped node -> 0
+          if (ok) gp = __ldg(&ggenv[(ix * k.ry + iy) * k.rz + iz]);
+          const float wt = wab * st.w[c][2];
+          const float q[3] = {wt * gp.x, wt * gp.y, wt * gp.z};
+          const float u[3] = {uab[0] + (float)c * Ac[2][0], uab[1] + (float)c * Ac[2][1], uab[2] + (float)c * Ac[2][2]};
+          const float gwt = k.p_mass * gp.w + (gp.x * u[0] + gp.y * u[1] + gp.z * u[2]);
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
-            gv[i] += wt * k.p_mass * gpv[i];
-            float Ad = o.affine(i, 0) * d0 + o.affine(i, 1) * d1 + o.affine(i, 2) * d2;
-            gwt += gpv[i] * (mv[i] + Ad);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) gA(i, j) += wt * gpv[i] * dd[j];
+            Sab[i] += q[i];
+            Zab[i] += (float)c * q[i];
           }
-#pragma unroll
-          for (int j = 0; j < 3; ++j)
-            gfx[j] -= k.dx * wt * (o.affine(0, j) * gpv[0] + o.affine(1, j) * gpv[1] + o.affine(2, j) * gpv[2]);
-          gw[a][0] += gwt * st.w[b][1] * st.w[c][2];
-          gw[b][1] += gwt * st.w[a][0] * st.w[c][2];
-          gw[c][2] += gwt * st.w[a][0] * st.w[b][1];
+          P += gwt * st.w[c][2];
+          Q += gwt * st.dw[c][2];
         }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          Sa[i] += Sab[i];
+          Ya[i] += (float)b * Sab[i];
+          Za[i] += Zab[i];
+        }
+        P1 += P * st.w[b][1];
+        P2 += P * st.dw[b][1];
+        Q1 += Q * st.w[b][1];
       }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        S[i] += Sa[i];
+        TX[i] += (float)a * Sa[i];
+        TY[i] += Ya[i];
+        TZ[i] += Za[i];
+      }
+      gfx[0] += P1 * st.dw[a][0];
+      gfx[1] += P2 * st.w[a][0];
+      gfx[2] += Q1 * st.w[a][0];
     }
+    Mat3 gA;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      gA(i, 0) = k.dx * (TX[i] - S[i] * st.fx[0]);
+      gA(i, 1) = k.dx * (TY[i] - S[i] * st.fx[1]);
+      gA(i, 2) = k.dx * (TZ[i] - S[i] * st.fx[2]);
+    }
+    // dpos = (off - fx) dx: direct fx path, gfx_j -= dx (A^T S)_j = Ac[j] . S
+#pragma unroll
+    for (int j = 0; j < 3; ++j) gfx[j] -= Ac[j][0] * S[0] + Ac[j][1] * S[1] + Ac[j][2] * S[2];
     Mat3 gF2out, gC, gF;
 #pragma unroll
     for (int c = 0; c < 9; ++c) gF2out.m[c] = gs[(PS_F + c) * N + g];
     constitutive_bwd(k, C, F, o, gA, gF2out, gC, gF, gmu, gla);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      gfx[d] += gw[0][d] * st.dw[0][d] + gw[1][d] * st.dw[1][d] + gw[2][d] * st.dw[2][d];
       gs[(PS_X + d) * N + g] += k.inv_dx * gfx[d];
-      gs[(PS_V + d) * N + g] = gv[d];
+      gs[(PS_V + d) * N + g] = k.p_mass * S[d];
     }
 #pragma unroll
     for (int c = 0; c < 9; ++c) gs[(PS_C + c) * N + g] = gC.m[c];
@@ -634,11 +700,11 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   }
 }
 
-void launch_p2g_bwd(const MpmConst& k, const float* ps_in, const float* mu_s, const float* la_s,
-                    const MpmWs& ws, cudaStream_t st) {
+void launch_p2g_bwd(const MpmConst& k, const float* ps_in, const float* svd_in, const float* mu_s,
+                    const float* la_s, const MpmWs& ws, cudaStream_t st) {
   KScope ks_(KC_P2G_BWD, st);
-  k_p2g_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ws.ggrid, ws.gs, mu_s, la_s, ws.mat_s, ws.h_s,
-                                                     ws.g_scal);
+  k_p2g_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, svd_in, ws.ggrid, ws.gs, mu_s, la_s, ws.mat_s,
+                                                     ws.h_s, ws.g_scal);
 }
 
 // ------------------------------------------------------------------------------------------------
