@@ -58,32 +58,65 @@ def build_scene(sim, density):
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clock, power and throttle reasons of one GPU through NVML every 10 ms DURING the timed region
+    (nvidia-smi takes longer per query than the whole region; it is the fallback when pynvml is missing)."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        except Exception:
+            pw = 0.0
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        return [str(sm), str(mx)] + [("Active" if r & bits[k] else "Not Active") for k in
+                                     ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")] + [pw]
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    self.rows.append([c.strip() for c in out.strip().split(",")] + [0.0])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.01 if self.nvml is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        sm = sorted(int(r[0]) for r in self.rows if r and str(r[0]).isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and str(r[1]).isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if str(v).lower().startswith("active")})
+        pw = [float(r[6]) for r in self.rows if len(r) > 6]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_max": round(max(pw), 1) if pw else None,
+                "reasons": reasons, "samples": len(sm), "via": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def make_cotangents(state, seed):
@@ -179,13 +212,16 @@ def workload_name(n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--density", type=float, default=DENSITY)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--p2g-mode", type=int, default=0)
+    ap.add_argument("--tune", default="", help="development A/B switches, e.g. svd_warm=0")
+    ap.add_argument("--settle", type=int, default=8, help="env steps run before timing to reach a mid-push state")
+    ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -203,6 +239,9 @@ def main():
     from unidom_b200 import _lib, confs
     from unidom_b200.mpm_simulator import SimpleMPMSimulator
     L = _lib.lib()
+    for kv in filter(None, args.tune.split(",")):
+        name, val = kv.split("=")
+        assert L.ud_tuning_set(name.encode(), int(val)) >= 0, kv
     conf = confs.shape_elasto_plastic_conf()
     sim = SimpleMPMSimulator(conf, args.envs, device=dev, p2g_mode=args.p2g_mode)
     state = build_scene(sim, args.density)
@@ -219,10 +258,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # ---------------- settle: advance the scene so that every timed step starts from the SAME representative
+    # mid-push state (deformed plasticine, F != I); otherwise ms/step would depend on how many steps ran before
+    with torch.no_grad():
+        for _ in range(args.settle):
+            state, _ = sim.step_jax(state, action)
+    state = detach_state(state)
+
     # ---------------- device-resident timing (value)
     for _ in range(max(args.warmup, 3)):
         out, grads, _ = fwd_bwd(sim, state, action, cot)
-        state = detach_state(out)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -231,7 +276,6 @@ def main():
     e0.record()
     for _ in range(args.steps):
         out, grads, _ = fwd_bwd(sim, state, action, cot)
-        state = detach_state(out)
     e1.record()
     barrier()
     launches = int(L.ud_launch_count(0))
@@ -250,9 +294,8 @@ def main():
         torch.cuda.synchronize(dev)
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        s2 = state
         for _ in range(args.steps):
-            s2, _ = sim.step_jax(s2, action)
+            sim.step_jax(state, action)
         f1.record()
         torch.cuda.synchronize(dev)
     fwd_value = world * units_per_step * args.steps / (f0.elapsed_time(f1) * 1e-3)
@@ -262,7 +305,6 @@ def main():
     nprof = min(args.steps, 5)
     for _ in range(nprof):
         out, grads, _ = fwd_bwd(sim, state, action, cot)
-        state = detach_state(out)
     torch.cuda.synchronize(dev)
     ncls = L.ud_timing_num_classes()
     msb = (C.c_double * ncls)()
@@ -309,13 +351,13 @@ def main():
             host_g[k].copy_(t, non_blocking=True)
         host_ga.copy_(gr[4], non_blocking=True)
 
-    for _ in range(2):
+    for _ in range(0 if args.no_e2e else 2):
         e2e_step()
     barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     g0.record()
-    for _ in range(args.steps):
+    for _ in range(1 if args.no_e2e else args.steps):
         e2e_step()
     g1.record()
     barrier()
@@ -341,7 +383,7 @@ def main():
             "metric": "particle-substeps/s fwd+bwd", "value": value, "unit": "particle-substeps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(n), "envs_per_gpu": B, "particles_per_env": n, "substeps": S,
+            "config": {"workload": workload_name(n), "state": f"every step starts from the scene after {args.settle} settle steps", "envs_per_gpu": B, "particles_per_env": n, "substeps": S,
                        "l2": f"inputs larger than L2 (state+checkpoints {B * n * 96 * (S + 1) / 1e9:.2f} GB per step)",
                        "p2g_mode": "atomic" if args.p2g_mode == 0 else "deterministic",
                        "collective": "none in the step (envs are independent; APG's policy-gradient all-reduce "

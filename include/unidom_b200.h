@@ -172,6 +172,10 @@ int ud_cloth_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const 
  * stream; ud_timing_collect synchronises those events and returns, per class, the summed device
  * milliseconds and number of launches since the last collect.  Class names: ud_timing_class_name. */
 uint64_t ud_launch_count(int reset);
+/* A/B switches for the measurements DESIGN.md quotes (process-global, not thread-safe, default = the fast path):
+ *   "svd_warm"  1: warm-start the per-particle Jacobi SVD from the previous substep's V (default) / 0: cold start
+ * Returns the previous value, or -1 for an unknown name. */
+int ud_tuning_set(const char* name, int value);
 void ud_timing_enable(int on);
 int ud_timing_num_classes(void);
 const char* ud_timing_class_name(int cls);

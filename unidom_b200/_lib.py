@@ -101,7 +101,7 @@ EXPORTS = (
     "ud_version", "ud_last_error", "ud_mpm_fwd_workspace_bytes", "ud_mpm_bwd_workspace_bytes",
     "ud_mpm_step_fwd", "ud_mpm_step_bwd", "ud_mpm_sort_bins", "ud_mpm_num_keys",
     "ud_cloth_workspace_bytes", "ud_cloth_step_fwd", "ud_cloth_step_bwd",
-    "ud_launch_count", "ud_timing_enable", "ud_timing_collect",
+    "ud_launch_count", "ud_timing_enable", "ud_timing_collect", "ud_tuning_set",
 )
 
 

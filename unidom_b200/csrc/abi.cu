@@ -38,6 +38,7 @@ KScope::~KScope() {
   cudaEventRecord(g_recs[slot].b, st);
 }
 
+static int g_svd_warm = 1;
 static thread_local const char* g_last_error = "";
 static int fail(int code, const char* what) {
   g_last_error = what;
@@ -117,6 +118,7 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
   w.jrows = (float*)take(4 * (size_t)k.B * S * 9);
   if (!bwd) {
     w.ps = (float*)take(4 * (size_t)PS_NCOMP * N);
+    w.vt_roll = (float*)take(4 * (size_t)9 * N);
     w.grid_raw = (float4*)take(16 * BG);
     w.grid_out = w.grid_raw;
   } else {
@@ -164,6 +166,10 @@ uint64_t ud_launch_count(int reset) {
   return v;
 }
 void ud_timing_enable(int on) { g_timing = on != 0; }
+int ud_tuning_set(const char* name, int value) {
+  if (name && !strcmp(name, "svd_warm")) { int o = g_svd_warm; g_svd_warm = value; return o; }
+  return -1;
+}
 int ud_timing_num_classes(void) { return KC_COUNT; }
 const char* ud_timing_class_name(int cls) {
   static const char* names[KC_COUNT] = {"sort", "gather", "fk", "p2g", "grid", "g2p", "unsort", "g2p_bwd",
@@ -240,7 +246,8 @@ int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   zero_async(ws.jrows, 4 * (size_t)k.B * k.S * 9, st);
   for (int f = 0; f < k.S; ++f) {
     zero_async(ws.grid_raw, 16 * (size_t)k.B * k.G, st);
-    launch_p2g(k, ws.ps, ws.ps, ws.grid_raw, in->mu, in->lamda, nullptr, ws, st);
+    launch_p2g(k, ws.ps, ws.ps, ws.grid_raw, in->mu, in->lamda, (g_svd_warm && (f % SVD_RESTART)) ? ws.vt_roll : nullptr, ws.vt_roll,
+               nullptr, ws, st);
     launch_grid_fwd(k, ws.grid_raw, ws.grid_raw, f, in, ws, st);
     launch_g2p(k, ws.ps, ws.ps, ws.grid_raw, f, ws, st);
   }
@@ -275,7 +282,10 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   for (int f = 0; f < k.S; ++f) {
     const float* s_in = ws.ps + slot * f;
     float* s_out = ws.ps + slot * (f + 1);
-    launch_p2g(k, s_in, s_out, ws.grid_raw + BG * f, in->mu, in->lamda, ws.svd_s + (size_t)SV_NCOMP * k.N * f, ws, st);
+    float* sv_f = ws.svd_s + (size_t)SV_NCOMP * k.N * f;
+    launch_p2g(k, s_in, s_out, ws.grid_raw + BG * f, in->mu, in->lamda,
+               (g_svd_warm && (f % SVD_RESTART)) ? sv_f - (size_t)SV_NCOMP * k.N + (size_t)SV_VT * k.N : nullptr, nullptr,
+               sv_f, ws, st);
     launch_grid_fwd(k, ws.grid_raw + BG * f, ws.grid_out + BG * f, f, in, ws, st);
     launch_g2p(k, s_in, s_out, ws.grid_out + BG * f, f, ws, st);
   }

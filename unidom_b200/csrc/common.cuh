@@ -97,7 +97,9 @@ UD_DEV float jacobi_pair(float* bp, float* bq, float* vp, float* vq) {
   float tau = beta - alpha;
   float den = tau + copysignf(fast_sqrt(tau * tau + g2 * g2), tau);
   float t = den != 0.f ? fast_div(g2, den) : 0.f;
-  float c = fast_rsqrt(1.f + t * t);
+  float n2 = 1.f + t * t;
+  float c = fast_rsqrt(n2);
+  c = c * (1.5f - 0.5f * n2 * (c * c));  // one Newton step: V stays orthonormal to fp32 along warm-started chains
   float s = c * t;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -121,11 +123,45 @@ UD_DEV void swap3(float* a, float* b) {
   }
 }
 
-UD_DEV void svd3(const Mat3& A, Mat3& U, float s[3], Mat3& Vt) {
+// Vt0 (optional, row-major V^T of a nearby matrix, e.g. the previous substep's): warm start.  The sweeps
+// then start from B = A V0, whose columns are already nearly orthogonal, and typically stop after 1-2
+// sweeps instead of 3-4.  Any orthogonal V0 is valid; the result is an SVD of A either way.
+UD_DEV void svd3_ws(const Mat3& A, Mat3& U, float s[3], Mat3& Vt, bool warm, const float (&Vt0)[9]) {
   // columns of B and V kept as separate arrays
   float b0[3] = {A(0, 0), A(1, 0), A(2, 0)}, b1[3] = {A(0, 1), A(1, 1), A(2, 1)},
         b2[3] = {A(0, 2), A(1, 2), A(2, 2)};
   float v0[3] = {1.f, 0.f, 0.f}, v1[3] = {0.f, 1.f, 0.f}, v2[3] = {0.f, 0.f, 1.f};
+  if (warm) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      v0[i] = Vt0[i];
+      v1[i] = Vt0[3 + i];
+      v2[i] = Vt0[6 + i];
+    }
+    // re-orthonormalise V0 (Gram-Schmidt + cross product): every rotation is orthogonal only to ~1e-7, and
+    // along a warm-started chain that drift would otherwise accumulate into U diag(s) Vt != A
+    {
+      float n0 = v0[0] * v0[0] + v0[1] * v0[1] + v0[2] * v0[2];
+      float r0 = fast_rsqrt(n0);
+      r0 = r0 * (1.5f - 0.5f * n0 * (r0 * r0));
+      v0[0] *= r0; v0[1] *= r0; v0[2] *= r0;
+      float d = v0[0] * v1[0] + v0[1] * v1[1] + v0[2] * v1[2];
+      v1[0] -= d * v0[0]; v1[1] -= d * v0[1]; v1[2] -= d * v0[2];
+      float n1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+      float r1 = fast_rsqrt(n1);
+      r1 = r1 * (1.5f - 0.5f * n1 * (r1 * r1));
+      v1[0] *= r1; v1[1] *= r1; v1[2] *= r1;
+      float cx = v0[1] * v1[2] - v0[2] * v1[1], cy = v0[2] * v1[0] - v0[0] * v1[2], cz = v0[0] * v1[1] - v0[1] * v1[0];
+      float sg = (cx * v2[0] + cy * v2[1] + cz * v2[2]) < 0.f ? -1.f : 1.f;
+      v2[0] = sg * cx; v2[1] = sg * cy; v2[2] = sg * cz;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // B = A V0: column j of B = A v_j
+      b0[i] = A(i, 0) * v0[0] + A(i, 1) * v0[1] + A(i, 2) * v0[2];
+      b1[i] = A(i, 0) * v1[0] + A(i, 1) * v1[1] + A(i, 2) * v1[2];
+      b2[i] = A(i, 0) * v2[0] + A(i, 1) * v2[1] + A(i, 2) * v2[2];
+    }
+  }
   // cyclic sweeps; quadratic convergence: once every normalised off-diagonal met in a sweep is
   // < 2e-4 the defect left after that sweep is O(1e-8), below fp32 resolution
 #pragma unroll 1
@@ -181,6 +217,11 @@ UD_DEV void svd3(const Mat3& A, Mat3& U, float s[3], Mat3& Vt) {
     Vt(1, i) = v1[i];
     Vt(2, i) = v2[i];
   }
+}
+
+UD_DEV void svd3(const Mat3& A, Mat3& U, float s[3], Mat3& Vt) {
+  const float none[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  svd3_ws(A, U, s, Vt, false, none);
 }
 
 // Reference VJP of the SVD, svd_safe_batch.py:65-102, real square case:

@@ -14,6 +14,8 @@ namespace ud {
 constexpr int PS_X = 0, PS_V = 3, PS_C = 6, PS_F = 15, PS_NCOMP = 24;
 // SVD of F1 kept by the recompute pass for the adjoint: U (row-major 9), s (3), Vt (row-major 9)
 constexpr int SV_U = 0, SV_S = 9, SV_VT = 12, SV_NCOMP = 21;
+// the SVD warm-start chain restarts from V = I every SVD_RESTART substeps (bounds rounding drift of V)
+constexpr int SVD_RESTART = 16;
 // per-env scalar cotangent accumulators (bwd)
 //   0 friction, 1 mu, 2 lamda, then per primitive q: 3+4q .. : size(3), friction(1)
 constexpr int GS_FRICTION = 0, GS_MU = 1, GS_LAMDA = 2, GS_PRIM = 3, GS_PRIM_STRIDE = 4;
@@ -32,6 +34,7 @@ struct MpmWs {
   float* ps;            // fwd: [24*N]; bwd: [(S+1)*24*N] start-of-substep states
   float4* grid_raw;     // fwd: [B*G]; bwd: [S*B*G] scattered (p,m)
   float4* grid_out;     // fwd: == grid_raw; bwd: [S*B*G] updated velocities
+  float* vt_roll;       // fwd only: [9*N] V^T of the previous substep's SVD (warm start)
   float* svd_s;         // bwd only: [S*21*N] SVD of F1 per substep (written by the recompute P2G)
   float* fk_pos;        // [B*P*(S+1)*3] (row S = clamp copy of row S-1)
   float* fk_rot;        // [B*P*(S+1)*4]
@@ -72,7 +75,8 @@ void launch_sort(const MpmConst& k, const float* x_aos, const MpmWs& ws, int32_t
 void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
                          const MpmWs& ws, float* ps_slot, cudaStream_t st);
 void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
-                const float* la_s, float* svd_out, const MpmWs& ws, cudaStream_t st);
+                const float* la_s, const float* vt_in, float* vt_out, float* svd_out, const MpmWs& ws,
+                cudaStream_t st);
 void launch_g2p(const MpmConst& k, const float* ps_in, float* ps_out, const float4* grid, int substep,
                 const MpmWs& ws, cudaStream_t st);
 void launch_unsort_state(const MpmConst& k, const float* ps_slot, const float* J_in, const MpmWs& ws,

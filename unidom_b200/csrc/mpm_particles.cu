@@ -138,56 +138,114 @@ void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Shared-memory staged scatter.  A CTA owns UD_BLOCK consecutive particles of the per-frame sort, so
-// particles that share a base cell form a few contiguous runs (~59 particles per cell in the
-// plasticine scene).  Phase 1: every particle stages its NV = 27*NC node values in shared memory
-// (value-major, +1 padded: conflict-free both ways).  Phase 2: thread t < NV owns one (node, comp)
-// and sums it over each run in particle order; one global RED per (run, node, comp) -- ~2.5 atomics
-// per particle instead of 27 vector atomics, and the summation order inside a CTA is fixed.
+// Shared-memory staged scatter.  A CTA owns UD_BLOCK consecutive particles of the per-frame sort.
+// Phase 0 (stage_group): rows are GROUPED by base cell inside the CTA.  At the start of a step the sort
+// makes each cell one contiguous run (~3.4 runs per CTA in the plasticine scene), but the sort is per
+// frame and particles cross cell faces during the 16 substeps: measured, the contiguous runs fragment to
+// 10-16 per CTA by the end of a step while the DISTINCT cells stay at 4-6.  Grouping restores one
+// segment per distinct cell, so the number of global REDs per CTA does not grow with fragmentation.
+// Phase 1: every particle stages its node values at its grouped row (value-major, +1 padded columns).
+// Phase 2 (stage_flush): thread (node, comp) sums its column over each segment in fixed row order and
+// issues ONE 16-byte vector RED per (segment, node).
 // ------------------------------------------------------------------------------------------------
 constexpr int STG_PAD = UD_BLOCK + 1;
 struct StageMeta {
-  int key[UD_BLOCK];
-  int base[UD_BLOCK][3];
-  int run_start[UD_BLOCK + 1];
-  int warp_heads[UD_BLOCK / 32];
+  int key[UD_BLOCK];            // by grouped row
+  int base[UD_BLOCK][3];        // by grouped row
+  int run_start[UD_BLOCK + 1];  // segment starts (grouped rows)
   int n_runs;
+  // scratch of stage_group: one entry per (warp, distinct key in that warp)
+  int warp_cnt[UD_BLOCK / 32];
+  int ekey[UD_BLOCK];
+  unsigned emask[UD_BLOCK];
+  int efirst[UD_BLOCK];
+  int egid[UD_BLOCK];
+  int estart[UD_BLOCK];
 };
 constexpr int DEAD_KEY = 0x40000000;
 UD_DEV int base_key(const int base[3]) { return (base[0] * 2048 + base[1]) * 2048 + base[2]; }
 
-// builds meta.run_start / n_runs from meta.key (call by all threads, after key/base are stored)
-__device__ __forceinline__ void stage_runs(StageMeta& m) {
-  __syncthreads();
+// Groups the CTA's rows by key.  Returns this thread's grouped row; fills m.key / m.base / m.run_start /
+// m.n_runs.  Deterministic: groups are ordered by first occurrence (warp, lane), rows inside a group by
+// (warp, lane).  All threads of the CTA must call it; it ends with a barrier.
+__device__ __forceinline__ int stage_group(StageMeta& m, int key, const int base[3]) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  bool head = t == 0 || m.key[t] != m.key[t - 1];
-  unsigned hb = __ballot_sync(0xffffffffu, head);
-  if (lane == 0) m.warp_heads[wid] = __popc(hb);
+  const unsigned lt = (1u << lane) - 1u;
+  const unsigned mm = __match_any_sync(0xffffffffu, key);   // lanes of my warp with my key
+  const int leadlane = __ffs(mm) - 1;
+  const bool lead = lane == leadlane;
+  const unsigned lb = __ballot_sync(0xffffffffu, lead);
+  if (lane == 0) m.warp_cnt[wid] = __popc(lb);
   __syncthreads();
-  int before = __popc(hb & ((1u << lane) - 1u));
-  for (int w = 0; w < wid; ++w) before += m.warp_heads[w];
-  if (head) m.run_start[before] = t;
-  if (t == UD_BLOCK - 1) {
-    int total = before + (head ? 1 : 0);
-    m.n_runs = total;
-    m.run_start[total] = UD_BLOCK;
+  int ebase = 0, E = 0;
+#pragma unroll
+  for (int w = 0; w < UD_BLOCK / 32; ++w) {
+    const int c = m.warp_cnt[w];
+    ebase += w < wid ? c : 0;
+    E += c;
+  }
+  const int e = ebase + __popc(lb & lt);   // entry index (meaningful on leader lanes)
+  if (lead) {
+    m.ekey[e] = key;
+    m.emask[e] = mm;
   }
   __syncthreads();
+  if (t < E) {  // first entry with the same key
+    const int kk = m.ekey[t];
+    int first = t;
+    for (int j = t - 1; j >= 0; --j) first = m.ekey[j] == kk ? j : first;
+    m.efirst[t] = first;
+  }
+  __syncthreads();
+  if (t < E) {  // group id = number of group heads before my head
+    const int first = m.efirst[t];
+    int gid = 0;
+    for (int j = 0; j < first; ++j) gid += m.efirst[j] == j;
+    m.egid[t] = gid;
+  }
+  __syncthreads();
+  if (t < E) {  // start row of my entry = rows of earlier groups + rows of earlier entries of my group
+    const int gid = m.egid[t];
+    int start = 0, ng = 0;
+    for (int j = 0; j < E; ++j) {
+      const int gj = m.egid[j];
+      const int cnt = __popc(m.emask[j]);
+      start += (gj < gid || (gj == gid && j < t)) ? cnt : 0;
+      ng = max(ng, gj + 1);
+    }
+    m.estart[t] = start;
+    if (m.efirst[t] == t) m.run_start[gid] = start;
+    if (t == 0) {
+      m.n_runs = ng;
+      m.run_start[ng] = UD_BLOCK;
+    }
+  }
+  __syncthreads();
+  const int pos = m.estart[__shfl_sync(0xffffffffu, e, leadlane)] + __popc(mm & lt);
+  m.key[pos] = key;
+  m.base[pos][0] = base[0];
+  m.base[pos][1] = base[1];
+  m.base[pos][2] = base[2];
+  __syncthreads();
+  return pos;
 }
 
-// phase 2: NC (3 or 4) components per node, staged value-major as column (node*NC + comp).
-// Thread t < 108 = node*4 + comp sums its column over each run; the 4 lanes of a node then assemble a
+// phase 2: NC (3 or 4) components per node, staged value-major as column (node_local*NC + comp).
+// Thread t = node_local*4 + comp sums its column over each run; the 4 lanes of a node then assemble a
 // float4 with three shuffles and lane comp==0 issues ONE 16-byte vector RED (REDG.E.ADD.F32x4) per
 // (run, node): scalar REDs cost ~4x more L2 atomic work (measured: 76 of 236 us in k_p2g).
+// The 27 nodes are staged in windows of NPH nodes ([j0, j0+nj)), which divides the shared-memory
+// footprint (and multiplies the resident CTAs per SM) without changing the amount of flush work.
 template <int NC, bool CLAMP>
 __device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __restrict__ sv, const StageMeta& m,
-                                            float4* __restrict__ genv) {
+                                            float4* __restrict__ genv, int j0, int nj) {
   const int t = threadIdx.x;
-  if (t >= 128) return;  // threads 108..127 stay for the warp shuffles; only whole extra warps leave
-  const int j = t >> 2, c = t & 3;
-  const bool sums = t < 108 && c < NC;
+  if (t >= ((nj * 4 + 31) & ~31)) return;  // whole extra warps leave; partial warps stay for the shuffles
+  const int jl = t >> 2, c = t & 3;
+  const bool sums = jl < nj && c < NC;
+  const int j = j0 + jl;
   const int a = j / 9, b = (j / 3) % 3, cc = j % 3;
-  const float* col = sv + (j * NC + (c < NC ? c : 0)) * STG_PAD;
+  const float* col = sv + ((jl < nj ? jl : 0) * NC + (c < NC ? c : 0)) * STG_PAD;
   const int nr = m.n_runs;
   for (int r = 0; r < nr; ++r) {
     const int s0 = m.run_start[r], s1 = m.run_start[r + 1];
@@ -209,7 +267,7 @@ __device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __re
     val.y = __shfl_down_sync(0xffffffffu, acc, 1);
     val.z = __shfl_down_sync(0xffffffffu, acc, 2);
     val.w = __shfl_down_sync(0xffffffffu, acc, 3);
-    if (c != 0 || t >= 108) continue;
+    if (c != 0 || jl >= nj) continue;
     int ix, iy, iz;
     if (CLAMP) {
       ix = idx_gather(m.base[s0][0] + a, k.rx);
@@ -224,6 +282,9 @@ __device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __re
     atomicAdd(&genv[(ix * k.ry + iy) * k.rz + iz], val);
   }
 }
+constexpr size_t stage_smem_bytes(int nc, int nph) { return sizeof(float) * nph * nc * STG_PAD + sizeof(StageMeta); }
+constexpr int P2G_NPH = 14;      // nodes per staging window of k_p2g (27 nodes -> 2 windows)
+constexpr int G2PB_NPH = 27;     // k_g2p_bwd: one window
 
 // ------------------------------------------------------------------------------------------------
 // P2G: F update + SVD + plasticity + stress (mpm_simulator.py:238-268), then the 27-node scatter of
@@ -245,23 +306,36 @@ UD_DEV void load_particle(const float* ps, size_t N, int g, float x[3], float v[
 __global__ void __launch_bounds__(UD_BLOCK)
 k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
-      const float* __restrict__ h_s, float* __restrict__ svd_out) {
+      const float* __restrict__ h_s, const float* __restrict__ vt_in, float* __restrict__ vt_out,
+      float* __restrict__ svd_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sv = reinterpret_cast<float*>(smem_raw);                               // [108][STG_PAD]
-  StageMeta& meta = *reinterpret_cast<StageMeta*>(sv + 27 * 4 * STG_PAD);
+  float* sv = reinterpret_cast<float*>(smem_raw);                               // [P2G_NPH*4][STG_PAD]
+  StageMeta& meta = *reinterpret_cast<StageMeta*>(sv + P2G_NPH * 4 * STG_PAD);
   UD_PARTICLE_INDEX(k, env, g);
   const size_t N = k.N;
-  const int t = threadIdx.x;
   float x[3], v[3];
   Mat3 C, F;
   load_particle(ps_in, N, g, x, v, C, F);
   Stencil st;
   make_stencil(x, k.inv_dx, st);
+  const int row = stage_group(meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base);
   Consti o;
-  constitutive_fwd(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+  float vt0[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  const bool warm = vt_in != nullptr;  // warm start of the Jacobi SVD from the previous substep's V^T (grid-uniform)
+  if (warm) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) vt0[c] = vt_in[c * N + g];
+  }
+  constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+  svd3_ws(o.F1, o.U, o.s, o.Vt, warm, vt0);
+  constitutive_post(k, C, o);
   if (live_) {
 #pragma unroll
     for (int c = 0; c < 9; ++c) ps_out[(PS_F + c) * N + g] = o.F2.m[c];
+    if (vt_out) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) vt_out[c * N + g] = o.Vt.m[c];
+    }
     if (svd_out) {  // recompute pass of the adjoint: keep the SVD so that P2G^T does not redo it
 #pragma unroll
       for (int c = 0; c < 9; ++c) svd_out[(SV_U + c) * N + g] = o.U.m[c];
@@ -271,10 +345,6 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       for (int c = 0; c < 9; ++c) svd_out[(SV_VT + c) * N + g] = o.Vt.m[c];
     }
   }
-  meta.key[t] = live_ ? (base_key(st.base) & ~DEAD_KEY) : (DEAD_KEY | t);
-  meta.base[t][0] = st.base[0];
-  meta.base[t][1] = st.base[1];
-  meta.base[t][2] = st.base[2];
   // value at node (a,b,c):  wt * (u + a*Ax + b*Ay + c*Az),  u = p_mass v - dx A fx,  A* = dx * columns of A
   const float lw = live_ ? 1.f : 0.f;
   float u[3], Ac[3][3];
@@ -285,40 +355,46 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
     u[i] = k.p_mass * v[i] - (Ac[0][i] * st.fx[0] + Ac[1][i] * st.fx[1] + Ac[2][i] * st.fx[2]);
   }
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float wa = st.w[a][0] * lw;
-    float ua[3] = {u[0] + (float)a * Ac[0][0], u[1] + (float)a * Ac[0][1], u[2] + (float)a * Ac[0][2]};
+  for (int j0 = 0; j0 < 27; j0 += P2G_NPH) {
+    if (j0) __syncthreads();  // the previous window has been flushed
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const float wab = wa * st.w[b][1];
-      float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
+    for (int a = 0; a < 3; ++a) {
+      const float wa = st.w[a][0] * lw;
+      float ua[3] = {u[0] + (float)a * Ac[0][0], u[1] + (float)a * Ac[0][1], u[2] + (float)a * Ac[0][2]};
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float wt = wab * st.w[c][2];
-        float* dst = sv + ((a * 9 + b * 3 + c) * 4) * STG_PAD + t;
-        dst[0] = wt * (uab[0] + (float)c * Ac[2][0]);
-        dst[STG_PAD] = wt * (uab[1] + (float)c * Ac[2][1]);
-        dst[2 * STG_PAD] = wt * (uab[2] + (float)c * Ac[2][2]);
-        dst[3 * STG_PAD] = wt * k.p_mass;
+      for (int b = 0; b < 3; ++b) {
+        const float wab = wa * st.w[b][1];
+        float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int j = a * 9 + b * 3 + c;
+          if (j < j0 || j >= j0 + P2G_NPH) continue;  // compile-time after unrolling
+          const float wt = wab * st.w[c][2];
+          float* dst = sv + ((j - j0) * 4) * STG_PAD + row;
+          dst[0] = wt * (uab[0] + (float)c * Ac[2][0]);
+          dst[STG_PAD] = wt * (uab[1] + (float)c * Ac[2][1]);
+          dst[2 * STG_PAD] = wt * (uab[2] + (float)c * Ac[2][2]);
+          dst[3 * STG_PAD] = wt * k.p_mass;
+        }
       }
     }
+    __syncthreads();
+    stage_flush<4, false>(k, sv, meta, grid + (size_t)env * k.G, j0, (27 - j0) < P2G_NPH ? (27 - j0) : P2G_NPH);
   }
-  stage_runs(meta);
-  stage_flush<4, false>(k, sv, meta, grid + (size_t)env * k.G);
 }
 
-constexpr size_t stage_smem_bytes(int nc) { return sizeof(float) * 27 * nc * STG_PAD + sizeof(StageMeta); }
 
 void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
-                const float* la_s, float* svd_out, const MpmWs& ws, cudaStream_t st) {
+                const float* la_s, const float* vt_in, float* vt_out, float* svd_out, const MpmWs& ws,
+                cudaStream_t st) {
   KScope ks_(KC_P2G, st);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_p2g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4));
+    cudaFuncSetAttribute(k_p2g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4, P2G_NPH));
     attr_set = true;
   }
-  k_p2g<<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4), st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s,
-                                                                    svd_out);
+  k_p2g<<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4, P2G_NPH), st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s,
+                                                                    vt_in, vt_out, svd_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,10 +544,9 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
           float* __restrict__ gs, float4* __restrict__ ggrid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sv = reinterpret_cast<float*>(smem_raw);                               // [81][STG_PAD]
-  StageMeta& meta = *reinterpret_cast<StageMeta*>(sv + 27 * 3 * STG_PAD);
+  StageMeta& meta = *reinterpret_cast<StageMeta*>(sv + G2PB_NPH * 3 * STG_PAD);
   UD_PARTICLE_INDEX(k, env, g);
   const size_t N = k.N;
-  const int t = threadIdx.x;
   float x[3], gxo[3], gvt[3];
   Mat3 gC;
 #pragma unroll
@@ -484,10 +559,7 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   for (int c = 0; c < 9; ++c) gC.m[c] = gs[(PS_C + c) * N + g];
   Stencil st;
   make_stencil(x, k.inv_dx, st);
-  meta.key[t] = live_ ? (base_key(st.base) & ~DEAD_KEY) : (DEAD_KEY | t);
-  meta.base[t][0] = st.base[0];
-  meta.base[t][1] = st.base[1];
-  meta.base[t][2] = st.base[2];
+  const int row = stage_group(meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base);
   const float lw = live_ ? 1.f : 0.f;
   const float4* genv = grid_out + (size_t)env * k.G;
   const float c4 = 4.f * k.inv_dx;
@@ -519,7 +591,7 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
         const float wt = wab * st.w[c][2];
         const float4 gv = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
         const float r[3] = {rab[0] + (float)c * K[2][0], rab[1] + (float)c * K[2][1], rab[2] + (float)c * K[2][2]};
-        float* dst = sv + ((a * 9 + b * 3 + c) * 3) * STG_PAD + t;
+        float* dst = sv + ((a * 9 + b * 3 + c) * 3) * STG_PAD + row;
         dst[0] = wt * r[0];
         dst[STG_PAD] = wt * r[1];
         dst[2 * STG_PAD] = wt * r[2];
@@ -546,15 +618,15 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
       gs[(PS_X + d) * N + g] = gxo[d] + k.inv_dx * gfx[d];
     }
   }
-  stage_runs(meta);
+  __syncthreads();
   // transpose of the clamping gather: clamped target index
-  stage_flush<3, true>(k, sv, meta, ggrid + (size_t)env * k.G);
+  stage_flush<3, true>(k, sv, meta, ggrid + (size_t)env * k.G, 0, 27);
 }
 
 void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
                     cudaStream_t st) {
   KScope ks_(KC_G2P_BWD, st);
-  k_g2p_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(3), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
+  k_g2p_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(3, G2PB_NPH), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
 }
 
 // P2G^T (gather of the cotangents of scattered momentum/mass; dropped nodes contribute nothing),
@@ -566,7 +638,7 @@ void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_ou
 //   gv = p_mass S            S = sum q            T_j = sum off_j q
 //   gA_ij = dx (T_ij - S_i fx_j)                  gfx(direct) = -dx A^T S
 //   gwt = p_mass g_m + g_p . (p_mass v + A dpos)  contracted hierarchically with (w, dw) over c, b, a
-__global__ void __launch_bounds__(UD_BLOCK)
+__global__ void __launch_bounds__(UD_BLOCK, 4)
 k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__ svd_in,
           const float4* __restrict__ ggrid, float* __restrict__ gs, const float* __restrict__ mu_s,
           const float* __restrict__ la_s, const int32_t* __restrict__ mat_s, const float* __restrict__ h_s,
