@@ -39,7 +39,9 @@ extern "C" {
 #define UD_SDF_CONTAINER 1  /* core/engine/primitives/container.py:8-16 */
 
 #define UD_P2G_ATOMIC 0        /* vector RED per touched cell (fast, order-nondeterministic)   */
-#define UD_P2G_DETERMINISTIC 1 /* sorted per-cell gather (bit-reproducible run to run)         */
+#define UD_P2G_DETERMINISTIC 1 /* same sorted in-CTA segment sums, combined across CTAs with 64-bit
+                                  fixed-point integer REDs (associative): bit-reproducible run to run and
+                                  between the forward and the adjoint's recompute pass            */
 
 /* Scalars of the reference's per-task DefaultConf (e.g. envs/shape_elasto_plastic.py:23-54).
  * Doubles are the Python floats of the conf; the library folds derived constants in

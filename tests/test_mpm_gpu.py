@@ -179,3 +179,33 @@ def test_step_backward_parity(built_lib, material, n_prim, pos_control, cot_scal
         if float(ref[k].abs().max()) > 1e-12:
             assert cs >= 0.999, (k, cs)
             assert e < max(1e-3, 20 * fl), (k, e, fl)
+
+
+def test_p2g_deterministic_mode_is_bit_reproducible(built_lib):
+    """UD_P2G_DETERMINISTIC: fixed-point integer accumulation across CTAs.  Two runs are bit-identical (the
+    race canary of SURVEY section 5) and agree with the fp32-RED mode to rounding."""
+    from unidom_b200 import _lib
+    conf = _conf(steps=16)
+    B = 3
+    sim_d = _sim(conf, B, p2g_mode=_lib.UD_P2G_DETERMINISTIC)
+    st = util.mini_plasticine(sim_d, B, seed=21, density=2.0)      # ~8 particles per cell: contended cells
+    act = _actions(B, 1, seed=2).to(st.x.device)
+    outs = []
+    for _ in range(3):
+        x = st.x.clone().requires_grad_(True)
+        o, _ = sim_d.step_jax(st._replace(x=x), act)
+        (gx,) = torch.autograd.grad((o.x * o.v).sum(), [x])
+        outs.append((o, gx))
+    for o, gx in outs[1:]:
+        for k in ("x", "v", "C", "F", "J"):
+            assert torch.equal(getattr(o, k), getattr(outs[0][0], k)), k
+    sim_a = _sim(conf, B, p2g_mode=_lib.UD_P2G_ATOMIC)
+    sim_a.material, sim_a.h = sim_d.material, sim_d.h
+    sim_a.n_particles, sim_a._material_dev, sim_a._h_dev = sim_d.n_particles, sim_d._material_dev, sim_d._h_dev
+    oa, _ = sim_a.step_jax(st, act)
+    for k in ("x", "v", "C", "F"):
+        e = util.rel_err(getattr(oa, k), getattr(outs[0][0], k))
+        print(f"deterministic vs fp32-RED mode {k}: rel {e:.3e}")
+        assert e < 2e-5, (k, e)
+    ref = _oracle_step(conf, sim_d, st, act)
+    assert util.rel_err(outs[0][0].x, ref.x) < 1e-4 and util.rel_err(outs[0][0].F, ref.F) < 1e-4

@@ -51,6 +51,7 @@ bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k) {
   if (p->res[0] < 1 || p->res[1] < 1 || p->res[2] < 1 || p->n_grid < 1) return false;
   if (p->n_primitive < 0 || p->n_primitive > UD_MAX_PRIM) return false;
   if (p->sdf_kind != UD_SDF_BOX && p->sdf_kind != UD_SDF_CONTAINER) return false;
+  if (p->p2g_mode != UD_P2G_ATOMIC && p->p2g_mode != UD_P2G_DETERMINISTIC) return false;
   if (!(p->dt > 0) || !(p->dx > 0) || !(p->inv_dx > 0) || !(p->p_mass > 0) || !(p->p_vol > 0)) return false;
   long long N = (long long)p->num_envs * p->n_particles;
   long long G = (long long)p->res[0] * p->res[1] * p->res[2];
@@ -136,6 +137,7 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
     w.g_act = (float*)take(4 * (size_t)k.B * P * 6);
     w.norm2 = (float*)take(4 * (size_t)k.B * 2);
   }
+  if (k.p2g_mode == UD_P2G_DETERMINISTIC) w.grid_fix = (long long*)take(32 * BG);
   w.bytes = off;
   if (ws) *ws = w;
   return off;
@@ -245,10 +247,11 @@ int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   launch_fk_fwd(k, in, action, out, ws, st);
   zero_async(ws.jrows, 4 * (size_t)k.B * k.S * 9, st);
   for (int f = 0; f < k.S; ++f) {
-    zero_async(ws.grid_raw, 16 * (size_t)k.B * k.G, st);
+    if (ws.grid_fix) zero_async(ws.grid_fix, 32 * (size_t)k.B * k.G, st);
+    else zero_async(ws.grid_raw, 16 * (size_t)k.B * k.G, st);
     launch_p2g(k, ws.ps, ws.ps, ws.grid_raw, in->mu, in->lamda, (g_svd_warm && (f % SVD_RESTART)) ? ws.vt_roll : nullptr, ws.vt_roll,
                nullptr, ws, st);
-    launch_grid_fwd(k, ws.grid_raw, ws.grid_raw, f, in, ws, st);
+    launch_grid_fwd(k, ws.grid_raw, ws.grid_raw, ws.grid_fix, f, in, ws, st);
     launch_g2p(k, ws.ps, ws.ps, ws.grid_raw, f, ws, st);
   }
   launch_unsort_state(k, ws.ps, in->J, ws, out, st);
@@ -278,15 +281,16 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   launch_sort(k, in->x, ws, nullptr, st);
   launch_gather_state(k, in, material, h, ws, ws.ps, st);
   launch_fk_fwd(k, in, action, nullptr, ws, st);
-  zero_async(ws.grid_raw, 16 * BG * k.S, st);
+  if (!ws.grid_fix) zero_async(ws.grid_raw, 16 * BG * k.S, st);
   for (int f = 0; f < k.S; ++f) {
     const float* s_in = ws.ps + slot * f;
     float* s_out = ws.ps + slot * (f + 1);
+    if (ws.grid_fix) zero_async(ws.grid_fix, 32 * BG, st);
     float* sv_f = ws.svd_s + (size_t)SV_NCOMP * k.N * f;
     launch_p2g(k, s_in, s_out, ws.grid_raw + BG * f, in->mu, in->lamda,
                (g_svd_warm && (f % SVD_RESTART)) ? sv_f - (size_t)SV_NCOMP * k.N + (size_t)SV_VT * k.N : nullptr, nullptr,
                sv_f, ws, st);
-    launch_grid_fwd(k, ws.grid_raw + BG * f, ws.grid_out + BG * f, f, in, ws, st);
+    launch_grid_fwd(k, ws.grid_raw + BG * f, ws.grid_out + BG * f, ws.grid_fix, f, in, ws, st);
     launch_g2p(k, s_in, s_out, ws.grid_out + BG * f, f, ws, st);
   }
   // ---- reverse pass

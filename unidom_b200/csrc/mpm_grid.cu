@@ -148,12 +148,21 @@ UD_DEV void load_prim_f(const MpmConst& k, const ud_mpm_state& in, const float* 
 }
 
 __global__ void __launch_bounds__(128)
-k_grid_fwd(MpmConst k, const float4* grid_in, float4* grid_out, int f,
+k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, const long long* __restrict__ grid_fix, int f,
            ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
            const float* __restrict__ fk_vw) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)k.B * k.G) return;
-  float4 g = grid_in[idx];
+  float4 g;
+  if (grid_fix) {  // deterministic P2G: fixed-point accumulators -> float {p, m}
+    const longlong2 a = reinterpret_cast<const longlong2*>(grid_fix)[2 * idx];
+    const longlong2 b = reinterpret_cast<const longlong2*>(grid_fix)[2 * idx + 1];
+    g = make_float4((float)((double)a.x * FIX_INV), (float)((double)a.y * FIX_INV), (float)((double)b.x * FIX_INV),
+                    (float)((double)b.y * FIX_INV));
+    if (grid_out != grid_in) grid_in[idx] = g;  // the adjoint reads the raw grid
+  } else {
+    g = grid_in[idx];
+  }
   if (!(g.w > 0.f)) {
     if (grid_out != grid_in) grid_out[idx] = g;
     return;
@@ -170,10 +179,10 @@ k_grid_fwd(MpmConst k, const float4* grid_in, float4* grid_out, int f,
   grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
 }
 
-void launch_grid_fwd(const MpmConst& k, const float4* grid_in, float4* grid_out, int substep,
+void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const long long* grid_fix, int substep,
                      const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st) {
   KScope ks_(KC_GRID, st);
-  k_grid_fwd<<<cdiv((long long)k.B * k.G, 128), 128, 0, st>>>(k, grid_in, grid_out, substep, *in, ws.fk_pos,
+  k_grid_fwd<<<cdiv((long long)k.B * k.G, 128), 128, 0, st>>>(k, grid_in, grid_out, grid_fix, substep, *in, ws.fk_pos,
                                                               ws.fk_rot, ws.fk_vw);
 }
 

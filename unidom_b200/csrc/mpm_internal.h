@@ -16,6 +16,9 @@ constexpr int PS_X = 0, PS_V = 3, PS_C = 6, PS_F = 15, PS_NCOMP = 24;
 constexpr int SV_U = 0, SV_S = 9, SV_VT = 12, SV_NCOMP = 21;
 // the SVD warm-start chain restarts from V = I every SVD_RESTART substeps (bounds rounding drift of V)
 constexpr int SVD_RESTART = 16;
+// deterministic P2G: values are accumulated as round(v * 2^52) in int64 (range +-2048, resolution 2.2e-16);
+// integer addition is associative, so the result is independent of the order the REDs arrive in
+constexpr double FIX_SCALE = 4503599627370496.0, FIX_INV = 1.0 / 4503599627370496.0;
 // per-env scalar cotangent accumulators (bwd)
 //   0 friction, 1 mu, 2 lamda, then per primitive q: 3+4q .. : size(3), friction(1)
 constexpr int GS_FRICTION = 0, GS_MU = 1, GS_LAMDA = 2, GS_PRIM = 3, GS_PRIM_STRIDE = 4;
@@ -34,6 +37,7 @@ struct MpmWs {
   float* ps;            // fwd: [24*N]; bwd: [(S+1)*24*N] start-of-substep states
   float4* grid_raw;     // fwd: [B*G]; bwd: [S*B*G] scattered (p,m)
   float4* grid_out;     // fwd: == grid_raw; bwd: [S*B*G] updated velocities
+  long long* grid_fix;  // deterministic P2G only: [B*G*4] 64-bit fixed-point accumulators of one substep
   float* vt_roll;       // fwd only: [9*N] V^T of the previous substep's SVD (warm start)
   float* svd_s;         // bwd only: [S*21*N] SVD of F1 per substep (written by the recompute P2G)
   float* fk_pos;        // [B*P*(S+1)*3] (row S = clamp copy of row S-1)
@@ -93,7 +97,9 @@ void launch_finish_bwd(const MpmConst& k, const ud_mpm_state* in, const ud_mpm_s
 // Launchers implemented in mpm_grid.cu (compiled with --fmad=false)
 void launch_fk_fwd(const MpmConst& k, const ud_mpm_state* in, const float* action, ud_mpm_state* out,
                    const MpmWs& ws, cudaStream_t st);
-void launch_grid_fwd(const MpmConst& k, const float4* grid_in, float4* grid_out, int substep,
+// grid_fix != null (deterministic P2G): the raw {p,m} is first converted from the fixed-point accumulators
+// into grid_in (which the adjoint reads later), then updated into grid_out.
+void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const long long* grid_fix, int substep,
                      const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st);
 void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,
                      const MpmWs& ws, cudaStream_t st);

@@ -236,7 +236,7 @@ __device__ __forceinline__ int stage_group(StageMeta& m, int key, const int base
 // (run, node): scalar REDs cost ~4x more L2 atomic work (measured: 76 of 236 us in k_p2g).
 // The 27 nodes are staged in windows of NPH nodes ([j0, j0+nj)), which divides the shared-memory
 // footprint (and multiplies the resident CTAs per SM) without changing the amount of flush work.
-template <int NC, bool CLAMP>
+template <int NC, bool CLAMP, bool DET = false>
 __device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __restrict__ sv, const StageMeta& m,
                                             float4* __restrict__ genv, int j0, int nj) {
   const int t = threadIdx.x;
@@ -279,7 +279,16 @@ __device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __re
       iz = idx_scatter(m.base[s0][2] + cc, k.rz);
       if ((ix | iy | iz) < 0) continue;
     }
-    atomicAdd(&genv[(ix * k.ry + iy) * k.rz + iz], val);
+    const int cell = (ix * k.ry + iy) * k.rz + iz;
+    if (DET) {  // UD_P2G_DETERMINISTIC: 4 integer REDs on 64-bit fixed point (associative => order-independent)
+      unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(genv) + 4 * (size_t)cell;
+      atomicAdd(acc64 + 0, (unsigned long long)__double2ll_rn((double)val.x * FIX_SCALE));
+      atomicAdd(acc64 + 1, (unsigned long long)__double2ll_rn((double)val.y * FIX_SCALE));
+      atomicAdd(acc64 + 2, (unsigned long long)__double2ll_rn((double)val.z * FIX_SCALE));
+      atomicAdd(acc64 + 3, (unsigned long long)__double2ll_rn((double)val.w * FIX_SCALE));
+    } else {
+      atomicAdd(&genv[cell], val);
+    }
   }
 }
 constexpr size_t stage_smem_bytes(int nc, int nph) { return sizeof(float) * nph * nc * STG_PAD + sizeof(StageMeta); }
@@ -303,6 +312,7 @@ UD_DEV void load_particle(const float* ps, size_t N, int g, float x[3], float v[
   for (int c = 0; c < 9; ++c) F.m[c] = ps[(PS_F + c) * N + g];
 }
 
+template <bool DET>
 __global__ void __launch_bounds__(UD_BLOCK)
 k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
@@ -379,7 +389,9 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       }
     }
     __syncthreads();
-    stage_flush<4, false>(k, sv, meta, grid + (size_t)env * k.G, j0, (27 - j0) < P2G_NPH ? (27 - j0) : P2G_NPH);
+    // DET: `grid` is the int64 accumulator array (32 B per cell = 2 float4 slots per cell)
+    stage_flush<4, false, DET>(k, sv, meta, grid + (size_t)env * k.G * (DET ? 2 : 1), j0,
+                               (27 - j0) < P2G_NPH ? (27 - j0) : P2G_NPH);
   }
 }
 
@@ -390,11 +402,16 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
   KScope ks_(KC_P2G, st);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_p2g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4, P2G_NPH));
+    cudaFuncSetAttribute(k_p2g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4, P2G_NPH));
+    cudaFuncSetAttribute(k_p2g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4, P2G_NPH));
     attr_set = true;
   }
-  k_p2g<<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4, P2G_NPH), st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s,
-                                                                    vt_in, vt_out, svd_out);
+  if (ws.grid_fix)
+    k_p2g<true><<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4, P2G_NPH), st>>>(
+        k, ps_in, ps_out, reinterpret_cast<float4*>(ws.grid_fix), mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out);
+  else
+    k_p2g<false><<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4, P2G_NPH), st>>>(
+        k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out);
 }
 
 // ------------------------------------------------------------------------------------------------
