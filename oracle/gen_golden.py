@@ -283,6 +283,66 @@ def cloth_case(mods, name, float_stiffness, seed, from_reset, B=2, n_calls=1, gr
           + (f"  |g_x|max={np.abs(out['g_x']).max():.3e} |g_action|max={np.abs(out['g_action']).max():.3e}" if grads else ""))
 
 
+def cloth_env_case(name, ep_len, B, seed):
+    """Env level (the callers of the step): the reference's FoldCloth3Env.step_diff (cloth_env.py:204-231) with
+    get_pnp_actions / calc_chamfer / get_obs as they are, driven by the APG rollout of apg.py:177-215 with the
+    policy MLP written in torch (brax/flax are not importable; weights and sampling noise are fixtures)."""
+    sys.path.insert(0, os.path.join(HERE, "jaxshim"))
+    import stubs
+    stubs.install()
+    import torch
+    import jax
+    import jax.numpy as jnp
+    from daxbench.core.envs import fold_cloth3_env
+    from daxbench.core.utils import util as rutil
+    sys.path.insert(0, ROOT)
+    from unidom_b200 import apg
+    rng = np.random.RandomState(seed)
+    env = fold_cloth3_env.FoldCloth3Env(batch_size=B, aux_reward=True)
+    obs0, st = env.reset(jax.random.PRNGKey(0))
+    shift = rng.randn(2).astype(np.float32) * 0.05                        # cloth_env.py:183 with a seeded numpy draw
+    x0 = np.asarray(env.simulator.reset_jax().x).copy()
+    x0[..., 0] += shift[0]
+    x0[..., 2] += shift[1]
+    st = st._replace(x=jnp.array(x0))
+    params = apg.init_policy(env.observation_size, env.action_size, seed=seed)
+    params[-1] = params[-1] + torch.tensor([0.0, 0.0, 0.0, 0.6, 0.0, 0.4, -2, -2, -2, -2, -2, -2])   # aim at the cloth
+    eps = torch.from_numpy(rng.randn(ep_len, B, env.action_size).astype(np.float32))
+    out = {"goal": np.asarray(env.goal), "eps": eps.numpy(), "shift": shift, "ep_len": np.array(ep_len),
+           "policy_seed": np.array(seed), "param5": params[-1].numpy()}      # weights are regenerated from the seed
+    for k in CLOTH_F:
+        out["in_" + k] = np.asarray(getattr(st, k))
+    req = [p.clone().requires_grad_(True) for p in params]
+    rewards, state = [], st
+    for t in range(ep_len):
+        obs = env.get_obs(state)
+        actions = apg.sample_actions(apg.policy_apply(req, obs.t), eps[t], True)
+        out[f"actions{t}"] = actions.detach().numpy()
+        out[f"obs{t}"] = np.asarray(obs)
+        if t == 0:
+            out["pnp0"] = np.asarray(env.get_pnp_actions(jax.numpy.array(actions.detach().numpy()), state))
+            out["chamfer0"] = np.asarray(rutil.calc_chamfer(state.x, env.goal))
+        _, reward, done, info = env.step_diff(jax.Array(actions), state)
+        state = info["state"]
+        rewards.append(reward.t)
+        out[f"reward{t}"] = reward.t.detach().numpy()
+        out[f"real_reward{t}"] = np.asarray(info["real_reward"].t.detach())
+        out[f"x{t + 1}"] = state.x.t.detach().numpy()
+        out[f"v{t + 1}"] = state.v.t.detach().numpy()
+        out[f"primitive0_{t + 1}"] = state.primitive0.t.detach().numpy()
+    loss = -torch.stack(rewards).mean()
+    grads = torch.autograd.grad(loss, req)
+    out["loss"] = loss.detach().numpy()
+    # the first two layers' gradients (3.7 MB) follow from the last layer's by the same torch MLP backward on both
+    # sides; the fixture keeps layer 3 (W3, b3) and the full-gradient norm
+    out["gparam4"], out["gparam5"] = grads[4].numpy(), grads[5].numpy()
+    out["gnorm"] = np.array(float(torch.sqrt(sum((g * g).sum() for g in grads))))
+    path = os.path.join(GOLD, f"ref_clothenv_{name}.npz")
+    np.savez_compressed(path, **out)
+    gn = float(torch.sqrt(sum((g * g).sum() for g in grads)))
+    print(f"wrote {path}: ep_len={ep_len} B={B} loss={float(loss):.6f} |grad|={gn:.4e}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--real-jax", action="store_true")
@@ -309,6 +369,9 @@ def main():
         "cloth_w1_contact": lambda: cloth_case(mods, "w1_contact", True, 27, False, window=1, contact=True),
         "cloth_w4_contact": lambda: cloth_case(mods, "w4_contact", False, 28, False, window=4, contact=True),
     }
+    cases["clothenv_ep1"] = lambda: cloth_env_case("ep1", 1, 2, 31)
+    # BASELINE.json configs[0]: fold_cloth3 APG ep_len=3 num_envs=4 (reference states + policy gradient; ~20 min here)
+    cases["clothenv_ep3"] = lambda: cloth_env_case("ep3", 3, 4, 0)
     for name, fn in cases.items():
         if args.only and args.only not in name:
             continue

@@ -207,9 +207,13 @@ class _AtKey:
             idx = [(i[keep] if isinstance(i, torch.Tensor) and i.dtype == torch.int64 else i) for i in idx]
             if val.dim() > 0 and val.shape[0] == keep.shape[0]:
                 val = val[keep]
-        if arrs and accumulate:
-            if not all(it[0] == "arr" for it in items[:len(arrs)]) or any(it[0] not in ("arr", "slice") for it in items):
-                raise NotImplementedError("jaxshim: .at[].add with a mixed key")
+        leading = all(it[0] == "arr" for it in items[:len(arrs)]) and all(it[0] in ("arr", "slice") for it in items)
+        if arrs and accumulate and not leading:
+            # slices before the index array: supported when the index array has no duplicates (then add == set of sum)
+            for _, it in arrs:
+                assert it[1].numel() == it[1].unique().numel(), "jaxshim: duplicate indices in a mixed .at[].add key"
+            new[tuple(idx)] = new[tuple(idx)] + val
+        elif arrs and accumulate:
             ia = tuple(i for i in idx[:len(arrs)])
             shape = torch.broadcast_shapes(*[i.shape for i in ia]) + new.shape[len(arrs):]
             new.index_put_(ia, val.expand(shape), accumulate=True)

@@ -1,0 +1,94 @@
+"""Env level (the callers of the step): `unidom_b200.envs.ClothEnv` and the APG rollout against golden vectors of
+the reference's own FoldCloth3Env.step_diff + get_pnp_actions + calc_chamfer (run under oracle/jaxshim by
+oracle/gen_golden.py::cloth_env_case).  CPU tests cover the pure host functions; GPU tests the full env step."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import util
+from unidom_b200 import apg, confs
+
+CASES = [n for n in ("ep1", "ep3") if os.path.exists(os.path.join(util.GOLD, f"ref_clothenv_{n}.npz"))]
+
+
+def _load(name):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in np.load(os.path.join(util.GOLD, f"ref_clothenv_{name}.npz")).items()}
+
+
+def _state(d, device):
+    from unidom_b200.cloth_simulator import ClothState
+    B = d["in_x"].shape[0]
+    z = torch.zeros((B, 2), dtype=torch.int32)
+    return ClothState(x=d["in_x"], v=d["in_v"], primitive0=d["in_primitive0"], primitive1=d["in_primitive1"],
+                      action0=d["in_action0"], action1=d["in_action1"], key=z, cur_step=z[:, 0].clone(),
+                      stiffness=d["in_stiffness"], mu=d["in_mu"])._replace() if device == "cpu" else None
+
+
+def _policy(d):
+    params = apg.init_policy(512 * 3 + 8, 6, seed=int(d["policy_seed"]))
+    params[-1] = d["param5"].clone()
+    return params
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_functions_match_reference(name):
+    """get_pnp_actions (cloth_env.py:136-173), calc_chamfer (util.py:138-153), get_obs, policy sampling: exact."""
+    from unidom_b200 import envs
+    from unidom_b200.cloth_simulator import ClothState
+    d = _load(name)
+    B = d["in_x"].shape[0]
+    z = torch.zeros((B, 2), dtype=torch.int32)
+    st = ClothState(x=d["in_x"], v=d["in_v"], primitive0=d["in_primitive0"], primitive1=d["in_primitive1"],
+                    action0=d["in_action0"], action1=d["in_action1"], key=z, cur_step=z[:, 0].clone(),
+                    stiffness=d["in_stiffness"], mu=d["in_mu"])
+    obs = torch.cat([st.x.flatten(1), st.primitive0, st.primitive1], dim=1)
+    assert torch.equal(obs, d["obs0"])
+    actions = apg.sample_actions(apg.policy_apply(_policy(d), obs), d["eps"][0], True)
+    assert util.rel_err(actions, d["actions0"]) < 1e-6
+    sub = envs.get_pnp_actions(d["actions0"], st)
+    assert sub.shape == d["pnp0"].shape and util.rel_err(sub, d["pnp0"]) < 1e-7
+    ch = envs.calc_chamfer(st.x, d["goal"])
+    assert util.rel_err(ch, d["chamfer0"]) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_env_rollout_and_policy_gradient_vs_reference(built_lib, name):
+    """BASELINE configs[0] (fold_cloth3 APG): the full rollout is 2 000 chaotic substeps per env step, so states
+    are compared loosely and printed next to the reward / loss / policy-gradient agreement."""
+    from unidom_b200 import envs
+    from unidom_b200.cloth_simulator import ClothState
+    d = _load(name)
+    B, ep_len = d["in_x"].shape[0], int(d["ep_len"])
+    conf = confs.ClothConf()
+    env = envs.ClothEnv(conf, B, 4, confs.fold_cloth_mask(conf), goal=d["goal"].numpy(), aux_reward=True)
+    dev = env.device
+    z = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+    st = ClothState(x=d["in_x"].to(dev), v=d["in_v"].to(dev), primitive0=d["in_primitive0"].to(dev),
+                    primitive1=d["in_primitive1"].to(dev), action0=d["in_action0"].to(dev), action1=d["in_action1"].to(dev),
+                    key=z, cur_step=z[:, 0].clone(), stiffness=d["in_stiffness"].to(dev), mu=d["in_mu"].to(dev))
+    params = [p.to(dev).requires_grad_(True) for p in _policy(d)]
+    eps = d["eps"].to(dev)
+    # rollout, keeping the per-step states for the comparison
+    rewards, state = [], st
+    for t in range(ep_len):
+        obs = env.get_obs(state)
+        actions = apg.sample_actions(apg.policy_apply(params, obs), eps[t], True)
+        _, reward, _, info = env.step_diff(actions, state)
+        state = info["state"]
+        rewards.append(reward)
+        ex = util.rel_err(state.x, d[f"x{t + 1}"])
+        er = util.rel_err(reward, d[f"reward{t}"])
+        print(f"clothenv {name} step {t}: x rel {ex:.3e}  reward rel {er:.3e}  (reward {reward.tolist()} ref {d[f'reward{t}'].tolist()})")
+        assert util.rel_err(state.primitive0, d[f"primitive0_{t + 1}"]) < 1e-5
+        assert ex < 0.2 and er < 0.05, (t, ex, er)
+    loss = -torch.stack(rewards).mean()
+    grads = torch.autograd.grad(loss, params)
+    gn = float(torch.sqrt(sum((g * g).sum() for g in grads)))
+    print(f"clothenv {name}: loss {float(loss):.6f} ref {float(d['loss']):.6f}   |grad| {gn:.4e} ref {float(d['gnorm']):.4e}")
+    for i in (4, 5):
+        cs, e = util.cosine(grads[i], d[f"gparam{i}"]), util.rel_err(grads[i], d[f"gparam{i}"])
+        print(f"clothenv {name}: policy gradient layer-3 param {i}: cos {cs:.6f} rel {e:.3e}")
+    assert abs(float(loss) - float(d["loss"])) < 0.02 * abs(float(d["loss"]))

@@ -56,7 +56,7 @@ def test_mpm_cuda_matches_reference_golden(built_lib, name):
 
 @pytest.mark.parametrize("name", CLOTH_CASES)
 def test_cloth_cuda_matches_reference_golden(built_lib, name):
-    from oracle import cloth as oc      # conf + mask helpers only (host-side scene description)
+    from unidom_b200 import confs as oc
     from unidom_b200.cloth_simulator import ClothSimulator, ClothState
     d = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in np.load(os.path.join(util.GOLD, f"ref_cloth_{name}.npz")).items()}
     conf = oc.ClothConf()

@@ -1,0 +1,126 @@
+"""Analytic policy gradient (APG) around the B200 simulator step: the caller of `env.step_diff` and the ONLY
+collective of the path.
+
+Mirrors DaXBench/daxbench/algorithms/apg/apg.py:
+  policy   make_direct_optimization_model (:353-358): MLP obs -> 512 -> 256 -> 2A, swish
+  sampling brax NormalTanhDistribution: a = tanh(loc + (softplus(raw_scale) + 0.001) * eps); cloth envs apply
+           sigmoid on top (:181-186)
+  loss     -mean(rewards) over a lax.scan of ep_len env steps (:207-215)
+  update   nan_to_num -> per-device global-norm clip -> pmean over devices -> adam (:233-240, 260-267)
+
+Multi-GPU: one process per GPU; rank r simulates envs [r*B/N, (r+1)*B/N) (:83-85); the policy gradient lives in
+ONE flat fp32 buffer that is scrubbed and clipped per rank and then averaged with a single all-reduce
+(NCCL over NVLink on the GPU box, gloo in the CPU tests).  The ORDER matters for parity: clip BEFORE the mean.
+All tensor math here is device-agnostic torch (it is plumbing around the kernels, 0.9 M parameters).
+"""
+import math
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as Fnn
+
+
+def shard_envs(num_envs: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """apg.py:83-85: num_envs // devices per device; returns (first env, envs on this rank)."""
+    if num_envs % world_size:
+        raise ValueError(f"num_envs={num_envs} is not divisible by the number of devices ({world_size})")
+    per = num_envs // world_size
+    return rank * per, per
+
+
+def init_policy(obs_size: int, action_size: int, seed: int = 0, device="cpu") -> List[torch.Tensor]:
+    """[W1,b1,W2,b2,W3,b3] of the 512-256-2A MLP.  LeCun-uniform kernels / zero biases like flax's Dense default;
+    the PRNG stream is torch's (brax's threefry init is not reproducible here), so weights are an INPUT of parity
+    tests, never compared across frameworks."""
+    g = torch.Generator().manual_seed(seed)
+    sizes = [obs_size, 512, 256, 2 * action_size]
+    params = []
+    for fan_in, fan_out in zip(sizes[:-1], sizes[1:]):
+        lim = math.sqrt(3.0 / fan_in)
+        params.append(((torch.rand((fan_in, fan_out), generator=g) * 2 - 1) * lim).to(device))
+        params.append(torch.zeros(fan_out, device=device))
+    return params
+
+
+def policy_apply(params: List[torch.Tensor], obs: torch.Tensor) -> torch.Tensor:
+    h = obs
+    for i in range(0, len(params), 2):
+        h = h @ params[i] + params[i + 1]
+        if i + 2 < len(params):
+            h = Fnn.silu(h)           # linen.swish
+    return h
+
+
+def sample_actions(logits: torch.Tensor, eps: torch.Tensor, sigmoid: bool = True) -> torch.Tensor:
+    """NormalTanhDistribution.sample (brax 0.0.13, min_std = 0.001) followed by apg.py:185-186."""
+    loc, raw_scale = logits.chunk(2, dim=-1)
+    a = torch.tanh(loc + (Fnn.softplus(raw_scale) + 0.001) * eps)
+    return torch.sigmoid(a) if sigmoid else a
+
+
+def apg_loss(env, params, state, eps: torch.Tensor, sigmoid: bool = True):
+    """apg.py:177-215: roll the policy through `ep_len = eps.shape[0]` env steps; loss = -mean(reward)."""
+    rewards = []
+    for t in range(eps.shape[0]):
+        obs = env.get_obs(state)
+        actions = sample_actions(policy_apply(params, obs), eps[t], sigmoid)
+        _, reward, _, info = env.step_diff(actions, state)
+        state = info["state"]
+        rewards.append(reward)
+    rewards = torch.stack(rewards)
+    return -rewards.mean(), rewards, state
+
+
+def flatten(tensors) -> torch.Tensor:
+    return torch.cat([t.reshape(-1) for t in tensors])
+
+
+def unflatten(flat: torch.Tensor, like) -> List[torch.Tensor]:
+    out, o = [], 0
+    for t in like:
+        out.append(flat[o:o + t.numel()].view_as(t))
+        o += t.numel()
+    return out
+
+
+def reduce_policy_gradient(flat_grad: torch.Tensor, max_grad_norm: float, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """apg.py:233-235 + :260-267 on one flat buffer, in the reference's order:
+    nan_to_num (per rank) -> clip to max_grad_norm by the per-rank global norm -> mean over ranks.
+    Returns (reduced gradient, this rank's raw gradient norm = the `grad_norm` metric of :242)."""
+    g = torch.nan_to_num(flat_grad)
+    g_norm = torch.sqrt((g * g).sum())
+    g = torch.where(g_norm < max_grad_norm, g, (g / g_norm) * max_grad_norm)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)       # one collective per iteration
+        g = g / dist.get_world_size(group)
+    return g, g_norm
+
+
+class Adam:
+    """optax.adam(lr) (b1 0.9, b2 0.999, eps 1e-8, eps_root 0) on the flat parameter buffer."""
+
+    def __init__(self, n: int, lr: float, device):
+        self.lr, self.b1, self.b2, self.eps = lr, 0.9, 0.999, 1e-8
+        self.m = torch.zeros(n, device=device)
+        self.v = torch.zeros(n, device=device)
+        self.t = 0
+
+    def step(self, flat_params: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+        self.t += 1
+        self.m = self.b1 * self.m + (1 - self.b1) * g
+        self.v = self.b2 * self.v + (1 - self.b2) * g * g
+        mhat = self.m / (1 - self.b1 ** self.t)
+        vhat = self.v / (1 - self.b2 ** self.t)
+        return flat_params - self.lr * mhat / (torch.sqrt(vhat) + self.eps)
+
+
+def train_iteration(env, params, opt: Adam, state, eps, max_grad_norm: float, sigmoid: bool = True, group=None):
+    """One `minimize` call (apg.py:217-258) on this rank's env shard.  Returns (new params, metrics)."""
+    req = [p.detach().clone().requires_grad_(True) for p in params]
+    loss, rewards, _ = apg_loss(env, req, state, eps, sigmoid)
+    grads = torch.autograd.grad(loss, req)
+    g, g_norm = reduce_policy_gradient(flatten(grads), max_grad_norm, group)
+    new_flat = opt.step(flatten([p.detach() for p in params]), g)
+    new_params = unflatten(new_flat, params)
+    return new_params, {"loss": float(loss), "reward": rewards.detach(), "grad_norm": float(g_norm)}

@@ -86,3 +86,36 @@ def build_shape_elasto_plastic(sim, density=3.0):
     state.primitives.append(create_primitive(conf, friction=0.1, softness=666, color=[0.5, 0.5, 0.5],
                                              size=[0.015, 0.06, 0.015], init_pos=[0.5, 0.01, 0.45]))
     return sim.reset_jax(state)
+
+
+class ClothConf:
+    """envs/fold_cloth3_env.py:18-37 (shared by fold_cloth1/3, unfold_cloth1/3; fold_cloth1_para randomises
+    `stiffness` per env, fold_cloth1_para_env.py:15-33)."""
+    N = 80
+    gravity = 0.5
+    stiffness = 900
+    damping = 2
+    dt = 2e-3
+    max_v = 2.0
+    small_num = 1e-8
+    mu = 0.5
+    seed = 1
+    mem_saving_level = 2
+    task = "fold_cloth3"
+
+    @property
+    def cell_size(self):
+        return 1.0 / self.N
+
+    @property
+    def size(self):
+        return int(self.N / 5.0)
+
+
+def fold_cloth_mask(conf):
+    """create_cloth_mask, envs/fold_cloth3_env.py:51-56: a 16 x 32 patch of the N x N board (512 nodes)."""
+    import numpy as np
+    N, size = conf.N, conf.size
+    m = np.zeros((N, N), dtype=np.float32)
+    m[size * 2:size * 3, size * 2:size * 4] = 1
+    return m

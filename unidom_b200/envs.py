@@ -1,0 +1,101 @@
+"""Host-side mirror of the reference's env wrappers around the simulator step (the callers of the hot path).
+
+Mirrors DaXBench/daxbench/core/envs/basic/cloth_env.py (ClothEnv: get_obs :97-132, get_pnp_actions :136-173,
+reset :178-188, step_diff :204-231) and core/utils/util.py (calc_chamfer :138-153, calc_l2 :156-159).
+Everything here is glue around `ClothSimulator.step_jax` (the B200 kernels): torch ops on the simulator's
+device, differentiable through torch autograd so that APG's rollout gradient reaches the policy.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .cloth_simulator import ClothSimulator, ClothState
+
+
+def calc_chamfer(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """util.py:138-153.  x (B,P,3), y (Q,3) -> (B,).  Note the reference's distance is sqrt(mean(d^2)) over the
+    3 coordinates, not the Euclidean norm."""
+    d = torch.sqrt(((x[:, :, None, :] - y[None, None, :, :]) ** 2).mean(-1))     # (B,P,Q)
+    x2y = d.min(-1).values.mean(1)
+    y2x = d.min(-2).values.mean(1)
+    return y2x + x2y
+
+
+def calc_l2(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """util.py:156-159."""
+    return torch.sqrt(((x - y[None]) ** 2).mean(-1)).mean(-1)
+
+
+def get_pnp_actions(actions: torch.Tensor, state: ClothState) -> torch.Tensor:
+    """cloth_env.py:136-173, batched: pick-and-place (B,6) -> 40 sub-actions (40,B,8):
+    3 approach (suction 1) + 10 lift + 20 move + 7 release; the second gripper's half is zero."""
+    B, dev, dt = actions.shape[0], actions.device, actions.dtype
+    zero = torch.zeros((B, 1), device=dev, dtype=dt)
+    pick = torch.cat([actions[:, 0:1], zero, actions[:, 2:3]], dim=1)
+    place = torch.cat([actions[:, 3:4], zero, actions[:, 5:6]], dim=1)
+    act_down = torch.cat([(pick - state.primitive0[:, :3]) / 3, torch.ones((B, 1), device=dev, dtype=dt)], dim=1)
+    act_down = act_down[None].expand(3, B, 4)
+    up = torch.tensor([0.0, 0.06, 0.0], device=dev, dtype=dt) / 10
+    act_up = torch.cat([up, torch.zeros(1, device=dev, dtype=dt)])[None, None].expand(10, B, 4)
+    mv = place - pick
+    mv = torch.cat([mv[:, 0:1], zero, mv[:, 2:3]], dim=1)
+    act_move = torch.cat([mv / 20, zero], dim=1)[None].expand(20, B, 4)
+    act_release = torch.tensor([0.0, 0.0, 0.0, 1.0], device=dev, dtype=dt)[None, None].expand(7, B, 4)
+    sub = torch.cat([act_down, act_up, act_move, act_release], dim=0)
+    return torch.cat([sub, torch.zeros_like(sub)], dim=2)
+
+
+class ClothEnv:
+    """B200 drop-in for the reference's ClothEnv (fold_cloth1/3, unfold_cloth1/3, fold_cloth1_para)."""
+
+    def __init__(self, conf, batch_size, max_steps, cloth_mask, goal=None, aux_reward=False, device="cuda",
+                 para=False):
+        self.conf, self.batch_size, self.max_steps, self.aux_reward = conf, batch_size, max_steps, aux_reward
+        self.simulator = ClothSimulator(conf, batch_size, None, cloth_mask, device=device)
+        self.device = self.simulator.device
+        self.action_size = 6
+        self.para = para                                     # cloth_env_para.py: obs carries the normalised stiffness
+        n = self.simulator.n_nodes
+        self.observation_size = n * 3 + 8 + (1 if para else 0)
+        goal = np.zeros((1, 3), np.float32) if goal is None else np.asarray(goal, np.float32)
+        self.goal = torch.from_numpy(goal).to(self.device)
+
+    def get_obs(self, state: ClothState) -> torch.Tensor:
+        """cloth_env.py:119-128 (PARTICLE): [x.flatten(), primitive0, primitive1] (+ stiffness/2000, cloth_env_para.py:130)."""
+        parts = [state.x.flatten(1), state.primitive0, state.primitive1]
+        if self.para:
+            parts.append((state.stiffness.to(state.x.dtype) / 2000.0)[:, None])
+        return torch.cat(parts, dim=1)
+
+    def reset(self, shift_xz=None):
+        """cloth_env.py:178-188: the lattice plus ONE N(0, 0.05^2) xz shift shared by all envs.  The reference
+        draws it from threefry (not reproducible here); pass `shift_xz` (2,) or get a seeded numpy draw."""
+        st = self.simulator.reset_jax()
+        if shift_xz is None:
+            shift_xz = np.random.RandomState(getattr(self.conf, "seed", 1)).randn(2).astype(np.float32) * 0.05
+        sh = torch.as_tensor(shift_xz, dtype=st.x.dtype, device=self.device)
+        x = st.x.clone()
+        x[..., 0] += sh[0]
+        x[..., 2] += sh[1]
+        st = st._replace(x=x)
+        return self.get_obs(st), st
+
+    def step_diff(self, actions: torch.Tensor, state: ClothState):
+        """cloth_env.py:204-231: 40 sub-actions x 50 substeps through the simulator, reward
+        e^(-10 chamfer) (+ e^(-contact)) * 0.99^cur_step."""
+        old_chamfer = calc_chamfer(state.x, self.goal)
+        contact = torch.sqrt(((actions[:, None, :3] - state.x) ** 2).sum(-1)).min(-1).values
+        sub = get_pnp_actions(actions, state)
+        for a in sub:                                   # lax.scan(self.simulator.step_jax, ...) (:211)
+            state, _ = self.simulator.step_jax(state, a)
+        state = state._replace(cur_step=state.cur_step + 1)
+        obs = self.get_obs(state)
+        chamfer = calc_chamfer(state.x, self.goal)
+        reward = math.e ** (-chamfer * 10)
+        if self.aux_reward:
+            reward = reward + math.e ** (-contact)
+        reward = reward * 0.99 ** state.cur_step.to(reward.dtype)
+        done = state.cur_step >= self.max_steps
+        info = {"state": state, "real_reward": old_chamfer - chamfer + 0.1 * contact}
+        return obs, reward, done, info
