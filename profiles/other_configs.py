@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Throughput / memory of the BASELINE.json configs that are NOT the bench line (configs[2..4]), one GPU:
+  pour_water   synthetic 99 998 liquid particles/env, 16 envs (= 128 envs over 8 GPUs), 2 bowl colliders, S=23
+  whip_rope    long horizon: density 25 -> ~49 k particles, S=70 substeps/step, position control; peak HBM of an
+               episode with step-granularity checkpoints vs the store-every-substep estimate
+  fold_cloth1_para  128 envs/GPU (= 1024 over 8), float stiffness: cloth sub-action fwd+bwd
+Prints one JSON line per config (run on the GPU box:  python profiles/other_configs.py > gpurun_out/other.jsonl)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from unidom_b200 import _lib, confs  # noqa: E402
+from unidom_b200.cloth_simulator import ClothSimulator  # noqa: E402
+from unidom_b200.mpm_simulator import SimpleMPMSimulator, create_primitive  # noqa: E402
+
+
+def timed(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def mpm_fwd_bwd(sim, state, action):
+    leaves = {k: getattr(state, k).detach().requires_grad_(True) for k in ("x", "v", "C", "F")}
+    a = action.detach().requires_grad_(True)
+    out, _ = sim.step_jax(state._replace(**leaves), a)
+    loss = (out.x * 1e-3).sum() + (out.v * 1e-4).sum()
+    torch.autograd.grad(loss, list(leaves.values()) + [a])
+
+
+def pour_water():
+    B = 16
+    conf = confs.pour_water_conf(res=(64, 48, 64))
+    sim = SimpleMPMSimulator(conf, B, sdf_kind=_lib.UD_SDF_CONTAINER)
+    st = sim.add_box(conf=conf, state=None, hardness=1, size=[0.3655] * 3, init_pos=[0.4, 0.3, 0.4], material=0, density=4)
+    st.primitives.append(create_primitive(conf, 0.1, 666, [0.5] * 3, [0.35, 0.0, 0.02], [0.4, 0.3, 0.4]))
+    st.primitives.append(create_primitive(conf, 0.1, 666, [0.5] * 3, [0.3, 0.0, 0.02], [0.4, 0.08, 0.2]))
+    st = st._replace(primitives=[p._replace(action_scale=p.action_scale * 0.01) for p in st.primitives])
+    state = sim.reset_jax(st)
+    n = state.x.shape[1]
+    action = torch.zeros((B, 12), device="cuda")
+    action[:, 0], action[:, 5] = 0.3, 0.2
+    with torch.no_grad():
+        for _ in range(4):
+            state, _ = sim.step_jax(state, action)
+        fwd = timed(lambda: sim.step_jax(state, action))
+    fb = timed(lambda: mpm_fwd_bwd(sim, state, action))
+    units = B * n * conf.steps
+    assert torch.isfinite(state.x).all()
+    return {"config": "pour_water synthetic", "envs": B, "particles_per_env": n, "substeps": conf.steps, "res": list(conf.res),
+            "fwd_ms": fwd, "fwdbwd_ms": fb, "fwd_Gpss": units / fwd / 1e6, "fwdbwd_Gpss": units / fb / 1e6,
+            "particles_per_occupied_cell": float(n / len(torch.unique((state.x[0] * conf.inv_dx - 0.5).int(), dim=0)))}
+
+
+def whip_rope():
+    B, ep = 8, 5
+    conf = confs.whip_rope_conf()
+    sim = SimpleMPMSimulator(conf, B, use_position_control=True)
+    st = sim.add_box(conf=conf, state=None, hardness=1.0, size=[0.15, 0.005, 0.005], init_pos=[0.25, 0.05, 0.25], material=1,
+                     density=25)
+    st.primitives.append(create_primitive(conf, 0.1, 666, [0.5] * 3, [0.02, 0.02, 0.02], [0.25, 0.05, 0.15]))
+    st = st._replace(primitives=[p._replace(action_scale=p.action_scale * 0.02) for p in st.primitives])
+    state = sim.reset_jax(st)
+    n = state.x.shape[1]
+    action = torch.zeros((B, 6), device="cuda")
+    action[:, 1] = 0.5
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    t0 = time.perf_counter()
+    x = state.x.detach().requires_grad_(True)
+    a = action.detach().requires_grad_(True)
+    s = state._replace(x=x)
+    for _ in range(ep):
+        s, _ = sim.step_jax(s, a)
+    (gx, ga) = torch.autograd.grad((s.x * 1e-3).sum(), [x, a])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    peak = torch.cuda.max_memory_allocated() - base
+    store_all = ep * conf.steps * B * n * 100 + ep * conf.steps * B * int(np.prod(conf.res)) * 32
+    assert torch.isfinite(gx).all()
+    return {"config": "whip_rope long horizon", "envs": B, "particles_per_env": n, "substeps_per_step": conf.steps,
+            "episode_steps": ep, "episode_substeps": ep * conf.steps, "fwdbwd_s": dt,
+            "fwdbwd_Gpss": B * n * conf.steps * ep / dt / 1e9, "peak_hbm_bytes": int(peak),
+            "store_every_substep_bytes_estimate": int(store_all), "state_bytes_per_checkpoint": B * n * 100}
+
+
+def cloth_para():
+    B = 128
+    conf = confs.ClothConf()
+    sim = ClothSimulator(conf, B, None, confs.fold_cloth_mask(conf))
+    st = sim.reset_jax()
+    g = torch.Generator().manual_seed(0)
+    st = st._replace(stiffness=(200 + 1600 * torch.rand(B, generator=g)).cuda(),
+                     primitive0=torch.cat([st.x[:, 0], torch.full((B, 1), 0.01, device="cuda")], dim=1))
+    act = torch.tensor([0.0, 0.3, 0.1, 0.0, 0, 0, 0, 1.0], device="cuda").repeat(B, 1)
+
+    def fb():
+        x = st.x.detach().requires_grad_(True)
+        a = act.detach().requires_grad_(True)
+        o, _ = sim.step_jax(st._replace(x=x), a)
+        torch.autograd.grad((o.x * o.x).sum(), [x, a])
+    with torch.no_grad():
+        fwd = timed(lambda: sim.step_jax(st, act), n=20)
+    t = timed(fb, n=20)
+    units = B * sim.n_nodes * 50
+    return {"config": "fold_cloth1_para sub-action", "envs": B, "nodes": sim.n_nodes, "substeps": 50, "fwd_ms": fwd,
+            "fwdbwd_ms": t, "fwd_Gnss": units / fwd / 1e6, "fwdbwd_Gnss": units / t / 1e6}
+
+
+if __name__ == "__main__":
+    for fn in (pour_water, whip_rope, cloth_para):
+        print(json.dumps(fn()), flush=True)

@@ -169,10 +169,12 @@ class SimpleMPMSimulator:
             center = np.array([0.5, 0.01, 0.5], dtype=np.float32)
             lower = -(np.float32(0.5) * size) + center
             upper = (np.float32(0.5) * size) + center
-            a, b, c = np.indices((n_grid, n_grid, n_grid))
-            gi = np.stack([a, b, c], axis=-1).astype(np.float32) * np.float32(1.0) / np.float32(n_grid)
-            mask = np.all((gi <= upper) & (gi >= lower), axis=-1)
-            x_ = gi[mask] - center
+            # the reference masks a full (n_grid^3, 3) index lattice; the mask is separable per axis, so only the
+            # 1-D candidates are formed here (same float32 values, same row-major order of the surviving points)
+            ax = np.arange(n_grid).astype(np.float32) * np.float32(1.0) / np.float32(n_grid)
+            keep = [ax[(ax <= upper[d]) & (ax >= lower[d])] for d in range(3)]
+            a, b, c = np.meshgrid(keep[0], keep[1], keep[2], indexing="ij")
+            x_ = np.stack([a, b, c], axis=-1).reshape(-1, 3) - center
             x_[:, [0, 2]] = x_[:, [0, 2]] @ rot.T
             x_ = x_ + init_pos
         return self.add_box_from_points(conf, state, torch.from_numpy(x_.astype(np.float32)), hardness, material)
