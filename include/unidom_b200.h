@@ -176,6 +176,9 @@ int ud_cloth_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const 
 uint64_t ud_launch_count(int reset);
 /* A/B switches for the measurements DESIGN.md quotes (process-global, not thread-safe, default = the fast path):
  *   "svd_warm"  1: warm-start the per-particle Jacobi SVD from the previous substep's V (default) / 0: cold start
+ *   "sort"      1: per-frame binning by grid block (default) / 0: particles stay in input order (ud_mpm_sort_bins unaffected)
+ *   "stage"     1: P2G staged in shared memory, one vector RED per (cell segment, node) (default) /
+ *               0: 27 vector REDs per particle straight to the grid in HBM
  * Returns the previous value, or -1 for an unknown name. */
 int ud_tuning_set(const char* name, int value);
 void ud_timing_enable(int on);

@@ -38,12 +38,15 @@ KScope::~KScope() {
   cudaEventRecord(g_recs[slot].b, st);
 }
 
-static int g_svd_warm = 1;
+static int g_svd_warm = 1, g_sort = 1, g_stage = 1;
 static thread_local const char* g_last_error = "";
 static int fail(int code, const char* what) {
   g_last_error = what;
   return code;
 }
+
+int tuning_sort() { return g_sort; }
+int tuning_stage() { return g_stage; }
 
 bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k) {
   if (!p) return false;
@@ -170,6 +173,8 @@ uint64_t ud_launch_count(int reset) {
 void ud_timing_enable(int on) { g_timing = on != 0; }
 int ud_tuning_set(const char* name, int value) {
   if (name && !strcmp(name, "svd_warm")) { int o = g_svd_warm; g_svd_warm = value; return o; }
+  if (name && !strcmp(name, "sort")) { int o = g_sort; g_sort = value; return o; }
+  if (name && !strcmp(name, "stage")) { int o = g_stage; g_stage = value; return o; }
   return -1;
 }
 int ud_timing_num_classes(void) { return KC_COUNT; }

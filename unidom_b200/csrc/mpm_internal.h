@@ -70,6 +70,10 @@ struct KScope {
   ~KScope();
 };
 
+// A/B switches (ud_tuning_set): 1 = the fast path (default)
+int tuning_sort();   // 0: identity permutation instead of the per-frame binning
+int tuning_stage();  // 0: 27 vector REDs per particle straight to HBM instead of the shared-memory staged scatter
+
 // Host helpers (abi.cu)
 bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k);
 size_t mpm_carve(const ud_mpm_params* p, const MpmConst& k, bool bwd, void* base, MpmWs* ws);

@@ -94,7 +94,17 @@ __global__ void k_rank(MpmConst k, const int32_t* __restrict__ keys, const int32
   perm[(size_t)env * k.n + lo + rank] = p;
 }
 
+__global__ void k_identity_perm(MpmConst k, int32_t* __restrict__ perm) {
+  UD_PARTICLE_INDEX(k, env, g);
+  if (live_) perm[g] = g - env * k.n;
+}
+
 void launch_sort(const MpmConst& k, const float* x_aos, const MpmWs& ws, int32_t* out_base, cudaStream_t st) {
+  if (!tuning_sort() && !out_base) {  // A/B: no binning
+    KScope ks_(KC_SORT, st, 1);
+    k_identity_perm<<<pgrid(k, 256), 256, 0, st>>>(k, ws.perm);
+    return;
+  }
   KScope ks_(KC_SORT, st, 6);
   cudaMemsetAsync(ws.cell_start, 0, sizeof(int32_t) * (size_t)k.B * (k.NK + 1), st);
   cudaMemsetAsync(ws.cursor, 0, sizeof(int32_t) * (size_t)k.B * k.NK, st);
@@ -312,7 +322,9 @@ UD_DEV void load_particle(const float* ps, size_t N, int g, float x[3], float v[
   for (int c = 0; c < 9; ++c) F.m[c] = ps[(PS_F + c) * N + g];
 }
 
-template <bool DET>
+// MODE 0: staged scatter + fp32 vector REDs; 1: staged + 64-bit fixed-point REDs (deterministic);
+//      2: A/B baseline -- every particle issues its 27 vector REDs itself (no shared memory, no grouping)
+template <int MODE>
 __global__ void __launch_bounds__(UD_BLOCK)
 k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
@@ -328,7 +340,9 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
   load_particle(ps_in, N, g, x, v, C, F);
   Stencil st;
   make_stencil(x, k.inv_dx, st);
-  const int row = stage_group(meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base);
+  constexpr bool DET = MODE == 1;
+  int row = 0;
+  if (MODE != 2) row = stage_group(meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base);
   Consti o;
   float vt0[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
   const bool warm = vt_in != nullptr;  // warm start of the Jacobi SVD from the previous substep's V^T (grid-uniform)
@@ -364,6 +378,28 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
     for (int j = 0; j < 3; ++j) Ac[j][i] = k.dx * o.affine(i, j);
     u[i] = k.p_mass * v[i] - (Ac[0][i] * st.fx[0] + Ac[1][i] * st.fx[1] + Ac[2][i] * st.fx[2]);
   }
+  if constexpr (MODE == 2) {
+    float4* genv = grid + (size_t)env * k.G;
+    if (live_) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int ix = idx_scatter(st.base[0] + a, k.rx), iy = idx_scatter(st.base[1] + b, k.ry),
+                      iz = idx_scatter(st.base[2] + c, k.rz);
+            if ((ix | iy | iz) < 0) continue;
+            const float wt = st.w[a][0] * st.w[b][1] * st.w[c][2];
+            float4 val;
+            val.x = wt * (u[0] + (float)a * Ac[0][0] + (float)b * Ac[1][0] + (float)c * Ac[2][0]);
+            val.y = wt * (u[1] + (float)a * Ac[0][1] + (float)b * Ac[1][1] + (float)c * Ac[2][1]);
+            val.z = wt * (u[2] + (float)a * Ac[0][2] + (float)b * Ac[1][2] + (float)c * Ac[2][2]);
+            val.w = wt * k.p_mass;
+            atomicAdd(&genv[(ix * k.ry + iy) * k.rz + iz], val);
+          }
+    }
+  } else {
 #pragma unroll
   for (int j0 = 0; j0 < 27; j0 += P2G_NPH) {
     if (j0) __syncthreads();  // the previous window has been flushed
@@ -393,6 +429,7 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
     stage_flush<4, false, DET>(k, sv, meta, grid + (size_t)env * k.G * (DET ? 2 : 1), j0,
                                (27 - j0) < P2G_NPH ? (27 - j0) : P2G_NPH);
   }
+  }
 }
 
 
@@ -402,15 +439,18 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
   KScope ks_(KC_P2G, st);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_p2g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4, P2G_NPH));
-    cudaFuncSetAttribute(k_p2g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4, P2G_NPH));
+    cudaFuncSetAttribute(k_p2g<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4, P2G_NPH));
+    cudaFuncSetAttribute(k_p2g<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4, P2G_NPH));
     attr_set = true;
   }
-  if (ws.grid_fix)
-    k_p2g<true><<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4, P2G_NPH), st>>>(
+  if (!tuning_stage() && !ws.grid_fix)
+    k_p2g<2><<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in,
+                                                      vt_out, svd_out);
+  else if (ws.grid_fix)
+    k_p2g<1><<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4, P2G_NPH), st>>>(
         k, ps_in, ps_out, reinterpret_cast<float4*>(ws.grid_fix), mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out);
   else
-    k_p2g<false><<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4, P2G_NPH), st>>>(
+    k_p2g<0><<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4, P2G_NPH), st>>>(
         k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out);
 }
 
