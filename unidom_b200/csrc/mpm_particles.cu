@@ -707,6 +707,13 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     float x[3], v[3];
     Mat3 C, F;
     load_particle(ps_in, N, g, x, v, C, F);
+    // incoming cotangents of x' (partial) and F': issued with the state loads, consumed at the very end
+    float gx_in[3];
+    Mat3 gF2out;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) gx_in[d] = gs[(PS_X + d) * N + g];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) gF2out.m[c] = gs[(PS_F + c) * N + g];
     Stencil st;
     make_stencil(x, k.inv_dx, st);
     Consti o;
@@ -791,13 +798,11 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     // dpos = (off - fx) dx: direct fx path, gfx_j -= dx (A^T S)_j = Ac[j] . S
 #pragma unroll
     for (int j = 0; j < 3; ++j) gfx[j] -= Ac[j][0] * S[0] + Ac[j][1] * S[1] + Ac[j][2] * S[2];
-    Mat3 gF2out, gC, gF;
-#pragma unroll
-    for (int c = 0; c < 9; ++c) gF2out.m[c] = gs[(PS_F + c) * N + g];
+    Mat3 gC, gF;
     constitutive_bwd(k, C, F, o, gA, gF2out, gC, gF, gmu, gla);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      gs[(PS_X + d) * N + g] += k.inv_dx * gfx[d];
+      gs[(PS_X + d) * N + g] = gx_in[d] + k.inv_dx * gfx[d];
       gs[(PS_V + d) * N + g] = k.p_mass * S[d];
     }
 #pragma unroll
