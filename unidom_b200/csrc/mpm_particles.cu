@@ -158,19 +158,26 @@ void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_
 // Phase 2 (stage_flush): thread (node, comp) sums its column over each segment in fixed row order and
 // issues ONE 16-byte vector RED per (segment, node).
 // ------------------------------------------------------------------------------------------------
-constexpr int STG_PAD = UD_BLOCK + 1;
+template <int SB> constexpr int stg_pad() { return SB + 4; }  // multiple of 4: 16-byte aligned columns for LDS.128; +4 keeps 8 neighbouring
+                                       // columns in distinct 16-byte bank groups
+constexpr int RUN_TAB = 23;            // segments whose 27 target cells are tabulated (aliases the grouping scratch)
+template <int SB>
 struct StageMeta {
-  int key[UD_BLOCK];            // by grouped row
-  int base[UD_BLOCK][3];        // by grouped row
-  int run_start[UD_BLOCK + 1];  // segment starts (grouped rows)
+  int key[SB];            // by grouped row
+  int base[SB][3];        // by grouped row
+  int run_start[SB + 1];  // segment starts (grouped rows)
   int n_runs;
-  // scratch of stage_group: one entry per (warp, distinct key in that warp)
-  int warp_cnt[UD_BLOCK / 32];
-  int ekey[UD_BLOCK];
-  unsigned emask[UD_BLOCK];
-  int efirst[UD_BLOCK];
-  int egid[UD_BLOCK];
-  int estart[UD_BLOCK];
+  int warp_cnt[SB / 32];
+  union {
+    struct {  // scratch of stage_group: one entry per (warp, distinct key in that warp)
+      int ekey[SB];
+      unsigned emask[SB];
+      int efirst[SB];
+      int egid[SB];
+      int estart[SB];
+    };
+    int cell[RUN_TAB][27];  // after grouping: linear cell index of node j of segment r, or -1 (dropped)
+  };
 };
 constexpr int DEAD_KEY = 0x40000000;
 UD_DEV int base_key(const int base[3]) { return (base[0] * 2048 + base[1]) * 2048 + base[2]; }
@@ -178,7 +185,8 @@ UD_DEV int base_key(const int base[3]) { return (base[0] * 2048 + base[1]) * 204
 // Groups the CTA's rows by key.  Returns this thread's grouped row; fills m.key / m.base / m.run_start /
 // m.n_runs.  Deterministic: groups are ordered by first occurrence (warp, lane), rows inside a group by
 // (warp, lane).  All threads of the CTA must call it; it ends with a barrier.
-__device__ __forceinline__ int stage_group(StageMeta& m, int key, const int base[3]) {
+template <bool CLAMP, int SB>
+__device__ __forceinline__ int stage_group(const MpmConst& k, StageMeta<SB>& m, int key, const int base[3]) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const unsigned mm = __match_any_sync(0xffffffffu, key);   // lanes of my warp with my key
@@ -189,7 +197,7 @@ __device__ __forceinline__ int stage_group(StageMeta& m, int key, const int base
   __syncthreads();
   int ebase = 0, E = 0;
 #pragma unroll
-  for (int w = 0; w < UD_BLOCK / 32; ++w) {
+  for (int w = 0; w < SB / 32; ++w) {
     const int c = m.warp_cnt[w];
     ebase += w < wid ? c : 0;
     E += c;
@@ -227,7 +235,7 @@ __device__ __forceinline__ int stage_group(StageMeta& m, int key, const int base
     if (m.efirst[t] == t) m.run_start[gid] = start;
     if (t == 0) {
       m.n_runs = ng;
-      m.run_start[ng] = UD_BLOCK;
+      m.run_start[ng] = SB;
     }
   }
   __syncthreads();
@@ -236,8 +244,27 @@ __device__ __forceinline__ int stage_group(StageMeta& m, int key, const int base
   m.base[pos][0] = base[0];
   m.base[pos][1] = base[1];
   m.base[pos][2] = base[2];
-  __syncthreads();
-  return pos;
+  __syncthreads();  // the scratch is dead from here on: its storage becomes the cell table
+  const int nr = m.n_runs;
+  if (nr <= RUN_TAB) {  // target cells of every (segment, node), computed once by all 128 threads
+    for (int e = t; e < nr * 27; e += SB) {
+      const int r = e / 27, j = e - r * 27;
+      const int s0 = m.run_start[r];
+      const int a = j / 9, b = (j / 3) % 3, c = j % 3;
+      int ix, iy, iz;
+      if (CLAMP) {
+        ix = idx_gather(m.base[s0][0] + a, k.rx);
+        iy = idx_gather(m.base[s0][1] + b, k.ry);
+        iz = idx_gather(m.base[s0][2] + c, k.rz);
+      } else {
+        ix = idx_scatter(m.base[s0][0] + a, k.rx);
+        iy = idx_scatter(m.base[s0][1] + b, k.ry);
+        iz = idx_scatter(m.base[s0][2] + c, k.rz);
+      }
+      m.cell[r][j] = ((ix | iy | iz) < 0 || (m.key[s0] & DEAD_KEY)) ? -1 : (ix * k.ry + iy) * k.rz + iz;
+    }
+  }
+  return pos;  // callers barrier between staging and flush, which also publishes the table
 }
 
 // phase 2: NC (3 or 4) components per node, staged value-major as column (node_local*NC + comp).
@@ -246,8 +273,8 @@ __device__ __forceinline__ int stage_group(StageMeta& m, int key, const int base
 // (run, node): scalar REDs cost ~4x more L2 atomic work (measured: 76 of 236 us in k_p2g).
 // The 27 nodes are staged in windows of NPH nodes ([j0, j0+nj)), which divides the shared-memory
 // footprint (and multiplies the resident CTAs per SM) without changing the amount of flush work.
-template <int NC, bool CLAMP, bool DET = false>
-__device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __restrict__ sv, const StageMeta& m,
+template <int NC, bool CLAMP, bool DET, int SB>
+__device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __restrict__ sv, const StageMeta<SB>& m,
                                             float4* __restrict__ genv, int j0, int nj) {
   const int t = threadIdx.x;
   if (t >= ((nj * 4 + 31) & ~31)) return;  // whole extra warps leave; partial warps stay for the shuffles
@@ -255,19 +282,22 @@ __device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __re
   const bool sums = jl < nj && c < NC;
   const int j = j0 + jl;
   const int a = j / 9, b = (j / 3) % 3, cc = j % 3;
-  const float* col = sv + ((jl < nj ? jl : 0) * NC + (c < NC ? c : 0)) * STG_PAD;
+  const float* col = sv + ((jl < nj ? jl : 0) * NC + (c < NC ? c : 0)) * stg_pad<SB>();
   const int nr = m.n_runs;
+  const bool tab = nr <= RUN_TAB;  // block-uniform
   for (int r = 0; r < nr; ++r) {
     const int s0 = m.run_start[r], s1 = m.run_start[r + 1];
     if (m.key[s0] & DEAD_KEY) continue;  // block-uniform
     float acc = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;  // independent partial sums (fixed order)
     if (sums) {
       int p = s0;
-      for (; p + 3 < s1; p += 4) {
-        acc += col[p];
-        acc1 += col[p + 1];
-        acc2 += col[p + 2];
-        acc3 += col[p + 3];
+      for (; (p & 3) && p < s1; ++p) acc += col[p];            // head up to a 16-byte boundary
+      for (; p + 3 < s1; p += 4) {                             // body: one LDS.128 per 4 rows
+        const float4 q = *reinterpret_cast<const float4*>(col + p);
+        acc += q.x;
+        acc1 += q.y;
+        acc2 += q.z;
+        acc3 += q.w;
       }
       for (; p < s1; ++p) acc += col[p];
       acc = (acc + acc1) + (acc2 + acc3);
@@ -278,18 +308,24 @@ __device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __re
     val.z = __shfl_down_sync(0xffffffffu, acc, 2);
     val.w = __shfl_down_sync(0xffffffffu, acc, 3);
     if (c != 0 || jl >= nj) continue;
-    int ix, iy, iz;
-    if (CLAMP) {
-      ix = idx_gather(m.base[s0][0] + a, k.rx);
-      iy = idx_gather(m.base[s0][1] + b, k.ry);
-      iz = idx_gather(m.base[s0][2] + cc, k.rz);
+    int cell;
+    if (tab) {
+      cell = m.cell[r][j];
+      if (cell < 0) continue;
     } else {
-      ix = idx_scatter(m.base[s0][0] + a, k.rx);
-      iy = idx_scatter(m.base[s0][1] + b, k.ry);
-      iz = idx_scatter(m.base[s0][2] + cc, k.rz);
-      if ((ix | iy | iz) < 0) continue;
+      int ix, iy, iz;
+      if (CLAMP) {
+        ix = idx_gather(m.base[s0][0] + a, k.rx);
+        iy = idx_gather(m.base[s0][1] + b, k.ry);
+        iz = idx_gather(m.base[s0][2] + cc, k.rz);
+      } else {
+        ix = idx_scatter(m.base[s0][0] + a, k.rx);
+        iy = idx_scatter(m.base[s0][1] + b, k.ry);
+        iz = idx_scatter(m.base[s0][2] + cc, k.rz);
+        if ((ix | iy | iz) < 0) continue;
+      }
+      cell = (ix * k.ry + iy) * k.rz + iz;
     }
-    const int cell = (ix * k.ry + iy) * k.rz + iz;
     if (DET) {  // UD_P2G_DETERMINISTIC: 4 integer REDs on 64-bit fixed point (associative => order-independent)
       unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(genv) + 4 * (size_t)cell;
       atomicAdd(acc64 + 0, (unsigned long long)__double2ll_rn((double)val.x * FIX_SCALE));
@@ -301,9 +337,13 @@ __device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __re
     }
   }
 }
-constexpr size_t stage_smem_bytes(int nc, int nph) { return sizeof(float) * nph * nc * STG_PAD + sizeof(StageMeta); }
+template <int SB>
+constexpr size_t stage_smem_bytes(int nc, int nph) { return sizeof(float) * nph * nc * stg_pad<SB>() + sizeof(StageMeta<SB>); }
+constexpr int P2G_BLOCK = 64;    // threads (= particles) per CTA of k_p2g: with 14-node windows the 56 flush lanes are
+                                 // the whole CTA, so no warp idles at a barrier while others sum columns
+constexpr int G2PB_BLOCK = UD_BLOCK;  // k_g2p_bwd: one window of 27 nodes, 108 flush lanes of 128 (two windows cost it registers)
 constexpr int P2G_NPH = 14;      // nodes per staging window of k_p2g (27 nodes -> 2 windows)
-constexpr int G2PB_NPH = 27;     // k_g2p_bwd: one window
+constexpr int G2PB_NPH = 27;
 
 // ------------------------------------------------------------------------------------------------
 // P2G: F update + SVD + plasticity + stress (mpm_simulator.py:238-268), then the 27-node scatter of
@@ -325,14 +365,15 @@ UD_DEV void load_particle(const float* ps, size_t N, int g, float x[3], float v[
 // MODE 0: staged scatter + fp32 vector REDs; 1: staged + 64-bit fixed-point REDs (deterministic);
 //      2: A/B baseline -- every particle issues its 27 vector REDs itself (no shared memory, no grouping)
 template <int MODE>
-__global__ void __launch_bounds__(UD_BLOCK)
+__global__ void __launch_bounds__(P2G_BLOCK)
 k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
       const float* __restrict__ h_s, const float* __restrict__ vt_in, float* __restrict__ vt_out,
       float* __restrict__ svd_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sv = reinterpret_cast<float*>(smem_raw);                               // [P2G_NPH*4][STG_PAD]
-  StageMeta& meta = *reinterpret_cast<StageMeta*>(sv + P2G_NPH * 4 * STG_PAD);
+  constexpr int STG_PAD = stg_pad<P2G_BLOCK>();
+  StageMeta<P2G_BLOCK>& meta = *reinterpret_cast<StageMeta<P2G_BLOCK>*>(sv + P2G_NPH * 4 * STG_PAD);
   UD_PARTICLE_INDEX(k, env, g);
   const size_t N = k.N;
   float x[3], v[3];
@@ -342,7 +383,7 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
   make_stencil(x, k.inv_dx, st);
   constexpr bool DET = MODE == 1;
   int row = 0;
-  if (MODE != 2) row = stage_group(meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base);
+  if (MODE != 2) row = stage_group<false, P2G_BLOCK>(k, meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base);
   Consti o;
   float vt0[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
   const bool warm = vt_in != nullptr;  // warm start of the Jacobi SVD from the previous substep's V^T (grid-uniform)
@@ -426,7 +467,7 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
     }
     __syncthreads();
     // DET: `grid` is the int64 accumulator array (32 B per cell = 2 float4 slots per cell)
-    stage_flush<4, false, DET>(k, sv, meta, grid + (size_t)env * k.G * (DET ? 2 : 1), j0,
+    stage_flush<4, false, DET, P2G_BLOCK>(k, sv, meta, grid + (size_t)env * k.G * (DET ? 2 : 1), j0,
                                (27 - j0) < P2G_NPH ? (27 - j0) : P2G_NPH);
   }
   }
@@ -439,18 +480,18 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
   KScope ks_(KC_P2G, st);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_p2g<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4, P2G_NPH));
-    cudaFuncSetAttribute(k_p2g<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes(4, P2G_NPH));
+    cudaFuncSetAttribute(k_p2g<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH));
+    cudaFuncSetAttribute(k_p2g<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH));
     attr_set = true;
   }
   if (!tuning_stage() && !ws.grid_fix)
-    k_p2g<2><<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in,
+    k_p2g<2><<<pgrid(k, P2G_BLOCK), P2G_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in,
                                                       vt_out, svd_out);
   else if (ws.grid_fix)
-    k_p2g<1><<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4, P2G_NPH), st>>>(
+    k_p2g<1><<<pgrid(k, P2G_BLOCK), P2G_BLOCK, stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH), st>>>(
         k, ps_in, ps_out, reinterpret_cast<float4*>(ws.grid_fix), mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out);
   else
-    k_p2g<0><<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(4, P2G_NPH), st>>>(
+    k_p2g<0><<<pgrid(k, P2G_BLOCK), P2G_BLOCK, stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH), st>>>(
         k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out);
 }
 
@@ -596,12 +637,13 @@ void launch_gather_cot(const MpmConst& k, const ud_mpm_state* gout, const MpmWs&
 // G2P^T: v' = sum wt g ; C' = sum 4 inv_dx wt g (x) d ; x' = x + dt v'   (d = off - fx)
 // Scatters the cotangent of the updated grid velocity (clamped index = transpose of the clamping
 // gather) and leaves the partial position cotangent gx' + inv_dx * gfx in gs.X.
-__global__ void __launch_bounds__(UD_BLOCK)
+__global__ void __launch_bounds__(G2PB_BLOCK)
 k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict__ grid_out,
           float* __restrict__ gs, float4* __restrict__ ggrid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sv = reinterpret_cast<float*>(smem_raw);                               // [81][STG_PAD]
-  StageMeta& meta = *reinterpret_cast<StageMeta*>(sv + G2PB_NPH * 3 * STG_PAD);
+  constexpr int STG_PAD = stg_pad<G2PB_BLOCK>();
+  StageMeta<G2PB_BLOCK>& meta = *reinterpret_cast<StageMeta<G2PB_BLOCK>*>(sv + G2PB_NPH * 3 * STG_PAD);
   UD_PARTICLE_INDEX(k, env, g);
   const size_t N = k.N;
   float x[3], gxo[3], gvt[3];
@@ -616,7 +658,7 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   for (int c = 0; c < 9; ++c) gC.m[c] = gs[(PS_C + c) * N + g];
   Stencil st;
   make_stencil(x, k.inv_dx, st);
-  const int row = stage_group(meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base);
+  const int row = stage_group<true, G2PB_BLOCK>(k, meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base);
   const float lw = live_ ? 1.f : 0.f;
   const float4* genv = grid_out + (size_t)env * k.G;
   const float c4 = 4.f * k.inv_dx;
@@ -677,13 +719,13 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   }
   __syncthreads();
   // transpose of the clamping gather: clamped target index
-  stage_flush<3, true>(k, sv, meta, ggrid + (size_t)env * k.G, 0, 27);
+  stage_flush<3, true, false, G2PB_BLOCK>(k, sv, meta, ggrid + (size_t)env * k.G, 0, 27);
 }
 
 void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
                     cudaStream_t st) {
   KScope ks_(KC_G2P_BWD, st);
-  k_g2p_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, stage_smem_bytes(3, G2PB_NPH), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
+  k_g2p_bwd<<<pgrid(k, G2PB_BLOCK), G2PB_BLOCK, stage_smem_bytes<G2PB_BLOCK>(3, G2PB_NPH), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
 }
 
 // P2G^T (gather of the cotangents of scattered momentum/mass; dropped nodes contribute nothing),
