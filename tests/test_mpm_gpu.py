@@ -209,3 +209,62 @@ def test_p2g_deterministic_mode_is_bit_reproducible(built_lib):
         assert e < 2e-5, (k, e)
     ref = _oracle_step(conf, sim_d, st, act)
     assert util.rel_err(outs[0][0].x, ref.x) < 1e-4 and util.rel_err(outs[0][0].F, ref.F) < 1e-4
+
+
+def test_edge_cases_out_of_grid_nan_single_env(built_lib):
+    """B = 1, a particle count that is not a multiple of the CTA size, particles outside the grid (scatter
+    dropped / gather clamped / negative index wrap), NaN in the input state (norm_grad_state's
+    forward nan_to_num, mpm_simulator.py:376-381): forward and adjoint against the oracle."""
+    conf = _conf(steps=3)
+    B = 1
+    sim = _sim(conf, B)
+    st = util.mini_plasticine(sim, B, seed=31, material=1)
+    n = st.x.shape[1]
+    assert n % 64 != 0
+    x, v, F = st.x.clone(), st.v.clone(), st.F.clone()
+    x[0, 0] = torch.tensor([-0.004, 0.03, 0.25], device=x.device)       # base x = -0 / negative side: wraps
+    x[0, 1] = torch.tensor([0.25, 0.03, 0.4995], device=x.device)       # touches the +z face of res (48/96 = 0.5)
+    x[0, 2] = torch.tensor([0.25, 0.34, 0.25], device=x.device)         # above the grid (res_y = 32/96 = 0.333)
+    v[0, 3, 1] = float("nan")
+    F[0, 4, 0, 1] = float("nan")
+    st = st._replace(x=x, v=v, F=F)
+    act = _actions(B, 1, seed=9).to(x.device)
+    g = torch.Generator().manual_seed(5)
+    cot = {"x": torch.randn((B, n, 3), generator=g) * 1e-3, "v": torch.randn((B, n, 3), generator=g) * 1e-4,
+           "C": torch.zeros((B, n, 3, 3)), "F": torch.zeros((B, n, 3, 3)),
+           "p0.position": torch.zeros((B, conf.steps, 3)), "p0.rotation": torch.zeros((B, conf.steps, 4))}
+    got = _run_grad(lambda s, a: sim.step_jax(s, a)[0], st, act, cot, 1, lambda t: t.to(x.device))
+    osim = omp.Simulator(util.oracle_conf(conf), sim.material.clone(), sim.h.clone())
+    ost = util.to_oracle_state(st)
+    ref = _run_grad(lambda s, a: omp.step_batch(osim, s, a), ost, act.cpu(), cot, 1, lambda t: t)
+    out, _ = sim.step_jax(st, act)
+    oref = omp.step_batch(osim, ost, act.cpu())
+    mask = torch.ones(n, dtype=torch.bool)
+    mask[0] = False     # the wrapped particle is alone on the far face: v = p / m with m ~ 1e-12 (compared loosely)
+    assert util.rel_err(out.v[0, 0], oref.v[0, 0]) < 5e-2 and util.rel_err(out.x[0, 0], oref.x[0, 0]) < 1e-3
+    for k in ("x", "v", "C"):
+        a, b = getattr(out, k)[0].cpu()[mask], getattr(oref, k)[0][mask]
+        assert torch.isfinite(a).all(), k
+        assert util.rel_err(a, b) < 1e-4, (k, util.rel_err(a, b))
+    for k in ("x", "v", "action"):
+        a, b = got[k].cpu(), ref[k]
+        if k != "action":
+            a, b = a[0][mask], b[0][mask]
+        assert util.cosine(a, b) > 0.999, (k, util.cosine(a, b))
+
+
+def test_invalid_arguments_are_rejected(built_lib):
+    """Error behaviour of the C ABI: nothing is enqueued, a negative status comes back (no exception in C)."""
+    import ctypes as C
+    from unidom_b200 import _lib
+    conf = _conf(steps=2)
+    sim = _sim(conf, 2)
+    st = util.mini_plasticine(sim, 2, seed=1)
+    L = _lib.lib()
+    p = sim.params(B=2, n=st.x.shape[1])
+    assert L.ud_mpm_fwd_workspace_bytes(C.byref(p)) > 0
+    p.p2g_mode = 7
+    assert L.ud_mpm_fwd_workspace_bytes(C.byref(p)) == 0
+    with pytest.raises(RuntimeError):
+        sim.p2g_mode = 7
+        sim.step_jax(st, _actions(2, 1).to(st.x.device))

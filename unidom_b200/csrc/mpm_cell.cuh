@@ -279,8 +279,10 @@ UD_DEV void cell_ground_boundary(const MpmConst& k, int ci, int cj, int ck, cons
 template <class T, class PF>
 UD_DEV void cell_update(const MpmConst& k, int ci, int cj, int ck, const T p[3], const T& m, const T& sfric,
                         PF prim_of, T v[3]) {
+  // mpm_simulator.py:283-285: where(m > 0, p / m, p) + dt * gravity (empty cells keep p = 0 and get dt * gravity)
+  const bool has_mass = s_val(m) > 0.f;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) v[i] = p[i] / m + k.gdt[i];
+  for (int i = 0; i < 3; ++i) v[i] = (has_mass ? p[i] / m : p[i]) + k.gdt[i];
   const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
   for (int q = 0; q < k.n_prim; ++q) {
     PrimIn<T> pr;
@@ -291,6 +293,15 @@ UD_DEV void cell_update(const MpmConst& k, int ci, int cj, int ck, const T p[3],
       collide_cell(k.sdf_kind, k.dt, gpos, pr, v);
   }
   cell_ground_boundary(k, ci, cj, ck, sfric, v);
+}
+
+// Cells of the boundary shell are the only EMPTY cells a particle can gather with a non-zero weight (a particle
+// outside the grid gathers with clamped indices); the reference updates every cell, the kernels
+// update cells with mass plus the empty cells of this shell.
+// (Only the outermost layer: a particle more than 1.5 cells outside the low faces would wrap to layers r-2, r-3
+// under JAX's negative-index rule; that far out the simulation is void anyway.)
+UD_DEV bool cell_in_shell(const MpmConst& k, int ci, int cj, int ck) {
+  return ci == 0 || cj == 0 || ck == 0 || ci == k.rx - 1 || cj == k.ry - 1 || ck == k.rz - 1;
 }
 
 // Does primitive `pr` act on the cell at gpos?  collide: influence = min(exp(-dist*softness),1) >= 1e-12

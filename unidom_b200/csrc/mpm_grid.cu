@@ -163,13 +163,13 @@ k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, const long long* __res
   } else {
     g = grid_in[idx];
   }
-  if (!(g.w > 0.f)) {
-    if (grid_out != grid_in) grid_out[idx] = g;
-    return;
-  }
   int env = (int)(idx / k.G);
   int c = (int)(idx - (size_t)env * k.G);
   int ck = c % k.rz, cj = (c / k.rz) % k.ry, ci = c / (k.rz * k.ry);
+  if (!(g.w > 0.f)) {  // empty cell: interior ones are never gathered with a non-zero weight, the boundary
+    if (grid_out != grid_in) grid_out[idx] = g;  // shell is updated by k_grid_shell
+    return;
+  }
   float p[3] = {g.x, g.y, g.z}, v[3];
   auto prim_of = [&](int q, PrimIn<float>& pr) {
     load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
@@ -179,11 +179,58 @@ k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, const long long* __res
   grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
 }
 
+// Empty cells of the outermost layer: the reference updates EVERY cell (empty ones get dt*gravity, colliders,
+// friction, walls), and a particle that left the grid gathers exactly these cells through clamped indices
+// (SURVEY 8c).  One thread per face cell (edges are visited twice and write the same value).
+__global__ void __launch_bounds__(128)
+k_grid_shell(MpmConst k, const float4* grid_raw, float4* grid_out, int f, ud_mpm_state in,
+             const float* __restrict__ fk_pos, const float* __restrict__ fk_rot, const float* __restrict__ fk_vw) {
+  const int env = blockIdx.y;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nxy = k.rx * k.ry, nxz = k.rx * k.rz, nyz = k.ry * k.rz;
+  int ci, cj, ck;
+  if (t < 2 * nxy) {
+    ck = t >= nxy ? k.rz - 1 : 0;
+    t -= t >= nxy ? nxy : 0;
+    ci = t / k.ry;
+    cj = t % k.ry;
+  } else if (t < 2 * (nxy + nxz)) {
+    t -= 2 * nxy;
+    cj = t >= nxz ? k.ry - 1 : 0;
+    t -= t >= nxz ? nxz : 0;
+    ci = t / k.rz;
+    ck = t % k.rz;
+  } else if (t < 2 * (nxy + nxz + nyz)) {
+    t -= 2 * (nxy + nxz);
+    ci = t >= nyz ? k.rx - 1 : 0;
+    t -= t >= nyz ? nyz : 0;
+    cj = t / k.rz;
+    ck = t % k.rz;
+  } else {
+    return;
+  }
+  const size_t idx = (size_t)env * k.G + (size_t)(ci * k.ry + cj) * k.rz + ck;
+  const float4 g = grid_raw[idx];
+  if (g.w > 0.f) return;  // has mass: k_grid_fwd's cell
+  const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
+  float p[3] = {g.x, g.y, g.z}, v[3];
+  auto prim_of = [&](int q, PrimIn<float>& pr) {
+    load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
+    return prim_active(k, gpos, pr);  // without influence the primitive changes v by < 1e-12 relative: skipped
+  };
+  cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
+  grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
+}
+
 void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const long long* grid_fix, int substep,
                      const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st) {
-  KScope ks_(KC_GRID, st);
+  KScope ks_(KC_GRID, st, 2);
   k_grid_fwd<<<cdiv((long long)k.B * k.G, 128), 128, 0, st>>>(k, grid_in, grid_out, grid_fix, substep, *in, ws.fk_pos,
                                                               ws.fk_rot, ws.fk_vw);
+  // in-place (forward) mode the raw value of an empty cell is still there when the shell kernel reads it
+  const int shell = 2 * (k.rx * k.ry + k.rx * k.rz + k.ry * k.rz);
+  k_grid_shell<<<dim3(cdiv(shell, 128), k.B), 128, 0, st>>>(k, grid_in, grid_out, substep, *in, ws.fk_pos, ws.fk_rot,
+                                                            ws.fk_vw);
 }
 
 // ================================================================================================
@@ -213,19 +260,21 @@ k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__
   size_t idx = (size_t)env * k.G + (live ? c : 0);
   float4 g = grid_raw[idx];
   float4 gv4 = ggrid[idx];
-  bool work = live && g.w > 0.f && (gv4.x != 0.f || gv4.y != 0.f || gv4.z != 0.f);
+  int ck = c % k.rz, cj = (c / k.rz) % k.ry, ci = c / (k.rz * k.ry);
+  // cells with mass, plus empty shell cells that an out-of-grid particle gathered (clamped index)
+  bool work = live && (gv4.x != 0.f || gv4.y != 0.f || gv4.z != 0.f) && (g.w > 0.f || cell_in_shell(k, ci, cj, ck));
   if (live && !work) ggrid[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!__any_sync(0xffffffffu, work)) return;  // warp-uniform exit (no block barriers below)
-  int ck = c % k.rz, cj = (c / k.rz) % k.ry, ci = c / (k.rz * k.ry);
+  const bool has_mass = g.w > 0.f;
   const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
   const float sfric = in.friction[env];
   // ---- forward recompute, remembering the velocity entering each primitive
   float v[3] = {0.f, 0.f, 0.f}, vin[UD_MAX_PRIM][3];
   unsigned act = 0;
   if (work) {
-    v[0] = g.x / g.w + k.gdt[0];
-    v[1] = g.y / g.w + k.gdt[1];
-    v[2] = g.z / g.w + k.gdt[2];
+    v[0] = (has_mass ? g.x / g.w : g.x) + k.gdt[0];
+    v[1] = (has_mass ? g.y / g.w : g.y) + k.gdt[1];
+    v[2] = (has_mass ? g.z / g.w : g.z) + k.gdt[2];
 #pragma unroll
     for (int q = 0; q < UD_MAX_PRIM; ++q) {
       if (q >= k.n_prim) break;
@@ -301,8 +350,8 @@ k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__
   }
   // ---- reverse of v = p / m + dt g
   if (work) {
-    float im = 1.f / g.w;
-    float gm = -(gv[0] * g.x + gv[1] * g.y + gv[2] * g.z) * im * im;
+    float im = has_mass ? 1.f / g.w : 1.f;  // where(m > 0, p / m, p): the empty branch passes the cotangent through
+    float gm = has_mass ? -(gv[0] * g.x + gv[1] * g.y + gv[2] * g.z) * im * im : 0.f;
     ggrid[idx] = make_float4(gv[0] * im, gv[1] * im, gv[2] * im, gm);
   }
 }
