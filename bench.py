@@ -323,8 +323,12 @@ def main():
             ent["gbs"] = ALG_BYTES[name] * B * n / (avg_ms * 1e-3) / 1e9
         kern[name] = ent
     dom = max((k for k in kern if k in ALG_BYTES), key=lambda k: kern[k]["share"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)      # DRAM bytes per launch from the committed ncu --set full capture
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": kern[dom]["share"],
                 "algorithmic_bytes_per_launch": ALG_BYTES[dom] * B * n,
                 "step_frac_fwdbwd": (value / world) * ALG_BYTES_FWDBWD / 1e9 / peak,
