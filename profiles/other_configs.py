@@ -114,11 +114,25 @@ def cloth_para():
     with torch.no_grad():
         fwd = timed(lambda: sim.step_jax(st, act), n=20)
     t = timed(fb, n=20)
+    # device time of the two kernels alone (CUDA events recorded by the library around its launches)
+    import ctypes as C
+    L = _lib.lib()
+    L.ud_timing_enable(1)
+    for _ in range(10):
+        fb()
+    torch.cuda.synchronize()
+    ncls = L.ud_timing_num_classes()
+    msb, cnt = (C.c_double * ncls)(), (C.c_int64 * ncls)()
+    L.ud_timing_collect(msb, cnt, ncls)
+    L.ud_timing_enable(0)
+    L.ud_timing_class_name.restype = C.c_char_p
+    kern = {L.ud_timing_class_name(i).decode(): msb[i] / cnt[i] for i in range(ncls) if cnt[i] > 0}
     units = B * sim.n_nodes * 50
-    return {"config": "fold_cloth1_para sub-action", "envs": B, "nodes": sim.n_nodes, "substeps": 50, "fwd_ms": fwd,
+    return {"config": "fold_cloth1_para sub-action", "kernel_ms": kern, "envs": B, "nodes": sim.n_nodes, "substeps": 50, "fwd_ms": fwd,
             "fwdbwd_ms": t, "fwd_Gnss": units / fwd / 1e6, "fwdbwd_Gnss": units / t / 1e6}
 
 
 if __name__ == "__main__":
-    for fn in (pour_water, whip_rope, cloth_para):
+    only = sys.argv[1:] or ["pour_water", "whip_rope", "cloth_para"]
+    for fn in [f for f in (pour_water, whip_rope, cloth_para) if f.__name__ in only]:
         print(json.dumps(fn()), flush=True)

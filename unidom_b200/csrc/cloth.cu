@@ -45,6 +45,13 @@ __device__ __forceinline__ float clipf(float a, float lo, float hi) { return fmi
 __device__ __forceinline__ float clip_grad(float a, float lo, float hi) {
   return (a > lo && a < hi) ? 1.f : ((a == lo || a == hi) ? 0.5f : 0.f);
 }
+// a / b given rb = RN(1 / b): one Newton correction on the remainder reproduces the correctly rounded IEEE quotient
+// (normal range), so several divisions by the same denominator share one reciprocal.  The cloth is chaotic; keeping
+// the reference's exact quotients keeps the trajectories on the reference's branch for as long as possible.
+__device__ __forceinline__ float div_rn(float a, float b, float rb) {
+  const float q = a * rb;
+  return __fmaf_rn(__fmaf_rn(-q, b, a), rb, q);
+}
 __device__ __forceinline__ float nan0(float a) {
   if (a != a) return 0.f;
   if (isinf(a)) return a > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
@@ -88,7 +95,8 @@ struct Sub {  // forward intermediates of one substep for one node (kept for the
 
 // one forward substep for one node; xs = shared positions of all nodes (already synchronised)
 __device__ __forceinline__ void cloth_substep(const ClothK& k, const float* __restrict__ xs, const int nbr[8],
-                                              const float L0[8], float stiff, float mu, const float a0[4],
+                                              const float L0[8], const float iL0[8], float stiff, float mu,
+                                              const float a0[4],
                                               const float a1[4], const float ps0[4], const float ps1[4],
                                               float x[3], float v[3], Sub& o) {
   o.vg[0] = v[0];
@@ -101,9 +109,12 @@ __device__ __forceinline__ void cloth_substep(const ClothK& k, const float* __re
     float r0 = xs[3 * nbr[q]] - x[0], r1 = xs[3 * nbr[q] + 1] - x[1], r2 = xs[3 * nbr[q] + 2] - x[2];
     float cur = sqrtf(fmaxf(r0 * r0 + r1 * r1 + r2 * r2, 1e-12f));
     float e = cur - L0[q];
-    fs[0] += stiff * r0 / cur * e / L0[q];
-    fs[1] += stiff * r1 / cur * e / L0[q];
-    fs[2] += stiff * r2 / cur * e / L0[q];
+    // ((stiffness * rel) / cur * (cur - L0)) / L0, evaluated left to right as :266-267 does, with the six
+    // divisions per link sharing two reciprocals (48 IEEE divisions per node and substep dominated the kernel)
+    const float ic = __frcp_rn(cur);
+    fs[0] += div_rn(div_rn(stiff * r0, cur, ic) * e, L0[q], iL0[q]);
+    fs[1] += div_rn(div_rn(stiff * r1, cur, ic) * e, L0[q], iL0[q]);
+    fs[2] += div_rn(div_rn(stiff * r2, cur, ic) * e, L0[q], iL0[q]);
   }
   o.fr[0] = fs[0];
   o.fr[1] = fs[1] - k.g;
@@ -115,8 +126,9 @@ __device__ __forceinline__ void cloth_substep(const ClothK& k, const float* __re
   o.dyn = o.fmask && (o.sV > k.small_num);
   float fx = o.fr[0], fz = o.fr[2];
   if (o.dyn) {
-    fx = fx - o.muF * o.vg[0] / o.sV;
-    fz = fz - o.muF * o.vg[2] / o.sV;
+    const float is = __frcp_rn(o.sV);
+    fx = fx - div_rn(o.muF * o.vg[0], o.sV, is);
+    fz = fz - div_rn(o.muF * o.vg[2], o.sV, is);
   }
   o.stat = o.fmask && (o.sV <= k.small_num);
   o.sF = sqrtf(fx * fx + fz * fz + k.small_num);
@@ -192,7 +204,7 @@ k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
   const bool live = t < k.P;
   const int n = live ? t : 0;
   const size_t o = (size_t)env * k.P + n;
-  float x[3], v[3], L0[8], a0[4], a1[4], ps0[4], ps1[4];
+  float x[3], v[3], L0[8], iL0[8], a0[4], a1[4], ps0[4], ps1[4];
   int nbr[8];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -203,6 +215,7 @@ k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
   for (int q = 0; q < 8; ++q) {
     nbr[q] = live ? nbr_t[n * 8 + q] : -1;
     L0[q] = L0_t[n * 8 + q];
+    iL0[q] = __frcp_rn(L0[q]);
   }
   load_actions(action, env, a0, a1);
 #pragma unroll
@@ -236,7 +249,7 @@ k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
     }
     __syncthreads();
     Sub sb;
-    cloth_substep(k, xs, nbr, L0, stiff, mu, a0, a1, ps0, ps1, x, v, sb);
+    cloth_substep(k, xs, nbr, L0, iL0, stiff, mu, a0, a1, ps0, ps1, x, v, sb);
     advance_gripper(a0, ps0);
     advance_gripper(a1, ps1);
     __syncthreads();
@@ -285,12 +298,13 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
   const int n = live ? t : 0;
   const size_t o = (size_t)env * k.P + n;
   const int mirror[8] = {1, 0, 3, 2, 7, 6, 5, 4};  // link k of i  <->  link mirror[k] of its neighbour
-  float L0[8], a0[4], a1[4];
+  float L0[8], iL0[8], a0[4], a1[4];
   int nbr[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     nbr[q] = live ? nbr_t[n * 8 + q] : -1;
     L0[q] = L0_t[n * 8 + q];
+    iL0[q] = __frcp_rn(L0[q]);
   }
   load_actions(action, env, a0, a1);
   const float stiff = in.stiffness[env], mu = in.mu[env];
@@ -336,7 +350,7 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
     }
     __syncthreads();
     Sub f;
-    cloth_substep(k, xs, nbr, L0, stiff, mu, a0, a1, ps0, ps1, x, v, f);  // x,v now hold the outputs (unused)
+    cloth_substep(k, xs, nbr, L0, iL0, stiff, mu, a0, a1, ps0, ps1, x, v, f);  // x,v now hold the outputs (unused)
     // ---- (1) trailing norm_grads on x', v', ps0', ps1' (:331-334)
     float nx = live ? gx[0] * gx[0] + gx[1] * gx[1] + gx[2] * gx[2] : 0.f;
     float nv = live ? gv[0] * gv[0] + gv[1] * gv[1] + gv[2] * gv[2] : 0.f;
@@ -420,9 +434,10 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
     {
       // recompute the pre-static values
       float fx1 = f.fr[0], fz1 = f.fr[2];
+      const float isV = __frcp_rn(f.sV);
       if (f.dyn) {
-        fx1 = fx1 - f.muF * f.vg[0] / f.sV;
-        fz1 = fz1 - f.muF * f.vg[2] / f.sV;
+        fx1 = fx1 - div_rn(f.muF * f.vg[0], f.sV, isV);
+        fz1 = fz1 - div_rn(f.muF * f.vg[2], f.sV, isV);
       }
       float gfx1 = gf[0], gfz1 = gf[2];
       if (f.zero) {
@@ -442,10 +457,11 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
       gfr[2] = gfz1;
       if (f.dyn) {
         // fx1 = fr0 - muF vg0 / sV ; sV = sqrt(vg0^2 + vg2^2 + small)
-        gmuF += -(gfx1 * f.vg[0] + gfz1 * f.vg[2]) / f.sV;
-        float gsV = (gfx1 * f.vg[0] + gfz1 * f.vg[2]) * f.muF / (f.sV * f.sV);
-        gvg[0] += -gfx1 * f.muF / f.sV + gsV * f.vg[0] / f.sV;
-        gvg[2] += -gfz1 * f.muF / f.sV + gsV * f.vg[2] / f.sV;
+        const float gd = gfx1 * f.vg[0] + gfz1 * f.vg[2];
+        gmuF += -gd * isV;
+        float gsV = gd * f.muF * (isV * isV);
+        gvg[0] += (-gfx1 * f.muF + gsV * f.vg[0]) * isV;
+        gvg[2] += (-gfz1 * f.muF + gsV * f.vg[2]) * isV;
       }
       // muF = -mu * min(fr1, 0)
       if (live) gmup += gmuF * (-fminf(f.fr[1], 0.f));
@@ -462,13 +478,13 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
         float cur = sqrtf(fmaxf(sq, 1e-12f));
         float e = cur - L0[q];
         float dot = gfr[0] * r0 + gfr[1] * r1 + gfr[2] * r2;
-        float sc = stiff / L0[q];
-        float a = sc * e / cur;                                   // d f_c / d rel_c (direct)
-        float b = sq >= 1e-12f ? sc * L0[q] * dot / (cur * cur * cur) : 0.f;  // through cur
+        const float inv = __frcp_rn(cur);
+        float a = (stiff * iL0[q]) * (e * inv);                   // d f_c / d rel_c (direct)
+        float b = sq >= 1e-12f ? stiff * dot * (inv * inv * inv) : 0.f;  // through cur
         g0 = a * gfr[0] + b * r0;
         g1 = a * gfr[1] + b * r1;
         g2 = a * gfr[2] + b * r2;
-        if (k.stiff_float) gstiffp += dot * e / (cur * L0[q]);
+        if (k.stiff_float) gstiffp += dot * (e * inv) * iL0[q];
         gxi[0] -= g0;
         gxi[1] -= g1;
         gxi[2] -= g2;
