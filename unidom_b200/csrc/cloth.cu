@@ -52,6 +52,14 @@ __device__ __forceinline__ float div_rn(float a, float b, float rb) {
   const float q = a * rb;
   return __fmaf_rn(__fmaf_rn(-q, b, a), rb, q);
 }
+__device__ __forceinline__ float nan0(float a);
+// norm_grad's backward on one component: nan_to_num(g / n) / mask_sum (:190-192), n and mask_sum shared by many
+// components.  rn = RN(1/n); when n == 0 the reciprocal is inf and the true division decides (0/0 -> NaN -> 0,
+// x/0 -> inf -> FLT_MAX), exactly as the reference's arithmetic does.
+__device__ __forceinline__ float norm_div(float g, float n, float rn, float ms, float rms) {
+  const float q = isinf(rn) ? g / n : div_rn(g, n, rn);
+  return div_rn(nan0(q), ms, rms);
+}
 __device__ __forceinline__ float nan0(float a) {
   if (a != a) return 0.f;
   if (isinf(a)) return a > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
@@ -279,8 +287,9 @@ k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
 __device__ __forceinline__ void norm_grad4(const ClothK& k, float g[4]) {
   float n2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + g[3] * g[3];
   float nrm = sqrtf(n2);
+  const float rn = __frcp_rn(nrm), rms = __frcp_rn(k.mask_sum);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) g[c] = nan0(g[c] / nrm) / k.mask_sum;
+  for (int c = 0; c < 4; ++c) g[c] = norm_div(g[c], nrm, rn, k.mask_sum, rms);
 }
 
 // Adjoint of the 50-substep sub-action.  Expects `save` filled by k_cloth_fwd (recompute pass).
@@ -308,6 +317,7 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
   }
   load_actions(action, env, a0, a1);
   const float stiff = in.stiffness[env], mu = in.mu[env];
+  const float rms = __frcp_rn(k.mask_sum);
   // incoming cotangents
   float gx[3], gv[3], gps0[4], gps1[4];
 #pragma unroll
@@ -359,8 +369,8 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
     nv = sqrtf(nv);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      gx[c] = nan0(gx[c] / nx) / k.mask_sum;
-      gv[c] = nan0(gv[c] / nv) / k.mask_sum;
+      gx[c] = norm_div(gx[c], nx, __frcp_rn(nx), k.mask_sum, rms);
+      gv[c] = norm_div(gv[c], nv, __frcp_rn(nv), k.mask_sum, rms);
     }
     norm_grad4(k, gps0);
     norm_grad4(k, gps1);
@@ -392,7 +402,7 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
     float gx1[3], gv1[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float gxq = nan0(gx2[c] / nx) / k.mask_sum, gvq = nan0(gv2[c] / nv) / k.mask_sum;
+      float gxq = norm_div(gx2[c], nx, __frcp_rn(nx), k.mask_sum, rms), gvq = norm_div(gv2[c], nv, __frcp_rn(nv), k.mask_sum, rms);
       gx1[c] = gxq;
       if (f.m1 && live) {
         gv1[c] = a1[3] * gvq;
@@ -411,7 +421,7 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
     float gxs[3], gv0[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float gxq = nan0(gx1[c] / nx) / k.mask_sum, gvq = nan0(gv1[c] / nv) / k.mask_sum;
+      float gxq = norm_div(gx1[c], nx, __frcp_rn(nx), k.mask_sum, rms), gvq = norm_div(gv1[c], nv, __frcp_rn(nv), k.mask_sum, rms);
       gxs[c] = gxq;  // x passes through either branch of the where()
       if (f.m0 && live) {
         gv0[c] = a0[3] * gvq;
@@ -446,12 +456,13 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
       }
       if (f.nonz) {
         // fx = R xF, fz = R yF, R = 1 - muF / sF, sF = sqrt(xF^2 + yF^2 + small)
-        float R = 1.f - f.muF / f.sF;
+        const float isF = __frcp_rn(f.sF);
+        float R = 1.f - div_rn(f.muF, f.sF, isF);
         float gR = gf[0] * fx1 + gf[2] * fz1;
-        gmuF += -gR / f.sF;
-        float gsF = gR * f.muF / (f.sF * f.sF);
-        gfx1 = gf[0] * R + gsF * fx1 / f.sF;
-        gfz1 = gf[2] * R + gsF * fz1 / f.sF;
+        gmuF += -gR * isF;
+        float gsF = gR * f.muF * (isF * isF);
+        gfx1 = gf[0] * R + gsF * fx1 * isF;
+        gfz1 = gf[2] * R + gsF * fz1 * isF;
       }
       gfr[0] = gfx1;
       gfr[2] = gfz1;
