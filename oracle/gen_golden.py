@@ -343,6 +343,52 @@ def cloth_env_case(name, ep_len, B, seed):
     print(f"wrote {path}: ep_len={ep_len} B={B} loss={float(loss):.6f} |grad|={gn:.4e}")
 
 
+def mpm_env_case(name, B, density, seed):
+    """Env level for MPM: the reference's push task (envs/shape_elasto_plastic.py: ShapeRopeEnv.step_diff = focus
+    shift, get_primitive_actions, 20 sub-actions x 16 substeps, reward e^(-10 l2) + e^(-contact)) on a reduced
+    particle density, forward + gradient of the summed reward w.r.t. the 6-vector action."""
+    sys.path.insert(0, os.path.join(HERE, "jaxshim"))
+    import stubs
+    stubs.install()
+    import torch
+    import jax
+    import jax.numpy as jnp
+    from daxbench.core.envs import shape_elasto_plastic as sep
+    from daxbench.core.engine.primitives.primitives import set_sdf
+    from daxbench.core.engine.primitives.box import _sdf_batch as box_sdf
+    rng = np.random.RandomState(seed)
+    env = sep.ShapeRopeEnv(batch_size=B, seed=1, aux_reward=True)
+    env.aux_reward = True
+    set_sdf(box_sdf)
+    conf = env.conf
+    # reset() of :139-157 with a reduced density (the shipped density 3 gives 23 940 particles)
+    state = env.simulator.add_box(conf=conf, state=None, hardness=conf.rope_hardness, size=conf.rope_width,
+                                  init_pos=conf.rope_init_pos, z_rotation_angle=conf.rope_z_rotation_angle, material=2,
+                                  density=density)
+    state = env.create_primitive(conf=conf, state=state, friction=0.1, color=[0.5, 0.5, 0.5], size=[0.015, 0.06, 0.015],
+                                 init_pos=[0.5, 0.01, 0.45])
+    env.initialize_after_adding_particle_primitives(state)
+    st = env.state
+    n = st.x.shape[1]
+    goal = np.asarray(st.x)[0] + np.array([0.03, 0.0, 0.02], np.float32)
+    env.goal = jnp.array(goal)
+    x0 = np.asarray(st.x)
+    acts = np.stack([np.concatenate([x0[b].mean(0) + [-0.06, 0, -0.03 * (b + 1)], x0[b].mean(0) + [0.05, 0, 0.02]])
+                     for b in range(B)]).astype(np.float32)
+    out = {"goal": goal, "actions": acts, "density": np.array(density), "in_x": x0,
+           "material": np.asarray(env.simulator.material).astype(np.int32), "h": np.asarray(env.simulator.h).astype(np.float32)}
+    a = torch.from_numpy(acts).requires_grad_(True)
+    obs, reward, done, info = env.step_diff(jax.Array(a), st)
+    ns = info["state"]
+    (ga,) = torch.autograd.grad(reward.t.sum(), [a])
+    out.update({"reward": reward.t.detach().numpy(), "g_actions": ga.numpy(), "out_x": np.asarray(ns.x.t.detach()),
+                "out_v": np.asarray(ns.v.t.detach()), "out_F": np.asarray(ns.F.t.detach()),
+                "out_prim_pos": np.asarray(ns.primitives[0].position.t.detach()), "obs": np.asarray(obs.t.detach())})
+    path = os.path.join(GOLD, f"ref_mpmenv_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: n={n} B={B} reward={out['reward']} |g_actions|max={np.abs(out['g_actions']).max():.3e}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--real-jax", action="store_true")
@@ -369,6 +415,7 @@ def main():
         "cloth_w1_contact": lambda: cloth_case(mods, "w1_contact", True, 27, False, window=1, contact=True),
         "cloth_w4_contact": lambda: cloth_case(mods, "w4_contact", False, 28, False, window=4, contact=True),
     }
+    cases["mpmenv_push"] = lambda: mpm_env_case("push", 2, 1.3, 41)
     cases["clothenv_ep1"] = lambda: cloth_env_case("ep1", 1, 2, 31)
     # BASELINE.json configs[0]: fold_cloth3 APG ep_len=3 num_envs=4 (reference states + policy gradient; ~20 min here)
     cases["clothenv_ep3"] = lambda: cloth_env_case("ep3", 3, 4, 0)

@@ -385,6 +385,9 @@ class Array:
             return self.T
         return W(self.t.permute(*axes))
 
+    def swapaxes(self, a, b):
+        return W(self.t.transpose(a, b))
+
     def squeeze(self, axis=None):
         return W(self.t.squeeze() if axis is None else self.t.squeeze(axis))
 

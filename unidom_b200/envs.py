@@ -99,3 +99,111 @@ class ClothEnv:
         done = state.cur_step >= self.max_steps
         info = {"state": state, "real_reward": old_chamfer - chamfer + 0.1 * contact}
         return obs, reward, done, info
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# MPM env (core/envs/basic/mpm_env.py) with the push task of core/envs/shape_elasto_plastic.py ("push_plasticine")
+# -------------------------------------------------------------------------------------------------------------------
+class MPMEnv:
+    """B200 drop-in for the reference's MPMEnv (mpm_env.py:18-167): focus shift (pre_step/post_step :99-125),
+    task-specific `get_primitive_actions`, scan of `simulator.step_jax` over the sub-actions (:141), state
+    nan_to_num (:150-154), reward e^(-10 l2) (+ e^(-contact)) (:91-94,156-158), auto-reset on done (:159-161)."""
+
+    def __init__(self, conf, batch_size, max_steps, goal=None, aux_reward=False, focus_computation=True, device="cuda",
+                 use_position_control=False):
+        from .mpm_simulator import SimpleMPMSimulator
+        self.conf, self.batch_size, self.max_steps = conf, batch_size, max_steps
+        self.aux_reward, self.focus_computation = aux_reward, focus_computation
+        self.simulator = SimpleMPMSimulator(conf, batch_size, use_position_control, device=device)
+        self.device = self.simulator.device
+        self.action_size = 6
+        goal = np.zeros((1, 3), np.float32) if goal is None else np.asarray(goal, np.float32)
+        self.goal = torch.from_numpy(goal).to(self.device)
+        self.init_state = None
+
+    @staticmethod
+    def get_obs(state):
+        """mpm_env.py:60-76 (PARTICLE): [x.flatten(), v.flatten(), primitives[0].position.flatten()]."""
+        return torch.cat([state.x.flatten(1), state.v.flatten(1), state.primitives[0].position.flatten(1)], dim=1)
+
+    # task hooks (overridden per task)
+    def get_primitive_actions(self, actions, state):
+        raise NotImplementedError
+
+    def process_pre_step_actions(self, actions, shift):
+        raise NotImplementedError
+
+    def auto_reset(self, init_state, state):
+        return state
+
+    def _shift(self, state, shift):
+        prims = [p._replace(position=p.position + shift[:, None, :]) if q < self.conf.n_primitive else p
+                 for q, p in enumerate(state.primitives)]
+        return state._replace(x=state.x + shift[:, None, :], primitives=prims)
+
+    def step_diff(self, actions, state):
+        contact = torch.sqrt(((actions[:, None, :3] - state.x) ** 2).sum(-1)).min(-1).values
+        shift = None
+        if self.focus_computation:                                           # pre_step (:99-114)
+            centre = state.x.mean(1)
+            target = torch.tensor(self.conf.res, dtype=centre.dtype, device=centre.device) * 0.5 / self.conf.n_grid
+            shift = target - centre
+            shift = torch.cat([shift[:, 0:1], torch.zeros_like(shift[:, 1:2]), shift[:, 2:3]], dim=1)
+            actions = self.process_pre_step_actions(actions, shift)
+            state = self._shift(state, shift)
+        sub, state = self.get_primitive_actions(actions, state)              # (B, T, 6 n_prim)
+        for t in range(sub.shape[1]):                                        # lax.scan(self.simulator.step_jax, ...) (:141)
+            state, _ = self.simulator.step_jax(state, sub[:, t])
+        state = state._replace(cur_step=state.cur_step + 1)
+        if self.focus_computation:                                           # post_step (:116-125)
+            state = self._shift(state, -shift)
+        done = state.cur_step >= self.max_steps
+        state = state._replace(**{k: torch.nan_to_num(getattr(state, k)) for k in ("x", "v", "C", "F", "J")})
+        reward = math.e ** (-calc_l2(state.x, self.goal) * 10)
+        if self.aux_reward:
+            reward = reward + math.e ** (-contact)
+        if bool(done.any()) and self.init_state is not None:                 # auto_reset + where(done) (:159-161)
+            new = self.auto_reset(self.init_state, state)
+            state = _where_state(done, new, state)
+        return self.get_obs(state), reward, done, {"state": state}
+
+
+def _where_state(done, new, old):
+    def pick(a, b):
+        if not torch.is_tensor(a):
+            return b
+        d = done.reshape(done.shape + (1,) * (a.dim() - done.dim()))
+        return torch.where(d, a.detach(), b)
+    prims = [type(po)(*[pick(a, b) for a, b in zip(pn, po)]) for pn, po in zip(new.primitives, old.primitives)]
+    vals = {k: pick(getattr(new, k), getattr(old, k)) for k in old._fields if k != "primitives"}
+    return old._replace(primitives=prims, **vals)
+
+
+class ShapeElastoPlasticEnv(MPMEnv):
+    """core/envs/shape_elasto_plastic.py:56-157 (class ShapeRopeEnv there): a box pusher starts at `start`, moves
+    towards `end` by at most 0.1 in 20 sub-actions (:95-123); BASELINE configs[1] "push_plasticine"."""
+
+    def __init__(self, conf, batch_size, max_steps=6, density=3.0, **kw):
+        super().__init__(conf, batch_size, max_steps, focus_computation=True, **kw)
+        from . import confs
+        self.state = confs.build_shape_elasto_plastic(self.simulator, density=density)
+        self.init_state = self.state
+
+    def process_pre_step_actions(self, actions, shift):
+        return torch.cat([actions[:, 0:3] + shift, actions[:, 3:] + shift], dim=1)      # :88-92
+
+    def get_primitive_actions(self, actions, state):
+        start, end = actions[:, :3], actions[:, 3:]
+        y = torch.full_like(start[:, 1:2], 0.01)
+        start = torch.cat([start[:, 0:1], y, start[:, 2:3]], dim=1)
+        end = torch.cat([end[:, 0:1], y, end[:, 2:3]], dim=1)
+        norm = torch.sqrt(((end - start) ** 2).sum(-1, keepdim=True)) + 1e-8
+        vec = (end - start) / norm
+        end = start + vec * torch.minimum(torch.maximum(norm, torch.zeros_like(norm)), torch.full_like(norm, 0.1))
+        p = state.primitives[0]
+        position = torch.cat([start[:, None, :], p.position[:, 1:]], dim=1)
+        prims = [p._replace(position=position)] + list(state.primitives[1:])
+        push = (end - start)[:, None, :].expand(-1, 20, -1) / 20
+        push = torch.cat([push[..., 0:1], torch.zeros_like(push[..., 1:2]), push[..., 2:3]], dim=-1)
+        sub = torch.cat([push, torch.zeros_like(push)], dim=-1)
+        return sub, state._replace(primitives=prims)
