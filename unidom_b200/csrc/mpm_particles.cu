@@ -290,16 +290,38 @@ __device__ __forceinline__ void stage_flush(const MpmConst& k, const float* __re
     if (m.key[s0] & DEAD_KEY) continue;  // block-uniform
     float acc = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;  // independent partial sums (fixed order)
     if (sums) {
-      int p = s0;
-      for (; (p & 3) && p < s1; ++p) acc += col[p];            // head up to a 16-byte boundary
-      for (; p + 3 < s1; p += 4) {                             // body: one LDS.128 per 4 rows
-        const float4 q = *reinterpret_cast<const float4*>(col + p);
-        acc += q.x;
-        acc1 += q.y;
-        acc2 += q.z;
-        acc3 += q.w;
+      const float* pc = col + s0;
+      int left = s1 - s0;
+      int head = (4 - (s0 & 3)) & 3;  // rows up to a 16-byte boundary
+      head = head < left ? head : left;
+      left -= head;
+#pragma unroll 1
+      for (; head > 0; --head) acc += *pc++;
+      const float4* p4 = reinterpret_cast<const float4*>(pc);
+#pragma unroll 1
+      for (; left >= 8; left -= 8) {  // body: two LDS.128 per 8 rows
+        const float4 q0 = p4[0], q1 = p4[1];
+        p4 += 2;
+        acc += q0.x;
+        acc1 += q0.y;
+        acc2 += q0.z;
+        acc3 += q0.w;
+        acc += q1.x;
+        acc1 += q1.y;
+        acc2 += q1.z;
+        acc3 += q1.w;
       }
-      for (; p < s1; ++p) acc += col[p];
+      if (left >= 4) {
+        const float4 q0 = *p4++;
+        acc += q0.x;
+        acc1 += q0.y;
+        acc2 += q0.z;
+        acc3 += q0.w;
+        left -= 4;
+      }
+      pc = reinterpret_cast<const float*>(p4);
+#pragma unroll 1
+      for (; left > 0; --left) acc += *pc++;
       acc = (acc + acc1) + (acc2 + acc3);
     }
     float4 val;
