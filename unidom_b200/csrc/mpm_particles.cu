@@ -768,36 +768,34 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
   const size_t N = k.N;
   float gmu = 0.f, gla = 0.f;
   if (live_) {
-    float x[3], v[3];
-    Mat3 C, F;
-    load_particle(ps_in, N, g, x, v, C, F);
-    // incoming cotangents of x' (partial) and F': issued with the state loads, consumed at the very end
-    float gx_in[3];
-    Mat3 gF2out;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) gx_in[d] = gs[(PS_X + d) * N + g];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) gF2out.m[c] = gs[(PS_F + c) * N + g];
+    // Phase 1: everything the 27-node gather needs is the stencil, A = dx * affine and u0.  The matrices that
+    // produce them (C, F, U, s, Vt, F1, F2, D: ~80 registers) die here and are loaded again (L2 hits) for the
+    // constitutive reverse after the gather, instead of staying live across it.
     Stencil st;
-    make_stencil(x, k.inv_dx, st);
-    Consti o;
-    constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
-#pragma unroll
-    for (int c = 0; c < 9; ++c) o.U.m[c] = svd_in[(SV_U + c) * N + g];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) o.s[c] = svd_in[(SV_S + c) * N + g];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) o.Vt.m[c] = svd_in[(SV_VT + c) * N + g];
-    constitutive_post(k, C, o);
-    const float4* ggenv = ggrid + (size_t)env * k.G;
-    // u(a,b,c) = p_mass v + A dpos = u0 + a Ax + b Ay + c Az,  A* = dx * columns of affine
     float Ac[3][3], u0[3];
+    {
+      float x[3], v[3];
+      Mat3 C, F;
+      load_particle(ps_in, N, g, x, v, C, F);
+      make_stencil(x, k.inv_dx, st);
+      Consti o;
+      constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+      for (int c = 0; c < 9; ++c) o.U.m[c] = svd_in[(SV_U + c) * N + g];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) Ac[j][i] = k.dx * o.affine(i, j);
-      u0[i] = k.p_mass * v[i] - (Ac[0][i] * st.fx[0] + Ac[1][i] * st.fx[1] + Ac[2][i] * st.fx[2]);
+      for (int c = 0; c < 3; ++c) o.s[c] = svd_in[(SV_S + c) * N + g];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) o.Vt.m[c] = svd_in[(SV_VT + c) * N + g];
+      constitutive_post(k, C, o);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Ac[j][i] = k.dx * o.affine(i, j);
+        u0[i] = k.p_mass * v[i] - (Ac[0][i] * st.fx[0] + Ac[1][i] * st.fx[1] + Ac[2][i] * st.fx[2]);
+      }
     }
+    const float4* ggenv = ggrid + (size_t)env * k.G;
+    // u(a,b,c) = p_mass v + A dpos = u0 + a Ax + b Ay + c Az,  A* = dx * columns of affine (phase 1)
     float S[3] = {0.f, 0.f, 0.f}, TX[3] = {0.f, 0.f, 0.f}, TY[3] = {0.f, 0.f, 0.f}, TZ[3] = {0.f, 0.f, 0.f};
     float gfx[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -862,7 +860,26 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     // dpos = (off - fx) dx: direct fx path, gfx_j -= dx (A^T S)_j = Ac[j] . S
 #pragma unroll
     for (int j = 0; j < 3; ++j) gfx[j] -= Ac[j][0] * S[0] + Ac[j][1] * S[1] + Ac[j][2] * S[2];
-    Mat3 gC, gF;
+    // Phase 2: reload (ld.global.cg so that the compiler cannot keep the phase-1 registers alive) and reverse
+    Mat3 C, F, gF2out, gC, gF;
+    Consti o;
+    float gx_in[3];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) C.m[c] = __ldcg(&ps_in[(PS_C + c) * N + g]);
+#pragma unroll
+    for (int c = 0; c < 9; ++c) F.m[c] = __ldcg(&ps_in[(PS_F + c) * N + g]);
+#pragma unroll
+    for (int c = 0; c < 9; ++c) o.U.m[c] = __ldcg(&svd_in[(SV_U + c) * N + g]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o.s[c] = __ldcg(&svd_in[(SV_S + c) * N + g]);
+#pragma unroll
+    for (int c = 0; c < 9; ++c) o.Vt.m[c] = __ldcg(&svd_in[(SV_VT + c) * N + g]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) gx_in[d] = gs[(PS_X + d) * N + g];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) gF2out.m[c] = gs[(PS_F + c) * N + g];
+    constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+    constitutive_post(k, C, o);
     constitutive_bwd(k, C, F, o, gA, gF2out, gC, gF, gmu, gla);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
