@@ -123,4 +123,62 @@ def train_iteration(env, params, opt: Adam, state, eps, max_grad_norm: float, si
     g, g_norm = reduce_policy_gradient(flatten(grads), max_grad_norm, group)
     new_flat = opt.step(flatten([p.detach() for p in params]), g)
     new_params = unflatten(new_flat, params)
-    return new_params, {"loss": float(loss), "reward": rewards.detach(), "grad_norm": float(g_norm)}
+    return new_params, {"loss": float(loss.detach()), "reward": rewards.detach(), "grad_norm": float(g_norm)}
+
+
+def main(argv=None):
+    """`python -m unidom_b200.apg --env fold_cloth3 --ep_len 3 --num_envs 4 --lr 1e-4 --seed 0 --max_it 2`
+    (the reference's README command, apg.py:384-443; one process per GPU under torchrun, envs sharded by rank)."""
+    import argparse
+    import os
+    import time
+
+    import numpy as np
+
+    from . import confs, envs
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--env", default="fold_cloth3", choices=["fold_cloth1", "fold_cloth3", "fold_cloth1_para"])
+    ap.add_argument("--ep_len", type=int, default=3)
+    ap.add_argument("--num_envs", type=int, default=4)
+    ap.add_argument("--lr", type=float, default=1e-4)
+    ap.add_argument("--max_it", type=int, default=2)
+    ap.add_argument("--max_grad_norm", type=float, default=0.3)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args(argv)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    first, per = shard_envs(args.num_envs, world, rank)
+    conf = confs.ClothConf()
+    para = args.env.endswith("_para")
+    goal = np.zeros((1, 3), np.float32)                  # goals/*.npy are reference data files: pass your own
+    env = envs.ClothEnv(conf, per, 4, confs.fold_cloth_mask(conf), goal=goal, aux_reward=True, device=dev, para=para)
+    params = init_policy(env.observation_size, env.action_size, seed=args.seed, device=dev)   # replicated
+    opt = Adam(sum(p.numel() for p in params), args.lr, dev)
+    g = torch.Generator().manual_seed(args.seed + 1)
+    for it in range(args.max_it):
+        _, state = env.reset()
+        if para:                                          # apg_para.py:326-329: per-env stiffness ~ U(200, 1800)
+            stiff = 200 + 1600 * torch.rand(args.num_envs, generator=g)[first:first + per]
+            state = state._replace(stiffness=stiff.to(dev))
+        eps = torch.randn((args.ep_len, args.num_envs, env.action_size), generator=g)[:, first:first + per].to(dev)
+        t0 = time.perf_counter()
+        params, m = train_iteration(env, params, opt, state, eps, args.max_grad_norm)
+        torch.cuda.synchronize(dev)
+        pn = float(torch.sqrt(sum((p * p).sum() for p in params)))
+        print(f"[rank {rank}/{world}] it {it}: loss {m['loss']:.6f} grad_norm {m['grad_norm']:.4e} "
+              f"params_norm {pn:.6f} ({time.perf_counter() - t0:.2f} s, envs {first}..{first + per - 1})", flush=True)
+    if world > 1:
+        # replicas must stay in sync: same reduced gradient + same Adam state on every rank
+        flat = flatten(params)
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(flat, ref), "policy replicas diverged"
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
