@@ -130,6 +130,8 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
     w.grid_raw = (float4*)take(16 * BG * S);
     w.grid_out = (float4*)take(16 * BG * S);
     w.svd_s = (float*)take(4 * (size_t)SV_NCOMP * N * S);
+    w.act_list = (int32_t*)take(4 * BG * S);
+    w.act_count = (int32_t*)take(4 * S);
     w.gs = (float*)take(4 * (size_t)PS_NCOMP * N);
     w.ggrid = (float4*)take(16 * BG);
     w.g_fk_pos = (float*)take(4 * (size_t)k.B * P * (S + 1) * 3);
@@ -287,6 +289,7 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   launch_gather_state(k, in, material, h, ws, ws.ps, st);
   launch_fk_fwd(k, in, action, nullptr, ws, st);
   if (!ws.grid_fix) zero_async(ws.grid_raw, 16 * BG * k.S, st);
+  zero_async(ws.act_count, 4 * (size_t)k.S, st);
   for (int f = 0; f < k.S; ++f) {
     const float* s_in = ws.ps + slot * f;
     float* s_out = ws.ps + slot * (f + 1);

@@ -150,26 +150,40 @@ UD_DEV void load_prim_f(const MpmConst& k, const ud_mpm_state& in, const float* 
 __global__ void __launch_bounds__(128)
 k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, const long long* __restrict__ grid_fix, int f,
            ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
-           const float* __restrict__ fk_vw) {
+           const float* __restrict__ fk_vw, int32_t* __restrict__ act_list, int32_t* __restrict__ act_count) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)k.B * k.G) return;
-  float4 g;
-  if (grid_fix) {  // deterministic P2G: fixed-point accumulators -> float {p, m}
-    const longlong2 a = reinterpret_cast<const longlong2*>(grid_fix)[2 * idx];
-    const longlong2 b = reinterpret_cast<const longlong2*>(grid_fix)[2 * idx + 1];
-    g = make_float4((float)((double)a.x * FIX_INV), (float)((double)a.y * FIX_INV), (float)((double)b.x * FIX_INV),
-                    (float)((double)b.y * FIX_INV));
-    if (grid_out != grid_in) grid_in[idx] = g;  // the adjoint reads the raw grid
-  } else {
-    g = grid_in[idx];
+  const bool in_range = idx < (size_t)k.B * k.G;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (in_range) {
+    if (grid_fix) {  // deterministic P2G: fixed-point accumulators -> float {p, m}
+      const longlong2 a = reinterpret_cast<const longlong2*>(grid_fix)[2 * idx];
+      const longlong2 b = reinterpret_cast<const longlong2*>(grid_fix)[2 * idx + 1];
+      g = make_float4((float)((double)a.x * FIX_INV), (float)((double)a.y * FIX_INV), (float)((double)b.x * FIX_INV),
+                      (float)((double)b.y * FIX_INV));
+      if (grid_out != grid_in) grid_in[idx] = g;  // the adjoint reads the raw grid
+    } else {
+      g = grid_in[idx];
+    }
+  }
+  const bool has_mass = in_range && g.w > 0.f;
+  if (act_list) {  // recompute pass of the adjoint: list the cells with mass for k_grid_bwd (warp-aggregated append)
+    const unsigned m = __ballot_sync(0xffffffffu, has_mass);
+    if (m) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == __ffs(m) - 1) base = atomicAdd(act_count, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      if (has_mass) act_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)idx;
+    }
+  }
+  if (!in_range) return;
+  if (!has_mass) {  // empty cell: interior ones are never gathered with a non-zero weight, the boundary
+    if (grid_out != grid_in) grid_out[idx] = g;  // shell is updated by k_grid_shell
+    return;
   }
   int env = (int)(idx / k.G);
   int c = (int)(idx - (size_t)env * k.G);
   int ck = c % k.rz, cj = (c / k.rz) % k.ry, ci = c / (k.rz * k.ry);
-  if (!(g.w > 0.f)) {  // empty cell: interior ones are never gathered with a non-zero weight, the boundary
-    if (grid_out != grid_in) grid_out[idx] = g;  // shell is updated by k_grid_shell
-    return;
-  }
   float p[3] = {g.x, g.y, g.z}, v[3];
   auto prim_of = [&](int q, PrimIn<float>& pr) {
     load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
@@ -184,9 +198,11 @@ k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, const long long* __res
 // (SURVEY 8c).  One thread per face cell (edges are visited twice and write the same value).
 __global__ void __launch_bounds__(128)
 k_grid_shell(MpmConst k, const float4* grid_raw, float4* grid_out, int f, ud_mpm_state in,
-             const float* __restrict__ fk_pos, const float* __restrict__ fk_rot, const float* __restrict__ fk_vw) {
+             const float* __restrict__ fk_pos, const float* __restrict__ fk_rot, const float* __restrict__ fk_vw,
+             int32_t* __restrict__ act_list, int32_t* __restrict__ act_count) {
   const int env = blockIdx.y;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t0 = t;
   const int nxy = k.rx * k.ry, nxz = k.rx * k.rz, nyz = k.ry * k.rz;
   int ci, cj, ck;
   if (t < 2 * nxy) {
@@ -214,23 +230,35 @@ k_grid_shell(MpmConst k, const float4* grid_raw, float4* grid_out, int f, ud_mpm
   if (g.w > 0.f) return;  // has mass: k_grid_fwd's cell
   const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
   float p[3] = {g.x, g.y, g.z}, v[3];
+  bool any_active = false;
   auto prim_of = [&](int q, PrimIn<float>& pr) {
     load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
-    return prim_active(k, gpos, pr);  // without influence the primitive changes v by < 1e-12 relative: skipped
+    const bool a = prim_active(k, gpos, pr);  // without influence the primitive changes v by < 1e-12 relative: skipped
+    any_active |= a;
+    return a;
   };
   cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
   grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
+  // an empty shell cell under a primitive's influence can carry a cotangent to that primitive: list it for k_grid_bwd
+  // (edge cells are visited twice: the duplicate entry is harmless only if it is not added, so one face owns each cell)
+  if (act_list && any_active) {
+    const bool owner = (ck == 0 || ck == k.rz - 1) ? (t0 < 2 * nxy)
+                       : ((cj == 0 || cj == k.ry - 1) ? (t0 >= 2 * nxy && t0 < 2 * (nxy + nxz)) : true);
+    if (owner) act_list[atomicAdd(act_count, 1)] = (int32_t)idx;
+  }
 }
 
 void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const long long* grid_fix, int substep,
                      const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st) {
   KScope ks_(KC_GRID, st, 2);
+  int32_t* al = (grid_out != grid_in && ws.act_list) ? ws.act_list + (size_t)substep * k.B * k.G : nullptr;
+  int32_t* ac = al ? ws.act_count + substep : nullptr;
   k_grid_fwd<<<cdiv((long long)k.B * k.G, 128), 128, 0, st>>>(k, grid_in, grid_out, grid_fix, substep, *in, ws.fk_pos,
-                                                              ws.fk_rot, ws.fk_vw);
+                                                              ws.fk_rot, ws.fk_vw, al, ac);
   // in-place (forward) mode the raw value of an empty cell is still there when the shell kernel reads it
   const int shell = 2 * (k.rx * k.ry + k.rx * k.rz + k.ry * k.rz);
   k_grid_shell<<<dim3(cdiv(shell, 128), k.B), 128, 0, st>>>(k, grid_in, grid_out, substep, *in, ws.fk_pos, ws.fk_rot,
-                                                            ws.fk_vw);
+                                                            ws.fk_vw, al, ac);
 }
 
 // ================================================================================================
@@ -253,18 +281,36 @@ __global__ void __launch_bounds__(128)
 k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__ ggrid, int f,
            ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
            const float* __restrict__ fk_vw, float* __restrict__ g_fk_pos, float* __restrict__ g_fk_rot,
-           float* __restrict__ g_fk_v, float* __restrict__ g_scal) {
-  int env = blockIdx.y;
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  bool live = c < k.G;
-  size_t idx = (size_t)env * k.G + (live ? c : 0);
+           float* __restrict__ g_fk_v, float* __restrict__ g_scal, const int32_t* __restrict__ act_list,
+           const int32_t* __restrict__ act_count) {
+  // Persistent grid-stride loop over the cells the recompute pass listed (cells with mass + empty shell cells under
+  // a primitive): ~5 % of the grid.  Every other cell keeps the zero the memset gave it.  Whole warps iterate
+  // together (the warp reductions below need all lanes).
+  const int count = *act_count;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int wbase = warp0 * 32; wbase < count; wbase += nwarps * 32) {
+  const bool live = wbase + lane < count;
+  const size_t idx = live ? (size_t)act_list[wbase + lane] : 0;
+  const int env = (int)(idx / k.G);
+  const int c = (int)(idx - (size_t)env * k.G);
   float4 g = grid_raw[idx];
   float4 gv4 = ggrid[idx];
   int ck = c % k.rz, cj = (c / k.rz) % k.ry, ci = c / (k.rz * k.ry);
-  // cells with mass, plus empty shell cells that an out-of-grid particle gathered (clamped index)
-  bool work = live && (gv4.x != 0.f || gv4.y != 0.f || gv4.z != 0.f) && (g.w > 0.f || cell_in_shell(k, ci, cj, ck));
+  bool work = live && (gv4.x != 0.f || gv4.y != 0.f || gv4.z != 0.f);
   if (live && !work) ggrid[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!__any_sync(0xffffffffu, work)) return;  // warp-uniform exit (no block barriers below)
+  if (!__any_sync(0xffffffffu, work)) continue;  // warp-uniform
+  // per-env reductions: the 32 listed cells of a warp almost always belong to one env (warp sum + one atomic);
+  // a warp that straddles two envs (or holds dead lanes) lets every lane add its own contribution
+  const bool uniform = __match_any_sync(0xffffffffu, live ? env : -1) == 0xffffffffu;
+  auto reduce_add = [&](float val, float* addr) {
+    if (uniform) {
+      const float tot = warp_sum(val);
+      if (lane == 0 && tot != 0.f) atomicAdd(addr, tot);
+    } else if (val != 0.f) {
+      atomicAdd(addr, val);
+    }
+  };
   const bool has_mass = g.w > 0.f;
   const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
   const float sfric = in.friction[env];
@@ -304,10 +350,7 @@ k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__
     for (int j = 0; j < 3; ++j) gv[j] = gv4.x * dv[0].d[j] + gv4.y * dv[1].d[j] + gv4.z * dv[2].d[j];
     gsf = gv4.x * dv[0].d[3] + gv4.y * dv[1].d[3] + gv4.z * dv[2].d[3];
   }
-  {
-    float tot = warp_sum(gsf);
-    if ((threadIdx.x & 31) == 0 && tot != 0.f) atomicAdd(&g_scal[env * GS_STRIDE + GS_FRICTION], tot);
-  }
+  reduce_add(gsf, &g_scal[env * GS_STRIDE + GS_FRICTION]);
   // ---- reverse of the primitives, last to first
   for (int q = k.n_prim - 1; q >= 0; --q) {
     bool mine = work && ((act >> q) & 1u);
@@ -337,15 +380,15 @@ k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__
     float* tr = g_fk_rot + t * (k.S + 1) * 4;
 #pragma unroll
     for (int j = 0; j < PRIM_NIN; ++j) {
-      float tot = warp_sum(pg.g[j]);
-      if ((threadIdx.x & 31) != 0 || tot == 0.f) continue;
-      if (j < 3) atomicAdd(&tp[f * 3 + j], tot);
-      else if (j < 7) atomicAdd(&tr[f * 4 + (j - 3)], tot);
-      else if (j < 10) atomicAdd(&tp[(f + 1) * 3 + (j - 7)], tot);
-      else if (j < 14) atomicAdd(&tr[(f + 1) * 4 + (j - 10)], tot);
-      else if (j < 17) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + (j - 14)], tot);
-      else if (j < 18) atomicAdd(&g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + 3], tot);
-      else atomicAdd(&g_fk_v[(t * k.S + f) * 3 + (j - 18)], tot);
+      float* dst;
+      if (j < 3) dst = &tp[f * 3 + j];
+      else if (j < 7) dst = &tr[f * 4 + (j - 3)];
+      else if (j < 10) dst = &tp[(f + 1) * 3 + (j - 7)];
+      else if (j < 14) dst = &tr[(f + 1) * 4 + (j - 10)];
+      else if (j < 17) dst = &g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + (j - 14)];
+      else if (j < 18) dst = &g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + 3];
+      else dst = &g_fk_v[(t * k.S + f) * 3 + (j - 18)];
+      reduce_add(pg.g[j], dst);
     }
   }
   // ---- reverse of v = p / m + dt g
@@ -354,14 +397,15 @@ k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__
     float gm = has_mass ? -(gv[0] * g.x + gv[1] * g.y + gv[2] * g.z) * im * im : 0.f;
     ggrid[idx] = make_float4(gv[0] * im, gv[1] * im, gv[2] * im, gm);
   }
+  }  // listed cells
 }
 
 void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,
                      const MpmWs& ws, cudaStream_t st) {
-  dim3 grid(cdiv(k.G, 128), k.B);
   KScope ks_(KC_GRID_BWD, st);
-  k_grid_bwd<<<grid, 128, 0, st>>>(k, grid_raw, ws.ggrid, substep, *in, ws.fk_pos, ws.fk_rot, ws.fk_vw,
-                                   ws.g_fk_pos, ws.g_fk_rot, ws.g_fk_v, ws.g_scal);
+  k_grid_bwd<<<148 * 8, 128, 0, st>>>(k, grid_raw, ws.ggrid, substep, *in, ws.fk_pos, ws.fk_rot, ws.fk_vw,
+                                      ws.g_fk_pos, ws.g_fk_rot, ws.g_fk_v, ws.g_scal,
+                                      ws.act_list + (size_t)substep * k.B * k.G, ws.act_count + substep);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -39,6 +39,8 @@ struct MpmWs {
   float4* grid_out;     // fwd: == grid_raw; bwd: [S*B*G] updated velocities
   long long* grid_fix;  // deterministic P2G only: [B*G*4] 64-bit fixed-point accumulators of one substep
   float* vt_roll;       // fwd only: [9*N] V^T of the previous substep's SVD (warm start)
+  int32_t* act_list;    // bwd only: [S][B*G] cells listed by the recompute pass for the grid adjoint
+  int32_t* act_count;   // bwd only: [S]
   float* svd_s;         // bwd only: [S*21*N] SVD of F1 per substep (written by the recompute P2G)
   float* fk_pos;        // [B*P*(S+1)*3] (row S = clamp copy of row S-1)
   float* fk_rot;        // [B*P*(S+1)*4]
