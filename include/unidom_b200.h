@@ -168,6 +168,23 @@ int ud_cloth_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const 
                       const float* action, const ud_cloth_state* gout, ud_cloth_state* gin, float* gaction,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Fused env step (replaces jax.lax.scan(self.simulator.step_jax, state, actions) of envs/basic/cloth_env.py:211):
+ * `actions` is [T,B,8] (the 40 pick-and-place sub-actions of get_pnp_actions, :136-173); the forward runs all
+ * T*substeps substeps in ONE launch with the node state in registers and, when `ckpt` is non-null, leaves the state at
+ * the start of every sub-action there (caller-owned, ud_cloth_multi_ckpt_bytes, 256-byte aligned, must stay untouched
+ * until the matching bwd call).  The adjoint recomputes and reverses sub-action by sub-action from those checkpoints;
+ * `gout` = cotangents of the FINAL state, `gin` (all of x, v, primitive0/1, stiffness, mu required) = cotangents of the
+ * input state, `gactions` [T,B,8]. */
+size_t ud_cloth_multi_ckpt_bytes(const ud_cloth_params* p, int32_t T);
+size_t ud_cloth_multi_workspace_bytes(const ud_cloth_params* p, int32_t T);
+int ud_cloth_multi_step_fwd(const ud_cloth_params* p, const ud_cloth_state* in, const int32_t* nbr, const float* L0,
+                            const float* actions, int32_t T, ud_cloth_state* out, void* ckpt, size_t ckpt_bytes,
+                            void* stream);
+int ud_cloth_multi_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const int32_t* nbr, const float* L0,
+                            const float* actions, int32_t T, const void* ckpt, const ud_cloth_state* gout,
+                            ud_cloth_state* gin, float* gactions, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* ---- instrumentation (bench.py): launch counting and per-kernel-class CUDA-event timing ------
  * ud_launch_count: kernels + memsets enqueued by this library since the last reset (host counter).
  * ud_timing_enable(1): subsequent calls bracket every kernel class with cudaEvents on the call's

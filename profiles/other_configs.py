@@ -132,7 +132,36 @@ def cloth_para():
             "fwdbwd_ms": t, "fwd_Gnss": units / fwd / 1e6, "fwdbwd_Gnss": units / t / 1e6}
 
 
+def cloth_env_step():
+    """One ClothEnv.step_diff (40 sub-actions x 50 substeps, cloth_env.py:211) fwd+bwd: fused scan vs 40 calls."""
+    from unidom_b200 import envs
+    B = 128
+    conf = confs.ClothConf()
+    res = {"config": "fold_cloth3 env step (40 sub-actions x 50 substeps)", "envs": B}
+    for fused in (True, False):
+        env = envs.ClothEnv(conf, B, 4, confs.fold_cloth_mask(conf), goal=np.zeros((1, 3), np.float32), aux_reward=True,
+                            fused=fused)
+        _, state = env.reset()
+        g = torch.Generator().manual_seed(0)
+        act = torch.rand((B, env.action_size), generator=g).cuda()
+
+        def fb():
+            a = act.detach().requires_grad_(True)
+            _, r, _, info = env.step_diff(a, state)
+            torch.autograd.grad(r.sum(), [a])
+
+        def fw():
+            with torch.no_grad():
+                env.step_diff(act, state)
+        key = "fused" if fused else "stepwise"
+        res[key + "_fwd_ms"] = timed(fw, n=5)
+        res[key + "_fwdbwd_ms"] = timed(fb, n=5)
+    units = B * 512 * 2000
+    res["fused_fwdbwd_Gnss"] = units / res["fused_fwdbwd_ms"] / 1e6
+    return res
+
+
 if __name__ == "__main__":
-    only = sys.argv[1:] or ["pour_water", "whip_rope", "cloth_para"]
-    for fn in [f for f in (pour_water, whip_rope, cloth_para) if f.__name__ in only]:
+    only = sys.argv[1:] or ["pour_water", "whip_rope", "cloth_para", "cloth_env_step"]
+    for fn in [f for f in (pour_water, whip_rope, cloth_para, cloth_env_step) if f.__name__ in only]:
         print(json.dumps(fn()), flush=True)

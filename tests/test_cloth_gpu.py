@@ -156,3 +156,39 @@ def test_cloth_adjoint_window_from_contact_state(built_lib, substeps):
         e = util.rel_err(a, b)
         print(f"cloth window[{substeps}] grad {name}: rel {e:.3e} cos {cs:.12f}")
         assert cs > 0.9999999 and e < 1e-4, (name, cs, e)
+
+
+def test_fused_scan_is_bit_identical_to_step_by_step(built_lib):
+    """ud_cloth_multi_step_{fwd,bwd} (the scan over sub-actions of cloth_env.py:211 in one call) against the loop of
+    ud_cloth_step_{fwd,bwd}: same kernels, same order => bit-identical states and gradients."""
+    B, T = 3, 6
+    conf, mask, sim, st, act = _scene(B, 4, True)
+    dev = st.x.device
+    g = torch.Generator().manual_seed(8)
+    actions = (torch.rand((T, B, 8), generator=g) * 1.2 - 0.4).to(dev)
+    actions[..., 3] = (actions[..., 3] > 0.3).float()
+    cx = torch.randn(st.x.shape, generator=g).to(dev)
+
+    def run(fused):
+        x = st.x.detach().clone().requires_grad_(True)
+        mu = st.mu.detach().clone().requires_grad_(True)
+        k = st.stiffness.detach().clone().requires_grad_(True)
+        a = actions.detach().clone().requires_grad_(True)
+        s = st._replace(x=x, mu=mu, stiffness=k)
+        if fused:
+            s = sim.scan_step_jax(s, a)
+        else:
+            for t in range(T):
+                s, _ = sim.step_jax(s, a[t])
+        L = (s.x * cx).sum() + (s.v * cx).sum() + s.primitive0.sum()
+        return s, torch.autograd.grad(L, [x, mu, k, a])
+
+    s1, g1 = run(False)
+    s2, g2 = run(True)
+    for k in ("x", "v", "primitive0", "primitive1", "action0", "action1"):
+        assert torch.equal(getattr(s1, k), getattr(s2, k)), k
+    for name, a, b in zip(("x", "mu", "stiffness", "actions"), g1, g2):
+        assert torch.equal(a, b), (name, float((a - b).abs().max()))
+    with torch.no_grad():                      # forward-only path keeps no checkpoints
+        s3 = sim.scan_step_jax(st, actions)
+    assert torch.equal(s3.x, s1.x)

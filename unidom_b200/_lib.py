@@ -93,6 +93,16 @@ def lib():
         L.ud_cloth_step_bwd.restype = C.c_int
         L.ud_cloth_step_bwd.argtypes = [P(ClothParams), P(ClothState), _fp, _fp, _fp, P(ClothState), P(ClothState),
                                         _fp, _fp, C.c_size_t, _fp]
+    L.ud_cloth_multi_ckpt_bytes.restype = C.c_size_t
+    L.ud_cloth_multi_ckpt_bytes.argtypes = [P(ClothParams), C.c_int32]
+    L.ud_cloth_multi_workspace_bytes.restype = C.c_size_t
+    L.ud_cloth_multi_workspace_bytes.argtypes = [P(ClothParams), C.c_int32]
+    L.ud_cloth_multi_step_fwd.restype = C.c_int
+    L.ud_cloth_multi_step_fwd.argtypes = [P(ClothParams), P(ClothState), _fp, _fp, _fp, C.c_int32, P(ClothState), _fp,
+                                          C.c_size_t, _fp]
+    L.ud_cloth_multi_step_bwd.restype = C.c_int
+    L.ud_cloth_multi_step_bwd.argtypes = [P(ClothParams), P(ClothState), _fp, _fp, _fp, C.c_int32, _fp, P(ClothState),
+                                          P(ClothState), _fp, _fp, C.c_size_t, _fp]
     _lib = L
     return L
 
@@ -100,7 +110,8 @@ def lib():
 EXPORTS = (
     "ud_version", "ud_last_error", "ud_mpm_fwd_workspace_bytes", "ud_mpm_bwd_workspace_bytes",
     "ud_mpm_step_fwd", "ud_mpm_step_bwd", "ud_mpm_sort_bins", "ud_mpm_num_keys",
-    "ud_cloth_workspace_bytes", "ud_cloth_step_fwd", "ud_cloth_step_bwd",
+    "ud_cloth_workspace_bytes", "ud_cloth_step_fwd", "ud_cloth_step_bwd", "ud_cloth_multi_ckpt_bytes",
+    "ud_cloth_multi_workspace_bytes", "ud_cloth_multi_step_fwd", "ud_cloth_multi_step_bwd",
     "ud_launch_count", "ud_timing_enable", "ud_timing_collect", "ud_tuning_set",
 )
 

@@ -51,6 +51,26 @@ class _ClothStep(torch.autograd.Function):
         return (None, gaction, *gin)
 
 
+class _ClothMultiStep(torch.autograd.Function):
+    """One custom VJP for a whole scan over T sub-actions (cloth_env.py:211): forward = one launch, the adjoint
+    recomputes from per-sub-action checkpoints inside the library."""
+
+    @staticmethod
+    def forward(ctx, sim, keep, actions, *leaves):
+        leaves = [_f32c(t) for t in leaves]
+        actions = _f32c(actions)
+        out, ckpt = sim._call_multi_fwd(leaves, actions, keep)
+        ctx.sim, ctx.ckpt = sim, ckpt
+        ctx.save_for_backward(actions, *leaves)
+        return tuple(out)
+
+    @staticmethod
+    def backward(ctx, *gout):
+        actions, *leaves = ctx.saved_tensors
+        gin, gactions = ctx.sim._call_multi_bwd(leaves, actions, ctx.ckpt, list(gout))
+        return (None, None, gactions, *gin)
+
+
 class ClothSimulator:
     """B200 drop-in for ClothSimulator (cloth_simulator.py:26-70)."""
 
@@ -152,6 +172,47 @@ class ClothSimulator:
                                        _ptr(gaction), ws, nbytes, self._stream())
         _lib.check(rc, "ud_cloth_step_bwd")
         return gin, gaction
+
+    def _call_multi_fwd(self, leaves, actions, keep):
+        T = actions.shape[0]
+        p = self.params(leaves[0].shape[0], self._stiff_float)
+        out = [torch.empty_like(t) for t in leaves]
+        ckpt, nbytes, cptr = None, 0, C.c_void_p(0)
+        if keep:
+            nbytes = self._L.ud_cloth_multi_ckpt_bytes(C.byref(p), T)
+            ckpt = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            cptr = C.c_void_p(ckpt.data_ptr() + (-ckpt.data_ptr()) % 256)
+        rc = self._L.ud_cloth_multi_step_fwd(C.byref(p), C.byref(self._pack(leaves)), _ptr(self._nbr), _ptr(self._L0),
+                                             _ptr(actions), T, C.byref(self._pack(out)), cptr, nbytes, self._stream())
+        _lib.check(rc, "ud_cloth_multi_step_fwd")
+        return out, ckpt
+
+    def _call_multi_bwd(self, leaves, actions, ckpt, gout):
+        T = actions.shape[0]
+        p = self.params(leaves[0].shape[0], self._stiff_float)
+        gout = [(_f32c(g) if g is not None else None) for g in gout]
+        gin = [torch.zeros_like(t) for t in leaves]
+        gactions = torch.zeros_like(actions)
+        ws, nbytes = self._ws.get(self._L.ud_cloth_multi_workspace_bytes(C.byref(p), T))
+        cptr = C.c_void_p(ckpt.data_ptr() + (-ckpt.data_ptr()) % 256)
+        rc = self._L.ud_cloth_multi_step_bwd(C.byref(p), C.byref(self._pack(leaves)), _ptr(self._nbr), _ptr(self._L0),
+                                             _ptr(actions), T, cptr, C.byref(self._pack(gout)), C.byref(self._pack(gin)),
+                                             _ptr(gactions), ws, nbytes, self._stream())
+        _lib.check(rc, "ud_cloth_multi_step_bwd")
+        return gin, gactions
+
+    def scan_step_jax(self, state: ClothState, actions: torch.Tensor):
+        """jax.lax.scan(self.step_jax, state, actions)[0] for actions [T,B,8] (cloth_env.py:211) as ONE fused call."""
+        self._stiff_float = state.stiffness.is_floating_point()
+        leaves = [getattr(state, k) for k in _LEAVES]
+        leaves[6] = leaves[6].to(torch.float32)
+        # grad mode is off inside Function.forward, so decide here whether the adjoint will need checkpoints
+        keep = torch.is_grad_enabled() and (actions.requires_grad or any(t.requires_grad for t in leaves))
+        out = _ClothMultiStep.apply(self, keep, actions, *leaves)
+        vals = dict(zip(_LEAVES, out))
+        if not self._stiff_float:
+            vals["stiffness"] = state.stiffness
+        return state._replace(**vals)
 
     def step_jax(self, state: ClothState, action: torch.Tensor):
         """vmap(jit(robot_step_wrapper)) (:68-70,107-180): returns (state, state)."""

@@ -206,7 +206,10 @@ __device__ __forceinline__ size_t save_stride(const ClothK& k) { return (size_t)
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT)
 k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, const float* __restrict__ L0_t,
-            const float* __restrict__ action, ud_cloth_state out, float* __restrict__ save) {
+            const float* __restrict__ action, ud_cloth_state out, float* __restrict__ save, int T,
+            float* __restrict__ ckpt) {
+  // T sub-actions (action is [T,B,8]) run back to back with the node state in registers; `ckpt` (nullable) receives
+  // the state at the START of every sub-action: x [T,B,P,3] | v [T,B,P,3] | primitive0 [T,B,4] | primitive1 [T,B,4]
   extern __shared__ float xs[];  // [P*3]
   const int env = blockIdx.x, t = threadIdx.x;
   const bool live = t < k.P;
@@ -225,13 +228,35 @@ k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
     L0[q] = L0_t[n * 8 + q];
     iL0[q] = __frcp_rn(L0[q]);
   }
-  load_actions(action, env, a0, a1);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     ps0[c] = in.primitive0[env * 4 + c];
     ps1[c] = in.primitive1[env * 4 + c];
   }
   const float stiff = in.stiffness[env], mu = in.mu[env];
+  for (int ta = 0; ta < T; ++ta) {
+  load_actions(action + (size_t)ta * k.B * 8, env, a0, a1);
+  if (ckpt) {
+    const size_t BP3 = (size_t)k.B * k.P * 3;
+    float* cx = ckpt + (size_t)ta * BP3 + 3 * o;
+    float* cv = ckpt + (size_t)T * BP3 + (size_t)ta * BP3 + 3 * o;
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        cx[c] = x[c];
+        cv[c] = v[c];
+      }
+    }
+    if (t == 0) {
+      float* c0 = ckpt + 2 * (size_t)T * BP3 + ((size_t)ta * k.B + env) * 4;
+      float* c1 = c0 + (size_t)T * k.B * 4;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        c0[c] = ps0[c];
+        c1[c] = ps1[c];
+      }
+    }
+  }
   for (int s = 0; s < k.S; ++s) {
     if (save) {
       float* sv = save + ((size_t)env * k.S + s) * save_stride(k);
@@ -262,6 +287,7 @@ k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
     advance_gripper(a1, ps1);
     __syncthreads();
   }
+  }  // sub-actions
   if (!out.x) return;
   if (live) {
 #pragma unroll
@@ -588,9 +614,9 @@ int ud_cloth_step_fwd(const ud_cloth_params* p, const ud_cloth_state* in, const 
   cudaStream_t st = (cudaStream_t)stream;
   KScope ks(KC_CLOTH_FWD, st);
   if (k.threads <= 512)
-    k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, *out, nullptr);
+    k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, *out, nullptr, 1, nullptr);
   else
-    k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, *out, nullptr);
+    k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, *out, nullptr, 1, nullptr);
   return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
 }
 
@@ -615,9 +641,9 @@ int ud_cloth_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const 
   {
     KScope ks(KC_CLOTH_FWD, st);  // recompute pass: checkpoint = the sub-action input
     if (k.threads <= 512)
-      k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, none, (float*)workspace);
+      k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, none, (float*)workspace, 1, nullptr);
     else
-      k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, none, (float*)workspace);
+      k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, none, (float*)workspace, 1, nullptr);
   }
   {
     KScope ks(KC_CLOTH_BWD, st);
@@ -625,6 +651,106 @@ int ud_cloth_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const 
       k_cloth_bwd<512><<<k.B, k.threads, smem, st>>>(k, *in, nbr, L0, action, *gout, *gin, gaction, (const float*)workspace);
     else
       k_cloth_bwd<1024><<<k.B, k.threads, smem, st>>>(k, *in, nbr, L0, action, *gout, *gin, gaction, (const float*)workspace);
+  }
+  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+}
+
+// ---- fused env step: T sub-actions per call (cloth_env.py:211 scans robot_step over the 40 pick-and-place
+// sub-actions).  Forward = ONE launch for T*substeps substeps; the adjoint walks the sub-actions backwards from the
+// checkpoints the forward left (recompute 50 substeps, reverse them), all enqueued from here: 2T launches, no host
+// round trips.
+static size_t cloth_ckpt_floats(const ClothK& k, int T) { return (size_t)T * k.B * ((size_t)k.P * 6 + 8); }
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t ud_cloth_multi_ckpt_bytes(const ud_cloth_params* p, int32_t T) {
+  ClothK k;
+  if (!cloth_fold(p, &k) || T < 1) return 0;
+  return al256(cloth_ckpt_floats(k, T) * sizeof(float));
+}
+
+size_t ud_cloth_multi_workspace_bytes(const ud_cloth_params* p, int32_t T) {
+  ClothK k;
+  if (!cloth_fold(p, &k) || T < 1) return 0;
+  // per-substep save slots of one sub-action + two cotangent sets (x, v, primitive0/1, action0/1, stiffness, mu)
+  return ud_cloth_workspace_bytes(p) + 2 * al256(sizeof(float) * (size_t)k.B * ((size_t)k.P * 6 + 18));
+}
+
+int ud_cloth_multi_step_fwd(const ud_cloth_params* p, const ud_cloth_state* in, const int32_t* nbr, const float* L0,
+                            const float* actions, int32_t T, ud_cloth_state* out, void* ckpt, size_t ckpt_bytes,
+                            void* stream) {
+  ClothK k;
+  if (!cloth_fold(p, &k) || T < 1) return UD_E_INVALID;
+  if (!cloth_state_ok(in) || !cloth_state_ok(out) || !nbr || !L0 || !actions) return UD_E_INVALID;
+  if (ckpt && (ckpt_bytes < ud_cloth_multi_ckpt_bytes(p, T) || ((uintptr_t)ckpt & 255))) return UD_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  KScope ks(KC_CLOTH_FWD, st);
+  if (k.threads <= 512)
+    k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, actions, *out, nullptr, T, (float*)ckpt);
+  else
+    k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, actions, *out, nullptr, T, (float*)ckpt);
+  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+}
+
+int ud_cloth_multi_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const int32_t* nbr, const float* L0,
+                            const float* actions, int32_t T, const void* ckpt, const ud_cloth_state* gout,
+                            ud_cloth_state* gin, float* gactions, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  ClothK k;
+  if (!cloth_fold(p, &k) || T < 1) return UD_E_INVALID;
+  if (!cloth_state_ok(in) || !gout || !gin || !nbr || !L0 || !actions || !ckpt || !gactions) return UD_E_INVALID;
+  if (!gin->x || !gin->v || !gin->primitive0 || !gin->primitive1 || !gin->stiffness || !gin->mu) return UD_E_INVALID;
+  if (!workspace || workspace_bytes < ud_cloth_multi_workspace_bytes(p, T) || ((uintptr_t)workspace & 255))
+    return UD_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t BP3 = (size_t)k.B * k.P * 3;
+  float* save = (float*)workspace;
+  // two cotangent sets for the ping-pong between sub-actions
+  ud_cloth_state g[2];
+  char* base = (char*)workspace + ud_cloth_workspace_bytes(p);
+  for (int i = 0; i < 2; ++i) {
+    float* f = (float*)(base + i * al256(sizeof(float) * (size_t)k.B * ((size_t)k.P * 6 + 18)));
+    g[i].x = f;
+    g[i].v = f + BP3;
+    g[i].primitive0 = f + 2 * BP3;
+    g[i].primitive1 = g[i].primitive0 + 4 * k.B;
+    g[i].action0 = g[i].primitive1 + 4 * k.B;
+    g[i].action1 = g[i].action0 + 4 * k.B;
+    g[i].stiffness = g[i].action1 + 4 * k.B;
+    g[i].mu = g[i].stiffness + k.B;
+  }
+  ud_cloth_state none;
+  memset(&none, 0, sizeof(none));
+  size_t smem = sizeof(float) * ((size_t)27 * k.P + 64);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_cloth_bwd<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (27 * 512 + 64)));
+    cudaFuncSetAttribute(k_cloth_bwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (27 * 1024 + 64)));
+    attr = true;
+  }
+  const float* ck = (const float*)ckpt;
+  for (int t = T - 1; t >= 0; --t) {
+    ud_cloth_state s_in = *in;  // state at the start of sub-action t (stiffness / mu are constants of the call)
+    s_in.x = const_cast<float*>(ck + (size_t)t * BP3);
+    s_in.v = const_cast<float*>(ck + (size_t)T * BP3 + (size_t)t * BP3);
+    s_in.primitive0 = const_cast<float*>(ck + 2 * (size_t)T * BP3 + (size_t)t * k.B * 4);
+    s_in.primitive1 = s_in.primitive0 + (size_t)T * k.B * 4;
+    const float* a_t = actions + (size_t)t * k.B * 8;
+    const ud_cloth_state& go = (t == T - 1) ? *gout : g[(t + 1) & 1];
+    const ud_cloth_state& gi = (t == 0) ? *gin : g[t & 1];
+    {
+      KScope ks(KC_CLOTH_FWD, st);
+      if (k.threads <= 512)
+        k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, s_in, nbr, L0, a_t, none, save, 1, nullptr);
+      else
+        k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, s_in, nbr, L0, a_t, none, save, 1, nullptr);
+    }
+    {
+      KScope ks(KC_CLOTH_BWD, st);
+      if (k.threads <= 512)
+        k_cloth_bwd<512><<<k.B, k.threads, smem, st>>>(k, s_in, nbr, L0, a_t, go, gi, gactions + (size_t)t * k.B * 8, save);
+      else
+        k_cloth_bwd<1024><<<k.B, k.threads, smem, st>>>(k, s_in, nbr, L0, a_t, go, gi, gactions + (size_t)t * k.B * 8, save);
+    }
   }
   return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
 }

@@ -50,8 +50,9 @@ class ClothEnv:
     """B200 drop-in for the reference's ClothEnv (fold_cloth1/3, unfold_cloth1/3, fold_cloth1_para)."""
 
     def __init__(self, conf, batch_size, max_steps, cloth_mask, goal=None, aux_reward=False, device="cuda",
-                 para=False):
+                 para=False, fused=True):
         self.conf, self.batch_size, self.max_steps, self.aux_reward = conf, batch_size, max_steps, aux_reward
+        self.fused = fused                                   # scan over the 40 sub-actions inside the library
         self.simulator = ClothSimulator(conf, batch_size, None, cloth_mask, device=device)
         self.device = self.simulator.device
         self.action_size = 6
@@ -87,8 +88,11 @@ class ClothEnv:
         old_chamfer = calc_chamfer(state.x, self.goal)
         contact = torch.sqrt(((actions[:, None, :3] - state.x) ** 2).sum(-1)).min(-1).values
         sub = get_pnp_actions(actions, state)
-        for a in sub:                                   # lax.scan(self.simulator.step_jax, ...) (:211)
-            state, _ = self.simulator.step_jax(state, a)
+        if self.fused:                                  # lax.scan(self.simulator.step_jax, ...) (:211) as one call
+            state = self.simulator.scan_step_jax(state, sub.contiguous())
+        else:
+            for a in sub:
+                state, _ = self.simulator.step_jax(state, a)
         state = state._replace(cur_step=state.cur_step + 1)
         obs = self.get_obs(state)
         chamfer = calc_chamfer(state.x, self.goal)
