@@ -220,6 +220,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--p2g-mode", type=int, default=0)
     ap.add_argument("--tune", default="", help="development A/B switches, e.g. svd_warm=0")
+    ap.add_argument("--adjoint", default="auto", choices=["auto", "tape", "recompute"],
+                    help="tape: the forward of a differentiated step keeps its substep residuals in HBM (default when "
+                         "they fit); recompute: keep the step input only and re-run the substeps in the backward")
     ap.add_argument("--settle", type=int, default=8, help="env steps run before timing to reach a mid-push state")
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer leg")
     args = ap.parse_args()
@@ -243,7 +246,7 @@ def main():
         name, val = kv.split("=")
         assert L.ud_tuning_set(name.encode(), int(val)) >= 0, kv
     conf = confs.shape_elasto_plastic_conf()
-    sim = SimpleMPMSimulator(conf, args.envs, device=dev, p2g_mode=args.p2g_mode)
+    sim = SimpleMPMSimulator(conf, args.envs, device=dev, p2g_mode=args.p2g_mode, adjoint=args.adjoint)
     state = build_scene(sim, args.density)
     B, n = state.x.shape[:2]
     S = conf.steps
@@ -413,6 +416,9 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(n), "state": f"every step starts from the scene after {args.settle} settle steps", "envs_per_gpu": B, "particles_per_env": n, "substeps": S,
                        "l2": f"inputs larger than L2 (state+checkpoints {B * n * 96 * (S + 1) / 1e9:.2f} GB per step)",
+                       "adjoint": f"{args.adjoint}: " + ("substep residuals kept in HBM by the forward ("
+                                   f"{L.ud_mpm_tape_bytes(C.byref(sim.params())) / 1e9:.2f} GB per step in flight)"
+                                   if args.adjoint != "recompute" else "step input kept, substeps recomputed"),
                        "p2g_mode": "atomic" if args.p2g_mode == 0 else "deterministic",
                        "collective": "none in the step (envs are independent; APG's policy-gradient all-reduce "
                                      "is outside this path)"},

@@ -117,6 +117,22 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
                     ud_mpm_state* gin, float* gaction, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* Taped pair: the same step, but the forward keeps every substep's start state, both grids, the
+ * SVD factors and the active-cell lists in `tape` (ud_mpm_tape_bytes(p) bytes, 256-byte aligned,
+ * caller-owned), and ud_mpm_step_bwd_taped reverses from it without recomputing the S substeps.
+ * This is what jax.grad of the reference does implicitly (XLA keeps the residuals of every substep
+ * of the lax.scan, mpm_simulator.py:425); ud_mpm_step_bwd is the low-memory alternative.  The tape
+ * must stay untouched between the two calls; it is only read by the reverse pass (its tail holds
+ * the reverse pass's scratch), so the same tape can be reversed more than once.  Same results as
+ * ud_mpm_step_fwd / ud_mpm_step_bwd: bit-identical with UD_P2G_DETERMINISTIC. */
+size_t ud_mpm_tape_bytes(const ud_mpm_params* p);
+int ud_mpm_step_fwd_taped(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material,
+                          const float* h, const float* action, ud_mpm_state* out, void* tape,
+                          size_t tape_bytes, void* stream);
+int ud_mpm_step_bwd_taped(const ud_mpm_params* p, const ud_mpm_state* in, const float* action,
+                          const ud_mpm_state* gout, ud_mpm_state* gin, float* gaction, void* tape,
+                          size_t tape_bytes, void* stream);
+
 /* The per-frame binning the step uses, exposed for the bit-exactness check:
  * base = int32(x*inv_dx - 0.5) (mpm_simulator.py:233, no FMA contraction),
  * key  = 4x4x4-block-major cell key, perm = stable argsort(key) per env.

@@ -211,6 +211,51 @@ def test_p2g_deterministic_mode_is_bit_reproducible(built_lib):
     assert util.rel_err(outs[0][0].x, ref.x) < 1e-4 and util.rel_err(outs[0][0].F, ref.F) < 1e-4
 
 
+def test_taped_adjoint_matches_recompute_adjoint(built_lib):
+    """ud_mpm_step_fwd_taped/_bwd_taped (residuals of every substep kept in HBM) against ud_mpm_step_fwd/_bwd (step
+    input kept, substeps recomputed): the same kernels on the same data, so the forward is bit-identical in
+    deterministic mode and the gradients differ only by the order of the fp32 REDs of G2P^T."""
+    from unidom_b200 import _lib
+    conf = _conf(steps=16, n_primitive=1)
+    B = 3
+    sims = {m: _sim(conf, B, p2g_mode=_lib.UD_P2G_DETERMINISTIC, adjoint=m) for m in ("tape", "recompute", "auto")}
+    st = util.mini_plasticine(sims["tape"], B, seed=5, density=2.0)
+    for m in ("recompute", "auto"):
+        sims[m].material, sims[m].h, sims[m].n_particles = sims["tape"].material, sims["tape"].h, sims["tape"].n_particles
+        sims[m]._material_dev, sims[m]._h_dev = sims["tape"]._material_dev, sims["tape"]._h_dev
+    sims["auto"].tape_budget_bytes = 0                       # budget exhausted -> must fall back to recompute
+    act = (_actions(B, 1, seed=6) * 0.8).to(st.x.device)
+    g = torch.Generator().manual_seed(9)
+    n = st.x.shape[1]
+    cot = {"x": torch.randn((B, n, 3), generator=g) * 1e-3, "v": torch.randn((B, n, 3), generator=g) * 1e-4,
+           "C": torch.randn((B, n, 3, 3), generator=g) * 1e-6, "F": torch.randn((B, n, 3, 3), generator=g) * 1e-4,
+           "p0.position": torch.randn((B, 16, 3), generator=g) * 1e-3, "p0.rotation": torch.zeros((B, 16, 4))}
+    res, outs, chose, held = {}, {}, {}, {}
+    tape_bytes = sims["tape"]._L.ud_mpm_tape_bytes(__import__("ctypes").byref(sims["tape"].params()))
+    for m, sim in sims.items():
+        def step(s, a, sim=sim, m=m):
+            outs[m] = sim.step_jax(s, a)[0]
+            return outs[m]
+        m0 = torch.cuda.memory_allocated()
+        res[m] = _run_grad(step, st, act, cot, 1, lambda t: t.to(st.x.device))
+        chose[m], held[m] = sim.last_adjoint, torch.cuda.memory_allocated() - m0
+    assert chose == {"tape": "tape", "recompute": "recompute", "auto": "recompute"}, chose
+    assert held["tape"] < tape_bytes // 2, (held, tape_bytes)   # the tape went with the graph's buffers, outputs still held
+    for k in ("x", "v", "C", "F", "J"):
+        assert torch.equal(getattr(outs["tape"], k), getattr(outs["recompute"], k)), k
+    assert torch.equal(outs["tape"].primitives[0].position, outs["recompute"].primitives[0].position)
+    # the reverse pass is the same code on bit-identical residuals; what differs run to run is the order of the fp32
+    # REDs of G2P^T, amplified by 16 substeps of SVD adjoints: "auto" IS a second recompute run = the noise floor
+    for k in res["tape"]:
+        if float(res["recompute"][k].abs().max()) <= 1e-20:
+            continue
+        e = util.rel_err(res["tape"][k], res["recompute"][k])
+        fl = util.rel_err(res["auto"][k], res["recompute"][k])
+        cs = util.cosine(res["tape"][k], res["recompute"][k])
+        print(f"taped vs recompute grad {k:18s} rel {e:.3e} cos {cs:.8f} | recompute vs recompute rel {fl:.3e}")
+        assert cs > 0.999999 and e < max(1e-3, 10 * fl), (k, e, fl, cs)
+
+
 def test_edge_cases_out_of_grid_nan_single_env(built_lib):
     """B = 1, a particle count that is not a multiple of the CTA size, particles outside the grid (scatter
     dropped / gather clamped / negative index wrap), NaN in the input state (norm_grad_state's

@@ -83,6 +83,13 @@ def lib():
     L.ud_mpm_step_bwd.restype = C.c_int
     L.ud_mpm_step_bwd.argtypes = [P(MpmParams), P(MpmState), _fp, _fp, _fp, P(MpmState), P(MpmState), _fp,
                                   _fp, C.c_size_t, _fp]
+    L.ud_mpm_tape_bytes.restype = C.c_size_t
+    L.ud_mpm_tape_bytes.argtypes = [P(MpmParams)]
+    L.ud_mpm_step_fwd_taped.restype = C.c_int
+    L.ud_mpm_step_fwd_taped.argtypes = [P(MpmParams), P(MpmState), _fp, _fp, _fp, P(MpmState), _fp, C.c_size_t, _fp]
+    L.ud_mpm_step_bwd_taped.restype = C.c_int
+    L.ud_mpm_step_bwd_taped.argtypes = [P(MpmParams), P(MpmState), _fp, P(MpmState), P(MpmState), _fp, _fp,
+                                        C.c_size_t, _fp]
     L.ud_mpm_sort_bins.restype = C.c_int
     L.ud_mpm_sort_bins.argtypes = [P(MpmParams), _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]
     if hasattr(L, "ud_cloth_step_fwd"):
@@ -109,7 +116,8 @@ def lib():
 
 EXPORTS = (
     "ud_version", "ud_last_error", "ud_mpm_fwd_workspace_bytes", "ud_mpm_bwd_workspace_bytes",
-    "ud_mpm_step_fwd", "ud_mpm_step_bwd", "ud_mpm_sort_bins", "ud_mpm_num_keys",
+    "ud_mpm_step_fwd", "ud_mpm_step_bwd", "ud_mpm_tape_bytes", "ud_mpm_step_fwd_taped", "ud_mpm_step_bwd_taped",
+    "ud_mpm_sort_bins", "ud_mpm_num_keys",
     "ud_cloth_workspace_bytes", "ud_cloth_step_fwd", "ud_cloth_step_bwd", "ud_cloth_multi_ckpt_bytes",
     "ud_cloth_multi_workspace_bytes", "ud_cloth_multi_step_fwd", "ud_cloth_multi_step_bwd",
     "ud_launch_count", "ud_timing_enable", "ud_timing_collect", "ud_tuning_set",

@@ -269,25 +269,14 @@ int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   return UD_OK;
 }
 
-int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material, const float* h,
-                    const float* action, const ud_mpm_state* gout, ud_mpm_state* gin, float* gaction,
-                    void* workspace, size_t workspace_bytes, void* stream) {
-  MpmConst k;
-  if (!mpm_fold_constants(p, &k)) return fail(UD_E_INVALID, "ud_mpm_step_bwd: invalid params");
-  if (!state_ok(k, in) || !gout || !gin || !material || !h || (k.n_prim > 0 && !action))
-    return fail(UD_E_INVALID, "ud_mpm_step_bwd: null pointer");
-  MpmWs ws;
-  size_t need = mpm_carve(p, k, true, workspace, &ws);
-  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
-    return fail(UD_E_WORKSPACE, "ud_mpm_step_bwd: workspace too small or misaligned");
-  cudaStream_t st = (cudaStream_t)stream;
+// Forward sweep that keeps every substep's start state, both grids, the SVDs and the active-cell lists in a
+// bwd-layout workspace (the "tape"): the adjoint's recompute pass, and the whole of the taped forward.
+static void mpm_record_pass(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
+                            const float* action, ud_mpm_state* out, MpmWs& ws, cudaStream_t st) {
   const size_t slot = (size_t)PS_NCOMP * k.N, BG = (size_t)k.B * k.G;
-  const size_t P = k.n_prim > 0 ? k.n_prim : 1;
-
-  // ---- recompute pass: checkpoint = the step input; every substep's start state and grids are kept
   launch_sort(k, in->x, ws, nullptr, st);
   launch_gather_state(k, in, material, h, ws, ws.ps, st);
-  launch_fk_fwd(k, in, action, nullptr, ws, st);
+  launch_fk_fwd(k, in, action, out, ws, st);
   if (!ws.grid_fix) zero_async(ws.grid_raw, 16 * BG * k.S, st);
   zero_async(ws.act_count, 4 * (size_t)k.S, st);
   for (int f = 0; f < k.S; ++f) {
@@ -301,7 +290,12 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
     launch_grid_fwd(k, ws.grid_raw + BG * f, ws.grid_out + BG * f, ws.grid_fix, f, in, ws, st);
     launch_g2p(k, s_in, s_out, ws.grid_out + BG * f, f, ws, st);
   }
-  // ---- reverse pass
+}
+
+static void mpm_reverse_pass(const MpmConst& k, const ud_mpm_state* in, const float* action, const ud_mpm_state* gout,
+                             ud_mpm_state* gin, float* gaction, MpmWs& ws, cudaStream_t st) {
+  const size_t slot = (size_t)PS_NCOMP * k.N, BG = (size_t)k.B * k.G;
+  const size_t P = k.n_prim > 0 ? k.n_prim : 1;
   launch_gather_cot(k, gout, ws, st);
   zero_async(ws.g_fk_pos, 4 * (size_t)k.B * P * (k.S + 1) * 3, st);
   zero_async(ws.g_fk_rot, 4 * (size_t)k.B * P * (k.S + 1) * 4, st);
@@ -318,7 +312,61 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   }
   launch_fk_bwd(k, in, action, gout, ws, st);
   launch_finish_bwd(k, in, gout, gin, action, gaction, ws, st);
+}
+
+int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material, const float* h,
+                    const float* action, const ud_mpm_state* gout, ud_mpm_state* gin, float* gaction,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  MpmConst k;
+  if (!mpm_fold_constants(p, &k)) return fail(UD_E_INVALID, "ud_mpm_step_bwd: invalid params");
+  if (!state_ok(k, in) || !gout || !gin || !material || !h || (k.n_prim > 0 && !action))
+    return fail(UD_E_INVALID, "ud_mpm_step_bwd: null pointer");
+  MpmWs ws;
+  size_t need = mpm_carve(p, k, true, workspace, &ws);
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
+    return fail(UD_E_WORKSPACE, "ud_mpm_step_bwd: workspace too small or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  mpm_record_pass(k, in, material, h, action, nullptr, ws, st);   // checkpoint = the step input
+  mpm_reverse_pass(k, in, action, gout, gin, gaction, ws, st);
   if (cudaGetLastError() != cudaSuccess) return fail(UD_E_CUDA, "ud_mpm_step_bwd: launch failed");
+  return UD_OK;
+}
+
+size_t ud_mpm_tape_bytes(const ud_mpm_params* p) { return ud_mpm_bwd_workspace_bytes(p); }
+
+int ud_mpm_step_fwd_taped(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material, const float* h,
+                          const float* action, ud_mpm_state* out, void* tape, size_t tape_bytes, void* stream) {
+  MpmConst k;
+  if (!mpm_fold_constants(p, &k)) return fail(UD_E_INVALID, "ud_mpm_step_fwd_taped: invalid params");
+  if (!state_ok(k, in) || !state_ok(k, out) || !material || !h || (k.n_prim > 0 && !action))
+    return fail(UD_E_INVALID, "ud_mpm_step_fwd_taped: null pointer");
+  MpmWs ws;
+  size_t need = mpm_carve(p, k, true, tape, &ws);
+  if (!tape || tape_bytes < need || ((uintptr_t)tape & 255))
+    return fail(UD_E_WORKSPACE, "ud_mpm_step_fwd_taped: tape too small or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  mpm_record_pass(k, in, material, h, action, out, ws, st);
+  launch_unsort_state(k, ws.ps + (size_t)PS_NCOMP * k.N * k.S, in->J, ws, out, st);
+  cudaMemcpyAsync(out->friction, in->friction, 4 * (size_t)k.B, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(out->mu, in->mu, 4 * (size_t)k.B, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(out->lamda, in->lamda, 4 * (size_t)k.B, cudaMemcpyDeviceToDevice, st);
+  if (cudaGetLastError() != cudaSuccess) return fail(UD_E_CUDA, "ud_mpm_step_fwd_taped: launch failed");
+  return UD_OK;
+}
+
+int ud_mpm_step_bwd_taped(const ud_mpm_params* p, const ud_mpm_state* in, const float* action,
+                          const ud_mpm_state* gout, ud_mpm_state* gin, float* gaction, void* tape, size_t tape_bytes,
+                          void* stream) {
+  MpmConst k;
+  if (!mpm_fold_constants(p, &k)) return fail(UD_E_INVALID, "ud_mpm_step_bwd_taped: invalid params");
+  if (!state_ok(k, in) || !gout || !gin || (k.n_prim > 0 && !action))
+    return fail(UD_E_INVALID, "ud_mpm_step_bwd_taped: null pointer");
+  MpmWs ws;
+  size_t need = mpm_carve(p, k, true, tape, &ws);
+  if (!tape || tape_bytes < need || ((uintptr_t)tape & 255))
+    return fail(UD_E_WORKSPACE, "ud_mpm_step_bwd_taped: tape too small or misaligned");
+  mpm_reverse_pass(k, in, action, gout, gin, gaction, ws, (cudaStream_t)stream);
+  if (cudaGetLastError() != cudaSuccess) return fail(UD_E_CUDA, "ud_mpm_step_bwd_taped: launch failed");
   return UD_OK;
 }
 

@@ -78,6 +78,10 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def _aligned(buf):
+    return C.c_void_p(buf.data_ptr() + (-buf.data_ptr()) % 256)
+
+
 def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
@@ -106,31 +110,39 @@ def flatten_state(state: MPMState, n_prim: int):
 
 
 class _MpmStep(torch.autograd.Function):
-    """One custom VJP per (env batch, sub-action): fwd = S substeps, bwd = recompute + reverse
+    """One custom VJP per (env batch, sub-action): fwd = S substeps; bwd = reverse from the tape the forward kept,
+    or recompute + reverse when the step ran without a tape
     (replaces substep_wrapper / norm_grad* custom_vjps, mpm_simulator.py:332-411)."""
 
     @staticmethod
-    def forward(ctx, sim, softness_list, action, *leaves):
+    def forward(ctx, sim, softness_list, want_tape, action, *leaves):
         leaves = [_f32c(t) for t in leaves]
         action = _f32c(action)
-        out_leaves = sim._call_fwd(leaves, softness_list, action)
+        out_leaves, tape = sim._call_fwd(leaves, softness_list, action, want_tape)
         ctx.sim = sim
         ctx.softness_list = softness_list
-        ctx.save_for_backward(action, *leaves)
+        ctx.taped = tape is not None
+        # the tape is a saved tensor, so autograd frees it with the graph's buffers right after the backward
+        ctx.save_for_backward(action, *leaves, *([tape] if ctx.taped else []))
         return tuple(out_leaves)
 
     @staticmethod
     def backward(ctx, *gout):
         action, *leaves = ctx.saved_tensors
-        gin, gaction = ctx.sim._call_bwd(leaves, ctx.softness_list, action, list(gout))
-        return (None, None, gaction, *gin)
+        tape = leaves.pop() if ctx.taped else None
+        gin, gaction = ctx.sim._call_bwd(leaves, ctx.softness_list, action, list(gout), tape)
+        return (None, None, None, gaction, *gin)
 
 
 class SimpleMPMSimulator:
     """B200 drop-in for SimpleMPMSimulator (mpm_simulator.py:27-63)."""
 
     def __init__(self, conf, batch_size, use_position_control=False, device="cuda", sdf_kind=None,
-                 p2g_mode=_lib.UD_P2G_ATOMIC):
+                 p2g_mode=_lib.UD_P2G_ATOMIC, adjoint="auto", tape_budget_bytes=None):
+        """adjoint: "tape" keeps every substep's residuals of a differentiated step in HBM until its backward (what
+        jax.grad of the reference's lax.scan does); "recompute" keeps only the step input and re-runs the S substeps
+        in the backward (1/S of the memory, +40 % time); "auto" tapes while this process's allocated device memory plus
+        the new tape stays within `tape_budget_bytes` (default: 70 % of the device's memory) and recomputes beyond."""
         self._L = _lib.lib()  # raises when the extension is missing
         if not torch.cuda.is_available():
             raise RuntimeError("unidom_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -148,6 +160,13 @@ class SimpleMPMSimulator:
         self.p2g_mode = int(p2g_mode)
         self._ws_fwd = _Workspace(self.device)
         self._ws_bwd = _Workspace(self.device)
+        if adjoint not in ("auto", "tape", "recompute"):
+            raise ValueError(f"adjoint={adjoint!r}: expected 'auto', 'tape' or 'recompute'")
+        self.adjoint = adjoint
+        if tape_budget_bytes is None:
+            tape_budget_bytes = torch.cuda.get_device_properties(self.device).total_memory * 7 // 10
+        self.tape_budget_bytes = int(tape_budget_bytes)
+        self.last_adjoint = None        # "tape" / "recompute": what the last differentiated forward chose
         self._rng = np.random.RandomState(getattr(conf, "seed", 0))
 
     # ------------------------------------------------------------- scene construction
@@ -254,24 +273,41 @@ class SimpleMPMSimulator:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _call_fwd(self, leaves, softness_list, action):
+    def _call_fwd(self, leaves, softness_list, action, want_tape=False):
         p = self.params(B=leaves[0].shape[0], n=leaves[0].shape[1])
         out = [torch.empty_like(t) for t in leaves]
         soft_out = [torch.empty_like(t) for t in softness_list]
         sin, sout = self._pack(leaves, softness_list), self._pack(out, soft_out)
+        if want_tape and self.adjoint != "recompute":
+            need = self._L.ud_mpm_tape_bytes(C.byref(p))
+            if self.adjoint == "tape" or torch.cuda.memory_allocated(self.device) + need <= self.tape_budget_bytes:
+                tape = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+                rc = self._L.ud_mpm_step_fwd_taped(C.byref(p), C.byref(sin), _ptr(self._material_dev),
+                                                   _ptr(self._h_dev), _ptr(action), C.byref(sout), _aligned(tape),
+                                                   need, self._stream())
+                _lib.check(rc, "ud_mpm_step_fwd_taped")
+                self.last_adjoint = "tape"
+                return out, tape
+        if want_tape:
+            self.last_adjoint = "recompute"
         ws, nbytes = self._ws_fwd.get(self._L.ud_mpm_fwd_workspace_bytes(C.byref(p)))
         rc = self._L.ud_mpm_step_fwd(C.byref(p), C.byref(sin), _ptr(self._material_dev), _ptr(self._h_dev),
                                      _ptr(action), C.byref(sout), ws, nbytes, self._stream())
         _lib.check(rc, "ud_mpm_step_fwd")
-        return out
+        return out, None
 
-    def _call_bwd(self, leaves, softness_list, action, gout):
+    def _call_bwd(self, leaves, softness_list, action, gout, tape=None):
         p = self.params(B=leaves[0].shape[0], n=leaves[0].shape[1])
         gout = [(_f32c(g) if g is not None else None) for g in gout]
         gin = [torch.zeros_like(t) for t in leaves]
         gaction = torch.zeros_like(action)
         sin = self._pack(leaves, softness_list)
         sgo, sgi = self._pack(gout, None), self._pack(gin, None)
+        if tape is not None:
+            rc = self._L.ud_mpm_step_bwd_taped(C.byref(p), C.byref(sin), _ptr(action), C.byref(sgo), C.byref(sgi),
+                                               _ptr(gaction), _aligned(tape), tape.numel() - 256, self._stream())
+            _lib.check(rc, "ud_mpm_step_bwd_taped")
+            return gin, gaction
         ws, nbytes = self._ws_bwd.get(self._L.ud_mpm_bwd_workspace_bytes(C.byref(p)))
         rc = self._L.ud_mpm_step_bwd(C.byref(p), C.byref(sin), _ptr(self._material_dev), _ptr(self._h_dev),
                                      _ptr(action), C.byref(sgo), C.byref(sgi), _ptr(gaction), ws, nbytes,
@@ -284,7 +320,9 @@ class SimpleMPMSimulator:
         n_prim = int(self.conf.n_primitive)
         leaves = flatten_state(state, n_prim)
         softness = [_f32c(state.primitives[q].softness) for q in range(n_prim)]
-        out = _MpmStep.apply(self, softness, action, *leaves)
+        # grad mode is off inside Function.forward: decide here whether a backward can follow
+        want_tape = torch.is_grad_enabled() and (action.requires_grad or any(t.requires_grad for t in leaves))
+        out = _MpmStep.apply(self, softness, want_tape, action, *leaves)
         vals = dict(zip(_STATE_LEAVES, out[:len(_STATE_LEAVES)]))
         prims = []
         n0, npl = len(_STATE_LEAVES), len(_PRIM_LEAVES)
