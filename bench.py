@@ -34,6 +34,7 @@ import torch  # noqa: E402
 # algorithmic bytes per particle per launch of each kernel class:
 ALG_BYTES = {"p2g": 132, "g2p": 72, "g2p_bwd": 84, "p2g_bwd": 240}
 ALG_BYTES_FWD, ALG_BYTES_FWDBWD = 200, 700          # SURVEY.md section 8(d) contract figures
+ALG_BYTES_TAPED = 500                               # section 8(d) "store-all variant": no recompute pass
 
 DENSITY, ENVS_PER_GPU = 3.9, 32
 
@@ -220,9 +221,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--p2g-mode", type=int, default=0)
     ap.add_argument("--tune", default="", help="development A/B switches, e.g. svd_warm=0")
-    ap.add_argument("--adjoint", default="auto", choices=["auto", "tape", "recompute"],
-                    help="tape: the forward of a differentiated step keeps its substep residuals in HBM (default when "
-                         "they fit); recompute: keep the step input only and re-run the substeps in the backward")
+    ap.add_argument("--adjoint", default="recompute", choices=["auto", "tape", "recompute"],
+                    help="recompute (headline, what north_star asks for): keep the step input only and re-run the "
+                         "substeps in the backward; tape: the forward keeps its substep residuals in HBM (reported "
+                         "next to the headline as `taped`)")
     ap.add_argument("--settle", type=int, default=8, help="env steps run before timing to reach a mid-push state")
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer leg")
     args = ap.parse_args()
@@ -303,6 +305,32 @@ def main():
         torch.cuda.synchronize(dev)
     fwd_value = world * units_per_step * args.steps / (f0.elapsed_time(f1) * 1e-3)
 
+    # ---------------- the same step with the taped adjoint (forward keeps the substep residuals; no recompute pass)
+    taped = None
+    if args.adjoint == "recompute":
+        sim.adjoint = "tape"
+        for _ in range(3):
+            fwd_bwd(sim, state, action, cot)
+        torch.cuda.synchronize(dev)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            out_t, grads_t, _ = fwd_bwd(sim, state, action, cot)
+        t1.record()
+        barrier()
+        tms = t0.elapsed_time(t1)
+        if dist is not None:
+            t = torch.tensor([tms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tms = float(t.item())
+        tv = world * units_per_step * args.steps / (tms * 1e-3)
+        taped = {"value": tv, "unit": "particle-substeps/s", "ms_per_step": tms / args.steps,
+                 "tape_bytes_per_step": int(L.ud_mpm_tape_bytes(C.byref(sim.params()))),
+                 "algorithmic_bytes_per_particle_substep": ALG_BYTES_TAPED,
+                 "step_frac": (tv / world) * ALG_BYTES_TAPED / 1e9 / peaks()[0]}
+        del out_t, grads_t
+        sim.adjoint = "recompute"
+
     # ---------------- per-kernel-class timing (roofline), live CUDA events on the launch stream
     L.ud_timing_enable(1)
     nprof = min(args.steps, 5)
@@ -334,7 +362,8 @@ def main():
                 "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": kern[dom]["share"],
                 "algorithmic_bytes_per_launch": ALG_BYTES[dom] * B * n,
-                "step_frac_fwdbwd": (value / world) * ALG_BYTES_FWDBWD / 1e9 / peak,
+                "step_frac_fwdbwd": (value / world) * (ALG_BYTES_FWDBWD if args.adjoint == "recompute"
+                                                        else ALG_BYTES_TAPED) / 1e9 / peak,
                 "step_frac_fwd": (fwd_value / world) * ALG_BYTES_FWD / 1e9 / peak}
 
     # ---------------- end-to-end with host buffers (pinned), copies inside the timed region
@@ -418,11 +447,13 @@ def main():
                        "l2": f"inputs larger than L2 (state+checkpoints {B * n * 96 * (S + 1) / 1e9:.2f} GB per step)",
                        "adjoint": f"{args.adjoint}: " + ("substep residuals kept in HBM by the forward ("
                                    f"{L.ud_mpm_tape_bytes(C.byref(sim.params())) / 1e9:.2f} GB per step in flight)"
-                                   if args.adjoint != "recompute" else "step input kept, substeps recomputed"),
+                                   if args.adjoint != "recompute" else
+                                   "step input kept, the S substeps recomputed in the backward"),
                        "p2g_mode": "atomic" if args.p2g_mode == 0 else "deterministic",
                        "collective": "none in the step (envs are independent; APG's policy-gradient all-reduce "
                                      "is outside this path)"},
             "forward_only": {"value": fwd_value, "unit": "particle-substeps/s"},
+            "taped": taped,
             "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,

@@ -201,6 +201,22 @@ int ud_cloth_multi_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, 
                             ud_cloth_state* gin, float* gactions, void* workspace, size_t workspace_bytes,
                             void* stream);
 
+/* ---- reward kernels either side of the step inside the differentiated rollout -----------------
+ * calc_chamfer(x, y) (DaXBench/daxbench/core/utils/util.py:138-153, metric l2, direction bi):
+ *   out[b] = mean_q min_p d(x[b,p], y[q]) + mean_p min_q d(x[b,p], y[q]),  d(a,b) = sqrt(mean_c (a_c-b_c)^2)
+ * x [B,P,3] per env, y [Q,3] the goal shared by all envs (cloth_env.py:205,217), out [B].
+ * `residuals` (ud_chamfer_residual_bytes, 256-byte aligned, caller-owned) receives per point the minimum squared
+ * distance and the number of exact ties; ud_chamfer_bwd needs it unchanged.  The adjoint splits the cotangent evenly
+ * over ties like jnp.min's VJP and returns d out / d x only (the goal is a constant of the task). */
+size_t ud_chamfer_residual_bytes(int32_t B, int32_t P, int32_t Q);
+int ud_chamfer_fwd(const float* x, const float* y, int32_t B, int32_t P, int32_t Q, float* out, void* residuals,
+                   size_t residual_bytes, void* stream);
+int ud_chamfer_bwd(const float* x, const float* y, int32_t B, int32_t P, int32_t Q, const float* gout,
+                   const void* residuals, size_t residual_bytes, float* gx, void* stream);
+/* calc_l2(x, y) (util.py:156-159): out[b] = mean_p sqrt(mean_c (x[b,p,c]-y[p,c])^2); y [P,3] (mpm_env.py:91-94). */
+int ud_l2_fwd(const float* x, const float* y, int32_t B, int32_t P, float* out, void* stream);
+int ud_l2_bwd(const float* x, const float* y, int32_t B, int32_t P, const float* gout, float* gx, void* stream);
+
 /* ---- instrumentation (bench.py): launch counting and per-kernel-class CUDA-event timing ------
  * ud_launch_count: kernels + memsets enqueued by this library since the last reset (host counter).
  * ud_timing_enable(1): subsequent calls bracket every kernel class with cudaEvents on the call's

@@ -90,6 +90,17 @@ def lib():
     L.ud_mpm_step_bwd_taped.restype = C.c_int
     L.ud_mpm_step_bwd_taped.argtypes = [P(MpmParams), P(MpmState), _fp, P(MpmState), P(MpmState), _fp, _fp,
                                         C.c_size_t, _fp]
+    i32 = C.c_int32
+    L.ud_chamfer_residual_bytes.restype = C.c_size_t
+    L.ud_chamfer_residual_bytes.argtypes = [i32, i32, i32]
+    L.ud_chamfer_fwd.restype = C.c_int
+    L.ud_chamfer_fwd.argtypes = [_fp, _fp, i32, i32, i32, _fp, _fp, C.c_size_t, _fp]
+    L.ud_chamfer_bwd.restype = C.c_int
+    L.ud_chamfer_bwd.argtypes = [_fp, _fp, i32, i32, i32, _fp, _fp, C.c_size_t, _fp, _fp]
+    L.ud_l2_fwd.restype = C.c_int
+    L.ud_l2_fwd.argtypes = [_fp, _fp, i32, i32, _fp, _fp]
+    L.ud_l2_bwd.restype = C.c_int
+    L.ud_l2_bwd.argtypes = [_fp, _fp, i32, i32, _fp, _fp, _fp]
     L.ud_mpm_sort_bins.restype = C.c_int
     L.ud_mpm_sort_bins.argtypes = [P(MpmParams), _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]
     if hasattr(L, "ud_cloth_step_fwd"):
@@ -120,6 +131,7 @@ EXPORTS = (
     "ud_mpm_sort_bins", "ud_mpm_num_keys",
     "ud_cloth_workspace_bytes", "ud_cloth_step_fwd", "ud_cloth_step_bwd", "ud_cloth_multi_ckpt_bytes",
     "ud_cloth_multi_workspace_bytes", "ud_cloth_multi_step_fwd", "ud_cloth_multi_step_bwd",
+    "ud_chamfer_residual_bytes", "ud_chamfer_fwd", "ud_chamfer_bwd", "ud_l2_fwd", "ud_l2_bwd",
     "ud_launch_count", "ud_timing_enable", "ud_timing_collect", "ud_tuning_set",
 )
 

@@ -20,6 +20,7 @@ UNITS = [
     ("mpm_particles.cu", []),
     ("mpm_grid.cu", ["--fmad=false"]),
     ("cloth.cu", []),
+    ("reward.cu", []),
 ]
 
 

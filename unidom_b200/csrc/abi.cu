@@ -182,7 +182,7 @@ int ud_tuning_set(const char* name, int value) {
 int ud_timing_num_classes(void) { return KC_COUNT; }
 const char* ud_timing_class_name(int cls) {
   static const char* names[KC_COUNT] = {"sort", "gather", "fk", "p2g", "grid", "g2p", "unsort", "g2p_bwd",
-                                        "grid_bwd", "p2g_bwd", "finish_bwd", "memset", "cloth_fwd", "cloth_bwd"};
+                                        "grid_bwd", "p2g_bwd", "finish_bwd", "memset", "cloth_fwd", "cloth_bwd", "reward"};
   return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "";
 }
 int ud_timing_collect(double* ms_by_class, int64_t* launches_by_class, int n_classes) {

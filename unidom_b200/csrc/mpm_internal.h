@@ -62,7 +62,7 @@ struct MpmWs {
 
 // Kernel classes for the optional per-kernel CUDA-event timing (ud_timing_*).
 enum KClass { KC_SORT = 0, KC_GATHER, KC_FK, KC_P2G, KC_GRID, KC_G2P, KC_UNSORT, KC_G2P_BWD, KC_GRID_BWD,
-              KC_P2G_BWD, KC_FINISH_BWD, KC_MEMSET, KC_CLOTH_FWD, KC_CLOTH_BWD, KC_COUNT };
+              KC_P2G_BWD, KC_FINISH_BWD, KC_MEMSET, KC_CLOTH_FWD, KC_CLOTH_BWD, KC_REWARD, KC_COUNT };
 // RAII scope: counts launches and (when timing is enabled) brackets them with events on `st`.
 struct KScope {
   int cls;

@@ -2,29 +2,91 @@
 
 Mirrors DaXBench/daxbench/core/envs/basic/cloth_env.py (ClothEnv: get_obs :97-132, get_pnp_actions :136-173,
 reset :178-188, step_diff :204-231) and core/utils/util.py (calc_chamfer :138-153, calc_l2 :156-159).
-Everything here is glue around `ClothSimulator.step_jax` (the B200 kernels): torch ops on the simulator's
-device, differentiable through torch autograd so that APG's rollout gradient reaches the policy.
+The rewards (calc_chamfer / calc_l2 and their adjoints) are kernels of libunidom_b200.so (csrc/reward.cu); the rest
+is glue around `ClothSimulator.step_jax` / `SimpleMPMSimulator.step_jax`: torch ops on the simulator's device,
+differentiable through torch autograd so that APG's rollout gradient reaches the policy.
 """
+import ctypes as C
 import math
 
 import numpy as np
 import torch
 
+from . import _lib
 from .cloth_simulator import ClothSimulator, ClothState
+from .mpm_simulator import _aligned, _ptr
+
+
+def _dev_f32(t, like=None):
+    t = torch.as_tensor(t)
+    if like is not None and t.device != like.device:
+        t = t.to(like.device)
+    if not t.is_cuda:
+        raise RuntimeError("unidom_b200 reward kernels need CUDA tensors (sm_100a); there is no CPU path")
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+class _Chamfer(torch.autograd.Function):
+    """ud_chamfer_fwd / ud_chamfer_bwd (csrc/reward.cu): no (B,P,Q,3) tensor, residuals = 8 B per point."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        L = _lib.lib()
+        xc, yc = _dev_f32(x), _dev_f32(y, x)
+        B, P, Q = xc.shape[0], xc.shape[1], yc.shape[0]
+        nbytes = L.ud_chamfer_residual_bytes(B, P, Q)
+        res = torch.empty(nbytes + 256, dtype=torch.uint8, device=xc.device)
+        out = torch.empty(B, dtype=torch.float32, device=xc.device)
+        _lib.check(L.ud_chamfer_fwd(_ptr(xc), _ptr(yc), B, P, Q, _ptr(out), _aligned(res), nbytes, _stream(xc)),
+                   "ud_chamfer_fwd")
+        ctx.save_for_backward(xc, yc, res)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, yc, res = ctx.saved_tensors
+        L = _lib.lib()
+        B, P, Q = xc.shape[0], xc.shape[1], yc.shape[0]
+        gx = torch.empty_like(xc)
+        _lib.check(L.ud_chamfer_bwd(_ptr(xc), _ptr(yc), B, P, Q, _ptr(_dev_f32(g)), _aligned(res), res.numel() - 256,
+                                    _ptr(gx), _stream(xc)), "ud_chamfer_bwd")
+        return gx, None
+
+
+class _L2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        L = _lib.lib()
+        xc = _dev_f32(x)
+        yc = _dev_f32(y, x).expand(xc.shape[1], 3).contiguous()
+        out = torch.empty(xc.shape[0], dtype=torch.float32, device=xc.device)
+        _lib.check(L.ud_l2_fwd(_ptr(xc), _ptr(yc), xc.shape[0], xc.shape[1], _ptr(out), _stream(xc)), "ud_l2_fwd")
+        ctx.save_for_backward(xc, yc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, yc = ctx.saved_tensors
+        gx = torch.empty_like(xc)
+        _lib.check(_lib.lib().ud_l2_bwd(_ptr(xc), _ptr(yc), xc.shape[0], xc.shape[1], _ptr(_dev_f32(g)), _ptr(gx),
+                                        _stream(xc)), "ud_l2_bwd")
+        return gx, None
 
 
 def calc_chamfer(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """util.py:138-153.  x (B,P,3), y (Q,3) -> (B,).  Note the reference's distance is sqrt(mean(d^2)) over the
-    3 coordinates, not the Euclidean norm."""
-    d = torch.sqrt(((x[:, :, None, :] - y[None, None, :, :]) ** 2).mean(-1))     # (B,P,Q)
-    x2y = d.min(-1).values.mean(1)
-    y2x = d.min(-2).values.mean(1)
-    return y2x + x2y
+    """util.py:138-153.  x (B,P,3), y (Q,3) -> (B,).  The reference's point distance is sqrt(mean(d^2)) over the
+    3 coordinates, not the Euclidean norm; ties of the minima share the cotangent like jnp.min's VJP.
+    Differentiable in x only (the goal is a constant of the task)."""
+    return _Chamfer.apply(x, y)
 
 
 def calc_l2(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """util.py:156-159."""
-    return torch.sqrt(((x - y[None]) ** 2).mean(-1)).mean(-1)
+    """util.py:156-159.  x (B,P,3), y (P,3) or (1,3) -> (B,)."""
+    return _L2.apply(x, y)
 
 
 def get_pnp_actions(actions: torch.Tensor, state: ClothState) -> torch.Tensor:

@@ -138,10 +138,10 @@ class SimpleMPMSimulator:
     """B200 drop-in for SimpleMPMSimulator (mpm_simulator.py:27-63)."""
 
     def __init__(self, conf, batch_size, use_position_control=False, device="cuda", sdf_kind=None,
-                 p2g_mode=_lib.UD_P2G_ATOMIC, adjoint="auto", tape_budget_bytes=None):
-        """adjoint: "tape" keeps every substep's residuals of a differentiated step in HBM until its backward (what
-        jax.grad of the reference's lax.scan does); "recompute" keeps only the step input and re-runs the S substeps
-        in the backward (1/S of the memory, +40 % time); "auto" tapes while this process's allocated device memory plus
+                 p2g_mode=_lib.UD_P2G_ATOMIC, adjoint="recompute", tape_budget_bytes=None):
+        """adjoint: "recompute" (default) keeps only the step input and re-runs the S substeps in the backward;
+        "tape" keeps every substep's residuals of a differentiated step in HBM until its backward (what jax.grad of
+        the reference's lax.scan does: S times the memory, 0.71x the time); "auto" tapes while this process's allocated device memory plus
         the new tape stays within `tape_budget_bytes` (default: 70 % of the device's memory) and recomputes beyond."""
         self._L = _lib.lib()  # raises when the extension is missing
         if not torch.cuda.is_available():
