@@ -161,7 +161,30 @@ def cloth_env_step():
     return res
 
 
+def reward_kernels():
+    """calc_chamfer fwd+bwd: fused kernels vs the reference's formulation (materialised (B,P,Q) distances) in torch."""
+    from unidom_b200 import envs
+    res = {"config": "calc_chamfer fwd+bwd"}
+    for tag, B, P, torch_too in (("cloth_128x512x512", 128, 512, True), ("plasticine_32x50625x50625", 32, 50625, False)):
+        g = torch.Generator().manual_seed(0)
+        x = torch.rand((B, P, 3), generator=g).cuda()
+        y = torch.rand((P, 3), generator=g).cuda()
+
+        def fb(fn):
+            xr = x.detach().requires_grad_(True)
+            torch.autograd.grad(fn(xr, y).sum(), [xr])
+
+        def ref(xr, yy):
+            d = torch.sqrt(((xr[:, :, None, :] - yy[None, None, :, :]) ** 2).mean(-1))
+            return d.amin(-1).mean(1) + d.amin(-2).mean(1)
+        res[tag + "_ms"] = timed(lambda: fb(envs.calc_chamfer), n=5)
+        res[tag + "_Gpairs_per_s"] = 3 * B * P * P / res[tag + "_ms"] / 1e6      # 2 scans + 1 adjoint pass
+        if torch_too:
+            res[tag + "_torch_ms"] = timed(lambda: fb(ref), n=5)
+    return res
+
+
 if __name__ == "__main__":
-    only = sys.argv[1:] or ["pour_water", "whip_rope", "cloth_para", "cloth_env_step"]
-    for fn in [f for f in (pour_water, whip_rope, cloth_para, cloth_env_step) if f.__name__ in only]:
+    only = sys.argv[1:] or ["pour_water", "whip_rope", "cloth_para", "cloth_env_step", "reward_kernels"]
+    for fn in [f for f in (pour_water, whip_rope, cloth_para, cloth_env_step, reward_kernels) if f.__name__ in only]:
         print(json.dumps(fn()), flush=True)
