@@ -150,7 +150,8 @@ int32_t ud_mpm_num_keys(const ud_mpm_params* p);
  *   nbr [P,8] int32 : node index of the k-th link neighbour (links order of :48), or -1 when the
  *                     link carries no force (neighbour outside the mask, or zero rest length)
  *   L0  [P,8] float : rest length cell_size*|link| clipped to >= 1e-12 (:61-63)
- * n_nodes <= 1024 (one thread per node, one CTA per environment).                                  */
+ * One thread per node.  n_nodes <= 1024: one CTA per environment; up to 8192 (fold_tshirt: 3 573):
+ * one thread-block cluster (<= 8 CTAs, distributed shared memory) per environment.                 */
 typedef struct ud_cloth_params {
   int32_t num_envs;   /* B                                       */
   int32_t n_nodes;    /* P = cloth_mask.sum()                    */
@@ -228,6 +229,8 @@ uint64_t ud_launch_count(int reset);
  *   "sort"      1: per-frame binning by grid block (default) / 0: particles stay in input order (ud_mpm_sort_bins unaffected)
  *   "stage"     1: P2G staged in shared memory, one vector RED per (cell segment, node) (default) /
  *               0: 27 vector REDs per particle straight to the grid in HBM
+ *   "cloth_cta_nodes"  cloth nodes per CTA (default and maximum 1024, multiple of 32); an env with more nodes runs
+ *               on a thread-block cluster of ceil(n_nodes / value) <= 8 CTAs (tests force small cloths onto it)
  * Returns the previous value, or -1 for an unknown name. */
 int ud_tuning_set(const char* name, int value);
 void ud_timing_enable(int on);

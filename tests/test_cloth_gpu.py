@@ -192,3 +192,112 @@ def test_fused_scan_is_bit_identical_to_step_by_step(built_lib):
     with torch.no_grad():                      # forward-only path keeps no checkpoints
         s3 = sim.scan_step_jax(st, actions)
     assert torch.equal(s3.x, s1.x)
+
+
+def _tshirt_mask(N):
+    """A T-shirt-like mask on the central (N/2)^2 window (fold_cloth_tshirt_env.py:52-71 reads it from a jpg)."""
+    h = N // 2
+    m = np.zeros((h, h), np.int32)
+    m[h // 8: h // 8 + h // 4, :] = 1                    # sleeves
+    m[h // 8:, h // 4: h - h // 4] = 1                   # body
+    m[h // 8: h // 8 + h // 16, h // 2 - h // 10: h // 2 + h // 10] = 0   # collar notch
+    full = np.zeros((N, N), np.int32)
+    full[N // 2 - h // 2: N // 2 - h // 2 + h, N // 2 - h // 2: N // 2 - h // 2 + h] = m
+    return full
+
+
+def _big_scene(B, N, seed, substeps):
+    from unidom_b200.cloth_simulator import ClothSimulator
+    conf = oc.ClothConf()
+    conf.N, conf.stiffness, conf.dt, conf.mu = N, 5000, 0.5e-3, 0.9         # fold_cloth_tshirt_env.py:21-31
+    mask = _tshirt_mask(N)
+    sim = ClothSimulator(conf, B, None, mask)
+    sim.SUBSTEPS = substeps
+    st = sim.reset_jax()
+    g = torch.Generator().manual_seed(seed)
+    dev = st.x.device
+    x = st.x.cpu() + 0.001 * torch.randn(st.x.shape, generator=g)
+    x[..., 1] = (x[..., 1].abs() * 3 + 0.01 * torch.rand(x[..., 1].shape, generator=g)) * (torch.rand(x[..., 1].shape, generator=g) > 0.5)
+    v = 0.05 * torch.randn(st.v.shape, generator=g)
+    P = x.shape[1]
+    p0 = torch.cat([x[:, P // 5], torch.full((B, 1), 0.02)], dim=1)           # gripper 0 on a node of the first CTA
+    p1 = torch.cat([x[:, P - 7] + 0.002, torch.full((B, 1), 0.015)], dim=1)   # gripper 1 next to a node of the last CTA
+    st = st._replace(x=x.to(dev), v=v.to(dev), primitive0=p0.to(dev), primitive1=p1.to(dev),
+                     stiffness=(4000.0 + 2000 * torch.rand(B, generator=g)).to(dev), mu=(0.3 + 0.6 * torch.rand(B, generator=g)).to(dev))
+    act = torch.tensor([[0.3, 0.5, -0.2, 0.0, -0.1, 0.2, 0.4, 0.3], [0.6, -0.4, 0.1, 1.0, 0.0, 0.3, 0.0, 0.0]])[:B].to(dev)
+    return conf, mask, sim, st, act
+
+
+def _cloth_grads(step, state, action, cot, names, todev):
+    req = {k: getattr(state, k).detach().clone().requires_grad_(True) for k in names}
+    a = action.detach().clone().requires_grad_(True)
+    out = step(state._replace(**req), a)
+    L = sum((getattr(out, k) * todev(cot[k]).to(getattr(out, k).dtype)).sum() for k in cot)
+    gr = torch.autograd.grad(L, [req[k] for k in names] + [a], allow_unused=True)
+    res = {k: (g_ if g_ is not None else torch.zeros_like(req[k])) for k, g_ in zip(names, gr[:-1])}
+    res["action"] = gr[-1]
+    return out, res
+
+
+@pytest.mark.parametrize("N", [160, 180])
+def test_tshirt_sized_cloth_on_a_cluster_matches_oracle(built_lib, N):
+    """fold_tshirt scale (fold_cloth_tshirt_env.py: N = 180, 3 573 nodes): one thread-block
+    cluster per env -- N=160 gives 3 5xx nodes on 7 CTAs x 512 threads, N=180 4 512 nodes on 5 CTAs x 1024 threads.
+    Teacher-forced windows (5 substeps forward, 3 substeps adjoint) against the oracle, next to its fp32-vs-fp64 floor."""
+    B = 2
+    conf, mask, sim, st, act = _big_scene(B, N, 3, 5)
+    P = st.x.shape[1]
+    assert P > 3000 and P == int(mask.sum())
+    out, _ = sim.step_jax(st, act)
+    osim = oc.ClothSim(conf, mask)
+    with torch.no_grad():
+        ref = oc.step_batch(osim, _to_oracle(st), act.cpu(), 5)
+        ref64 = oc.step_batch(oc.ClothSim(conf, mask, torch.float64), _to_oracle(st, torch.float64), act.cpu().double(), 5)
+    for k in ("x", "v", "primitive0", "primitive1"):
+        e = util.rel_err(getattr(out, k), getattr(ref, k))
+        fl = util.rel_err(getattr(ref, k), getattr(ref64, k))
+        print(f"tshirt cloth ({P} nodes) fwd {k}: rel {e:.3e} | oracle32-vs-64 {fl:.3e}")
+        assert e < max(2e-5, 3 * fl), (k, e, fl)
+    sim.SUBSTEPS = 3
+    g = torch.Generator().manual_seed(5)
+    cot = {"x": torch.randn(st.x.shape, generator=g), "v": torch.randn(st.v.shape, generator=g),
+           "primitive0": torch.randn((B, 4), generator=g), "primitive1": torch.randn((B, 4), generator=g)}
+    names = ["x", "v", "primitive0", "primitive1", "mu", "stiffness"]
+    _, got = _cloth_grads(lambda s, a: sim.step_jax(s, a)[0], st, act, cot, names, lambda t: t.to(st.x.device))
+    _, want = _cloth_grads(lambda s, a: oc.step_batch(osim, s, a, 3), _to_oracle(st), act.cpu(), cot, names, lambda t: t)
+    for k in want:
+        if float(want[k].abs().max()) <= 1e-20:
+            continue
+        e, cs = util.rel_err(got[k], want[k]), util.cosine(got[k], want[k])
+        print(f"tshirt cloth adjoint {k:12s} rel {e:.3e} cos {cs:.8f}")
+        assert cs >= 0.99999 and e < 1e-3, (k, cs, e)
+
+
+def test_cluster_path_equals_single_cta_path(built_lib):
+    """The 512-node cloth forced onto a 4-CTA cluster (ud_tuning_set cloth_cta_nodes=128): the forward has no
+    reductions -> bit-identical; the adjoint differs only by the order of the per-env norm sums."""
+    from unidom_b200 import _lib
+    B = 3
+    conf, mask, sim, st, act = _scene(B, 6, True, 50)
+    g = torch.Generator().manual_seed(12)
+    cot = {"x": torch.randn(st.x.shape, generator=g), "v": torch.randn(st.v.shape, generator=g),
+           "primitive0": torch.randn((B, 4), generator=g), "primitive1": torch.randn((B, 4), generator=g)}
+    names = ["x", "v", "primitive0", "primitive1", "mu", "stiffness"]
+    dev = st.x.device
+    L = _lib.lib()
+    res = {}
+    try:
+        for nodes in (1024, 128):
+            assert L.ud_tuning_set(b"cloth_cta_nodes", nodes) >= 0
+            res[nodes] = _cloth_grads(lambda s, a: sim.step_jax(s, a)[0], st, act, cot, names, lambda t: t.to(dev))
+    finally:
+        L.ud_tuning_set(b"cloth_cta_nodes", 1024)
+    (o1, g1), (o2, g2) = res[1024], res[128]
+    for k in ("x", "v", "primitive0", "primitive1", "action0", "action1"):
+        assert torch.equal(getattr(o1, k), getattr(o2, k)), k
+    for k in g1:
+        if float(g1[k].abs().max()) <= 1e-20:
+            continue
+        e, cs = util.rel_err(g2[k], g1[k]), util.cosine(g2[k], g1[k])
+        print(f"cluster vs single CTA adjoint {k:12s} rel {e:.3e} cos {cs:.8f}")
+        assert cs > 0.9999 and e < 1e-2, (k, cs, e)       # 50 chaotic substeps amplify the last-bit differences of the norms

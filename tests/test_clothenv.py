@@ -100,3 +100,32 @@ def test_env_rollout_and_policy_gradient_vs_reference(built_lib, name):
         else:
             assert cs >= 0.99, (i, cs, e)                  # free-running 3-step episode (6 000 chaotic substeps)
     assert abs(float(loss.detach()) - float(d["loss"])) < 0.02 * abs(float(d["loss"]))
+
+
+@pytest.mark.gpu
+def test_tshirt_env_step_on_clusters(built_lib):
+    """fold_tshirt (fold_cloth_tshirt_env.py): N = 180, ~3 500 nodes per env -> thread-block clusters; obs keeps every
+    10th node (:100).  One differentiable env step = 40 sub-actions x 50 substeps; fused scan == step-by-step."""
+    from unidom_b200 import envs
+    conf = confs.FoldTshirtConf()
+    img = np.full((90, 90, 3), 255, np.uint8)
+    img[8:26, :] = 0          # sleeves
+    img[8:85, 22:58] = 0      # body
+    mask = confs.tshirt_mask_from_image(conf, img)
+    P = int(mask.sum())
+    assert 3000 < P < 4096
+    B = 2
+    goal = np.random.RandomState(0).rand(P, 3).astype(np.float32) * 0.2 + 0.4
+    outs = []
+    for fused in (True, False):
+        env = envs.ClothEnv(conf, B, 5, mask, goal=goal, aux_reward=True, fused=fused, obs_stride=10)
+        obs, state = env.reset(shift_xz=np.zeros(2, np.float32))
+        assert obs.shape == (B, -(-P // 10) * 3 + 8) == (B, env.observation_size)
+        a = torch.tensor([[0.4523, 0.0, 0.5011, 0.55, 0.0, 0.6], [0.5017, 0.0, 0.4531, 0.4, 0.0, 0.55]], device="cuda").requires_grad_(True)
+        obs2, reward, done, info = env.step_diff(a, state)
+        (ga,) = torch.autograd.grad(reward.sum(), [a])
+        assert torch.isfinite(reward).all(), reward
+        assert torch.isfinite(ga).all() and float(ga.abs().max()) > 0, ga
+        assert float((info["state"].x - state.x).abs().max()) > 1e-3          # the gripper moved the cloth
+        outs.append((info["state"].x, reward, ga))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])

@@ -112,6 +112,31 @@ class ClothConf:
         return int(self.N / 5.0)
 
 
+class FoldTshirtConf(ClothConf):
+    """envs/fold_cloth_tshirt_env.py:20-38: N = 180, 3 573 nodes -> one thread-block cluster per env.
+    Use with ClothEnv(conf, B, 5, tshirt_mask_from_image(conf, img), obs_stride=10)."""
+    N = 180
+    stiffness = 5000
+    dt = 0.5e-3
+    mu = 0.9
+    task = "fold_tshirt"
+
+
+def tshirt_mask_from_image(conf, img):
+    """create_cloth_mask, fold_cloth_tshirt_env.py:52-71, from the already decoded + resized + rotated image: `img` is
+    the (N/2, N/2, 3) uint8 array the reference gets from cv2.imread/resize/rotate of others/t-shirt.jpg (cv2 is not
+    a dependency here); dark pixels (channel sum < 100) are cloth, centred on the N x N board."""
+    import numpy as np
+    size = conf.N // 2
+    h = size // 2
+    img = np.asarray(img)
+    assert img.shape[:2] == (size, size), img.shape
+    mask = (img.astype(np.int64).sum(-1) < 100).astype(np.float32)
+    m = np.zeros((conf.N, conf.N), dtype=np.float32)
+    m[conf.N // 2 - h:conf.N // 2 + h, conf.N // 2 - h:conf.N // 2 + h] = mask
+    return m
+
+
 def fold_cloth_mask(conf):
     """create_cloth_mask, envs/fold_cloth3_env.py:51-56: a 16 x 32 patch of the N x N board (512 nodes)."""
     import numpy as np

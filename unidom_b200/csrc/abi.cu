@@ -45,6 +45,7 @@ static int fail(int code, const char* what) {
   return code;
 }
 
+int cloth_tuning_cta_nodes(int v);   // cloth.cu
 int tuning_sort() { return g_sort; }
 int tuning_stage() { return g_stage; }
 
@@ -177,6 +178,7 @@ int ud_tuning_set(const char* name, int value) {
   if (name && !strcmp(name, "svd_warm")) { int o = g_svd_warm; g_svd_warm = value; return o; }
   if (name && !strcmp(name, "sort")) { int o = g_sort; g_sort = value; return o; }
   if (name && !strcmp(name, "stage")) { int o = g_stage; g_stage = value; return o; }
+  if (name && !strcmp(name, "cloth_cta_nodes")) return cloth_tuning_cta_nodes(value);
   return -1;
 }
 int ud_timing_num_classes(void) { return KC_COUNT; }

@@ -2,8 +2,13 @@
 // node: positions/velocities live in registers, neighbour positions are exchanged through shared
 // memory, and all `substeps` (50) substeps of a sub-action run inside ONE launch -- the cloth state
 // (512 nodes x 24 B) never round-trips HBM between substeps.
+// Cloths with more than 1024 nodes (fold_tshirt: 3 573) run on a thread-block CLUSTER per environment
+// (up to 8 CTAs x 1024 threads): every CTA keeps a full copy of the node positions that the owners
+// update through distributed shared memory, the spring cotangents stay in the owner's shared memory
+// and are read remotely, and the per-env norms are reduced across the cluster, barrier by barrier.
 // Reference: DaXBench/daxbench/core/engine/cloth_simulator.py:163-180 (robot_step), :198-226 (grippers),
 // :257-337 (step), :182-196 (norm_grad, re-normalises the cotangent 8x per substep in the adjoint).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -14,19 +19,32 @@
 
 namespace ud {
 
+namespace cg = cooperative_groups;
+
 struct ClothK {
-  int B, P, S, threads;
+  int B, P, S, threads, CL;   // threads per CTA, CTAs (cluster size) per env
   float dt, g, gdt, damp, max_v, small_num, mask_sum;
   int stiff_float;
 };
 
+static int g_cta_nodes = 1024;   // nodes per CTA before an env spills onto a cluster (A/B + test switch, <= 1024)
+int cloth_tuning_cta_nodes(int v) {
+  int o = g_cta_nodes;
+  if (v >= 32 && v <= 1024) g_cta_nodes = v / 32 * 32;
+  return o;
+}
+
 static bool cloth_fold(const ud_cloth_params* p, ClothK* k) {
-  if (!p || p->num_envs < 1 || p->n_nodes < 1 || p->n_nodes > 1024 || p->substeps < 1) return false;
+  if (!p || p->num_envs < 1 || p->n_nodes < 1 || p->n_nodes > 8 * g_cta_nodes || p->substeps < 1) return false;
   if (!(p->dt > 0) || !(p->mask_sum > 0)) return false;
   k->B = p->num_envs;
   k->P = p->n_nodes;
   k->S = p->substeps;
-  k->threads = (p->n_nodes + 31) / 32 * 32;
+  int per = g_cta_nodes;
+  // beyond one CTA prefer 512-thread CTAs (128 registers per thread, no spills) while 8 of them cover the cloth
+  if (p->n_nodes > per && per == 1024 && p->n_nodes <= 8 * 512) per = 512;
+  k->CL = (p->n_nodes + per - 1) / per;
+  k->threads = ((p->n_nodes + k->CL - 1) / k->CL + 31) / 32 * 32;
   k->dt = (float)p->dt;
   k->g = (float)p->gravity;
   k->gdt = (float)(p->gravity * p->dt);                 // jnp.array([0, gravity*dt, 0]) (:259)
@@ -66,8 +84,38 @@ __device__ __forceinline__ float nan0(float a) {
   return a;
 }
 
-// block-wide sums of two values (all threads must call); result broadcast to every thread
-__device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
+// One env = one CTA (CLUSTER = false) or one thread-block cluster (CLUSTER = true).
+template <bool CLUSTER>
+struct Team {
+  __device__ __forceinline__ static int rank() { return CLUSTER ? (int)cg::this_cluster().block_rank() : 0; }
+  __device__ __forceinline__ static int size() { return CLUSTER ? (int)cg::this_cluster().num_blocks() : 1; }
+  __device__ __forceinline__ static int env() { return CLUSTER ? (int)(blockIdx.x / cg::this_cluster().num_blocks()) : (int)blockIdx.x; }
+  __device__ __forceinline__ static void sync() {
+    if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
+  }
+  // publish this node's position into the position table of every CTA of the env
+  __device__ __forceinline__ static void publish(float* xs, int n, const float x[3]) {
+    if (CLUSTER) {
+      cg::cluster_group cl = cg::this_cluster();
+      for (unsigned r = 0; r < cl.num_blocks(); ++r) {
+        float* d = cl.map_shared_rank(xs, r);
+        d[3 * n] = x[0];
+        d[3 * n + 1] = x[1];
+        d[3 * n + 2] = x[2];
+      }
+    } else {
+      xs[3 * n] = x[0];
+      xs[3 * n + 1] = x[1];
+      xs[3 * n + 2] = x[2];
+    }
+  }
+};
+
+// env-wide sums of two values (all threads of the env must call); result broadcast to every thread.
+// red: [64] per CTA; redc: [2][16] per CTA, double-buffered by `par` (a fast CTA may already be writing the next
+// reduction's partials while a slow one still reads this one's).  Fixed summation order: deterministic.
+template <bool CLUSTER>
+__device__ __forceinline__ void team_sum2(float& a, float& b, float* red, float* redc, int& par) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     a += __shfl_down_sync(0xffffffffu, a, off);
@@ -81,9 +129,26 @@ __device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
   }
   __syncthreads();
   float sa = 0.f, sb = 0.f;
-  for (int w = 0; w < nw; ++w) {  // fixed order: deterministic
+  for (int w = 0; w < nw; ++w) {
     sa += red[w];
     sb += red[32 + w];
+  }
+  if (CLUSTER) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int nb = (int)cl.num_blocks(), me = (int)cl.block_rank();
+    if ((int)threadIdx.x < nb) {
+      float* r = cl.map_shared_rank(redc, threadIdx.x);
+      r[par * 16 + me] = sa;
+      r[par * 16 + 8 + me] = sb;
+    }
+    cl.sync();
+    sa = 0.f;
+    sb = 0.f;
+    for (int r = 0; r < nb; ++r) {
+      sa += redc[par * 16 + r];
+      sb += redc[par * 16 + 8 + r];
+    }
+    par ^= 1;
   }
   a = sa;
   b = sb;
@@ -203,7 +268,7 @@ __device__ __forceinline__ void load_actions(const float* __restrict__ action, i
 // save layout per (env, substep): [P*3 x][P*3 v][ps0 4][ps1 4]
 __device__ __forceinline__ size_t save_stride(const ClothK& k) { return (size_t)k.P * 6 + 8; }
 
-template <int MAXT>
+template <int MAXT, bool CLUSTER>
 __global__ void __launch_bounds__(MAXT)
 k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, const float* __restrict__ L0_t,
             const float* __restrict__ action, ud_cloth_state out, float* __restrict__ save, int T,
@@ -211,9 +276,12 @@ k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
   // T sub-actions (action is [T,B,8]) run back to back with the node state in registers; `ckpt` (nullable) receives
   // the state at the START of every sub-action: x [T,B,P,3] | v [T,B,P,3] | primitive0 [T,B,4] | primitive1 [T,B,4]
   extern __shared__ float xs[];  // [P*3]
-  const int env = blockIdx.x, t = threadIdx.x;
-  const bool live = t < k.P;
-  const int n = live ? t : 0;
+  typedef Team<CLUSTER> TM;
+  const int env = TM::env(), t = threadIdx.x;
+  const int nn = TM::rank() * k.threads + t;   // node of this thread
+  const bool live = nn < k.P;
+  const bool lead = nn == 0;                   // the env's one writer of per-env values
+  const int n = live ? nn : 0;
   const size_t o = (size_t)env * k.P + n;
   float x[3], v[3], L0[8], iL0[8], a0[4], a1[4], ps0[4], ps1[4];
   int nbr[8];
@@ -247,7 +315,7 @@ k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
         cv[c] = v[c];
       }
     }
-    if (t == 0) {
+    if (lead) {
       float* c0 = ckpt + 2 * (size_t)T * BP3 + ((size_t)ta * k.B + env) * 4;
       float* c1 = c0 + (size_t)T * k.B * 4;
 #pragma unroll
@@ -267,7 +335,7 @@ k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
           sv[(size_t)k.P * 3 + 3 * n + c] = v[c];
         }
       }
-      if (t == 0) {
+      if (lead) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           sv[(size_t)k.P * 6 + c] = ps0[c];
@@ -275,17 +343,13 @@ k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
         }
       }
     }
-    if (live) {
-      xs[3 * n] = x[0];
-      xs[3 * n + 1] = x[1];
-      xs[3 * n + 2] = x[2];
-    }
-    __syncthreads();
+    if (live) TM::publish(xs, n, x);
+    TM::sync();
     Sub sb;
     cloth_substep(k, xs, nbr, L0, iL0, stiff, mu, a0, a1, ps0, ps1, x, v, sb);
     advance_gripper(a0, ps0);
     advance_gripper(a1, ps1);
-    __syncthreads();
+    TM::sync();
   }
   }  // sub-actions
   if (!out.x) return;
@@ -296,7 +360,7 @@ k_cloth_fwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
       out.v[3 * o + c] = v[c];
     }
   }
-  if (t == 0) {
+  if (lead) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       out.primitive0[env * 4 + c] = ps0[c];
@@ -319,18 +383,22 @@ __device__ __forceinline__ void norm_grad4(const ClothK& k, float g[4]) {
 }
 
 // Adjoint of the 50-substep sub-action.  Expects `save` filled by k_cloth_fwd (recompute pass).
-template <int MAXT>
+template <int MAXT, bool CLUSTER>
 __global__ void __launch_bounds__(MAXT)
 k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, const float* __restrict__ L0_t,
             const float* __restrict__ action, ud_cloth_state gout, ud_cloth_state gin,
             float* __restrict__ gaction, const float* __restrict__ save) {
   extern __shared__ float sm[];
-  float* xs = sm;                    // [P*3]
-  float* grel = sm + 3 * k.P;        // [P*8*3] cotangents of the spring vectors
-  float* red = grel + 24 * k.P;      // [64]
-  const int env = blockIdx.x, t = threadIdx.x;
-  const bool live = t < k.P;
-  const int n = live ? t : 0;
+  typedef Team<CLUSTER> TM;
+  float* xs = sm;                          // [P*3] positions of ALL nodes of the env (a copy per CTA)
+  float* grel = sm + 3 * k.P;              // [threads*8*3] cotangents of the spring vectors of THIS CTA's nodes
+  float* red = grel + 24 * k.threads;      // [64]
+  float* redc = red + 64;                  // [2][16] cluster partials
+  int par = 0;
+  const int env = TM::env(), t = threadIdx.x;
+  const int nn = TM::rank() * k.threads + t;
+  const bool live = nn < k.P;
+  const int n = live ? nn : 0;
   const size_t o = (size_t)env * k.P + n;
   const int mirror[8] = {1, 0, 3, 2, 7, 6, 5, 4};  // link k of i  <->  link mirror[k] of its neighbour
   float L0[8], iL0[8], a0[4], a1[4];
@@ -378,19 +446,15 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
       ps1[c] = sv[(size_t)k.P * 6 + 4 + c];
     }
     const float xin[3] = {x[0], x[1], x[2]};
-    __syncthreads();
-    if (live) {
-      xs[3 * n] = x[0];
-      xs[3 * n + 1] = x[1];
-      xs[3 * n + 2] = x[2];
-    }
-    __syncthreads();
+    TM::sync();
+    if (live) TM::publish(xs, n, x);
+    TM::sync();
     Sub f;
     cloth_substep(k, xs, nbr, L0, iL0, stiff, mu, a0, a1, ps0, ps1, x, v, f);  // x,v now hold the outputs (unused)
     // ---- (1) trailing norm_grads on x', v', ps0', ps1' (:331-334)
     float nx = live ? gx[0] * gx[0] + gx[1] * gx[1] + gx[2] * gx[2] : 0.f;
     float nv = live ? gv[0] * gv[0] + gv[1] * gv[1] + gv[2] * gv[2] : 0.f;
-    block_sum2(nx, nv, red);
+    team_sum2<CLUSTER>(nx, nv, red, redc, par);
     nx = sqrtf(nx);
     nv = sqrtf(nv);
 #pragma unroll
@@ -422,7 +486,7 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
     // ---- (4) gripper 1: norm_grad(x2), norm_grad(v2), then the where()
     nx = live ? gx2[0] * gx2[0] + gx2[1] * gx2[1] + gx2[2] * gx2[2] : 0.f;
     nv = live ? gv2[0] * gv2[0] + gv2[1] * gv2[1] + gv2[2] * gv2[2] : 0.f;
-    block_sum2(nx, nv, red);
+    team_sum2<CLUSTER>(nx, nv, red, redc, par);
     nx = sqrtf(nx);
     nv = sqrtf(nv);
     float gx1[3], gv1[3];
@@ -441,7 +505,7 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
     // ---- (5) gripper 0
     nx = live ? gx1[0] * gx1[0] + gx1[1] * gx1[1] + gx1[2] * gx1[2] : 0.f;
     nv = live ? gv1[0] * gv1[0] + gv1[1] * gv1[1] + gv1[2] * gv1[2] : 0.f;
-    block_sum2(nx, nv, red);
+    team_sum2<CLUSTER>(nx, nv, red, redc, par);
     nx = sqrtf(nx);
     nv = sqrtf(nv);
     float gxs[3], gv0[3];
@@ -527,17 +591,25 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
         gxi[2] -= g2;
       }
       if (live) {
-        grel[(n * 8 + q) * 3] = g0;
-        grel[(n * 8 + q) * 3 + 1] = g1;
-        grel[(n * 8 + q) * 3 + 2] = g2;
+        grel[(t * 8 + q) * 3] = g0;
+        grel[(t * 8 + q) * 3 + 1] = g1;
+        grel[(t * 8 + q) * 3 + 2] = g2;
       }
     }
-    __syncthreads();
+    TM::sync();
     if (live) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         if (nbr[q] < 0) continue;
-        const float* gr = grel + (nbr[q] * 8 + mirror[q]) * 3;  // the neighbour's spring towards me
+        // the neighbour's spring towards me, in the shared memory of the CTA that owns the neighbour
+        const float* gown = grel;
+        int nl = nbr[q];
+        if (CLUSTER) {
+          const int owner = nbr[q] / k.threads;
+          nl = nbr[q] - owner * k.threads;
+          gown = cg::this_cluster().map_shared_rank(grel, owner);
+        }
+        const float* gr = gown + (nl * 8 + mirror[q]) * 3;
         gxi[0] += gr[0];
         gxi[1] += gr[1];
         gxi[2] += gr[2];
@@ -559,8 +631,9 @@ k_cloth_bwd(ClothK k, ud_cloth_state in, const int32_t* __restrict__ nbr_t, cons
   }
   // reduce the per-thread partials: (ga0p[0..3], ga1p[0..3], gstiffp, gmup)
   float pr[10] = {ga0p[0], ga0p[1], ga0p[2], ga0p[3], ga1p[0], ga1p[1], ga1p[2], ga1p[3], gstiffp, gmup};
-  for (int i = 0; i < 10; i += 2) block_sum2(pr[i], pr[i + 1], red);
-  if (t == 0) {
+  for (int i = 0; i < 10; i += 2) team_sum2<CLUSTER>(pr[i], pr[i + 1], red, redc, par);
+  if (CLUSTER) TM::sync();   // no CTA leaves while its shared memory may still be read remotely
+  if (nn == 0) {
     float ga0[4], ga1[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -591,6 +664,68 @@ static bool cloth_state_ok(const ud_cloth_state* s) {
   return s && s->x && s->v && s->primitive0 && s->primitive1 && s->action0 && s->action1 && s->stiffness && s->mu;
 }
 
+// ---- launch helpers: one CTA per env up to 1024 nodes, a cluster of k.CL CTAs per env beyond --------------------
+static size_t cloth_fwd_smem(const ClothK& k) { return sizeof(float) * 3 * (size_t)k.P; }
+static size_t cloth_bwd_smem(const ClothK& k) { return sizeof(float) * (3 * (size_t)k.P + 24 * (size_t)k.threads + 64 + 32); }
+
+template <class Kern, class... Args>
+static void launch_cluster(Kern kern, const ClothK& k, size_t smem, cudaStream_t st, Args... args) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(k.B * k.CL));
+  cfg.blockDim = dim3((unsigned)k.threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)k.CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+static void launch_cloth_fwd(const ClothK& k, cudaStream_t st, const ud_cloth_state& in, const int32_t* nbr, const float* L0,
+                             const float* action, const ud_cloth_state& out, float* save, int T, float* ckpt) {
+  const size_t smem = cloth_fwd_smem(k);
+  if (k.CL > 1 && k.threads <= 512)
+    launch_cluster(k_cloth_fwd<512, true>, k, smem, st, k, in, nbr, L0, action, out, save, T, ckpt);
+  else if (k.CL > 1)
+    launch_cluster(k_cloth_fwd<1024, true>, k, smem, st, k, in, nbr, L0, action, out, save, T, ckpt);
+  else if (k.threads <= 512)
+    k_cloth_fwd<512, false><<<k.B, k.threads, smem, st>>>(k, in, nbr, L0, action, out, save, T, ckpt);
+  else
+    k_cloth_fwd<1024, false><<<k.B, k.threads, smem, st>>>(k, in, nbr, L0, action, out, save, T, ckpt);
+}
+
+static void launch_cloth_bwd(const ClothK& k, cudaStream_t st, const ud_cloth_state& in, const int32_t* nbr, const float* L0,
+                             const float* action, const ud_cloth_state& gout, const ud_cloth_state& gin, float* gaction,
+                             const float* save) {
+  const size_t smem = cloth_bwd_smem(k);
+  if (k.CL > 1) {
+    if (k.threads <= 512)
+      launch_cluster(k_cloth_bwd<512, true>, k, smem, st, k, in, nbr, L0, action, gout, gin, gaction, save);
+    else
+      launch_cluster(k_cloth_bwd<1024, true>, k, smem, st, k, in, nbr, L0, action, gout, gin, gaction, save);
+    return;
+  }
+  static bool attr = false;
+  if (!attr) {
+    ClothK m = k;
+    m.P = m.threads = 512;
+    cudaFuncSetAttribute(k_cloth_bwd<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cloth_bwd_smem(m));
+    m.P = m.threads = 1024;
+    cudaFuncSetAttribute(k_cloth_bwd<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cloth_bwd_smem(m));
+    attr = true;
+  }
+  if (k.threads <= 512)
+    k_cloth_bwd<512, false><<<k.B, k.threads, smem, st>>>(k, in, nbr, L0, action, gout, gin, gaction, save);
+  else
+    k_cloth_bwd<1024, false><<<k.B, k.threads, smem, st>>>(k, in, nbr, L0, action, gout, gin, gaction, save);
+}
+
 }  // namespace ud
 
 using namespace ud;
@@ -613,10 +748,7 @@ int ud_cloth_step_fwd(const ud_cloth_params* p, const ud_cloth_state* in, const 
   if (!cloth_state_ok(in) || !cloth_state_ok(out) || !nbr || !L0 || !action) return UD_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   KScope ks(KC_CLOTH_FWD, st);
-  if (k.threads <= 512)
-    k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, *out, nullptr, 1, nullptr);
-  else
-    k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, *out, nullptr, 1, nullptr);
+  launch_cloth_fwd(k, st, *in, nbr, L0, action, *out, nullptr, 1, nullptr);
   return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
 }
 
@@ -631,26 +763,13 @@ int ud_cloth_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const 
   cudaStream_t st = (cudaStream_t)stream;
   ud_cloth_state none;
   memset(&none, 0, sizeof(none));
-  size_t smem = sizeof(float) * ((size_t)27 * k.P + 64);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_cloth_bwd<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (27 * 512 + 64)));
-    cudaFuncSetAttribute(k_cloth_bwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (27 * 1024 + 64)));
-    attr = true;
-  }
   {
     KScope ks(KC_CLOTH_FWD, st);  // recompute pass: checkpoint = the sub-action input
-    if (k.threads <= 512)
-      k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, none, (float*)workspace, 1, nullptr);
-    else
-      k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, action, none, (float*)workspace, 1, nullptr);
+    launch_cloth_fwd(k, st, *in, nbr, L0, action, none, (float*)workspace, 1, nullptr);
   }
   {
     KScope ks(KC_CLOTH_BWD, st);
-    if (k.threads <= 512)
-      k_cloth_bwd<512><<<k.B, k.threads, smem, st>>>(k, *in, nbr, L0, action, *gout, *gin, gaction, (const float*)workspace);
-    else
-      k_cloth_bwd<1024><<<k.B, k.threads, smem, st>>>(k, *in, nbr, L0, action, *gout, *gin, gaction, (const float*)workspace);
+    launch_cloth_bwd(k, st, *in, nbr, L0, action, *gout, *gin, gaction, (const float*)workspace);
   }
   return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
 }
@@ -684,10 +803,7 @@ int ud_cloth_multi_step_fwd(const ud_cloth_params* p, const ud_cloth_state* in, 
   if (ckpt && (ckpt_bytes < ud_cloth_multi_ckpt_bytes(p, T) || ((uintptr_t)ckpt & 255))) return UD_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   KScope ks(KC_CLOTH_FWD, st);
-  if (k.threads <= 512)
-    k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, actions, *out, nullptr, T, (float*)ckpt);
-  else
-    k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, *in, nbr, L0, actions, *out, nullptr, T, (float*)ckpt);
+  launch_cloth_fwd(k, st, *in, nbr, L0, actions, *out, nullptr, T, (float*)ckpt);
   return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
 }
 
@@ -720,13 +836,6 @@ int ud_cloth_multi_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, 
   }
   ud_cloth_state none;
   memset(&none, 0, sizeof(none));
-  size_t smem = sizeof(float) * ((size_t)27 * k.P + 64);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_cloth_bwd<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (27 * 512 + 64)));
-    cudaFuncSetAttribute(k_cloth_bwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (27 * 1024 + 64)));
-    attr = true;
-  }
   const float* ck = (const float*)ckpt;
   for (int t = T - 1; t >= 0; --t) {
     ud_cloth_state s_in = *in;  // state at the start of sub-action t (stiffness / mu are constants of the call)
@@ -739,17 +848,11 @@ int ud_cloth_multi_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, 
     const ud_cloth_state& gi = (t == 0) ? *gin : g[t & 1];
     {
       KScope ks(KC_CLOTH_FWD, st);
-      if (k.threads <= 512)
-        k_cloth_fwd<512><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, s_in, nbr, L0, a_t, none, save, 1, nullptr);
-      else
-        k_cloth_fwd<1024><<<k.B, k.threads, sizeof(float) * 3 * k.P, st>>>(k, s_in, nbr, L0, a_t, none, save, 1, nullptr);
+      launch_cloth_fwd(k, st, s_in, nbr, L0, a_t, none, save, 1, nullptr);
     }
     {
       KScope ks(KC_CLOTH_BWD, st);
-      if (k.threads <= 512)
-        k_cloth_bwd<512><<<k.B, k.threads, smem, st>>>(k, s_in, nbr, L0, a_t, go, gi, gactions + (size_t)t * k.B * 8, save);
-      else
-        k_cloth_bwd<1024><<<k.B, k.threads, smem, st>>>(k, s_in, nbr, L0, a_t, go, gi, gactions + (size_t)t * k.B * 8, save);
+      launch_cloth_bwd(k, st, s_in, nbr, L0, a_t, go, gi, gactions + (size_t)t * k.B * 8, save);
     }
   }
   return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;

@@ -112,21 +112,22 @@ class ClothEnv:
     """B200 drop-in for the reference's ClothEnv (fold_cloth1/3, unfold_cloth1/3, fold_cloth1_para)."""
 
     def __init__(self, conf, batch_size, max_steps, cloth_mask, goal=None, aux_reward=False, device="cuda",
-                 para=False, fused=True):
+                 para=False, fused=True, obs_stride=1):
         self.conf, self.batch_size, self.max_steps, self.aux_reward = conf, batch_size, max_steps, aux_reward
         self.fused = fused                                   # scan over the 40 sub-actions inside the library
         self.simulator = ClothSimulator(conf, batch_size, None, cloth_mask, device=device)
         self.device = self.simulator.device
         self.action_size = 6
         self.para = para                                     # cloth_env_para.py: obs carries the normalised stiffness
+        self.obs_stride = obs_stride                         # fold_cloth_tshirt_env.py:100: every 10th node
         n = self.simulator.n_nodes
-        self.observation_size = n * 3 + 8 + (1 if para else 0)
+        self.observation_size = -(-n // obs_stride) * 3 + 8 + (1 if para else 0)
         goal = np.zeros((1, 3), np.float32) if goal is None else np.asarray(goal, np.float32)
         self.goal = torch.from_numpy(goal).to(self.device)
 
     def get_obs(self, state: ClothState) -> torch.Tensor:
         """cloth_env.py:119-128 (PARTICLE): [x.flatten(), primitive0, primitive1] (+ stiffness/2000, cloth_env_para.py:130)."""
-        parts = [state.x.flatten(1), state.primitive0, state.primitive1]
+        parts = [state.x[:, ::self.obs_stride].flatten(1), state.primitive0, state.primitive1]
         if self.para:
             parts.append((state.stiffness.to(state.x.dtype) / 2000.0)[:, None])
         return torch.cat(parts, dim=1)
