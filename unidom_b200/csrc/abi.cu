@@ -38,7 +38,7 @@ KScope::~KScope() {
   cudaEventRecord(g_recs[slot].b, st);
 }
 
-static int g_svd_warm = 1, g_sort = 1, g_stage = 1;
+static int g_svd_warm = 1, g_sort = 1, g_stage = 1, g_mark = 2;
 static thread_local const char* g_last_error = "";
 static int fail(int code, const char* what) {
   g_last_error = what;
@@ -87,6 +87,7 @@ bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k) {
   k->sdf_kind = p->sdf_kind;
   k->pos_control = p->use_position_control ? 1 : 0;
   k->p2g_mode = p->p2g_mode;
+  k->mark = g_mark;
   return true;
 }
 
@@ -121,6 +122,9 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
   w.fk_vw = (float*)take(4 * (size_t)k.B * P * 6);
   w.fk_act = (float*)take(4 * (size_t)k.B * P * 6);
   w.jrows = (float*)take(4 * (size_t)k.B * S * 9);
+  w.blk_flag = (int32_t*)take(4 * (size_t)k.B * k.nbx * k.nby * k.nbz);
+  w.blk_list = (int32_t*)take(8 * (size_t)k.B * k.nbx * k.nby * k.nbz);
+  w.blk_count = (int32_t*)take(4 * S);
   if (!bwd) {
     w.ps = (float*)take(4 * (size_t)PS_NCOMP * N);
     w.vt_roll = (float*)take(4 * (size_t)9 * N);
@@ -178,6 +182,7 @@ int ud_tuning_set(const char* name, int value) {
   if (name && !strcmp(name, "svd_warm")) { int o = g_svd_warm; g_svd_warm = value; return o; }
   if (name && !strcmp(name, "sort")) { int o = g_sort; g_sort = value; return o; }
   if (name && !strcmp(name, "stage")) { int o = g_stage; g_stage = value; return o; }
+  if (name && !strcmp(name, "mark")) { int o = g_mark; g_mark = value; return o; }
   if (name && !strcmp(name, "cloth_cta_nodes")) return cloth_tuning_cta_nodes(value);
   return -1;
 }
@@ -255,9 +260,13 @@ int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   launch_gather_state(k, in, material, h, ws, ws.ps, st);
   launch_fk_fwd(k, in, action, out, ws, st);
   zero_async(ws.jrows, 4 * (size_t)k.B * k.S * 9, st);
+  // the grid is zeroed in full once per call; between substeps only the 4x4x4 blocks P2G marked are re-zeroed
+  zero_async(ws.blk_flag, 4 * (size_t)k.B * k.nbx * k.nby * k.nbz, st);
+  zero_async(ws.blk_count, 4 * (size_t)k.S, st);
+  zero_async(ws.grid_raw, 16 * (size_t)k.B * k.G, st);
+  if (ws.grid_fix) zero_async(ws.grid_fix, 32 * (size_t)k.B * k.G, st);
   for (int f = 0; f < k.S; ++f) {
-    if (ws.grid_fix) zero_async(ws.grid_fix, 32 * (size_t)k.B * k.G, st);
-    else zero_async(ws.grid_raw, 16 * (size_t)k.B * k.G, st);
+    if (f) launch_grid_clear(k, ws.grid_raw, f - 1, ws, st);
     launch_p2g(k, ws.ps, ws.ps, ws.grid_raw, in->mu, in->lamda, (g_svd_warm && (f % SVD_RESTART)) ? ws.vt_roll : nullptr, ws.vt_roll,
                nullptr, ws, st);
     launch_grid_fwd(k, ws.grid_raw, ws.grid_raw, ws.grid_fix, f, in, ws, st);
@@ -279,12 +288,14 @@ static void mpm_record_pass(const MpmConst& k, const ud_mpm_state* in, const int
   launch_sort(k, in->x, ws, nullptr, st);
   launch_gather_state(k, in, material, h, ws, ws.ps, st);
   launch_fk_fwd(k, in, action, out, ws, st);
-  if (!ws.grid_fix) zero_async(ws.grid_raw, 16 * BG * k.S, st);
+  zero_async(ws.grid_raw, 16 * BG * k.S, st);
+  if (ws.grid_fix) zero_async(ws.grid_fix, 32 * BG, st);   // consumed (re-zeroed) cell by cell by k_grid_fwd
+  zero_async(ws.blk_flag, 4 * (size_t)k.B * k.nbx * k.nby * k.nbz, st);
+  zero_async(ws.blk_count, 4 * (size_t)k.S, st);
   zero_async(ws.act_count, 4 * (size_t)k.S, st);
   for (int f = 0; f < k.S; ++f) {
     const float* s_in = ws.ps + slot * f;
     float* s_out = ws.ps + slot * (f + 1);
-    if (ws.grid_fix) zero_async(ws.grid_fix, 32 * BG, st);
     float* sv_f = ws.svd_s + (size_t)SV_NCOMP * k.N * f;
     launch_p2g(k, s_in, s_out, ws.grid_raw + BG * f, in->mu, in->lamda,
                (g_svd_warm && (f % SVD_RESTART)) ? sv_f - (size_t)SV_NCOMP * k.N + (size_t)SV_VT * k.N : nullptr, nullptr,

@@ -147,64 +147,85 @@ UD_DEV void load_prim_f(const MpmConst& k, const ud_mpm_state& in, const float* 
   pr.softness = in.prim[q].softness[env];
 }
 
+// Compacts the block marks P2G left (ws.blk_flag) into a list and consumes them: one warp per 32 blocks, one
+// warp-aggregated append.  ~3-6 % of the blocks are marked in the shipped scenes.
 __global__ void __launch_bounds__(128)
-k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, const long long* __restrict__ grid_fix, int f,
-           ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
-           const float* __restrict__ fk_vw, int32_t* __restrict__ act_list, int32_t* __restrict__ act_count) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = idx < (size_t)k.B * k.G;
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (in_range) {
-    if (grid_fix) {  // deterministic P2G: fixed-point accumulators -> float {p, m}
-      const longlong2 a = reinterpret_cast<const longlong2*>(grid_fix)[2 * idx];
-      const longlong2 b = reinterpret_cast<const longlong2*>(grid_fix)[2 * idx + 1];
-      g = make_float4((float)((double)a.x * FIX_INV), (float)((double)a.y * FIX_INV), (float)((double)b.x * FIX_INV),
-                      (float)((double)b.y * FIX_INV));
-      if (grid_out != grid_in) grid_in[idx] = g;  // the adjoint reads the raw grid
-    } else {
-      g = grid_in[idx];
-    }
-  }
-  const bool has_mass = in_range && g.w > 0.f;
-  if (act_list) {  // recompute pass of the adjoint: list the cells with mass for k_grid_bwd (warp-aggregated append)
-    const unsigned m = __ballot_sync(0xffffffffu, has_mass);
-    if (m) {
-      const int lane = threadIdx.x & 31;
-      int base = 0;
-      if (lane == __ffs(m) - 1) base = atomicAdd(act_count, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-      if (has_mass) act_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)idx;
-    }
-  }
-  if (!in_range) return;
-  if (!has_mass) {  // empty cell: interior ones are never gathered with a non-zero weight, the boundary
-    if (grid_out != grid_in) grid_out[idx] = g;  // shell is updated by k_grid_shell
-    return;
-  }
-  int env = (int)(idx / k.G);
-  int c = (int)(idx - (size_t)env * k.G);
-  int ck = c % k.rz, cj = (c / k.rz) % k.ry, ci = c / (k.rz * k.ry);
-  float p[3] = {g.x, g.y, g.z}, v[3];
-  auto prim_of = [&](int q, PrimIn<float>& pr) {
-    load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
-    return true;
-  };
-  cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
-  grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
+k_blk_compact(int total, int32_t* __restrict__ blk_flag, int32_t* __restrict__ list, int32_t* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool marked = i < total && blk_flag[i] != 0;
+  if (marked) blk_flag[i] = 0;
+  const unsigned m = __ballot_sync(0xffffffffu, marked);
+  if (!m) return;
+  int base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (marked) list[base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
-// Empty cells of the outermost layer: the reference updates EVERY cell (empty ones get dt*gravity, colliders,
-// friction, walls), and a particle that left the grid gathers exactly these cells through clamped indices
-// (SURVEY 8c).  One thread per face cell (edges are visited twice and write the same value).
+// Grid update over the listed 4x4x4 blocks: persistent warps, one block (64 cells, 2 per lane) per iteration.
 __global__ void __launch_bounds__(128)
-k_grid_shell(MpmConst k, const float4* grid_raw, float4* grid_out, int f, ud_mpm_state in,
-             const float* __restrict__ fk_pos, const float* __restrict__ fk_rot, const float* __restrict__ fk_vw,
-             int32_t* __restrict__ act_list, int32_t* __restrict__ act_count) {
-  const int env = blockIdx.y;
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t0 = t;
+k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, long long* __restrict__ grid_fix, int f,
+           ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
+           const float* __restrict__ fk_vw, const int32_t* __restrict__ blk_list, const int32_t* __restrict__ blk_count,
+           int32_t* __restrict__ act_list, int32_t* __restrict__ act_count) {
+  const int nblk = k.nbx * k.nby * k.nbz;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int count = *blk_count;
+  for (int li = warp0; li < count; li += nwarps) {
+  const int w = blk_list[li];
+  const int env = w / nblk, bid = w - env * nblk;
+  const int bz = bid % k.nbz, by = (bid / k.nbz) % k.nby, bx = bid / (k.nbz * k.nby);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int lc = lane + 32 * it;
+    const int ci = bx * 4 + (lc >> 4), cj = by * 4 + ((lc >> 2) & 3), ck = bz * 4 + (lc & 3);
+    const bool in_range = ci < k.rx && cj < k.ry && ck < k.rz;
+    const size_t idx = (size_t)env * k.G + (size_t)(ci * k.ry + cj) * k.rz + ck;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in_range) {
+      if (grid_fix) {  // deterministic P2G: fixed-point accumulators -> float {p, m}; consumed (re-zeroed) here
+        longlong2* fx = reinterpret_cast<longlong2*>(grid_fix) + 2 * idx;
+        const longlong2 a = fx[0], b = fx[1];
+        fx[0] = make_longlong2(0, 0);
+        fx[1] = make_longlong2(0, 0);
+        g = make_float4((float)((double)a.x * FIX_INV), (float)((double)a.y * FIX_INV), (float)((double)b.x * FIX_INV),
+                        (float)((double)b.y * FIX_INV));
+        if (grid_out != grid_in) grid_in[idx] = g;  // the adjoint reads the raw grid
+      } else {
+        g = grid_in[idx];
+      }
+    }
+    const bool has_mass = in_range && g.w > 0.f;
+    if (act_list) {  // recompute pass of the adjoint: list the cells with mass for k_grid_bwd (warp-aggregated append)
+      const unsigned m = __ballot_sync(0xffffffffu, has_mass);
+      if (m) {
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(act_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (has_mass) act_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)idx;
+      }
+    }
+    if (!in_range) continue;
+    if (!has_mass) {  // empty cell: interior ones are never gathered with a non-zero weight, the boundary
+      if (grid_out != grid_in || grid_fix) grid_out[idx] = g;  // shell is updated by k_grid_shell
+      continue;
+    }
+    float p[3] = {g.x, g.y, g.z}, v[3];
+    auto prim_of = [&](int q, PrimIn<float>& pr) {
+      load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
+      return true;
+    };
+    cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
+    grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
+  }
+  }  // listed blocks of this warp
+}
+
+// Face cell number t of the grid's outermost layer (z faces, then y faces, then x faces; edges appear twice).
+__device__ __forceinline__ bool shell_cell(const MpmConst& k, int t, int& ci, int& cj, int& ck) {
   const int nxy = k.rx * k.ry, nxz = k.rx * k.rz, nyz = k.ry * k.rz;
-  int ci, cj, ck;
   if (t < 2 * nxy) {
     ck = t >= nxy ? k.rz - 1 : 0;
     t -= t >= nxy ? nxy : 0;
@@ -223,8 +244,56 @@ k_grid_shell(MpmConst k, const float4* grid_raw, float4* grid_out, int f, ud_mpm
     cj = t / k.rz;
     ck = t % k.rz;
   } else {
+    return false;
+  }
+  return true;
+}
+
+// In-place forward only, between substeps, instead of a memset of the whole grid: re-zero (a) the empty face cells
+// k_grid_shell wrote velocities into -- CTAs [0, shell_ctas) -- and (b) the blocks the previous substep's P2G touched
+// -- the remaining CTAs, persistent warps over the block list.
+__global__ void __launch_bounds__(128)
+k_grid_clear(MpmConst k, float4* __restrict__ grid, const int32_t* __restrict__ blk_list,
+             const int32_t* __restrict__ blk_count, int shell_ctas_per_env) {
+  const int shell_ctas = shell_ctas_per_env * k.B;
+  if ((int)blockIdx.x < shell_ctas) {
+    const int env = blockIdx.x / shell_ctas_per_env;
+    int ci, cj, ck;
+    if (!shell_cell(k, (blockIdx.x - env * shell_ctas_per_env) * blockDim.x + threadIdx.x, ci, cj, ck)) return;
+    grid[(size_t)env * k.G + (size_t)(ci * k.ry + cj) * k.rz + ck] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
+  const int nblk = k.nbx * k.nby * k.nbz;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (int)((((size_t)blockIdx.x - shell_ctas) * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)(((gridDim.x - shell_ctas) * blockDim.x) >> 5);
+  const int count = *blk_count;
+  for (int li = warp0; li < count; li += nwarps) {
+    const int w = blk_list[li];
+    const int env = w / nblk, bid = w - env * nblk;
+    const int bz = bid % k.nbz, by = (bid / k.nbz) % k.nby, bx = bid / (k.nbz * k.nby);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int lc = lane + 32 * it;
+      const int ci = bx * 4 + (lc >> 4), cj = by * 4 + ((lc >> 2) & 3), ck = bz * 4 + (lc & 3);
+      if (ci < k.rx && cj < k.ry && ck < k.rz)
+        grid[(size_t)env * k.G + (size_t)(ci * k.ry + cj) * k.rz + ck] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// Empty cells of the outermost layer: the reference updates EVERY cell (empty ones get dt*gravity, colliders,
+// friction, walls), and a particle that left the grid gathers exactly these cells through clamped indices
+// (SURVEY 8c).  One thread per face cell (edges are visited twice and write the same value).
+__global__ void __launch_bounds__(128)
+k_grid_shell(MpmConst k, const float4* grid_raw, float4* grid_out, int f, ud_mpm_state in,
+             const float* __restrict__ fk_pos, const float* __restrict__ fk_rot, const float* __restrict__ fk_vw,
+             int32_t* __restrict__ act_list, int32_t* __restrict__ act_count) {
+  const int env = blockIdx.y;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nxy = k.rx * k.ry, nxz = k.rx * k.rz;
+  int ci, cj, ck;
+  if (!shell_cell(k, t0, ci, cj, ck)) return;
   const size_t idx = (size_t)env * k.G + (size_t)(ci * k.ry + cj) * k.rz + ck;
   const float4 g = grid_raw[idx];
   if (g.w > 0.f) return;  // has mass: k_grid_fwd's cell
@@ -250,15 +319,28 @@ k_grid_shell(MpmConst k, const float4* grid_raw, float4* grid_out, int f, ud_mpm
 
 void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const long long* grid_fix, int substep,
                      const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st) {
-  KScope ks_(KC_GRID, st, 2);
+  KScope ks_(KC_GRID, st, 3);
   int32_t* al = (grid_out != grid_in && ws.act_list) ? ws.act_list + (size_t)substep * k.B * k.G : nullptr;
   int32_t* ac = al ? ws.act_count + substep : nullptr;
-  k_grid_fwd<<<cdiv((long long)k.B * k.G, 128), 128, 0, st>>>(k, grid_in, grid_out, grid_fix, substep, *in, ws.fk_pos,
-                                                              ws.fk_rot, ws.fk_vw, al, ac);
+  const int total = k.B * k.nbx * k.nby * k.nbz;
+  int32_t* bl = ws.blk_list + (size_t)(substep & 1) * total;   // double-buffered: k_grid_clear reads the previous one
+  int32_t* bc = ws.blk_count + substep;
+  k_blk_compact<<<cdiv(total, 128), 128, 0, st>>>(total, ws.blk_flag, bl, bc);
+  k_grid_fwd<<<148 * 8, 128, 0, st>>>(k, grid_in, grid_out, const_cast<long long*>(grid_fix), substep, *in, ws.fk_pos,
+                                      ws.fk_rot, ws.fk_vw, bl, bc, al, ac);
   // in-place (forward) mode the raw value of an empty cell is still there when the shell kernel reads it
   const int shell = 2 * (k.rx * k.ry + k.rx * k.rz + k.ry * k.rz);
   k_grid_shell<<<dim3(cdiv(shell, 128), k.B), 128, 0, st>>>(k, grid_in, grid_out, substep, *in, ws.fk_pos, ws.fk_rot,
                                                             ws.fk_vw, al, ac);
+}
+
+void launch_grid_clear(const MpmConst& k, float4* grid, int prev_substep, const MpmWs& ws, cudaStream_t st) {
+  KScope ks_(KC_GRID, st);
+  const int total = k.B * k.nbx * k.nby * k.nbz;
+  const int shell = 2 * (k.rx * k.ry + k.rx * k.rz + k.ry * k.rz);
+  const int sc = cdiv(shell, 128);
+  k_grid_clear<<<sc * k.B + 148 * 4, 128, 0, st>>>(k, grid, ws.blk_list + (size_t)(prev_substep & 1) * total,
+                                                   ws.blk_count + prev_substep, sc);
 }
 
 // ================================================================================================

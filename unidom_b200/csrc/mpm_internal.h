@@ -38,6 +38,9 @@ struct MpmWs {
   float4* grid_raw;     // fwd: [B*G]; bwd: [S*B*G] scattered (p,m)
   float4* grid_out;     // fwd: == grid_raw; bwd: [S*B*G] updated velocities
   long long* grid_fix;  // deterministic P2G only: [B*G*4] 64-bit fixed-point accumulators of one substep
+  int32_t* blk_flag;    // [B*nbx*nby*nbz] 4x4x4 grid blocks that P2G scattered into this substep
+  int32_t* blk_list;    // [2][B*nbx*nby*nbz] the marked blocks, compacted (double-buffered by substep parity)
+  int32_t* blk_count;   // [S] number of listed blocks per substep
   float* vt_roll;       // fwd only: [9*N] V^T of the previous substep's SVD (warm start)
   int32_t* act_list;    // bwd only: [S][B*G] cells listed by the recompute pass for the grid adjoint
   int32_t* act_count;   // bwd only: [S]
@@ -105,6 +108,7 @@ void launch_fk_fwd(const MpmConst& k, const ud_mpm_state* in, const float* actio
                    const MpmWs& ws, cudaStream_t st);
 // grid_fix != null (deterministic P2G): the raw {p,m} is first converted from the fixed-point accumulators
 // into grid_in (which the adjoint reads later), then updated into grid_out.
+void launch_grid_clear(const MpmConst& k, float4* grid, int prev_substep, const MpmWs& ws, cudaStream_t st);
 void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const long long* grid_fix, int substep,
                      const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st);
 void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,

@@ -17,6 +17,7 @@ struct MpmConst {
   float gdt[3];              // float(dt)*float(gravity)     (:285)
   float sig_lo, sig_hi;      // float(1-2.5e-2*10), float(1+4.5e-3*100)  (:250)
   int n_prim, sdf_kind, pos_control, p2g_mode;
+  int mark;  // development switch: 0 no block marks (timing only, wrong results), 1 every (segment,node), 2 corner nodes
 };
 
 // mul / sub without FMA contraction (the binning key must match the reference bit for bit)

@@ -180,13 +180,21 @@ struct StageMeta {
   };
 };
 constexpr int DEAD_KEY = 0x40000000;
+// Marks the 4x4x4 grid block of cell (ix,iy,iz) as scattered-into: a fire-and-forget store (a load-then-store would
+// put an L2 round trip on every CTA's path to its first barrier: measured +20 us on k_p2g).
+UD_DEV void mark_block(const MpmConst& k, int32_t* __restrict__ flag_env, int ix, int iy, int iz) {
+  flag_env[((ix >> 2) * k.nby + (iy >> 2)) * k.nbz + (iz >> 2)] = 1;
+}
 UD_DEV int base_key(const int base[3]) { return (base[0] * 2048 + base[1]) * 2048 + base[2]; }
 
 // Groups the CTA's rows by key.  Returns this thread's grouped row; fills m.key / m.base / m.run_start /
 // m.n_runs.  Deterministic: groups are ordered by first occurrence (warp, lane), rows inside a group by
 // (warp, lane).  All threads of the CTA must call it; it ends with a barrier.
+// `blk_flag` (nullable, already offset to the env): P2G marks the 4x4x4 grid blocks it scatters into, so that the grid
+// update visits only those (k_grid_fwd).
 template <bool CLAMP, int SB>
-__device__ __forceinline__ int stage_group(const MpmConst& k, StageMeta<SB>& m, int key, const int base[3]) {
+__device__ __forceinline__ int stage_group(const MpmConst& k, StageMeta<SB>& m, int key, const int base[3],
+                                           int32_t* __restrict__ blk_flag = nullptr) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const unsigned mm = __match_any_sync(0xffffffffu, key);   // lanes of my warp with my key
@@ -246,7 +254,8 @@ __device__ __forceinline__ int stage_group(const MpmConst& k, StageMeta<SB>& m, 
   m.base[pos][2] = base[2];
   __syncthreads();  // the scratch is dead from here on: its storage becomes the cell table
   const int nr = m.n_runs;
-  if (nr <= RUN_TAB) {  // target cells of every (segment, node), computed once by all 128 threads
+  const bool tab = nr <= RUN_TAB;
+  if (tab || (!CLAMP && blk_flag)) {  // target cells of every (segment, node), computed once by all threads of the CTA
     for (int e = t; e < nr * 27; e += SB) {
       const int r = e / 27, j = e - r * 27;
       const int s0 = m.run_start[r];
@@ -261,7 +270,11 @@ __device__ __forceinline__ int stage_group(const MpmConst& k, StageMeta<SB>& m, 
         iy = idx_scatter(m.base[s0][1] + b, k.ry);
         iz = idx_scatter(m.base[s0][2] + c, k.rz);
       }
-      m.cell[r][j] = ((ix | iy | iz) < 0 || (m.key[s0] & DEAD_KEY)) ? -1 : (ix * k.ry + iy) * k.rz + iz;
+      const bool dropped = (ix | iy | iz) < 0 || (m.key[s0] & DEAD_KEY);
+      if (tab) m.cell[r][j] = dropped ? -1 : (ix * k.ry + iy) * k.rz + iz;
+      // a 3-node span touches at most two blocks per axis, both reached by its end nodes: corners mark everything
+      const bool corner = a != 1 && b != 1 && c != 1;
+      if (!CLAMP && blk_flag && !dropped && (k.mark == 1 || (k.mark == 2 && corner))) mark_block(k, blk_flag, ix, iy, iz);
     }
   }
   return pos;  // callers barrier between staging and flush, which also publishes the table
@@ -387,11 +400,11 @@ UD_DEV void load_particle(const float* ps, size_t N, int g, float x[3], float v[
 // MODE 0: staged scatter + fp32 vector REDs; 1: staged + 64-bit fixed-point REDs (deterministic);
 //      2: A/B baseline -- every particle issues its 27 vector REDs itself (no shared memory, no grouping)
 template <int MODE>
-__global__ void __launch_bounds__(P2G_BLOCK)
+__global__ void __launch_bounds__(P2G_BLOCK, 12)   // 80 registers: 12 CTAs per SM, what the staging shared memory allows too
 k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
       const float* __restrict__ h_s, const float* __restrict__ vt_in, float* __restrict__ vt_out,
-      float* __restrict__ svd_out) {
+      float* __restrict__ svd_out, int32_t* __restrict__ blk_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sv = reinterpret_cast<float*>(smem_raw);                               // [P2G_NPH*4][STG_PAD]
   constexpr int STG_PAD = stg_pad<P2G_BLOCK>();
@@ -405,7 +418,9 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
   make_stencil(x, k.inv_dx, st);
   constexpr bool DET = MODE == 1;
   int row = 0;
-  if (MODE != 2) row = stage_group<false, P2G_BLOCK>(k, meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base);
+  if (MODE != 2)
+    row = stage_group<false, P2G_BLOCK>(k, meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base,
+                                        blk_flag + (size_t)env * (k.nbx * k.nby * k.nbz));
   Consti o;
   float vt0[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
   const bool warm = vt_in != nullptr;  // warm start of the Jacobi SVD from the previous substep's V^T (grid-uniform)
@@ -453,6 +468,7 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
             const int ix = idx_scatter(st.base[0] + a, k.rx), iy = idx_scatter(st.base[1] + b, k.ry),
                       iz = idx_scatter(st.base[2] + c, k.rz);
             if ((ix | iy | iz) < 0) continue;
+            mark_block(k, blk_flag + (size_t)env * (k.nbx * k.nby * k.nbz), ix, iy, iz);
             const float wt = st.w[a][0] * st.w[b][1] * st.w[c][2];
             float4 val;
             val.x = wt * (u[0] + (float)a * Ac[0][0] + (float)b * Ac[1][0] + (float)c * Ac[2][0]);
@@ -508,13 +524,14 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
   }
   if (!tuning_stage() && !ws.grid_fix)
     k_p2g<2><<<pgrid(k, P2G_BLOCK), P2G_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in,
-                                                      vt_out, svd_out);
+                                                      vt_out, svd_out, ws.blk_flag);
   else if (ws.grid_fix)
     k_p2g<1><<<pgrid(k, P2G_BLOCK), P2G_BLOCK, stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH), st>>>(
-        k, ps_in, ps_out, reinterpret_cast<float4*>(ws.grid_fix), mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out);
+        k, ps_in, ps_out, reinterpret_cast<float4*>(ws.grid_fix), mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out,
+        ws.blk_flag);
   else
     k_p2g<0><<<pgrid(k, P2G_BLOCK), P2G_BLOCK, stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH), st>>>(
-        k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out);
+        k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out, ws.blk_flag);
 }
 
 // ------------------------------------------------------------------------------------------------
