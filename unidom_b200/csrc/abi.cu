@@ -123,7 +123,8 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
   w.fk_act = (float*)take(4 * (size_t)k.B * P * 6);
   w.jrows = (float*)take(4 * (size_t)k.B * S * 9);
   w.blk_flag = (int32_t*)take(4 * (size_t)k.B * k.nbx * k.nby * k.nbz);
-  w.blk_list = (int32_t*)take(8 * (size_t)k.B * k.nbx * k.nby * k.nbz);
+  w.blk_nbuf = bwd ? k.S : 2;
+  w.blk_list = (int32_t*)take(4 * (size_t)w.blk_nbuf * k.B * k.nbx * k.nby * k.nbz);
   w.blk_count = (int32_t*)take(4 * S);
   if (!bwd) {
     w.ps = (float*)take(4 * (size_t)PS_NCOMP * N);
@@ -316,9 +317,12 @@ static void mpm_reverse_pass(const MpmConst& k, const ud_mpm_state* in, const fl
   zero_async(ws.g_scal, 4 * (size_t)k.B * GS_STRIDE, st);
   zero_async(ws.g_prim_in, 4 * (size_t)k.B * P * 16, st);
   zero_async(ws.g_act, 4 * (size_t)k.B * P * 6, st);
+  zero_async(ws.ggrid, 16 * BG, st);
   for (int f = k.S - 1; f >= 0; --f) {
     const float* s_in = ws.ps + slot * f;
-    zero_async(ws.ggrid, 16 * BG, st);
+    // G2P^T of substep f scatters into the blocks P2G(f) marked (+ face cells through clamped indices): only those
+    // are re-zeroed before the next (earlier) substep scatters
+    if (f < k.S - 1) launch_grid_clear(k, ws.ggrid, f + 1, ws, st);
     launch_g2p_bwd(k, s_in, ws.grid_out + BG * f, ws, st);
     launch_grid_bwd(k, ws.grid_raw + BG * f, f, in, ws, st);
     launch_p2g_bwd(k, s_in, ws.svd_s + (size_t)SV_NCOMP * k.N * f, in->mu, in->lamda, ws, st);

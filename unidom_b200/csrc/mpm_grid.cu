@@ -323,7 +323,7 @@ void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const
   int32_t* al = (grid_out != grid_in && ws.act_list) ? ws.act_list + (size_t)substep * k.B * k.G : nullptr;
   int32_t* ac = al ? ws.act_count + substep : nullptr;
   const int total = k.B * k.nbx * k.nby * k.nbz;
-  int32_t* bl = ws.blk_list + (size_t)(substep & 1) * total;   // double-buffered: k_grid_clear reads the previous one
+  int32_t* bl = ws.blk_list + (size_t)(substep % ws.blk_nbuf) * total;
   int32_t* bc = ws.blk_count + substep;
   k_blk_compact<<<cdiv(total, 128), 128, 0, st>>>(total, ws.blk_flag, bl, bc);
   k_grid_fwd<<<148 * 8, 128, 0, st>>>(k, grid_in, grid_out, const_cast<long long*>(grid_fix), substep, *in, ws.fk_pos,
@@ -339,7 +339,7 @@ void launch_grid_clear(const MpmConst& k, float4* grid, int prev_substep, const 
   const int total = k.B * k.nbx * k.nby * k.nbz;
   const int shell = 2 * (k.rx * k.ry + k.rx * k.rz + k.ry * k.rz);
   const int sc = cdiv(shell, 128);
-  k_grid_clear<<<sc * k.B + 148 * 4, 128, 0, st>>>(k, grid, ws.blk_list + (size_t)(prev_substep & 1) * total,
+  k_grid_clear<<<sc * k.B + 148 * 4, 128, 0, st>>>(k, grid, ws.blk_list + (size_t)(prev_substep % ws.blk_nbuf) * total,
                                                    ws.blk_count + prev_substep, sc);
 }
 

@@ -39,7 +39,9 @@ struct MpmWs {
   float4* grid_out;     // fwd: == grid_raw; bwd: [S*B*G] updated velocities
   long long* grid_fix;  // deterministic P2G only: [B*G*4] 64-bit fixed-point accumulators of one substep
   int32_t* blk_flag;    // [B*nbx*nby*nbz] 4x4x4 grid blocks that P2G scattered into this substep
-  int32_t* blk_list;    // [2][B*nbx*nby*nbz] the marked blocks, compacted (double-buffered by substep parity)
+  int32_t* blk_list;    // [blk_nbuf][B*nbx*nby*nbz] the marked blocks, compacted; slot = substep % blk_nbuf
+  int blk_nbuf;         // fwd: 2 (k_grid_clear reads the previous substep's list); bwd: S (the reverse pass re-zeroes
+                        // the cotangent grid block by block)
   int32_t* blk_count;   // [S] number of listed blocks per substep
   float* vt_roll;       // fwd only: [9*N] V^T of the previous substep's SVD (warm start)
   int32_t* act_list;    // bwd only: [S][B*G] cells listed by the recompute pass for the grid adjoint
