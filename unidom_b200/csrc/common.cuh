@@ -230,11 +230,10 @@ UD_DEV void svd3(const Mat3& A, Mat3& U, float s[3], Mat3& Vt) {
 // (the L and projector terms vanish identically for real 3x3 input).
 UD_DEV float safe_inv(float x) { return x / (x * x + 1e-12f); }
 
-UD_DEV Mat3 svd3_bwd(const Mat3& U, const float s[3], const Mat3& Vt, const Mat3& dU, const float dS[3],
-                     const Mat3& dVt) {
+// Core of the VJP given U^T dU and Vt dVt^T.
+UD_DEV Mat3 svd3_bwd_rotated(const Mat3& U, const float s[3], const Mat3& Vt, const Mat3& UtdU, const float dS[3],
+                             const Mat3& VdV) {
   float s2[3] = {s[0] * s[0], s[1] * s[1], s[2] * s[2]};
-  Mat3 UtdU = mat_mul_tn(U, dU);
-  Mat3 VdV = mat_mul_nt(Vt, dVt);
   Mat3 M;  // diag(dS) + (J+J^T) o S_col + S_row-scaled (K+K^T)
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -253,6 +252,11 @@ UD_DEV Mat3 svd3_bwd(const Mat3& U, const float s[3], const Mat3& Vt, const Mat3
       }
     }
   return mat_mul(mat_mul(U, M), Vt);
+}
+
+UD_DEV Mat3 svd3_bwd(const Mat3& U, const float s[3], const Mat3& Vt, const Mat3& dU, const float dS[3],
+                     const Mat3& dVt) {
+  return svd3_bwd_rotated(U, s, Vt, mat_mul_tn(U, dU), dS, mat_mul_nt(Vt, dVt));
 }
 
 }  // namespace ud

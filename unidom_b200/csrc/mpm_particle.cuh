@@ -136,6 +136,95 @@ UD_DEV void constitutive_fwd(const MpmConst& k, const Mat3& C, const Mat3& F, fl
   constitutive_post(k, C, o);
 }
 
+// Plastic material only (F2 = U diag(sc) Vt, R = U Vt): the stress needs neither F1 nor Vt,
+//   M = (F2 - R) F2^T = U diag((sc - 1) sc) U^T.
+// Used by the adjoint's gather phase, which only needs `affine` (1 symmetric product instead of 4 matrix products).
+UD_DEV void plastic_affine(const MpmConst& k, const Mat3& C, const Mat3& U, const float s[3], float mu_s, float la_s,
+                           float h, Mat3& affine) {
+  const float hc = fminf(fmaxf(h, 0.1f), 5.f);
+  const float mu = mu_s * hc, la = la_s * hc;
+  float sc[3], m[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    sc[i] = fminf(fmaxf(s[i], k.sig_lo), k.sig_hi);
+    m[i] = (sc[i] - 1.f) * sc[i];
+  }
+  const float J = sc[0] * sc[1] * sc[2];
+  const float iso = la * J * (J - 1.f);
+  const float cs = k.c_stress_mul / k.c_stress_div;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j) {
+      const float Mij = U(i, 0) * m[0] * U(j, 0) + U(i, 1) * m[1] * U(j, 1) + U(i, 2) * m[2] * U(j, 2);
+      const float st = 2.f * mu * Mij + (i == j ? iso : 0.f);
+      affine(i, j) = cs * st + k.p_mass * C(i, j);
+      if (i != j) affine(j, i) = cs * st + k.p_mass * C(j, i);
+    }
+}
+
+// Reverse of constitutive_fwd for a plastic particle, in the frame of the SVD.  The same formulas as
+// constitutive_bwd (chain through F2 = U diag(sc) Vt, D = F2 - R, M = D F2^T and the reference's SVD VJP), with every
+// product by U / Vt that cancels carried out symbolically: with Gs = U^T gS U, G = 2 mu Gs, H = U^T gF2out V,
+//   U^T gD  V = G diag(sc)                         =: X
+//   U^T gF2 V = G^T diag(sc - 1) + X + H           =: Y
+//   U^T gU    = -X + Y diag(sc),   Vt gVt^T = -X^T + Y^T diag(sc),   gsc_i = gJ prod_{j != i} sc_j + Y_ii
+//   <gS, M>   = sum_i (sc_i - 1) sc_i Gs_ii
+// 8 matrix products instead of 17, and neither F1, F2, D nor R is formed.
+UD_DEV void constitutive_bwd_plastic(const MpmConst& k, const Mat3& C, const Mat3& F, const Mat3& U, const float s[3],
+                                     const Mat3& Vt, float mu_s, float la_s, float h, const Mat3& gA,
+                                     const Mat3& gF2out, Mat3& gC, Mat3& gF, float& gmu_s, float& gla_s) {
+  const float hc = fminf(fmaxf(h, 0.1f), 5.f);
+  const float mu = mu_s * hc, la = la_s * hc;
+  float sc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sc[i] = fminf(fmaxf(s[i], k.sig_lo), k.sig_hi);
+  const float J = sc[0] * sc[1] * sc[2];
+  const float cs = k.c_stress_mul / k.c_stress_div;
+  Mat3 gS;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) gS.m[i] = gA.m[i] * cs;
+  const float trS = gS.m[0] + gS.m[4] + gS.m[8];
+  const Mat3 Gs = mat_mul(mat_mul_tn(U, gS), U);
+  float gmu = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) gmu += (sc[i] - 1.f) * sc[i] * Gs(i, i);
+  gmu_s = 2.f * gmu * hc;
+  gla_s = J * (J - 1.f) * trS * hc;
+  const float gJ = la * (2.f * J - 1.f) * trS;
+  const Mat3 H = mat_mul_nt(mat_mul_tn(U, gF2out), Vt);
+  const float tm = 2.f * mu;
+  Mat3 UtdU, VdV;
+  float gsc[3] = {gJ * sc[1] * sc[2], gJ * sc[0] * sc[2], gJ * sc[0] * sc[1]};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float Xij = tm * Gs(i, j) * sc[j], Xji = tm * Gs(j, i) * sc[i];
+      const float Yij = tm * Gs(j, i) * (sc[j] - 1.f) + Xij + H(i, j);
+      const float Yji = tm * Gs(i, j) * (sc[i] - 1.f) + Xji + H(j, i);
+      UtdU(i, j) = -Xij + Yij * sc[j];
+      VdV(i, j) = -Xji + Yji * sc[j];
+      if (i == j) gsc[i] += Yij;
+    }
+  float gs[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    gs[i] = (s[i] > k.sig_lo && s[i] < k.sig_hi) ? gsc[i]
+            : ((s[i] == k.sig_lo || s[i] == k.sig_hi) ? 0.5f * gsc[i] : 0.f);   // jnp.clip tie rule
+  const Mat3 gF1 = svd3_bwd_rotated(U, s, Vt, UtdU, gs, VdV);
+  const Mat3 gCf = mat_mul_nt(gF1, F);
+  Mat3 A;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A.m[i] = k.dt * C.m[i];
+  A.m[0] += 1.f;
+  A.m[4] += 1.f;
+  A.m[8] += 1.f;
+  gF = mat_mul_tn(A, gF1);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) gC.m[i] = k.p_mass * gA.m[i] + k.dt * gCf.m[i];
+}
+
 // Reverse of constitutive_fwd.  Inputs: cotangents of affine (gA) and of the output F (gF2out).
 // Outputs: gC (adds p_mass*gA + dt*gF1 F^T), gF, and the per-particle contributions to the
 // cotangents of state.mu / state.lamda.

@@ -790,20 +790,32 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     // constitutive reverse after the gather, instead of staying live across it.
     Stencil st;
     float Ac[3][3], u0[3];
+    const bool plastic = mat_s[g] == 2;
     {
       float x[3], v[3];
       Mat3 C, F;
-      load_particle(ps_in, N, g, x, v, C, F);
-      make_stencil(x, k.inv_dx, st);
       Consti o;
-      constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) x[c] = ps_in[(PS_X + c) * N + g];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = ps_in[(PS_V + c) * N + g];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) C.m[c] = ps_in[(PS_C + c) * N + g];
+      make_stencil(x, k.inv_dx, st);
 #pragma unroll
       for (int c = 0; c < 9; ++c) o.U.m[c] = svd_in[(SV_U + c) * N + g];
 #pragma unroll
       for (int c = 0; c < 3; ++c) o.s[c] = svd_in[(SV_S + c) * N + g];
+      if (plastic) {  // the stress of a plastic particle is a function of (U, clip(s)) alone
+        plastic_affine(k, C, o.U, o.s, mu_s[env], la_s[env], h_s[g], o.affine);
+      } else {
 #pragma unroll
-      for (int c = 0; c < 9; ++c) o.Vt.m[c] = svd_in[(SV_VT + c) * N + g];
-      constitutive_post(k, C, o);
+        for (int c = 0; c < 9; ++c) F.m[c] = ps_in[(PS_F + c) * N + g];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) o.Vt.m[c] = svd_in[(SV_VT + c) * N + g];
+        constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+        constitutive_post(k, C, o);
+      }
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
 #pragma unroll
@@ -895,9 +907,13 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     for (int d = 0; d < 3; ++d) gx_in[d] = gs[(PS_X + d) * N + g];
 #pragma unroll
     for (int c = 0; c < 9; ++c) gF2out.m[c] = gs[(PS_F + c) * N + g];
-    constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
-    constitutive_post(k, C, o);
-    constitutive_bwd(k, C, F, o, gA, gF2out, gC, gF, gmu, gla);
+    if (plastic) {
+      constitutive_bwd_plastic(k, C, F, o.U, o.s, o.Vt, mu_s[env], la_s[env], h_s[g], gA, gF2out, gC, gF, gmu, gla);
+    } else {
+      constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+      constitutive_post(k, C, o);
+      constitutive_bwd(k, C, F, o, gA, gF2out, gC, gF, gmu, gla);
+    }
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       gs[(PS_X + d) * N + g] = gx_in[d] + k.inv_dx * gfx[d];
