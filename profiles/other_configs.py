@@ -161,6 +161,36 @@ def cloth_env_step():
     return res
 
 
+def small_scene_graph():
+    """The reference's own whip_rope size (67 particles, res 32^3, S = 70): launch-bound; eager vs CUDA-graph replay
+    of a 5-step forward scan."""
+    from unidom_b200.graphs import GraphedMPMScan
+    B, T = 16, 5
+    conf = confs.whip_rope_conf()
+    sim = SimpleMPMSimulator(conf, B, use_position_control=True)
+    st = sim.add_box(conf, None, size=[0.25, 0.01, 0.01], init_pos=[0.5, 0.02, 0.5], hardness=1.0, material=1,
+                     density=2.75)
+    prim = create_primitive(conf, friction=0.0, softness=666.0, color=[0.5] * 3, size=[0.01, 0.01, 0.01],
+                            init_pos=[0.37, 0.02, 0.5])
+    st = st._replace(primitives=[prim])
+    state = sim.reset_jax(st)
+    acts = torch.zeros((T, B, 6), device="cuda")
+    acts[..., 1] = 0.5
+
+    def eager():
+        s = state
+        with torch.no_grad():
+            for t in range(T):
+                s, _ = sim.step_jax(s, acts[t])
+    graph = GraphedMPMScan(sim, state, acts)
+    te = timed(eager, n=10)
+    tg = timed(lambda: graph(state, acts), n=10)
+    n = state.x.shape[1]
+    return {"config": "whip_rope shipped size, forward scan", "envs": B, "particles_per_env": n, "substeps": conf.steps * T,
+            "eager_ms": te, "graph_ms": tg, "eager_us_per_substep": 1e3 * te / (conf.steps * T),
+            "graph_us_per_substep": 1e3 * tg / (conf.steps * T)}
+
+
 def reward_kernels():
     """calc_chamfer fwd+bwd: fused kernels vs the reference's formulation (materialised (B,P,Q) distances) in torch."""
     from unidom_b200 import envs
@@ -185,6 +215,6 @@ def reward_kernels():
 
 
 if __name__ == "__main__":
-    only = sys.argv[1:] or ["pour_water", "whip_rope", "cloth_para", "cloth_env_step", "reward_kernels"]
-    for fn in [f for f in (pour_water, whip_rope, cloth_para, cloth_env_step, reward_kernels) if f.__name__ in only]:
+    only = sys.argv[1:] or ["pour_water", "whip_rope", "cloth_para", "cloth_env_step", "reward_kernels", "small_scene_graph"]
+    for fn in [f for f in (pour_water, whip_rope, cloth_para, cloth_env_step, reward_kernels, small_scene_graph) if f.__name__ in only]:
         print(json.dumps(fn()), flush=True)

@@ -313,3 +313,27 @@ def test_invalid_arguments_are_rejected(built_lib):
     with pytest.raises(RuntimeError):
         sim.p2g_mode = 7
         sim.step_jax(st, _actions(2, 1).to(st.x.device))
+
+
+def test_cuda_graph_replay_of_the_forward_scan(built_lib):
+    """unidom_b200.graphs.GraphedMPMScan: T step_jax calls captured once, replayed with new inputs; deterministic P2G
+    makes replay and eager launches bit-identical."""
+    from unidom_b200 import _lib
+    from unidom_b200.graphs import GraphedMPMScan
+    conf = _conf(steps=8)
+    B, T = 2, 3
+    sim = _sim(conf, B, p2g_mode=_lib.UD_P2G_DETERMINISTIC)
+    st = util.mini_plasticine(sim, B, seed=41)
+    acts = torch.stack([_actions(B, 1, seed=50 + t) for t in range(T)]).to(st.x.device)
+    graph = GraphedMPMScan(sim, st, acts)
+    for trial in range(2):                                   # second trial: different inputs through the same graph
+        s_in = st._replace(x=st.x + 1e-3 * trial, v=st.v * (1 + trial))
+        a_in = acts * (1 - 0.3 * trial)
+        out = graph(s_in, a_in)
+        ref = s_in
+        with torch.no_grad():
+            for t in range(T):
+                ref, _ = sim.step_jax(ref, a_in[t])
+        for k in ("x", "v", "C", "F", "J"):
+            assert torch.equal(getattr(out, k), getattr(ref, k)), (trial, k)
+        assert torch.equal(out.primitives[0].position, ref.primitives[0].position)

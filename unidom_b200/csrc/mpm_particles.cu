@@ -1,5 +1,7 @@
 // Particle-side kernels of the MLS-MPM step: per-frame binning, P2G scatter, G2P gather and their
 // adjoints.  sm_100a.  Reference: DaXBench/daxbench/core/engine/mpm_simulator.py:178-330.
+#include <type_traits>
+
 #include "mpm_internal.h"
 
 namespace ud {
@@ -194,7 +196,7 @@ UD_DEV int base_key(const int base[3]) { return (base[0] * 2048 + base[1]) * 204
 // update visits only those (k_grid_fwd).
 template <bool CLAMP, int SB>
 __device__ __forceinline__ int stage_group(const MpmConst& k, StageMeta<SB>& m, int key, const int base[3],
-                                           int32_t* __restrict__ blk_flag = nullptr) {
+                                           int32_t* __restrict__ blk_flag = nullptr, int* my_run = nullptr) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const unsigned mm = __match_any_sync(0xffffffffu, key);   // lanes of my warp with my key
@@ -247,7 +249,9 @@ __device__ __forceinline__ int stage_group(const MpmConst& k, StageMeta<SB>& m, 
     }
   }
   __syncthreads();
-  const int pos = m.estart[__shfl_sync(0xffffffffu, e, leadlane)] + __popc(mm & lt);
+  const int my_entry = __shfl_sync(0xffffffffu, e, leadlane);
+  const int pos = m.estart[my_entry] + __popc(mm & lt);
+  if (my_run) *my_run = m.egid[my_entry];   // segment of this thread's row (read before the scratch dies)
   m.key[pos] = key;
   m.base[pos][0] = base[0];
   m.base[pos][1] = base[1];
@@ -379,6 +383,10 @@ constexpr int P2G_BLOCK = 64;    // threads (= particles) per CTA of k_p2g: with
 constexpr int G2PB_BLOCK = UD_BLOCK;  // k_g2p_bwd: one window of 27 nodes, 108 flush lanes of 128 (two windows cost it registers)
 constexpr int P2G_NPH = 14;      // nodes per staging window of k_p2g (27 nodes -> 2 windows)
 constexpr int G2PB_NPH = 27;
+constexpr int G2PB_TILE_RUNS = 12;  // segments whose 27 grid velocities k_g2p_bwd keeps in shared memory (5.2 KB: the CTA
+                                    // stays at 4 per SM); CTAs with more distinct cells gather from L1/L2 as before
+constexpr size_t g2pb_tile_offset() { return (stage_smem_bytes<G2PB_BLOCK>(3, G2PB_NPH) + 15) & ~(size_t)15; }
+constexpr size_t g2pb_smem_bytes() { return g2pb_tile_offset() + sizeof(float4) * G2PB_TILE_RUNS * 27; }
 
 // ------------------------------------------------------------------------------------------------
 // P2G: F update + SVD + plasticity + stress (mpm_simulator.py:238-268), then the 27-node scatter of
@@ -538,7 +546,7 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
 // G2P (g2p_micro, :196-221) + advection (:326).  Out-of-range nodes clamp (JAX gather rule).
 // Rows of C' of original particles 0..2 are kept for the J update quirk (:327).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UD_BLOCK)
+__global__ void __launch_bounds__(UD_BLOCK, 8)
 k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ grid,
       const int32_t* __restrict__ perm, float* __restrict__ jrows, int substep) {
   UD_PARTICLE_INDEX(k, env, g);
@@ -683,6 +691,7 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   float* sv = reinterpret_cast<float*>(smem_raw);                               // [81][STG_PAD]
   constexpr int STG_PAD = stg_pad<G2PB_BLOCK>();
   StageMeta<G2PB_BLOCK>& meta = *reinterpret_cast<StageMeta<G2PB_BLOCK>*>(sv + G2PB_NPH * 3 * STG_PAD);
+  float4* tile = reinterpret_cast<float4*>(smem_raw + g2pb_tile_offset());  // [G2PB_TILE_RUNS][27]
   UD_PARTICLE_INDEX(k, env, g);
   const size_t N = k.N;
   float x[3], gxo[3], gvt[3];
@@ -697,9 +706,23 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   for (int c = 0; c < 9; ++c) gC.m[c] = gs[(PS_C + c) * N + g];
   Stencil st;
   make_stencil(x, k.inv_dx, st);
-  const int row = stage_group<true, G2PB_BLOCK>(k, meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base);
+  int my_run = 0;
+  const int row = stage_group<true, G2PB_BLOCK>(k, meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base,
+                                                nullptr, &my_run);
   const float lw = live_ ? 1.f : 0.f;
   const float4* genv = grid_out + (size_t)env * k.G;
+  // The CTA's particles sit in a handful of cells: the 27 grid velocities of every segment are fetched ONCE into
+  // shared memory (coalesced over the cell table) and every particle of the segment reads them from there.
+  __syncthreads();   // publishes the cell table
+  const bool tiled = meta.n_runs <= G2PB_TILE_RUNS;   // block-uniform
+  if (tiled) {
+    for (int e = threadIdx.x; e < meta.n_runs * 27; e += G2PB_BLOCK) {
+      const int cell = meta.cell[e / 27][e % 27];
+      tile[e] = cell >= 0 ? __ldg(&genv[cell]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+  }
+  const float4* my_tile = tile + my_run * 27;
   const float c4 = 4.f * k.inv_dx;
   // r(a,b,c) = gv' + 4 inv_dx gC' (off - fx) = r0 + a K0 + b K1 + c K2   (K_j = 4 inv_dx * column j of gC')
   float K[3][3], r0[3];
@@ -711,43 +734,53 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   }
   // accumulators: Wg = sum wt g ; the weight cotangent gwt = g . r is contracted hierarchically with (w, dw)
   float Wg[3] = {0.f, 0.f, 0.f}, gfx[3] = {0.f, 0.f, 0.f};
+  auto nodes = [&](auto tiled_tag) {
+    constexpr bool TILED = decltype(tiled_tag)::value;
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const int ix = idx_gather(st.base[0] + a, k.rx);
-    const float wa = st.w[a][0] * lw;
-    float ra[3] = {r0[0] + (float)a * K[0][0], r0[1] + (float)a * K[0][1], r0[2] + (float)a * K[0][2]};
-    float P1 = 0.f, P2 = 0.f, Q1 = 0.f;  // sum_b (sum_c gwt w_c) w_b, ... dw_b, sum_b (sum_c gwt dw_c) w_b
+    for (int a = 0; a < 3; ++a) {
+      const int ix = TILED ? 0 : idx_gather(st.base[0] + a, k.rx);
+      const float wa = st.w[a][0] * lw;
+      float ra[3] = {r0[0] + (float)a * K[0][0], r0[1] + (float)a * K[0][1], r0[2] + (float)a * K[0][2]};
+      float P1 = 0.f, P2 = 0.f, Q1 = 0.f;  // sum_b (sum_c gwt w_c) w_b, ... dw_b, sum_b (sum_c gwt dw_c) w_b
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const int iy = idx_gather(st.base[1] + b, k.ry);
-      const float wab = wa * st.w[b][1];
-      float rab[3] = {ra[0] + (float)b * K[1][0], ra[1] + (float)b * K[1][1], ra[2] + (float)b * K[1][2]};
-      float P = 0.f, Q = 0.f;
+      for (int b = 0; b < 3; ++b) {
+        const int iy = TILED ? 0 : idx_gather(st.base[1] + b, k.ry);
+        const float wab = wa * st.w[b][1];
+        float rab[3] = {ra[0] + (float)b * K[1][0], ra[1] + (float)b * K[1][1], ra[2] + (float)b * K[1][2]};
+        float P = 0.f, Q = 0.f;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int iz = idx_gather(st.base[2] + c, k.rz);
-        const float wt = wab * st.w[c][2];
-        const float4 gv = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
-        const float r[3] = {rab[0] + (float)c * K[2][0], rab[1] + (float)c * K[2][1], rab[2] + (float)c * K[2][2]};
-        float* dst = sv + ((a * 9 + b * 3 + c) * 3) * STG_PAD + row;
-        dst[0] = wt * r[0];
-        dst[STG_PAD] = wt * r[1];
-        dst[2 * STG_PAD] = wt * r[2];
-        const float gwt = gv.x * r[0] + gv.y * r[1] + gv.z * r[2];
-        Wg[0] += wt * gv.x;
-        Wg[1] += wt * gv.y;
-        Wg[2] += wt * gv.z;
-        P += gwt * st.w[c][2];
-        Q += gwt * st.dw[c][2];
+        for (int c = 0; c < 3; ++c) {
+          const float wt = wab * st.w[c][2];
+          float4 gv;
+          if (TILED) {
+            gv = my_tile[a * 9 + b * 3 + c];
+          } else {
+            const int iz = idx_gather(st.base[2] + c, k.rz);
+            gv = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
+          }
+          const float r[3] = {rab[0] + (float)c * K[2][0], rab[1] + (float)c * K[2][1], rab[2] + (float)c * K[2][2]};
+          float* dst = sv + ((a * 9 + b * 3 + c) * 3) * STG_PAD + row;
+          dst[0] = wt * r[0];
+          dst[STG_PAD] = wt * r[1];
+          dst[2 * STG_PAD] = wt * r[2];
+          const float gwt = gv.x * r[0] + gv.y * r[1] + gv.z * r[2];
+          Wg[0] += wt * gv.x;
+          Wg[1] += wt * gv.y;
+          Wg[2] += wt * gv.z;
+          P += gwt * st.w[c][2];
+          Q += gwt * st.dw[c][2];
+        }
+        P1 += P * st.w[b][1];
+        P2 += P * st.dw[b][1];
+        Q1 += Q * st.w[b][1];
       }
-      P1 += P * st.w[b][1];
-      P2 += P * st.dw[b][1];
-      Q1 += Q * st.w[b][1];
+      gfx[0] += P1 * st.dw[a][0];
+      gfx[1] += P2 * st.w[a][0];
+      gfx[2] += Q1 * st.w[a][0];
     }
-    gfx[0] += P1 * st.dw[a][0];
-    gfx[1] += P2 * st.w[a][0];
-    gfx[2] += Q1 * st.w[a][0];
-  }
+  };
+  if (tiled) nodes(std::true_type{});
+  else nodes(std::false_type{});
   if (live_) {
     // fx enters d = off - fx with a minus sign: gfx_j -= sum_n wt (K_j . g) = K_j . Wg
 #pragma unroll
@@ -764,7 +797,12 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
 void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
                     cudaStream_t st) {
   KScope ks_(KC_G2P_BWD, st);
-  k_g2p_bwd<<<pgrid(k, G2PB_BLOCK), G2PB_BLOCK, stage_smem_bytes<G2PB_BLOCK>(3, G2PB_NPH), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_g2p_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2pb_smem_bytes());
+    attr_set = true;
+  }
+  k_g2p_bwd<<<pgrid(k, G2PB_BLOCK), G2PB_BLOCK, g2pb_smem_bytes(), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
 }
 
 // P2G^T (gather of the cotangents of scattered momentum/mass; dropped nodes contribute nothing),
