@@ -240,7 +240,15 @@ def test_taped_adjoint_matches_recompute_adjoint(built_lib):
         res[m] = _run_grad(step, st, act, cot, 1, lambda t: t.to(st.x.device))
         chose[m], held[m] = sim.last_adjoint, torch.cuda.memory_allocated() - m0
     assert chose == {"tape": "tape", "recompute": "recompute", "auto": "recompute"}, chose
-    assert held["tape"] < tape_bytes // 2, (held, tape_bytes)   # the tape went with the graph's buffers, outputs still held
+    # the tape went back to the simulator's free list with the backward (outputs still held): the next step reuses it
+    assert len(sims["tape"]._tape_pool) == 1 and sims["tape"]._tape_pool[0].numel() == tape_bytes + 256
+    x2 = st.x.clone().requires_grad_(True)
+    o2 = sims["tape"].step_jax(st._replace(x=x2), act)[0]
+    assert len(sims["tape"]._tape_pool) == 0
+    (o2.x.sum()).backward(retain_graph=True)
+    assert len(sims["tape"]._tape_pool) == 1
+    with pytest.raises(RuntimeError, match="tape was released"):
+        (o2.v.sum()).backward()
     for k in ("x", "v", "C", "F", "J"):
         assert torch.equal(getattr(outs["tape"], k), getattr(outs["recompute"], k)), k
     assert torch.equal(outs["tape"].primitives[0].position, outs["recompute"].primitives[0].position)

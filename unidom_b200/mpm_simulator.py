@@ -109,6 +109,32 @@ def flatten_state(state: MPMState, n_prim: int):
     return leaves
 
 
+class _Tape:
+    """One step's substep residuals.  Buffers are recycled through the simulator's own free list: a 6 GB request per
+    differentiated step that goes through torch's caching allocator gets its cached block split by the small
+    allocations in between and ends in cudaMalloc/cudaFree churn (measured: 11 -> 16-29 ms per step, erratic)."""
+
+    def __init__(self, sim, nbytes):
+        self.sim, self.nbytes = sim, nbytes
+        pool = sim._tape_pool
+        i = next((i for i, b in enumerate(pool) if b.numel() == nbytes + 256), None)
+        self.buf = pool.pop(i) if i is not None else torch.empty(nbytes + 256, dtype=torch.uint8, device=sim.device)
+
+    def release(self):
+        """Called after the step's backward: the buffer goes back to the free list (a second backward through the same
+        step needs adjoint="recompute", like retain_graph needs saved tensors)."""
+        if self.buf is not None:
+            if len(self.sim._tape_pool) < self.sim.tape_pool_size:
+                self.sim._tape_pool.append(self.buf)
+            self.buf = None
+
+    def __del__(self):      # forward that never saw a backward
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class _MpmStep(torch.autograd.Function):
     """One custom VJP per (env batch, sub-action): fwd = S substeps; bwd = reverse from the tape the forward kept,
     or recompute + reverse when the step ran without a tape
@@ -118,19 +144,22 @@ class _MpmStep(torch.autograd.Function):
     def forward(ctx, sim, softness_list, want_tape, action, *leaves):
         leaves = [_f32c(t) for t in leaves]
         action = _f32c(action)
-        out_leaves, tape = sim._call_fwd(leaves, softness_list, action, want_tape)
+        out_leaves, ctx.tape = sim._call_fwd(leaves, softness_list, action, want_tape)
         ctx.sim = sim
         ctx.softness_list = softness_list
-        ctx.taped = tape is not None
-        # the tape is a saved tensor, so autograd frees it with the graph's buffers right after the backward
-        ctx.save_for_backward(action, *leaves, *([tape] if ctx.taped else []))
+        ctx.save_for_backward(action, *leaves)
         return tuple(out_leaves)
 
     @staticmethod
     def backward(ctx, *gout):
         action, *leaves = ctx.saved_tensors
-        tape = leaves.pop() if ctx.taped else None
+        tape = ctx.tape
+        if tape is not None and tape.buf is None:
+            raise RuntimeError("this step's tape was released by an earlier backward; differentiate it once, or build "
+                               "the simulator with adjoint='recompute'")
         gin, gaction = ctx.sim._call_bwd(leaves, ctx.softness_list, action, list(gout), tape)
+        if tape is not None:
+            tape.release()
         return (None, None, None, gaction, *gin)
 
 
@@ -167,6 +196,8 @@ class SimpleMPMSimulator:
             tape_budget_bytes = torch.cuda.get_device_properties(self.device).total_memory * 7 // 10
         self.tape_budget_bytes = int(tape_budget_bytes)
         self.last_adjoint = None        # "tape" / "recompute": what the last differentiated forward chose
+        self._tape_pool = []            # free tape buffers (see _Tape)
+        self.tape_pool_size = 2
         self._rng = np.random.RandomState(getattr(conf, "seed", 0))
 
     # ------------------------------------------------------------- scene construction
@@ -280,10 +311,12 @@ class SimpleMPMSimulator:
         sin, sout = self._pack(leaves, softness_list), self._pack(out, soft_out)
         if want_tape and self.adjoint != "recompute":
             need = self._L.ud_mpm_tape_bytes(C.byref(p))
-            if self.adjoint == "tape" or torch.cuda.memory_allocated(self.device) + need <= self.tape_budget_bytes:
-                tape = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+            pooled = any(b.numel() == need + 256 for b in self._tape_pool)      # already counted in memory_allocated
+            if (self.adjoint == "tape" or pooled
+                    or torch.cuda.memory_allocated(self.device) + need <= self.tape_budget_bytes):
+                tape = _Tape(self, need)
                 rc = self._L.ud_mpm_step_fwd_taped(C.byref(p), C.byref(sin), _ptr(self._material_dev),
-                                                   _ptr(self._h_dev), _ptr(action), C.byref(sout), _aligned(tape),
+                                                   _ptr(self._h_dev), _ptr(action), C.byref(sout), _aligned(tape.buf),
                                                    need, self._stream())
                 _lib.check(rc, "ud_mpm_step_fwd_taped")
                 self.last_adjoint = "tape"
@@ -305,7 +338,7 @@ class SimpleMPMSimulator:
         sgo, sgi = self._pack(gout, None), self._pack(gin, None)
         if tape is not None:
             rc = self._L.ud_mpm_step_bwd_taped(C.byref(p), C.byref(sin), _ptr(action), C.byref(sgo), C.byref(sgi),
-                                               _ptr(gaction), _aligned(tape), tape.numel() - 256, self._stream())
+                                               _ptr(gaction), _aligned(tape.buf), tape.nbytes, self._stream())
             _lib.check(rc, "ud_mpm_step_bwd_taped")
             return gin, gaction
         ws, nbytes = self._ws_bwd.get(self._L.ud_mpm_bwd_workspace_bytes(C.byref(p)))
