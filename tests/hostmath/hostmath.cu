@@ -68,6 +68,32 @@ void hm_constitutive(int n, const double* consts, const float* C, const float* F
   }
 }
 
+// The adjoint's plastic fast path (plastic_affine + constitutive_bwd_plastic: same formulas in the SVD frame)
+void hm_constitutive_plastic(int n, const double* consts, const float* C, const float* F, float mu_s, float la_s,
+                             const float* h, const float* gA, const float* gF2, float* affine, float* gC, float* gF,
+                             float* gmu, float* gla) {
+  MpmConst k = make_k(consts);
+  for (int i = 0; i < n; ++i) {
+    Mat3 c, f, ga, gf2, gc, gf, aff;
+    for (int j = 0; j < 9; ++j) {
+      c.m[j] = C[9 * i + j];
+      f.m[j] = F[9 * i + j];
+      ga.m[j] = gA[9 * i + j];
+      gf2.m[j] = gF2[9 * i + j];
+    }
+    Consti o;
+    constitutive_pre(k, c, f, mu_s, la_s, h[i], 2, o);
+    svd3(o.F1, o.U, o.s, o.Vt);
+    plastic_affine(k, c, o.U, o.s, mu_s, la_s, h[i], aff);
+    constitutive_bwd_plastic(k, c, f, o.U, o.s, o.Vt, mu_s, la_s, h[i], ga, gf2, gc, gf, gmu[i], gla[i]);
+    for (int j = 0; j < 9; ++j) {
+      affine[9 * i + j] = aff.m[j];
+      gC[9 * i + j] = gc.m[j];
+      gF[9 * i + j] = gf.m[j];
+    }
+  }
+}
+
 // forward collide / position control on one cell
 void hm_prim_fwd(int pos_control, int kind, float dt, const float* gpos, const float* prim, float softness,
                  const float* vin, float* vout) {

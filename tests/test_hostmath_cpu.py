@@ -96,6 +96,21 @@ def test_constitutive_forward_and_reverse_vs_oracle(hm, material):
     assert cosF > 0.99999
     assert abs(gmu.astype(np.float64).sum() - float(rmu)) < 1e-4 * (abs(float(rmu)) + 1e-6)
     assert abs(gla.astype(np.float64).sum() - float(rla)) < 1e-4 * (abs(float(rla)) + 1e-6)
+    if material == 2:
+        # the adjoint kernel's plastic fast path: the same chain carried out in the frame of the SVD
+        # (plastic_affine + constitutive_bwd_plastic, 8 matrix products instead of 21) against the generic path
+        # above and the fp64 oracle
+        fast = {k: np.empty((n, 3, 3), np.float32) for k in ("affine", "gC", "gF")}
+        fmu = np.empty(n, np.float32); fla = np.empty(n, np.float32)
+        hm.hm_constitutive_plastic(n, fp(consts), fp(Cm), fp(F), C.c_float(mu_s), C.c_float(la_s), fp(h), fp(gA), fp(gF2),
+                                   fp(fast["affine"]), fp(fast["gC"]), fp(fast["gF"]), fp(fmu), fp(fla))
+        assert rel(fast["affine"], aff) < 2e-5
+        assert rel(fast["gC"], rC) < 1e-4
+        assert rel(fast["gF"], rF) < 2e-3
+        assert np.abs(fast["gF"] - outs["gF"]).max() < 2e-4 * np.abs(outs["gF"]).max()      # fast vs generic path
+        assert np.abs(fast["gC"] - outs["gC"]).max() < 2e-5 * np.abs(outs["gC"]).max()
+        assert abs(fmu.astype(np.float64).sum() - float(rmu)) < 1e-4 * (abs(float(rmu)) + 1e-6)
+        assert abs(fla.astype(np.float64).sum() - float(rla)) < 1e-4 * (abs(float(rla)) + 1e-6)
 
 
 @pytest.mark.parametrize("kind,pos_control", [(0, 0), (1, 0), (0, 1)])
