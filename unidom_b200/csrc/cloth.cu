@@ -78,10 +78,9 @@ __device__ __forceinline__ float norm_div(float g, float n, float rn, float ms, 
   const float q = isinf(rn) ? g / n : div_rn(g, n, rn);
   return div_rn(nan0(q), ms, rms);
 }
-__device__ __forceinline__ float nan0(float a) {
-  if (a != a) return 0.f;
-  if (isinf(a)) return a > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
-  return a;
+__device__ __forceinline__ float nan0(float a) {   // jnp.nan_to_num: NaN -> 0, +-inf -> +-FLT_MAX
+  const float c = fminf(fmaxf(a, -3.4028234663852886e38f), 3.4028234663852886e38f);
+  return a == a ? c : 0.f;
 }
 
 // One env = one CTA (CLUSTER = false) or one thread-block cluster (CLUSTER = true).
@@ -128,10 +127,13 @@ __device__ __forceinline__ void team_sum2(float& a, float& b, float* red, float*
     red[32 + wid] = b;
   }
   __syncthreads();
-  float sa = 0.f, sb = 0.f;
-  for (int w = 0; w < nw; ++w) {
-    sa += red[w];
-    sb += red[32 + w];
+  // second stage: every warp folds the <= 32 warp partials with the same xor butterfly, so all threads hold the
+  // bit-identical total (fixed tree: deterministic) after 2 loads + 10 shuffles instead of 2 * nw loads
+  float sa = lane < nw ? red[lane] : 0.f, sb = lane < nw ? red[32 + lane] : 0.f;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, off);
+    sb += __shfl_xor_sync(0xffffffffu, sb, off);
   }
   if (CLUSTER) {
     cg::cluster_group cl = cg::this_cluster();
