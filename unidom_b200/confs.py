@@ -88,6 +88,20 @@ def build_shape_elasto_plastic(sim, density=3.0):
     return sim.reset_jax(state)
 
 
+def build_whip_rope(sim, density=2.75):
+    """reset() of envs/whip_rope_env.py:119-137 before its random xz shift: a 0.38-long rope rotated by pi/2 about y and
+    a 0.02 box gripper (position control) at [0.5, 0.01, 0.3]; 67 particles at the shipped density."""
+    import math
+
+    from .mpm_simulator import create_primitive
+    conf = sim.conf
+    state = sim.add_box(conf=conf, state=None, hardness=1.0, size=[0.38, 0.006, 0.006], init_pos=[0.5, 0.01, 0.5],
+                        z_rotation_angle=math.pi / 2, material=1, density=density)
+    state.primitives.append(create_primitive(conf, friction=0.1, softness=666, color=[0.5, 0.5, 0.5],
+                                             size=[0.02, 0.02, 0.02], init_pos=[0.5, 0.01, 0.3]))
+    return sim.reset_jax(state)
+
+
 class ClothConf:
     """envs/fold_cloth3_env.py:18-37 (shared by fold_cloth1/3, unfold_cloth1/3; fold_cloth1_para randomises
     `stiffness` per env, fold_cloth1_para_env.py:15-33)."""

@@ -274,3 +274,36 @@ class ShapeElastoPlasticEnv(MPMEnv):
         push = torch.cat([push[..., 0:1], torch.zeros_like(push[..., 1:2]), push[..., 2:3]], dim=-1)
         sub = torch.cat([push, torch.zeros_like(push)], dim=-1)
         return sub, state._replace(primitives=prims)
+
+
+class WhipRopeEnv(MPMEnv):
+    """core/envs/whip_rope_env.py:78-137: an elastic rope whipped by a position-controlled box gripper; ONE sub-action
+    of conf.steps (70) substeps per env step; BASELINE configs[4] "whip_rope long horizon" (max_steps 70)."""
+
+    def __init__(self, conf, batch_size, max_steps=70, density=2.75, **kw):
+        kw.setdefault("use_position_control", True)
+        super().__init__(conf, batch_size, max_steps, focus_computation=True, **kw)
+        from . import confs
+        self.state = confs.build_whip_rope(self.simulator, density=density)
+        self.init_state = self.state
+        self._rng = np.random.RandomState(getattr(conf, "seed", 1))
+
+    def process_pre_step_actions(self, actions, shift):
+        return actions                                                               # :88-90
+
+    def get_primitive_actions(self, actions, state):
+        a = (actions + 1e-12) / 50.0                                                 # :107-113
+        a = torch.cat([a[:, :3], torch.zeros_like(a[:, 3:])], dim=1)
+        return a[:, None, :], state
+
+    def auto_reset(self, init_state, state):
+        """:92-104: the initial scene with a fresh N(0, 0.02^2) xz shift per env on rope and gripper.  The reference
+        draws it from threefry (not reproducible here): a seeded NumPy stream stands in."""
+        B = self.batch_size
+        sh = torch.from_numpy(self._rng.randn(B, 2).astype(np.float32) * 0.02).to(self.device)
+        shift = torch.stack([sh[:, 0], torch.zeros_like(sh[:, 0]), sh[:, 1]], dim=1)
+        p = init_state.primitives[0]
+        pos = p.position.clone()
+        pos[:, 0] = pos[:, 0] + shift
+        prims = [p._replace(position=pos)] + list(init_state.primitives[1:])
+        return init_state._replace(x=init_state.x + shift[:, None, :], primitives=prims)
