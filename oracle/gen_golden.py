@@ -389,42 +389,56 @@ def mpm_env_case(name, B, density, seed):
     print(f"wrote {path}: n={n} B={B} reward={out['reward']} |g_actions|max={np.abs(out['g_actions']).max():.3e}")
 
 
-def whip_env_case(name, B, seed):
-    """Env level for the position-controlled rope: the reference's WhipRopeEnv (envs/whip_rope_env.py: reset with the
-    random xz shift of auto_reset, get_primitive_actions = actions / 50 with zero rotation, ONE sub-action of 70
-    substeps under position control, focus shift, reward e^(-10 l2) against goals/whip_rope/goal.npy) at its shipped
-    size (67 particles): two consecutive step_diff calls, gradient of the summed rewards w.r.t. both actions."""
+def task_env_case(name, B, seed, steps=2):
+    """Env level for the remaining shipped MPM tasks, at their shipped sizes, run from the reference's own env classes:
+      whip  envs/whip_rope_env.py  WhipRopeEnv: 67 elastic particles, position-controlled box gripper, get_primitive_actions
+            = actions / 50 with zero rotation, ONE sub-action of 70 substeps per env step;
+      pour  envs/pour_water_env.py PourWaterEnv: 702 liquid particles, two bowl colliders (container SDF),
+            get_primitive_actions = [actions / 500, 0 for the second bowl], one sub-action of 23 substeps.
+    reset() (with the random xz shift of auto_reset), `steps` consecutive step_diff calls (focus shift, reward
+    e^(-10 l2) against goals/<task>/goal.npy), gradient of the summed rewards w.r.t. all actions."""
     sys.path.insert(0, os.path.join(HERE, "jaxshim"))
     import stubs
     stubs.install()
     import torch
     import jax
-    from daxbench.core.envs import whip_rope_env as wre
     rng = np.random.RandomState(seed)
-    env = wre.WhipRopeEnv(batch_size=B, seed=1)
+    if name == "whip":
+        from daxbench.core.envs import whip_rope_env as mod
+        env = mod.WhipRopeEnv(batch_size=B, seed=1)
+        acts = np.concatenate([rng.uniform(-0.8, 0.8, (steps, B, 3)), np.zeros((steps, B, 3))], axis=-1).astype(np.float32)
+        acts[:, :, 1] = np.abs(acts[:, :, 1])                       # lift, do not push into the ground
+    else:
+        from daxbench.core.envs import pour_water_env as mod
+        # rendering only (writes a .ply through the `sdf` + trimesh + pyrender stack, stubbed here): not on the path
+        mod.PourWaterEnv.create_mesh_for_render = lambda self, size: None
+        env = mod.PourWaterEnv(batch_size=B, seed=1)
+        acts = rng.uniform(-1.0, 1.0, (steps, B, 6)).astype(np.float32)
+        acts[:, :, 3:] *= 20.0                                      # tilt the bowl
     obs, st = env.reset(env.simulator.key_global)
-    acts = np.concatenate([rng.uniform(-0.8, 0.8, (2, B, 3)), np.zeros((2, B, 3))], axis=-1).astype(np.float32)
-    acts[:, :, 1] = np.abs(acts[:, :, 1])                       # lift, do not push into the ground
-    prim = st.primitives[0]
     out = {"goal": np.asarray(env.goal), "actions": acts, "in_x": np.asarray(st.x),
-           "in_prim_pos": np.asarray(prim.position), "in_prim_rot": np.asarray(prim.rotation),
            "material": np.asarray(env.simulator.material).astype(np.int32), "h": np.asarray(env.simulator.h).astype(np.float32)}
+    for q, prim in enumerate(st.primitives):
+        out[f"in_prim{q}_pos"] = np.asarray(prim.position)
+        out[f"in_prim{q}_rot"] = np.asarray(prim.rotation)
     a = torch.from_numpy(acts).requires_grad_(True)
     total, s = 0, st
-    for t in range(2):
+    for t in range(steps):
         obs, reward, done, info = env.step_diff(jax.Array(a[t]), s)
         s = info["state"]
         total = total + reward.t.sum()
         out[f"reward{t}"] = reward.t.detach().numpy()
         out[f"x{t}"] = np.asarray(s.x.t.detach())
         out[f"v{t}"] = np.asarray(s.v.t.detach())
-        out[f"prim_pos{t}"] = np.asarray(s.primitives[0].position.t.detach())
+        for q, prim in enumerate(s.primitives):
+            out[f"prim{q}_pos{t}"] = np.asarray(prim.position.t.detach())
+            out[f"prim{q}_rot{t}"] = np.asarray(prim.rotation.t.detach())
     (ga,) = torch.autograd.grad(total, [a])
     out["g_actions"] = ga.numpy()
     out["obs"] = np.asarray(obs.t.detach())
     path = os.path.join(GOLD, f"ref_mpmenv_{name}.npz")
     np.savez_compressed(path, **out)
-    print(f"wrote {path}: n={st.x.shape[1]} B={B} rewards={out['reward0']} {out['reward1']} "
+    print(f"wrote {path}: n={st.x.shape[1]} B={B} rewards={[out[f'reward{t}'] for t in range(steps)]} "
           f"|g_actions|max={np.abs(out['g_actions']).max():.3e}")
 
 
@@ -455,7 +469,8 @@ def main():
         "cloth_w4_contact": lambda: cloth_case(mods, "w4_contact", False, 28, False, window=4, contact=True),
     }
     cases["mpmenv_push"] = lambda: mpm_env_case("push", 2, 1.3, 41)
-    cases["mpmenv_whip"] = lambda: whip_env_case("whip", 2, 43)
+    cases["mpmenv_whip"] = lambda: task_env_case("whip", 2, 43)
+    cases["mpmenv_pour"] = lambda: task_env_case("pour", 2, 44)
     cases["clothenv_ep1"] = lambda: cloth_env_case("ep1", 1, 2, 31)
     # BASELINE.json configs[0]: fold_cloth3 APG ep_len=3 num_envs=4 (reference states + policy gradient; ~20 min here)
     cases["clothenv_ep3"] = lambda: cloth_env_case("ep3", 3, 4, 0)

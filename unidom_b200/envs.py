@@ -307,3 +307,44 @@ class WhipRopeEnv(MPMEnv):
         pos[:, 0] = pos[:, 0] + shift
         prims = [p._replace(position=pos)] + list(init_state.primitives[1:])
         return init_state._replace(x=init_state.x + shift[:, None, :], primitives=prims)
+
+
+class PourWaterEnv(MPMEnv):
+    """core/envs/pour_water_env.py:66-137: 702 liquid particles in a bowl (cut hollow sphere, container SDF) that the
+    6-vector action translates / tilts, a second bowl on the ground; one sub-action of conf.steps (23) substeps per env
+    step; BASELINE configs[2] "pour_water".  `points`: the liquid's particle positions (the reference draws them
+    with jax.random.uniform, mpm_simulator.py:89; default = a seeded NumPy draw of the same box)."""
+
+    def __init__(self, conf, batch_size, max_steps=100, points=None, **kw):
+        super().__init__(conf, batch_size, max_steps, focus_computation=True, **kw)
+        from .mpm_simulator import create_primitive
+        sim = self.simulator
+        if points is None:
+            state = sim.add_box(conf=conf, state=None, hardness=1, size=[0.07, 0.07, 0.07], init_pos=[0.5, 0.2, 0.5],
+                                z_rotation_angle=0, material=0, density=4)
+        else:
+            state = sim.add_box_from_points(conf, None, torch.as_tensor(np.asarray(points), dtype=torch.float32),
+                                            hardness=1, material=0)
+        for size, pos in (([0.09, 0.0, 0.008], [0.5, 0.2, 0.5]), ([0.08, 0.0, 0.008], [0.5, 0.06, 0.3])):   # :123-129
+            state.primitives.append(create_primitive(conf, friction=0.1, softness=666, color=[0.5, 0.5, 0.5], size=size,
+                                                     init_pos=pos))
+        self.state = sim.reset_jax(state)
+        self.init_state = self.state
+        self._rng = np.random.RandomState(getattr(conf, "seed", 1))
+
+    def process_pre_step_actions(self, actions, shift):
+        return actions                                                               # :92-94
+
+    def get_primitive_actions(self, actions, state):
+        a = torch.cat([actions[:, :3] / 500.0, actions[:, 3:6] / 500.0, torch.zeros_like(actions)], dim=1) + 1e-12   # :79-88
+        a = torch.cat([a[:, 0:1], torch.zeros_like(a[:, 1:2]), a[:, 2:]], dim=1)
+        return a[:, None, :], state
+
+    def auto_reset(self, init_state, state):
+        """:96-105: bowl 0 back to [0.5, 0.2, 0.5] plus an N(0, 0.02^2) xz shift per env (seeded NumPy stream)."""
+        B = self.batch_size
+        sh = torch.from_numpy(self._rng.randn(B, 2).astype(np.float32) * 0.02).to(self.device)
+        p = init_state.primitives[0]
+        pos = p.position.clone()
+        pos[:, 0] = torch.tensor([0.5, 0.2, 0.5], device=self.device) + torch.stack([sh[:, 0], torch.zeros_like(sh[:, 0]), sh[:, 1]], 1)
+        return init_state._replace(primitives=[p._replace(position=pos)] + list(init_state.primitives[1:]))
