@@ -229,6 +229,9 @@ uint64_t ud_launch_count(int reset);
  *   "sort"      1: per-frame binning by grid block (default) / 0: particles stay in input order (ud_mpm_sort_bins unaffected)
  *   "stage"     1: P2G staged in shared memory, one vector RED per (cell segment, node) (default) /
  *               0: 27 vector REDs per particle straight to the grid in HBM
+ *   "mark"      2: P2G marks the 4x4x4 grid blocks it scatters into from the corner nodes of every cell segment
+ *               (default) / 1: from all 27 nodes / 0: no marks (timing experiments only: the grid update then
+ *               visits nothing and the results are wrong)
  *   "cloth_cta_nodes"  cloth nodes per CTA (default and maximum 1024, multiple of 32); an env with more nodes runs
  *               on a thread-block cluster of ceil(n_nodes / value) <= 8 CTAs (tests force small cloths onto it)
  * Returns the previous value, or -1 for an unknown name. */

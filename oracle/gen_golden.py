@@ -389,10 +389,12 @@ def mpm_env_case(name, B, density, seed):
     print(f"wrote {path}: n={n} B={B} reward={out['reward']} |g_actions|max={np.abs(out['g_actions']).max():.3e}")
 
 
-def task_env_case(name, B, seed, steps=2):
+def task_env_case(name, B, seed, steps=2):  # noqa: C901
     """Env level for the remaining shipped MPM tasks, at their shipped sizes, run from the reference's own env classes:
       whip  envs/whip_rope_env.py  WhipRopeEnv: 67 elastic particles, position-controlled box gripper, get_primitive_actions
             = actions / 50 with zero rotation, ONE sub-action of 70 substeps per env step;
+      rope  envs/shape_rope_env.py ShapeRopeEnv: 582 plastic particles, box pusher, 30 sub-actions x 133 substeps per env
+            step, reset() followed by the reference's two random pushes (the fixture carries the pushed state);
       pour  envs/pour_water_env.py PourWaterEnv: 702 liquid particles, two bowl colliders (container SDF),
             get_primitive_actions = [actions / 500, 0 for the second bowl], one sub-action of 23 substeps.
     reset() (with the random xz shift of auto_reset), `steps` consecutive step_diff calls (focus shift, reward
@@ -403,7 +405,12 @@ def task_env_case(name, B, seed, steps=2):
     import torch
     import jax
     rng = np.random.RandomState(seed)
-    if name == "whip":
+    if name == "rope":
+        from daxbench.core.envs import shape_rope_env as mod
+        env = mod.ShapeRopeEnv(batch_size=B, seed=1)
+        np.random.seed(seed)                                        # reset() ends with two np.random pushes (:173)
+        acts = None
+    elif name == "whip":
         from daxbench.core.envs import whip_rope_env as mod
         env = mod.WhipRopeEnv(batch_size=B, seed=1)
         acts = np.concatenate([rng.uniform(-0.8, 0.8, (steps, B, 3)), np.zeros((steps, B, 3))], axis=-1).astype(np.float32)
@@ -416,7 +423,12 @@ def task_env_case(name, B, seed, steps=2):
         acts = rng.uniform(-1.0, 1.0, (steps, B, 6)).astype(np.float32)
         acts[:, :, 3:] *= 20.0                                      # tilt the bowl
     obs, st = env.reset(env.simulator.key_global)
+    if acts is None:                                                # push across the rope: start / end around its centroid
+        c = np.asarray(st.x).mean(1)
+        acts = np.stack([np.concatenate([c + [-0.05, 0, -0.04 * (1 + t)], c + [0.06, 0, 0.05]], axis=1)
+                         for t in range(steps)]).astype(np.float32)
     out = {"goal": np.asarray(env.goal), "actions": acts, "in_x": np.asarray(st.x),
+           "in_v": np.asarray(st.v), "in_C": np.asarray(st.C), "in_F": np.asarray(st.F), "in_J": np.asarray(st.J),
            "material": np.asarray(env.simulator.material).astype(np.int32), "h": np.asarray(env.simulator.h).astype(np.float32)}
     for q, prim in enumerate(st.primitives):
         out[f"in_prim{q}_pos"] = np.asarray(prim.position)
@@ -471,6 +483,7 @@ def main():
     cases["mpmenv_push"] = lambda: mpm_env_case("push", 2, 1.3, 41)
     cases["mpmenv_whip"] = lambda: task_env_case("whip", 2, 43)
     cases["mpmenv_pour"] = lambda: task_env_case("pour", 2, 44)
+    cases["mpmenv_rope"] = lambda: task_env_case("rope", 1, 45, steps=1)      # 3 990 substeps per env step: ~30 min here
     cases["clothenv_ep1"] = lambda: cloth_env_case("ep1", 1, 2, 31)
     # BASELINE.json configs[0]: fold_cloth3 APG ep_len=3 num_envs=4 (reference states + policy gradient; ~20 min here)
     cases["clothenv_ep3"] = lambda: cloth_env_case("ep3", 3, 4, 0)

@@ -19,7 +19,27 @@ __version__ = "0.0-shim"
 
 
 def jit(f, *a, **k):
-    return f
+    """No compilation, but the one observable thing jax.jit does to its inputs: NumPy arrays arrive as jax arrays
+    (float64 -> float32, int64 -> int32 with x64 disabled), e.g. shape_rope_env.py:129 feeds np actions to a jitted
+    step_diff that then uses `.at[]`."""
+    import functools
+
+    import numpy as _np
+
+    def conv(l):
+        if isinstance(l, _np.ndarray):
+            t = _torch.from_numpy(_np.ascontiguousarray(l))
+            if t.dtype == _torch.float64:
+                t = t.to(_torch.float32)
+            elif t.dtype == _torch.int64:
+                t = t.to(_torch.int32)
+            return _W(t)
+        return l
+
+    @functools.wraps(f)
+    def wrapped(*args, **kw):
+        return f(*[tree_util.tree_map(conv, x) for x in args], **{n: tree_util.tree_map(conv, x) for n, x in kw.items()})
+    return wrapped
 
 
 def _rebuild(tree):

@@ -129,3 +129,19 @@ def test_tshirt_env_step_on_clusters(built_lib):
         assert float((info["state"].x - state.x).abs().max()) > 1e-3          # the gripper moved the cloth
         outs.append((info["state"].x, reward, ga))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+@pytest.mark.gpu
+def test_unfold_task_reset_by_random_folds(built_lib):
+    """unfold_cloth3 (envs/unfold_cloth3_env.py): friction 3, reset = lattice + 3 random pick-and-place folds."""
+    from unidom_b200 import envs
+    conf = confs.UnfoldClothConf()
+    B = 3
+    env = envs.ClothEnv(conf, B, 15, confs.fold_cloth_mask(conf), goal=np.zeros((1, 3), np.float32))
+    _, st = env.reset(shift_xz=np.zeros(2, np.float32))
+    assert float(st.mu[0]) == 3.0
+    folded = env.random_fold(st, step=3, rng=np.random.RandomState(5))
+    assert int(folded.cur_step[0]) == 3 and torch.isfinite(folded.x).all()
+    assert float((folded.x - st.x).abs().max()) > 0.02                    # the cloth was folded
+    # x' = clip(x, 0, 1) + dt * clip(v, +-max_v) (cloth_simulator.py:328-329): at most dt * max_v = 0.004 outside the box
+    assert float(folded.x[..., 1].min()) >= -0.0041 and float(folded.x.max()) <= 1.0041

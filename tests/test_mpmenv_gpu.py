@@ -126,3 +126,37 @@ def test_pour_water_env_two_steps_vs_reference(built_lib):
     # two correct fp32 evaluations of the same formulas differ at this level ("Numerics")
     assert cs >= 0.999 and eg < 5e-3
     assert util.rel_err(obs, d["obs"]) < 2e-3
+
+
+def test_shape_rope_env_step_vs_reference(built_lib):
+    """The reference's ShapeRopeEnv (envs/shape_rope_env.py) at its shipped size (582 plastic particles, n_grid 128,
+    30 sub-actions x 133 substeps = 3 990 substeps per env step) from the state its reset() leaves after the two random
+    pushes: one env step, reward and action gradient."""
+    path = os.path.join(util.GOLD, "ref_mpmenv_rope.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    from unidom_b200 import confs, envs
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in np.load(path).items()}
+    B = d["in_x"].shape[0]
+    conf = confs.shape_rope_conf()
+    env = envs.ShapeRopeEnv(conf, B, goal=d["goal"].numpy())
+    st = env.state
+    assert st.x.shape[1] == d["in_x"].shape[1] == 582
+    assert torch.equal(env.simulator.material.cpu(), d["material"]) and torch.equal(env.simulator.h.cpu(), d["h"])
+    p = st.primitives[0]._replace(position=d["in_prim0_pos"].to(env.device), rotation=d["in_prim0_rot"].to(env.device))
+    st = st._replace(primitives=[p], **{k: d[f"in_{k}"].to(env.device) for k in ("x", "v", "C", "F", "J")})
+    a = d["actions"].to(env.device).requires_grad_(True)
+    obs, reward, done, info = env.step_diff(a[0], st)
+    s = info["state"]
+    (ga,) = torch.autograd.grad(reward.sum(), [a])
+    ex, er = util.rel_err(s.x, d["x0"]), util.rel_err(reward, d["reward0"])
+    print(f"rope env: x rel {ex:.3e} reward {reward.tolist()} ref {d['reward0'].tolist()} rel {er:.3e}")
+    assert ex < 1e-4 and er < 1e-4
+    assert util.rel_err(s.primitives[0].position, d["prim0_pos0"]) < 1e-5
+    cs, eg = util.cosine(ga, d["g_actions"]), util.rel_err(ga, d["g_actions"])
+    print(f"rope env action gradient cos {cs:.6f} rel {eg:.3e}  ours {ga.tolist()} ref {d['g_actions'].tolist()}")
+    assert cs >= 0.999 and eg < 1e-3
+    # the reference's own reset continues with random pushes: they run and keep the rope on the table
+    env.state = s
+    s2 = env.random_push(step=1, rng=np.random.RandomState(0))
+    assert torch.isfinite(s2.x).all() and float(s2.x[..., 1].min()) > -1e-3

@@ -88,6 +88,18 @@ def build_shape_elasto_plastic(sim, density=3.0):
     return sim.reset_jax(state)
 
 
+def build_shape_rope(sim, density=3):
+    """reset() of envs/shape_rope_env.py:154-171 before its random pushes: a 0.25 x 0.006 x 0.006 plastic rope (582
+    particles at density 3 = goals/shape_rope/goal.npy) and the box pusher."""
+    from .mpm_simulator import create_primitive
+    conf = sim.conf
+    state = sim.add_box(conf=conf, state=None, hardness=1.0, size=[0.25, 0.006, 0.006], init_pos=[0.5, 0.01, 0.5],
+                        z_rotation_angle=0, material=2, density=density)
+    state.primitives.append(create_primitive(conf, friction=0.1, softness=666, color=[0.5, 0.5, 0.5],
+                                             size=[0.015, 0.06, 0.015], init_pos=[0.5, 0.01, 0.45]))
+    return sim.reset_jax(state)
+
+
 def build_whip_rope(sim, density=2.75):
     """reset() of envs/whip_rope_env.py:119-137 before its random xz shift: a 0.38-long rope rotated by pi/2 about y and
     a 0.02 box gripper (position control) at [0.5, 0.01, 0.3]; 67 particles at the shipped density."""
@@ -124,6 +136,13 @@ class ClothConf:
     @property
     def size(self):
         return int(self.N / 5.0)
+
+
+class UnfoldClothConf(ClothConf):
+    """envs/unfold_cloth3_env.py:17-35 (unfold_cloth1 alike): the fold_cloth scene with friction mu = 3, max_steps 15;
+    reset = lattice + N(0, 1e-4^2) noise + 3 random pick-and-place folds (ClothEnv.random_fold)."""
+    mu = 3
+    task = "unfold_cloth3"
 
 
 class FoldTshirtConf(ClothConf):

@@ -145,6 +145,21 @@ class ClothEnv:
         st = st._replace(x=x)
         return self.get_obs(st), st
 
+    def random_fold(self, state: ClothState, step=3, rng=None) -> ClothState:
+        """unfold_cloth3_env.py:57-70: `step` pick-and-place actions between two random nodes of each env (the
+        reference draws them from np.random), without gradients: the start state of the unfold tasks."""
+        rng = rng or np.random
+        B, P = state.x.shape[:2]
+        bidx = torch.arange(B, device=self.device)
+        for _ in range(step):
+            st = torch.from_numpy(rng.randint(0, P, size=(B,))).to(self.device)
+            ed = torch.from_numpy(rng.randint(0, P, size=(B,))).to(self.device)
+            actions = torch.cat([state.x[bidx, st], state.x[bidx, ed]], dim=-1)
+            with torch.no_grad():
+                _, _, _, info = self.step_diff(actions, state)
+            state = info["state"]
+        return state
+
     def step_diff(self, actions: torch.Tensor, state: ClothState):
         """cloth_env.py:204-231: 40 sub-actions x 50 substeps through the simulator, reward
         e^(-10 chamfer) (+ e^(-contact)) * 0.99^cur_step."""
@@ -250,11 +265,16 @@ class ShapeElastoPlasticEnv(MPMEnv):
     """core/envs/shape_elasto_plastic.py:56-157 (class ShapeRopeEnv there): a box pusher starts at `start`, moves
     towards `end` by at most 0.1 in 20 sub-actions (:95-123); BASELINE configs[1] "push_plasticine"."""
 
+    MAX_PUSH, N_SUB = 0.1, 20            # :91, :99
+
     def __init__(self, conf, batch_size, max_steps=6, density=3.0, **kw):
         super().__init__(conf, batch_size, max_steps, focus_computation=True, **kw)
-        from . import confs
-        self.state = confs.build_shape_elasto_plastic(self.simulator, density=density)
+        self.state = self._build(density)
         self.init_state = self.state
+
+    def _build(self, density):
+        from . import confs
+        return confs.build_shape_elasto_plastic(self.simulator, density=density)
 
     def process_pre_step_actions(self, actions, shift):
         return torch.cat([actions[:, 0:3] + shift, actions[:, 3:] + shift], dim=1)      # :88-92
@@ -266,14 +286,43 @@ class ShapeElastoPlasticEnv(MPMEnv):
         end = torch.cat([end[:, 0:1], y, end[:, 2:3]], dim=1)
         norm = torch.sqrt(((end - start) ** 2).sum(-1, keepdim=True)) + 1e-8
         vec = (end - start) / norm
-        end = start + vec * torch.minimum(torch.maximum(norm, torch.zeros_like(norm)), torch.full_like(norm, 0.1))
+        end = start + vec * torch.minimum(torch.maximum(norm, torch.zeros_like(norm)), torch.full_like(norm, self.MAX_PUSH))
         p = state.primitives[0]
         position = torch.cat([start[:, None, :], p.position[:, 1:]], dim=1)
         prims = [p._replace(position=position)] + list(state.primitives[1:])
-        push = (end - start)[:, None, :].expand(-1, 20, -1) / 20
+        push = (end - start)[:, None, :].expand(-1, self.N_SUB, -1) / self.N_SUB
         push = torch.cat([push[..., 0:1], torch.zeros_like(push[..., 1:2]), push[..., 2:3]], dim=-1)
         sub = torch.cat([push, torch.zeros_like(push)], dim=-1)
         return sub, state._replace(primitives=prims)
+
+
+class ShapeRopeEnv(ShapeElastoPlasticEnv):
+    """core/envs/shape_rope_env.py:70-174 (and shape_rope_hard_env.py, which only pushes the rope around 8 more times
+    at reset): a thin plastic rope (582 particles) pushed by at most 0.3 in 30 sub-actions of conf.steps (133) substeps.
+    The reference's reset ends with random pushes drawn from np.random (:124-131,173): call `random_push` for the same."""
+
+    MAX_PUSH, N_SUB = 0.3, 30            # :103, :42,109
+
+    def _build(self, density):
+        from . import confs
+        return confs.build_shape_rope(self.simulator, density=density)
+
+    def auto_reset(self, init_state, state):
+        return state                                                                 # :83-86 ("TODO" in the reference)
+
+    def random_push(self, step=2, radius=0.05, rng=None):
+        rng = rng or np.random
+        for _ in range(step):
+            pc = self.state.x[0].detach().cpu().numpy()
+            ids = rng.randint(0, pc.shape[0], self.batch_size)
+            ang = rng.random((self.batch_size,)) * np.pi * 2
+            off = np.stack([np.cos(ang) * radius, np.zeros_like(ang), np.sin(ang) * radius], axis=1)
+            acts = np.concatenate([pc[ids] - off, pc[ids] + off], axis=1).astype(np.float32)
+            acts[:, 1] = 0
+            with torch.no_grad():
+                _, _, _, info = self.step_diff(torch.from_numpy(acts).to(self.device), self.state)
+            self.state = info["state"]
+        return self.state
 
 
 class WhipRopeEnv(MPMEnv):
