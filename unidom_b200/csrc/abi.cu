@@ -325,7 +325,7 @@ static void mpm_reverse_pass(const MpmConst& k, const ud_mpm_state* in, const fl
     if (f < k.S - 1) launch_grid_clear(k, ws.ggrid, f + 1, ws, st);
     launch_g2p_bwd(k, s_in, ws.grid_out + BG * f, ws, st);
     launch_grid_bwd(k, ws.grid_raw + BG * f, f, in, ws, st);
-    launch_p2g_bwd(k, s_in, ws.svd_s + (size_t)SV_NCOMP * k.N * f, in->mu, in->lamda, ws, st);
+    launch_p2g_bwd(k, s_in, ws.svd_s + (size_t)SV_NCOMP * k.N * f, in->mu, in->lamda, f == 0, ws, st);
   }
   launch_fk_bwd(k, in, action, gout, ws, st);
   launch_finish_bwd(k, in, gout, gin, action, gaction, ws, st);

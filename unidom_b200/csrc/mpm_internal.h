@@ -100,7 +100,7 @@ void launch_gather_cot(const MpmConst& k, const ud_mpm_state* gout, const MpmWs&
 void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
                     cudaStream_t st);
 void launch_p2g_bwd(const MpmConst& k, const float* ps_in, const float* svd_in, const float* mu_s,
-                    const float* la_s, const MpmWs& ws, cudaStream_t st);
+                    const float* la_s, bool first_substep, const MpmWs& ws, cudaStream_t st);
 void launch_finish_bwd(const MpmConst& k, const ud_mpm_state* in, const ud_mpm_state* gout,
                        ud_mpm_state* gin, const float* action, float* gaction, const MpmWs& ws,
                        cudaStream_t st);

@@ -818,10 +818,13 @@ __global__ void __launch_bounds__(UD_BLOCK, 4)
 k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__ svd_in,
           const float4* __restrict__ ggrid, float* __restrict__ gs, const float* __restrict__ mu_s,
           const float* __restrict__ la_s, const int32_t* __restrict__ mat_s, const float* __restrict__ h_s,
-          float* __restrict__ g_scal) {
+          float* __restrict__ g_scal, float* __restrict__ norm2) {
+  // norm2 != nullptr on the step's first substep (the last one reversed): the cotangents written here are the
+  // step's input cotangents, so norm_grad_state's nan_to_num + per-env sum of squares (mpm_simulator.py:389-408)
+  // happen on the way out instead of in a separate pass over the 24 components
   UD_PARTICLE_INDEX(k, env, g);
   const size_t N = k.N;
-  float gmu = 0.f, gla = 0.f;
+  float gmu = 0.f, gla = 0.f, gn2 = 0.f;
   if (live_) {
     // Phase 1: everything the 27-node gather needs is the stencil, A = dx * affine and u0.  The matrices that
     // produce them (C, F, U, s, Vt, F1, F2, D: ~80 registers) die here and are loaded again (L2 hits) for the
@@ -952,10 +955,30 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
       constitutive_post(k, C, o);
       constitutive_bwd(k, C, F, o, gA, gF2out, gC, gF, gmu, gla);
     }
+    float ox[3], ov[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      gs[(PS_X + d) * N + g] = gx_in[d] + k.inv_dx * gfx[d];
-      gs[(PS_V + d) * N + g] = k.p_mass * S[d];
+      ox[d] = gx_in[d] + k.inv_dx * gfx[d];
+      ov[d] = k.p_mass * S[d];
+    }
+    if (norm2) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        ox[d] = nan_to_num(ox[d]);
+        ov[d] = nan_to_num(ov[d]);
+        gn2 += ox[d] * ox[d] + ov[d] * ov[d];
+      }
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        gC.m[c] = nan_to_num(gC.m[c]);
+        gF.m[c] = nan_to_num(gF.m[c]);
+        gn2 += gC.m[c] * gC.m[c] + gF.m[c] * gF.m[c];
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      gs[(PS_X + d) * N + g] = ox[d];
+      gs[(PS_V + d) * N + g] = ov[d];
     }
 #pragma unroll
     for (int c = 0; c < 9; ++c) gs[(PS_C + c) * N + g] = gC.m[c];
@@ -967,60 +990,42 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
   for (int off = 16; off > 0; off >>= 1) {
     gmu += __shfl_down_sync(0xffffffffu, gmu, off);
     gla += __shfl_down_sync(0xffffffffu, gla, off);
+    gn2 += __shfl_down_sync(0xffffffffu, gn2, off);
   }
-  __shared__ float smu[UD_BLOCK / 32], sla[UD_BLOCK / 32];
+  __shared__ float smu[UD_BLOCK / 32], sla[UD_BLOCK / 32], sn2[UD_BLOCK / 32];
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) {
     smu[wid] = gmu;
     sla[wid] = gla;
+    sn2[wid] = gn2;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float a = 0.f, b = 0.f;
+    float a = 0.f, b = 0.f, c = 0.f;
     for (int i = 0; i < UD_BLOCK / 32; ++i) {
       a += smu[i];
       b += sla[i];
+      c += sn2[i];
     }
     atomicAdd(&g_scal[env * GS_STRIDE + GS_MU], a);
     atomicAdd(&g_scal[env * GS_STRIDE + GS_LAMDA], b);
+    if (norm2) atomicAdd(&norm2[env * 2], c);
   }
 }
 
 void launch_p2g_bwd(const MpmConst& k, const float* ps_in, const float* svd_in, const float* mu_s,
-                    const float* la_s, const MpmWs& ws, cudaStream_t st) {
+                    const float* la_s, bool first_substep, const MpmWs& ws, cudaStream_t st) {
   KScope ks_(KC_P2G_BWD, st);
+  if (first_substep) cudaMemsetAsync(ws.norm2, 0, 4 * (size_t)k.B * 2, st);
   k_p2g_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, svd_in, ws.ggrid, ws.gs, mu_s, la_s, ws.mat_s,
-                                                     ws.h_s, ws.g_scal);
+                                                     ws.h_s, ws.g_scal, first_substep ? ws.norm2 : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
 // norm_grad_state / norm_grad backward (mpm_simulator.py:389-408): nan_to_num every cotangent leaf,
-// per-env global L2 norm over ALL leaves of the state, divide when the norm is >= 1.
+// per-env global L2 norm over ALL leaves of the state, divide when the norm is >= 1.  The particle leaves are scrubbed
+// and squared by the last k_p2g_bwd of the step (its `norm2` argument); the small leaves follow here.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_norm_particles(MpmConst k, float* __restrict__ gs, float* __restrict__ norm2) {
-  UD_PARTICLE_INDEX(k, env, g);
-  const size_t N = k.N;
-  float acc = 0.f;
-  if (live_) {
-    for (int c = 0; c < PS_NCOMP; ++c) {
-      float t = nan_to_num(gs[c * N + g]);
-      gs[c * N + g] = t;
-      acc += t * t;
-    }
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-  __shared__ float sh[8];
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) sh[wid] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float a = 0.f;
-    for (int i = 0; i < (blockDim.x >> 5); ++i) a += sh[i];
-    atomicAdd(&norm2[env * 2], a);
-  }
-}
-
 // one thread per env: small leaves (per-env scalars, primitive leaves, action).  Adds pass-through
 // output cotangents, scrubs, accumulates the norms and stores the scrubbed values back.
 __global__ void k_norm_small(MpmConst k, ud_mpm_state gout, float* __restrict__ g_scal,
@@ -1131,8 +1136,7 @@ void launch_finish_bwd(const MpmConst& k, const ud_mpm_state* in, const ud_mpm_s
   KScope ks_(KC_FINISH_BWD, st, 5);
   (void)in;
   (void)action;
-  cudaMemsetAsync(ws.norm2, 0, 4 * (size_t)k.B * 2, st);
-  k_norm_particles<<<pgrid(k, 256), 256, 0, st>>>(k, ws.gs, ws.norm2);
+  // the particle part of the norm (and the nan_to_num of the particle cotangents) was done by the last k_p2g_bwd
   k_norm_small<<<cdiv(k.B, 64), 64, 0, st>>>(k, *gout, ws.g_scal, ws.g_prim_in, ws.g_act, ws.norm2);
   k_unsort_cot<<<pgrid(k, 256), 256, 0, st>>>(k, ws.gs, ws.perm, ws.norm2, gin->x, gin->v, gin->C, gin->F,
                                               gin->J);
