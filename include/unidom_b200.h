@@ -218,6 +218,15 @@ int ud_chamfer_bwd(const float* x, const float* y, int32_t B, int32_t P, int32_t
 int ud_l2_fwd(const float* x, const float* y, int32_t B, int32_t P, float* out, void* stream);
 int ud_l2_bwd(const float* x, const float* y, int32_t B, int32_t P, const float* gout, float* gx, void* stream);
 
+/* APG update on the flat fp32 policy-gradient buffer (DaXBench/daxbench/algorithms/apg/apg.py:233-240, 260-267).
+ * ud_apg_scrub_clip: grad <- nan_to_num(grad); norm = ||grad||; grad <- norm < max ? grad : (grad / norm) * max, in
+ *   place, per rank, BEFORE the mean over ranks; *sumsq (device, 1 float) receives norm^2 (the `grad_norm` metric).
+ * The caller all-reduces (SUM) grad over the ranks, then
+ * ud_adam_step: g = grad / world_size; optax.adam(lr, b1, b2, eps) step number t >= 1 on params with moments m, v. */
+int ud_apg_scrub_clip(float* grad, int64_t n, float max_grad_norm, float* sumsq, void* stream);
+int ud_adam_step(float* params, const float* grad, float* m, float* v, int64_t n, int32_t world_size, double lr,
+                 double b1, double b2, double eps, int32_t t, void* stream);
+
 /* ---- instrumentation (bench.py): launch counting and per-kernel-class CUDA-event timing ------
  * ud_launch_count: kernels + memsets enqueued by this library since the last reset (host counter).
  * ud_timing_enable(1): subsequent calls bracket every kernel class with cudaEvents on the call's

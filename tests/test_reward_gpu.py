@@ -95,3 +95,32 @@ def test_chamfer_full_size_translation_property(built_lib):
     gwant = 2 * shift[:3] / (3 * torch.sqrt((shift[:3] ** 2).mean(-1, keepdim=True))) / P
     assert util.rel_err(gx[:3].sum(1), gwant * P) < 1e-3
     assert torch.isnan(gx[3]).all() or float(gx[3].abs().max()) == 0.0   # coincident clouds: 0 * inf, as in the reference
+
+
+def test_apg_update_kernels_match_the_host_logic(built_lib):
+    """ud_apg_scrub_clip + ud_adam_step (apg.py:233-240, 260-267 on the flat buffer) against the torch host logic that
+    the gloo CPU tests pin: NaN/inf scrub, clip only when the norm exceeds max_grad_norm, three Adam steps."""
+    from unidom_b200 import apg
+    g = torch.Generator().manual_seed(3)
+    n = 925964                                            # the fold_cloth policy (SURVEY 8e)
+    for scale, max_norm in ((1e-4, 0.3), (5e-3, 0.3)):     # below / above the clip
+        grad = torch.randn(n, generator=g) * scale
+        grad[17] = float("nan")
+        grad[99] = float("inf") if scale < 1e-3 else 0.0   # inf -> FLT_MAX -> the norm overflows -> everything scaled to ~0
+        ref, ref_norm = apg.reduce_policy_gradient(grad.clone(), max_norm)
+        got, got_norm = apg.reduce_policy_gradient(grad.clone().cuda(), max_norm)
+        assert torch.isfinite(got).all()
+        if torch.isfinite(ref_norm):
+            assert abs(float(got_norm) - float(ref_norm)) < 1e-5 * float(ref_norm)
+            assert util.rel_err(got, ref) < 1e-6
+        else:
+            assert not torch.isfinite(got_norm) and float(got.abs().max()) == float(ref.abs().max()) == 0.0
+    params = torch.randn(n, generator=g)
+    o_cpu, o_gpu = apg.Adam(n, 1e-4, "cpu"), apg.Adam(n, 1e-4, "cuda")
+    p_cpu, p_gpu = params.clone(), params.clone().cuda()
+    for it in range(3):
+        grad = torch.randn(n, generator=g) * 1e-3
+        p_cpu = o_cpu.step(p_cpu, grad)
+        p_gpu = o_gpu.step(p_gpu, grad.cuda())
+    assert util.rel_err(p_gpu, p_cpu) < 1e-7 and float((p_gpu.cpu() - params).abs().max()) > 1e-5
+    assert util.rel_err(o_gpu.m, o_cpu.m) < 1e-6 and util.rel_err(o_gpu.v, o_cpu.v) < 1e-6

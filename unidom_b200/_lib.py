@@ -101,6 +101,11 @@ def lib():
     L.ud_l2_fwd.argtypes = [_fp, _fp, i32, i32, _fp, _fp]
     L.ud_l2_bwd.restype = C.c_int
     L.ud_l2_bwd.argtypes = [_fp, _fp, i32, i32, _fp, _fp, _fp]
+    L.ud_apg_scrub_clip.restype = C.c_int
+    L.ud_apg_scrub_clip.argtypes = [_fp, C.c_int64, C.c_float, _fp, _fp]
+    L.ud_adam_step.restype = C.c_int
+    L.ud_adam_step.argtypes = [_fp, _fp, _fp, _fp, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
+                               C.c_int32, _fp]
     L.ud_mpm_sort_bins.restype = C.c_int
     L.ud_mpm_sort_bins.argtypes = [P(MpmParams), _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]
     if hasattr(L, "ud_cloth_step_fwd"):
@@ -131,7 +136,7 @@ EXPORTS = (
     "ud_mpm_sort_bins", "ud_mpm_num_keys",
     "ud_cloth_workspace_bytes", "ud_cloth_step_fwd", "ud_cloth_step_bwd", "ud_cloth_multi_ckpt_bytes",
     "ud_cloth_multi_workspace_bytes", "ud_cloth_multi_step_fwd", "ud_cloth_multi_step_bwd",
-    "ud_chamfer_residual_bytes", "ud_chamfer_fwd", "ud_chamfer_bwd", "ud_l2_fwd", "ud_l2_bwd",
+    "ud_chamfer_residual_bytes", "ud_chamfer_fwd", "ud_chamfer_bwd", "ud_l2_fwd", "ud_l2_bwd", "ud_apg_scrub_clip", "ud_adam_step",
     "ud_launch_count", "ud_timing_enable", "ud_timing_collect", "ud_tuning_set",
 )
 

@@ -88,9 +88,20 @@ def reduce_policy_gradient(flat_grad: torch.Tensor, max_grad_norm: float, group=
     """apg.py:233-235 + :260-267 on one flat buffer, in the reference's order:
     nan_to_num (per rank) -> clip to max_grad_norm by the per-rank global norm -> mean over ranks.
     Returns (reduced gradient, this rank's raw gradient norm = the `grad_norm` metric of :242)."""
-    g = torch.nan_to_num(flat_grad)
-    g_norm = torch.sqrt((g * g).sum())
-    g = torch.where(g_norm < max_grad_norm, g, (g / g_norm) * max_grad_norm)
+    if flat_grad.is_cuda:          # fused scrub + norm + clip (csrc/reward.cu); the collective below stays NCCL
+        import ctypes as C
+
+        from . import _lib
+        g = flat_grad.detach().to(torch.float32).contiguous().clone()
+        sumsq = torch.empty(1, dtype=torch.float32, device=g.device)
+        st = C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+        _lib.check(_lib.lib().ud_apg_scrub_clip(C.c_void_p(g.data_ptr()), g.numel(), float(max_grad_norm),
+                                                C.c_void_p(sumsq.data_ptr()), st), "ud_apg_scrub_clip")
+        g_norm = torch.sqrt(sumsq[0])
+    else:                          # host logic under the gloo CPU tests
+        g = torch.nan_to_num(flat_grad)
+        g_norm = torch.sqrt((g * g).sum())
+        g = torch.where(g_norm < max_grad_norm, g, (g / g_norm) * max_grad_norm)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)       # one collective per iteration
         g = g / dist.get_world_size(group)
@@ -108,6 +119,17 @@ class Adam:
 
     def step(self, flat_params: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
         self.t += 1
+        if flat_params.is_cuda:    # one fused pass (csrc/reward.cu k_adam_step), same arithmetic order as below
+            import ctypes as C
+
+            from . import _lib
+            p = flat_params.detach().to(torch.float32).contiguous().clone()
+            g = g.detach().to(torch.float32).contiguous()
+            ptr = lambda t: C.c_void_p(t.data_ptr())       # noqa: E731
+            st = C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
+            _lib.check(_lib.lib().ud_adam_step(ptr(p), ptr(g), ptr(self.m), ptr(self.v), p.numel(), 1, self.lr, self.b1,
+                                               self.b2, self.eps, self.t, st), "ud_adam_step")
+            return p
         self.m = self.b1 * self.m + (1 - self.b1) * g
         self.v = self.b2 * self.v + (1 - self.b2) * g * g
         mhat = self.m / (1 - self.b1 ** self.t)

@@ -232,3 +232,79 @@ int ud_l2_bwd(const float* x, const float* y, int32_t B, int32_t P, const float*
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// APG update on the flat policy-gradient buffer (DaXBench/daxbench/algorithms/apg/apg.py:233-240,
+// 260-267): per-rank nan_to_num + global norm, clip to max_grad_norm, [all-reduce by the caller], mean + optax.adam.
+// Three element-wise passes over ~1 M floats instead of ~15 framework launches; the collective stays NCCL.
+// ------------------------------------------------------------------------------------------------------------------
+namespace ud {
+
+__global__ void __launch_bounds__(256) k_apg_scrub_sumsq(float* __restrict__ g, long long n, float* __restrict__ sumsq) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float t = g[i];
+    t = t == t ? fminf(fmaxf(t, -3.4028234663852886e38f), 3.4028234663852886e38f) : 0.f;   // jnp.nan_to_num
+    g[i] = t;
+    acc += t * t;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(sumsq, acc);
+}
+
+// g <- where(norm < max_norm, g, (g / norm) * max_norm)   (apg.py:264-266, evaluated as written)
+__global__ void __launch_bounds__(256)
+k_apg_clip(float* __restrict__ g, long long n, const float* __restrict__ sumsq, float max_norm) {
+  const float norm = sqrtf(*sumsq);
+  if (norm < max_norm) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    g[i] = (g[i] / norm) * max_norm;
+}
+
+// g' = g / world (pmean after the caller's all-reduce SUM), then optax.adam: m, v, bias corrections c1 = 1 - b1^t,
+// c2 = 1 - b2^t, p -= lr * (m / c1) / (sqrt(v / c2) + eps)
+__global__ void __launch_bounds__(256)
+k_adam_step(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+            float world, float lr, float b1, float b2, float omb1, float omb2, float eps, float c1, float c2) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = world == 1.f ? g[i] : g[i] / world;
+    // one rounding per operation, like the op-by-op host evaluation (no FMA contraction)
+    const float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(omb1, gi));
+    const float vi = __fadd_rn(__fmul_rn(b2, v[i]), __fmul_rn(__fmul_rn(omb2, gi), gi));
+    m[i] = mi;
+    v[i] = vi;
+    const float mhat = __fdiv_rn(mi, c1), vhat = __fdiv_rn(vi, c2);
+    p[i] = __fsub_rn(p[i], __fdiv_rn(__fmul_rn(lr, mhat), __fadd_rn(__fsqrt_rn(vhat), eps)));
+  }
+}
+
+}  // namespace ud
+
+extern "C" {
+
+int ud_apg_scrub_clip(float* grad, int64_t n, float max_grad_norm, float* sumsq, void* stream) {
+  if (!grad || !sumsq || n < 1) return UD_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  KScope ks(KC_REWARD, st, 2);
+  cudaMemsetAsync(sumsq, 0, sizeof(float), st);
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  k_apg_scrub_sumsq<<<blocks, 256, 0, st>>>(grad, n, sumsq);
+  k_apg_clip<<<blocks, 256, 0, st>>>(grad, n, sumsq, max_grad_norm);
+  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+}
+
+int ud_adam_step(float* params, const float* grad, float* m, float* v, int64_t n, int32_t world_size, double lr, double b1,
+                 double b2, double eps, int32_t t, void* stream) {
+  if (!params || !grad || !m || !v || n < 1 || world_size < 1 || t < 1) return UD_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  KScope ks(KC_REWARD, st);
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  // scalars evaluated in double and rounded once, as Python evaluates optax's / apg.Adam's
+  const float c1 = (float)(1.0 - pow(b1, (double)t)), c2 = (float)(1.0 - pow(b2, (double)t));
+  k_adam_step<<<blocks, 256, 0, st>>>(params, grad, m, v, n, (float)world_size, (float)lr, (float)b1, (float)b2,
+                                      (float)(1.0 - b1), (float)(1.0 - b2), (float)eps, c1, c2);
+  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+}
+
+}  // extern "C"
