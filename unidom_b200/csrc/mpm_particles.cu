@@ -383,6 +383,7 @@ constexpr int P2G_BLOCK = 64;    // threads (= particles) per CTA of k_p2g: with
 constexpr int G2PB_BLOCK = UD_BLOCK;  // k_g2p_bwd: one window of 27 nodes, 108 flush lanes of 128 (two windows cost it registers)
 constexpr int P2G_NPH = 14;      // nodes per staging window of k_p2g (27 nodes -> 2 windows)
 constexpr int G2PB_NPH = 27;
+constexpr int G2P_TILE_CELLS = 4;    // distinct base cells per warp whose stencils k_g2p keeps in shared memory
 constexpr int G2PB_TILE_RUNS = 12;  // segments whose 27 grid velocities k_g2p_bwd keeps in shared memory (5.2 KB: the CTA
                                     // stays at 4 per SM); CTAs with more distinct cells gather from L1/L2 as before
 constexpr size_t g2pb_tile_offset() { return (stage_smem_bytes<G2PB_BLOCK>(3, G2PB_NPH) + 15) & ~(size_t)15; }
@@ -549,8 +550,11 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
 __global__ void __launch_bounds__(UD_BLOCK, 8)
 k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ grid,
       const int32_t* __restrict__ perm, float* __restrict__ jrows, int substep) {
+  // Warp-local node tile: the 32 particles of a warp sit in a few cells (sorted order), so the warp fetches the 27
+  // grid velocities of each DISTINCT base cell once (<= G2P_TILE_CELLS cells, one coalesced pass, no block barrier)
+  // and every lane reads its stencil from shared memory; warps spanning more cells gather from L1/L2 as before.
+  __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_CELLS * 27];
   UD_PARTICLE_INDEX(k, env, g);
-  if (!live_) return;
   const size_t N = k.N;
   float x[3];
 #pragma unroll
@@ -558,34 +562,70 @@ k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ 
   Stencil st;
   make_stencil(x, k.inv_dx, st);
   const float4* genv = grid + (size_t)env * k.G;
+  const int lane = threadIdx.x & 31;
+  const int key = live_ ? base_key(st.base) : 0x7fffffff - lane;   // dead lanes: singleton groups no base can collide with
+  const unsigned mm = __match_any_sync(0xffffffffu, key);
+  const int leadlane = __ffs(mm) - 1;
+  const unsigned lb = __ballot_sync(0xffffffffu, lane == leadlane && live_);
+  const int ngroups = __popc(lb);
+  const int gid = __popc(lb & ((1u << leadlane) - 1u));
+  const bool tiled = ngroups <= G2P_TILE_CELLS && ngroups > 0;    // warp-uniform
+  float4* tile = wtile[threadIdx.x >> 5];
+  if (tiled) {
+    const int total = ngroups * 27;
+    for (int e0 = 0; e0 < total; e0 += 32) {                       // warp-uniform trip count
+      const int e = e0 + lane;
+      const int ge = min(e / 27, ngroups - 1), j = e - (e / 27) * 27;
+      const int src = __fns(lb, 0, ge + 1);                        // lane of the ge-th leader
+      const int b0 = __shfl_sync(0xffffffffu, st.base[0], src), b1 = __shfl_sync(0xffffffffu, st.base[1], src),
+                b2 = __shfl_sync(0xffffffffu, st.base[2], src);
+      if (e < total) {
+        const int ix = idx_gather(b0 + j / 9, k.rx), iy = idx_gather(b1 + (j / 3) % 3, k.ry), iz = idx_gather(b2 + j % 3, k.rz);
+        tile[e] = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
+      }
+    }
+    __syncwarp();
+  }
+  if (!live_) return;
+  const float4* my_tile = tile + gid * 27;
   float nv[3] = {0.f, 0.f, 0.f};
   Mat3 nC = mat_zero();
+  auto nodes = [&](auto tiled_tag) {
+    constexpr bool TILED = decltype(tiled_tag)::value;
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    int ix = idx_gather(st.base[0] + a, k.rx);
-    float d0 = (float)a - st.fx[0];
+    for (int a = 0; a < 3; ++a) {
+      const int ix = TILED ? 0 : idx_gather(st.base[0] + a, k.rx);
+      float d0 = (float)a - st.fx[0];
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      int iy = idx_gather(st.base[1] + b, k.ry);
-      float d1 = (float)b - st.fx[1];
-      float wab = st.w[a][0] * st.w[b][1];
+      for (int b = 0; b < 3; ++b) {
+        const int iy = TILED ? 0 : idx_gather(st.base[1] + b, k.ry);
+        float d1 = (float)b - st.fx[1];
+        float wab = st.w[a][0] * st.w[b][1];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        int iz = idx_gather(st.base[2] + c, k.rz);
-        float d2 = (float)c - st.fx[2];
-        float wt = wab * st.w[c][2];
-        float4 gv = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
-        float wg[3] = {wt * gv.x, wt * gv.y, wt * gv.z};
-        float dd[3] = {d0, d1, d2};
+        for (int c = 0; c < 3; ++c) {
+          float d2 = (float)c - st.fx[2];
+          float wt = wab * st.w[c][2];
+          float4 gv;
+          if (TILED) {
+            gv = my_tile[a * 9 + b * 3 + c];
+          } else {
+            const int iz = idx_gather(st.base[2] + c, k.rz);
+            gv = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
+          }
+          float wg[3] = {wt * gv.x, wt * gv.y, wt * gv.z};
+          float dd[3] = {d0, d1, d2};
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          nv[i] += wg[i];
+          for (int i = 0; i < 3; ++i) {
+            nv[i] += wg[i];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) nC(i, j) += wg[i] * dd[j];
+            for (int j = 0; j < 3; ++j) nC(i, j) += wg[i] * dd[j];
+          }
         }
       }
     }
-  }
+  };
+  if (tiled) nodes(std::true_type{});
+  else nodes(std::false_type{});
   {  // C' = 4 inv_dx sum wt g (x) d   (the factor is applied once, after the 27-node sum)
     const float c4 = 4.f * k.inv_dx;
 #pragma unroll
