@@ -36,19 +36,19 @@ _LEAVES = ("x", "v", "primitive0", "primitive1", "action0", "action1", "stiffnes
 
 class _ClothStep(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, sim, action, *leaves):
+    def forward(ctx, sim, stiff_float, action, *leaves):
         leaves = [_f32c(t) for t in leaves]
         action = _f32c(action)
-        out = sim._call_fwd(leaves, action)
-        ctx.sim = sim
+        out = sim._call_fwd(leaves, action, stiff_float)
+        ctx.sim, ctx.stiff_float = sim, stiff_float      # the dtype of THIS call's stiffness leaf, not the simulator's last
         ctx.save_for_backward(action, *leaves)
         return tuple(out)
 
     @staticmethod
     def backward(ctx, *gout):
         action, *leaves = ctx.saved_tensors
-        gin, gaction = ctx.sim._call_bwd(leaves, action, list(gout))
-        return (None, gaction, *gin)
+        gin, gaction = ctx.sim._call_bwd(leaves, action, list(gout), ctx.stiff_float)
+        return (None, None, gaction, *gin)
 
 
 class _ClothMultiStep(torch.autograd.Function):
@@ -56,19 +56,19 @@ class _ClothMultiStep(torch.autograd.Function):
     recomputes from per-sub-action checkpoints inside the library."""
 
     @staticmethod
-    def forward(ctx, sim, keep, actions, *leaves):
+    def forward(ctx, sim, keep, stiff_float, actions, *leaves):
         leaves = [_f32c(t) for t in leaves]
         actions = _f32c(actions)
-        out, ckpt = sim._call_multi_fwd(leaves, actions, keep)
-        ctx.sim, ctx.ckpt = sim, ckpt
+        out, ckpt = sim._call_multi_fwd(leaves, actions, keep, stiff_float)
+        ctx.sim, ctx.ckpt, ctx.stiff_float = sim, ckpt, stiff_float
         ctx.save_for_backward(actions, *leaves)
         return tuple(out)
 
     @staticmethod
     def backward(ctx, *gout):
         actions, *leaves = ctx.saved_tensors
-        gin, gactions = ctx.sim._call_multi_bwd(leaves, actions, ctx.ckpt, list(gout))
-        return (None, None, gactions, *gin)
+        gin, gactions = ctx.sim._call_multi_bwd(leaves, actions, ctx.ckpt, list(gout), ctx.stiff_float)
+        return (None, None, None, gactions, *gin)
 
 
 class ClothSimulator:
@@ -152,8 +152,8 @@ class ClothSimulator:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _call_fwd(self, leaves, action):
-        p = self.params(leaves[0].shape[0], self._stiff_float)
+    def _call_fwd(self, leaves, action, stiff_float):
+        p = self.params(leaves[0].shape[0], stiff_float)
         out = [torch.empty_like(t) for t in leaves]
         sin, sout = self._pack(leaves), self._pack(out)
         rc = self._L.ud_cloth_step_fwd(C.byref(p), C.byref(sin), _ptr(self._nbr), _ptr(self._L0), _ptr(action),
@@ -161,8 +161,8 @@ class ClothSimulator:
         _lib.check(rc, "ud_cloth_step_fwd")
         return out
 
-    def _call_bwd(self, leaves, action, gout):
-        p = self.params(leaves[0].shape[0], self._stiff_float)
+    def _call_bwd(self, leaves, action, gout, stiff_float):
+        p = self.params(leaves[0].shape[0], stiff_float)
         gout = [(_f32c(g) if g is not None else None) for g in gout]
         gin = [torch.zeros_like(t) for t in leaves]
         gaction = torch.zeros_like(action)
@@ -173,9 +173,9 @@ class ClothSimulator:
         _lib.check(rc, "ud_cloth_step_bwd")
         return gin, gaction
 
-    def _call_multi_fwd(self, leaves, actions, keep):
+    def _call_multi_fwd(self, leaves, actions, keep, stiff_float):
         T = actions.shape[0]
-        p = self.params(leaves[0].shape[0], self._stiff_float)
+        p = self.params(leaves[0].shape[0], stiff_float)
         out = [torch.empty_like(t) for t in leaves]
         ckpt, nbytes, cptr = None, 0, C.c_void_p(0)
         if keep:
@@ -187,9 +187,9 @@ class ClothSimulator:
         _lib.check(rc, "ud_cloth_multi_step_fwd")
         return out, ckpt
 
-    def _call_multi_bwd(self, leaves, actions, ckpt, gout):
+    def _call_multi_bwd(self, leaves, actions, ckpt, gout, stiff_float):
         T = actions.shape[0]
-        p = self.params(leaves[0].shape[0], self._stiff_float)
+        p = self.params(leaves[0].shape[0], stiff_float)
         gout = [(_f32c(g) if g is not None else None) for g in gout]
         gin = [torch.zeros_like(t) for t in leaves]
         gactions = torch.zeros_like(actions)
@@ -203,25 +203,25 @@ class ClothSimulator:
 
     def scan_step_jax(self, state: ClothState, actions: torch.Tensor):
         """jax.lax.scan(self.step_jax, state, actions)[0] for actions [T,B,8] (cloth_env.py:211) as ONE fused call."""
-        self._stiff_float = state.stiffness.is_floating_point()
+        stiff_float = state.stiffness.is_floating_point()
         leaves = [getattr(state, k) for k in _LEAVES]
         leaves[6] = leaves[6].to(torch.float32)
         # grad mode is off inside Function.forward, so decide here whether the adjoint will need checkpoints
         keep = torch.is_grad_enabled() and (actions.requires_grad or any(t.requires_grad for t in leaves))
-        out = _ClothMultiStep.apply(self, keep, actions, *leaves)
+        out = _ClothMultiStep.apply(self, keep, stiff_float, actions, *leaves)
         vals = dict(zip(_LEAVES, out))
-        if not self._stiff_float:
+        if not stiff_float:
             vals["stiffness"] = state.stiffness
         return state._replace(**vals)
 
     def step_jax(self, state: ClothState, action: torch.Tensor):
         """vmap(jit(robot_step_wrapper)) (:68-70,107-180): returns (state, state)."""
-        self._stiff_float = state.stiffness.is_floating_point()
+        stiff_float = state.stiffness.is_floating_point()
         leaves = [getattr(state, k) for k in _LEAVES]
         leaves[6] = leaves[6].to(torch.float32)
-        out = _ClothStep.apply(self, action, *leaves)
+        out = _ClothStep.apply(self, stiff_float, action, *leaves)
         vals = dict(zip(_LEAVES, out))
-        if not self._stiff_float:
+        if not stiff_float:
             vals["stiffness"] = state.stiffness
         new_state = state._replace(**vals)
         return new_state, new_state

@@ -40,10 +40,11 @@ KScope::~KScope() {
 
 static int g_svd_warm = 1, g_sort = 1, g_stage = 1, g_mark = 2;
 static thread_local const char* g_last_error = "";
-static int fail(int code, const char* what) {
+int set_error(int code, const char* what) {
   g_last_error = what;
   return code;
 }
+static int fail(int code, const char* what) { return set_error(code, what); }
 
 int cloth_tuning_cta_nodes(int v);   // cloth.cu
 int tuning_sort() { return g_sort; }

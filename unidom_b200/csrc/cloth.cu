@@ -713,19 +713,14 @@ static void launch_cloth_bwd(const ClothK& k, cudaStream_t st, const ud_cloth_st
       launch_cluster(k_cloth_bwd<1024, true>, k, smem, st, k, in, nbr, L0, action, gout, gin, gaction, save);
     return;
   }
-  static bool attr = false;
-  if (!attr) {
-    ClothK m = k;
-    m.P = m.threads = 512;
-    cudaFuncSetAttribute(k_cloth_bwd<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cloth_bwd_smem(m));
-    m.P = m.threads = 1024;
-    cudaFuncSetAttribute(k_cloth_bwd<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cloth_bwd_smem(m));
-    attr = true;
-  }
-  if (k.threads <= 512)
+  // per-DEVICE attribute (one host thread per device under pmap): set on every launch, like launch_cluster
+  if (k.threads <= 512) {
+    cudaFuncSetAttribute(k_cloth_bwd<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_cloth_bwd<512, false><<<k.B, k.threads, smem, st>>>(k, in, nbr, L0, action, gout, gin, gaction, save);
-  else
+  } else {
+    cudaFuncSetAttribute(k_cloth_bwd<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_cloth_bwd<1024, false><<<k.B, k.threads, smem, st>>>(k, in, nbr, L0, action, gout, gin, gaction, save);
+  }
 }
 
 }  // namespace ud
@@ -746,22 +741,22 @@ int ud_cloth_step_fwd(const ud_cloth_params* p, const ud_cloth_state* in, const 
   (void)workspace;
   (void)workspace_bytes;
   ClothK k;
-  if (!cloth_fold(p, &k)) return UD_E_INVALID;
-  if (!cloth_state_ok(in) || !cloth_state_ok(out) || !nbr || !L0 || !action) return UD_E_INVALID;
+  if (!cloth_fold(p, &k)) return set_error(UD_E_INVALID, "ud_cloth_step_fwd: invalid ud_cloth_params (num_envs / n_nodes / substeps / T < 1, n_nodes above 8 CTAs x 1024 nodes, dt or mask_sum <= 0)");
+  if (!cloth_state_ok(in) || !cloth_state_ok(out) || !nbr || !L0 || !action) return set_error(UD_E_INVALID, "ud_cloth_step_fwd: invalid argument (null pointer, size or parameter out of range)");
   cudaStream_t st = (cudaStream_t)stream;
   KScope ks(KC_CLOTH_FWD, st);
   launch_cloth_fwd(k, st, *in, nbr, L0, action, *out, nullptr, 1, nullptr);
-  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? UD_OK : set_error(UD_E_CUDA, "ud_cloth_step_fwd: launch failed");
 }
 
 int ud_cloth_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const int32_t* nbr, const float* L0,
                       const float* action, const ud_cloth_state* gout, ud_cloth_state* gin, float* gaction,
                       void* workspace, size_t workspace_bytes, void* stream) {
   ClothK k;
-  if (!cloth_fold(p, &k)) return UD_E_INVALID;
-  if (!cloth_state_ok(in) || !gout || !gin || !nbr || !L0 || !action) return UD_E_INVALID;
+  if (!cloth_fold(p, &k)) return set_error(UD_E_INVALID, "ud_cloth_step_bwd: invalid ud_cloth_params (num_envs / n_nodes / substeps / T < 1, n_nodes above 8 CTAs x 1024 nodes, dt or mask_sum <= 0)");
+  if (!cloth_state_ok(in) || !gout || !gin || !nbr || !L0 || !action) return set_error(UD_E_INVALID, "ud_cloth_step_bwd: invalid argument (null pointer, size or parameter out of range)");
   size_t need = ud_cloth_workspace_bytes(p);
-  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255)) return UD_E_WORKSPACE;
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255)) return set_error(UD_E_WORKSPACE, "ud_cloth_step_bwd: workspace / checkpoint buffer too small or not 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   ud_cloth_state none;
   memset(&none, 0, sizeof(none));
@@ -773,7 +768,7 @@ int ud_cloth_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const 
     KScope ks(KC_CLOTH_BWD, st);
     launch_cloth_bwd(k, st, *in, nbr, L0, action, *gout, *gin, gaction, (const float*)workspace);
   }
-  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? UD_OK : set_error(UD_E_CUDA, "ud_cloth_step_bwd: launch failed");
 }
 
 // ---- fused env step: T sub-actions per call (cloth_env.py:211 scans robot_step over the 40 pick-and-place
@@ -800,13 +795,13 @@ int ud_cloth_multi_step_fwd(const ud_cloth_params* p, const ud_cloth_state* in, 
                             const float* actions, int32_t T, ud_cloth_state* out, void* ckpt, size_t ckpt_bytes,
                             void* stream) {
   ClothK k;
-  if (!cloth_fold(p, &k) || T < 1) return UD_E_INVALID;
-  if (!cloth_state_ok(in) || !cloth_state_ok(out) || !nbr || !L0 || !actions) return UD_E_INVALID;
-  if (ckpt && (ckpt_bytes < ud_cloth_multi_ckpt_bytes(p, T) || ((uintptr_t)ckpt & 255))) return UD_E_WORKSPACE;
+  if (!cloth_fold(p, &k) || T < 1) return set_error(UD_E_INVALID, "ud_cloth_multi_step_fwd: invalid ud_cloth_params (num_envs / n_nodes / substeps / T < 1, n_nodes above 8 CTAs x 1024 nodes, dt or mask_sum <= 0)");
+  if (!cloth_state_ok(in) || !cloth_state_ok(out) || !nbr || !L0 || !actions) return set_error(UD_E_INVALID, "ud_cloth_multi_step_fwd: invalid argument (null pointer, size or parameter out of range)");
+  if (ckpt && (ckpt_bytes < ud_cloth_multi_ckpt_bytes(p, T) || ((uintptr_t)ckpt & 255))) return set_error(UD_E_WORKSPACE, "ud_cloth_multi_step_fwd: workspace / checkpoint buffer too small or not 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   KScope ks(KC_CLOTH_FWD, st);
   launch_cloth_fwd(k, st, *in, nbr, L0, actions, *out, nullptr, T, (float*)ckpt);
-  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? UD_OK : set_error(UD_E_CUDA, "ud_cloth_multi_step_fwd: launch failed");
 }
 
 int ud_cloth_multi_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, const int32_t* nbr, const float* L0,
@@ -814,11 +809,11 @@ int ud_cloth_multi_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, 
                             ud_cloth_state* gin, float* gactions, void* workspace, size_t workspace_bytes,
                             void* stream) {
   ClothK k;
-  if (!cloth_fold(p, &k) || T < 1) return UD_E_INVALID;
-  if (!cloth_state_ok(in) || !gout || !gin || !nbr || !L0 || !actions || !ckpt || !gactions) return UD_E_INVALID;
-  if (!gin->x || !gin->v || !gin->primitive0 || !gin->primitive1 || !gin->stiffness || !gin->mu) return UD_E_INVALID;
+  if (!cloth_fold(p, &k) || T < 1) return set_error(UD_E_INVALID, "ud_cloth_multi_step_bwd: invalid ud_cloth_params (num_envs / n_nodes / substeps / T < 1, n_nodes above 8 CTAs x 1024 nodes, dt or mask_sum <= 0)");
+  if (!cloth_state_ok(in) || !gout || !gin || !nbr || !L0 || !actions || !ckpt || !gactions) return set_error(UD_E_INVALID, "ud_cloth_multi_step_bwd: invalid argument (null pointer, size or parameter out of range)");
+  if (!gin->x || !gin->v || !gin->primitive0 || !gin->primitive1 || !gin->stiffness || !gin->mu) return set_error(UD_E_INVALID, "ud_cloth_multi_step_bwd: invalid argument (null pointer, size or parameter out of range)");
   if (!workspace || workspace_bytes < ud_cloth_multi_workspace_bytes(p, T) || ((uintptr_t)workspace & 255))
-    return UD_E_WORKSPACE;
+    return set_error(UD_E_WORKSPACE, "ud_cloth_multi_step_bwd: workspace / checkpoint buffer too small or not 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t BP3 = (size_t)k.B * k.P * 3;
   float* save = (float*)workspace;
@@ -857,7 +852,7 @@ int ud_cloth_multi_step_bwd(const ud_cloth_params* p, const ud_cloth_state* in, 
       launch_cloth_bwd(k, st, s_in, nbr, L0, a_t, go, gi, gactions + (size_t)t * k.B * 8, save);
     }
   }
-  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? UD_OK : set_error(UD_E_CUDA, "ud_cloth_multi_step_bwd: launch failed");
 }
 
 }  // extern "C"

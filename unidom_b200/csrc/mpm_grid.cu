@@ -284,7 +284,7 @@ k_grid_clear(MpmConst k, float4* __restrict__ grid, const int32_t* __restrict__ 
 
 // Empty cells of the outermost layer: the reference updates EVERY cell (empty ones get dt*gravity, colliders,
 // friction, walls), and a particle that left the grid gathers exactly these cells through clamped indices
-// (SURVEY 8c).  One thread per face cell (edges are visited twice and write the same value).
+// (SURVEY 8c).  One thread per face cell; edge / corner cells are written by one owning face only.
 __global__ void __launch_bounds__(128)
 k_grid_shell(MpmConst k, const float4* grid_raw, float4* grid_out, int f, ud_mpm_state in,
              const float* __restrict__ fk_pos, const float* __restrict__ fk_rot, const float* __restrict__ fk_vw,
@@ -294,6 +294,11 @@ k_grid_shell(MpmConst k, const float4* grid_raw, float4* grid_out, int f, ud_mpm
   const int nxy = k.rx * k.ry, nxz = k.rx * k.rz;
   int ci, cj, ck;
   if (!shell_cell(k, t0, ci, cj, ck)) return;
+  // edge and corner cells belong to two or three faces: ONE face owns each (z faces first, then y, then x), so that the
+  // in-place forward (grid_out == grid_raw) can never re-read a value it has already updated
+  const bool owner = (ck == 0 || ck == k.rz - 1) ? (t0 < 2 * nxy)
+                     : ((cj == 0 || cj == k.ry - 1) ? (t0 >= 2 * nxy && t0 < 2 * (nxy + nxz)) : true);
+  if (!owner) return;
   const size_t idx = (size_t)env * k.G + (size_t)(ci * k.ry + cj) * k.rz + ck;
   const float4 g = grid_raw[idx];
   if (g.w > 0.f) return;  // has mass: k_grid_fwd's cell
@@ -309,12 +314,7 @@ k_grid_shell(MpmConst k, const float4* grid_raw, float4* grid_out, int f, ud_mpm
   cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
   grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
   // an empty shell cell under a primitive's influence can carry a cotangent to that primitive: list it for k_grid_bwd
-  // (edge cells are visited twice: the duplicate entry is harmless only if it is not added, so one face owns each cell)
-  if (act_list && any_active) {
-    const bool owner = (ck == 0 || ck == k.rz - 1) ? (t0 < 2 * nxy)
-                       : ((cj == 0 || cj == k.ry - 1) ? (t0 >= 2 * nxy && t0 < 2 * (nxy + nxz)) : true);
-    if (owner) act_list[atomicAdd(act_count, 1)] = (int32_t)idx;
-  }
+  if (act_list && any_active) act_list[atomicAdd(act_count, 1)] = (int32_t)idx;
 }
 
 void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const long long* grid_fix, int substep,

@@ -82,6 +82,7 @@ int tuning_sort();   // 0: identity permutation instead of the per-frame binning
 int tuning_stage();  // 0: 27 vector REDs per particle straight to HBM instead of the shared-memory staged scatter
 
 // Host helpers (abi.cu)
+int set_error(int code, const char* what);   // records the message ud_last_error() returns (thread-local); returns code
 bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k);
 size_t mpm_carve(const ud_mpm_params* p, const MpmConst& k, bool bwd, void* base, MpmWs* ws);
 

@@ -525,12 +525,9 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
                 const float* la_s, const float* vt_in, float* vt_out, float* svd_out, const MpmWs& ws,
                 cudaStream_t st) {
   KScope ks_(KC_P2G, st);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_p2g<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH));
-    cudaFuncSetAttribute(k_p2g<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH));
-    attr_set = true;
-  }
+  // the attribute is per DEVICE (a process may drive several, one host thread each: SURVEY 8b): set it on every launch
+  cudaFuncSetAttribute(k_p2g<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH));
+  cudaFuncSetAttribute(k_p2g<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH));
   if (!tuning_stage() && !ws.grid_fix)
     k_p2g<2><<<pgrid(k, P2G_BLOCK), P2G_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in,
                                                       vt_out, svd_out, ws.blk_flag);
@@ -837,11 +834,7 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
 void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
                     cudaStream_t st) {
   KScope ks_(KC_G2P_BWD, st);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_g2p_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2pb_smem_bytes());
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(k_g2p_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2pb_smem_bytes());   // per device
   k_g2p_bwd<<<pgrid(k, G2PB_BLOCK), G2PB_BLOCK, g2pb_smem_bytes(), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
 }
 

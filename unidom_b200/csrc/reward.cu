@@ -186,9 +186,9 @@ size_t ud_chamfer_residual_bytes(int32_t B, int32_t P, int32_t Q) {
 
 int ud_chamfer_fwd(const float* x, const float* y, int32_t B, int32_t P, int32_t Q, float* out, void* residuals,
                    size_t residual_bytes, void* stream) {
-  if (!x || !y || !out || B < 1 || P < 1 || Q < 1 || B > 65535) return UD_E_INVALID;
+  if (!x || !y || !out || B < 1 || P < 1 || Q < 1 || B > 65535) return set_error(UD_E_INVALID, "ud_chamfer_fwd: invalid argument (null pointer, size or parameter out of range)");
   if (!residuals || ((uintptr_t)residuals & 255) || residual_bytes < chamfer_carve(nullptr, B, P, Q).bytes)
-    return UD_E_WORKSPACE;
+    return set_error(UD_E_WORKSPACE, "ud_chamfer_fwd: workspace / checkpoint buffer too small or not 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   ChamferRes r = chamfer_carve(residuals, B, P, Q);
   {
@@ -197,38 +197,38 @@ int ud_chamfer_fwd(const float* x, const float* y, int32_t B, int32_t P, int32_t
     k_nn_scan<<<dim3(cdiv(Q, NN_BLOCK), B), NN_BLOCK, 0, st>>>(y, 0, Q, x, (size_t)P * 3, P, r.miny, r.cnty);
     k_chamfer_finish<<<B, 256, 0, st>>>(r.minx, P, r.miny, Q, out);
   }
-  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? UD_OK : set_error(UD_E_CUDA, "ud_chamfer_fwd: launch failed");
 }
 
 int ud_chamfer_bwd(const float* x, const float* y, int32_t B, int32_t P, int32_t Q, const float* gout,
                    const void* residuals, size_t residual_bytes, float* gx, void* stream) {
-  if (!x || !y || !gout || !gx || B < 1 || P < 1 || Q < 1 || B > 65535) return UD_E_INVALID;
+  if (!x || !y || !gout || !gx || B < 1 || P < 1 || Q < 1 || B > 65535) return set_error(UD_E_INVALID, "ud_chamfer_bwd: invalid argument (null pointer, size or parameter out of range)");
   if (!residuals || ((uintptr_t)residuals & 255) || residual_bytes < chamfer_carve(nullptr, B, P, Q).bytes)
-    return UD_E_WORKSPACE;
+    return set_error(UD_E_WORKSPACE, "ud_chamfer_bwd: workspace / checkpoint buffer too small or not 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   ChamferRes r = chamfer_carve((void*)residuals, B, P, Q);
   {
     KScope ks(KC_REWARD, st);
     k_chamfer_bwd<<<dim3(cdiv(P, NN_BLOCK), B), NN_BLOCK, 0, st>>>(x, y, P, Q, r.minx, r.cntx, r.miny, r.cnty, gout, gx);
   }
-  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? UD_OK : set_error(UD_E_CUDA, "ud_chamfer_bwd: launch failed");
 }
 
 int ud_l2_fwd(const float* x, const float* y, int32_t B, int32_t P, float* out, void* stream) {
-  if (!x || !y || !out || B < 1 || P < 1) return UD_E_INVALID;
+  if (!x || !y || !out || B < 1 || P < 1) return set_error(UD_E_INVALID, "ud_l2_fwd: invalid argument (null pointer, size or parameter out of range)");
   cudaStream_t st = (cudaStream_t)stream;
   KScope ks(KC_REWARD, st);
   k_l2_fwd<<<B, 256, 0, st>>>(x, y, P, out);
-  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? UD_OK : set_error(UD_E_CUDA, "ud_l2_fwd: launch failed");
 }
 
 int ud_l2_bwd(const float* x, const float* y, int32_t B, int32_t P, const float* gout, float* gx, void* stream) {
-  if (!x || !y || !gout || !gx || B < 1 || P < 1) return UD_E_INVALID;
+  if (!x || !y || !gout || !gx || B < 1 || P < 1) return set_error(UD_E_INVALID, "ud_l2_bwd: invalid argument (null pointer, size or parameter out of range)");
   cudaStream_t st = (cudaStream_t)stream;
   KScope ks(KC_REWARD, st);
   const size_t n = (size_t)B * P;
   k_l2_bwd<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, B, P, gout, gx);
-  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? UD_OK : set_error(UD_E_CUDA, "ud_l2_bwd: launch failed");
 }
 
 }  // extern "C"
@@ -284,19 +284,19 @@ k_adam_step(float* __restrict__ p, const float* __restrict__ g, float* __restric
 extern "C" {
 
 int ud_apg_scrub_clip(float* grad, int64_t n, float max_grad_norm, float* sumsq, void* stream) {
-  if (!grad || !sumsq || n < 1) return UD_E_INVALID;
+  if (!grad || !sumsq || n < 1) return set_error(UD_E_INVALID, "ud_apg_scrub_clip: invalid argument (null pointer, size or parameter out of range)");
   cudaStream_t st = (cudaStream_t)stream;
   KScope ks(KC_REWARD, st, 2);
   cudaMemsetAsync(sumsq, 0, sizeof(float), st);
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
   k_apg_scrub_sumsq<<<blocks, 256, 0, st>>>(grad, n, sumsq);
   k_apg_clip<<<blocks, 256, 0, st>>>(grad, n, sumsq, max_grad_norm);
-  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? UD_OK : set_error(UD_E_CUDA, "ud_apg_scrub_clip: launch failed");
 }
 
 int ud_adam_step(float* params, const float* grad, float* m, float* v, int64_t n, int32_t world_size, double lr, double b1,
                  double b2, double eps, int32_t t, void* stream) {
-  if (!params || !grad || !m || !v || n < 1 || world_size < 1 || t < 1) return UD_E_INVALID;
+  if (!params || !grad || !m || !v || n < 1 || world_size < 1 || t < 1) return set_error(UD_E_INVALID, "ud_adam_step: invalid argument (null pointer, size or parameter out of range)");
   cudaStream_t st = (cudaStream_t)stream;
   KScope ks(KC_REWARD, st);
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
@@ -304,7 +304,7 @@ int ud_adam_step(float* params, const float* grad, float* m, float* v, int64_t n
   const float c1 = (float)(1.0 - pow(b1, (double)t)), c2 = (float)(1.0 - pow(b2, (double)t));
   k_adam_step<<<blocks, 256, 0, st>>>(params, grad, m, v, n, (float)world_size, (float)lr, (float)b1, (float)b2,
                                       (float)(1.0 - b1), (float)(1.0 - b2), (float)eps, c1, c2);
-  return cudaGetLastError() == cudaSuccess ? UD_OK : UD_E_CUDA;
+  return cudaGetLastError() == cudaSuccess ? UD_OK : set_error(UD_E_CUDA, "ud_adam_step: launch failed");
 }
 
 }  // extern "C"

@@ -46,6 +46,23 @@ class GraphedMPMScan:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.s_out = self._scan(self.s_in, self.a_in)
+        # the graph holds the raw pointer of the simulator's forward workspace: pin it, so that a later eager call that
+        # needs a larger workspace fails loudly instead of freeing memory the next replay would write
+        sim._ws_fwd.pins += 1
+        self._pinned = True
+
+    def close(self):
+        """Drops the graph and releases its hold on the simulator's workspace."""
+        if getattr(self, "_pinned", False):
+            self.sim._ws_fwd.pins -= 1
+            self._pinned = False
+        self.graph = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _scan(self, state, actions):
         for t in range(actions.shape[0]):
@@ -56,5 +73,7 @@ class GraphedMPMScan:
         with torch.no_grad():
             _copy_state_(self.s_in, state)
             self.a_in.copy_(actions)
+        if self.graph is None:
+            raise RuntimeError("GraphedMPMScan was closed")
         self.graph.replay()
         return self.s_out

@@ -92,9 +92,15 @@ class _Workspace:
     def __init__(self, device):
         self.device = device
         self.buf = None
+        self.pins = 0       # live CUDA graphs that captured the pointer of `buf` (graphs.GraphedMPMScan)
 
     def get(self, nbytes):
         if self.buf is None or self.buf.numel() < nbytes:
+            if self.pins:
+                raise RuntimeError(
+                    f"this simulator's workspace ({0 if self.buf is None else self.buf.numel()} B) is captured by a live "
+                    f"CUDA graph and cannot grow to {nbytes} B: use a second simulator for the larger batch, or drop the "
+                    "graph (GraphedMPMScan.close()) first")
             self.buf = None
             self.buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
         base = self.buf.data_ptr()
