@@ -343,6 +343,66 @@ def cloth_env_case(name, ep_len, B, seed):
     print(f"wrote {path}: ep_len={ep_len} B={B} loss={float(loss):.6f} |grad|={gn:.4e}")
 
 
+def cloth_env_para_case(name, B, seed, it):
+    """BASELINE configs[3] (GenDOM parameter-aware APG): the reference's FoldCloth1ParaEnv (fold_cloth1_para_env.py:39,
+    cloth_env_para.py:98-135 get_obs with the normalised stiffness, :199-233 step_diff) with the stiffness drawn the
+    way apg_para.py:326-329 draws it for iteration `it`, one APG rollout step (apg_para.py:201-240) with the torch
+    policy; outputs obs, reward, the policy gradient and d loss / d stiffness."""
+    sys.path.insert(0, os.path.join(HERE, "jaxshim"))
+    import stubs
+    stubs.install()
+    import torch
+    import jax
+    import jax.numpy as jnp
+    from daxbench.core.envs import fold_cloth1_para_env
+    sys.path.insert(0, ROOT)
+    from unidom_b200 import apg
+    rng = np.random.RandomState(seed)
+    np.random.seed(it)                                                    # apg_para.py:326-329, verbatim
+    stiffness = np.random.uniform(200, 1800)
+    eval_mm = [100, 2000]
+    env = fold_cloth1_para_env.FoldCloth1ParaEnv(batch_size=B, aux_reward=True, seed=0, stiffness=stiffness,
+                                                 eval_min_max_stiff=eval_mm)
+    _, st = env.reset(jax.random.PRNGKey(0))
+    shift = rng.randn(2).astype(np.float32) * 0.05
+    x0 = np.asarray(env.simulator.reset_jax().x).copy()
+    x0[..., 0] += shift[0]
+    x0[..., 2] += shift[1]
+    stiff_t = torch.as_tensor(np.asarray(st.stiffness)).clone().requires_grad_(True)
+    st = st._replace(x=jnp.array(x0), stiffness=jax.Array(stiff_t))
+    params = apg.init_policy(env.observation_size, env.action_size, seed=seed)
+    params[-1] = params[-1] + torch.tensor([0.0, 0.0, 0.0, 0.6, 0.0, 0.4, -2, -2, -2, -2, -2, -2])
+    eps = torch.from_numpy(rng.randn(1, B, env.action_size).astype(np.float32))
+    out = {"goal": np.asarray(env.goal), "eps": eps.numpy(), "shift": shift, "policy_seed": np.array(seed),
+           "param5": params[-1].numpy(), "stiffness_draw": np.array(stiffness, np.float64), "it": np.array(it),
+           "eval_min_max_stiff": np.array(eval_mm, np.float64)}
+    for k in CLOTH_F:
+        v = getattr(st, k)
+        out["in_" + k] = (v.t.detach().numpy() if hasattr(v, "t") else np.asarray(v))
+    req = [p.clone().requires_grad_(True) for p in params]
+    eval_tile = np.tile(np.array(eval_mm), (B, 1))
+    obs = env.get_obs(st, eval_min_max_stiff=eval_tile)                     # apg_para.py:205-208
+    out["obs0"] = obs.t.detach().numpy()
+    actions = apg.sample_actions(apg.policy_apply(req, obs.t), eps[0], True)
+    out["actions0"] = actions.detach().numpy()
+    obs1, reward, done, info = env.step_diff(jax.Array(actions), st)
+    state = info["state"]
+    out["obs1"] = obs1.t.detach().numpy()
+    out["reward0"] = reward.t.detach().numpy()
+    out["x1"] = state.x.t.detach().numpy()
+    out["stiffness1"] = state.stiffness.t.detach().numpy()
+    loss = -reward.t.mean()
+    grads = torch.autograd.grad(loss, req + [stiff_t], allow_unused=True)
+    out["loss"] = loss.detach().numpy()
+    out["gparam4"], out["gparam5"] = grads[4].numpy(), grads[5].numpy()
+    out["gnorm"] = np.array(float(torch.sqrt(sum((g * g).sum() for g in grads[:6]))))
+    out["g_stiffness"] = np.zeros(B, np.float32) if grads[6] is None else grads[6].numpy()
+    path = os.path.join(GOLD, f"ref_clothenv_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: B={B} stiffness={stiffness:.4f} loss={float(loss):.6f} |grad|={float(out['gnorm']):.4e} "
+          f"g_stiffness={out['g_stiffness']}")
+
+
 def mpm_env_case(name, B, density, seed):
     """Env level for MPM: the reference's push task (envs/shape_elasto_plastic.py: ShapeRopeEnv.step_diff = focus
     shift, get_primitive_actions, 20 sub-actions x 16 substeps, reward e^(-10 l2) + e^(-contact)) on a reduced
@@ -485,6 +545,8 @@ def main():
     cases["mpmenv_pour"] = lambda: task_env_case("pour", 2, 44)
     cases["mpmenv_rope"] = lambda: task_env_case("rope", 1, 45, steps=1)      # 3 990 substeps per env step: ~30 min here
     cases["clothenv_ep1"] = lambda: cloth_env_case("ep1", 1, 2, 31)
+    # BASELINE.json configs[3]: fold_cloth1_para, stiffness of training iteration 3 (apg_para.py:326-329)
+    cases["clothenv_para"] = lambda: cloth_env_para_case("para", 2, 33, 3)
     # BASELINE.json configs[0]: fold_cloth3 APG ep_len=3 num_envs=4 (reference states + policy gradient; ~20 min here)
     cases["clothenv_ep3"] = lambda: cloth_env_case("ep3", 3, 4, 0)
     for name, fn in cases.items():

@@ -50,8 +50,13 @@ def _rebuild(tree):
 
 
 def vmap(f, in_axes=0, out_axes=0):
-    def batched(*args):
-        axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+    def batched(*args, **kwargs):
+        # jax.vmap maps keyword arguments over axis 0 (cloth_env_para.py:191 passes eval_min_max_stiff by keyword)
+        kw_names = list(kwargs)
+        n_pos = len(args)
+        axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * n_pos
+        args = tuple(args) + tuple(kwargs[k] if isinstance(kwargs[k], Array) else numpy.array(kwargs[k]) for k in kw_names)
+        axes = tuple(axes) + (0,) * len(kw_names)
         B = None
         for a, ax in zip(args, axes):
             if ax is None:
@@ -65,7 +70,7 @@ def vmap(f, in_axes=0, out_axes=0):
         for b in range(B):
             sl = [a if ax is None else tree_util.tree_map(lambda l, ax=ax: _W(_T(l).select(ax, b)), a)
                   for a, ax in zip(args, axes)]
-            outs.append(f(*sl))
+            outs.append(f(*sl[:n_pos], **dict(zip(kw_names, sl[n_pos:]))))
         return tree_util.tree_map(lambda *ls: _W(_torch.stack([_T(l) for l in ls], dim=out_axes)), outs[0], *outs[1:])
     return batched
 

@@ -106,7 +106,11 @@ _PRIM_FLOAT_FIELDS = ("size", "friction", "softness", "color", "position", "rota
 class Simulator:
     """Per-environment functional core of SimpleMPMSimulator."""
 
-    def __init__(self, conf: MPMConf, material: torch.Tensor, h: torch.Tensor, dtype=torch.float32):
+    def __init__(self, conf: MPMConf, material: torch.Tensor, h: torch.Tensor, dtype=torch.float32,
+                 checkpoint_substeps=False):
+        # checkpoint_substeps: torch.utils.checkpoint around every substep (same numbers; autograd keeps one substep's
+        # graph at a time instead of S of them: full-size scenes with S = 70 would otherwise need tens of GB on the host)
+        self.checkpoint_substeps = checkpoint_substeps
         self.conf = conf
         self.material = material
         self.h = h.to(dtype)
@@ -249,7 +253,7 @@ class Simulator:
                  for i in range(c.n_primitive)] + list(state.primitives[c.n_primitive:])
         state = state._replace(primitives=prims)
         for f in range(c.steps):
-            state = self.substep(f, state)
+            state = self._substep_ckpt(f, state) if self.checkpoint_substeps else self.substep(f, state)
         # copy_frame(steps, 0) (:365-373): source row S clamps to S-1
         prims = []
         for i, p in enumerate(state.primitives):
@@ -259,6 +263,24 @@ class Simulator:
                 p = p._replace(position=position, rotation=rotation)
             prims.append(p)
         return state._replace(primitives=prims)
+
+    def _substep_ckpt(self, f, state):
+        from torch.utils.checkpoint import checkpoint
+        n_prim = len(state.primitives)
+        fields = [k for k in state._fields if k != "primitives"]
+        pf = P.PrimitiveState._fields
+
+        def pack(st):
+            return [getattr(st, k) for k in fields] + [getattr(p, k) for p in st.primitives for k in pf]
+
+        def unpack(ls):
+            vals = dict(zip(fields, ls[:len(fields)]))
+            rest = ls[len(fields):]
+            prims = [P.PrimitiveState(*rest[i * len(pf):(i + 1) * len(pf)]) for i in range(n_prim)]
+            return MPMState(primitives=prims, **vals)
+
+        out = checkpoint(lambda *ls: tuple(pack(self.substep(f, unpack(list(ls))))), *pack(state), use_reentrant=False)
+        return unpack(list(out))
 
     def _norm_grad_in(self, state, action):
         """norm_grad_state(state), norm_grad(action) (:415-416)."""

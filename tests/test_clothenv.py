@@ -102,6 +102,66 @@ def test_env_rollout_and_policy_gradient_vs_reference(built_lib, name):
     assert abs(float(loss.detach()) - float(d["loss"])) < 0.02 * abs(float(d["loss"]))
 
 
+PARA = os.path.exists(os.path.join(util.GOLD, "ref_clothenv_para.npz"))
+
+
+@pytest.mark.skipif(not PARA, reason="fixture missing")
+def test_para_obs_and_stiffness_draw_match_reference():
+    """BASELINE configs[3] host logic: apg_para.py:326-329's per-iteration stiffness draw (bit for bit) and
+    cloth_env_para.py:124-131's observation (normalised by eval_min_max_stiff, not by 2000)."""
+    d = _load("para")
+    assert float(d["stiffness_draw"]) == apg.para_stiffness(int(d["it"]), 200, 1800)
+    assert np.float32(float(d["stiffness_draw"])) == d["in_stiffness"].numpy()[0]
+    lo, hi = [float(v) for v in d["eval_min_max_stiff"]]
+    obs = torch.cat([d["in_x"].flatten(1), d["in_primitive0"], d["in_primitive1"],
+                     ((d["in_stiffness"] - lo) / (hi - lo))[:, None]], dim=1)
+    assert obs.shape[1] == 1545 and util.rel_err(obs, d["obs0"]) < 1e-7
+    assert abs(float(d["obs0"][0, -1]) - float(d["in_stiffness"][0]) / 2000.0) > 1e-2      # the round-1 formula was wrong
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not PARA, reason="fixture missing")
+def test_para_env_step_and_gradients_vs_reference(built_lib):
+    """The reference's FoldCloth1ParaEnv.step_diff under the shim vs unidom_b200.envs.FoldCloth1ParaEnv: obs, reward,
+    policy gradient and d loss / d stiffness after one env step (2 000 substeps) with a FLOAT stiffness leaf."""
+    from unidom_b200 import envs
+    from unidom_b200.cloth_simulator import ClothState
+    d = _load("para")
+    B = d["in_x"].shape[0]
+    env = envs.FoldCloth1ParaEnv(B, aux_reward=True, stiffness=float(d["stiffness_draw"]), goal=d["goal"].numpy(),
+                                 eval_min_max_stiff=[float(v) for v in d["eval_min_max_stiff"]])
+    dev = env.device
+    _, st0 = env.reset(shift_xz=d["shift"].numpy())
+    assert torch.equal(st0.stiffness.cpu(), d["in_stiffness"]) and st0.stiffness.is_floating_point()
+    assert util.rel_err(st0.x, d["in_x"]) < 1e-6
+    z = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+    stiff = d["in_stiffness"].to(dev).requires_grad_(True)
+    st = ClothState(x=d["in_x"].to(dev), v=d["in_v"].to(dev), primitive0=d["in_primitive0"].to(dev),
+                    primitive1=d["in_primitive1"].to(dev), action0=d["in_action0"].to(dev), action1=d["in_action1"].to(dev),
+                    key=z, cur_step=z[:, 0].clone(), stiffness=stiff, mu=d["in_mu"].to(dev))
+    params = apg.init_policy(1545, 6, seed=int(d["policy_seed"]))
+    params[-1] = d["param5"].clone()
+    params = [p.to(dev).requires_grad_(True) for p in params]
+    obs = env.get_obs(st)
+    assert util.rel_err(obs, d["obs0"]) < 1e-7
+    actions = apg.sample_actions(apg.policy_apply(params, obs), d["eps"][0].to(dev), True)
+    assert util.rel_err(actions, d["actions0"]) < 1e-5
+    obs1, reward, _, info = env.step_diff(actions, st)
+    ex, er = util.rel_err(info["state"].x, d["x1"]), util.rel_err(reward, d["reward0"])
+    print(f"para env: x rel {ex:.3e} reward rel {er:.3e} (reward {reward.tolist()} ref {d['reward0'].tolist()})")
+    assert torch.equal(obs1[:, -1].cpu(), d["obs1"][:, -1])                # the stiffness column is exact
+    assert ex < 0.2 and er < 0.05                                          # chaotic 2 000 substeps: see DESIGN.md section 2
+    loss = -reward.mean()
+    grads = torch.autograd.grad(loss, params + [stiff])
+    for i in (4, 5):
+        cs, e = util.cosine(grads[i], d[f"gparam{i}"]), util.rel_err(grads[i], d[f"gparam{i}"])
+        print(f"para env: policy gradient layer-3 param {i}: cos {cs:.6f} rel {e:.3e}")
+        assert cs >= 0.999 and e < 1e-3, (i, cs, e)
+    gs, gs_ref = grads[6].cpu(), d["g_stiffness"]
+    print(f"para env: d loss / d stiffness {gs.tolist()}  reference {gs_ref.tolist()}")
+    assert util.rel_err(gs, gs_ref) < max(1e-3, 0.0) or float(gs_ref.abs().max()) < 1e-12, (gs, gs_ref)
+
+
 @pytest.mark.gpu
 def test_tshirt_env_step_on_clusters(built_lib):
     """fold_tshirt (fold_cloth_tshirt_env.py): N = 180, ~3 500 nodes per env -> thread-block clusters; obs keeps every

@@ -148,6 +148,14 @@ def train_iteration(env, params, opt: Adam, state, eps, max_grad_norm: float, si
     return new_params, {"loss": float(loss.detach()), "reward": rewards.detach(), "grad_norm": float(g_norm)}
 
 
+def para_stiffness(it: int, train_min: float, train_max: float) -> float:
+    """apg_para.py:326-329: ONE cloth stiffness per training iteration, `np.random.seed(it);
+    np.random.uniform(train_min_stiff, train_max_stiff)` -- NumPy's legacy global generator, reproduced bit for bit
+    (every rank draws the same value, every env of the iteration shares it)."""
+    import numpy as np
+    return float(np.random.RandomState(it).uniform(train_min, train_max))
+
+
 def main(argv=None):
     """`python -m unidom_b200.apg --env fold_cloth3 --ep_len 3 --num_envs 4 --lr 1e-4 --seed 0 --max_it 2`
     (the reference's README command, apg.py:384-443; one process per GPU under torchrun, envs sharded by rank)."""
@@ -166,6 +174,13 @@ def main(argv=None):
     ap.add_argument("--max_it", type=int, default=2)
     ap.add_argument("--max_grad_norm", type=float, default=0.3)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--goal", default=None, help="goal point cloud (.npy, (Q,3)); the reference reads "
+                    "core/envs/goals/<task>/goal.npy (cloth_env.py:45), which is a data file of the reference")
+    # apg_para.py:540-563
+    ap.add_argument("--train_min_stiff", type=int, default=200)
+    ap.add_argument("--train_max_stiff", type=int, default=1800)
+    ap.add_argument("--eval_min_stiff", type=int, default=100)
+    ap.add_argument("--eval_max_stiff", type=int, default=2000)
     args = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -174,25 +189,33 @@ def main(argv=None):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     first, per = shard_envs(args.num_envs, world, rank)
-    conf = confs.ClothConf()
     para = args.env.endswith("_para")
-    goal = np.zeros((1, 3), np.float32)                  # goals/*.npy are reference data files: pass your own
-    env = envs.ClothEnv(conf, per, 4, confs.fold_cloth_mask(conf), goal=goal, aux_reward=True, device=dev, para=para)
+    goal = np.load(args.goal).astype(np.float32) if args.goal else np.zeros((1, 3), np.float32)
+
+    def make_env(it):
+        if para:
+            stiffness = para_stiffness(it, args.train_min_stiff, args.train_max_stiff)
+            return envs.FoldCloth1ParaEnv(per, aux_reward=True, seed=args.seed, stiffness=stiffness, goal=goal, device=dev,
+                                          eval_min_max_stiff=[args.eval_min_stiff, args.eval_max_stiff])
+        conf = confs.ClothConf()
+        return envs.ClothEnv(conf, per, 4, confs.fold_cloth_mask(conf), goal=goal, aux_reward=True, device=dev)
+
+    env = make_env(0)
     params = init_policy(env.observation_size, env.action_size, seed=args.seed, device=dev)   # replicated
     opt = Adam(sum(p.numel() for p in params), args.lr, dev)
     g = torch.Generator().manual_seed(args.seed + 1)
     for it in range(args.max_it):
+        if para and it:
+            env = make_env(it)                            # apg_para.py:333-339: the env is rebuilt every iteration
         _, state = env.reset()
-        if para:                                          # apg_para.py:326-329: per-env stiffness ~ U(200, 1800)
-            stiff = 200 + 1600 * torch.rand(args.num_envs, generator=g)[first:first + per]
-            state = state._replace(stiffness=stiff.to(dev))
         eps = torch.randn((args.ep_len, args.num_envs, env.action_size), generator=g)[:, first:first + per].to(dev)
         t0 = time.perf_counter()
         params, m = train_iteration(env, params, opt, state, eps, args.max_grad_norm)
         torch.cuda.synchronize(dev)
         pn = float(torch.sqrt(sum((p * p).sum() for p in params)))
+        extra = f" stiffness {float(state.stiffness[0]):.3f}" if para else ""
         print(f"[rank {rank}/{world}] it {it}: loss {m['loss']:.6f} grad_norm {m['grad_norm']:.4e} "
-              f"params_norm {pn:.6f} ({time.perf_counter() - t0:.2f} s, envs {first}..{first + per - 1})", flush=True)
+              f"params_norm {pn:.6f}{extra} ({time.perf_counter() - t0:.2f} s, envs {first}..{first + per - 1})", flush=True)
     if world > 1:
         # replicas must stay in sync: same reduced gradient + same Adam state on every rank
         flat = flatten(params)

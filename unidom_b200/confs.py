@@ -138,6 +138,14 @@ class ClothConf:
         return int(self.N / 5.0)
 
 
+class FoldCloth1ParaConf(ClothConf):
+    """envs/fold_cloth1_para_env.py:15-33: the fold_cloth scene whose `stiffness` the env constructor overwrites
+    (default 900; apg_para.py:326-339 draws one value per training iteration)."""
+    stiffness = 9
+    task = "fold_cloth1"
+    use_substep_obs = True
+
+
 class UnfoldClothConf(ClothConf):
     """envs/unfold_cloth3_env.py:17-35 (unfold_cloth1 alike): the fold_cloth scene with friction mu = 3, max_steps 15;
     reset = lattice + N(0, 1e-4^2) noise + 3 random pick-and-place folds (ClothEnv.random_fold)."""

@@ -112,13 +112,14 @@ class ClothEnv:
     """B200 drop-in for the reference's ClothEnv (fold_cloth1/3, unfold_cloth1/3, fold_cloth1_para)."""
 
     def __init__(self, conf, batch_size, max_steps, cloth_mask, goal=None, aux_reward=False, device="cuda",
-                 para=False, fused=True, obs_stride=1):
+                 para=False, fused=True, obs_stride=1, eval_min_max_stiff=(100, 2000)):
         self.conf, self.batch_size, self.max_steps, self.aux_reward = conf, batch_size, max_steps, aux_reward
         self.fused = fused                                   # scan over the 40 sub-actions inside the library
         self.simulator = ClothSimulator(conf, batch_size, None, cloth_mask, device=device)
         self.device = self.simulator.device
         self.action_size = 6
         self.para = para                                     # cloth_env_para.py: obs carries the normalised stiffness
+        self.eval_min_max_stiff = [float(eval_min_max_stiff[0]), float(eval_min_max_stiff[1])]   # cloth_env_para.py:41
         self.obs_stride = obs_stride                         # fold_cloth_tshirt_env.py:100: every 10th node
         n = self.simulator.n_nodes
         self.observation_size = -(-n // obs_stride) * 3 + 8 + (1 if para else 0)
@@ -126,10 +127,13 @@ class ClothEnv:
         self.goal = torch.from_numpy(goal).to(self.device)
 
     def get_obs(self, state: ClothState) -> torch.Tensor:
-        """cloth_env.py:119-128 (PARTICLE): [x.flatten(), primitive0, primitive1] (+ stiffness/2000, cloth_env_para.py:130)."""
+        """cloth_env.py:119-128 (PARTICLE): [x.flatten(), primitive0, primitive1]; the parameter-aware env appends
+        (stiffness - eval_min) / (eval_max - eval_min) (cloth_env_para.py:124-131; the bounds are the env's
+        `eval_min_max_stiff`, default [100, 2000], fold_cloth1_para_env.py:41)."""
         parts = [state.x[:, ::self.obs_stride].flatten(1), state.primitive0, state.primitive1]
         if self.para:
-            parts.append((state.stiffness.to(state.x.dtype) / 2000.0)[:, None])
+            lo, hi = self.eval_min_max_stiff
+            parts.append(((state.stiffness.to(state.x.dtype) - lo) / (hi - lo))[:, None])
         return torch.cat(parts, dim=1)
 
     def reset(self, shift_xz=None):
@@ -181,6 +185,22 @@ class ClothEnv:
         done = state.cur_step >= self.max_steps
         info = {"state": state, "real_reward": old_chamfer - chamfer + 0.1 * contact}
         return obs, reward, done, info
+
+
+class FoldCloth1ParaEnv(ClothEnv):
+    """core/envs/fold_cloth1_para_env.py:39-53 (GenDOM's parameter-aware fold task, BASELINE configs[3]): same
+    constructor arguments; `stiffness` becomes `conf.stiffness` (a Python number: a float draw makes the state's
+    stiffness leaf float32 and differentiable, the integer default 900 does not), the observation carries the
+    stiffness normalised by `eval_min_max_stiff`; max_steps = 3, observation_size = 1545."""
+
+    def __init__(self, batch_size, conf=None, aux_reward=False, seed=1, stiffness=900, eval_min_max_stiff=(100, 2000),
+                 goal=None, device="cuda", fused=True):
+        from . import confs
+        conf = confs.FoldCloth1ParaConf() if conf is None else conf
+        conf.stiffness = stiffness
+        super().__init__(conf, batch_size, 3, confs.fold_cloth_mask(conf), goal=goal, aux_reward=aux_reward, device=device,
+                         para=True, fused=fused, eval_min_max_stiff=eval_min_max_stiff)
+        assert self.observation_size == 1545
 
 
 # -------------------------------------------------------------------------------------------------------------------
