@@ -49,6 +49,7 @@ static int fail(int code, const char* what) { return set_error(code, what); }
 int cloth_tuning_cta_nodes(int v);   // cloth.cu
 int tuning_sort() { return g_sort; }
 int tuning_stage() { return g_stage; }
+int tuning_warp(int v);   // mpm_particles.cu
 
 bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k) {
   if (!p) return false;
@@ -60,12 +61,14 @@ bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k) {
   if (!(p->dt > 0) || !(p->dx > 0) || !(p->inv_dx > 0) || !(p->p_mass > 0) || !(p->p_vol > 0)) return false;
   long long N = (long long)p->num_envs * p->n_particles;
   long long G = (long long)p->res[0] * p->res[1] * p->res[2];
-  if (N > 0x7fffffffLL / 32 || G > 0x7fffffffLL / 4) return false;
+  if ((N + 32LL * p->num_envs) > 0x7fffffffLL / 32 || G > 0x7fffffffLL / 4) return false;
   memset(k, 0, sizeof(*k));
   k->B = p->num_envs;
   k->n = p->n_particles;
   k->S = p->steps;
   k->N = (int)N;
+  k->n_pad = (p->n_particles + 31) / 32 * 32;
+  k->N_pad = k->B * k->n_pad;
   k->G = (int)G;
   k->rx = p->res[0];
   k->ry = p->res[1];
@@ -108,7 +111,7 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
     off += al(bytes);
     return r;
   };
-  const size_t N = k.N, BG = (size_t)k.B * k.G, P = k.n_prim > 0 ? k.n_prim : 1, S = k.S;
+  const size_t N = k.N, NP = k.N_pad, BG = (size_t)k.B * k.G, P = k.n_prim > 0 ? k.n_prim : 1, S = k.S;
   MpmWs w;
   memset(&w, 0, sizeof(w));
   w.keys = (int32_t*)take(4 * N);
@@ -128,18 +131,18 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
   w.blk_list = (int32_t*)take(4 * (size_t)w.blk_nbuf * k.B * k.nbx * k.nby * k.nbz);
   w.blk_count = (int32_t*)take(4 * S);
   if (!bwd) {
-    w.ps = (float*)take(4 * (size_t)PS_NCOMP * N);
-    w.vt_roll = (float*)take(4 * (size_t)9 * N);
+    w.ps = (float*)take(4 * (size_t)PS_NCOMP * NP);
+    w.vt_roll = (float*)take(4 * (size_t)VT_NCOMP * NP);
     w.grid_raw = (float4*)take(16 * BG);
     w.grid_out = w.grid_raw;
   } else {
-    w.ps = (float*)take(4 * (size_t)PS_NCOMP * N * (S + 1));
+    w.ps = (float*)take(4 * (size_t)PS_NCOMP * NP * (S + 1));
     w.grid_raw = (float4*)take(16 * BG * S);
     w.grid_out = (float4*)take(16 * BG * S);
-    w.svd_s = (float*)take(4 * (size_t)SV_NCOMP * N * S);
+    w.svd_s = (float*)take(4 * (size_t)SV_NCOMP * NP * S);
     w.act_list = (int32_t*)take(4 * BG * S);
     w.act_count = (int32_t*)take(4 * S);
-    w.gs = (float*)take(4 * (size_t)PS_NCOMP * N);
+    w.gs = (float*)take(4 * (size_t)PS_NCOMP * NP);
     w.ggrid = (float4*)take(16 * BG);
     w.g_fk_pos = (float*)take(4 * (size_t)k.B * P * (S + 1) * 3);
     w.g_fk_rot = (float*)take(4 * (size_t)k.B * P * (S + 1) * 4);
@@ -185,6 +188,7 @@ int ud_tuning_set(const char* name, int value) {
   if (name && !strcmp(name, "sort")) { int o = g_sort; g_sort = value; return o; }
   if (name && !strcmp(name, "stage")) { int o = g_stage; g_stage = value; return o; }
   if (name && !strcmp(name, "mark")) { int o = g_mark; g_mark = value; return o; }
+  if (name && !strcmp(name, "warp")) return tuning_warp(value);
   if (name && !strcmp(name, "cloth_cta_nodes")) return cloth_tuning_cta_nodes(value);
   return -1;
 }
@@ -286,7 +290,7 @@ int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
 // bwd-layout workspace (the "tape"): the adjoint's recompute pass, and the whole of the taped forward.
 static void mpm_record_pass(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
                             const float* action, ud_mpm_state* out, MpmWs& ws, cudaStream_t st) {
-  const size_t slot = (size_t)PS_NCOMP * k.N, BG = (size_t)k.B * k.G;
+  const size_t slot = (size_t)PS_NCOMP * k.N_pad, BG = (size_t)k.B * k.G;
   launch_sort(k, in->x, ws, nullptr, st);
   launch_gather_state(k, in, material, h, ws, ws.ps, st);
   launch_fk_fwd(k, in, action, out, ws, st);
@@ -298,9 +302,9 @@ static void mpm_record_pass(const MpmConst& k, const ud_mpm_state* in, const int
   for (int f = 0; f < k.S; ++f) {
     const float* s_in = ws.ps + slot * f;
     float* s_out = ws.ps + slot * (f + 1);
-    float* sv_f = ws.svd_s + (size_t)SV_NCOMP * k.N * f;
+    float* sv_f = ws.svd_s + (size_t)SV_NCOMP * k.N_pad * f;
     launch_p2g(k, s_in, s_out, ws.grid_raw + BG * f, in->mu, in->lamda,
-               (g_svd_warm && (f % SVD_RESTART)) ? sv_f - (size_t)SV_NCOMP * k.N + (size_t)SV_VT * k.N : nullptr, nullptr,
+               (g_svd_warm && (f % SVD_RESTART)) ? sv_f - (size_t)SV_NCOMP * k.N_pad : nullptr, nullptr,
                sv_f, ws, st);
     launch_grid_fwd(k, ws.grid_raw + BG * f, ws.grid_out + BG * f, ws.grid_fix, f, in, ws, st);
     launch_g2p(k, s_in, s_out, ws.grid_out + BG * f, f, ws, st);
@@ -309,7 +313,7 @@ static void mpm_record_pass(const MpmConst& k, const ud_mpm_state* in, const int
 
 static void mpm_reverse_pass(const MpmConst& k, const ud_mpm_state* in, const float* action, const ud_mpm_state* gout,
                              ud_mpm_state* gin, float* gaction, MpmWs& ws, cudaStream_t st) {
-  const size_t slot = (size_t)PS_NCOMP * k.N, BG = (size_t)k.B * k.G;
+  const size_t slot = (size_t)PS_NCOMP * k.N_pad, BG = (size_t)k.B * k.G;
   const size_t P = k.n_prim > 0 ? k.n_prim : 1;
   launch_gather_cot(k, gout, ws, st);
   zero_async(ws.g_fk_pos, 4 * (size_t)k.B * P * (k.S + 1) * 3, st);
@@ -326,7 +330,7 @@ static void mpm_reverse_pass(const MpmConst& k, const ud_mpm_state* in, const fl
     if (f < k.S - 1) launch_grid_clear(k, ws.ggrid, f + 1, ws, st);
     launch_g2p_bwd(k, s_in, ws.grid_out + BG * f, ws, st);
     launch_grid_bwd(k, ws.grid_raw + BG * f, f, in, ws, st);
-    launch_p2g_bwd(k, s_in, ws.svd_s + (size_t)SV_NCOMP * k.N * f, in->mu, in->lamda, f == 0, ws, st);
+    launch_p2g_bwd(k, s_in, ws.svd_s + (size_t)SV_NCOMP * k.N_pad * f, in->mu, in->lamda, f == 0, ws, st);
   }
   launch_fk_bwd(k, in, action, gout, ws, st);
   launch_finish_bwd(k, in, gout, gin, action, gaction, ws, st);
@@ -364,7 +368,7 @@ int ud_mpm_step_fwd_taped(const ud_mpm_params* p, const ud_mpm_state* in, const 
     return fail(UD_E_WORKSPACE, "ud_mpm_step_fwd_taped: tape too small or misaligned");
   cudaStream_t st = (cudaStream_t)stream;
   mpm_record_pass(k, in, material, h, action, out, ws, st);
-  launch_unsort_state(k, ws.ps + (size_t)PS_NCOMP * k.N * k.S, in->J, ws, out, st);
+  launch_unsort_state(k, ws.ps + (size_t)PS_NCOMP * k.N_pad * k.S, in->J, ws, out, st);
   cudaMemcpyAsync(out->friction, in->friction, 4 * (size_t)k.B, cudaMemcpyDeviceToDevice, st);
   cudaMemcpyAsync(out->mu, in->mu, 4 * (size_t)k.B, cudaMemcpyDeviceToDevice, st);
   cudaMemcpyAsync(out->lamda, in->lamda, 4 * (size_t)k.B, cudaMemcpyDeviceToDevice, st);

@@ -9,11 +9,57 @@
 
 namespace ud {
 
-// Sorted particle state is structure-of-arrays: component c of particle g lives at base[c*N + g].
+// Sorted particle state is an array of warp tiles (AoSoA): tile t = gp >> 5 holds 32 consecutive particles of the
+// per-frame sort, gp = env * n_pad + slot (every env starts on a tile boundary).  Inside a tile the components are
+// grouped in QUADS: float4 number (t * NQ + q) * 32 + lane holds components 4q..4q+3 of particle `lane`, so a warp
+// moves 4 components of its 32 particles with ONE 512-byte LDG.128 / STG.128 and every address is
+// tile base + immediate.  State tile (NQ = 6):
 //   0..2 x, 3..5 v, 6..14 C (row-major), 15..23 F (row-major)
-constexpr int PS_X = 0, PS_V = 3, PS_C = 6, PS_F = 15, PS_NCOMP = 24;
-// SVD of F1 kept by the recompute pass for the adjoint: U (row-major 9), s (3), Vt (row-major 9)
-constexpr int SV_U = 0, SV_S = 9, SV_VT = 12, SV_NCOMP = 21;
+constexpr int PS_X = 0, PS_V = 3, PS_C = 6, PS_F = 15, PS_NCOMP = 24, PS_NQ = 6;
+// SVD of F1 kept by the recompute pass for the adjoint: U (row-major 9), s (3), Vt (row-major 9), 3 pad (NQ = 6)
+constexpr int SV_U = 0, SV_S = 9, SV_VT = 12, SV_NCOMP = 24, SV_NQ = 6;
+// forward-only warm-start buffer: Vt (9) + 3 pad (NQ = 3)
+constexpr int VT_NCOMP = 12, VT_NQ = 3;
+
+UD_DEV size_t quad_index(int gp, int q, int nq) { return ((size_t)(gp >> 5) * nq + q) * 32 + (gp & 31); }
+UD_DEV size_t comp_index(int gp, int c, int nq) { return quad_index(gp, c >> 2, nq) * 4 + (c & 3); }
+
+// components [C0, C0+NC) of particle gp from a tile array with NQ quads: one 16-byte load per covering quad
+template <int C0, int NC, int NQ, bool CG = false>
+__device__ __forceinline__ void load_comps(const float* __restrict__ base, int gp, float* out) {
+  const float4* t = reinterpret_cast<const float4*>(base) + quad_index(gp, 0, NQ);
+  constexpr int Q0 = C0 / 4, Q1 = (C0 + NC - 1) / 4;
+#pragma unroll
+  for (int q = Q0; q <= Q1; ++q) {
+    const float4 v = CG ? __ldcg(t + q * 32) : t[q * 32];
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = q * 4 + i;
+      if (c >= C0 && c < C0 + NC) out[c - C0] = e[i];
+    }
+  }
+}
+// stores components [C0, C0+NC): whole quads as one 16-byte store, partially covered quads component by component
+template <int C0, int NC, int NQ>
+__device__ __forceinline__ void store_comps(float* __restrict__ base, int gp, const float* in) {
+  float4* t = reinterpret_cast<float4*>(base) + quad_index(gp, 0, NQ);
+  constexpr int Q0 = C0 / 4, Q1 = (C0 + NC - 1) / 4;
+#pragma unroll
+  for (int q = Q0; q <= Q1; ++q) {
+    const bool full = q * 4 >= C0 && q * 4 + 3 < C0 + NC;
+    if (full) {
+      t[q * 32] = make_float4(in[q * 4 - C0], in[q * 4 + 1 - C0], in[q * 4 + 2 - C0], in[q * 4 + 3 - C0]);
+    } else {
+      float* f = reinterpret_cast<float*>(t + q * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = q * 4 + i;
+        if (c >= C0 && c < C0 + NC) f[i] = in[c - C0];
+      }
+    }
+  }
+}
 // the SVD warm-start chain restarts from V = I every SVD_RESTART substeps (bounds rounding drift of V)
 constexpr int SVD_RESTART = 16;
 // deterministic P2G: values are accumulated as round(v * 2^52) in int64 (range +-2048, resolution 2.2e-16);
@@ -34,7 +80,7 @@ struct MpmWs {
   int32_t* mat_s;       // [N] material in sorted order
   float* h_s;           // [N] hardness in sorted order
   // state
-  float* ps;            // fwd: [24*N]; bwd: [(S+1)*24*N] start-of-substep states
+  float* ps;            // fwd: [24*N_pad]; bwd: [(S+1)*24*N_pad] start-of-substep states (tiles, see above)
   float4* grid_raw;     // fwd: [B*G]; bwd: [S*B*G] scattered (p,m)
   float4* grid_out;     // fwd: == grid_raw; bwd: [S*B*G] updated velocities
   long long* grid_fix;  // deterministic P2G only: [B*G*4] 64-bit fixed-point accumulators of one substep
@@ -43,17 +89,17 @@ struct MpmWs {
   int blk_nbuf;         // fwd: 2 (k_grid_clear reads the previous substep's list); bwd: S (the reverse pass re-zeroes
                         // the cotangent grid block by block)
   int32_t* blk_count;   // [S] number of listed blocks per substep
-  float* vt_roll;       // fwd only: [9*N] V^T of the previous substep's SVD (warm start)
+  float* vt_roll;       // fwd only: [12*N_pad] V^T of the previous substep's SVD (warm start)
   int32_t* act_list;    // bwd only: [S][B*G] cells listed by the recompute pass for the grid adjoint
   int32_t* act_count;   // bwd only: [S]
-  float* svd_s;         // bwd only: [S*21*N] SVD of F1 per substep (written by the recompute P2G)
+  float* svd_s;         // bwd only: [S*24*N_pad] SVD of F1 per substep (written by the recompute P2G)
   float* fk_pos;        // [B*P*(S+1)*3] (row S = clamp copy of row S-1)
   float* fk_rot;        // [B*P*(S+1)*4]
   float* fk_vw;         // [B*P*6] per-substep (v,w) row
   float* fk_act;        // [B*P*6] clipped action
   float* jrows;         // [B*S*9] rows i<3 of C' of original particles 0..2 (J update, :327)
   // adjoint
-  float* gs;            // [24*N] cotangent SoA (sorted order)
+  float* gs;            // [24*N_pad] cotangent tiles (sorted order)
   float4* ggrid;        // [B*G]
   float* g_fk_pos;      // [B*P*(S+1)*3]
   float* g_fk_rot;      // [B*P*(S+1)*4]

@@ -9,6 +9,7 @@ namespace ud {
 
 struct MpmConst {
   int B, n, S, N;            // envs, particles/env, substeps, B*n
+  int n_pad, N_pad;          // n rounded up to a whole warp tile (32), B*n_pad: extent of the sorted tile arrays
   int G, rx, ry, rz, n_grid; // cells/env, res, conf.n_grid
   int nbx, nby, nbz, NK;     // 4x4x4 blocks per axis, keys per env (= nbx*nby*nbz*64)
   float dt, dx, inv_dx, p_mass;

@@ -11,12 +11,16 @@ namespace ud {
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 static inline dim3 pgrid(const MpmConst& k, int block) { return dim3(cdiv(k.n, block), k.B); }
 
-// particle index of this thread: blockIdx.y = env, blockIdx.x*blockDim.x + threadIdx.x = slot in env
+// particle index of this thread: blockIdx.y = env, blockIdx.x*blockDim.x + threadIdx.x = slot in env.
+//   g  = env*n + slot      index into the per-particle arrays (perm, material, h, AoS leaves)
+//   gp = env*n_pad + slot  index into the sorted tile arrays (mpm_internal.h); slots in [n, n_pad) are padding that
+//                          exists in memory (dead lanes may read it, never write it)
 #define UD_PARTICLE_INDEX(k, env, g)                         \
   int env = blockIdx.y;                                      \
   int slot_ = blockIdx.x * blockDim.x + threadIdx.x;         \
   bool live_ = slot_ < (k).n;                                \
-  int g = env * (k).n + (live_ ? slot_ : 0);
+  int g = env * (k).n + (live_ ? slot_ : 0);                 \
+  int gp = env * (k).n_pad + (slot_ < (k).n_pad ? slot_ : 0);
 
 // ------------------------------------------------------------------------------------------------
 // Binning: key = 4x4x4-block-major cell key of base = int32(x*inv_dx - 0.5) (mpm_simulator.py:233),
@@ -126,20 +130,26 @@ __global__ void k_gather_state(MpmConst k, const float* __restrict__ x, const fl
                                const int32_t* __restrict__ perm, float* __restrict__ ps,
                                int32_t* __restrict__ mat_s, float* __restrict__ h_s) {
   UD_PARTICLE_INDEX(k, env, g);
-  if (!live_) return;
-  int p = perm[g];
-  size_t o = (size_t)env * k.n + p;
-  const size_t N = k.N;
+  if (slot_ >= k.n_pad) return;
+  float st[PS_NCOMP];
+  if (live_) {
+    int p = perm[g];
+    size_t o = (size_t)env * k.n + p;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) ps[(PS_X + c) * N + g] = nan_to_num(x[3 * o + c]);
+    for (int c = 0; c < 3; ++c) st[PS_X + c] = nan_to_num(x[3 * o + c]);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) ps[(PS_V + c) * N + g] = nan_to_num(v[3 * o + c]);
+    for (int c = 0; c < 3; ++c) st[PS_V + c] = nan_to_num(v[3 * o + c]);
 #pragma unroll
-  for (int c = 0; c < 9; ++c) ps[(PS_C + c) * N + g] = nan_to_num(C[9 * o + c]);
+    for (int c = 0; c < 9; ++c) st[PS_C + c] = nan_to_num(C[9 * o + c]);
 #pragma unroll
-  for (int c = 0; c < 9; ++c) ps[(PS_F + c) * N + g] = nan_to_num(F[9 * o + c]);
-  mat_s[g] = material[p];
-  h_s[g] = h[p];
+    for (int c = 0; c < 9; ++c) st[PS_F + c] = nan_to_num(F[9 * o + c]);
+    mat_s[g] = material[p];
+    h_s[g] = h[p];
+  } else {  // padding of the env's last tile: a harmless particle (F = I) that dead lanes may read
+#pragma unroll
+    for (int c = 0; c < PS_NCOMP; ++c) st[c] = (c == PS_F || c == PS_F + 4 || c == PS_F + 8) ? 1.f : 0.f;
+  }
+  store_comps<0, PS_NCOMP, PS_NQ>(ps, gp, st);
 }
 
 void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
@@ -394,20 +404,76 @@ constexpr size_t g2pb_smem_bytes() { return g2pb_tile_offset() + sizeof(float4) 
 // {momentum, mass} (p2g_micro, :178-194) as ONE 16-byte vector reduction per node
 // (red.global.add.v4.f32 -> REDG.E.ADD.F32x4).  Out-of-range nodes are dropped (JAX scatter rule).
 // ------------------------------------------------------------------------------------------------
-UD_DEV void load_particle(const float* ps, size_t N, int g, float x[3], float v[3], Mat3& C,
-                          Mat3& F) {
+__device__ __forceinline__ void load_particle(const float* __restrict__ ps, int gp, float x[3], float v[3], Mat3& C, Mat3& F) {
+  float st[PS_NCOMP];
+  load_comps<0, PS_NCOMP, PS_NQ>(ps, gp, st);   // 6 x LDG.128, tile base + immediate
 #pragma unroll
-  for (int c = 0; c < 3; ++c) x[c] = ps[(PS_X + c) * N + g];
+  for (int c = 0; c < 3; ++c) x[c] = st[PS_X + c];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) v[c] = ps[(PS_V + c) * N + g];
+  for (int c = 0; c < 3; ++c) v[c] = st[PS_V + c];
 #pragma unroll
-  for (int c = 0; c < 9; ++c) C.m[c] = ps[(PS_C + c) * N + g];
+  for (int c = 0; c < 9; ++c) C.m[c] = st[PS_C + c];
 #pragma unroll
-  for (int c = 0; c < 9; ++c) F.m[c] = ps[(PS_F + c) * N + g];
+  for (int c = 0; c < 9; ++c) F.m[c] = st[PS_F + c];
 }
 
-// MODE 0: staged scatter + fp32 vector REDs; 1: staged + 64-bit fixed-point REDs (deterministic);
+// Per-particle front half of P2G, shared by the scatter variants: load, F update, SVD (warm-started from the previous
+// substep's V^T), plastic clip, stress; stores F' (+ V^T for the next warm start, or the whole SVD in the recompute
+// pass).  Returns the stencil and the affine scatter value at node (a,b,c):
+//   wt * (u + a*Ac[0] + b*Ac[1] + c*Ac[2]),  u = p_mass v - dx A fx,  Ac[j] = dx * column j of A
+// `vt_in` is the forward's warm-start buffer (VT tile) or, in the recompute pass (svd_out != null), the previous
+// substep's SVD tile.
+__device__ __forceinline__ void p2g_front(const MpmConst& k, int env, int g, int gp, bool wr, const float* __restrict__ ps_in,
+                                          float* __restrict__ ps_out, const float* __restrict__ mu_s,
+                                          const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
+                                          const float* __restrict__ h_s, const float* __restrict__ vt_in,
+                                          float* __restrict__ vt_out, float* __restrict__ svd_out, Stencil& st,
+                                          float u[3], float Ac[3][3]) {
+  float x[3], v[3];
+  Mat3 C, F;
+  load_particle(ps_in, gp, x, v, C, F);
+  make_stencil(x, k.inv_dx, st);
+  Consti o;
+  float vt0[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  const bool warm = vt_in != nullptr;  // grid-uniform
+  if (warm) {
+    if (svd_out) load_comps<SV_VT, 9, SV_NQ>(vt_in, gp, vt0);
+    else load_comps<0, 9, VT_NQ>(vt_in, gp, vt0);
+  }
+  constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+  svd3_ws(o.F1, o.U, o.s, o.Vt, warm, vt0);
+  constitutive_post(k, C, o);
+  if (wr) {   // padding lanes of an env's last tile write too: the next substep's dead lanes read initialised memory
+    store_comps<PS_F, 9, PS_NQ>(ps_out, gp, o.F2.m);
+    if (vt_out) {
+      float t[VT_NCOMP];
+#pragma unroll
+      for (int c = 0; c < VT_NCOMP; ++c) t[c] = c < 9 ? o.Vt.m[c] : 0.f;
+      store_comps<0, VT_NCOMP, VT_NQ>(vt_out, gp, t);
+    }
+    if (svd_out) {  // recompute pass of the adjoint: keep the SVD so that P2G^T does not redo it
+      float t[SV_NCOMP];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) t[SV_U + c] = o.U.m[c];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) t[SV_S + c] = o.s[c];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) t[SV_VT + c] = o.Vt.m[c];
+      t[21] = t[22] = t[23] = 0.f;
+      store_comps<0, SV_NCOMP, SV_NQ>(svd_out, gp, t);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Ac[j][i] = k.dx * o.affine(i, j);
+    u[i] = k.p_mass * v[i] - (Ac[0][i] * st.fx[0] + Ac[1][i] * st.fx[1] + Ac[2][i] * st.fx[2]);
+  }
+}
+
+// MODE 0: CTA-staged scatter + fp32 vector REDs; 1: staged + 64-bit fixed-point REDs (deterministic);
 //      2: A/B baseline -- every particle issues its 27 vector REDs itself (no shared memory, no grouping)
+// (round-1 kernel, kept as the A/B partner of k_p2g_warp: ud_tuning_set("warp", 0))
 template <int MODE>
 __global__ void __launch_bounds__(P2G_BLOCK, 12)   // 80 registers: 12 CTAs per SM, what the staging shared memory allows too
 k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
@@ -419,52 +485,15 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
   constexpr int STG_PAD = stg_pad<P2G_BLOCK>();
   StageMeta<P2G_BLOCK>& meta = *reinterpret_cast<StageMeta<P2G_BLOCK>*>(sv + P2G_NPH * 4 * STG_PAD);
   UD_PARTICLE_INDEX(k, env, g);
-  const size_t N = k.N;
-  float x[3], v[3];
-  Mat3 C, F;
-  load_particle(ps_in, N, g, x, v, C, F);
   Stencil st;
-  make_stencil(x, k.inv_dx, st);
+  float u[3], Ac[3][3];
+  p2g_front(k, env, g, gp, slot_ < k.n_pad, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, st, u, Ac);
   constexpr bool DET = MODE == 1;
   int row = 0;
   if (MODE != 2)
     row = stage_group<false, P2G_BLOCK>(k, meta, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base,
                                         blk_flag + (size_t)env * (k.nbx * k.nby * k.nbz));
-  Consti o;
-  float vt0[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
-  const bool warm = vt_in != nullptr;  // warm start of the Jacobi SVD from the previous substep's V^T (grid-uniform)
-  if (warm) {
-#pragma unroll
-    for (int c = 0; c < 9; ++c) vt0[c] = vt_in[c * N + g];
-  }
-  constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
-  svd3_ws(o.F1, o.U, o.s, o.Vt, warm, vt0);
-  constitutive_post(k, C, o);
-  if (live_) {
-#pragma unroll
-    for (int c = 0; c < 9; ++c) ps_out[(PS_F + c) * N + g] = o.F2.m[c];
-    if (vt_out) {
-#pragma unroll
-      for (int c = 0; c < 9; ++c) vt_out[c * N + g] = o.Vt.m[c];
-    }
-    if (svd_out) {  // recompute pass of the adjoint: keep the SVD so that P2G^T does not redo it
-#pragma unroll
-      for (int c = 0; c < 9; ++c) svd_out[(SV_U + c) * N + g] = o.U.m[c];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) svd_out[(SV_S + c) * N + g] = o.s[c];
-#pragma unroll
-      for (int c = 0; c < 9; ++c) svd_out[(SV_VT + c) * N + g] = o.Vt.m[c];
-    }
-  }
-  // value at node (a,b,c):  wt * (u + a*Ax + b*Ay + c*Az),  u = p_mass v - dx A fx,  A* = dx * columns of A
   const float lw = live_ ? 1.f : 0.f;
-  float u[3], Ac[3][3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) Ac[j][i] = k.dx * o.affine(i, j);
-    u[i] = k.p_mass * v[i] - (Ac[0][i] * st.fx[0] + Ac[1][i] * st.fx[1] + Ac[2][i] * st.fx[2]);
-  }
   if constexpr (MODE == 2) {
     float4* genv = grid + (size_t)env * k.G;
     if (live_) {
@@ -520,11 +549,196 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-local staged scatter (round 2).  A WARP owns one tile of 32 consecutive particles of the per-frame sort and
+// never talks to another warp: no block barrier, no cross-warp merge.
+//   group : __match_any_sync on the base cell -> segments (lanes sharing a cell); rows of a segment are made contiguous
+//           (segments in leader-lane order, rows in lane order), so the reduction order is fixed
+//   stage : every lane writes its node values as float4 {px,py,pz,m} at tile[row][node] (one STS.128 per node; the
+//           432-byte row stride is conflict-free for 16-byte accesses)
+//   flush : lane = (node, row group) sums its node's float4 column over the rows of each segment (LDS.128 + 4 FADD per
+//           row) and issues ONE 16-byte vector RED per (segment, node)
+// NW = 1: one window of all 27 nodes (13.8 KB per warp); NW = 3: three windows of 9 nodes (one per x offset, 4.6 KB
+// per warp), each flushed by 9 nodes x 3 row groups.
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+struct WarpGroup {
+  unsigned mm;   // lanes whose particle sits in my base cell
+  unsigned lb;   // leader lanes, one per distinct cell of the warp
+  int row;       // my staging row
+};
+__device__ __forceinline__ WarpGroup warp_group(int key) {
+  const int lane = threadIdx.x & 31;
+  WarpGroup g;
+  g.mm = __match_any_sync(FULL, key);
+  const int lead = __ffs(g.mm) - 1;
+  g.lb = __ballot_sync(FULL, lane == lead);
+  int start = 0;
+  for (unsigned b = g.lb; b; b &= b - 1) {   // warp-uniform trip count = distinct cells (2-4 in the plasticine scene)
+    const int L = __ffs(b) - 1;
+    const int cnt = __popc(__shfl_sync(FULL, g.mm, L));
+    start += L < lead ? cnt : 0;
+  }
+  g.row = start + __popc(g.mm & ((1u << lane) - 1u));
+  return g;
+}
+template <int NW> constexpr int warp_tile_nodes() { return 27 / NW; }
+template <int NW> constexpr size_t warp_tile_bytes() { return sizeof(float4) * 32 * warp_tile_nodes<NW>(); }
+
+// Flush of one window: nodes [j0, j0 + WN).  `tile` is this warp's [32][WN] float4 array.
+template <int NW, bool CLAMP, bool DET>
+__device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __restrict__ tile, const WarpGroup& g,
+                                           const int base[3], bool live, int j0, float4* __restrict__ genv,
+                                           int32_t* __restrict__ blk_flag) {
+  constexpr int WN = warp_tile_nodes<NW>(), RG = NW == 1 ? 1 : 3;
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < WN * RG;
+  const int jl = act ? lane % WN : 0, h = act ? lane / WN : 0;
+  const int j = j0 + jl;
+  const int a = j / 9, b = (j / 3) % 3, c = j % 3;
+  int s0 = 0;
+  for (unsigned bits = g.lb; bits; bits &= bits - 1) {
+    const int L = __ffs(bits) - 1;
+    const int cnt = __popc(__shfl_sync(FULL, g.mm, L));
+    const int bx = __shfl_sync(FULL, base[0], L), by = __shfl_sync(FULL, base[1], L), bz = __shfl_sync(FULL, base[2], L);
+    const int lv = __shfl_sync(FULL, (int)live, L);
+    const int r_begin = s0;
+    s0 += cnt;
+    if (!lv) continue;   // warp-uniform: the padding lanes of an env's last tile
+    int ix, iy, iz;
+    if (CLAMP) {
+      ix = idx_gather(bx + a, k.rx);
+      iy = idx_gather(by + b, k.ry);
+      iz = idx_gather(bz + c, k.rz);
+    } else {
+      ix = idx_scatter(bx + a, k.rx);
+      iy = idx_scatter(by + b, k.ry);
+      iz = idx_scatter(bz + c, k.rz);
+    }
+    const bool ok = act && (ix | iy | iz) >= 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+      // rows [lo, hi) of the segment for my row group, summed in row order
+      const int per = (cnt + RG - 1) / RG;
+      const int lo = r_begin + min(h * per, cnt), hi = r_begin + min((h + 1) * per, cnt);
+      const float4* p = tile + lo * WN + jl;
+      int left = hi - lo;
+      for (; left >= 4; left -= 4) {
+        const float4 q0 = p[0], q1 = p[WN], q2 = p[2 * WN], q3 = p[3 * WN];
+        p += 4 * WN;
+        acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
+        acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
+        acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
+        acc.x += q3.x; acc.y += q3.y; acc.z += q3.z; acc.w += q3.w;
+      }
+      for (; left > 0; --left) {
+        const float4 q0 = *p;
+        p += WN;
+        acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
+      }
+    }
+    if (RG == 3) {   // row groups 1, 2 hand their partial sums to group 0 (fixed order)
+      const float4 t1 = make_float4(__shfl_down_sync(FULL, acc.x, WN), __shfl_down_sync(FULL, acc.y, WN),
+                                    __shfl_down_sync(FULL, acc.z, WN), __shfl_down_sync(FULL, acc.w, WN));
+      const float4 t2 = make_float4(__shfl_down_sync(FULL, acc.x, 2 * WN), __shfl_down_sync(FULL, acc.y, 2 * WN),
+                                    __shfl_down_sync(FULL, acc.z, 2 * WN), __shfl_down_sync(FULL, acc.w, 2 * WN));
+      acc.x = (acc.x + t1.x) + t2.x; acc.y = (acc.y + t1.y) + t2.y; acc.z = (acc.z + t1.z) + t2.z; acc.w = (acc.w + t1.w) + t2.w;
+    }
+    if (!ok || h != 0) continue;
+    const int cell = (ix * k.ry + iy) * k.rz + iz;
+    if (DET) {  // UD_P2G_DETERMINISTIC: 4 integer REDs on 64-bit fixed point (associative => order-independent)
+      unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(genv) + 4 * (size_t)cell;
+      atomicAdd(acc64 + 0, (unsigned long long)__double2ll_rn((double)acc.x * FIX_SCALE));
+      atomicAdd(acc64 + 1, (unsigned long long)__double2ll_rn((double)acc.y * FIX_SCALE));
+      atomicAdd(acc64 + 2, (unsigned long long)__double2ll_rn((double)acc.z * FIX_SCALE));
+      atomicAdd(acc64 + 3, (unsigned long long)__double2ll_rn((double)acc.w * FIX_SCALE));
+    } else {
+      atomicAdd(&genv[cell], acc);
+    }
+    // a 3-node span touches at most two 4x4x4 blocks per axis, both reached by its end nodes: corners mark everything
+    if (!CLAMP && blk_flag && (k.mark == 1 || (k.mark == 2 && a != 1 && b != 1 && c != 1))) mark_block(k, blk_flag, ix, iy, iz);
+  }
+}
+
+constexpr int P2GW_BLOCK = 128;   // 4 independent warps per CTA (the CTA is only the unit shared memory is carved in)
+template <int NW, bool DET>
+__global__ void __launch_bounds__(P2GW_BLOCK)
+k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
+           const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
+           const float* __restrict__ h_s, const float* __restrict__ vt_in, float* __restrict__ vt_out,
+           float* __restrict__ svd_out, int32_t* __restrict__ blk_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int WN = warp_tile_nodes<NW>();
+  float4* tile = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * warp_tile_bytes<NW>());   // [32][WN]
+  UD_PARTICLE_INDEX(k, env, g);
+  if (slot_ - (int)(threadIdx.x & 31) >= k.n) return;   // warp-uniform: tiles beyond the env's last particle
+  Stencil st;
+  float u[3], Ac[3][3];
+  p2g_front(k, env, g, gp, true, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, st, u, Ac);
+  const WarpGroup wg = warp_group(live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY);
+  float4* genv = grid + (size_t)env * k.G * (DET ? 2 : 1);   // DET: the int64 accumulator array (32 B per cell)
+  int32_t* flag_env = blk_flag + (size_t)env * (k.nbx * k.nby * k.nbz);
+  float4* myrow = tile + wg.row * WN;
+  const float lw = live_ ? 1.f : 0.f;
+#pragma unroll
+  for (int win = 0; win < NW; ++win) {
+    if (win) __syncwarp();   // the previous window has been flushed
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (NW == 3 && a != win) continue;
+      const float wa = st.w[a][0] * lw;
+      const float ua[3] = {u[0] + (float)a * Ac[0][0], u[1] + (float)a * Ac[0][1], u[2] + (float)a * Ac[0][2]};
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const float wab = wa * st.w[b][1];
+        const float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float wt = wab * st.w[c][2];
+          myrow[(NW == 3 ? 0 : a * 9) + b * 3 + c] =
+              make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
+                          wt * (uab[2] + (float)c * Ac[2][2]), wt * k.p_mass);
+        }
+      }
+    }
+    __syncwarp();
+    warp_flush<NW, false, DET>(k, tile, wg, st.base, live_, win * WN, genv, flag_env);
+  }
+}
+
+static int g_warp_nw = 1;   // staging windows of the warp-local kernels (1 or 3); 0 = the round-1 CTA-staged kernels
+int tuning_warp(int v) {
+  int o = g_warp_nw;
+  if (v == 0 || v == 1 || v == 3) g_warp_nw = v;
+  return o;
+}
+
+template <int NW, bool DET>
+static void launch_p2g_warp(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
+                            const float* la_s, const float* vt_in, float* vt_out, float* svd_out, const MpmWs& ws,
+                            cudaStream_t st) {
+  const size_t smem = warp_tile_bytes<NW>() * (P2GW_BLOCK / 32);
+  // per-DEVICE attribute (one host thread per device under pmap): set on every launch
+  cudaFuncSetAttribute(k_p2g_warp<NW, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_p2g_warp<NW, DET><<<pgrid(k, P2GW_BLOCK), P2GW_BLOCK, smem, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s,
+                                                                     vt_in, vt_out, svd_out, ws.blk_flag);
+}
 
 void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
                 const float* la_s, const float* vt_in, float* vt_out, float* svd_out, const MpmWs& ws,
                 cudaStream_t st) {
   KScope ks_(KC_P2G, st);
+  if (tuning_stage() && g_warp_nw) {
+    float4* fix = reinterpret_cast<float4*>(ws.grid_fix);
+    if (g_warp_nw == 1) {
+      if (fix) launch_p2g_warp<1, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, ws, st);
+      else launch_p2g_warp<1, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, ws, st);
+    } else {
+      if (fix) launch_p2g_warp<3, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, ws, st);
+      else launch_p2g_warp<3, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, ws, st);
+    }
+    return;
+  }
   // the attribute is per DEVICE (a process may drive several, one host thread each: SURVEY 8b): set it on every launch
   cudaFuncSetAttribute(k_p2g<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH));
   cudaFuncSetAttribute(k_p2g<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH));
@@ -548,14 +762,14 @@ __global__ void __launch_bounds__(UD_BLOCK, 8)
 k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ grid,
       const int32_t* __restrict__ perm, float* __restrict__ jrows, int substep) {
   // Warp-local node tile: the 32 particles of a warp sit in a few cells (sorted order), so the warp fetches the 27
-  // grid velocities of each DISTINCT base cell once (<= G2P_TILE_CELLS cells, one coalesced pass, no block barrier)
-  // and every lane reads its stencil from shared memory; warps spanning more cells gather from L1/L2 as before.
+  // grid velocities of each DISTINCT base cell once (<= G2P_TILE_CELLS cells, no block barrier) and every lane reads
+  // its stencil from shared memory; warps spanning more cells gather from L1/L2 as before.
   __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_CELLS * 27];
+  __shared__ int4 wbase[UD_BLOCK / 32][G2P_TILE_CELLS];
   UD_PARTICLE_INDEX(k, env, g);
-  const size_t N = k.N;
+  if (slot_ - (int)(threadIdx.x & 31) >= k.n) return;   // warp-uniform
   float x[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) x[c] = ps_in[(PS_X + c) * N + g];
+  load_comps<PS_X, 3, PS_NQ>(ps_in, gp, x);
   Stencil st;
   make_stencil(x, k.inv_dx, st);
   const float4* genv = grid + (size_t)env * k.G;
@@ -569,21 +783,36 @@ k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ 
   const bool tiled = ngroups <= G2P_TILE_CELLS && ngroups > 0;    // warp-uniform
   float4* tile = wtile[threadIdx.x >> 5];
   if (tiled) {
+    int4* cb = wbase[threadIdx.x >> 5];
+    if (lane == leadlane && live_) cb[gid] = make_int4(st.base[0], st.base[1], st.base[2], 0);
+    __syncwarp();
     const int total = ngroups * 27;
-    for (int e0 = 0; e0 < total; e0 += 32) {                       // warp-uniform trip count
-      const int e = e0 + lane;
-      const int ge = min(e / 27, ngroups - 1), j = e - (e / 27) * 27;
-      const int src = __fns(lb, 0, ge + 1);                        // lane of the ge-th leader
-      const int b0 = __shfl_sync(0xffffffffu, st.base[0], src), b1 = __shfl_sync(0xffffffffu, st.base[1], src),
-                b2 = __shfl_sync(0xffffffffu, st.base[2], src);
+    // all loads of the tile are issued before the first one is consumed (one L2 round trip instead of up to four)
+    float4 tmp[(G2P_TILE_CELLS * 27 + 31) / 32];
+#pragma unroll
+    for (int it = 0; it < (G2P_TILE_CELLS * 27 + 31) / 32; ++it) {
+      const int e = it * 32 + lane;
       if (e < total) {
-        const int ix = idx_gather(b0 + j / 9, k.rx), iy = idx_gather(b1 + (j / 3) % 3, k.ry), iz = idx_gather(b2 + j % 3, k.rz);
-        tile[e] = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
+        const int ge = e / 27, j = e - ge * 27;
+        const int4 b = cb[ge];
+        const int ix = idx_gather(b.x + j / 9, k.rx), iy = idx_gather(b.y + (j / 3) % 3, k.ry), iz = idx_gather(b.z + j % 3, k.rz);
+        tmp[it] = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
       }
+    }
+#pragma unroll
+    for (int it = 0; it < (G2P_TILE_CELLS * 27 + 31) / 32; ++it) {
+      const int e = it * 32 + lane;
+      if (e < total) tile[e] = tmp[it];
     }
     __syncwarp();
   }
-  if (!live_) return;
+  if (!live_) {   // padding lanes of the env's last tile stay a harmless particle at the origin
+    float z[15];
+#pragma unroll
+    for (int c = 0; c < 15; ++c) z[c] = 0.f;
+    store_comps<0, 15, PS_NQ>(ps_out, gp, z);
+    return;
+  }
   const float4* my_tile = tile + gid * 27;
   float nv[3] = {0.f, 0.f, 0.f};
   Mat3 nC = mat_zero();
@@ -623,17 +852,21 @@ k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ 
   };
   if (tiled) nodes(std::true_type{});
   else nodes(std::false_type{});
+  float outv[15];
   {  // C' = 4 inv_dx sum wt g (x) d   (the factor is applied once, after the 27-node sum)
     const float c4 = 4.f * k.inv_dx;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) nC.m[c] *= c4;
+    for (int c = 0; c < 9; ++c) {
+      nC.m[c] *= c4;
+      outv[PS_C + c] = nC.m[c];
+    }
   }
 #pragma unroll
-  for (int c = 0; c < 3; ++c) ps_out[(PS_X + c) * N + g] = x[c] + k.dt * nv[c];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) ps_out[(PS_V + c) * N + g] = nv[c];
-#pragma unroll
-  for (int c = 0; c < 9; ++c) ps_out[(PS_C + c) * N + g] = nC.m[c];
+  for (int c = 0; c < 3; ++c) {
+    outv[PS_X + c] = x[c] + k.dt * nv[c];
+    outv[PS_V + c] = nv[c];
+  }
+  store_comps<0, 15, PS_NQ>(ps_out, gp, outv);
   int p = perm[g];
   if (p < 3) {
     float* jr = jrows + ((size_t)env * k.S + substep) * 9 + p * 3;
@@ -656,17 +889,18 @@ __global__ void k_unsort_state(MpmConst k, const float* __restrict__ ps, const f
                                float* __restrict__ F, float* __restrict__ J) {
   UD_PARTICLE_INDEX(k, env, g);
   if (!live_) return;
-  const size_t N = k.N;
   int p = perm[g];
   size_t o = (size_t)env * k.n + p;
+  float st[PS_NCOMP];
+  load_comps<0, PS_NCOMP, PS_NQ>(ps, gp, st);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) x[3 * o + c] = ps[(PS_X + c) * N + g];
+  for (int c = 0; c < 3; ++c) x[3 * o + c] = st[PS_X + c];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) v[3 * o + c] = ps[(PS_V + c) * N + g];
+  for (int c = 0; c < 3; ++c) v[3 * o + c] = st[PS_V + c];
 #pragma unroll
-  for (int c = 0; c < 9; ++c) C[9 * o + c] = ps[(PS_C + c) * N + g];
+  for (int c = 0; c < 9; ++c) C[9 * o + c] = st[PS_C + c];
 #pragma unroll
-  for (int c = 0; c < 9; ++c) F[9 * o + c] = ps[(PS_F + c) * N + g];
+  for (int c = 0; c < 9; ++c) F[9 * o + c] = st[PS_F + c];
   float j = nan_to_num(J_in[o]);
   int nr = min(3, k.n);
   for (int f = 0; f < k.S; ++f) {
@@ -699,23 +933,42 @@ __global__ void k_gather_cot(MpmConst k, const float* __restrict__ gx, const flo
                              const float* __restrict__ gC, const float* __restrict__ gF,
                              const int32_t* __restrict__ perm, float* __restrict__ gs) {
   UD_PARTICLE_INDEX(k, env, g);
-  if (!live_) return;
-  int p = perm[g];
-  size_t o = (size_t)env * k.n + p;
-  const size_t N = k.N;
+  if (slot_ >= k.n_pad) return;
+  float st[PS_NCOMP];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) gs[(PS_X + c) * N + g] = gx ? gx[3 * o + c] : 0.f;
+  for (int c = 0; c < PS_NCOMP; ++c) st[c] = 0.f;   // padding slots carry zero cotangents
+  if (live_) {
+    int p = perm[g];
+    size_t o = (size_t)env * k.n + p;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) gs[(PS_V + c) * N + g] = gv ? gv[3 * o + c] : 0.f;
+    for (int c = 0; c < 3; ++c) st[PS_X + c] = gx ? gx[3 * o + c] : 0.f;
 #pragma unroll
-  for (int c = 0; c < 9; ++c) gs[(PS_C + c) * N + g] = gC ? gC[9 * o + c] : 0.f;
+    for (int c = 0; c < 3; ++c) st[PS_V + c] = gv ? gv[3 * o + c] : 0.f;
 #pragma unroll
-  for (int c = 0; c < 9; ++c) gs[(PS_F + c) * N + g] = gF ? gF[9 * o + c] : 0.f;
+    for (int c = 0; c < 9; ++c) st[PS_C + c] = gC ? gC[9 * o + c] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) st[PS_F + c] = gF ? gF[9 * o + c] : 0.f;
+  }
+  store_comps<0, PS_NCOMP, PS_NQ>(gs, gp, st);
 }
 
 void launch_gather_cot(const MpmConst& k, const ud_mpm_state* gout, const MpmWs& ws, cudaStream_t st) {
   KScope ks_(KC_GATHER, st);
   k_gather_cot<<<pgrid(k, 256), 256, 0, st>>>(k, gout->x, gout->v, gout->C, gout->F, ws.perm, ws.gs);
+}
+
+// loads of G2P^T: the particle's position and the cotangents of (x', v', C') it produced
+__device__ __forceinline__ void g2pb_load(const MpmConst& k, const float* __restrict__ ps_in, const float* __restrict__ gs,
+                                          int gp, float x[3], float gxo[3], float gvt[3], Mat3& gC) {
+  load_comps<PS_X, 3, PS_NQ>(ps_in, gp, x);
+  float g15[15];
+  load_comps<0, 15, PS_NQ>(gs, gp, g15);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) gxo[c] = g15[PS_X + c];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) gvt[c] = g15[PS_V + c] + k.dt * gxo[c];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) gC.m[c] = g15[PS_C + c];
 }
 
 // G2P^T: v' = sum wt g ; C' = sum 4 inv_dx wt g (x) d ; x' = x + dt v'   (d = off - fx)
@@ -730,17 +983,9 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   StageMeta<G2PB_BLOCK>& meta = *reinterpret_cast<StageMeta<G2PB_BLOCK>*>(sv + G2PB_NPH * 3 * STG_PAD);
   float4* tile = reinterpret_cast<float4*>(smem_raw + g2pb_tile_offset());  // [G2PB_TILE_RUNS][27]
   UD_PARTICLE_INDEX(k, env, g);
-  const size_t N = k.N;
   float x[3], gxo[3], gvt[3];
   Mat3 gC;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) x[c] = ps_in[(PS_X + c) * N + g];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) gxo[c] = gs[(PS_X + c) * N + g];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) gvt[c] = gs[(PS_V + c) * N + g] + k.dt * gxo[c];
-#pragma unroll
-  for (int c = 0; c < 9; ++c) gC.m[c] = gs[(PS_C + c) * N + g];
+  g2pb_load(k, ps_in, gs, gp, x, gxo, gvt, gC);
   Stencil st;
   make_stencil(x, k.inv_dx, st);
   int my_run = 0;
@@ -821,19 +1066,175 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
   if (live_) {
     // fx enters d = off - fx with a minus sign: gfx_j -= sum_n wt (K_j . g) = K_j . Wg
 #pragma unroll
+    float ox[3];
+#pragma unroll
     for (int d = 0; d < 3; ++d) {
       gfx[d] -= K[d][0] * Wg[0] + K[d][1] * Wg[1] + K[d][2] * Wg[2];
-      gs[(PS_X + d) * N + g] = gxo[d] + k.inv_dx * gfx[d];
+      ox[d] = gxo[d] + k.inv_dx * gfx[d];
     }
+    store_comps<PS_X, 3, PS_NQ>(gs, gp, ox);
   }
   __syncthreads();
   // transpose of the clamping gather: clamped target index
   stage_flush<3, true, false, G2PB_BLOCK>(k, sv, meta, ggrid + (size_t)env * k.G, 0, 27);
 }
 
+// Warp-local G2P^T (round 2): the same arithmetic as k_g2p_bwd, but a warp owns its 32 particles end to end --
+// warp_group() for the segments, the 27 grid velocities of each distinct cell fetched once per WARP into a small
+// tile (all loads issued before the first use), the cotangent scatter staged as float4 rows and flushed by
+// warp_flush() with clamped target indices (transpose of the clamping gather).  No block barrier.
+constexpr int G2PBW_BLOCK = 64;
+constexpr int G2PBW_CELLS = 4;   // distinct cells per warp whose grid velocities are tiled; more -> gather from L1/L2
+template <int NW> constexpr size_t g2pbw_warp_bytes() { return warp_tile_bytes<NW>() + sizeof(float4) * G2PBW_CELLS * 27; }
+template <int NW>
+__global__ void __launch_bounds__(G2PBW_BLOCK)
+k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict__ grid_out,
+               float* __restrict__ gs, float4* __restrict__ ggrid) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int WN = warp_tile_nodes<NW>();
+  unsigned char* wbase = smem_raw + (threadIdx.x >> 5) * g2pbw_warp_bytes<NW>();
+  float4* tile = reinterpret_cast<float4*>(wbase);                              // [32][WN] staged cotangents
+  float4* vtile = reinterpret_cast<float4*>(wbase + warp_tile_bytes<NW>());     // [G2PBW_CELLS][27] grid velocities
+  UD_PARTICLE_INDEX(k, env, g);
+  const int lane = threadIdx.x & 31;
+  if (slot_ - lane >= k.n) return;   // warp-uniform
+  float x[3], gxo[3], gvt[3];
+  Mat3 gC;
+  g2pb_load(k, ps_in, gs, gp, x, gxo, gvt, gC);
+  Stencil st;
+  make_stencil(x, k.inv_dx, st);
+  const WarpGroup wg = warp_group(live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY);
+  const float4* genv = grid_out + (size_t)env * k.G;
+  const int nseg = __popc(wg.lb);
+  const int leadlane = __ffs(wg.mm) - 1;
+  const int my_seg = __popc(wg.lb & ((1u << leadlane) - 1u));
+  const bool tiled = nseg <= G2PBW_CELLS;   // warp-uniform
+  if (tiled) {
+    float4 tmp[(G2PBW_CELLS * 27 + 31) / 32];
+    const int total = nseg * 27;
+    static_assert(G2PBW_CELLS == 4, "lead_of[] below");
+    int lead_of[4];   // lanes of the (up to four) segment leaders
+    {
+      unsigned b = wg.lb;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        lead_of[i] = b ? __ffs(b) - 1 : 0;
+        b &= b - 1;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < (G2PBW_CELLS * 27 + 31) / 32; ++it) {
+      const int e = it * 32 + lane;
+      const int ge = min(e / 27, nseg - 1), j = e - (e / 27) * 27;
+      const int src = ge == 0 ? lead_of[0] : (ge == 1 ? lead_of[1] : (ge == 2 ? lead_of[2] : lead_of[3]));
+      const int b0 = __shfl_sync(FULL, st.base[0], src), b1 = __shfl_sync(FULL, st.base[1], src),
+                b2 = __shfl_sync(FULL, st.base[2], src);
+      if (e < total) {
+        const int ix = idx_gather(b0 + j / 9, k.rx), iy = idx_gather(b1 + (j / 3) % 3, k.ry), iz = idx_gather(b2 + j % 3, k.rz);
+        tmp[it] = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < (G2PBW_CELLS * 27 + 31) / 32; ++it) {
+      const int e = it * 32 + lane;
+      if (e < total) vtile[e] = tmp[it];
+    }
+    __syncwarp();
+  }
+  const float4* my_tile = vtile + my_seg * 27;
+  const float lw = live_ ? 1.f : 0.f;
+  const float c4 = 4.f * k.inv_dx;
+  // r(a,b,c) = gv' + 4 inv_dx gC' (off - fx) = r0 + a K0 + b K1 + c K2   (K_j = 4 inv_dx * column j of gC')
+  float K[3][3], r0[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) K[j][i] = c4 * gC(i, j);
+    r0[i] = gvt[i] - (K[0][i] * st.fx[0] + K[1][i] * st.fx[1] + K[2][i] * st.fx[2]);
+  }
+  float Wg[3] = {0.f, 0.f, 0.f}, gfx[3] = {0.f, 0.f, 0.f};
+  float4* myrow = tile + wg.row * WN;
+  float4* ggenv = ggrid + (size_t)env * k.G;
+  auto nodes = [&](auto tiled_tag) {
+    constexpr bool TILED = decltype(tiled_tag)::value;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (NW == 3 && a) __syncwarp();   // the previous window has been flushed
+      const int ix = TILED ? 0 : idx_gather(st.base[0] + a, k.rx);
+      const float wa = st.w[a][0] * lw;
+      float ra[3] = {r0[0] + (float)a * K[0][0], r0[1] + (float)a * K[0][1], r0[2] + (float)a * K[0][2]};
+      float P1 = 0.f, P2 = 0.f, Q1 = 0.f;  // sum_b (sum_c gwt w_c) w_b, ... dw_b, sum_b (sum_c gwt dw_c) w_b
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int iy = TILED ? 0 : idx_gather(st.base[1] + b, k.ry);
+        const float wab = wa * st.w[b][1];
+        float rab[3] = {ra[0] + (float)b * K[1][0], ra[1] + (float)b * K[1][1], ra[2] + (float)b * K[1][2]};
+        float P = 0.f, Q = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float wt = wab * st.w[c][2];
+          float4 gv;
+          if (TILED) {
+            gv = my_tile[a * 9 + b * 3 + c];
+          } else {
+            const int iz = idx_gather(st.base[2] + c, k.rz);
+            gv = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
+          }
+          const float r[3] = {rab[0] + (float)c * K[2][0], rab[1] + (float)c * K[2][1], rab[2] + (float)c * K[2][2]};
+          myrow[(NW == 3 ? 0 : a * 9) + b * 3 + c] = make_float4(wt * r[0], wt * r[1], wt * r[2], 0.f);
+          const float gwt = gv.x * r[0] + gv.y * r[1] + gv.z * r[2];
+          Wg[0] += wt * gv.x;
+          Wg[1] += wt * gv.y;
+          Wg[2] += wt * gv.z;
+          P += gwt * st.w[c][2];
+          Q += gwt * st.dw[c][2];
+        }
+        P1 += P * st.w[b][1];
+        P2 += P * st.dw[b][1];
+        Q1 += Q * st.w[b][1];
+      }
+      gfx[0] += P1 * st.dw[a][0];
+      gfx[1] += P2 * st.w[a][0];
+      gfx[2] += Q1 * st.w[a][0];
+      if (NW == 3) {
+        __syncwarp();
+        warp_flush<NW, true, false>(k, tile, wg, st.base, live_, a * WN, ggenv, nullptr);
+      }
+    }
+  };
+  if (tiled) nodes(std::true_type{});
+  else nodes(std::false_type{});
+  if (live_) {
+    // fx enters d = off - fx with a minus sign: gfx_j -= sum_n wt (K_j . g) = K_j . Wg
+    float ox[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      gfx[d] -= K[d][0] * Wg[0] + K[d][1] * Wg[1] + K[d][2] * Wg[2];
+      ox[d] = gxo[d] + k.inv_dx * gfx[d];
+    }
+    store_comps<PS_X, 3, PS_NQ>(gs, gp, ox);
+  }
+  if (NW == 1) {
+    __syncwarp();
+    warp_flush<NW, true, false>(k, tile, wg, st.base, live_, 0, ggenv, nullptr);
+  }
+}
+
+int tuning_warp(int v);
+template <int NW>
+static void launch_g2p_bwd_warp(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
+                                cudaStream_t st) {
+  const size_t smem = g2pbw_warp_bytes<NW>() * (G2PBW_BLOCK / 32);
+  cudaFuncSetAttribute(k_g2p_bwd_warp<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
+  k_g2p_bwd_warp<NW><<<pgrid(k, G2PBW_BLOCK), G2PBW_BLOCK, smem, st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
+}
+
 void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
                     cudaStream_t st) {
   KScope ks_(KC_G2P_BWD, st);
+  const int nw = tuning_warp(-1);
+  if (nw == 1) return launch_g2p_bwd_warp<1>(k, ps_in, grid_out, ws, st);
+  if (nw == 3) return launch_g2p_bwd_warp<3>(k, ps_in, grid_out, ws, st);
   cudaFuncSetAttribute(k_g2p_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2pb_smem_bytes());   // per device
   k_g2p_bwd<<<pgrid(k, G2PB_BLOCK), G2PB_BLOCK, g2pb_smem_bytes(), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
 }
@@ -856,7 +1257,6 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
   // step's input cotangents, so norm_grad_state's nan_to_num + per-env sum of squares (mpm_simulator.py:389-408)
   // happen on the way out instead of in a separate pass over the 24 components
   UD_PARTICLE_INDEX(k, env, g);
-  const size_t N = k.N;
   float gmu = 0.f, gla = 0.f, gn2 = 0.f;
   if (live_) {
     // Phase 1: everything the 27-node gather needs is the stencil, A = dx * affine and u0.  The matrices that
@@ -866,27 +1266,23 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     float Ac[3][3], u0[3];
     const bool plastic = mat_s[g] == 2;
     {
-      float x[3], v[3];
+      float xvc[15], us[12];
       Mat3 C, F;
       Consti o;
+      load_comps<0, 15, PS_NQ>(ps_in, gp, xvc);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) x[c] = ps_in[(PS_X + c) * N + g];
+      for (int c = 0; c < 9; ++c) C.m[c] = xvc[PS_C + c];
+      make_stencil(xvc + PS_X, k.inv_dx, st);
+      load_comps<SV_U, 12, SV_NQ>(svd_in, gp, us);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[c] = ps_in[(PS_V + c) * N + g];
+      for (int c = 0; c < 9; ++c) o.U.m[c] = us[c];
 #pragma unroll
-      for (int c = 0; c < 9; ++c) C.m[c] = ps_in[(PS_C + c) * N + g];
-      make_stencil(x, k.inv_dx, st);
-#pragma unroll
-      for (int c = 0; c < 9; ++c) o.U.m[c] = svd_in[(SV_U + c) * N + g];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) o.s[c] = svd_in[(SV_S + c) * N + g];
+      for (int c = 0; c < 3; ++c) o.s[c] = us[9 + c];
       if (plastic) {  // the stress of a plastic particle is a function of (U, clip(s)) alone
         plastic_affine(k, C, o.U, o.s, mu_s[env], la_s[env], h_s[g], o.affine);
       } else {
-#pragma unroll
-        for (int c = 0; c < 9; ++c) F.m[c] = ps_in[(PS_F + c) * N + g];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) o.Vt.m[c] = svd_in[(SV_VT + c) * N + g];
+        load_comps<PS_F, 9, PS_NQ>(ps_in, gp, F.m);
+        load_comps<SV_VT, 9, SV_NQ>(svd_in, gp, o.Vt.m);
         constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
         constitutive_post(k, C, o);
       }
@@ -894,7 +1290,7 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
       for (int i = 0; i < 3; ++i) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) Ac[j][i] = k.dx * o.affine(i, j);
-        u0[i] = k.p_mass * v[i] - (Ac[0][i] * st.fx[0] + Ac[1][i] * st.fx[1] + Ac[2][i] * st.fx[2]);
+        u0[i] = k.p_mass * xvc[PS_V + i] - (Ac[0][i] * st.fx[0] + Ac[1][i] * st.fx[1] + Ac[2][i] * st.fx[2]);
       }
     }
     const float4* ggenv = ggrid + (size_t)env * k.G;
@@ -967,20 +1363,22 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     Mat3 C, F, gF2out, gC, gF;
     Consti o;
     float gx_in[3];
+    {
+      float cf[18], sv[21];
+      load_comps<PS_C, 18, PS_NQ, true>(ps_in, gp, cf);
+      load_comps<0, 21, SV_NQ, true>(svd_in, gp, sv);
 #pragma unroll
-    for (int c = 0; c < 9; ++c) C.m[c] = __ldcg(&ps_in[(PS_C + c) * N + g]);
+      for (int c = 0; c < 9; ++c) {
+        C.m[c] = cf[c];
+        F.m[c] = cf[9 + c];
+        o.U.m[c] = sv[SV_U + c];
+        o.Vt.m[c] = sv[SV_VT + c];
+      }
 #pragma unroll
-    for (int c = 0; c < 9; ++c) F.m[c] = __ldcg(&ps_in[(PS_F + c) * N + g]);
-#pragma unroll
-    for (int c = 0; c < 9; ++c) o.U.m[c] = __ldcg(&svd_in[(SV_U + c) * N + g]);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) o.s[c] = __ldcg(&svd_in[(SV_S + c) * N + g]);
-#pragma unroll
-    for (int c = 0; c < 9; ++c) o.Vt.m[c] = __ldcg(&svd_in[(SV_VT + c) * N + g]);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) gx_in[d] = gs[(PS_X + d) * N + g];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) gF2out.m[c] = gs[(PS_F + c) * N + g];
+      for (int c = 0; c < 3; ++c) o.s[c] = sv[SV_S + c];
+    }
+    load_comps<PS_X, 3, PS_NQ>(gs, gp, gx_in);
+    load_comps<PS_F, 9, PS_NQ>(gs, gp, gF2out.m);
     if (plastic) {
       constitutive_bwd_plastic(k, C, F, o.U, o.s, o.Vt, mu_s[env], la_s[env], h_s[g], gA, gF2out, gC, gF, gmu, gla);
     } else {
@@ -1008,15 +1406,20 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
         gn2 += gC.m[c] * gC.m[c] + gF.m[c] * gF.m[c];
       }
     }
+    {
+      float og[PS_NCOMP];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      gs[(PS_X + d) * N + g] = ox[d];
-      gs[(PS_V + d) * N + g] = ov[d];
+      for (int d = 0; d < 3; ++d) {
+        og[PS_X + d] = ox[d];
+        og[PS_V + d] = ov[d];
+      }
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        og[PS_C + c] = gC.m[c];
+        og[PS_F + c] = gF.m[c];
+      }
+      store_comps<0, PS_NCOMP, PS_NQ>(gs, gp, og);
     }
-#pragma unroll
-    for (int c = 0; c < 9; ++c) gs[(PS_C + c) * N + g] = gC.m[c];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) gs[(PS_F + c) * N + g] = gF.m[c];
   }
   // block reduction of the per-env scalars
 #pragma unroll
@@ -1106,22 +1509,23 @@ __global__ void k_unsort_cot(MpmConst k, const float* __restrict__ gs, const int
                              float* __restrict__ gC, float* __restrict__ gF, float* __restrict__ gJ) {
   UD_PARTICLE_INDEX(k, env, g);
   if (!live_) return;
-  const size_t N = k.N;
   int p = perm[g];
   size_t o = (size_t)env * k.n + p;
   float n2 = norm2[env * 2];
+  float st[PS_NCOMP];
+  load_comps<0, PS_NCOMP, PS_NQ>(gs, gp, st);
   if (gx)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) gx[3 * o + c] = norm_div(gs[(PS_X + c) * N + g], n2);
+    for (int c = 0; c < 3; ++c) gx[3 * o + c] = norm_div(st[PS_X + c], n2);
   if (gv)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) gv[3 * o + c] = norm_div(gs[(PS_V + c) * N + g], n2);
+    for (int c = 0; c < 3; ++c) gv[3 * o + c] = norm_div(st[PS_V + c], n2);
   if (gC)
 #pragma unroll
-    for (int c = 0; c < 9; ++c) gC[9 * o + c] = norm_div(gs[(PS_C + c) * N + g], n2);
+    for (int c = 0; c < 9; ++c) gC[9 * o + c] = norm_div(st[PS_C + c], n2);
   if (gF)
 #pragma unroll
-    for (int c = 0; c < 9; ++c) gF[9 * o + c] = norm_div(gs[(PS_F + c) * N + g], n2);
+    for (int c = 0; c < 9; ++c) gF[9 * o + c] = norm_div(st[PS_F + c], n2);
   if (gJ) gJ[o] = 0.f;  // the cotangent of J is dropped by substep_bwd_loss (:343-350)
 }
 
