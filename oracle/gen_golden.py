@@ -337,6 +337,28 @@ def cloth_env_case(name, ep_len, B, seed):
     # sides; the fixture keeps layer 3 (W3, b3) and the full-gradient norm
     out["gparam4"], out["gparam5"] = grads[4].numpy(), grads[5].numpy()
     out["gnorm"] = np.array(float(torch.sqrt(sum((g * g).sum() for g in grads))))
+    if ep_len > 1:
+        # The reference's OWN sensitivity (the noise floor the GPU test asserts against): the same free-running
+        # rollout of the unmodified reference from input positions perturbed by 1e-7 (about one fp32 ulp of x).
+        prng = np.random.RandomState(seed + 1000)
+        xp = (x0 + 1e-7 * prng.randn(*x0.shape)).astype(np.float32)
+        req_p = [p.clone().requires_grad_(True) for p in params]
+        rs, state = [], st._replace(x=jnp.array(xp))
+        for t in range(ep_len):
+            obs = env.get_obs(state)
+            actions = apg.sample_actions(apg.policy_apply(req_p, obs.t), eps[t], True)
+            _, reward, done, info = env.step_diff(jax.Array(actions), state)
+            state = info["state"]
+            rs.append(reward.t)
+            out[f"pert_x{t + 1}"] = state.x.t.detach().numpy()
+            out[f"pert_reward{t}"] = reward.t.detach().numpy()
+        loss_p = -torch.stack(rs).mean()
+        gp = torch.autograd.grad(loss_p, req_p)
+        out["pert_loss"] = loss_p.detach().numpy()
+        out["pert_gparam4"], out["pert_gparam5"] = gp[4].numpy(), gp[5].numpy()
+        cos = lambda a, b: float((a * b).sum() / (a.norm() * b.norm()))
+        print(f"reference vs reference with 1e-7 input perturbation: loss {float(loss):.6f} / {float(loss_p):.6f}, "
+              f"policy-gradient cosine {cos(grads[4], gp[4]):.6f} / {cos(grads[5], gp[5]):.6f}")
     path = os.path.join(GOLD, f"ref_clothenv_{name}.npz")
     np.savez_compressed(path, **out)
     gn = float(torch.sqrt(sum((g * g).sum() for g in grads)))

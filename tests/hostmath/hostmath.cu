@@ -44,6 +44,36 @@ void hm_svd3(int n, const float* A, float* U, float* s, float* Vt) {
   }
 }
 
+// warm-started SVD (the previous substep's V^T as the starting basis), as k_p2g chains it over the substeps
+void hm_svd3_warm(int n, const float* A, const float* Vt0, float* U, float* s, float* Vt) {
+  for (int i = 0; i < n; ++i) {
+    Mat3 a, u, vt;
+    float v0[9];
+    for (int c = 0; c < 9; ++c) {
+      a.m[c] = A[9 * i + c];
+      v0[c] = Vt0[9 * i + c];
+    }
+    svd3_ws(a, u, s + 3 * i, vt, true, v0);
+    for (int c = 0; c < 9; ++c) {
+      U[9 * i + c] = u.m[c];
+      Vt[9 * i + c] = vt.m[c];
+    }
+  }
+}
+
+void hm_svd3_hestenes(int n, const float* A, float* U, float* s, float* Vt) {
+  const float none[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  for (int i = 0; i < n; ++i) {
+    Mat3 a, u, vt;
+    for (int c = 0; c < 9; ++c) a.m[c] = A[9 * i + c];
+    svd3_ws_hestenes(a, u, s + 3 * i, vt, false, none);
+    for (int c = 0; c < 9; ++c) {
+      U[9 * i + c] = u.m[c];
+      Vt[9 * i + c] = vt.m[c];
+    }
+  }
+}
+
 void hm_constitutive(int n, const double* consts, const float* C, const float* F, float mu_s, float la_s,
                      const float* h, const int* material, const float* gA, const float* gF2, float* F2,
                      float* affine, float* gC, float* gF, float* gmu, float* gla) {

@@ -55,6 +55,38 @@ def test_svd3_matches_lapack_invariants(hm):
     assert np.abs(R - R_ref)[ok].max() < 2e-5
 
 
+def test_svd3_warm_started_chain(hm):
+    """The chain k_p2g runs: F <- (I + dt C) F every substep, each SVD warm-started from the previous V^T.  After 64
+    substeps the factors must still reconstruct F, stay orthonormal and agree with LAPACK / the one-sided variant."""
+    rng = np.random.RandomState(5)
+    n = 2000
+    F = (np.eye(3)[None] + 0.05 * rng.randn(n, 3, 3)).astype(np.float32)
+    F[:100] = np.eye(3, dtype=np.float32)                      # at rest: all singular values equal
+    U = np.empty_like(F); Vt = np.empty_like(F); s = np.empty((n, 3), np.float32)
+    hm.hm_svd3(n, fp(F), fp(U), fp(s), fp(Vt))
+    eye = np.eye(3)[None]
+    for step in range(64):
+        Cm = (rng.randn(n, 3, 3) * 20).astype(np.float32)
+        Cm[:100] *= 1e-3
+        F = ((eye + 2e-4 * Cm) @ F).astype(np.float32)
+        Vt0 = Vt.copy()
+        hm.hm_svd3_warm(n, fp(F), fp(Vt0), fp(U), fp(s), fp(Vt))
+    s_ref = np.linalg.svd(F.astype(np.float64), compute_uv=False)
+    assert np.all(s[:, 0] >= s[:, 1]) and np.all(s[:, 1] >= s[:, 2])
+    assert np.abs(s - s_ref).max() < 2e-6 * s_ref.max()
+    rec = np.einsum("nij,nj,njk->nik", U.astype(np.float64), s.astype(np.float64), Vt.astype(np.float64))
+    assert np.abs(rec - F).max() < 3e-6
+    assert np.abs(np.einsum("nji,njk->nik", U, U) - eye).max() < 3e-6
+    assert np.abs(np.einsum("nij,nkj->nik", Vt, Vt) - eye).max() < 3e-6
+    Ur, sr, Vr = np.linalg.svd(F.astype(np.float64))
+    assert np.abs(U.astype(np.float64) @ Vt.astype(np.float64) - Ur @ Vr).max() < 1e-5
+    U2 = np.empty_like(F); Vt2 = np.empty_like(F); s2 = np.empty((n, 3), np.float32)
+    hm.hm_svd3_hestenes(n, fp(F), fp(U2), fp(s2), fp(Vt2))
+    print("one-sided (cold) vs LAPACK", np.abs(s2 - s_ref).max(), " two-sided (warm chain) vs LAPACK", np.abs(s - s_ref).max())
+    assert np.abs(s2 - s_ref).max() < 1e-4 * s_ref.max()      # the round-1 variant is the looser of the two
+    assert np.abs(U @ Vt - U2 @ Vt2).max() < 1e-4
+
+
 @pytest.mark.parametrize("material", [0, 1, 2])
 def test_constitutive_forward_and_reverse_vs_oracle(hm, material):
     rng = np.random.RandomState(1 + material)

@@ -64,11 +64,12 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("UNIDOM_B200_LIB") or LIB_PATH      # development A/B builds (build.py --variant)
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m unidom_b200.build` "
+            f"{path} is missing: build it with `python -m unidom_b200.build` "
             "(nvcc, sm_100a).  unidom_b200 has no CPU or eager fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     L.ud_version.restype = C.c_char_p
     L.ud_last_error.restype = C.c_char_p
     P = C.POINTER

@@ -43,10 +43,20 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: development A/B builds, e.g. build(variant="hestenes", defines=["-DUD_SVD_HESTENES"]) writes
+    libunidom_b200_hestenes.so, which `UNIDOM_B200_LIB=<path>` makes _lib.py load instead of the product library."""
+    if variant:
+        return _build(os.path.join(HERE, f"libunidom_b200_{variant}.so"), "." + variant, list(defines), verbose)
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read() == digest:
         return LIB
+    _build(LIB, "", [], verbose)
+    open(STAMP, "w").write(digest)
+    return LIB
+
+
+def _build(LIB, tag, defines, verbose):
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -54,8 +64,8 @@ def build(force=False, verbose=False):
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", path, "-o", obj]
+        obj = os.path.join(CSRC, src.replace(".cu", tag + ".o"))
+        cmd = [nvcc, *ARCH, *COMMON, *extra, *defines, "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -69,9 +79,10 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed for " + cmd[-3])
     cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"]
     subprocess.check_call(cmd)
-    open(STAMP, "w").write(digest)
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -117,8 +117,10 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
   w.keys = (int32_t*)take(4 * N);
   w.tmp_idx = (int32_t*)take(4 * N);
   w.perm = (int32_t*)take(4 * N);
+  w.inv_perm = (int32_t*)take(4 * N);
   w.cell_start = (int32_t*)take(4 * (size_t)k.B * (k.NK + 1));
   w.cursor = (int32_t*)take(4 * (size_t)k.B * k.NK);
+  w.chunk_sum = (int32_t*)take(4 * (size_t)k.B * ((k.NK + 1023) / 1024));
   w.mat_s = (int32_t*)take(4 * N);
   w.h_s = (float*)take(4 * N);
   w.fk_pos = (float*)take(4 * (size_t)k.B * P * (S + 1) * 3);
@@ -133,7 +135,7 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
   if (!bwd) {
     w.ps = (float*)take(4 * (size_t)PS_NCOMP * NP);
     w.vt_roll = (float*)take(4 * (size_t)VT_NCOMP * NP);
-    w.grid_raw = (float4*)take(16 * BG);
+    w.grid_raw = (float4*)take(16 * BG * 2);
     w.grid_out = w.grid_raw;
   } else {
     w.ps = (float*)take(4 * (size_t)PS_NCOMP * NP * (S + 1));
@@ -195,7 +197,8 @@ int ud_tuning_set(const char* name, int value) {
 int ud_timing_num_classes(void) { return KC_COUNT; }
 const char* ud_timing_class_name(int cls) {
   static const char* names[KC_COUNT] = {"sort", "gather", "fk", "p2g", "grid", "g2p", "unsort", "g2p_bwd",
-                                        "grid_bwd", "p2g_bwd", "finish_bwd", "memset", "cloth_fwd", "cloth_bwd", "reward"};
+                                        "grid_bwd", "p2g_bwd", "finish_bwd", "memset", "cloth_fwd", "cloth_bwd", "reward",
+                                        "apg"};
   return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "";
 }
 int ud_timing_collect(double* ms_by_class, int64_t* launches_by_class, int n_classes) {
@@ -266,17 +269,24 @@ int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   launch_gather_state(k, in, material, h, ws, ws.ps, st);
   launch_fk_fwd(k, in, action, out, ws, st);
   zero_async(ws.jrows, 4 * (size_t)k.B * k.S * 9, st);
-  // the grid is zeroed in full once per call; between substeps only the 4x4x4 blocks P2G marked are re-zeroed
+  // the grids are zeroed in full once per call; between substeps only the 4x4x4 blocks P2G marked are re-zeroed
   zero_async(ws.blk_flag, 4 * (size_t)k.B * k.nbx * k.nby * k.nbz, st);
   zero_async(ws.blk_count, 4 * (size_t)k.S, st);
-  zero_async(ws.grid_raw, 16 * (size_t)k.B * k.G, st);
-  if (ws.grid_fix) zero_async(ws.grid_fix, 32 * (size_t)k.B * k.G, st);
+  const size_t BG = (size_t)k.B * k.G;
+  zero_async(ws.grid_raw, 16 * BG * 2, st);
+  if (ws.grid_fix) zero_async(ws.grid_fix, 32 * BG, st);
+  auto vt_in = [&](int f) { return (g_svd_warm && (f % SVD_RESTART)) ? ws.vt_roll : nullptr; };
+  const bool lists = p2g_lists_blocks();
+  // Two grids, used alternately: substep f scatters into, updates and gathers from grid f % 2, and the grid launch of
+  // substep f also re-zeroes the OTHER grid block by block from the list of substep f - 1 (whose G2P has finished), so
+  // that P2G(f + 1) finds it empty: one grid-side launch per substep.
   for (int f = 0; f < k.S; ++f) {
-    if (f) launch_grid_clear(k, ws.grid_raw, f - 1, ws, st);
-    launch_p2g(k, ws.ps, ws.ps, ws.grid_raw, in->mu, in->lamda, (g_svd_warm && (f % SVD_RESTART)) ? ws.vt_roll : nullptr, ws.vt_roll,
-               nullptr, ws, st);
-    launch_grid_fwd(k, ws.grid_raw, ws.grid_raw, ws.grid_fix, f, in, ws, st);
-    launch_g2p(k, ws.ps, ws.ps, ws.grid_raw, f, ws, st);
+    float4* gf = ws.grid_raw + BG * (f & 1);
+    float4* gn = ws.grid_raw + BG * ((f + 1) & 1);
+    launch_p2g(k, ws.ps, ws.ps, gf, in->mu, in->lamda, vt_in(f), ws.vt_roll, nullptr, f, ws, st);
+    const bool clear = f >= 1 && f + 1 < k.S;
+    launch_grid_fwd(k, gf, gf, ws.grid_fix, f, in, ws, st, clear ? gn : nullptr, f - 1, lists);
+    launch_g2p(k, ws.ps, ws.ps, gf, f, ws, st);
   }
   launch_unsort_state(k, ws.ps, in->J, ws, out, st);
   cudaMemcpyAsync(out->friction, in->friction, 4 * (size_t)k.B, cudaMemcpyDeviceToDevice, st);
@@ -299,15 +309,14 @@ static void mpm_record_pass(const MpmConst& k, const ud_mpm_state* in, const int
   zero_async(ws.blk_flag, 4 * (size_t)k.B * k.nbx * k.nby * k.nbz, st);
   zero_async(ws.blk_count, 4 * (size_t)k.S, st);
   zero_async(ws.act_count, 4 * (size_t)k.S, st);
+  auto sv = [&](int f) { return ws.svd_s + (size_t)SV_NCOMP * k.N_pad * f; };
+  auto vt_in = [&](int f) { return (g_svd_warm && (f % SVD_RESTART)) ? sv(f - 1) : nullptr; };
+  auto ps = [&](int f) { return ws.ps + slot * f; };
+  const bool lists = p2g_lists_blocks();
   for (int f = 0; f < k.S; ++f) {
-    const float* s_in = ws.ps + slot * f;
-    float* s_out = ws.ps + slot * (f + 1);
-    float* sv_f = ws.svd_s + (size_t)SV_NCOMP * k.N_pad * f;
-    launch_p2g(k, s_in, s_out, ws.grid_raw + BG * f, in->mu, in->lamda,
-               (g_svd_warm && (f % SVD_RESTART)) ? sv_f - (size_t)SV_NCOMP * k.N_pad : nullptr, nullptr,
-               sv_f, ws, st);
-    launch_grid_fwd(k, ws.grid_raw + BG * f, ws.grid_out + BG * f, ws.grid_fix, f, in, ws, st);
-    launch_g2p(k, s_in, s_out, ws.grid_out + BG * f, f, ws, st);
+    launch_p2g(k, ps(f), ps(f + 1), ws.grid_raw + BG * f, in->mu, in->lamda, vt_in(f), nullptr, sv(f), f, ws, st);
+    launch_grid_fwd(k, ws.grid_raw + BG * f, ws.grid_out + BG * f, ws.grid_fix, f, in, ws, st, nullptr, 0, lists);
+    launch_g2p(k, ps(f), ps(f + 1), ws.grid_out + BG * f, f, ws, st);
   }
 }
 

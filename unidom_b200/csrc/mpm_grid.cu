@@ -150,11 +150,11 @@ UD_DEV void load_prim_f(const MpmConst& k, const ud_mpm_state& in, const float* 
 // Compacts the block marks P2G left (ws.blk_flag) into a list and consumes them: one warp per 32 blocks, one
 // warp-aggregated append.  ~3-6 % of the blocks are marked in the shipped scenes.
 __global__ void __launch_bounds__(128)
-k_blk_compact(int total, int32_t* __restrict__ blk_flag, int32_t* __restrict__ list, int32_t* __restrict__ count) {
+k_blk_compact(int total, int32_t* __restrict__ blk_flag, int32_t* __restrict__ list, int32_t* __restrict__ count, int stamp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const bool marked = i < total && blk_flag[i] != 0;
-  if (marked) blk_flag[i] = 0;
+  const bool marked = i < total && blk_flag[i] == BLK_MARK_CTA;
+  if (marked) blk_flag[i] = stamp;   // same state the self-listing warp kernels leave: flag == substep + 1 <=> listed
   const unsigned m = __ballot_sync(0xffffffffu, marked);
   if (!m) return;
   int base = 0;
@@ -163,15 +163,35 @@ k_blk_compact(int total, int32_t* __restrict__ blk_flag, int32_t* __restrict__ l
   if (marked) list[base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
+// update of one EMPTY boundary cell (raw value g, mass 0)
+__device__ __forceinline__ void
+empty_shell_cell(const MpmConst& k, int ci, int cj, int ck, size_t idx, int env, const float4& g, float4* grid_out, int f,
+                 const ud_mpm_state& in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
+                 const float* __restrict__ fk_vw, int32_t* __restrict__ act_list, int32_t* __restrict__ act_count) {
+  const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
+  float p[3] = {g.x, g.y, g.z}, v[3];
+  bool any_active = false;
+  auto prim_of = [&](int q, PrimIn<float>& pr) {
+    load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
+    const bool a = prim_active(k, gpos, pr);  // without influence the primitive changes v by < 1e-12 relative: skipped
+    any_active |= a;
+    return a;
+  };
+  cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
+  grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
+  // an empty shell cell under a primitive's influence can carry a cotangent to that primitive: list it for k_grid_bwd
+  if (act_list && any_active) act_list[atomicAdd(act_count, 1)] = (int32_t)idx;
+}
+
 // Grid update over the listed 4x4x4 blocks: persistent warps, one block (64 cells, 2 per lane) per iteration.
-__global__ void __launch_bounds__(128)
-k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, long long* __restrict__ grid_fix, int f,
-           ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
-           const float* __restrict__ fk_vw, const int32_t* __restrict__ blk_list, const int32_t* __restrict__ blk_count,
-           int32_t* __restrict__ act_list, int32_t* __restrict__ act_count) {
+__device__ __forceinline__ void
+grid_fwd_body(const MpmConst& k, float4* grid_in, float4* grid_out, long long* __restrict__ grid_fix, int f,
+              const ud_mpm_state& in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
+              const float* __restrict__ fk_vw, const int32_t* __restrict__ blk_list, const int32_t* __restrict__ blk_count,
+              int32_t* __restrict__ act_list, int32_t* __restrict__ act_count, int vblock, int nblocks) {
   const int nblk = k.nbx * k.nby * k.nbz;
   const int lane = threadIdx.x & 31;
-  const int warp0 = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int warp0 = (int)((vblock * (size_t)blockDim.x + threadIdx.x) >> 5), nwarps = (nblocks * blockDim.x) >> 5;
   const int count = *blk_count;
   for (int li = warp0; li < count; li += nwarps) {
   const int w = blk_list[li];
@@ -208,8 +228,12 @@ k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, long long* __restrict_
       }
     }
     if (!in_range) continue;
-    if (!has_mass) {  // empty cell: interior ones are never gathered with a non-zero weight, the boundary
-      if (grid_out != grid_in || grid_fix) grid_out[idx] = g;  // shell is updated by k_grid_shell
+    if (!has_mass) {  // empty cell: interior ones are never gathered with a non-zero weight
+      const bool on_shell = ci == 0 || cj == 0 || ck == 0 || ci == k.rx - 1 || cj == k.ry - 1 || ck == k.rz - 1;
+      if (on_shell)  // every cell of a listed block is this job's, its empty boundary cells included (the shell job
+        empty_shell_cell(k, ci, cj, ck, idx, env, g, grid_out, f, in, fk_pos, fk_rot, fk_vw, act_list, act_count);  // skips listed blocks)
+      else if (grid_out != grid_in || grid_fix)
+        grid_out[idx] = g;
       continue;
     }
     float p[3] = {g.x, g.y, g.z}, v[3];
@@ -252,21 +276,21 @@ __device__ __forceinline__ bool shell_cell(const MpmConst& k, int t, int& ci, in
 // In-place forward only, between substeps, instead of a memset of the whole grid: re-zero (a) the empty face cells
 // k_grid_shell wrote velocities into -- CTAs [0, shell_ctas) -- and (b) the blocks the previous substep's P2G touched
 // -- the remaining CTAs, persistent warps over the block list.
-__global__ void __launch_bounds__(128)
-k_grid_clear(MpmConst k, float4* __restrict__ grid, const int32_t* __restrict__ blk_list,
-             const int32_t* __restrict__ blk_count, int shell_ctas_per_env) {
+__device__ __forceinline__ void
+grid_clear_body(const MpmConst& k, float4* __restrict__ grid, const int32_t* __restrict__ blk_list,
+                const int32_t* __restrict__ blk_count, int shell_ctas_per_env, int vblock, int nblocks) {
   const int shell_ctas = shell_ctas_per_env * k.B;
-  if ((int)blockIdx.x < shell_ctas) {
-    const int env = blockIdx.x / shell_ctas_per_env;
+  if (vblock < shell_ctas) {
+    const int env = vblock / shell_ctas_per_env;
     int ci, cj, ck;
-    if (!shell_cell(k, (blockIdx.x - env * shell_ctas_per_env) * blockDim.x + threadIdx.x, ci, cj, ck)) return;
+    if (!shell_cell(k, (vblock - env * shell_ctas_per_env) * blockDim.x + threadIdx.x, ci, cj, ck)) return;
     grid[(size_t)env * k.G + (size_t)(ci * k.ry + cj) * k.rz + ck] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
   const int nblk = k.nbx * k.nby * k.nbz;
   const int lane = threadIdx.x & 31;
-  const int warp0 = (int)((((size_t)blockIdx.x - shell_ctas) * blockDim.x + threadIdx.x) >> 5);
-  const int nwarps = (int)(((gridDim.x - shell_ctas) * blockDim.x) >> 5);
+  const int warp0 = (int)((((size_t)vblock - shell_ctas) * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)(((nblocks - shell_ctas) * blockDim.x) >> 5);
   const int count = *blk_count;
   for (int li = warp0; li < count; li += nwarps) {
     const int w = blk_list[li];
@@ -284,61 +308,103 @@ k_grid_clear(MpmConst k, float4* __restrict__ grid, const int32_t* __restrict__ 
 
 // Empty cells of the outermost layer: the reference updates EVERY cell (empty ones get dt*gravity, colliders,
 // friction, walls), and a particle that left the grid gathers exactly these cells through clamped indices
-// (SURVEY 8c).  One thread per face cell; edge / corner cells are written by one owning face only.
-__global__ void __launch_bounds__(128)
-k_grid_shell(MpmConst k, const float4* grid_raw, float4* grid_out, int f, ud_mpm_state in,
-             const float* __restrict__ fk_pos, const float* __restrict__ fk_rot, const float* __restrict__ fk_vw,
-             int32_t* __restrict__ act_list, int32_t* __restrict__ act_count) {
-  const int env = blockIdx.y;
-  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+// (SURVEY 8c).  Cells of a block P2G listed this substep are updated by the block job (which calls empty_shell_cell
+// for them); the shell job, one thread per face cell, covers the blocks nobody scattered into.  Ownership is decided
+// by the block flag alone, never by re-reading a grid value another job may be writing.
+__device__ __forceinline__ void
+grid_shell_body(const MpmConst& k, const float4* grid_raw, float4* grid_out, int f, const ud_mpm_state& in,
+                const float* __restrict__ fk_pos, const float* __restrict__ fk_rot, const float* __restrict__ fk_vw,
+                int32_t* __restrict__ act_list, int32_t* __restrict__ act_count, const int32_t* __restrict__ blk_flag,
+                int env, int vblock) {
+  const int t0 = vblock * blockDim.x + threadIdx.x;
   const int nxy = k.rx * k.ry, nxz = k.rx * k.rz;
   int ci, cj, ck;
   if (!shell_cell(k, t0, ci, cj, ck)) return;
-  // edge and corner cells belong to two or three faces: ONE face owns each (z faces first, then y, then x), so that the
-  // in-place forward (grid_out == grid_raw) can never re-read a value it has already updated
+  // edge and corner cells belong to two or three faces: ONE face owns each (z faces first, then y, then x)
   const bool owner = (ck == 0 || ck == k.rz - 1) ? (t0 < 2 * nxy)
                      : ((cj == 0 || cj == k.ry - 1) ? (t0 >= 2 * nxy && t0 < 2 * (nxy + nxz)) : true);
   if (!owner) return;
+  if (blk_flag[(size_t)env * (k.nbx * k.nby * k.nbz) + ((ci >> 2) * k.nby + (cj >> 2)) * k.nbz + (ck >> 2)] == f + 1)
+    return;  // a listed block: the block job's cell
   const size_t idx = (size_t)env * k.G + (size_t)(ci * k.ry + cj) * k.rz + ck;
-  const float4 g = grid_raw[idx];
-  if (g.w > 0.f) return;  // has mass: k_grid_fwd's cell
-  const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
-  float p[3] = {g.x, g.y, g.z}, v[3];
-  bool any_active = false;
-  auto prim_of = [&](int q, PrimIn<float>& pr) {
-    load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
-    const bool a = prim_active(k, gpos, pr);  // without influence the primitive changes v by < 1e-12 relative: skipped
-    any_active |= a;
-    return a;
-  };
-  cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
-  grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
-  // an empty shell cell under a primitive's influence can carry a cotangent to that primitive: list it for k_grid_bwd
-  if (act_list && any_active) act_list[atomicAdd(act_count, 1)] = (int32_t)idx;
+  // nobody scattered into this block: the cell is empty, and grid_raw holds what the call's memset / the re-zeroing
+  // left there (zero)
+  empty_shell_cell(k, ci, cj, ck, idx, env, grid_raw[idx], grid_out, f, in, fk_pos, fk_rot, fk_vw, act_list, act_count);
 }
 
+// ONE launch per substep for the whole grid side: CTAs [0, NF) update the listed 4x4x4 blocks (persistent warps),
+// the next `shell` CTAs update the boundary cells of the blocks that are NOT listed, and -- in the in-place forward --
+// the remaining CTAs re-zero the OTHER grid (the one the next substep scatters into) from the block list of the
+// previous substep.  The three jobs touch disjoint cells.
+constexpr int GRID_FWD_CTAS = 148 * 8;
+struct GridClearArgs {
+  float4* grid;             // null: nothing to clear
+  const int32_t* blk_list;
+  const int32_t* blk_count;
+  int ctas;                 // shell_ctas_per_env * B + persistent CTAs
+  int shell_ctas_per_env;
+};
+__global__ void __launch_bounds__(128)
+k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, long long* __restrict__ grid_fix, int f,
+           ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
+           const float* __restrict__ fk_vw, const int32_t* __restrict__ blk_list, const int32_t* __restrict__ blk_count,
+           int32_t* __restrict__ act_list, int32_t* __restrict__ act_count, const int32_t* __restrict__ blk_flag,
+           int shell_ctas_per_env, GridClearArgs clr) {
+  int vb = blockIdx.x;
+  if (vb < GRID_FWD_CTAS) {
+    grid_fwd_body(k, grid_in, grid_out, grid_fix, f, in, fk_pos, fk_rot, fk_vw, blk_list, blk_count, act_list, act_count, vb,
+                  GRID_FWD_CTAS);
+    return;
+  }
+  vb -= GRID_FWD_CTAS;
+  if (vb < shell_ctas_per_env * k.B) {
+    const int env = vb / shell_ctas_per_env;
+    grid_shell_body(k, grid_in, grid_out, f, in, fk_pos, fk_rot, fk_vw, act_list, act_count, blk_flag, env,
+                    vb - env * shell_ctas_per_env);
+    return;
+  }
+  vb -= shell_ctas_per_env * k.B;
+  grid_clear_body(k, clr.grid, clr.blk_list, clr.blk_count, clr.shell_ctas_per_env, vb, clr.ctas);
+}
+__global__ void __launch_bounds__(128)
+k_grid_clear(MpmConst k, float4* __restrict__ grid, const int32_t* __restrict__ blk_list,
+             const int32_t* __restrict__ blk_count, int shell_ctas_per_env) {
+  grid_clear_body(k, grid, blk_list, blk_count, shell_ctas_per_env, blockIdx.x, gridDim.x);
+}
+
+static inline int shell_ctas_of(const MpmConst& k) { return cdiv(2 * (k.rx * k.ry + k.rx * k.rz + k.ry * k.rz), 128); }
+
+// clear_grid != null: additionally re-zero `clear_grid` from the block list of substep `clear_substep` (same launch).
+// lists_ready: the P2G kernel already appended the touched blocks to this substep's list (warp-local kernels);
+// otherwise the block marks are compacted first.
 void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const long long* grid_fix, int substep,
-                     const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st) {
-  KScope ks_(KC_GRID, st, 3);
+                     const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st, float4* clear_grid, int clear_substep,
+                     bool lists_ready) {
+  KScope ks_(KC_GRID, st, lists_ready ? 1 : 2);
   int32_t* al = (grid_out != grid_in && ws.act_list) ? ws.act_list + (size_t)substep * k.B * k.G : nullptr;
   int32_t* ac = al ? ws.act_count + substep : nullptr;
   const int total = k.B * k.nbx * k.nby * k.nbz;
   int32_t* bl = ws.blk_list + (size_t)(substep % ws.blk_nbuf) * total;
   int32_t* bc = ws.blk_count + substep;
-  k_blk_compact<<<cdiv(total, 128), 128, 0, st>>>(total, ws.blk_flag, bl, bc);
-  k_grid_fwd<<<148 * 8, 128, 0, st>>>(k, grid_in, grid_out, const_cast<long long*>(grid_fix), substep, *in, ws.fk_pos,
-                                      ws.fk_rot, ws.fk_vw, bl, bc, al, ac);
-  // in-place (forward) mode the raw value of an empty cell is still there when the shell kernel reads it
-  const int shell = 2 * (k.rx * k.ry + k.rx * k.rz + k.ry * k.rz);
-  k_grid_shell<<<dim3(cdiv(shell, 128), k.B), 128, 0, st>>>(k, grid_in, grid_out, substep, *in, ws.fk_pos, ws.fk_rot,
-                                                            ws.fk_vw, al, ac);
+  if (!lists_ready) k_blk_compact<<<cdiv(total, 128), 128, 0, st>>>(total, ws.blk_flag, bl, bc, substep + 1);
+  const int sc = shell_ctas_of(k);
+  GridClearArgs clr = {nullptr, nullptr, nullptr, 0, sc};
+  if (clear_grid) {
+    clr.grid = clear_grid;
+    clr.blk_list = ws.blk_list + (size_t)(clear_substep % ws.blk_nbuf) * total;
+    clr.blk_count = ws.blk_count + clear_substep;
+    clr.ctas = sc * k.B + 148 * 2;
+  }
+  // in-place (forward) mode the raw value of an empty cell is still there when the shell job reads it
+  k_grid_fwd<<<GRID_FWD_CTAS + sc * k.B + clr.ctas, 128, 0, st>>>(k, grid_in, grid_out, const_cast<long long*>(grid_fix),
+                                                                substep, *in, ws.fk_pos, ws.fk_rot, ws.fk_vw, bl, bc, al, ac,
+                                                                ws.blk_flag, sc, clr);
 }
 
 void launch_grid_clear(const MpmConst& k, float4* grid, int prev_substep, const MpmWs& ws, cudaStream_t st) {
   KScope ks_(KC_GRID, st);
   const int total = k.B * k.nbx * k.nby * k.nbz;
-  const int shell = 2 * (k.rx * k.ry + k.rx * k.rz + k.ry * k.rz);
-  const int sc = cdiv(shell, 128);
+  const int sc = shell_ctas_of(k);
   k_grid_clear<<<sc * k.B + 148 * 4, 128, 0, st>>>(k, grid, ws.blk_list + (size_t)(prev_substep % ws.blk_nbuf) * total,
                                                    ws.blk_count + prev_substep, sc);
 }

@@ -60,6 +60,10 @@ __device__ __forceinline__ void store_comps(float* __restrict__ base, int gp, co
     }
   }
 }
+// Block flags (ws.blk_flag, zeroed once per call): flag == substep + 1 <=> the block is on that substep's list.  The
+// warp-local P2G kernels stamp and list themselves; the round-1 CTA kernels store BLK_MARK_CTA and k_blk_compact turns
+// it into the stamp while listing.
+constexpr int BLK_MARK_CTA = 0x40000000;
 // the SVD warm-start chain restarts from V = I every SVD_RESTART substeps (bounds rounding drift of V)
 constexpr int SVD_RESTART = 16;
 // deterministic P2G: values are accumulated as round(v * 2^52) in int64 (range +-2048, resolution 2.2e-16);
@@ -72,6 +76,8 @@ constexpr int GS_STRIDE = GS_PRIM + GS_PRIM_STRIDE * UD_MAX_PRIM;
 
 struct MpmWs {
   // binning
+  int32_t* inv_perm;    // [N] sorted slot of original particle p (inverse of perm)
+  int32_t* chunk_sum;   // [B * ceil(NK / 1024)] totals of the 1024-key chunks of the count scan
   int32_t* keys;        // [N]
   int32_t* tmp_idx;     // [N]
   int32_t* perm;        // [N] sorted slot -> original particle index (per env)
@@ -81,7 +87,8 @@ struct MpmWs {
   float* h_s;           // [N] hardness in sorted order
   // state
   float* ps;            // fwd: [24*N_pad]; bwd: [(S+1)*24*N_pad] start-of-substep states (tiles, see above)
-  float4* grid_raw;     // fwd: [B*G]; bwd: [S*B*G] scattered (p,m)
+  float4* grid_raw;     // fwd: [2][B*G] (used alternately: the grid launch of substep f re-zeroes the other one);
+                        // bwd: [S*B*G] scattered (p,m)
   float4* grid_out;     // fwd: == grid_raw; bwd: [S*B*G] updated velocities
   long long* grid_fix;  // deterministic P2G only: [B*G*4] 64-bit fixed-point accumulators of one substep
   int32_t* blk_flag;    // [B*nbx*nby*nbz] 4x4x4 grid blocks that P2G scattered into this substep
@@ -113,7 +120,7 @@ struct MpmWs {
 
 // Kernel classes for the optional per-kernel CUDA-event timing (ud_timing_*).
 enum KClass { KC_SORT = 0, KC_GATHER, KC_FK, KC_P2G, KC_GRID, KC_G2P, KC_UNSORT, KC_G2P_BWD, KC_GRID_BWD,
-              KC_P2G_BWD, KC_FINISH_BWD, KC_MEMSET, KC_CLOTH_FWD, KC_CLOTH_BWD, KC_REWARD, KC_COUNT };
+              KC_P2G_BWD, KC_FINISH_BWD, KC_MEMSET, KC_CLOTH_FWD, KC_CLOTH_BWD, KC_REWARD, KC_APG, KC_COUNT };
 // RAII scope: counts launches and (when timing is enabled) brackets them with events on `st`.
 struct KScope {
   int cls;
@@ -137,8 +144,9 @@ void launch_sort(const MpmConst& k, const float* x_aos, const MpmWs& ws, int32_t
 void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
                          const MpmWs& ws, float* ps_slot, cudaStream_t st);
 void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
-                const float* la_s, const float* vt_in, float* vt_out, float* svd_out, const MpmWs& ws,
+                const float* la_s, const float* vt_in, float* vt_out, float* svd_out, int substep, const MpmWs& ws,
                 cudaStream_t st);
+bool p2g_lists_blocks();   // the P2G kernels in use list the touched grid blocks themselves (no compaction pass)
 void launch_g2p(const MpmConst& k, const float* ps_in, float* ps_out, const float4* grid, int substep,
                 const MpmWs& ws, cudaStream_t st);
 void launch_unsort_state(const MpmConst& k, const float* ps_slot, const float* J_in, const MpmWs& ws,
@@ -159,7 +167,8 @@ void launch_fk_fwd(const MpmConst& k, const ud_mpm_state* in, const float* actio
 // into grid_in (which the adjoint reads later), then updated into grid_out.
 void launch_grid_clear(const MpmConst& k, float4* grid, int prev_substep, const MpmWs& ws, cudaStream_t st);
 void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const long long* grid_fix, int substep,
-                     const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st);
+                     const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st, float4* clear_grid = nullptr,
+                     int clear_substep = 0, bool lists_ready = false);
 void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,
                      const MpmWs& ws, cudaStream_t st);
 void launch_fk_bwd(const MpmConst& k, const ud_mpm_state* in, const float* action,

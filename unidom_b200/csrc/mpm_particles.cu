@@ -51,30 +51,58 @@ __global__ void k_keys(MpmConst k, const float* __restrict__ x_aos, int32_t* __r
   atomicAdd(&count[(size_t)env * (k.NK + 1) + key], 1);
 }
 
-// one CTA per env: exclusive scan of NK counts in place (count -> start), start[NK] = n
-__global__ void k_scan(MpmConst k, int32_t* __restrict__ cell_start) {
-  __shared__ int part[1024];
-  int32_t* c = cell_start + (size_t)blockIdx.x * (k.NK + 1);
-  int per = (k.NK + blockDim.x - 1) / blockDim.x;
-  int lo = threadIdx.x * per, hi = min(lo + per, k.NK);
-  int s = 0;
-  for (int i = lo; i < hi; ++i) s += c[i];
-  part[threadIdx.x] = s;
+// Exclusive scan of the NK per-env key counts in place (count -> start), start[NK] = n.  Two levels, every CTA owns a
+// 1024-key chunk of one env: k_scan_sums leaves each chunk's total in `chunk_sum`, k_scan_chunks adds the totals of
+// the chunks before its own to a local scan.  (Round 1 ran ONE 1024-thread CTA per env serially over its NK = 73 728
+// keys: 74 us on 32 of 148 SMs.)
+constexpr int SCAN_CHUNK = 1024;
+__device__ __forceinline__ int block_sum_1024(int v, int* sh) {   // blockDim.x == 1024; returns the total to every thread
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (lane == 0) sh[wid] = v;
   __syncthreads();
-  // Hillis-Steele inclusive scan over blockDim partials
-  for (int off = 1; off < blockDim.x; off <<= 1) {
-    int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
-    __syncthreads();
-    part[threadIdx.x] += v;
-    __syncthreads();
+  int t = sh[lane];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+  return t;
+}
+__global__ void __launch_bounds__(SCAN_CHUNK)
+k_scan_sums(MpmConst k, const int32_t* __restrict__ cell_start, int32_t* __restrict__ chunk_sum) {
+  __shared__ int sh[32];
+  const int env = blockIdx.y, i = blockIdx.x * SCAN_CHUNK + threadIdx.x;
+  const int v = i < k.NK ? cell_start[(size_t)env * (k.NK + 1) + i] : 0;
+  const int t = block_sum_1024(v, sh);
+  if (threadIdx.x == 0) chunk_sum[env * gridDim.x + blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(SCAN_CHUNK)
+k_scan_chunks(MpmConst k, int32_t* __restrict__ cell_start, const int32_t* __restrict__ chunk_sum) {
+  __shared__ int sh[32], wsum[32];
+  const int env = blockIdx.y, i = blockIdx.x * SCAN_CHUNK + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int32_t* c = cell_start + (size_t)env * (k.NK + 1);
+  // totals of the chunks before mine (at most a few hundred values, strided over the block)
+  int before = 0;
+  for (int j = threadIdx.x; j < (int)blockIdx.x; j += SCAN_CHUNK) before += chunk_sum[env * gridDim.x + j];
+  before = block_sum_1024(before, sh);
+  const int v = i < k.NK ? c[i] : 0;
+  int incl = v;   // inclusive scan inside the warp, then across the 32 warps
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, off);
+    incl += lane >= off ? t : 0;
   }
-  int run = part[threadIdx.x] - s;
-  for (int i = lo; i < hi; ++i) {
-    int t = c[i];
-    c[i] = run;
-    run += t;
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  int wt = wsum[lane];
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, wt, off);
+    wt += lane >= off ? t : 0;
   }
-  if (threadIdx.x == blockDim.x - 1) c[k.NK] = part[threadIdx.x];
+  const int warp_before = __shfl_sync(0xffffffffu, wt, wid) - wsum[wid];
+  if (i < k.NK) c[i] = before + warp_before + incl - v;
+  if (i == k.NK - 1) c[k.NK] = before + warp_before + incl;
 }
 
 __global__ void k_place(MpmConst k, const int32_t* __restrict__ keys, const int32_t* __restrict__ cell_start,
@@ -87,7 +115,7 @@ __global__ void k_place(MpmConst k, const int32_t* __restrict__ keys, const int3
 }
 
 __global__ void k_rank(MpmConst k, const int32_t* __restrict__ keys, const int32_t* __restrict__ cell_start,
-                       const int32_t* __restrict__ tmp_idx, int32_t* __restrict__ perm) {
+                       const int32_t* __restrict__ tmp_idx, int32_t* __restrict__ perm, int32_t* __restrict__ inv_perm) {
   UD_PARTICLE_INDEX(k, env, g);
   if (!live_) return;
   int p = tmp_idx[g];
@@ -98,26 +126,29 @@ __global__ void k_rank(MpmConst k, const int32_t* __restrict__ keys, const int32
   int rank = 0;
   for (int j = lo; j < hi; ++j) rank += seg[j] < p;
   perm[(size_t)env * k.n + lo + rank] = p;
+  inv_perm[(size_t)env * k.n + p] = lo + rank;   // sorted slot of original particle p (the un-sort gathers by it)
 }
 
-__global__ void k_identity_perm(MpmConst k, int32_t* __restrict__ perm) {
+__global__ void k_identity_perm(MpmConst k, int32_t* __restrict__ perm, int32_t* __restrict__ inv_perm) {
   UD_PARTICLE_INDEX(k, env, g);
-  if (live_) perm[g] = g - env * k.n;
+  if (live_) perm[g] = inv_perm[g] = g - env * k.n;
 }
 
 void launch_sort(const MpmConst& k, const float* x_aos, const MpmWs& ws, int32_t* out_base, cudaStream_t st) {
   if (!tuning_sort() && !out_base) {  // A/B: no binning
     KScope ks_(KC_SORT, st, 1);
-    k_identity_perm<<<pgrid(k, 256), 256, 0, st>>>(k, ws.perm);
+    k_identity_perm<<<pgrid(k, 256), 256, 0, st>>>(k, ws.perm, ws.inv_perm);
     return;
   }
-  KScope ks_(KC_SORT, st, 6);
+  KScope ks_(KC_SORT, st, 7);
   cudaMemsetAsync(ws.cell_start, 0, sizeof(int32_t) * (size_t)k.B * (k.NK + 1), st);
   cudaMemsetAsync(ws.cursor, 0, sizeof(int32_t) * (size_t)k.B * k.NK, st);
   k_keys<<<pgrid(k, 256), 256, 0, st>>>(k, x_aos, ws.keys, ws.cell_start, out_base);
-  k_scan<<<k.B, 1024, 0, st>>>(k, ws.cell_start);
+  const dim3 sg(cdiv(k.NK, SCAN_CHUNK), k.B);
+  k_scan_sums<<<sg, SCAN_CHUNK, 0, st>>>(k, ws.cell_start, ws.chunk_sum);
+  k_scan_chunks<<<sg, SCAN_CHUNK, 0, st>>>(k, ws.cell_start, ws.chunk_sum);
   k_place<<<pgrid(k, 256), 256, 0, st>>>(k, ws.keys, ws.cell_start, ws.cursor, ws.tmp_idx);
-  k_rank<<<pgrid(k, 256), 256, 0, st>>>(k, ws.keys, ws.cell_start, ws.tmp_idx, ws.perm);
+  k_rank<<<pgrid(k, 256), 256, 0, st>>>(k, ws.keys, ws.cell_start, ws.tmp_idx, ws.perm, ws.inv_perm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -195,7 +226,7 @@ constexpr int DEAD_KEY = 0x40000000;
 // Marks the 4x4x4 grid block of cell (ix,iy,iz) as scattered-into: a fire-and-forget store (a load-then-store would
 // put an L2 round trip on every CTA's path to its first barrier: measured +20 us on k_p2g).
 UD_DEV void mark_block(const MpmConst& k, int32_t* __restrict__ flag_env, int ix, int iy, int iz) {
-  flag_env[((ix >> 2) * k.nby + (iy >> 2)) * k.nbz + (iz >> 2)] = 1;
+  flag_env[((ix >> 2) * k.nby + (iy >> 2)) * k.nbz + (iz >> 2)] = BLK_MARK_CTA;
 }
 UD_DEV int base_key(const int base[3]) { return (base[0] * 2048 + base[1]) * 2048 + base[2]; }
 
@@ -423,24 +454,28 @@ __device__ __forceinline__ void load_particle(const float* __restrict__ ps, int 
 //   wt * (u + a*Ac[0] + b*Ac[1] + c*Ac[2]),  u = p_mass v - dx A fx,  Ac[j] = dx * column j of A
 // `vt_in` is the forward's warm-start buffer (VT tile) or, in the recompute pass (svd_out != null), the previous
 // substep's SVD tile.
+// Every global load of the particle is issued before the first one is consumed (one DRAM round trip per warp, not
+// three: ncu showed the warm-start and per-particle parameter loads waiting behind the stencil of x).
 __device__ __forceinline__ void p2g_front(const MpmConst& k, int env, int g, int gp, bool wr, const float* __restrict__ ps_in,
                                           float* __restrict__ ps_out, const float* __restrict__ mu_s,
                                           const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
                                           const float* __restrict__ h_s, const float* __restrict__ vt_in,
                                           float* __restrict__ vt_out, float* __restrict__ svd_out, Stencil& st,
                                           float u[3], float Ac[3][3]) {
-  float x[3], v[3];
-  Mat3 C, F;
-  load_particle(ps_in, gp, x, v, C, F);
-  make_stencil(x, k.inv_dx, st);
-  Consti o;
   float vt0[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
   const bool warm = vt_in != nullptr;  // grid-uniform
   if (warm) {
     if (svd_out) load_comps<SV_VT, 9, SV_NQ>(vt_in, gp, vt0);
     else load_comps<0, 9, VT_NQ>(vt_in, gp, vt0);
   }
-  constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+  const float hp = h_s[g], mu_e = mu_s[env], la_e = la_s[env];
+  const int mat = mat_s[g];
+  float x[3], v[3];
+  Mat3 C, F;
+  load_particle(ps_in, gp, x, v, C, F);
+  make_stencil(x, k.inv_dx, st);
+  Consti o;
+  constitutive_pre(k, C, F, mu_e, la_e, hp, mat, o);
   svd3_ws(o.F1, o.U, o.s, o.Vt, warm, vt0);
   constitutive_post(k, C, o);
   if (wr) {   // padding lanes of an env's last tile write too: the next substep's dead lanes read initialised memory
@@ -562,6 +597,16 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
 // per warp), each flushed by 9 nodes x 3 row groups.
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;
+// The 4x4x4 grid blocks a substep's P2G scatters into, listed by the scatter itself: the first warp to touch a block
+// stamps its flag (flags are zeroed once per call, the stamp is substep + 1) and appends it to the substep's list, which
+// the grid update then walks.  The flag is read through L1 first: after the first touch per SM the check is an L1 hit
+// and the atomic is skipped (a stale "unmarked" only costs a redundant atomic, never a duplicate entry).
+struct BlkList {
+  int32_t* flag;    // [B * nblk]
+  int32_t* list;    // this substep's list
+  int32_t* count;   // this substep's counter
+  int stamp;
+};
 struct WarpGroup {
   unsigned mm;   // lanes whose particle sits in my base cell
   unsigned lb;   // leader lanes, one per distinct cell of the warp
@@ -588,8 +633,7 @@ template <int NW> constexpr size_t warp_tile_bytes() { return sizeof(float4) * 3
 // Flush of one window: nodes [j0, j0 + WN).  `tile` is this warp's [32][WN] float4 array.
 template <int NW, bool CLAMP, bool DET>
 __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __restrict__ tile, const WarpGroup& g,
-                                           const int base[3], bool live, int j0, float4* __restrict__ genv,
-                                           int32_t* __restrict__ blk_flag) {
+                                           const int base[3], bool live, int j0, float4* __restrict__ genv, int env) {
   constexpr int WN = warp_tile_nodes<NW>(), RG = NW == 1 ? 1 : 3;
   const int lane = threadIdx.x & 31;
   const bool act = lane < WN * RG;
@@ -655,18 +699,46 @@ __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __re
     } else {
       atomicAdd(&genv[cell], acc);
     }
-    // a 3-node span touches at most two 4x4x4 blocks per axis, both reached by its end nodes: corners mark everything
-    if (!CLAMP && blk_flag && (k.mark == 1 || (k.mark == 2 && a != 1 && b != 1 && c != 1))) mark_block(k, blk_flag, ix, iy, iz);
+  }
+}
+
+// Marks (and lists) the 4x4x4 grid blocks the warp's scatter touches.  A 3-node span touches at most two blocks per
+// axis, both reached by its end nodes, so the 8 corner nodes of every segment mark everything.  One lane per
+// (segment, corner), four segments per pass, AFTER the flush: the flag loads of a warp are one round trip instead of
+// one per segment inside the flush loop (ncu: 9 % of k_p2g_warp's stall samples sat on that dependent load).
+// Measured: 147.6 -> 140.0 us per launch; issuing the flag loads before the staging instead was slower (156.7 us).
+// The flag is read through L1 first: after the first touch per SM the check is an L1 hit and the atomic is skipped (a
+// stale "unmarked" only costs a redundant atomic, never a duplicate entry).
+__device__ __forceinline__ void warp_mark_blocks(const MpmConst& k, const WarpGroup& g, const int base[3], bool live,
+                                                 const BlkList& bl, int env) {
+  if (k.mark == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int a = (lane & 4) ? 2 : 0, b = (lane & 2) ? 2 : 0, c = (lane & 1) ? 2 : 0;
+  const int nseg = __popc(g.lb);
+  for (int s0 = 0; s0 < nseg; s0 += 4) {   // warp-uniform; warps spanning more than four cells are rare
+    const int my = s0 + (lane >> 3);
+    int L = 0, i = 0;
+    for (unsigned bits = g.lb; bits; bits &= bits - 1, ++i) L = i == my ? __ffs(bits) - 1 : L;
+    const int bx = __shfl_sync(FULL, base[0], L), by = __shfl_sync(FULL, base[1], L), bz = __shfl_sync(FULL, base[2], L);
+    const int lv = __shfl_sync(FULL, (int)live, L);
+    if (my >= nseg || !lv) continue;
+    const int ix = idx_scatter(bx + a, k.rx), iy = idx_scatter(by + b, k.ry), iz = idx_scatter(bz + c, k.rz);
+    if ((ix | iy | iz) < 0) continue;
+    const int w = env * (k.nbx * k.nby * k.nbz) + ((ix >> 2) * k.nby + (iy >> 2)) * k.nbz + (iz >> 2);
+    if (__ldca(bl.flag + w) != bl.stamp && atomicExch(bl.flag + w, bl.stamp) != bl.stamp) bl.list[atomicAdd(bl.count, 1)] = w;
   }
 }
 
 constexpr int P2GW_BLOCK = 128;   // 4 independent warps per CTA (the CTA is only the unit shared memory is carved in)
+#ifndef UD_P2G_MINB
+#define UD_P2G_MINB 1
+#endif
 template <int NW, bool DET>
-__global__ void __launch_bounds__(P2GW_BLOCK)
+__global__ void __launch_bounds__(P2GW_BLOCK, UD_P2G_MINB)
 k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
            const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
            const float* __restrict__ h_s, const float* __restrict__ vt_in, float* __restrict__ vt_out,
-           float* __restrict__ svd_out, int32_t* __restrict__ blk_flag) {
+           float* __restrict__ svd_out, BlkList bl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WN = warp_tile_nodes<NW>();
   float4* tile = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * warp_tile_bytes<NW>());   // [32][WN]
@@ -677,7 +749,6 @@ k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
   p2g_front(k, env, g, gp, true, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, st, u, Ac);
   const WarpGroup wg = warp_group(live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY);
   float4* genv = grid + (size_t)env * k.G * (DET ? 2 : 1);   // DET: the int64 accumulator array (32 B per cell)
-  int32_t* flag_env = blk_flag + (size_t)env * (k.nbx * k.nby * k.nbz);
   float4* myrow = tile + wg.row * WN;
   const float lw = live_ ? 1.f : 0.f;
 #pragma unroll
@@ -702,8 +773,9 @@ k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
       }
     }
     __syncwarp();
-    warp_flush<NW, false, DET>(k, tile, wg, st.base, live_, win * WN, genv, flag_env);
+    warp_flush<NW, false, DET>(k, tile, wg, st.base, live_, win * WN, genv, env);
   }
+  warp_mark_blocks(k, wg, st.base, live_, bl, env);
 }
 
 static int g_warp_nw = 1;   // staging windows of the warp-local kernels (1 or 3); 0 = the round-1 CTA-staged kernels
@@ -713,29 +785,38 @@ int tuning_warp(int v) {
   return o;
 }
 
+static BlkList blk_list_of(const MpmConst& k, const MpmWs& ws, int substep) {
+  const size_t total = (size_t)k.B * k.nbx * k.nby * k.nbz;
+  BlkList bl = {ws.blk_flag, ws.blk_list + (size_t)(substep % ws.blk_nbuf) * total, ws.blk_count + substep, substep + 1};
+  return bl;
+}
+
 template <int NW, bool DET>
 static void launch_p2g_warp(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
-                            const float* la_s, const float* vt_in, float* vt_out, float* svd_out, const MpmWs& ws,
-                            cudaStream_t st) {
+                            const float* la_s, const float* vt_in, float* vt_out, float* svd_out, int substep,
+                            const MpmWs& ws, cudaStream_t st) {
   const size_t smem = warp_tile_bytes<NW>() * (P2GW_BLOCK / 32);
   // per-DEVICE attribute (one host thread per device under pmap): set on every launch
   cudaFuncSetAttribute(k_p2g_warp<NW, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_p2g_warp<NW, DET><<<pgrid(k, P2GW_BLOCK), P2GW_BLOCK, smem, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s,
-                                                                     vt_in, vt_out, svd_out, ws.blk_flag);
+                                                                     vt_in, vt_out, svd_out, blk_list_of(k, ws, substep));
 }
 
+// true: the P2G kernels in use append the touched blocks to the substep's list themselves (no k_blk_compact pass)
+bool p2g_lists_blocks() { return tuning_stage() && g_warp_nw; }
+
 void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
-                const float* la_s, const float* vt_in, float* vt_out, float* svd_out, const MpmWs& ws,
+                const float* la_s, const float* vt_in, float* vt_out, float* svd_out, int substep, const MpmWs& ws,
                 cudaStream_t st) {
   KScope ks_(KC_P2G, st);
   if (tuning_stage() && g_warp_nw) {
     float4* fix = reinterpret_cast<float4*>(ws.grid_fix);
     if (g_warp_nw == 1) {
-      if (fix) launch_p2g_warp<1, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, ws, st);
-      else launch_p2g_warp<1, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, ws, st);
+      if (fix) launch_p2g_warp<1, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st);
+      else launch_p2g_warp<1, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st);
     } else {
-      if (fix) launch_p2g_warp<3, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, ws, st);
-      else launch_p2g_warp<3, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, ws, st);
+      if (fix) launch_p2g_warp<3, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st);
+      else launch_p2g_warp<3, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st);
     }
     return;
   }
@@ -758,117 +839,158 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
 // G2P (g2p_micro, :196-221) + advection (:326).  Out-of-range nodes clamp (JAX gather rule).
 // Rows of C' of original particles 0..2 are kept for the J update quirk (:327).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UD_BLOCK, 8)
-k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ grid,
-      const int32_t* __restrict__ perm, float* __restrict__ jrows, int substep) {
-  // Warp-local node tile: the 32 particles of a warp sit in a few cells (sorted order), so the warp fetches the 27
-  // grid velocities of each DISTINCT base cell once (<= G2P_TILE_CELLS cells, no block barrier) and every lane reads
-  // its stencil from shared memory; warps spanning more cells gather from L1/L2 as before.
-  __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_CELLS * 27];
-  __shared__ int4 wbase[UD_BLOCK / 32][G2P_TILE_CELLS];
-  UD_PARTICLE_INDEX(k, env, g);
-  if (slot_ - (int)(threadIdx.x & 31) >= k.n) return;   // warp-uniform
-  float x[3];
-  load_comps<PS_X, 3, PS_NQ>(ps_in, gp, x);
-  Stencil st;
-  make_stencil(x, k.inv_dx, st);
-  const float4* genv = grid + (size_t)env * k.G;
+// The 27-node gather of G2P for one warp: nv = sum wt g, nC = 4 inv_dx sum wt g (x) d.  The 32 particles of a warp
+// sit in a few cells (sorted order), so the warp fetches the 27 grid velocities of each DISTINCT base cell once
+// (<= G2P_TILE_CELLS cells, all loads issued before the first is consumed, no block barrier) into `tile` and every
+// lane reads its stencil from shared memory; warps spanning more cells gather from L1/L2.
+// All lanes of the warp must call it.  `tile` [G2P_TILE_CELLS*27] and `cb` [G2P_TILE_CELLS] are per-warp shared memory.
+// Fills this warp's node tile with the 27 grid values of each distinct base cell of the warp (<= G2P_TILE_CELLS cells;
+// all loads are issued before the first one is consumed: one L2 round trip).  CLAMP: gather rule (clamped indices);
+// otherwise the scatter rule's transpose (dropped nodes read as zero).  Returns false (warp-uniform) when the warp
+// spans more cells than the tile holds; *gid = index of my cell in the tile.  All lanes of the warp must call it.
+template <bool CLAMP>
+__device__ __forceinline__ bool warp_tile_fill(const MpmConst& k, const float4* __restrict__ genv, const int base[3], bool live,
+                                               float4* __restrict__ tile, int* gid_out) {
+  // tile layout: [cell][32] float4, node j = a*9 + b*3 + c of cell ge at tile[ge * 32 + j]: lane j fetches node j of
+  // every cell, so the node offsets (a, b, c) are per-lane constants (no per-element index arithmetic)
   const int lane = threadIdx.x & 31;
-  const int key = live_ ? base_key(st.base) : 0x7fffffff - lane;   // dead lanes: singleton groups no base can collide with
+  const int key = live ? base_key(base) : 0x7fffffff - lane;   // dead lanes: singleton groups no base can collide with
   const unsigned mm = __match_any_sync(0xffffffffu, key);
   const int leadlane = __ffs(mm) - 1;
-  const unsigned lb = __ballot_sync(0xffffffffu, lane == leadlane && live_);
+  const unsigned lb = __ballot_sync(0xffffffffu, lane == leadlane && live);
   const int ngroups = __popc(lb);
-  const int gid = __popc(lb & ((1u << leadlane) - 1u));
+  *gid_out = __popc(lb & ((1u << leadlane) - 1u));
   const bool tiled = ngroups <= G2P_TILE_CELLS && ngroups > 0;    // warp-uniform
-  float4* tile = wtile[threadIdx.x >> 5];
   if (tiled) {
-    int4* cb = wbase[threadIdx.x >> 5];
-    if (lane == leadlane && live_) cb[gid] = make_int4(st.base[0], st.base[1], st.base[2], 0);
-    __syncwarp();
-    const int total = ngroups * 27;
-    // all loads of the tile are issued before the first one is consumed (one L2 round trip instead of up to four)
-    float4 tmp[(G2P_TILE_CELLS * 27 + 31) / 32];
+    const int jn = lane < 27 ? lane : 0;
+    const int a = jn / 9, b = (jn / 3) % 3, c = jn % 3;
+    float4 tmp[G2P_TILE_CELLS];
+    unsigned bits = lb;
 #pragma unroll
-    for (int it = 0; it < (G2P_TILE_CELLS * 27 + 31) / 32; ++it) {
-      const int e = it * 32 + lane;
-      if (e < total) {
-        const int ge = e / 27, j = e - ge * 27;
-        const int4 b = cb[ge];
-        const int ix = idx_gather(b.x + j / 9, k.rx), iy = idx_gather(b.y + (j / 3) % 3, k.ry), iz = idx_gather(b.z + j % 3, k.rz);
-        tmp[it] = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
+    for (int ge = 0; ge < G2P_TILE_CELLS; ++ge) {
+      tmp[ge] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ge < ngroups) {   // warp-uniform
+        const int L = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int bx = __shfl_sync(0xffffffffu, base[0], L), by = __shfl_sync(0xffffffffu, base[1], L),
+                  bz = __shfl_sync(0xffffffffu, base[2], L);
+        int ix, iy, iz;
+        if (CLAMP) {
+          ix = idx_gather(bx + a, k.rx);
+          iy = idx_gather(by + b, k.ry);
+          iz = idx_gather(bz + c, k.rz);
+        } else {
+          ix = idx_scatter(bx + a, k.rx);
+          iy = idx_scatter(by + b, k.ry);
+          iz = idx_scatter(bz + c, k.rz);
+        }
+        if (lane < 27 && (CLAMP || (ix | iy | iz) >= 0)) tmp[ge] = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
       }
     }
 #pragma unroll
-    for (int it = 0; it < (G2P_TILE_CELLS * 27 + 31) / 32; ++it) {
-      const int e = it * 32 + lane;
-      if (e < total) tile[e] = tmp[it];
-    }
+    for (int ge = 0; ge < G2P_TILE_CELLS; ++ge)
+      if (ge < ngroups) tile[ge * 32 + lane] = tmp[ge];
     __syncwarp();
   }
-  if (!live_) {   // padding lanes of the env's last tile stay a harmless particle at the origin
-    float z[15];
+  return tiled;
+}
+
+// nv = sum wt g,  nC = 4 inv_dx sum wt g (x) (off - fx), contracted axis by axis (z, then y, then x) instead of node
+// by node: with o' = off - 1 in {-1, 0, 1} and f' = fx - 1 in [-0.5, 0.5),
+//   nC_ij = 4 inv_dx (X_j[i] - f'_j nv_i),   X_j = sum wt g o'_j
+// and every partial sum over c (then b) is shared by the four quantities: ~260 instead of ~430 FP instructions.
+__device__ __forceinline__ void g2p_gather(const MpmConst& k, const float4* __restrict__ genv, const Stencil& st, bool live,
+                                           float4* __restrict__ tile, float nv[3], Mat3& nC) {
+  int gid;
+  const bool tiled = warp_tile_fill<true>(k, genv, st.base, live, tile, &gid);
 #pragma unroll
-    for (int c = 0; c < 15; ++c) z[c] = 0.f;
-    store_comps<0, 15, PS_NQ>(ps_out, gp, z);
-    return;
-  }
-  const float4* my_tile = tile + gid * 27;
-  float nv[3] = {0.f, 0.f, 0.f};
-  Mat3 nC = mat_zero();
+  for (int c = 0; c < 3; ++c) nv[c] = 0.f;
+  nC = mat_zero();
+  if (!live) return;
+  const float4* my_tile = tile + gid * 32;
+  float Xa[3] = {0.f, 0.f, 0.f}, Xb[3] = {0.f, 0.f, 0.f}, Xc[3] = {0.f, 0.f, 0.f};
   auto nodes = [&](auto tiled_tag) {
     constexpr bool TILED = decltype(tiled_tag)::value;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const int ix = TILED ? 0 : idx_gather(st.base[0] + a, k.rx);
-      float d0 = (float)a - st.fx[0];
+      float U0[3] = {0.f, 0.f, 0.f}, Ub[3] = {0.f, 0.f, 0.f}, Uc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
         const int iy = TILED ? 0 : idx_gather(st.base[1] + b, k.ry);
-        float d1 = (float)b - st.fx[1];
-        float wab = st.w[a][0] * st.w[b][1];
+        float4 gv[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          float d2 = (float)c - st.fx[2];
-          float wt = wab * st.w[c][2];
-          float4 gv;
           if (TILED) {
-            gv = my_tile[a * 9 + b * 3 + c];
+            gv[c] = my_tile[a * 9 + b * 3 + c];
           } else {
             const int iz = idx_gather(st.base[2] + c, k.rz);
-            gv = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
-          }
-          float wg[3] = {wt * gv.x, wt * gv.y, wt * gv.z};
-          float dd[3] = {d0, d1, d2};
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            nv[i] += wg[i];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) nC(i, j) += wg[i] * dd[j];
+            gv[c] = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
           }
         }
+        const float g0[3] = {gv[0].x, gv[0].y, gv[0].z}, g1[3] = {gv[1].x, gv[1].y, gv[1].z}, g2[3] = {gv[2].x, gv[2].y, gv[2].z};
+        const float wy = st.w[b][1];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float p0 = st.w[0][2] * g0[i], p2 = st.w[2][2] * g2[i];
+          const float T0 = (p0 + st.w[1][2] * g1[i]) + p2;   // sum_c w_c g
+          const float T2 = p2 - p0;                            // sum_c w_c o'_c g
+          const float q = wy * T0;
+          U0[i] += q;
+          if (b == 0) Ub[i] -= q;
+          if (b == 2) Ub[i] += q;
+          Uc[i] += wy * T2;
+        }
+      }
+      const float wx = st.w[a][0];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float q = wx * U0[i];
+        nv[i] += q;
+        if (a == 0) Xa[i] -= q;
+        if (a == 2) Xa[i] += q;
+        Xb[i] += wx * Ub[i];
+        Xc[i] += wx * Uc[i];
       }
     }
   };
   if (tiled) nodes(std::true_type{});
   else nodes(std::false_type{});
-  float outv[15];
-  {  // C' = 4 inv_dx sum wt g (x) d   (the factor is applied once, after the 27-node sum)
-    const float c4 = 4.f * k.inv_dx;
+  const float c4 = 4.f * k.inv_dx;   // the factor is applied once, after the 27-node sum
+  const float f0 = st.fx[0] - 1.f, f1 = st.fx[1] - 1.f, f2 = st.fx[2] - 1.f;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) {
-      nC.m[c] *= c4;
-      outv[PS_C + c] = nC.m[c];
-    }
+  for (int i = 0; i < 3; ++i) {
+    nC(i, 0) = c4 * (Xa[i] - f0 * nv[i]);
+    nC(i, 1) = c4 * (Xb[i] - f1 * nv[i]);
+    nC(i, 2) = c4 * (Xc[i] - f2 * nv[i]);
   }
+}
+
+__global__ void __launch_bounds__(UD_BLOCK, 8)
+k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ grid,
+      const int32_t* __restrict__ perm, float* __restrict__ jrows, int substep) {
+  __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_CELLS * 32];
+  UD_PARTICLE_INDEX(k, env, g);
+  if (slot_ - (int)(threadIdx.x & 31) >= k.n) return;   // warp-uniform
+  const int p = perm[g];   // needed only at the end: issued with the first load
+  float x[3];
+  load_comps<PS_X, 3, PS_NQ>(ps_in, gp, x);
+  Stencil st;
+  make_stencil(x, k.inv_dx, st);
+  float nv[3];
+  Mat3 nC;
+  g2p_gather(k, grid + (size_t)env * k.G, st, live_, wtile[threadIdx.x >> 5], nv, nC);
+  // padding lanes of the env's last tile (nv = nC = 0) stay a harmless particle at the origin
+  float outv[15];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) outv[PS_C + c] = nC.m[c];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    outv[PS_X + c] = x[c] + k.dt * nv[c];
+    outv[PS_X + c] = live_ ? x[c] + k.dt * nv[c] : 0.f;
     outv[PS_V + c] = nv[c];
   }
   store_comps<0, 15, PS_NQ>(ps_out, gp, outv);
-  int p = perm[g];
-  if (p < 3) {
+  if (live_ && p < 3) {
     float* jr = jrows + ((size_t)env * k.S + substep) * 9 + p * 3;
     jr[0] = nC(p, 0);
     jr[1] = nC(p, 1);
@@ -882,17 +1004,19 @@ void launch_g2p(const MpmConst& k, const float* ps_in, float* ps_out, const floa
   k_g2p<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, ws.perm, ws.jrows, substep);
 }
 
-// sorted SoA -> AoS outputs; J' = J * prod_f (1 + dt * trace-quirk_f), sequentially as the reference
+// sorted tiles -> AoS outputs; J' = J * prod_f (1 + dt * trace-quirk_f), sequentially as the reference.
+// One thread per ORIGINAL particle, which gathers its sorted slot through the inverse permutation: the AoS stores of a
+// warp are contiguous, the scattered side is the read (round 1 scattered the stores: 160 us instead of ~70).
 __global__ void k_unsort_state(MpmConst k, const float* __restrict__ ps, const float* __restrict__ J_in,
-                               const int32_t* __restrict__ perm, const float* __restrict__ jrows,
+                               const int32_t* __restrict__ inv_perm, const float* __restrict__ jrows,
                                float* __restrict__ x, float* __restrict__ v, float* __restrict__ C,
                                float* __restrict__ F, float* __restrict__ J) {
   UD_PARTICLE_INDEX(k, env, g);
   if (!live_) return;
-  int p = perm[g];
-  size_t o = (size_t)env * k.n + p;
+  const size_t o = g;                                   // original particle env * n + slot_
+  const int sp = env * k.n_pad + inv_perm[g];           // its sorted slot
   float st[PS_NCOMP];
-  load_comps<0, PS_NCOMP, PS_NQ>(ps, gp, st);
+  load_comps<0, PS_NCOMP, PS_NQ>(ps, sp, st);
 #pragma unroll
   for (int c = 0; c < 3; ++c) x[3 * o + c] = st[PS_X + c];
 #pragma unroll
@@ -920,7 +1044,7 @@ __global__ void k_unsort_state(MpmConst k, const float* __restrict__ ps, const f
 void launch_unsort_state(const MpmConst& k, const float* ps_slot, const float* J_in, const MpmWs& ws,
                          ud_mpm_state* out, cudaStream_t st) {
   KScope ks_(KC_UNSORT, st);
-  k_unsort_state<<<pgrid(k, 256), 256, 0, st>>>(k, ps_slot, J_in, ws.perm, ws.jrows, out->x, out->v, out->C,
+  k_unsort_state<<<pgrid(k, 256), 256, 0, st>>>(k, ps_slot, J_in, ws.inv_perm, ws.jrows, out->x, out->v, out->C,
                                                   out->F, out->J);
 }
 
@@ -1085,7 +1209,7 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
 // warp_flush() with clamped target indices (transpose of the clamping gather).  No block barrier.
 constexpr int G2PBW_BLOCK = 64;
 constexpr int G2PBW_CELLS = 4;   // distinct cells per warp whose grid velocities are tiled; more -> gather from L1/L2
-template <int NW> constexpr size_t g2pbw_warp_bytes() { return warp_tile_bytes<NW>() + sizeof(float4) * G2PBW_CELLS * 27; }
+template <int NW> constexpr size_t g2pbw_warp_bytes() { return warp_tile_bytes<NW>() + sizeof(float4) * G2PBW_CELLS * 32; }
 template <int NW>
 __global__ void __launch_bounds__(G2PBW_BLOCK)
 k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict__ grid_out,
@@ -1094,7 +1218,7 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
   constexpr int WN = warp_tile_nodes<NW>();
   unsigned char* wbase = smem_raw + (threadIdx.x >> 5) * g2pbw_warp_bytes<NW>();
   float4* tile = reinterpret_cast<float4*>(wbase);                              // [32][WN] staged cotangents
-  float4* vtile = reinterpret_cast<float4*>(wbase + warp_tile_bytes<NW>());     // [G2PBW_CELLS][27] grid velocities
+  float4* vtile = reinterpret_cast<float4*>(wbase + warp_tile_bytes<NW>());     // [G2PBW_CELLS][32] grid velocities
   UD_PARTICLE_INDEX(k, env, g);
   const int lane = threadIdx.x & 31;
   if (slot_ - lane >= k.n) return;   // warp-uniform
@@ -1109,39 +1233,28 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
   const int leadlane = __ffs(wg.mm) - 1;
   const int my_seg = __popc(wg.lb & ((1u << leadlane) - 1u));
   const bool tiled = nseg <= G2PBW_CELLS;   // warp-uniform
-  if (tiled) {
-    float4 tmp[(G2PBW_CELLS * 27 + 31) / 32];
-    const int total = nseg * 27;
-    static_assert(G2PBW_CELLS == 4, "lead_of[] below");
-    int lead_of[4];   // lanes of the (up to four) segment leaders
-    {
-      unsigned b = wg.lb;
+  if (tiled) {   // vtile layout [cell][32]: lane j fetches node j of every cell (per-lane constant node offsets)
+    const int jn = lane < 27 ? lane : 0;
+    const int ja = jn / 9, jb = (jn / 3) % 3, jc = jn % 3;
+    float4 tmp[G2PBW_CELLS];
+    unsigned bits = wg.lb;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        lead_of[i] = b ? __ffs(b) - 1 : 0;
-        b &= b - 1;
+    for (int ge = 0; ge < G2PBW_CELLS; ++ge) {
+      if (ge < nseg) {   // warp-uniform
+        const int L = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int b0 = __shfl_sync(FULL, st.base[0], L), b1 = __shfl_sync(FULL, st.base[1], L),
+                  b2 = __shfl_sync(FULL, st.base[2], L);
+        const int ix = idx_gather(b0 + ja, k.rx), iy = idx_gather(b1 + jb, k.ry), iz = idx_gather(b2 + jc, k.rz);
+        tmp[ge] = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
       }
     }
 #pragma unroll
-    for (int it = 0; it < (G2PBW_CELLS * 27 + 31) / 32; ++it) {
-      const int e = it * 32 + lane;
-      const int ge = min(e / 27, nseg - 1), j = e - (e / 27) * 27;
-      const int src = ge == 0 ? lead_of[0] : (ge == 1 ? lead_of[1] : (ge == 2 ? lead_of[2] : lead_of[3]));
-      const int b0 = __shfl_sync(FULL, st.base[0], src), b1 = __shfl_sync(FULL, st.base[1], src),
-                b2 = __shfl_sync(FULL, st.base[2], src);
-      if (e < total) {
-        const int ix = idx_gather(b0 + j / 9, k.rx), iy = idx_gather(b1 + (j / 3) % 3, k.ry), iz = idx_gather(b2 + j % 3, k.rz);
-        tmp[it] = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < (G2PBW_CELLS * 27 + 31) / 32; ++it) {
-      const int e = it * 32 + lane;
-      if (e < total) vtile[e] = tmp[it];
-    }
+    for (int ge = 0; ge < G2PBW_CELLS; ++ge)
+      if (ge < nseg) vtile[ge * 32 + lane] = tmp[ge];
     __syncwarp();
   }
-  const float4* my_tile = vtile + my_seg * 27;
+  const float4* my_tile = vtile + my_seg * 32;
   const float lw = live_ ? 1.f : 0.f;
   const float c4 = 4.f * k.inv_dx;
   // r(a,b,c) = gv' + 4 inv_dx gC' (off - fx) = r0 + a K0 + b K1 + c K2   (K_j = 4 inv_dx * column j of gC')
@@ -1198,7 +1311,7 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
       gfx[2] += Q1 * st.w[a][0];
       if (NW == 3) {
         __syncwarp();
-        warp_flush<NW, true, false>(k, tile, wg, st.base, live_, a * WN, ggenv, nullptr);
+        warp_flush<NW, true, false>(k, tile, wg, st.base, live_, a * WN, ggenv, env);
       }
     }
   };
@@ -1216,7 +1329,7 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
   }
   if (NW == 1) {
     __syncwarp();
-    warp_flush<NW, true, false>(k, tile, wg, st.base, live_, 0, ggenv, nullptr);
+    warp_flush<NW, true, false>(k, tile, wg, st.base, live_, 0, ggenv, env);
   }
 }
 
@@ -1256,15 +1369,30 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
   // norm2 != nullptr on the step's first substep (the last one reversed): the cotangents written here are the
   // step's input cotangents, so norm_grad_state's nan_to_num + per-env sum of squares (mpm_simulator.py:389-408)
   // happen on the way out instead of in a separate pass over the 24 components
+  __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_CELLS * 32];
   UD_PARTICLE_INDEX(k, env, g);
   float gmu = 0.f, gla = 0.f, gn2 = 0.f;
+  // per-particle parameters: issued with the first load of the kernel, consumed after the tile fill
+  const int mat_p = mat_s[g];
+  const float h_p = h_s[g], mu_e = mu_s[env], la_e = la_s[env];
+  // the cotangents of the 27 nodes of each distinct base cell of the warp, fetched once per warp (dropped nodes = 0)
+  int tile_gid = 0;
+  bool tiled;
+  {
+    float x[3];
+    load_comps<PS_X, 3, PS_NQ>(ps_in, gp, x);
+    Stencil s0;
+    make_stencil(x, k.inv_dx, s0);
+    tiled = warp_tile_fill<false>(k, ggrid + (size_t)env * k.G, s0.base, live_, wtile[threadIdx.x >> 5], &tile_gid);
+  }
+  const float4* my_tile = wtile[threadIdx.x >> 5] + tile_gid * 32;
   if (live_) {
     // Phase 1: everything the 27-node gather needs is the stencil, A = dx * affine and u0.  The matrices that
     // produce them (C, F, U, s, Vt, F1, F2, D: ~80 registers) die here and are loaded again (L2 hits) for the
     // constitutive reverse after the gather, instead of staying live across it.
     Stencil st;
     float Ac[3][3], u0[3];
-    const bool plastic = mat_s[g] == 2;
+    const bool plastic = mat_p == 2;
     {
       float xvc[15], us[12];
       Mat3 C, F;
@@ -1279,11 +1407,11 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
 #pragma unroll
       for (int c = 0; c < 3; ++c) o.s[c] = us[9 + c];
       if (plastic) {  // the stress of a plastic particle is a function of (U, clip(s)) alone
-        plastic_affine(k, C, o.U, o.s, mu_s[env], la_s[env], h_s[g], o.affine);
+        plastic_affine(k, C, o.U, o.s, mu_e, la_e, h_p, o.affine);
       } else {
         load_comps<PS_F, 9, PS_NQ>(ps_in, gp, F.m);
         load_comps<SV_VT, 9, SV_NQ>(svd_in, gp, o.Vt.m);
-        constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+        constitutive_pre(k, C, F, mu_e, la_e, h_p, mat_p, o);
         constitutive_post(k, C, o);
       }
 #pragma unroll
@@ -1314,12 +1442,13 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
         for (int c = 0; c < 3; ++c) {
           const int iz = idx_scatter(st.base[2] + c, k.rz);
           const bool ok = (ix | iy | iz) >= 0;
-          float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);  // (g_momentum, g_mass); dropped node -> 0
-          if (ok) gp = __ldg(&ggenv[(ix * k.ry + iy) * k.rz + iz]);
+          float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);  // (g_momentum, g_mass); dropped node -> 0
+          if (tiled) gq = my_tile[a * 9 + b * 3 + c];
+          else if (ok) gq = __ldg(&ggenv[(ix * k.ry + iy) * k.rz + iz]);
           const float wt = wab * st.w[c][2];
-          const float q[3] = {wt * gp.x, wt * gp.y, wt * gp.z};
+          const float q[3] = {wt * gq.x, wt * gq.y, wt * gq.z};
           const float u[3] = {uab[0] + (float)c * Ac[2][0], uab[1] + (float)c * Ac[2][1], uab[2] + (float)c * Ac[2][2]};
-          const float gwt = k.p_mass * gp.w + (gp.x * u[0] + gp.y * u[1] + gp.z * u[2]);
+          const float gwt = k.p_mass * gq.w + (gq.x * u[0] + gq.y * u[1] + gq.z * u[2]);
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             Sab[i] += q[i];
@@ -1380,9 +1509,9 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     load_comps<PS_X, 3, PS_NQ>(gs, gp, gx_in);
     load_comps<PS_F, 9, PS_NQ>(gs, gp, gF2out.m);
     if (plastic) {
-      constitutive_bwd_plastic(k, C, F, o.U, o.s, o.Vt, mu_s[env], la_s[env], h_s[g], gA, gF2out, gC, gF, gmu, gla);
+      constitutive_bwd_plastic(k, C, F, o.U, o.s, o.Vt, mu_e, la_e, h_p, gA, gF2out, gC, gF, gmu, gla);
     } else {
-      constitutive_pre(k, C, F, mu_s[env], la_s[env], h_s[g], mat_s[g], o);
+      constitutive_pre(k, C, F, mu_e, la_e, h_p, mat_p, o);
       constitutive_post(k, C, o);
       constitutive_bwd(k, C, F, o, gA, gF2out, gC, gF, gmu, gla);
     }
@@ -1421,31 +1550,17 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
       store_comps<0, PS_NCOMP, PS_NQ>(gs, gp, og);
     }
   }
-  // block reduction of the per-env scalars
+  // per-env scalars: one reduction per warp, then straight to the accumulators (no block barrier at the tail)
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     gmu += __shfl_down_sync(0xffffffffu, gmu, off);
     gla += __shfl_down_sync(0xffffffffu, gla, off);
     gn2 += __shfl_down_sync(0xffffffffu, gn2, off);
   }
-  __shared__ float smu[UD_BLOCK / 32], sla[UD_BLOCK / 32], sn2[UD_BLOCK / 32];
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) {
-    smu[wid] = gmu;
-    sla[wid] = gla;
-    sn2[wid] = gn2;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float a = 0.f, b = 0.f, c = 0.f;
-    for (int i = 0; i < UD_BLOCK / 32; ++i) {
-      a += smu[i];
-      b += sla[i];
-      c += sn2[i];
-    }
-    atomicAdd(&g_scal[env * GS_STRIDE + GS_MU], a);
-    atomicAdd(&g_scal[env * GS_STRIDE + GS_LAMDA], b);
-    if (norm2) atomicAdd(&norm2[env * 2], c);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&g_scal[env * GS_STRIDE + GS_MU], gmu);
+    atomicAdd(&g_scal[env * GS_STRIDE + GS_LAMDA], gla);
+    if (norm2) atomicAdd(&norm2[env * 2], gn2);
   }
 }
 
@@ -1504,16 +1619,16 @@ UD_DEV float norm_div(float g, float n2) {
   return nrm < 1.0f ? g : g / nrm;
 }
 
-__global__ void k_unsort_cot(MpmConst k, const float* __restrict__ gs, const int32_t* __restrict__ perm,
+__global__ void k_unsort_cot(MpmConst k, const float* __restrict__ gs, const int32_t* __restrict__ inv_perm,
                              const float* __restrict__ norm2, float* __restrict__ gx, float* __restrict__ gv,
                              float* __restrict__ gC, float* __restrict__ gF, float* __restrict__ gJ) {
   UD_PARTICLE_INDEX(k, env, g);
   if (!live_) return;
-  int p = perm[g];
-  size_t o = (size_t)env * k.n + p;
+  const size_t o = g;                                   // one thread per ORIGINAL particle (contiguous AoS stores)
+  const int sp = env * k.n_pad + inv_perm[g];
   float n2 = norm2[env * 2];
   float st[PS_NCOMP];
-  load_comps<0, PS_NCOMP, PS_NQ>(gs, gp, st);
+  load_comps<0, PS_NCOMP, PS_NQ>(gs, sp, st);
   if (gx)
 #pragma unroll
     for (int c = 0; c < 3; ++c) gx[3 * o + c] = norm_div(st[PS_X + c], n2);
@@ -1575,7 +1690,7 @@ void launch_finish_bwd(const MpmConst& k, const ud_mpm_state* in, const ud_mpm_s
   (void)action;
   // the particle part of the norm (and the nan_to_num of the particle cotangents) was done by the last k_p2g_bwd
   k_norm_small<<<cdiv(k.B, 64), 64, 0, st>>>(k, *gout, ws.g_scal, ws.g_prim_in, ws.g_act, ws.norm2);
-  k_unsort_cot<<<pgrid(k, 256), 256, 0, st>>>(k, ws.gs, ws.perm, ws.norm2, gin->x, gin->v, gin->C, gin->F,
+  k_unsort_cot<<<pgrid(k, 256), 256, 0, st>>>(k, ws.gs, ws.inv_perm, ws.norm2, gin->x, gin->v, gin->C, gin->F,
                                               gin->J);
   k_write_small<<<cdiv(k.B, 64), 64, 0, st>>>(k, *gin, gaction, ws.g_scal, ws.g_prim_in, ws.g_act, ws.norm2);
 }
