@@ -117,6 +117,20 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
                     ud_mpm_state* gin, float* gaction, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* The same adjoint with K-spaced substep checkpoints INSIDE the step (north_star (e), SURVEY section 5 "save state
+ * every K substeps"; replaces the store-all residuals of the lax.scan at mpm_simulator.py:425 for long steps such as
+ * whip_rope's S = 70).  A checkpoint pass re-runs the forward in place from `in` and keeps the start state of every
+ * `window`-th substep (96 + 48 B per particle each); the windows are then recomputed one at a time, last first, into
+ * `window` state/SVD/grid slots and reversed.  Peak workspace is (ceil(S/window) * 144 + window * 192) B per particle +
+ * window * 36 B per cell instead of S * 192 B per particle + S * 36 B per cell, for one extra forward sweep.
+ * window >= S is ud_mpm_step_bwd itself.  Same results as ud_mpm_step_bwd (identical arithmetic; the fp32 REDs of the
+ * scatter kernels are order-dependent unless p2g_mode is UD_P2G_DETERMINISTIC). */
+size_t ud_mpm_bwd_windowed_workspace_bytes(const ud_mpm_params* p, int32_t window);
+int ud_mpm_step_bwd_windowed(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material,
+                             const float* h, const float* action, const ud_mpm_state* gout,
+                             ud_mpm_state* gin, float* gaction, int32_t window, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* Taped pair: the same step, but the forward keeps every substep's start state, both grids, the
  * SVD factors and the active-cell lists in `tape` (ud_mpm_tape_bytes(p) bytes, 256-byte aligned,
  * caller-owned), and ud_mpm_step_bwd_taped reverses from it without recomputing the S substeps.

@@ -127,6 +127,10 @@ def lib():
     L.ud_cloth_multi_step_bwd.restype = C.c_int
     L.ud_cloth_multi_step_bwd.argtypes = [P(ClothParams), P(ClothState), _fp, _fp, _fp, C.c_int32, _fp, P(ClothState),
                                           P(ClothState), _fp, _fp, C.c_size_t, _fp]
+    for kv in filter(None, os.environ.get("UNIDOM_B200_TUNE", "").split(",")):   # development A/B switches, "warp=2,..."
+        name, val = kv.split("=")
+        if L.ud_tuning_set(name.encode(), int(val)) < 0:
+            raise ValueError(f"UNIDOM_B200_TUNE: unknown switch {kv!r}")
     _lib = L
     return L
 

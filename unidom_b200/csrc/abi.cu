@@ -50,6 +50,7 @@ int cloth_tuning_cta_nodes(int v);   // cloth.cu
 int tuning_sort() { return g_sort; }
 int tuning_stage() { return g_stage; }
 int tuning_warp(int v);   // mpm_particles.cu
+int tuning_pers(int v);
 
 bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k) {
   if (!p) return false;
@@ -103,7 +104,8 @@ static inline void zero_async(void* p, size_t bytes, cudaStream_t st) {
 static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Carves `base` (may be null: size query only).  Returns total bytes.
-size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, MpmWs* ws) {
+// window > 0: layout of the windowed adjoint (per-substep arrays hold `window` substeps, plus the checkpoints).
+size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, MpmWs* ws, int window) {
   size_t off = 0;
   char* b = (char*)base;
   auto take = [&](size_t bytes) {
@@ -112,6 +114,7 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
     return r;
   };
   const size_t N = k.N, NP = k.N_pad, BG = (size_t)k.B * k.G, P = k.n_prim > 0 ? k.n_prim : 1, S = k.S;
+  const size_t W = window > 0 ? (size_t)window : S;   // substeps resident at a time in the per-substep arrays
   MpmWs w;
   memset(&w, 0, sizeof(w));
   w.keys = (int32_t*)take(4 * N);
@@ -138,11 +141,19 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
     w.grid_raw = (float4*)take(16 * BG * 2);
     w.grid_out = w.grid_raw;
   } else {
-    w.ps = (float*)take(4 * (size_t)PS_NCOMP * NP * (S + 1));
-    w.grid_raw = (float4*)take(16 * BG * S);
-    w.grid_out = (float4*)take(16 * BG * S);
-    w.svd_s = (float*)take(4 * (size_t)SV_NCOMP * NP * S);
-    w.act_list = (int32_t*)take(4 * BG * S);
+    w.ps = (float*)take(4 * (size_t)PS_NCOMP * NP * (W + 1));
+    w.grid_raw = (float4*)take(16 * BG * W);
+    w.grid_out = (float4*)take(16 * BG * W);
+    w.svd_s = (float*)take(4 * (size_t)SV_NCOMP * NP * W);
+    w.act_list = (int32_t*)take(4 * BG * W);
+    if (window > 0) {
+      const size_t n_win = (S + W - 1) / W;
+      w.ckpt_ps = (float*)take(4 * (size_t)PS_NCOMP * NP * n_win);
+      w.ckpt_vt = (float*)take(4 * (size_t)VT_NCOMP * NP * n_win);
+      w.run_ps = (float*)take(4 * (size_t)PS_NCOMP * NP);
+      w.run_vt = (float*)take(4 * (size_t)VT_NCOMP * NP);
+      w.run_grid = (float4*)take(16 * BG * 2);
+    }
     w.act_count = (int32_t*)take(4 * S);
     w.gs = (float*)take(4 * (size_t)PS_NCOMP * NP);
     w.ggrid = (float4*)take(16 * BG);
@@ -191,6 +202,7 @@ int ud_tuning_set(const char* name, int value) {
   if (name && !strcmp(name, "stage")) { int o = g_stage; g_stage = value; return o; }
   if (name && !strcmp(name, "mark")) { int o = g_mark; g_mark = value; return o; }
   if (name && !strcmp(name, "warp")) return tuning_warp(value);
+  if (name && !strcmp(name, "pers")) return tuning_pers(value);
   if (name && !strcmp(name, "cloth_cta_nodes")) return cloth_tuning_cta_nodes(value);
   return -1;
 }
@@ -298,31 +310,46 @@ int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
 
 // Forward sweep that keeps every substep's start state, both grids, the SVDs and the active-cell lists in a
 // bwd-layout workspace (the "tape"): the adjoint's recompute pass, and the whole of the taped forward.
-static void mpm_record_pass(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
-                            const float* action, ud_mpm_state* out, MpmWs& ws, cudaStream_t st) {
-  const size_t slot = (size_t)PS_NCOMP * k.N_pad, BG = (size_t)k.B * k.G;
+static void mpm_prepare(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
+                        const float* action, ud_mpm_state* out, MpmWs& ws, float* ps0, cudaStream_t st) {
   launch_sort(k, in->x, ws, nullptr, st);
-  launch_gather_state(k, in, material, h, ws, ws.ps, st);
+  launch_gather_state(k, in, material, h, ws, ps0, st);
   launch_fk_fwd(k, in, action, out, ws, st);
-  zero_async(ws.grid_raw, 16 * BG * k.S, st);
+}
+// Records substeps [f0, f1) into slots 0.. of the per-substep arrays (ws.sub0 must be f0).  start = state at f0
+// (null: ws.ps slot 0 already holds it); vt0 = V^T entering f0 in the forward's buffer layout (windowed adjoint).
+static void mpm_record_range(const MpmConst& k, const ud_mpm_state* in, MpmWs& ws, int f0, int f1, const float* start,
+                             const float* vt0, cudaStream_t st) {
+  const size_t slot = (size_t)PS_NCOMP * k.N_pad, BG = (size_t)k.B * k.G;
+  const int nf = f1 - f0;
+  zero_async(ws.grid_raw, 16 * BG * nf, st);
   if (ws.grid_fix) zero_async(ws.grid_fix, 32 * BG, st);   // consumed (re-zeroed) cell by cell by k_grid_fwd
   zero_async(ws.blk_flag, 4 * (size_t)k.B * k.nbx * k.nby * k.nbz, st);
-  zero_async(ws.blk_count, 4 * (size_t)k.S, st);
-  zero_async(ws.act_count, 4 * (size_t)k.S, st);
-  auto sv = [&](int f) { return ws.svd_s + (size_t)SV_NCOMP * k.N_pad * f; };
-  auto vt_in = [&](int f) { return (g_svd_warm && (f % SVD_RESTART)) ? sv(f - 1) : nullptr; };
-  auto ps = [&](int f) { return ws.ps + slot * f; };
+  zero_async(ws.blk_count + f0, 4 * (size_t)nf, st);
+  zero_async(ws.act_count + f0, 4 * (size_t)nf, st);
+  auto sv = [&](int f) { return ws.svd_s + (size_t)SV_NCOMP * k.N_pad * (f - f0); };
+  auto ps_rd = [&](int f) { return (f == f0 && start) ? start : ws.ps + slot * (f - f0); };
+  auto ps_wr = [&](int f) { return ws.ps + slot * (f - f0); };
   const bool lists = p2g_lists_blocks();
-  for (int f = 0; f < k.S; ++f) {
-    launch_p2g(k, ps(f), ps(f + 1), ws.grid_raw + BG * f, in->mu, in->lamda, vt_in(f), nullptr, sv(f), f, ws, st);
-    launch_grid_fwd(k, ws.grid_raw + BG * f, ws.grid_out + BG * f, ws.grid_fix, f, in, ws, st, nullptr, 0, lists);
-    launch_g2p(k, ps(f), ps(f + 1), ws.grid_out + BG * f, f, ws, st);
+  for (int f = f0; f < f1; ++f) {
+    const bool warm = g_svd_warm && (f % SVD_RESTART);
+    const bool from_ckpt = warm && f == f0 && vt0;
+    const float* vt_in = !warm ? nullptr : (from_ckpt ? vt0 : sv(f - 1));
+    launch_p2g(k, ps_rd(f), ps_wr(f + 1), ws.grid_raw + BG * (f - f0), in->mu, in->lamda, vt_in, nullptr, sv(f), f, ws, st,
+               from_ckpt);
+    launch_grid_fwd(k, ws.grid_raw + BG * (f - f0), ws.grid_out + BG * (f - f0), ws.grid_fix, f, in, ws, st, nullptr, 0, lists);
+    launch_g2p(k, ps_rd(f), ps_wr(f + 1), ws.grid_out + BG * (f - f0), f, ws, st);
   }
 }
+static void mpm_record_pass(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
+                            const float* action, ud_mpm_state* out, MpmWs& ws, cudaStream_t st) {
+  mpm_prepare(k, in, material, h, action, out, ws, ws.ps, st);
+  ws.sub0 = 0;
+  mpm_record_range(k, in, ws, 0, k.S, nullptr, nullptr, st);
+}
 
-static void mpm_reverse_pass(const MpmConst& k, const ud_mpm_state* in, const float* action, const ud_mpm_state* gout,
-                             ud_mpm_state* gin, float* gaction, MpmWs& ws, cudaStream_t st) {
-  const size_t slot = (size_t)PS_NCOMP * k.N_pad, BG = (size_t)k.B * k.G;
+static void mpm_reverse_begin(const MpmConst& k, const ud_mpm_state* gout, MpmWs& ws, cudaStream_t st) {
+  const size_t BG = (size_t)k.B * k.G;
   const size_t P = k.n_prim > 0 ? k.n_prim : 1;
   launch_gather_cot(k, gout, ws, st);
   zero_async(ws.g_fk_pos, 4 * (size_t)k.B * P * (k.S + 1) * 3, st);
@@ -332,17 +359,35 @@ static void mpm_reverse_pass(const MpmConst& k, const ud_mpm_state* in, const fl
   zero_async(ws.g_prim_in, 4 * (size_t)k.B * P * 16, st);
   zero_async(ws.g_act, 4 * (size_t)k.B * P * 6, st);
   zero_async(ws.ggrid, 16 * BG, st);
-  for (int f = k.S - 1; f >= 0; --f) {
-    const float* s_in = ws.ps + slot * f;
+}
+// Reverses substeps f1-1 .. f0 recorded in slots 0.. (ws.sub0 == f0).  start = state at f0 when it is not in slot 0.
+// first_of_call: no G2P^T has scattered into ws.ggrid yet.  Otherwise the grid still holds the cotangents of substep
+// f1, whose block list belongs to a window that is gone: it is re-zeroed in full.
+static void mpm_reverse_range(const MpmConst& k, const ud_mpm_state* in, MpmWs& ws, int f0, int f1, const float* start,
+                              bool first_of_call, cudaStream_t st) {
+  const size_t slot = (size_t)PS_NCOMP * k.N_pad, BG = (size_t)k.B * k.G;
+  for (int f = f1 - 1; f >= f0; --f) {
+    const float* s_in = (f == f0 && start) ? start : ws.ps + slot * (f - f0);
     // G2P^T of substep f scatters into the blocks P2G(f) marked (+ face cells through clamped indices): only those
     // are re-zeroed before the next (earlier) substep scatters
-    if (f < k.S - 1) launch_grid_clear(k, ws.ggrid, f + 1, ws, st);
-    launch_g2p_bwd(k, s_in, ws.grid_out + BG * f, ws, st);
-    launch_grid_bwd(k, ws.grid_raw + BG * f, f, in, ws, st);
-    launch_p2g_bwd(k, s_in, ws.svd_s + (size_t)SV_NCOMP * k.N_pad * f, in->mu, in->lamda, f == 0, ws, st);
+    if (f < f1 - 1) launch_grid_clear(k, ws.ggrid, f + 1, ws, st);
+    else if (!first_of_call) zero_async(ws.ggrid, 16 * BG, st);
+    launch_g2p_bwd(k, s_in, ws.grid_out + BG * (f - f0), ws, st);
+    launch_grid_bwd(k, ws.grid_raw + BG * (f - f0), f, in, ws, st);
+    launch_p2g_bwd(k, s_in, ws.svd_s + (size_t)SV_NCOMP * k.N_pad * (f - f0), in->mu, in->lamda, f == 0, ws, st);
   }
+}
+static void mpm_reverse_end(const MpmConst& k, const ud_mpm_state* in, const float* action, const ud_mpm_state* gout,
+                            ud_mpm_state* gin, float* gaction, MpmWs& ws, cudaStream_t st) {
   launch_fk_bwd(k, in, action, gout, ws, st);
   launch_finish_bwd(k, in, gout, gin, action, gaction, ws, st);
+}
+static void mpm_reverse_pass(const MpmConst& k, const ud_mpm_state* in, const float* action, const ud_mpm_state* gout,
+                             ud_mpm_state* gin, float* gaction, MpmWs& ws, cudaStream_t st) {
+  ws.sub0 = 0;
+  mpm_reverse_begin(k, gout, ws, st);
+  mpm_reverse_range(k, in, ws, 0, k.S, nullptr, true, st);
+  mpm_reverse_end(k, in, action, gout, gin, gaction, ws, st);
 }
 
 int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material, const float* h,
@@ -360,6 +405,66 @@ int ud_mpm_step_bwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   mpm_record_pass(k, in, material, h, action, nullptr, ws, st);   // checkpoint = the step input
   mpm_reverse_pass(k, in, action, gout, gin, gaction, ws, st);
   if (cudaGetLastError() != cudaSuccess) return fail(UD_E_CUDA, "ud_mpm_step_bwd: launch failed");
+  return UD_OK;
+}
+
+size_t ud_mpm_bwd_windowed_workspace_bytes(const ud_mpm_params* p, int32_t window) {
+  MpmConst k;
+  if (!mpm_fold_constants(p, &k) || window < 1) return 0;
+  if (window >= k.S) return ud_mpm_bwd_workspace_bytes(p);
+  return mpm_carve(p, k, true, nullptr, nullptr, window);
+}
+
+int ud_mpm_step_bwd_windowed(const ud_mpm_params* p, const ud_mpm_state* in, const int32_t* material, const float* h,
+                             const float* action, const ud_mpm_state* gout, ud_mpm_state* gin, float* gaction,
+                             int32_t window, void* workspace, size_t workspace_bytes, void* stream) {
+  MpmConst k;
+  if (!mpm_fold_constants(p, &k) || window < 1) return fail(UD_E_INVALID, "ud_mpm_step_bwd_windowed: invalid params");
+  if (window >= k.S)
+    return ud_mpm_step_bwd(p, in, material, h, action, gout, gin, gaction, workspace, workspace_bytes, stream);
+  if (!state_ok(k, in) || !gout || !gin || !material || !h || (k.n_prim > 0 && !action))
+    return fail(UD_E_INVALID, "ud_mpm_step_bwd_windowed: null pointer");
+  MpmWs ws;
+  size_t need = mpm_carve(p, k, true, workspace, &ws, window);
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255))
+    return fail(UD_E_WORKSPACE, "ud_mpm_step_bwd_windowed: workspace too small or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int W = window, S = k.S, n_win = (S + W - 1) / W;
+  const size_t slot = (size_t)PS_NCOMP * k.N_pad, vslot = (size_t)VT_NCOMP * k.N_pad, BG = (size_t)k.B * k.G;
+  // ---- checkpoint pass: the in-place forward from the step input, keeping the state entering every W-th substep
+  mpm_prepare(k, in, material, h, action, nullptr, ws, ws.ckpt_ps, st);
+  cudaMemcpyAsync(ws.run_ps, ws.ckpt_ps, 4 * slot, cudaMemcpyDeviceToDevice, st);
+  zero_async(ws.blk_flag, 4 * (size_t)k.B * k.nbx * k.nby * k.nbz, st);
+  zero_async(ws.blk_count, 4 * (size_t)S, st);
+  zero_async(ws.run_grid, 16 * BG * 2, st);
+  if (ws.grid_fix) zero_async(ws.grid_fix, 32 * BG, st);
+  {
+    const bool lists = p2g_lists_blocks();
+    const int last = (n_win - 1) * W;   // nothing after the last checkpoint is needed from this pass
+    for (int f = 0; f < last; ++f) {
+      float4* gf = ws.run_grid + BG * (f & 1);
+      float4* gn = ws.run_grid + BG * ((f + 1) & 1);
+      const float* vt_in = (g_svd_warm && (f % SVD_RESTART)) ? ws.run_vt : nullptr;
+      launch_p2g(k, ws.run_ps, ws.run_ps, gf, in->mu, in->lamda, vt_in, ws.run_vt, nullptr, f, ws, st);
+      launch_grid_fwd(k, gf, gf, ws.grid_fix, f, in, ws, st, (f >= 1 && f + 1 < last) ? gn : nullptr, f - 1, lists);
+      launch_g2p(k, ws.run_ps, ws.run_ps, gf, f, ws, st);
+      if ((f + 1) % W == 0) {
+        const int w = (f + 1) / W;
+        cudaMemcpyAsync(ws.ckpt_ps + slot * w, ws.run_ps, 4 * slot, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(ws.ckpt_vt + vslot * w, ws.run_vt, 4 * vslot, cudaMemcpyDeviceToDevice, st);
+      }
+    }
+  }
+  // ---- windows, last first: recompute W substeps from their checkpoint, reverse them
+  mpm_reverse_begin(k, gout, ws, st);
+  for (int w = n_win - 1; w >= 0; --w) {
+    const int f0 = w * W, f1 = f0 + W < S ? f0 + W : S;
+    ws.sub0 = f0;
+    mpm_record_range(k, in, ws, f0, f1, ws.ckpt_ps + slot * w, w ? ws.ckpt_vt + vslot * w : nullptr, st);
+    mpm_reverse_range(k, in, ws, f0, f1, ws.ckpt_ps + slot * w, w == n_win - 1, st);
+  }
+  mpm_reverse_end(k, in, action, gout, gin, gaction, ws, st);
+  if (cudaGetLastError() != cudaSuccess) return fail(UD_E_CUDA, "ud_mpm_step_bwd_windowed: launch failed");
   return UD_OK;
 }
 

@@ -63,9 +63,12 @@ UD_DEV Mat3 mat_zero() {
 // ---------------------------------------------------------------------------------------------
 // fast (approximate, <= 2 ulp) division / sqrt / rsqrt for the Jacobi rotations: the iteration is
 // self-correcting, only the final singular values and the U columns use IEEE sqrt / division.
+// single-instruction (flush-to-zero) forms: the operands are O(1) quantities of a rotation, never denormal
 UD_DEV float fast_div(float a, float b) {
 #ifdef __CUDA_ARCH__
-  return __fdividef(a, b);
+  float r;
+  asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
 #else
   return a / b;
 #endif
@@ -73,7 +76,7 @@ UD_DEV float fast_div(float a, float b) {
 UD_DEV float fast_sqrt(float a) {
 #ifdef __CUDA_ARCH__
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
   return r;
 #else
   return sqrtf(a);
@@ -81,7 +84,9 @@ UD_DEV float fast_sqrt(float a) {
 }
 UD_DEV float fast_rsqrt(float a) {
 #ifdef __CUDA_ARCH__
-  return rsqrtf(a);
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
 #else
   return 1.f / sqrtf(a);
 #endif

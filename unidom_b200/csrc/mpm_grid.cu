@@ -237,9 +237,14 @@ grid_fwd_body(const MpmConst& k, float4* grid_in, float4* grid_out, long long* _
       continue;
     }
     float p[3] = {g.x, g.y, g.z}, v[3];
+    const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
     auto prim_of = [&](int q, PrimIn<float>& pr) {
       load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
-      return true;
+      // A primitive whose influence on the cell is below 1e-12 leaves v unchanged to fp32 resolution (1 - influence
+      // rounds to 1): skipped, the same criterion the adjoint uses.  Most cells of a scene are far from every tool,
+      // and the collider chain (7 SDF evaluations for the finite-difference normal, 3 quaternion rotations) is
+      // ~20x the cost of this test.
+      return prim_active(k, gpos, pr);
     };
     cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
     grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
@@ -381,7 +386,7 @@ void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const
                      const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st, float4* clear_grid, int clear_substep,
                      bool lists_ready) {
   KScope ks_(KC_GRID, st, lists_ready ? 1 : 2);
-  int32_t* al = (grid_out != grid_in && ws.act_list) ? ws.act_list + (size_t)substep * k.B * k.G : nullptr;
+  int32_t* al = (grid_out != grid_in && ws.act_list) ? ws.act_list + (size_t)(substep - ws.sub0) * k.B * k.G : nullptr;
   int32_t* ac = al ? ws.act_count + substep : nullptr;
   const int total = k.B * k.nbx * k.nby * k.nbz;
   int32_t* bl = ws.blk_list + (size_t)(substep % ws.blk_nbuf) * total;
@@ -553,7 +558,7 @@ void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, con
   KScope ks_(KC_GRID_BWD, st);
   k_grid_bwd<<<148 * 8, 128, 0, st>>>(k, grid_raw, ws.ggrid, substep, *in, ws.fk_pos, ws.fk_rot, ws.fk_vw,
                                       ws.g_fk_pos, ws.g_fk_rot, ws.g_fk_v, ws.g_scal,
-                                      ws.act_list + (size_t)substep * k.B * k.G, ws.act_count + substep);
+                                      ws.act_list + (size_t)(substep - ws.sub0) * k.B * k.G, ws.act_count + substep);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -31,7 +31,12 @@ __device__ __forceinline__ void load_comps(const float* __restrict__ base, int g
   constexpr int Q0 = C0 / 4, Q1 = (C0 + NC - 1) / 4;
 #pragma unroll
   for (int q = Q0; q <= Q1; ++q) {
-    const float4 v = CG ? __ldcg(t + q * 32) : t[q * 32];
+    float4 v;
+    if (CG) {   // "reload": a volatile L1-cached load the compiler can neither merge with an earlier one nor hoist
+      asm volatile("ld.global.ca.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(t + q * 32));
+    } else {
+      v = t[q * 32];
+    }
     const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -98,6 +103,13 @@ struct MpmWs {
   int32_t* blk_count;   // [S] number of listed blocks per substep
   float* vt_roll;       // fwd only: [12*N_pad] V^T of the previous substep's SVD (warm start)
   int32_t* act_list;    // bwd only: [S][B*G] cells listed by the recompute pass for the grid adjoint
+  // windowed adjoint only (ud_mpm_step_bwd_windowed): K-spaced checkpoints and the checkpoint pass's scratch
+  float* ckpt_ps;       // [n_win][24*N_pad] start state of substep w*window (slot 0 = the gathered step input)
+  float* ckpt_vt;       // [n_win][12*N_pad] V^T entering that substep (SVD warm start)
+  float* run_ps;        // [24*N_pad] in-place state of the checkpoint pass
+  float* run_vt;        // [12*N_pad]
+  float4* run_grid;     // [2][B*G]
+  int sub0;             // first substep of the window the per-substep arrays (act_list) start at; 0 outside the windowed adjoint
   int32_t* act_count;   // bwd only: [S]
   float* svd_s;         // bwd only: [S*24*N_pad] SVD of F1 per substep (written by the recompute P2G)
   float* fk_pos;        // [B*P*(S+1)*3] (row S = clamp copy of row S-1)
@@ -137,15 +149,17 @@ int tuning_stage();  // 0: 27 vector REDs per particle straight to HBM instead o
 // Host helpers (abi.cu)
 int set_error(int code, const char* what);   // records the message ud_last_error() returns (thread-local); returns code
 bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k);
-size_t mpm_carve(const ud_mpm_params* p, const MpmConst& k, bool bwd, void* base, MpmWs* ws);
+size_t mpm_carve(const ud_mpm_params* p, const MpmConst& k, bool bwd, void* base, MpmWs* ws, int window = 0);
 
 // Launchers implemented in mpm_particles.cu
 void launch_sort(const MpmConst& k, const float* x_aos, const MpmWs& ws, int32_t* out_base, cudaStream_t st);
 void launch_gather_state(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
                          const MpmWs& ws, float* ps_slot, cudaStream_t st);
+// vt_in: warm start of the SVD (null: cold).  It is the forward's V^T buffer when svd_out is null or vt_in_is_vt is
+// set, else the previous substep's SVD tile.
 void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
                 const float* la_s, const float* vt_in, float* vt_out, float* svd_out, int substep, const MpmWs& ws,
-                cudaStream_t st);
+                cudaStream_t st, bool vt_in_is_vt = false);
 bool p2g_lists_blocks();   // the P2G kernels in use list the touched grid blocks themselves (no compaction pass)
 void launch_g2p(const MpmConst& k, const float* ps_in, float* ps_out, const float4* grid, int substep,
                 const MpmWs& ws, cudaStream_t st);

@@ -1,5 +1,6 @@
 // Particle-side kernels of the MLS-MPM step: per-frame binning, P2G scatter, G2P gather and their
 // adjoints.  sm_100a.  Reference: DaXBench/daxbench/core/engine/mpm_simulator.py:178-330.
+#include <algorithm>
 #include <type_traits>
 
 #include "mpm_internal.h"
@@ -9,6 +10,13 @@ namespace ud {
 #define UD_BLOCK 128
 
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+// SM count of the CURRENT device (a process may drive several devices: no process-wide cache)
+static inline int num_sms() {
+  int dev = 0, n = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
 static inline dim3 pgrid(const MpmConst& k, int block) { return dim3(cdiv(k.n, block), k.B); }
 
 // particle index of this thread: blockIdx.y = env, blockIdx.x*blockDim.x + threadIdx.x = slot in env.
@@ -21,6 +29,40 @@ static inline dim3 pgrid(const MpmConst& k, int block) { return dim3(cdiv(k.n, b
   bool live_ = slot_ < (k).n;                                \
   int g = env * (k).n + (live_ ? slot_ : 0);                 \
   int gp = env * (k).n_pad + (slot_ < (k).n_pad ? slot_ : 0);
+
+// Persistent particle kernels (round 2): the grid is one CTA per resident CTA slot and every WARP walks the 32-particle
+// tiles w, w + W, w + 2W, ... (W = warps in the grid), prefetching its next tile while it computes the current one.
+struct TileWalk {
+  int lane, nwarps, tpe, ntiles, t;   // tpe = tiles per env; t = current tile (global over envs)
+};
+__device__ __forceinline__ TileWalk tile_walk(const MpmConst& k) {
+  TileWalk w;
+  w.lane = threadIdx.x & 31;
+  w.nwarps = gridDim.x * (blockDim.x >> 5);
+  w.tpe = k.n_pad >> 5;
+  w.ntiles = k.B * w.tpe;
+  w.t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  return w;
+}
+// particle of this lane in tile t: env, g = index into per-particle arrays, gp = index into the sorted tile arrays
+__device__ __forceinline__ void tile_locate(const MpmConst& k, const TileWalk& w, int t, int& env, int& g, int& gp, bool& live) {
+  env = t / w.tpe;
+  const int slot = (t - env * w.tpe) * 32 + w.lane;
+  live = slot < k.n;
+  g = env * k.n + (live ? slot : 0);
+  gp = env * k.n_pad + slot;
+}
+static inline int persistent_ctas(const MpmConst& k, int warps_per_cta, int ctas_per_sm) {
+  return std::min(num_sms() * ctas_per_sm, cdiv((long long)k.B * (k.n_pad >> 5), warps_per_cta));
+}
+// fire-and-forget prefetch into L2 of this lane's 16 bytes of NQ quads of tile array `base` (a warp covers whole lines)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int Q0, int Q1, int NQ>
+__device__ __forceinline__ void prefetch_quads(const float* __restrict__ base, int gp) {
+  const float4* t = reinterpret_cast<const float4*>(base) + quad_index(gp, 0, NQ);
+#pragma unroll
+  for (int q = Q0; q <= Q1; ++q) prefetch_l2(t + q * 32);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Binning: key = 4x4x4-block-major cell key of base = int32(x*inv_dx - 0.5) (mpm_simulator.py:233),
@@ -456,26 +498,68 @@ __device__ __forceinline__ void load_particle(const float* __restrict__ ps, int 
 // substep's SVD tile.
 // Every global load of the particle is issued before the first one is consumed (one DRAM round trip per warp, not
 // three: ncu showed the warm-start and per-particle parameter loads waiting behind the stencil of x).
-__device__ __forceinline__ void p2g_front(const MpmConst& k, int env, int g, int gp, bool wr, const float* __restrict__ ps_in,
-                                          float* __restrict__ ps_out, const float* __restrict__ mu_s,
-                                          const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
-                                          const float* __restrict__ h_s, const float* __restrict__ vt_in,
-                                          float* __restrict__ vt_out, float* __restrict__ svd_out, Stencil& st,
-                                          float u[3], float Ac[3][3]) {
-  float vt0[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
-  const bool warm = vt_in != nullptr;  // grid-uniform
-  if (warm) {
-    if (svd_out) load_comps<SV_VT, 9, SV_NQ>(vt_in, gp, vt0);
-    else load_comps<0, 9, VT_NQ>(vt_in, gp, vt0);
+// everything P2G reads of one particle, as loaded (the persistent kernel holds the NEXT tile's loads in flight here)
+struct P2gIn {
+  float4 q[PS_NQ];   // state tile quads: x v C F
+  float4 vt[3];      // warm start: V^T (9) of the previous substep
+  float h, mu, la;
+  int mat;
+};
+__device__ __forceinline__ void p2g_issue_loads(int env, int g, int gp, const float* __restrict__ ps_in,
+                                                const float* __restrict__ mu_s, const float* __restrict__ la_s,
+                                                const int32_t* __restrict__ mat_s, const float* __restrict__ h_s,
+                                                const float* __restrict__ vt_in, bool vt_is_svd_tile, P2gIn& in) {
+  const float4* t = reinterpret_cast<const float4*>(ps_in) + quad_index(gp, 0, PS_NQ);
+#pragma unroll
+  for (int q = 0; q < PS_NQ; ++q) in.q[q] = t[q * 32];
+  if (vt_in) {   // grid-uniform
+    if (vt_is_svd_tile) {   // V^T = components 12..20 of the SVD tile: quads 3, 4, 5
+      const float4* v = reinterpret_cast<const float4*>(vt_in) + quad_index(gp, 0, SV_NQ);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) in.vt[q] = v[(3 + q) * 32];
+    } else {
+      const float4* v = reinterpret_cast<const float4*>(vt_in) + quad_index(gp, 0, VT_NQ);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) in.vt[q] = v[q * 32];
+    }
   }
-  const float hp = h_s[g], mu_e = mu_s[env], la_e = la_s[env];
-  const int mat = mat_s[g];
+  in.h = h_s[g];
+  in.mat = mat_s[g];
+  in.mu = mu_s[env];
+  in.la = la_s[env];
+}
+static_assert(SV_VT == 12 && PS_NQ == 6, "p2g_issue_loads reads V^T as whole quads");
+
+// Per-particle front half of P2G, shared by the scatter variants: F update, SVD (warm-started from the previous
+// substep's V^T), plastic clip, stress; stores F' (+ V^T for the next warm start, or the whole SVD in the recompute
+// pass).  Returns the stencil and the affine scatter value at node (a,b,c):
+//   wt * (u + a*Ac[0] + b*Ac[1] + c*Ac[2]),  u = p_mass v - dx A fx,  Ac[j] = dx * column j of A
+__device__ __forceinline__ void p2g_front_loaded(const MpmConst& k, int gp, bool wr, const P2gIn& in, bool warm,
+                                                 float* __restrict__ ps_out, float* __restrict__ vt_out,
+                                                 float* __restrict__ svd_out, Stencil& st, float u[3], float Ac[3][3]) {
+  const float sq[PS_NCOMP] = {in.q[0].x, in.q[0].y, in.q[0].z, in.q[0].w, in.q[1].x, in.q[1].y, in.q[1].z, in.q[1].w,
+                              in.q[2].x, in.q[2].y, in.q[2].z, in.q[2].w, in.q[3].x, in.q[3].y, in.q[3].z, in.q[3].w,
+                              in.q[4].x, in.q[4].y, in.q[4].z, in.q[4].w, in.q[5].x, in.q[5].y, in.q[5].z, in.q[5].w};
   float x[3], v[3];
   Mat3 C, F;
-  load_particle(ps_in, gp, x, v, C, F);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) x[c] = sq[PS_X + c];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v[c] = sq[PS_V + c];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) C.m[c] = sq[PS_C + c];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) F.m[c] = sq[PS_F + c];
+  float vt0[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  if (warm) {
+    // forward warm-start buffer: comps 0..8 of quads 0..2; SVD tile: comps 12..20 = quads 3..5 (same quad-relative layout)
+    vt0[0] = in.vt[0].x; vt0[1] = in.vt[0].y; vt0[2] = in.vt[0].z; vt0[3] = in.vt[0].w;
+    vt0[4] = in.vt[1].x; vt0[5] = in.vt[1].y; vt0[6] = in.vt[1].z; vt0[7] = in.vt[1].w;
+    vt0[8] = in.vt[2].x;
+  }
   make_stencil(x, k.inv_dx, st);
   Consti o;
-  constitutive_pre(k, C, F, mu_e, la_e, hp, mat, o);
+  constitutive_pre(k, C, F, in.mu, in.la, in.h, in.mat, o);
   svd3_ws(o.F1, o.U, o.s, o.Vt, warm, vt0);
   constitutive_post(k, C, o);
   if (wr) {   // padding lanes of an env's last tile write too: the next substep's dead lanes read initialised memory
@@ -505,6 +589,18 @@ __device__ __forceinline__ void p2g_front(const MpmConst& k, int env, int g, int
     u[i] = k.p_mass * v[i] - (Ac[0][i] * st.fx[0] + Ac[1][i] * st.fx[1] + Ac[2][i] * st.fx[2]);
   }
 }
+// load + front half (the one-tile-per-warp kernels): every global load of the particle is issued before the first one
+// is consumed (one DRAM round trip per warp, not three)
+__device__ __forceinline__ void p2g_front(const MpmConst& k, int env, int g, int gp, bool wr, const float* __restrict__ ps_in,
+                                          float* __restrict__ ps_out, const float* __restrict__ mu_s,
+                                          const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
+                                          const float* __restrict__ h_s, const float* __restrict__ vt_in,
+                                          float* __restrict__ vt_out, float* __restrict__ svd_out, bool vt_svd,
+                                          Stencil& st, float u[3], float Ac[3][3]) {
+  P2gIn in;
+  p2g_issue_loads(env, g, gp, ps_in, mu_s, la_s, mat_s, h_s, vt_in, vt_svd, in);
+  p2g_front_loaded(k, gp, wr, in, vt_in != nullptr, ps_out, vt_out, svd_out, st, u, Ac);
+}
 
 // MODE 0: CTA-staged scatter + fp32 vector REDs; 1: staged + 64-bit fixed-point REDs (deterministic);
 //      2: A/B baseline -- every particle issues its 27 vector REDs itself (no shared memory, no grouping)
@@ -514,7 +610,7 @@ __global__ void __launch_bounds__(P2G_BLOCK, 12)   // 80 registers: 12 CTAs per 
 k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
       const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
       const float* __restrict__ h_s, const float* __restrict__ vt_in, float* __restrict__ vt_out,
-      float* __restrict__ svd_out, int32_t* __restrict__ blk_flag) {
+      float* __restrict__ svd_out, int vt_svd, int32_t* __restrict__ blk_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sv = reinterpret_cast<float*>(smem_raw);                               // [P2G_NPH*4][STG_PAD]
   constexpr int STG_PAD = stg_pad<P2G_BLOCK>();
@@ -522,7 +618,7 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
   UD_PARTICLE_INDEX(k, env, g);
   Stencil st;
   float u[3], Ac[3][3];
-  p2g_front(k, env, g, gp, slot_ < k.n_pad, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, st, u, Ac);
+  p2g_front(k, env, g, gp, slot_ < k.n_pad, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, vt_svd != 0, st, u, Ac);
   constexpr bool DET = MODE == 1;
   int row = 0;
   if (MODE != 2)
@@ -627,16 +723,19 @@ __device__ __forceinline__ WarpGroup warp_group(int key) {
   g.row = start + __popc(g.mm & ((1u << lane) - 1u));
   return g;
 }
-template <int NW> constexpr int warp_tile_nodes() { return 27 / NW; }
-template <int NW> constexpr size_t warp_tile_bytes() { return sizeof(float4) * 32 * warp_tile_nodes<NW>(); }
+// NW windows of WN nodes: 1 x 27, 2 x 14 (nodes 0-13 and 14-26; rows padded to 15 float4 = 60 words so that the eight
+// rows of a 16-byte store phase fall into distinct bank groups), 3 x 9
+template <int NW> constexpr int warp_tile_nodes() { return NW == 1 ? 27 : (NW == 2 ? 14 : 9); }
+template <int NW> constexpr int warp_tile_stride() { return NW == 2 ? 15 : warp_tile_nodes<NW>(); }
+template <int NW> constexpr size_t warp_tile_bytes() { return sizeof(float4) * 32 * warp_tile_stride<NW>(); }
 
 // Flush of one window: nodes [j0, j0 + WN).  `tile` is this warp's [32][WN] float4 array.
 template <int NW, bool CLAMP, bool DET>
 __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __restrict__ tile, const WarpGroup& g,
                                            const int base[3], bool live, int j0, float4* __restrict__ genv, int env) {
-  constexpr int WN = warp_tile_nodes<NW>(), RG = NW == 1 ? 1 : 3;
+  constexpr int WN = warp_tile_nodes<NW>(), WS = warp_tile_stride<NW>(), RG = NW;   // RG row groups share a segment's rows
   const int lane = threadIdx.x & 31;
-  const bool act = lane < WN * RG;
+  const bool act = lane < WN * RG && j0 + lane % WN < 27;
   const int jl = act ? lane % WN : 0, h = act ? lane / WN : 0;
   const int j = j0 + jl;
   const int a = j / 9, b = (j / 3) % 3, c = j % 3;
@@ -665,11 +764,11 @@ __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __re
       // rows [lo, hi) of the segment for my row group, summed in row order
       const int per = (cnt + RG - 1) / RG;
       const int lo = r_begin + min(h * per, cnt), hi = r_begin + min((h + 1) * per, cnt);
-      const float4* p = tile + lo * WN + jl;
+      const float4* p = tile + lo * WS + jl;
       int left = hi - lo;
       for (; left >= 4; left -= 4) {
-        const float4 q0 = p[0], q1 = p[WN], q2 = p[2 * WN], q3 = p[3 * WN];
-        p += 4 * WN;
+        const float4 q0 = p[0], q1 = p[WS], q2 = p[2 * WS], q3 = p[3 * WS];
+        p += 4 * WS;
         acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
         acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
         acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
@@ -677,9 +776,15 @@ __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __re
       }
       for (; left > 0; --left) {
         const float4 q0 = *p;
-        p += WN;
+        p += WS;
         acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
       }
+    }
+    if (RG == 2) {   // row group 1 hands its partial sums to group 0
+      acc.x += __shfl_down_sync(FULL, acc.x, WN);
+      acc.y += __shfl_down_sync(FULL, acc.y, WN);
+      acc.z += __shfl_down_sync(FULL, acc.z, WN);
+      acc.w += __shfl_down_sync(FULL, acc.w, WN);
     }
     if (RG == 3) {   // row groups 1, 2 hand their partial sums to group 0 (fixed order)
       const float4 t1 = make_float4(__shfl_down_sync(FULL, acc.x, WN), __shfl_down_sync(FULL, acc.y, WN),
@@ -730,33 +835,32 @@ __device__ __forceinline__ void warp_mark_blocks(const MpmConst& k, const WarpGr
 }
 
 constexpr int P2GW_BLOCK = 128;   // 4 independent warps per CTA (the CTA is only the unit shared memory is carved in)
-#ifndef UD_P2G_MINB
-#define UD_P2G_MINB 1
-#endif
+// resident CTAs per SM the register allocation aims at = what the staging tiles leave room for
+template <int NW> constexpr int p2gw_min_blocks() { return NW == 1 ? 4 : 6; }
 template <int NW, bool DET>
-__global__ void __launch_bounds__(P2GW_BLOCK, UD_P2G_MINB)
+__global__ void __launch_bounds__(P2GW_BLOCK, p2gw_min_blocks<NW>())
 k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
            const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
            const float* __restrict__ h_s, const float* __restrict__ vt_in, float* __restrict__ vt_out,
-           float* __restrict__ svd_out, BlkList bl) {
+           float* __restrict__ svd_out, int vt_svd_i, BlkList bl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int WN = warp_tile_nodes<NW>();
-  float4* tile = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * warp_tile_bytes<NW>());   // [32][WN]
+  constexpr int WN = warp_tile_nodes<NW>(), WS = warp_tile_stride<NW>();
+  float4* tile = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * warp_tile_bytes<NW>());   // [32][WS]
   UD_PARTICLE_INDEX(k, env, g);
   if (slot_ - (int)(threadIdx.x & 31) >= k.n) return;   // warp-uniform: tiles beyond the env's last particle
   Stencil st;
   float u[3], Ac[3][3];
-  p2g_front(k, env, g, gp, true, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, st, u, Ac);
+  p2g_front(k, env, g, gp, true, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, vt_svd_i != 0, st, u, Ac);
   const WarpGroup wg = warp_group(live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY);
   float4* genv = grid + (size_t)env * k.G * (DET ? 2 : 1);   // DET: the int64 accumulator array (32 B per cell)
-  float4* myrow = tile + wg.row * WN;
+  float4* myrow = tile + wg.row * WS;
   const float lw = live_ ? 1.f : 0.f;
 #pragma unroll
   for (int win = 0; win < NW; ++win) {
     if (win) __syncwarp();   // the previous window has been flushed
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      if (NW == 3 && a != win) continue;
+      if ((a * 9 + 8) / WN < win || (a * 9) / WN > win) continue;   // no node of this a in the window (compile time)
       const float wa = st.w[a][0] * lw;
       const float ua[3] = {u[0] + (float)a * Ac[0][0], u[1] + (float)a * Ac[0][1], u[2] + (float)a * Ac[0][2]};
 #pragma unroll
@@ -765,8 +869,10 @@ k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
         const float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
+          const int j = a * 9 + b * 3 + c;
+          if (j / WN != win) continue;   // compile time after unrolling
           const float wt = wab * st.w[c][2];
-          myrow[(NW == 3 ? 0 : a * 9) + b * 3 + c] =
+          myrow[j - win * WN] =
               make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
                           wt * (uab[2] + (float)c * Ac[2][2]), wt * k.p_mass);
         }
@@ -778,10 +884,98 @@ k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
   warp_mark_blocks(k, wg, st.base, live_, bl, env);
 }
 
+// Persistent variant: one CTA slot per resident CTA, every warp walks the tiles w, w + W, w + 2W, ... and issues the
+// loads of its NEXT tile before it starts computing the current one, so a tile's DRAM latency (12 % of the one-tile
+// kernel's stall samples sat on the first use of x) is hidden behind a whole tile of arithmetic.
+template <int NW, bool DET>
+__global__ void __launch_bounds__(P2GW_BLOCK, p2gw_min_blocks<NW>())
+k_p2g_pers(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
+           const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
+           const float* __restrict__ h_s, const float* __restrict__ vt_in, float* __restrict__ vt_out,
+           float* __restrict__ svd_out, int vt_svd_i, BlkList bl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int WN = warp_tile_nodes<NW>(), WS = warp_tile_stride<NW>();
+  float4* tile = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * warp_tile_bytes<NW>());   // [32][WS]
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (P2GW_BLOCK / 32);
+  const int tpe = k.n_pad >> 5, ntiles = k.B * tpe;   // tiles per env, tiles in all
+  int t = blockIdx.x * (P2GW_BLOCK / 32) + (threadIdx.x >> 5);
+  if (t >= ntiles) return;
+  auto locate = [&](int tt, int& env, int& g, int& gp, bool& live) {
+    env = tt / tpe;
+    const int slot = (tt - env * tpe) * 32 + lane;
+    live = slot < k.n;
+    g = env * k.n + (live ? slot : 0);
+    gp = env * k.n_pad + slot;
+  };
+  const bool warm = vt_in != nullptr, vt_svd = vt_svd_i != 0;
+  P2gIn nx;
+  {
+    int env, g, gp;
+    bool live;
+    locate(t, env, g, gp, live);
+    p2g_issue_loads(env, g, gp, ps_in, mu_s, la_s, mat_s, h_s, vt_in, vt_svd, nx);
+  }
+  for (; t < ntiles; t += nwarps) {
+    int env, g, gp;
+    bool live_;
+    locate(t, env, g, gp, live_);
+    const P2gIn cur = nx;
+    if (t + nwarps < ntiles) {
+      int e2, g2, gp2;
+      bool l2;
+      locate(t + nwarps, e2, g2, gp2, l2);
+      p2g_issue_loads(e2, g2, gp2, ps_in, mu_s, la_s, mat_s, h_s, vt_in, vt_svd, nx);
+    }
+    Stencil st;
+    float u[3], Ac[3][3];
+    p2g_front_loaded(k, gp, true, cur, warm, ps_out, vt_out, svd_out, st, u, Ac);
+    const WarpGroup wg = warp_group(live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY);
+    float4* genv = grid + (size_t)env * k.G * (DET ? 2 : 1);   // DET: the int64 accumulator array (32 B per cell)
+    float4* myrow = tile + wg.row * WS;
+    const float lw = live_ ? 1.f : 0.f;
+    __syncwarp();   // every lane has left the previous tile's flush
+#pragma unroll
+    for (int win = 0; win < NW; ++win) {
+      if (win) __syncwarp();   // the previous window has been flushed
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if ((a * 9 + 8) / WN < win || (a * 9) / WN > win) continue;   // no node of this a in the window (compile time)
+        const float wa = st.w[a][0] * lw;
+        const float ua[3] = {u[0] + (float)a * Ac[0][0], u[1] + (float)a * Ac[0][1], u[2] + (float)a * Ac[0][2]};
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const float wab = wa * st.w[b][1];
+          const float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int j = a * 9 + b * 3 + c;
+            if (j / WN != win) continue;   // compile time after unrolling
+            const float wt = wab * st.w[c][2];
+            myrow[j - win * WN] =
+                make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
+                            wt * (uab[2] + (float)c * Ac[2][2]), wt * k.p_mass);
+          }
+        }
+      }
+      __syncwarp();
+      warp_flush<NW, false, DET>(k, tile, wg, st.base, live_, win * WN, genv, env);
+    }
+    warp_mark_blocks(k, wg, st.base, live_, bl, env);
+  }
+}
+
+static int g_pers = 1;   // 1: persistent P2G with next-tile prefetch; 0: one tile per warp
+int tuning_pers(int v) {
+  int o = g_pers;
+  if (v == 0 || v == 1) g_pers = v;
+  return o;
+}
+
 static int g_warp_nw = 1;   // staging windows of the warp-local kernels (1 or 3); 0 = the round-1 CTA-staged kernels
 int tuning_warp(int v) {
   int o = g_warp_nw;
-  if (v == 0 || v == 1 || v == 3) g_warp_nw = v;
+  if (v >= 0 && v <= 3) g_warp_nw = v;
   return o;
 }
 
@@ -794,12 +988,20 @@ static BlkList blk_list_of(const MpmConst& k, const MpmWs& ws, int substep) {
 template <int NW, bool DET>
 static void launch_p2g_warp(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
                             const float* la_s, const float* vt_in, float* vt_out, float* svd_out, int substep,
-                            const MpmWs& ws, cudaStream_t st) {
+                            const MpmWs& ws, cudaStream_t st, bool vt_svd) {
   const size_t smem = warp_tile_bytes<NW>() * (P2GW_BLOCK / 32);
   // per-DEVICE attribute (one host thread per device under pmap): set on every launch
   cudaFuncSetAttribute(k_p2g_warp<NW, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (g_pers) {
+    cudaFuncSetAttribute(k_p2g_pers<NW, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int ctas = std::min(num_sms() * p2gw_min_blocks<NW>(), cdiv((long long)k.B * (k.n_pad >> 5), P2GW_BLOCK / 32));
+    k_p2g_pers<NW, DET><<<ctas, P2GW_BLOCK, smem, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out,
+                                                        svd_out, (int)vt_svd, blk_list_of(k, ws, substep));
+    return;
+  }
   k_p2g_warp<NW, DET><<<pgrid(k, P2GW_BLOCK), P2GW_BLOCK, smem, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s,
-                                                                     vt_in, vt_out, svd_out, blk_list_of(k, ws, substep));
+                                                                     vt_in, vt_out, svd_out, (int)vt_svd,
+                                                                     blk_list_of(k, ws, substep));
 }
 
 // true: the P2G kernels in use append the touched blocks to the substep's list themselves (no k_blk_compact pass)
@@ -807,16 +1009,20 @@ bool p2g_lists_blocks() { return tuning_stage() && g_warp_nw; }
 
 void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
                 const float* la_s, const float* vt_in, float* vt_out, float* svd_out, int substep, const MpmWs& ws,
-                cudaStream_t st) {
+                cudaStream_t st, bool vt_in_is_vt) {
   KScope ks_(KC_P2G, st);
+  const bool vt_svd = svd_out != nullptr && !vt_in_is_vt;   // layout of vt_in: previous substep's SVD tile / V^T buffer
   if (tuning_stage() && g_warp_nw) {
     float4* fix = reinterpret_cast<float4*>(ws.grid_fix);
     if (g_warp_nw == 1) {
-      if (fix) launch_p2g_warp<1, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st);
-      else launch_p2g_warp<1, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st);
+      if (fix) launch_p2g_warp<1, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
+      else launch_p2g_warp<1, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
+    } else if (g_warp_nw == 2) {
+      if (fix) launch_p2g_warp<2, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
+      else launch_p2g_warp<2, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
     } else {
-      if (fix) launch_p2g_warp<3, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st);
-      else launch_p2g_warp<3, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st);
+      if (fix) launch_p2g_warp<3, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
+      else launch_p2g_warp<3, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
     }
     return;
   }
@@ -825,14 +1031,14 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
   cudaFuncSetAttribute(k_p2g<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH));
   if (!tuning_stage() && !ws.grid_fix)
     k_p2g<2><<<pgrid(k, P2G_BLOCK), P2G_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in,
-                                                      vt_out, svd_out, ws.blk_flag);
+                                                      vt_out, svd_out, (int)vt_svd, ws.blk_flag);
   else if (ws.grid_fix)
     k_p2g<1><<<pgrid(k, P2G_BLOCK), P2G_BLOCK, stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH), st>>>(
         k, ps_in, ps_out, reinterpret_cast<float4*>(ws.grid_fix), mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out,
-        ws.blk_flag);
+        (int)vt_svd, ws.blk_flag);
   else
     k_p2g<0><<<pgrid(k, P2G_BLOCK), P2G_BLOCK, stage_smem_bytes<P2G_BLOCK>(4, P2G_NPH), st>>>(
-        k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out, ws.blk_flag);
+        k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out, (int)vt_svd, ws.blk_flag);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1210,12 +1416,13 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
 constexpr int G2PBW_BLOCK = 64;
 constexpr int G2PBW_CELLS = 4;   // distinct cells per warp whose grid velocities are tiled; more -> gather from L1/L2
 template <int NW> constexpr size_t g2pbw_warp_bytes() { return warp_tile_bytes<NW>() + sizeof(float4) * G2PBW_CELLS * 32; }
+template <int NW> constexpr int g2pbw_min_blocks() { return NW == 1 ? 7 : 10; }
 template <int NW>
-__global__ void __launch_bounds__(G2PBW_BLOCK)
+__global__ void __launch_bounds__(G2PBW_BLOCK, g2pbw_min_blocks<NW>())
 k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict__ grid_out,
                float* __restrict__ gs, float4* __restrict__ ggrid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int WN = warp_tile_nodes<NW>();
+  constexpr int WN = warp_tile_nodes<NW>(), WS = warp_tile_stride<NW>();
   unsigned char* wbase = smem_raw + (threadIdx.x >> 5) * g2pbw_warp_bytes<NW>();
   float4* tile = reinterpret_cast<float4*>(wbase);                              // [32][WN] staged cotangents
   float4* vtile = reinterpret_cast<float4*>(wbase + warp_tile_bytes<NW>());     // [G2PBW_CELLS][32] grid velocities
@@ -1266,13 +1473,12 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
     r0[i] = gvt[i] - (K[0][i] * st.fx[0] + K[1][i] * st.fx[1] + K[2][i] * st.fx[2]);
   }
   float Wg[3] = {0.f, 0.f, 0.f}, gfx[3] = {0.f, 0.f, 0.f};
-  float4* myrow = tile + wg.row * WN;
+  float4* myrow = tile + wg.row * WS;
   float4* ggenv = ggrid + (size_t)env * k.G;
   auto nodes = [&](auto tiled_tag) {
     constexpr bool TILED = decltype(tiled_tag)::value;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      if (NW == 3 && a) __syncwarp();   // the previous window has been flushed
       const int ix = TILED ? 0 : idx_gather(st.base[0] + a, k.rx);
       const float wa = st.w[a][0] * lw;
       float ra[3] = {r0[0] + (float)a * K[0][0], r0[1] + (float)a * K[0][1], r0[2] + (float)a * K[0][2]};
@@ -1294,13 +1500,19 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
             gv = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
           }
           const float r[3] = {rab[0] + (float)c * K[2][0], rab[1] + (float)c * K[2][1], rab[2] + (float)c * K[2][2]};
-          myrow[(NW == 3 ? 0 : a * 9) + b * 3 + c] = make_float4(wt * r[0], wt * r[1], wt * r[2], 0.f);
+          const int j = a * 9 + b * 3 + c;          // compile time after unrolling
+          myrow[j % WN] = make_float4(wt * r[0], wt * r[1], wt * r[2], 0.f);
           const float gwt = gv.x * r[0] + gv.y * r[1] + gv.z * r[2];
           Wg[0] += wt * gv.x;
           Wg[1] += wt * gv.y;
           Wg[2] += wt * gv.z;
           P += gwt * st.w[c][2];
           Q += gwt * st.dw[c][2];
+          if (NW > 1 && (j % WN == WN - 1 || j == 26)) {   // last node of a window: flush it (compile-time position)
+            __syncwarp();
+            warp_flush<NW, true, false>(k, tile, wg, st.base, live_, (j / WN) * WN, ggenv, env);
+            if (j != 26) __syncwarp();   // the next window overwrites the rows
+          }
         }
         P1 += P * st.w[b][1];
         P2 += P * st.dw[b][1];
@@ -1309,10 +1521,6 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
       gfx[0] += P1 * st.dw[a][0];
       gfx[1] += P2 * st.w[a][0];
       gfx[2] += Q1 * st.w[a][0];
-      if (NW == 3) {
-        __syncwarp();
-        warp_flush<NW, true, false>(k, tile, wg, st.base, live_, a * WN, ggenv, env);
-      }
     }
   };
   if (tiled) nodes(std::true_type{});
@@ -1347,6 +1555,7 @@ void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_ou
   KScope ks_(KC_G2P_BWD, st);
   const int nw = tuning_warp(-1);
   if (nw == 1) return launch_g2p_bwd_warp<1>(k, ps_in, grid_out, ws, st);
+  if (nw == 2) return launch_g2p_bwd_warp<2>(k, ps_in, grid_out, ws, st);
   if (nw == 3) return launch_g2p_bwd_warp<3>(k, ps_in, grid_out, ws, st);
   cudaFuncSetAttribute(k_g2p_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2pb_smem_bytes());   // per device
   k_g2p_bwd<<<pgrid(k, G2PB_BLOCK), G2PB_BLOCK, g2pb_smem_bytes(), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
@@ -1370,19 +1579,42 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
   // step's input cotangents, so norm_grad_state's nan_to_num + per-env sum of squares (mpm_simulator.py:389-408)
   // happen on the way out instead of in a separate pass over the 24 components
   __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_CELLS * 32];
-  UD_PARTICLE_INDEX(k, env, g);
+  const TileWalk w = tile_walk(k);
+  if (w.t >= w.ntiles) return;
+  // Persistent: what the tile fill needs first (x quad, material, hardness) is loaded one tile ahead into registers;
+  // the other 15 quads a tile reads are prefetched into L2 one tile ahead (the kernel sits at its 128-register cap).
+  float4 nxq;
+  int nmat;
+  float nh;
+  auto issue = [&](int t) {
+    int e2, g2, gp2;
+    bool l2;
+    tile_locate(k, w, t, e2, g2, gp2, l2);
+    nxq = reinterpret_cast<const float4*>(ps_in)[quad_index(gp2, 0, PS_NQ)];
+    nmat = mat_s[g2];
+    nh = h_s[g2];
+    prefetch_quads<1, 5, PS_NQ>(ps_in, gp2);
+    prefetch_quads<0, 5, SV_NQ>(svd_in, gp2);
+    prefetch_quads<0, 0, PS_NQ>(gs, gp2);
+    prefetch_quads<3, 5, PS_NQ>(gs, gp2);
+  };
+  issue(w.t);
+  for (int t = w.t; t < w.ntiles; t += w.nwarps) {
+  int env, g, gp;
+  bool live_;
+  tile_locate(k, w, t, env, g, gp, live_);
   float gmu = 0.f, gla = 0.f, gn2 = 0.f;
-  // per-particle parameters: issued with the first load of the kernel, consumed after the tile fill
-  const int mat_p = mat_s[g];
-  const float h_p = h_s[g], mu_e = mu_s[env], la_e = la_s[env];
+  const int mat_p = nmat;
+  const float h_p = nh, mu_e = mu_s[env], la_e = la_s[env];
+  const float x0[3] = {nxq.x, nxq.y, nxq.z};
+  if (t + w.nwarps < w.ntiles) issue(t + w.nwarps);
   // the cotangents of the 27 nodes of each distinct base cell of the warp, fetched once per warp (dropped nodes = 0)
   int tile_gid = 0;
   bool tiled;
   {
-    float x[3];
-    load_comps<PS_X, 3, PS_NQ>(ps_in, gp, x);
     Stencil s0;
-    make_stencil(x, k.inv_dx, s0);
+    make_stencil(x0, k.inv_dx, s0);
+    __syncwarp();   // every lane is done with the previous tile's node tile
     tiled = warp_tile_fill<false>(k, ggrid + (size_t)env * k.G, s0.base, live_, wtile[threadIdx.x >> 5], &tile_gid);
   }
   const float4* my_tile = wtile[threadIdx.x >> 5] + tile_gid * 32;
@@ -1425,26 +1657,30 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     // u(a,b,c) = p_mass v + A dpos = u0 + a Ax + b Ay + c Az,  A* = dx * columns of affine (phase 1)
     float S[3] = {0.f, 0.f, 0.f}, TX[3] = {0.f, 0.f, 0.f}, TY[3] = {0.f, 0.f, 0.f}, TZ[3] = {0.f, 0.f, 0.f};
     float gfx[3] = {0.f, 0.f, 0.f};
+    auto gather = [&](auto tiled_tag) {
+    constexpr bool TILED = decltype(tiled_tag)::value;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const int ix = idx_scatter(st.base[0] + a, k.rx);
+      const int ix = TILED ? 0 : idx_scatter(st.base[0] + a, k.rx);
       float ua[3] = {u0[0] + (float)a * Ac[0][0], u0[1] + (float)a * Ac[0][1], u0[2] + (float)a * Ac[0][2]};
       float Sa[3] = {0.f, 0.f, 0.f}, Ya[3] = {0.f, 0.f, 0.f}, Za[3] = {0.f, 0.f, 0.f};
       float P1 = 0.f, P2 = 0.f, Q1 = 0.f;
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
-        const int iy = idx_scatter(st.base[1] + b, k.ry);
+        const int iy = TILED ? 0 : idx_scatter(st.base[1] + b, k.ry);
         const float wab = st.w[a][0] * st.w[b][1];
         float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
         float Sab[3] = {0.f, 0.f, 0.f}, Zab[3] = {0.f, 0.f, 0.f};
         float P = 0.f, Q = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const int iz = idx_scatter(st.base[2] + c, k.rz);
-          const bool ok = (ix | iy | iz) >= 0;
           float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);  // (g_momentum, g_mass); dropped node -> 0
-          if (tiled) gq = my_tile[a * 9 + b * 3 + c];
-          else if (ok) gq = __ldg(&ggenv[(ix * k.ry + iy) * k.rz + iz]);
+          if (TILED) {
+            gq = my_tile[a * 9 + b * 3 + c];
+          } else {
+            const int iz = idx_scatter(st.base[2] + c, k.rz);
+            if ((ix | iy | iz) >= 0) gq = __ldg(&ggenv[(ix * k.ry + iy) * k.rz + iz]);
+          }
           const float wt = wab * st.w[c][2];
           const float q[3] = {wt * gq.x, wt * gq.y, wt * gq.z};
           const float u[3] = {uab[0] + (float)c * Ac[2][0], uab[1] + (float)c * Ac[2][1], uab[2] + (float)c * Ac[2][2]};
@@ -1478,6 +1714,9 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
       gfx[1] += P2 * st.w[a][0];
       gfx[2] += Q1 * st.w[a][0];
     }
+    };
+    if (tiled) gather(std::true_type{});
+    else gather(std::false_type{});
     Mat3 gA;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -1488,7 +1727,8 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     // dpos = (off - fx) dx: direct fx path, gfx_j -= dx (A^T S)_j = Ac[j] . S
 #pragma unroll
     for (int j = 0; j < 3; ++j) gfx[j] -= Ac[j][0] * S[0] + Ac[j][1] * S[1] + Ac[j][2] * S[2];
-    // Phase 2: reload (ld.global.cg so that the compiler cannot keep the phase-1 registers alive) and reverse
+    // Phase 2: reload (volatile ld.global.ca: the compiler cannot keep the phase-1 registers alive, and the lines are
+    // still in L1 from phase 1 -- the round-1 ld.cg reload went to L2 and held 10 % of the kernel's stall samples)
     Mat3 C, F, gF2out, gC, gF;
     Consti o;
     float gx_in[3];
@@ -1562,13 +1802,14 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     atomicAdd(&g_scal[env * GS_STRIDE + GS_LAMDA], gla);
     if (norm2) atomicAdd(&norm2[env * 2], gn2);
   }
+  }  // tiles of this warp
 }
 
 void launch_p2g_bwd(const MpmConst& k, const float* ps_in, const float* svd_in, const float* mu_s,
                     const float* la_s, bool first_substep, const MpmWs& ws, cudaStream_t st) {
   KScope ks_(KC_P2G_BWD, st);
   if (first_substep) cudaMemsetAsync(ws.norm2, 0, 4 * (size_t)k.B * 2, st);
-  k_p2g_bwd<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, svd_in, ws.ggrid, ws.gs, mu_s, la_s, ws.mat_s,
+  k_p2g_bwd<<<persistent_ctas(k, UD_BLOCK / 32, 4), UD_BLOCK, 0, st>>>(k, ps_in, svd_in, ws.ggrid, ws.gs, mu_s, la_s, ws.mat_s,
                                                      ws.h_s, ws.g_scal, first_substep ? ws.norm2 : nullptr);
 }
 
