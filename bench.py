@@ -2,6 +2,13 @@
 """Benchmark of the DaXBench simulator step on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config push_plasticine|pour_water|whip_rope|cloth_para] [--ckpt-window K]
+
+The default (what the driver runs) is BASELINE configs[1]; --config selects the other BASELINE configs with the same
+JSON line: pour_water (configs[2]: 99 998 liquid particles/env, two bowl colliders, 16 envs/GPU = 128 over 8),
+whip_rope (configs[4]: 49 329 elastic particles/env, S = 70 substeps per step, adjoint with K-spaced substep
+checkpoints, peak HBM reported), cloth_para (configs[3]: fold_cloth1_para, 128 envs/GPU = 1024 over 8, one env step
+fwd+bwd + the policy-gradient all-reduce + Adam).
 
 Workload (config.workload): BASELINE configs[1] "push_plasticine" = the reference's
 envs/shape_elasto_plastic.py scene scaled to 50 625 particles/env (add_box density 3.9),
@@ -56,6 +63,132 @@ def build_scene(sim, density):
     state.primitives.append(create_primitive(conf, friction=0.1, softness=666, color=[0.5, 0.5, 0.5],
                                              size=[0.015, 0.06, 0.015], init_pos=[0.25, 0.01, 0.20]))
     return sim.reset_jax(state)
+
+
+def build_pour_water(sim):
+    """BASELINE configs[2]: pour_water scaled to ~100 k liquid particles per env (envs/pour_water_env.py:92-123 scene:
+    a liquid box and two bowls with the container SDF)."""
+    from unidom_b200.mpm_simulator import create_primitive
+    conf = sim.conf
+    st = sim.add_box(conf=conf, state=None, hardness=1, size=[0.3655] * 3, init_pos=[0.4, 0.3, 0.4], material=0, density=4)
+    st.primitives.append(create_primitive(conf, 0.1, 666, [0.5] * 3, [0.35, 0.0, 0.02], [0.4, 0.3, 0.4]))
+    st.primitives.append(create_primitive(conf, 0.1, 666, [0.5] * 3, [0.3, 0.0, 0.02], [0.4, 0.08, 0.2]))
+    st = st._replace(primitives=[p._replace(action_scale=p.action_scale * 0.01) for p in st.primitives])
+    return sim.reset_jax(st)
+
+
+def build_whip_rope(sim):
+    """BASELINE configs[4]: whip_rope at add_box density 25 (49 329 elastic particles), position-controlled gripper,
+    S = 70 substeps per step (envs/whip_rope_env.py:27-73)."""
+    from unidom_b200.mpm_simulator import create_primitive
+    conf = sim.conf
+    st = sim.add_box(conf=conf, state=None, hardness=1.0, size=[0.15, 0.005, 0.005], init_pos=[0.25, 0.05, 0.25],
+                     material=1, density=25)
+    st.primitives.append(create_primitive(conf, 0.1, 666, [0.5] * 3, [0.02, 0.02, 0.02], [0.25, 0.05, 0.15]))
+    st = st._replace(primitives=[p._replace(action_scale=p.action_scale * 0.02) for p in st.primitives])
+    return sim.reset_jax(st)
+
+
+def make_workload(args, dev, rank):
+    """-> (sim, state, action, description) of the selected BASELINE config."""
+    from unidom_b200 import _lib, confs
+    from unidom_b200.mpm_simulator import SimpleMPMSimulator
+    g = torch.Generator().manual_seed(1234 + rank)
+    if args.config == "push_plasticine":
+        conf = confs.shape_elasto_plastic_conf()
+        sim = SimpleMPMSimulator(conf, args.envs, device=dev, p2g_mode=args.p2g_mode, adjoint=args.adjoint,
+                                 ckpt_window=args.ckpt_window)
+        state = build_scene(sim, args.density)
+        B = state.x.shape[0]
+        action = (torch.tensor([0.003, 0.0, 0.004, 0.0, 0.0, 0.0]) + 5e-4 * torch.randn((B, 6), generator=g)).to(dev)
+        action[:, 3:] = 0
+        name = workload_name(state.x.shape[1], B)
+    elif args.config == "pour_water":
+        conf = confs.pour_water_conf(res=(64, 48, 64))
+        B = args.envs if args.envs != ENVS_PER_GPU else 16
+        sim = SimpleMPMSimulator(conf, B, device=dev, sdf_kind=_lib.UD_SDF_CONTAINER, p2g_mode=args.p2g_mode,
+                                 adjoint=args.adjoint, ckpt_window=args.ckpt_window)
+        state = build_pour_water(sim)
+        action = torch.zeros((B, 12), device=dev)
+        action[:, 0], action[:, 5] = 0.3, 0.2
+        action += (2e-2 * torch.randn((B, 12), generator=g)).to(dev)
+        name = (f"pour_water MLS-MPM liquid fwd+bwd, {state.x.shape[1]} particles/env, num_envs={B}/GPU, "
+                f"res={tuple(conf.res)}, {conf.steps} substeps/step, two container colliders")
+    elif args.config == "whip_rope":
+        conf = confs.whip_rope_conf()
+        B = args.envs if args.envs != ENVS_PER_GPU else 8
+        sim = SimpleMPMSimulator(conf, B, use_position_control=True, device=dev, p2g_mode=args.p2g_mode,
+                                 adjoint=args.adjoint, ckpt_window=args.ckpt_window if args.ckpt_window else 10)
+        state = build_whip_rope(sim)
+        action = torch.zeros((B, 6), device=dev)
+        action[:, 1] = 0.5
+        action += (2e-2 * torch.randn((B, 6), generator=g)).to(dev)
+        name = (f"whip_rope MLS-MPM elastic fwd+bwd, {state.x.shape[1]} particles/env, num_envs={B}/GPU, "
+                f"res={tuple(conf.res)}, {conf.steps} substeps/step, position control, "
+                f"substep checkpoints every {sim.ckpt_window}")
+    else:
+        raise ValueError(args.config)
+    return sim, state, action, name
+
+
+def bind_to_local_numa(local_rank):
+    """Pin this rank's host threads (and therefore the first-touch placement of its pinned buffers) to the CPUs NVML
+    reports as local to its GPU.  Returns a description for the bench line."""
+    info = {"cpus": None, "numa_nodes": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = f"{cpus[0]}-{cpus[-1]} ({len(cpus)})"
+    except Exception as e:      # noqa: BLE001 -- affinity is an optimisation, never a requirement
+        info["error"] = repr(e)[:80]
+    try:
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        info["numa_nodes"] = len(nodes)
+    except Exception:
+        pass
+    return info
+
+
+def apg_update_leg(dev, dist, world, iters=20):
+    """The path's one collective (algorithms/apg/apg.py:233-240, 260-267) on the policy gradient of the 512-256 MLP
+    (925 964 fp32): ud_apg_scrub_clip -> all-reduce -> ud_adam_step, timed on the device inside the region."""
+    from unidom_b200 import apg
+    n = 925964
+    g = torch.Generator().manual_seed(7)
+    grad = (torch.randn(n, generator=g) * 1e-3).to(dev)
+    params = torch.randn(n, generator=g).to(dev)
+    opt = apg.Adam(n, 1e-4, dev)
+    out = {}
+    for label, fused in (("nccl", False), ("fused", True)):
+        if fused and not apg.fused_update_available(dev):
+            continue
+        upd = apg.FusedUpdate(n, 1e-4, dev) if fused else None
+        p = params.clone()
+        for _ in range(3):
+            p = upd.step(p, grad, 0.3) if fused else opt.step(p, apg.reduce_policy_gradient(grad, 0.3)[0])
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            p = upd.step(p, grad, 0.3) if fused else opt.step(p, apg.reduce_policy_gradient(grad, 0.3)[0])
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / iters * 1e3], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[label + "_us"] = float(t.item())
+    out.update({"elements": n, "bytes_reduced_per_rank": 4 * n, "ranks": world,
+                "what": "scrub + per-rank global-norm clip -> mean over ranks -> Adam, per update, max over ranks"})
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -205,9 +338,70 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_name(n):
+def run_cloth_para(args, dev, dist, rank, world):
+    """BASELINE configs[3]: fold_cloth1_para parameter-aware APG (GenDOM), 128 envs per GPU (= 1024 over 8).  A "step"
+    is one APG training iteration with ep_len 1 on this rank's env shard: policy MLP, FoldCloth1ParaEnv.step_diff
+    (40 pick-and-place sub-actions x 50 substeps, ONE fused forward launch + adjoint), policy gradient, per-rank
+    scrub/clip, mean over ranks (the path's one collective), Adam.  Stiffness: one draw per iteration
+    (apg_para.py:326-329).  value = cloth node-substeps/s over all ranks."""
+    import numpy as np
+    from unidom_b200 import apg, envs
+    per = args.envs if args.envs != ENVS_PER_GPU else 128
+    goal = np.zeros((1, 3), np.float32)
+    env = envs.FoldCloth1ParaEnv(per, aux_reward=True, seed=0, stiffness=apg.para_stiffness(0, 200, 1800), goal=goal,
+                                 device=dev, eval_min_max_stiff=[100, 2000])
+    params = apg.init_policy(env.observation_size, env.action_size, seed=0, device=dev)
+    n_par = sum(p.numel() for p in params)
+    opt = apg.Adam(n_par, 1e-4, dev)
+    g = torch.Generator().manual_seed(1 + rank)
+    _, state = env.reset()
+    eps = torch.randn((1, per, env.action_size), generator=g).to(dev)
+    nodes = state.x.shape[1]
+    units = per * nodes * 40 * 50
+
+    def it():
+        nonlocal params
+        params, m = apg.train_iteration(env, params, opt, state, eps, 0.3)
+        return m
+    for _ in range(max(args.warmup, 3)):
+        it()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        m = it()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    apg_leg = apg_update_leg(dev, dist, world) if dist is not None else None
+    if rank == 0:
+        print(json.dumps({
+            "metric": "node-substeps/s fwd+bwd", "value": world * units * args.steps / (ms * 1e-3), "unit": "node-substeps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"fold_cloth1_para parameter-aware APG iteration (ep_len 1), {per} envs/GPU, {nodes} nodes, "
+                                   "40 sub-actions x 50 substeps per env step, policy 1545-512-256-16",
+                       "envs_per_gpu": per, "policy_parameters": n_par,
+                       "collective": "policy-gradient mean over ranks (one all-reduce per iteration)" if world > 1 else "none (1 GPU)"},
+            "loss": m["loss"], "grad_norm": m["grad_norm"], "apg_update": apg_leg, "clocks": clocks}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def workload_name(n, envs=ENVS_PER_GPU):
     return (f"push_plasticine = shape_elasto_plastic MLS-MPM fwd+bwd, {n} particles/env, "
-            f"num_envs={ENVS_PER_GPU}/GPU, res=(48,32,48), 16 substeps/step")
+            f"num_envs={envs}/GPU, res=(48,32,48), 16 substeps/step")
 
 
 def main():
@@ -227,6 +421,10 @@ def main():
                          "next to the headline as `taped`)")
     ap.add_argument("--settle", type=int, default=8, help="env steps run before timing to reach a mid-push state")
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer leg")
+    ap.add_argument("--config", default="push_plasticine", choices=["push_plasticine", "pour_water", "whip_rope", "cloth_para"],
+                    help="BASELINE.json config to time (the driver's line is the default)")
+    ap.add_argument("--ckpt-window", type=int, default=None,
+                    help="K-spaced substep checkpoints inside the recompute adjoint (default: none; whip_rope: 10)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -236,25 +434,23 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_local_numa(local_rank)          # before any pinned allocation: first touch places the pages
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    from unidom_b200 import _lib, confs
-    from unidom_b200.mpm_simulator import SimpleMPMSimulator
+    from unidom_b200 import _lib
     L = _lib.lib()
     for kv in filter(None, args.tune.split(",")):
         name, val = kv.split("=")
         assert L.ud_tuning_set(name.encode(), int(val)) >= 0, kv
-    conf = confs.shape_elasto_plastic_conf()
-    sim = SimpleMPMSimulator(conf, args.envs, device=dev, p2g_mode=args.p2g_mode, adjoint=args.adjoint)
-    state = build_scene(sim, args.density)
+    if args.config == "cloth_para":
+        return run_cloth_para(args, dev, dist, rank, world)
+    sim, state, action, wl_name = make_workload(args, dev, rank)
+    conf = sim.conf
     B, n = state.x.shape[:2]
     S = conf.steps
-    g = torch.Generator().manual_seed(1234 + rank)
-    action = (torch.tensor([0.003, 0.0, 0.004, 0.0, 0.0, 0.0]) + 5e-4 * torch.randn((B, 6), generator=g)).to(dev)
-    action[:, 3:] = 0
     cot = make_cotangents(state, 99 + rank)
     units_per_step = B * n * S
 
@@ -274,6 +470,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         out, grads, _ = fwd_bwd(sim, state, action, cot)
     barrier()
+    torch.cuda.reset_peak_memory_stats(dev)
     sampler = ClockSampler(local_rank)
     sampler.start()
     L.ud_launch_count(1)
@@ -285,6 +482,7 @@ def main():
     barrier()
     launches = int(L.ud_launch_count(0))
     clocks = sampler.stop()
+    peak_hbm = int(torch.cuda.max_memory_allocated(dev))
     ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([ms], device=dev)
@@ -367,47 +565,57 @@ def main():
                 "step_frac_fwd": (fwd_value / world) * ALG_BYTES_FWD / 1e9 / peak}
 
     # ---------------- end-to-end with host buffers (pinned), copies inside the timed region
+    # ONE flat pinned buffer and ONE cudaMemcpyAsync per direction and step (round 1 issued sixteen copies per step
+    # and rank, and the 8-GPU e2e number collapsed to half the device rate).
     names = ("x", "v", "C", "F", "J")
-    host_in = {k: getattr(state, k).detach().cpu().pin_memory() for k in names}
-    host_act = action.detach().cpu().pin_memory()
-    host_out = {k: torch.empty_like(host_in[k]).pin_memory() for k in names}
-    host_g = {k: torch.empty_like(host_in[k]).pin_memory() for k in ("x", "v", "C", "F")}
-    host_ga = torch.empty_like(host_act).pin_memory()
-    h2d = sum(t.numel() * 4 for t in host_in.values()) + host_act.numel() * 4
-    d2h = sum(t.numel() * 4 for t in host_out.values()) + sum(t.numel() * 4 for t in host_g.values()) \
-        + host_ga.numel() * 4
+    in_shapes = [tuple(getattr(state, k).shape) for k in names] + [tuple(action.shape)]
+    out_shapes = [tuple(getattr(state, k).shape) for k in names] + \
+                 [tuple(getattr(state, k).shape) for k in ("x", "v", "C", "F")] + [tuple(action.shape)]
+
+    def numel(sh):
+        r = 1
+        for d in sh:
+            r *= d
+        return r
+
+    def views(flat, shapes):
+        out, o = [], 0
+        for sh in shapes:
+            out.append(flat[o:o + numel(sh)].view(sh))
+            o += numel(sh)
+        return out
+    n_in, n_out = sum(numel(sh) for sh in in_shapes), sum(numel(sh) for sh in out_shapes)
+    host_in = torch.empty(n_in, dtype=torch.float32).pin_memory()
+    host_out = torch.empty(n_out, dtype=torch.float32).pin_memory()
+    for v_, src in zip(views(host_in, in_shapes), [getattr(state, k) for k in names] + [action]):
+        v_.copy_(src.detach().cpu())
+    h2d, d2h = 4 * n_in, 4 * n_out
 
     # Three streams, double-buffered device inputs: the H2D of step i+1 and the D2H of step i-1 overlap the kernels
     # of step i (all copies stay inside the timed region; PCIe is full duplex).
     s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     s_comp = torch.cuda.current_stream(dev)
-    dev_in = [{k: torch.empty_like(getattr(state, k)) for k in names} for _ in range(2)]
-    dev_act = [torch.empty_like(action) for _ in range(2)]
+    dev_in = [torch.empty(n_in, dtype=torch.float32, device=dev) for _ in range(2)]
+    dev_out = [torch.empty(n_out, dtype=torch.float32, device=dev) for _ in range(2)]
     ev_h2d = [torch.cuda.Event() for _ in range(2)]
     ev_comp = [torch.cuda.Event() for _ in range(2)]
     ev_d2h = [torch.cuda.Event() for _ in range(2)]
-    keep = [None, None]          # outputs of a slot stay referenced until their D2H has completed
 
     def e2e_step(i):
         slot = i % 2
         with torch.cuda.stream(s_h2d):
             s_h2d.wait_event(ev_comp[slot])          # the step that last read this slot has finished
-            for k in names:
-                dev_in[slot][k].copy_(host_in[k], non_blocking=True)
-            dev_act[slot].copy_(host_act, non_blocking=True)
+            dev_in[slot].copy_(host_in, non_blocking=True)
             ev_h2d[slot].record(s_h2d)
         s_comp.wait_event(ev_h2d[slot])
-        ev_d2h[slot].synchronize()                   # slot's previous outputs are on the host: safe to drop them
-        o, gr, _ = fwd_bwd(sim, state._replace(**dev_in[slot]), dev_act[slot], cot)
+        s_comp.wait_event(ev_d2h[slot])              # the slot's previous outputs have left the device
+        vin = views(dev_in[slot], in_shapes)
+        o, gr, _ = fwd_bwd(sim, state._replace(**dict(zip(names, vin[:5]))), vin[5], cot)
+        torch.cat([getattr(o, k).detach().reshape(-1) for k in names] + [t.reshape(-1) for t in gr], out=dev_out[slot])
         ev_comp[slot].record(s_comp)
-        keep[slot] = (o, gr)
         with torch.cuda.stream(s_d2h):
             s_d2h.wait_event(ev_comp[slot])
-            for k in names:
-                host_out[k].copy_(getattr(o, k).detach(), non_blocking=True)
-            for k, t in zip(("x", "v", "C", "F"), gr[:4]):
-                host_g[k].copy_(t, non_blocking=True)
-            host_ga.copy_(gr[4], non_blocking=True)
+            host_out.copy_(dev_out[slot], non_blocking=True)
             ev_d2h[slot].record(s_d2h)
 
     for i in range(0 if args.no_e2e else 2):
@@ -428,6 +636,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = world * units_per_step * args.steps / (e2e_ms * 1e-3)
+    del dev_in, dev_out
+
+    # ---------------- the path's one collective, timed in the same run (N > 1)
+    apg_leg = apg_update_leg(dev, dist, world) if dist is not None else None
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
@@ -443,19 +655,24 @@ def main():
             "metric": "particle-substeps/s fwd+bwd", "value": value, "unit": "particle-substeps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(n), "state": f"every step starts from the scene after {args.settle} settle steps", "envs_per_gpu": B, "particles_per_env": n, "substeps": S,
+            "config": {"workload": wl_name, "state": f"every step starts from the scene after {args.settle} settle steps", "envs_per_gpu": B, "particles_per_env": n, "substeps": S,
                        "l2": f"inputs larger than L2 (state+checkpoints {B * n * 96 * (S + 1) / 1e9:.2f} GB per step)",
                        "adjoint": f"{args.adjoint}: " + ("substep residuals kept in HBM by the forward ("
                                    f"{L.ud_mpm_tape_bytes(C.byref(sim.params())) / 1e9:.2f} GB per step in flight)"
                                    if args.adjoint != "recompute" else
                                    "step input kept, the S substeps recomputed in the backward"),
                        "p2g_mode": "atomic" if args.p2g_mode == 0 else "deterministic",
-                       "collective": "none in the step (envs are independent; APG's policy-gradient all-reduce "
-                                     "is outside this path)"},
+                       "ckpt_window": sim.ckpt_window,
+                       "collective": "none in the step (envs are independent); APG's policy-gradient all-reduce is "
+                                     "timed beside it as `apg_update` when N > 1"},
             "forward_only": {"value": fwd_value, "unit": "particle-substeps/s"},
             "taped": taped,
             "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "copies_per_step": 2, "host_gbs_per_rank": (h2d + d2h) / (e2e_ms / args.steps * 1e-3) / 1e9,
+                    "host_gbs_all_ranks": world * (h2d + d2h) / (e2e_ms / args.steps * 1e-3) / 1e9, "numa": numa},
+            "apg_update": apg_leg,
+            "peak_hbm_bytes": peak_hbm,
             "gpu_launches": launches,
             "roofline": roofline,
             "kernels": {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()}

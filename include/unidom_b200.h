@@ -241,6 +241,19 @@ int ud_apg_scrub_clip(float* grad, int64_t n, float max_grad_norm, float* sumsq,
 int ud_adam_step(float* params, const float* grad, float* m, float* v, int64_t n, int32_t world_size, double lr,
                  double b1, double b2, double eps, int32_t t, void* stream);
 
+/* The same update as ONE kernel per rank, the collective included ("fused clip + all-reduce + Adam"): scrub,
+ * per-rank global-norm clip, mean over the ranks, optax.adam -- identical arithmetic and order of operations to
+ * ud_apg_scrub_clip -> all-reduce(sum) -> ud_adam_step(world_size).  The ranks exchange the clipped gradient through
+ * peer-mapped device memory (NVLink): peer_stage[r] / peer_flags[r] are DEVICE arrays of `world` device pointers, one
+ * per rank, to that rank's staging buffer (float[2 * n]) and flag array (int32[>= world], zeroed once before the first
+ * call), valid in the calling process (cudaIpc / cuMem fabric handles / torch symmetric memory -- obtaining the mapping
+ * is the caller's business).  t = 1, 2, ... must advance by one per call on every rank.  scratch: 8 floats.
+ * Every rank sums the staged gradients in rank order, so replicas stay bit-identical.  world == 1 degenerates to
+ * scrub + clip + Adam in one launch. */
+int ud_apg_fused_update(float* params, const float* grad, float* m, float* v, int64_t n, float max_grad_norm,
+                        double lr, double b1, double b2, double eps, int32_t t, int32_t rank, int32_t world,
+                        const uint64_t* peer_stage, const uint64_t* peer_flags, float* scratch, void* stream);
+
 /* ---- instrumentation (bench.py): launch counting and per-kernel-class CUDA-event timing ------
  * ud_launch_count: kernels + memsets enqueued by this library since the last reset (host counter).
  * ud_timing_enable(1): subsequent calls bracket every kernel class with cudaEvents on the call's

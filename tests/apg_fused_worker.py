@@ -1,0 +1,44 @@
+"""Worker of tests/test_apg_gpu.py::test_fused_update_two_ranks_over_peer_memory (one process per GPU, torchrun)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from unidom_b200 import apg  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    assert apg.fused_update_available(dev), "symmetric memory / fused kernel unavailable"
+    n = 925964
+    g = torch.Generator().manual_seed(11)
+    params = torch.randn(n, generator=g).to(dev)                       # replicated
+    opt = apg.Adam(n, 1e-3, dev)
+    upd = apg.FusedUpdate(n, 1e-3, dev)
+    p_ref, p_fused = params.clone(), params.clone()
+    for t in range(1, 6):
+        gt = (torch.randn(n, generator=torch.Generator().manual_seed(100 * t + rank)) * (1e-3 if t < 4 else 1.0)).to(dev)
+        red, _ = apg.reduce_policy_gradient(gt, 0.3)
+        p_ref = opt.step(p_ref, red)
+        p_fused = upd.step(p_fused, gt, 0.3)
+        torch.cuda.synchronize()
+        err = float((p_fused - p_ref).abs().max())
+        other = p_fused.clone()
+        dist.broadcast(other, 0)
+        same = bool(torch.equal(other, p_fused))
+        print(f"[rank {rank}] t={t}: fused vs NCCL path max |dp| {err:.3e}; replica bit-identical to rank 0: {same}", flush=True)
+        assert same, "replicas diverged"
+        assert err <= 5e-7 * float(p_ref.abs().max()), err
+    dist.barrier()
+    if rank == 0:
+        print("fused update ok")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

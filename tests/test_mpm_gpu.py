@@ -345,3 +345,44 @@ def test_cuda_graph_replay_of_the_forward_scan(built_lib):
         for k in ("x", "v", "C", "F", "J"):
             assert torch.equal(getattr(out, k), getattr(ref, k)), (trial, k)
         assert torch.equal(out.primitives[0].position, ref.primitives[0].position)
+
+
+@pytest.mark.parametrize("window", [1, 3, 4, 8])
+def test_windowed_adjoint_matches_full_recompute(built_lib, window):
+    """ud_mpm_step_bwd_windowed (K-spaced substep checkpoints inside the step, north_star (e)) against ud_mpm_step_bwd:
+    the same kernels on the same data -- with deterministic P2G the recomputed trajectory is bit-identical, so the
+    gradients differ only by the order of the fp32 REDs of G2P^T (floor: a second full-recompute run).  K = 3 does
+    not divide S = 10 (ragged last window); K = 1 keeps every substep as a checkpoint; the workspace shrinks with K."""
+    from unidom_b200 import _lib
+    import ctypes as C
+    conf = _conf(steps=10, n_primitive=1)
+    B = 2
+    sims = {m: _sim(conf, B, p2g_mode=_lib.UD_P2G_DETERMINISTIC, ckpt_window=w)
+            for m, w in (("full", None), ("full2", None), ("win", window))}
+    st = util.mini_plasticine(sims["full"], B, seed=15, density=2.0)
+    for m in ("full2", "win"):
+        sims[m].material, sims[m].h, sims[m].n_particles = sims["full"].material, sims["full"].h, sims["full"].n_particles
+        sims[m]._material_dev, sims[m]._h_dev = sims["full"]._material_dev, sims["full"]._h_dev
+    act = (_actions(B, 1, seed=16) * 0.8).to(st.x.device)
+    g = torch.Generator().manual_seed(19)
+    n = st.x.shape[1]
+    cot = {"x": torch.randn((B, n, 3), generator=g) * 1e-3, "v": torch.randn((B, n, 3), generator=g) * 1e-4,
+           "C": torch.randn((B, n, 3, 3), generator=g) * 1e-6, "F": torch.randn((B, n, 3, 3), generator=g) * 1e-4,
+           "p0.position": torch.randn((B, 10, 3), generator=g) * 1e-3, "p0.rotation": torch.zeros((B, 10, 4))}
+    res = {m: _run_grad(lambda s, a, sim=sim: sim.step_jax(s, a)[0], st, act, cot, 1, lambda t: t.to(st.x.device))
+           for m, sim in sims.items()}
+    for k in res["full"]:
+        ref = res["full"][k]
+        if float(ref.abs().max()) == 0.0:
+            assert float(res["win"][k].abs().max()) == 0.0, k
+            continue
+        floor = util.rel_err(res["full2"][k], ref)
+        e = util.rel_err(res["win"][k], ref)
+        print(f"windowed K={window} grad {k:12s}: rel {e:.3e}  floor (two full-recompute runs) {floor:.3e}")
+        assert e <= max(1e-5, 20 * floor) and util.cosine(res["win"][k], ref) > 0.999999, (k, e, floor)
+    p = sims["win"].params(B=B, n=n)
+    full_b = sims["win"]._L.ud_mpm_bwd_workspace_bytes(C.byref(p))
+    win_b = sims["win"]._L.ud_mpm_bwd_windowed_workspace_bytes(C.byref(p), window)
+    print(f"windowed K={window}: workspace {win_b / 1e6:.2f} MB vs {full_b / 1e6:.2f} MB store-all-substeps")
+    if window <= 4:
+        assert win_b < full_b

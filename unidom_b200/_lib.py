@@ -84,6 +84,11 @@ def lib():
     L.ud_mpm_step_bwd.restype = C.c_int
     L.ud_mpm_step_bwd.argtypes = [P(MpmParams), P(MpmState), _fp, _fp, _fp, P(MpmState), P(MpmState), _fp,
                                   _fp, C.c_size_t, _fp]
+    L.ud_mpm_bwd_windowed_workspace_bytes.restype = C.c_size_t
+    L.ud_mpm_bwd_windowed_workspace_bytes.argtypes = [P(MpmParams), C.c_int32]
+    L.ud_mpm_step_bwd_windowed.restype = C.c_int
+    L.ud_mpm_step_bwd_windowed.argtypes = [P(MpmParams), P(MpmState), _fp, _fp, _fp, P(MpmState), P(MpmState), _fp,
+                                           C.c_int32, _fp, C.c_size_t, _fp]
     L.ud_mpm_tape_bytes.restype = C.c_size_t
     L.ud_mpm_tape_bytes.argtypes = [P(MpmParams)]
     L.ud_mpm_step_fwd_taped.restype = C.c_int
@@ -107,6 +112,9 @@ def lib():
     L.ud_adam_step.restype = C.c_int
     L.ud_adam_step.argtypes = [_fp, _fp, _fp, _fp, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
                                C.c_int32, _fp]
+    L.ud_apg_fused_update.restype = C.c_int
+    L.ud_apg_fused_update.argtypes = [_fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_double, C.c_double, C.c_double, C.c_double,
+                                      C.c_int32, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp]
     L.ud_mpm_sort_bins.restype = C.c_int
     L.ud_mpm_sort_bins.argtypes = [P(MpmParams), _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]
     if hasattr(L, "ud_cloth_step_fwd"):
@@ -137,11 +145,12 @@ def lib():
 
 EXPORTS = (
     "ud_version", "ud_last_error", "ud_mpm_fwd_workspace_bytes", "ud_mpm_bwd_workspace_bytes",
-    "ud_mpm_step_fwd", "ud_mpm_step_bwd", "ud_mpm_tape_bytes", "ud_mpm_step_fwd_taped", "ud_mpm_step_bwd_taped",
+    "ud_mpm_step_fwd", "ud_mpm_step_bwd", "ud_mpm_bwd_windowed_workspace_bytes", "ud_mpm_step_bwd_windowed",
+    "ud_mpm_tape_bytes", "ud_mpm_step_fwd_taped", "ud_mpm_step_bwd_taped",
     "ud_mpm_sort_bins", "ud_mpm_num_keys",
     "ud_cloth_workspace_bytes", "ud_cloth_step_fwd", "ud_cloth_step_bwd", "ud_cloth_multi_ckpt_bytes",
     "ud_cloth_multi_workspace_bytes", "ud_cloth_multi_step_fwd", "ud_cloth_multi_step_bwd",
-    "ud_chamfer_residual_bytes", "ud_chamfer_fwd", "ud_chamfer_bwd", "ud_l2_fwd", "ud_l2_bwd", "ud_apg_scrub_clip", "ud_adam_step",
+    "ud_chamfer_residual_bytes", "ud_chamfer_fwd", "ud_chamfer_bwd", "ud_l2_fwd", "ud_l2_bwd", "ud_apg_scrub_clip", "ud_adam_step", "ud_apg_fused_update",
     "ud_launch_count", "ud_timing_enable", "ud_timing_collect", "ud_tuning_set",
 )
 

@@ -137,6 +137,69 @@ class Adam:
         return flat_params - self.lr * mhat / (torch.sqrt(vhat) + self.eps)
 
 
+def fused_update_available(device) -> bool:
+    """The one-kernel update needs every rank's gradient buffer mapped into every peer (torch symmetric memory over
+    NVLink) -- NCCL process group with more than one rank on one node."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return False
+    if dist.get_backend() != "nccl" or not torch.device(device).type == "cuda":
+        return False
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401
+    except Exception:
+        return False
+    return hasattr(__import__("unidom_b200._lib", fromlist=["lib"]).lib(), "ud_apg_fused_update")
+
+
+class FusedUpdate:
+    """scrub + per-rank clip -> mean over ranks -> Adam as ONE kernel per rank (csrc/apg_fused.cu): every rank stages its
+    clipped gradient in a peer-mapped buffer, the ranks meet at a flag barrier in peer memory, and every rank then
+    reads all N staged gradients over NVLink in rank order (so the replicas stay bit-identical), divides by N and
+    applies Adam to its replica.  Same arithmetic, same order of operations as reduce_policy_gradient + Adam.step."""
+
+    def __init__(self, n: int, lr: float, device, group=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        self.n, self.lr, self.b1, self.b2, self.eps = n, lr, 0.9, 0.999, 1e-8
+        self.device = torch.device(device)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.m = torch.zeros(n, device=device)
+        self.v = torch.zeros(n, device=device)
+        self.t = 0
+        self._L = _lib.lib()
+        # two staging slots (iteration parity): a rank may start staging iteration t+1 while a peer still reads t
+        self.stage = symm_mem.empty(2 * n, dtype=torch.float32, device=self.device)
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=self.device)
+        self.flags.zero_()
+        h_stage = symm_mem.rendezvous(self.stage, self.group.group_name)
+        h_flags = symm_mem.rendezvous(self.flags, self.group.group_name)
+        self._keep = (h_stage, h_flags)
+        self.peer_stage = torch.tensor([int(p) for p in h_stage.buffer_ptrs], dtype=torch.int64, device=self.device)
+        self.peer_flags = torch.tensor([int(p) for p in h_flags.buffer_ptrs], dtype=torch.int64, device=self.device)
+        self.scratch = torch.zeros(8, dtype=torch.float32, device=self.device)
+        dist.barrier(self.group)
+        torch.cuda.synchronize(self.device)
+        self._C = C
+
+    def step(self, flat_params: torch.Tensor, flat_grad: torch.Tensor, max_grad_norm: float) -> torch.Tensor:
+        C = self._C
+        self.t += 1
+        p = flat_params.detach().to(torch.float32).contiguous().clone()
+        g = flat_grad.detach().to(torch.float32).contiguous()
+        ptr = lambda t: C.c_void_p(t.data_ptr())       # noqa: E731
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        from . import _lib
+        _lib.check(self._L.ud_apg_fused_update(ptr(p), ptr(g), ptr(self.m), ptr(self.v), self.n, float(max_grad_norm),
+                                               self.lr, self.b1, self.b2, self.eps, self.t, self.rank, self.world,
+                                               ptr(self.peer_stage), ptr(self.peer_flags), ptr(self.scratch), st),
+                   "ud_apg_fused_update")
+        return p
+
+
 def train_iteration(env, params, opt: Adam, state, eps, max_grad_norm: float, sigmoid: bool = True, group=None):
     """One `minimize` call (apg.py:217-258) on this rank's env shard.  Returns (new params, metrics)."""
     req = [p.detach().clone().requires_grad_(True) for p in params]

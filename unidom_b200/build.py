@@ -21,6 +21,7 @@ UNITS = [
     ("mpm_grid.cu", ["--fmad=false"]),
     ("cloth.cu", []),
     ("reward.cu", []),
+    ("apg_fused.cu", []),
 ]
 
 
@@ -82,7 +83,37 @@ def _build(LIB, tag, defines, verbose):
     return LIB
 
 
+def build_xla_adapter(verbose=False):
+    """csrc/xla_ffi.cc -> libunidom_b200_xla.so (the jax.ffi handlers) against jax's own XLA headers when jax is
+    importable; otherwise -- this image has no jax -- against the test-only API stand-in under tests/xla_stub, as a
+    compile check and for tests/test_xla_ffi.py (output next to the stub, never loaded by the product).
+    Returns (path, "jax" | "stub")."""
+    build()
+    src = os.path.join(CSRC, "xla_ffi.cc")
+    try:
+        import jax.ffi
+        inc, kind, out = jax.ffi.include_dir(), "jax", os.path.join(HERE, "libunidom_b200_xla.so")
+    except Exception:
+        stub = os.path.join(HERE, "..", "tests", "xla_stub")
+        inc, kind, out = stub, "stub", os.path.join(stub, "libunidom_b200_xla_stub.so")
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(_nvcc_path()))), "include")
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", inc, "-I", cuda_inc, "-o", out, src,
+           "-L", HERE, "-lunidom_b200", "-Wl,-rpath," + HERE]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return out, kind
+
+
+def _nvcc_path():
+    import shutil
+    n = _nvcc()
+    return n if os.path.isabs(n) else (shutil.which(n) or "/usr/local/cuda/bin/nvcc")
+
+
 if __name__ == "__main__":
     var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var,
                 defines=[a for a in sys.argv[1:] if a.startswith("-D")]))
+    if "--xla" in sys.argv:
+        print(*build_xla_adapter(verbose="-v" in sys.argv))

@@ -173,11 +173,14 @@ class SimpleMPMSimulator:
     """B200 drop-in for SimpleMPMSimulator (mpm_simulator.py:27-63)."""
 
     def __init__(self, conf, batch_size, use_position_control=False, device="cuda", sdf_kind=None,
-                 p2g_mode=_lib.UD_P2G_ATOMIC, adjoint="recompute", tape_budget_bytes=None):
+                 p2g_mode=_lib.UD_P2G_ATOMIC, adjoint="recompute", tape_budget_bytes=None, ckpt_window=None):
         """adjoint: "recompute" (default) keeps only the step input and re-runs the S substeps in the backward;
         "tape" keeps every substep's residuals of a differentiated step in HBM until its backward (what jax.grad of
         the reference's lax.scan does: S times the memory, 0.71x the time); "auto" tapes while this process's allocated device memory plus
-        the new tape stays within `tape_budget_bytes` (default: 70 % of the device's memory) and recomputes beyond."""
+        the new tape stays within `tape_budget_bytes` (default: 70 % of the device's memory) and recomputes beyond.
+        ckpt_window: K-spaced substep checkpoints inside the recompute adjoint (ud_mpm_step_bwd_windowed): the backward
+        keeps the state entering every K-th substep and recomputes K substeps at a time, so its workspace holds K instead
+        of conf.steps substeps (long steps: whip_rope's 70 substeps) for one extra forward sweep; None = conf.steps."""
         self._L = _lib.lib()  # raises when the extension is missing
         if not torch.cuda.is_available():
             raise RuntimeError("unidom_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -198,6 +201,9 @@ class SimpleMPMSimulator:
         if adjoint not in ("auto", "tape", "recompute"):
             raise ValueError(f"adjoint={adjoint!r}: expected 'auto', 'tape' or 'recompute'")
         self.adjoint = adjoint
+        if ckpt_window is not None and int(ckpt_window) < 1:
+            raise ValueError(f"ckpt_window={ckpt_window!r}: expected a positive number of substeps")
+        self.ckpt_window = None if ckpt_window is None else int(ckpt_window)
         if tape_budget_bytes is None:
             tape_budget_bytes = torch.cuda.get_device_properties(self.device).total_memory * 7 // 10
         self.tape_budget_bytes = int(tape_budget_bytes)
@@ -346,6 +352,14 @@ class SimpleMPMSimulator:
             rc = self._L.ud_mpm_step_bwd_taped(C.byref(p), C.byref(sin), _ptr(action), C.byref(sgo), C.byref(sgi),
                                                _ptr(gaction), _aligned(tape.buf), tape.nbytes, self._stream())
             _lib.check(rc, "ud_mpm_step_bwd_taped")
+            return gin, gaction
+        if self.ckpt_window is not None and self.ckpt_window < int(self.conf.steps):
+            K = self.ckpt_window
+            ws, nbytes = self._ws_bwd.get(self._L.ud_mpm_bwd_windowed_workspace_bytes(C.byref(p), K))
+            rc = self._L.ud_mpm_step_bwd_windowed(C.byref(p), C.byref(sin), _ptr(self._material_dev), _ptr(self._h_dev),
+                                                  _ptr(action), C.byref(sgo), C.byref(sgi), _ptr(gaction), K, ws, nbytes,
+                                                  self._stream())
+            _lib.check(rc, "ud_mpm_step_bwd_windowed")
             return gin, gaction
         ws, nbytes = self._ws_bwd.get(self._L.ud_mpm_bwd_workspace_bytes(C.byref(p)))
         rc = self._L.ud_mpm_step_bwd(C.byref(p), C.byref(sin), _ptr(self._material_dev), _ptr(self._h_dev),
