@@ -145,10 +145,12 @@ def fused_update_available(device) -> bool:
     if dist.get_backend() != "nccl" or not torch.device(device).type == "cuda":
         return False
     try:
-        import torch.distributed._symmetric_memory  # noqa: F401
+        import importlib
+        importlib.import_module("torch.distributed._symmetric_memory")
     except Exception:
         return False
-    return hasattr(__import__("unidom_b200._lib", fromlist=["lib"]).lib(), "ud_apg_fused_update")
+    from . import _lib
+    return hasattr(_lib.lib(), "ud_apg_fused_update")
 
 
 class FusedUpdate:

@@ -732,7 +732,8 @@ template <int NW> constexpr size_t warp_tile_bytes() { return sizeof(float4) * 3
 // Flush of one window: nodes [j0, j0 + WN).  `tile` is this warp's [32][WN] float4 array.
 template <int NW, bool CLAMP, bool DET>
 __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __restrict__ tile, const WarpGroup& g,
-                                           const int base[3], bool live, int j0, float4* __restrict__ genv, int env) {
+                                           const int base[3], bool live, int j0, float4* __restrict__ genv, int env,
+                                           float wscale = 1.f) {
   constexpr int WN = warp_tile_nodes<NW>(), WS = warp_tile_stride<NW>(), RG = NW;   // RG row groups share a segment's rows
   const int lane = threadIdx.x & 31;
   const bool act = lane < WN * RG && j0 + lane % WN < 27;
@@ -795,6 +796,7 @@ __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __re
     }
     if (!ok || h != 0) continue;
     const int cell = (ix * k.ry + iy) * k.rz + iz;
+    acc.w *= wscale;   // P2G stages the bare weight in .w: p_mass is applied once per (segment, node), not per particle
     if (DET) {  // UD_P2G_DETERMINISTIC: 4 integer REDs on 64-bit fixed point (associative => order-independent)
       unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(genv) + 4 * (size_t)cell;
       atomicAdd(acc64 + 0, (unsigned long long)__double2ll_rn((double)acc.x * FIX_SCALE));
@@ -874,12 +876,12 @@ k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
           const float wt = wab * st.w[c][2];
           myrow[j - win * WN] =
               make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
-                          wt * (uab[2] + (float)c * Ac[2][2]), wt * k.p_mass);
+                          wt * (uab[2] + (float)c * Ac[2][2]), wt);
         }
       }
     }
     __syncwarp();
-    warp_flush<NW, false, DET>(k, tile, wg, st.base, live_, win * WN, genv, env);
+    warp_flush<NW, false, DET>(k, tile, wg, st.base, live_, win * WN, genv, env, k.p_mass);
   }
   warp_mark_blocks(k, wg, st.base, live_, bl, env);
 }
@@ -954,12 +956,12 @@ k_p2g_pers(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
             const float wt = wab * st.w[c][2];
             myrow[j - win * WN] =
                 make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
-                            wt * (uab[2] + (float)c * Ac[2][2]), wt * k.p_mass);
+                            wt * (uab[2] + (float)c * Ac[2][2]), wt);
           }
         }
       }
       __syncwarp();
-      warp_flush<NW, false, DET>(k, tile, wg, st.base, live_, win * WN, genv, env);
+      warp_flush<NW, false, DET>(k, tile, wg, st.base, live_, win * WN, genv, env, k.p_mass);
     }
     warp_mark_blocks(k, wg, st.base, live_, bl, env);
   }
@@ -1172,7 +1174,10 @@ __device__ __forceinline__ void g2p_gather(const MpmConst& k, const float4* __re
   }
 }
 
-__global__ void __launch_bounds__(UD_BLOCK, 8)
+#ifndef UD_G2P_MINB
+#define UD_G2P_MINB 8
+#endif
+__global__ void __launch_bounds__(UD_BLOCK, UD_G2P_MINB)
 k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ grid,
       const int32_t* __restrict__ perm, float* __restrict__ jrows, int substep) {
   __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_CELLS * 32];
@@ -1210,41 +1215,80 @@ void launch_g2p(const MpmConst& k, const float* ps_in, float* ps_out, const floa
   k_g2p<<<pgrid(k, UD_BLOCK), UD_BLOCK, 0, st>>>(k, ps_in, ps_out, grid, ws.perm, ws.jrows, substep);
 }
 
+// Stores one AoS leaf with NC floats per particle for the warp's consecutive particles [o0, o0 + nlive): the lanes'
+// values go through a per-warp shared-memory tile so that every store instruction writes 32 CONSECUTIVE floats
+// (one 128-byte line) instead of 32 floats NC apart (NC lines): 3 / 9 times fewer sectors per request.
+template <int NC>
+__device__ __forceinline__ void warp_store_aos(float* __restrict__ dst, size_t o0, int nlive, const float* vals,
+                                               float* __restrict__ sm) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) sm[lane * NC + c] = vals[c];   // NC is odd (3, 9): conflict-free
+  __syncwarp();
+  float* out = dst + o0 * NC;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const int e = j * 32 + lane;
+    if (e < nlive * NC) out[e] = sm[e];
+  }
+}
+
 // sorted tiles -> AoS outputs; J' = J * prod_f (1 + dt * trace-quirk_f), sequentially as the reference.
-// One thread per ORIGINAL particle, which gathers its sorted slot through the inverse permutation: the AoS stores of a
-// warp are contiguous, the scattered side is the read (round 1 scattered the stores: 160 us instead of ~70).
-__global__ void k_unsort_state(MpmConst k, const float* __restrict__ ps, const float* __restrict__ J_in,
-                               const int32_t* __restrict__ inv_perm, const float* __restrict__ jrows,
-                               float* __restrict__ x, float* __restrict__ v, float* __restrict__ C,
-                               float* __restrict__ F, float* __restrict__ J) {
+// One thread per ORIGINAL particle, which gathers its sorted slot through the inverse permutation; the AoS stores go
+// through warp_store_aos (round 1 scattered the stores: 160 us; gather + strided stores: 139 us).
+__global__ void __launch_bounds__(256)
+k_unsort_state(MpmConst k, const float* __restrict__ ps, const float* __restrict__ J_in,
+               const int32_t* __restrict__ inv_perm, const float* __restrict__ jrows,
+               float* __restrict__ x, float* __restrict__ v, float* __restrict__ C,
+               float* __restrict__ F, float* __restrict__ J) {
+  __shared__ float sm[256 / 32][32 * 9];
+  __shared__ float jfac[128];
   UD_PARTICLE_INDEX(k, env, g);
-  if (!live_) return;
-  const size_t o = g;                                   // original particle env * n + slot_
-  const int sp = env * k.n_pad + inv_perm[g];           // its sorted slot
-  float st[PS_NCOMP];
-  load_comps<0, PS_NCOMP, PS_NQ>(ps, sp, st);
-#pragma unroll
-  for (int c = 0; c < 3; ++c) x[3 * o + c] = st[PS_X + c];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) v[3 * o + c] = st[PS_V + c];
-#pragma unroll
-  for (int c = 0; c < 9; ++c) C[9 * o + c] = st[PS_C + c];
-#pragma unroll
-  for (int c = 0; c < 9; ++c) F[9 * o + c] = st[PS_F + c];
-  float j = nan_to_num(J_in[o]);
-  int nr = min(3, k.n);
-  for (int f = 0; f < k.S; ++f) {
-    const float* jr = jrows + ((size_t)env * k.S + f) * 9;
+  // the J factor of every substep is the same for all particles of the env (the trace quirk reads rows of particles
+  // 0..2): formed once per CTA, applied sequentially per particle as before
+  const int nr = min(3, k.n);
+  if (threadIdx.x < 128 && (int)threadIdx.x < k.S && k.S <= 128) {   // S <= 128 in every shipped scene
+    const float* jr = jrows + ((size_t)env * k.S + threadIdx.x) * 9;
     float t[3] = {0.f, 0.f, 0.f};
     for (int i = 0; i < nr; ++i) {
       t[0] += jr[3 * i];
       t[1] += jr[3 * i + 1];
       t[2] += jr[3 * i + 2];
     }
-    float tr = (t[0] + t[1]) + t[2];
-    j = j * (1.f + k.dt * tr);
+    jfac[threadIdx.x] = 1.f + k.dt * ((t[0] + t[1]) + t[2]);
   }
-  J[o] = j;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int slot0 = slot_ - lane;
+  if (slot0 >= k.n) return;                 // warp-uniform
+  const int nlive = min(32, k.n - slot0);
+  const size_t o0 = (size_t)env * k.n + slot0;
+  const int sp = env * k.n_pad + (live_ ? inv_perm[g] : 0);   // sorted slot of the original particle
+  float st[PS_NCOMP];
+  load_comps<0, PS_NCOMP, PS_NQ>(ps, sp, st);
+  float* wsm = sm[threadIdx.x >> 5];
+  warp_store_aos<3>(x, o0, nlive, st + PS_X, wsm);
+  warp_store_aos<3>(v, o0, nlive, st + PS_V, wsm);
+  warp_store_aos<9>(C, o0, nlive, st + PS_C, wsm);
+  warp_store_aos<9>(F, o0, nlive, st + PS_F, wsm);
+  if (!live_) return;
+  float j = nan_to_num(J_in[g]);
+  if (k.S <= 128) {
+    for (int f = 0; f < k.S; ++f) j = j * jfac[f];
+  } else {   // longer steps than any shipped scene: straight from global memory
+    for (int f = 0; f < k.S; ++f) {
+      const float* jr = jrows + ((size_t)env * k.S + f) * 9;
+      float t[3] = {0.f, 0.f, 0.f};
+      for (int i = 0; i < nr; ++i) {
+        t[0] += jr[3 * i];
+        t[1] += jr[3 * i + 1];
+        t[2] += jr[3 * i + 2];
+      }
+      j = j * (1.f + k.dt * ((t[0] + t[1]) + t[2]));
+    }
+  }
+  J[g] = j;
 }
 
 void launch_unsort_state(const MpmConst& k, const float* ps_slot, const float* J_in, const MpmWs& ws,
@@ -1860,29 +1904,29 @@ UD_DEV float norm_div(float g, float n2) {
   return nrm < 1.0f ? g : g / nrm;
 }
 
-__global__ void k_unsort_cot(MpmConst k, const float* __restrict__ gs, const int32_t* __restrict__ inv_perm,
-                             const float* __restrict__ norm2, float* __restrict__ gx, float* __restrict__ gv,
-                             float* __restrict__ gC, float* __restrict__ gF, float* __restrict__ gJ) {
+__global__ void __launch_bounds__(256)
+k_unsort_cot(MpmConst k, const float* __restrict__ gs, const int32_t* __restrict__ inv_perm,
+             const float* __restrict__ norm2, float* __restrict__ gx, float* __restrict__ gv,
+             float* __restrict__ gC, float* __restrict__ gF, float* __restrict__ gJ) {
+  __shared__ float sm[256 / 32][32 * 9];
   UD_PARTICLE_INDEX(k, env, g);
-  if (!live_) return;
-  const size_t o = g;                                   // one thread per ORIGINAL particle (contiguous AoS stores)
-  const int sp = env * k.n_pad + inv_perm[g];
+  const int lane = threadIdx.x & 31;
+  const int slot0 = slot_ - lane;
+  if (slot0 >= k.n) return;                 // warp-uniform
+  const int nlive = min(32, k.n - slot0);
+  const size_t o0 = (size_t)env * k.n + slot0;   // one thread per ORIGINAL particle (coalesced AoS stores)
+  const int sp = env * k.n_pad + (live_ ? inv_perm[g] : 0);
   float n2 = norm2[env * 2];
   float st[PS_NCOMP];
   load_comps<0, PS_NCOMP, PS_NQ>(gs, sp, st);
-  if (gx)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) gx[3 * o + c] = norm_div(st[PS_X + c], n2);
-  if (gv)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) gv[3 * o + c] = norm_div(st[PS_V + c], n2);
-  if (gC)
-#pragma unroll
-    for (int c = 0; c < 9; ++c) gC[9 * o + c] = norm_div(st[PS_C + c], n2);
-  if (gF)
-#pragma unroll
-    for (int c = 0; c < 9; ++c) gF[9 * o + c] = norm_div(st[PS_F + c], n2);
-  if (gJ) gJ[o] = 0.f;  // the cotangent of J is dropped by substep_bwd_loss (:343-350)
+  for (int c = 0; c < PS_NCOMP; ++c) st[c] = norm_div(st[c], n2);
+  float* wsm = sm[threadIdx.x >> 5];
+  if (gx) warp_store_aos<3>(gx, o0, nlive, st + PS_X, wsm);
+  if (gv) warp_store_aos<3>(gv, o0, nlive, st + PS_V, wsm);
+  if (gC) warp_store_aos<9>(gC, o0, nlive, st + PS_C, wsm);
+  if (gF) warp_store_aos<9>(gF, o0, nlive, st + PS_F, wsm);
+  if (gJ && live_) gJ[g] = 0.f;  // the cotangent of J is dropped by substep_bwd_loss (:343-350)
 }
 
 __global__ void k_write_small(MpmConst k, ud_mpm_state gin, float* __restrict__ gaction,

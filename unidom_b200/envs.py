@@ -136,12 +136,16 @@ class ClothEnv:
             parts.append(((state.stiffness.to(state.x.dtype) - lo) / (hi - lo))[:, None])
         return torch.cat(parts, dim=1)
 
-    def reset(self, shift_xz=None):
-        """cloth_env.py:178-188: the lattice plus ONE N(0, 0.05^2) xz shift shared by all envs.  The reference
-        draws it from threefry (not reproducible here); pass `shift_xz` (2,) or get a seeded numpy draw."""
+    def reset(self, key=None, shift_xz=None):
+        """cloth_env.py:178-188: `key, _ = split(key); x[..., [0, 2]] += normal(key, (2,)) * 0.05` -- the lattice plus ONE
+        xz shift shared by all envs, drawn from the reference's own threefry stream (unidom_b200.jaxrng).  `key`: a
+        PRNGKey (2 x uint32) or an int seed, default PRNGKey(0) as in apg.py; `shift_xz` (2,) overrides the draw."""
         st = self.simulator.reset_jax()
         if shift_xz is None:
-            shift_xz = np.random.RandomState(getattr(self.conf, "seed", 1)).randn(2).astype(np.float32) * 0.05
+            from . import jaxrng
+            k = jaxrng.PRNGKey(0 if key is None else key) if (key is None or np.isscalar(key)) else np.asarray(key, np.uint32)
+            k = jaxrng.split(k)[0]
+            shift_xz = jaxrng.normal(k, (2,)) * np.float32(0.05)
         sh = torch.as_tensor(shift_xz, dtype=st.x.dtype, device=self.device)
         x = st.x.clone()
         x[..., 0] += sh[0]
@@ -206,17 +210,30 @@ class FoldCloth1ParaEnv(ClothEnv):
 # -------------------------------------------------------------------------------------------------------------------
 # MPM env (core/envs/basic/mpm_env.py) with the push task of core/envs/shape_elasto_plastic.py ("push_plasticine")
 # -------------------------------------------------------------------------------------------------------------------
+def _auto_reset_shifts(state, scale, device):
+    """The per-env draw of the reference's vmapped auto_reset (whip_rope_env.py:96-99, pour_water_env.py:98-101):
+    `key, _ = split(key); shift = normal(key, (2,)) * scale` on every env's own state.key.  Returns (shift [B,2] on
+    `device`, the new keys [B,2] int32)."""
+    from . import jaxrng
+    keys = state.key.detach().cpu().numpy().view(np.uint32)
+    new_keys = np.stack([jaxrng.split(k)[0] for k in keys])
+    sh = np.stack([jaxrng.normal(k, (2,)) for k in new_keys]).astype(np.float32) * np.float32(scale)
+    return torch.from_numpy(sh).to(device), torch.from_numpy(new_keys.view(np.int32).copy()).to(device)
+
+
 class MPMEnv:
     """B200 drop-in for the reference's MPMEnv (mpm_env.py:18-167): focus shift (pre_step/post_step :99-125),
     task-specific `get_primitive_actions`, scan of `simulator.step_jax` over the sub-actions (:141), state
     nan_to_num (:150-154), reward e^(-10 l2) (+ e^(-contact)) (:91-94,156-158), auto-reset on done (:159-161)."""
 
     def __init__(self, conf, batch_size, max_steps, goal=None, aux_reward=False, focus_computation=True, device="cuda",
-                 use_position_control=False):
+                 use_position_control=False, seed=0):
+        from . import jaxrng
         from .mpm_simulator import SimpleMPMSimulator
         self.conf, self.batch_size, self.max_steps = conf, batch_size, max_steps
         self.aux_reward, self.focus_computation = aux_reward, focus_computation
         self.simulator = SimpleMPMSimulator(conf, batch_size, use_position_control, device=device)
+        self.simulator.key_global = jaxrng.PRNGKey(seed)                             # mpm_env.py:54
         self.device = self.simulator.device
         self.action_size = 6
         goal = np.zeros((1, 3), np.float32) if goal is None else np.asarray(goal, np.float32)
@@ -366,16 +383,15 @@ class WhipRopeEnv(MPMEnv):
         return a[:, None, :], state
 
     def auto_reset(self, init_state, state):
-        """:92-104: the initial scene with a fresh N(0, 0.02^2) xz shift per env on rope and gripper.  The reference
-        draws it from threefry (not reproducible here): a seeded NumPy stream stands in."""
-        B = self.batch_size
-        sh = torch.from_numpy(self._rng.randn(B, 2).astype(np.float32) * 0.02).to(self.device)
+        """:92-104: the initial scene with a fresh N(0, 0.02^2) xz shift per env on rope and gripper, drawn from every
+        env's own threefry key like the reference's vmapped auto_reset (state.key advances with it)."""
+        sh, keys = _auto_reset_shifts(init_state, 0.02, self.device)
         shift = torch.stack([sh[:, 0], torch.zeros_like(sh[:, 0]), sh[:, 1]], dim=1)
         p = init_state.primitives[0]
         pos = p.position.clone()
         pos[:, 0] = pos[:, 0] + shift
         prims = [p._replace(position=pos)] + list(init_state.primitives[1:])
-        return init_state._replace(x=init_state.x + shift[:, None, :], primitives=prims)
+        return init_state._replace(x=init_state.x + shift[:, None, :], primitives=prims, key=keys)
 
 
 class PourWaterEnv(MPMEnv):
@@ -410,10 +426,9 @@ class PourWaterEnv(MPMEnv):
         return a[:, None, :], state
 
     def auto_reset(self, init_state, state):
-        """:96-105: bowl 0 back to [0.5, 0.2, 0.5] plus an N(0, 0.02^2) xz shift per env (seeded NumPy stream)."""
-        B = self.batch_size
-        sh = torch.from_numpy(self._rng.randn(B, 2).astype(np.float32) * 0.02).to(self.device)
+        """:96-105: bowl 0 back to [0.5, 0.2, 0.5] plus an N(0, 0.02^2) xz shift per env from the env's own threefry key."""
+        sh, keys = _auto_reset_shifts(init_state, 0.02, self.device)
         p = init_state.primitives[0]
         pos = p.position.clone()
         pos[:, 0] = torch.tensor([0.5, 0.2, 0.5], device=self.device) + torch.stack([sh[:, 0], torch.zeros_like(sh[:, 0]), sh[:, 1]], 1)
-        return init_state._replace(primitives=[p._replace(position=pos)] + list(init_state.primitives[1:]))
+        return init_state._replace(primitives=[p._replace(position=pos)] + list(init_state.primitives[1:]), key=keys)

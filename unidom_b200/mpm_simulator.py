@@ -214,8 +214,9 @@ class SimpleMPMSimulator:
 
     # ------------------------------------------------------------- scene construction
     def add_box(self, conf, state, size, init_pos, hardness=1, z_rotation_angle=0, material=0, density=1):
-        """mpm_simulator.py:65-125.  The liquid branch draws from a NumPy RandomState (the
-        reference's threefry stream, jax.random.uniform(conf.key), is not reproducible here)."""
+        """mpm_simulator.py:65-125.  The liquid branch draws jax.random.uniform(conf.key, (n_points, 3)) through the
+        NumPy threefry of unidom_b200.jaxrng when the conf carries a `key` (a PRNGKey or an int seed, like the
+        reference's confs: `key = random.PRNGKey(0)`); without one, a seeded NumPy stream."""
         assert density >= 1
         size = np.asarray(size, dtype=np.float32)
         init_pos = np.asarray(init_pos, dtype=np.float32)
@@ -223,7 +224,14 @@ class SimpleMPMSimulator:
         rot = np.array([[ca, -sa], [sa, ca]], dtype=np.float32)
         if material == 0:
             n_points = int(np.prod(size.astype(np.float64)) * conf.n_grid ** 3 * density)
-            x_ = (self._rng.uniform(size=(n_points, 3)).astype(np.float32) * 2 - 1) * (np.float32(0.5) * size)
+            key = getattr(conf, "key", None)
+            if key is not None:
+                from . import jaxrng
+                key = jaxrng.PRNGKey(key) if np.isscalar(key) else np.asarray(key, np.uint32)
+                u = jaxrng.uniform(key, (n_points, 3))                    # mpm_simulator.py:89, same stream
+            else:
+                u = self._rng.uniform(size=(n_points, 3)).astype(np.float32)
+            x_ = (u * np.float32(2) - np.float32(1)) * (np.float32(0.5) * size)
             x_[:, [0, 2]] = x_[:, [0, 2]] @ rot.T
             x_ = x_ + init_pos
         else:
@@ -276,10 +284,19 @@ class SimpleMPMSimulator:
             x=rep(state.x.to(torch.float32)), v=rep(torch.zeros((n, 3))), C=rep(torch.zeros((n, 3, 3))),
             F=rep(torch.eye(3).reshape(1, 3, 3).repeat(n, 1, 1)), J=rep(torch.ones((n,))),
             cur_step=rep(torch.tensor(0, dtype=torch.int32)), primitives=prims,
-            key=rep(torch.zeros(2, dtype=torch.int32)),
+            key=self._batch_keys(B).to(dev),
             friction=rep(torch.tensor([float(conf.ground_friction)])),
             mu=rep(torch.tensor([mu_0], dtype=torch.float32)),
             lamda=rep(torch.tensor([lambda_0], dtype=torch.float32)))
+
+    def _batch_keys(self, B):
+        """mpm_simulator.py:169: state.key = jax.random.split(key_global, batch_size) (uint32 bit patterns kept in the
+        int32 leaf); zeros when no key_global was set (the reference fails there)."""
+        if self.key_global is None:
+            return torch.zeros((B, 2), dtype=torch.int32)
+        from . import jaxrng
+        kg = jaxrng.PRNGKey(self.key_global) if np.isscalar(self.key_global) else np.asarray(self.key_global, np.uint32)
+        return torch.from_numpy(jaxrng.split(kg, B).view(np.int32).copy())
 
     # ------------------------------------------------------------------------ the step
     def params(self, B=None, n=None):
