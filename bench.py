@@ -78,15 +78,11 @@ def build_pour_water(sim):
 
 
 def build_whip_rope(sim):
-    """BASELINE configs[4]: whip_rope at add_box density 25 (49 329 elastic particles), position-controlled gripper,
-    S = 70 substeps per step (envs/whip_rope_env.py:27-73)."""
-    from unidom_b200.mpm_simulator import create_primitive
-    conf = sim.conf
-    st = sim.add_box(conf=conf, state=None, hardness=1.0, size=[0.15, 0.005, 0.005], init_pos=[0.25, 0.05, 0.25],
-                     material=1, density=25)
-    st.primitives.append(create_primitive(conf, 0.1, 666, [0.5] * 3, [0.02, 0.02, 0.02], [0.25, 0.05, 0.15]))
-    st = st._replace(primitives=[p._replace(action_scale=p.action_scale * 0.02) for p in st.primitives])
-    return sim.reset_jax(st)
+    """BASELINE configs[4]: the whip_rope scene (envs/whip_rope_env.py:27-73, confs.build_whip_rope) at add_box density 25
+    = 49 329 elastic particles, position-controlled gripper, S = 70 substeps per step."""
+    from unidom_b200 import confs
+    st = confs.build_whip_rope(sim, density=25)
+    return st._replace(primitives=[p._replace(action_scale=p.action_scale * 0.02) for p in st.primitives])
 
 
 def make_workload(args, dev, rank):
@@ -97,7 +93,7 @@ def make_workload(args, dev, rank):
     if args.config == "push_plasticine":
         conf = confs.shape_elasto_plastic_conf()
         sim = SimpleMPMSimulator(conf, args.envs, device=dev, p2g_mode=args.p2g_mode, adjoint=args.adjoint,
-                                 ckpt_window=args.ckpt_window)
+                                 ckpt_window=args.ckpt_window, env_groups=args.env_groups)
         state = build_scene(sim, args.density)
         B = state.x.shape[0]
         action = (torch.tensor([0.003, 0.0, 0.004, 0.0, 0.0, 0.0]) + 5e-4 * torch.randn((B, 6), generator=g)).to(dev)
@@ -107,7 +103,7 @@ def make_workload(args, dev, rank):
         conf = confs.pour_water_conf(res=(64, 48, 64))
         B = args.envs if args.envs != ENVS_PER_GPU else 16
         sim = SimpleMPMSimulator(conf, B, device=dev, sdf_kind=_lib.UD_SDF_CONTAINER, p2g_mode=args.p2g_mode,
-                                 adjoint=args.adjoint, ckpt_window=args.ckpt_window)
+                                 adjoint=args.adjoint, ckpt_window=args.ckpt_window, env_groups=args.env_groups)
         state = build_pour_water(sim)
         action = torch.zeros((B, 12), device=dev)
         action[:, 0], action[:, 5] = 0.3, 0.2
@@ -118,11 +114,11 @@ def make_workload(args, dev, rank):
         conf = confs.whip_rope_conf()
         B = args.envs if args.envs != ENVS_PER_GPU else 8
         sim = SimpleMPMSimulator(conf, B, use_position_control=True, device=dev, p2g_mode=args.p2g_mode,
-                                 adjoint=args.adjoint, ckpt_window=args.ckpt_window if args.ckpt_window else 10)
+                                 adjoint=args.adjoint, ckpt_window=args.ckpt_window if args.ckpt_window else 10,
+                                 env_groups=args.env_groups)
         state = build_whip_rope(sim)
-        action = torch.zeros((B, 6), device=dev)
-        action[:, 1] = 0.5
-        action += (2e-2 * torch.randn((B, 6), generator=g)).to(dev)
+        action = torch.tensor([[0.2, 0.5, 0.1, 0.0, 0.0, 0.0]], device=dev).repeat(B, 1)
+        action[:, :3] += (2e-2 * torch.randn((B, 3), generator=g)).to(dev)
         name = (f"whip_rope MLS-MPM elastic fwd+bwd, {state.x.shape[1]} particles/env, num_envs={B}/GPU, "
                 f"res={tuple(conf.res)}, {conf.steps} substeps/step, position control, "
                 f"substep checkpoints every {sim.ckpt_window}")
@@ -423,6 +419,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer leg")
     ap.add_argument("--config", default="push_plasticine", choices=["push_plasticine", "pour_water", "whip_rope", "cloth_para"],
                     help="BASELINE.json config to time (the driver's line is the default)")
+    ap.add_argument("--env-groups", type=int, default=2,
+                    help="run the envs of a call as this many sub-batches on separate CUDA streams (SimpleMPMSimulator)")
     ap.add_argument("--ckpt-window", type=int, default=None,
                     help="K-spaced substep checkpoints inside the recompute adjoint (default: none; whip_rope: 10)")
     args = ap.parse_args()
@@ -530,6 +528,10 @@ def main():
         sim.adjoint = "recompute"
 
     # ---------------- per-kernel-class timing (roofline), live CUDA events on the launch stream
+    groups_used = sim.env_groups
+    sim.env_groups = 1             # per-kernel durations are taken with the envs as ONE batch on one stream
+    for _ in range(2):
+        fwd_bwd(sim, state, action, cot)
     L.ud_timing_enable(1)
     nprof = min(args.steps, 5)
     for _ in range(nprof):
@@ -540,6 +542,7 @@ def main():
     cnt = (C.c_int64 * ncls)()
     L.ud_timing_collect(msb, cnt, ncls)
     L.ud_timing_enable(0)
+    sim.env_groups = groups_used
     L.ud_timing_class_name.restype = C.c_char_p
     classes = {L.ud_timing_class_name(i).decode(): (msb[i], cnt[i]) for i in range(ncls) if cnt[i] > 0}
     tot_ms = sum(v[0] for v in classes.values())
@@ -557,7 +560,9 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(dom)      # DRAM bytes per launch from the committed ncu --set full capture
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": kern[dom]["gbs"] / peak, "traffic": traffic,
+                "traffic_source": "profiles/traffic.json <- ncu --set full capture of this build (profiles/r02_ncu_full.md)",
+                "peak_source": peak_src,
                 "share_of_step": kern[dom]["share"],
                 "algorithmic_bytes_per_launch": ALG_BYTES[dom] * B * n,
                 "step_frac_fwdbwd": (value / world) * (ALG_BYTES_FWDBWD if args.adjoint == "recompute"
@@ -662,7 +667,7 @@ def main():
                                    if args.adjoint != "recompute" else
                                    "step input kept, the S substeps recomputed in the backward"),
                        "p2g_mode": "atomic" if args.p2g_mode == 0 else "deterministic",
-                       "ckpt_window": sim.ckpt_window,
+                       "ckpt_window": sim.ckpt_window, "env_groups": sim.env_groups,
                        "collective": "none in the step (envs are independent); APG's policy-gradient all-reduce is "
                                      "timed beside it as `apg_update` when N > 1"},
             "forward_only": {"value": fwd_value, "unit": "particle-substeps/s"},

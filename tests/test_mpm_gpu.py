@@ -386,3 +386,41 @@ def test_windowed_adjoint_matches_full_recompute(built_lib, window):
     print(f"windowed K={window}: workspace {win_b / 1e6:.2f} MB vs {full_b / 1e6:.2f} MB store-all-substeps")
     if window <= 4:
         assert win_b < full_b
+
+
+def test_cuda_graph_of_the_differentiated_scan(built_lib):
+    """graphs.GraphedMPMScanGrad: T step_jax calls and their adjoints as two CUDA graphs behind one autograd Function,
+    against the eager scan (deterministic P2G: forward bit-identical; gradients equal up to the order of the fp32 REDs
+    of G2P^T, floor = a second eager run); replayed with new inputs."""
+    from unidom_b200 import _lib
+    from unidom_b200.graphs import GraphedMPMScanGrad
+    conf = _conf(steps=6)
+    B, T = 2, 3
+    sim = _sim(conf, B, p2g_mode=_lib.UD_P2G_DETERMINISTIC)
+    st = util.mini_plasticine(sim, B, seed=43)
+    acts = torch.stack([_actions(B, 1, seed=60 + t) for t in range(T)]).to(st.x.device) * 0.6
+    scan = GraphedMPMScanGrad(sim, st, acts)
+    w = torch.linspace(-1, 1, st.x.numel(), device=st.x.device).reshape(st.x.shape) * 1e-3
+
+    def eager(x, a):
+        s = st._replace(x=x)
+        for t in range(T):
+            s, _ = sim.step_jax(s, a[t])
+        return s
+    for trial in range(2):
+        x0 = st.x + 1e-3 * trial
+        a0 = acts * (1 - 0.2 * trial)
+        res = []
+        for fn in (lambda x, a: scan(st._replace(x=x), a), eager, eager):
+            x = x0.clone().requires_grad_(True)
+            a = a0.clone().requires_grad_(True)
+            out = fn(x, a)
+            gx, ga = torch.autograd.grad((out.x * w).sum() + (out.v * w).sum() * 0.1, [x, a])
+            res.append((out, gx, ga))
+        for k in ("x", "v", "C", "F", "J"):
+            assert torch.equal(getattr(res[0][0], k), getattr(res[1][0], k)), (trial, k)
+        for i, name in ((1, "x"), (2, "action")):
+            e, fl = util.rel_err(res[0][i], res[1][i]), util.rel_err(res[2][i], res[1][i])
+            print(f"graphed vs eager scan, trial {trial}: grad {name} rel {e:.3e} (eager vs eager {fl:.3e})")
+            assert e <= max(1e-5, 20 * fl), (name, e, fl)
+    scan.close()

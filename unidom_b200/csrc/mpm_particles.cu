@@ -707,13 +707,20 @@ struct WarpGroup {
   unsigned mm;   // lanes whose particle sits in my base cell
   unsigned lb;   // leader lanes, one per distinct cell of the warp
   int row;       // my staging row
+  int nseg;      // distinct cells (segments) of the warp
 };
-__device__ __forceinline__ WarpGroup warp_group(int key) {
+// Per-warp segment table (shared memory, 32 x int2), written by the leader lanes while grouping and read by the flush
+// with one broadcast LDS.64 per segment instead of five shuffles + index arithmetic:
+//   .x = first row | rows << 6 | leader lane << 12 | live << 17 | interior << 18
+//   .y = linear cell index of the segment's base node (valid when interior: all 27 nodes in range, no wrap / clamp)
+constexpr int SEG_TABLE_BYTES = 32 * sizeof(int2);
+__device__ __forceinline__ WarpGroup warp_group(const MpmConst& k, int key, const int base[3], bool live, int2* __restrict__ seg) {
   const int lane = threadIdx.x & 31;
   WarpGroup g;
   g.mm = __match_any_sync(FULL, key);
   const int lead = __ffs(g.mm) - 1;
   g.lb = __ballot_sync(FULL, lane == lead);
+  g.nseg = __popc(g.lb);
   int start = 0;
   for (unsigned b = g.lb; b; b &= b - 1) {   // warp-uniform trip count = distinct cells (2-4 in the plasticine scene)
     const int L = __ffs(b) - 1;
@@ -721,81 +728,88 @@ __device__ __forceinline__ WarpGroup warp_group(int key) {
     start += L < lead ? cnt : 0;
   }
   g.row = start + __popc(g.mm & ((1u << lane) - 1u));
-  return g;
+  __syncwarp();   // persistent kernels: every lane has finished reading the previous tile's table
+  if (lane == lead) {
+    const bool interior = base[0] >= 0 && base[0] + 2 < k.rx && base[1] >= 0 && base[1] + 2 < k.ry && base[2] >= 0 &&
+                          base[2] + 2 < k.rz;
+    seg[__popc(g.lb & ((1u << lane) - 1u))] =
+        make_int2(start | (__popc(g.mm) << 6) | (lane << 12) | ((int)live << 17) | ((int)interior << 18),
+                  (base[0] * k.ry + base[1]) * k.rz + base[2]);
+  }
+  return g;   // callers __syncwarp() between staging and flush, which also publishes the table
 }
-// NW windows of WN nodes: 1 x 27, 2 x 14 (nodes 0-13 and 14-26; rows padded to 15 float4 = 60 words so that the eight
-// rows of a 16-byte store phase fall into distinct bank groups), 3 x 9
-template <int NW> constexpr int warp_tile_nodes() { return NW == 1 ? 27 : (NW == 2 ? 14 : 9); }
-template <int NW> constexpr int warp_tile_stride() { return NW == 2 ? 15 : warp_tile_nodes<NW>(); }
-template <int NW> constexpr size_t warp_tile_bytes() { return sizeof(float4) * 32 * warp_tile_stride<NW>(); }
+constexpr int WARP_TILE_NODES = 27;
+constexpr size_t WARP_TILE_BYTES = sizeof(float4) * 32 * WARP_TILE_NODES + SEG_TABLE_BYTES;   // staging rows + segment table
 
-// Flush of one window: nodes [j0, j0 + WN).  `tile` is this warp's [32][WN] float4 array.
-template <int NW, bool CLAMP, bool DET>
-__device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __restrict__ tile, const WarpGroup& g,
-                                           const int base[3], bool live, int j0, float4* __restrict__ genv, int env,
+// Flush: `tile` is this warp's [32][27] float4 array (432-byte rows: conflict-free 16-byte accesses).  Lane = node sums
+// its column over the rows of each segment in row order (two accumulators, eight rows in flight) and issues ONE 16-byte
+// vector RED per (segment, node).
+template <bool CLAMP, bool DET>
+__device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __restrict__ tile, const int2* __restrict__ seg,
+                                           const WarpGroup& g, const int base[3], float4* __restrict__ genv,
                                            float wscale = 1.f) {
-  constexpr int WN = warp_tile_nodes<NW>(), WS = warp_tile_stride<NW>(), RG = NW;   // RG row groups share a segment's rows
+  constexpr int WS = WARP_TILE_NODES;
   const int lane = threadIdx.x & 31;
-  const bool act = lane < WN * RG && j0 + lane % WN < 27;
-  const int jl = act ? lane % WN : 0, h = act ? lane / WN : 0;
-  const int j = j0 + jl;
+  const bool act = lane < 27;
+  const int j = act ? lane : 0;
   const int a = j / 9, b = (j / 3) % 3, c = j % 3;
-  int s0 = 0;
-  for (unsigned bits = g.lb; bits; bits &= bits - 1) {
-    const int L = __ffs(bits) - 1;
-    const int cnt = __popc(__shfl_sync(FULL, g.mm, L));
-    const int bx = __shfl_sync(FULL, base[0], L), by = __shfl_sync(FULL, base[1], L), bz = __shfl_sync(FULL, base[2], L);
-    const int lv = __shfl_sync(FULL, (int)live, L);
-    const int r_begin = s0;
-    s0 += cnt;
-    if (!lv) continue;   // warp-uniform: the padding lanes of an env's last tile
-    int ix, iy, iz;
-    if (CLAMP) {
-      ix = idx_gather(bx + a, k.rx);
-      iy = idx_gather(by + b, k.ry);
-      iz = idx_gather(bz + c, k.rz);
-    } else {
-      ix = idx_scatter(bx + a, k.rx);
-      iy = idx_scatter(by + b, k.ry);
-      iz = idx_scatter(bz + c, k.rz);
-    }
-    const bool ok = act && (ix | iy | iz) >= 0;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok) {
-      // rows [lo, hi) of the segment for my row group, summed in row order
-      const int per = (cnt + RG - 1) / RG;
-      const int lo = r_begin + min(h * per, cnt), hi = r_begin + min((h + 1) * per, cnt);
-      const float4* p = tile + lo * WS + jl;
-      int left = hi - lo;
-      for (; left >= 4; left -= 4) {
-        const float4 q0 = p[0], q1 = p[WS], q2 = p[2 * WS], q3 = p[3 * WS];
-        p += 4 * WS;
-        acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
-        acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
-        acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
-        acc.x += q3.x; acc.y += q3.y; acc.z += q3.z; acc.w += q3.w;
+  const int lane_off = (a * k.ry + b) * k.rz + c;
+  for (int s = 0; s < g.nseg; ++s) {
+    const int2 e = seg[s];   // broadcast
+    if (!((e.x >> 17) & 1)) continue;   // warp-uniform: the padding lanes of an env's last tile
+    const int r_begin = e.x & 63, cnt = (e.x >> 6) & 63;
+    int cell;
+    bool ok = act;
+    if ((e.x >> 18) & 1) {
+      cell = e.y + lane_off;
+    } else {   // a segment at the grid boundary: JAX's scatter (drop) / gather (clamp) index rules, node by node
+      const int L = (e.x >> 12) & 31;
+      const int bx = __shfl_sync(FULL, base[0], L), by = __shfl_sync(FULL, base[1], L), bz = __shfl_sync(FULL, base[2], L);
+      int ix, iy, iz;
+      if (CLAMP) {
+        ix = idx_gather(bx + a, k.rx);
+        iy = idx_gather(by + b, k.ry);
+        iz = idx_gather(bz + c, k.rz);
+      } else {
+        ix = idx_scatter(bx + a, k.rx);
+        iy = idx_scatter(by + b, k.ry);
+        iz = idx_scatter(bz + c, k.rz);
       }
-      for (; left > 0; --left) {
-        const float4 q0 = *p;
-        p += WS;
-        acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
-      }
+      ok = act && (ix | iy | iz) >= 0;
+      cell = (ix * k.ry + iy) * k.rz + iz;
     }
-    if (RG == 2) {   // row group 1 hands its partial sums to group 0
-      acc.x += __shfl_down_sync(FULL, acc.x, WN);
-      acc.y += __shfl_down_sync(FULL, acc.y, WN);
-      acc.z += __shfl_down_sync(FULL, acc.z, WN);
-      acc.w += __shfl_down_sync(FULL, acc.w, WN);
+    if (!ok) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* p = tile + r_begin * WS + j;
+    int left = cnt;
+    for (; left >= 8; left -= 8) {
+      const float4 q0 = p[0], q1 = p[WS], q2 = p[2 * WS], q3 = p[3 * WS];
+      const float4 q4 = p[4 * WS], q5 = p[5 * WS], q6 = p[6 * WS], q7 = p[7 * WS];
+      p += 8 * WS;
+      acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
+      acc2.x += q4.x; acc2.y += q4.y; acc2.z += q4.z; acc2.w += q4.w;
+      acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
+      acc2.x += q5.x; acc2.y += q5.y; acc2.z += q5.z; acc2.w += q5.w;
+      acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
+      acc2.x += q6.x; acc2.y += q6.y; acc2.z += q6.z; acc2.w += q6.w;
+      acc.x += q3.x; acc.y += q3.y; acc.z += q3.z; acc.w += q3.w;
+      acc2.x += q7.x; acc2.y += q7.y; acc2.z += q7.z; acc2.w += q7.w;
     }
-    if (RG == 3) {   // row groups 1, 2 hand their partial sums to group 0 (fixed order)
-      const float4 t1 = make_float4(__shfl_down_sync(FULL, acc.x, WN), __shfl_down_sync(FULL, acc.y, WN),
-                                    __shfl_down_sync(FULL, acc.z, WN), __shfl_down_sync(FULL, acc.w, WN));
-      const float4 t2 = make_float4(__shfl_down_sync(FULL, acc.x, 2 * WN), __shfl_down_sync(FULL, acc.y, 2 * WN),
-                                    __shfl_down_sync(FULL, acc.z, 2 * WN), __shfl_down_sync(FULL, acc.w, 2 * WN));
-      acc.x = (acc.x + t1.x) + t2.x; acc.y = (acc.y + t1.y) + t2.y; acc.z = (acc.z + t1.z) + t2.z; acc.w = (acc.w + t1.w) + t2.w;
+    if (left >= 4) {
+      const float4 q0 = p[0], q1 = p[WS], q2 = p[2 * WS], q3 = p[3 * WS];
+      p += 4 * WS;
+      left -= 4;
+      acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
+      acc2.x += q1.x; acc2.y += q1.y; acc2.z += q1.z; acc2.w += q1.w;
+      acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
+      acc2.x += q3.x; acc2.y += q3.y; acc2.z += q3.z; acc2.w += q3.w;
     }
-    if (!ok || h != 0) continue;
-    const int cell = (ix * k.ry + iy) * k.rz + iz;
+    for (; left > 0; --left) {
+      const float4 q0 = *p;
+      p += WS;
+      acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
+    }
+    acc.x += acc2.x; acc.y += acc2.y; acc.z += acc2.z; acc.w += acc2.w;
     acc.w *= wscale;   // P2G stages the bare weight in .w: p_mass is applied once per (segment, node), not per particle
     if (DET) {  // UD_P2G_DETERMINISTIC: 4 integer REDs on 64-bit fixed point (associative => order-independent)
       unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(genv) + 4 * (size_t)cell;
@@ -837,32 +851,31 @@ __device__ __forceinline__ void warp_mark_blocks(const MpmConst& k, const WarpGr
 }
 
 constexpr int P2GW_BLOCK = 128;   // 4 independent warps per CTA (the CTA is only the unit shared memory is carved in)
-// resident CTAs per SM the register allocation aims at = what the staging tiles leave room for
-template <int NW> constexpr int p2gw_min_blocks() { return NW == 1 ? 4 : 6; }
-template <int NW, bool DET>
-__global__ void __launch_bounds__(P2GW_BLOCK, p2gw_min_blocks<NW>())
+constexpr int P2GW_MIN_BLOCKS = 4;  // resident CTAs per SM = what the 14 KB staging tile per warp leaves room for
+// One tile (32 particles) per warp, one CTA per 4 tiles: the A/B partner of k_p2g_pers (ud_tuning_set("pers", 0)).
+template <bool DET>
+__global__ void __launch_bounds__(P2GW_BLOCK, P2GW_MIN_BLOCKS)
 k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
            const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
            const float* __restrict__ h_s, const float* __restrict__ vt_in, float* __restrict__ vt_out,
            float* __restrict__ svd_out, int vt_svd_i, BlkList bl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int WN = warp_tile_nodes<NW>(), WS = warp_tile_stride<NW>();
-  float4* tile = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * warp_tile_bytes<NW>());   // [32][WS]
+  unsigned char* wmem = smem_raw + (threadIdx.x >> 5) * WARP_TILE_BYTES;
+  float4* tile = reinterpret_cast<float4*>(wmem);                                                  // [32][27]
+  int2* seg = reinterpret_cast<int2*>(wmem + sizeof(float4) * 32 * WARP_TILE_NODES);               // segment table
   UD_PARTICLE_INDEX(k, env, g);
   if (slot_ - (int)(threadIdx.x & 31) >= k.n) return;   // warp-uniform: tiles beyond the env's last particle
-  Stencil st;
-  float u[3], Ac[3][3];
-  p2g_front(k, env, g, gp, true, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, vt_svd_i != 0, st, u, Ac);
-  const WarpGroup wg = warp_group(live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY);
-  float4* genv = grid + (size_t)env * k.G * (DET ? 2 : 1);   // DET: the int64 accumulator array (32 B per cell)
-  float4* myrow = tile + wg.row * WS;
-  const float lw = live_ ? 1.f : 0.f;
-#pragma unroll
-  for (int win = 0; win < NW; ++win) {
-    if (win) __syncwarp();   // the previous window has been flushed
+  {
+    Stencil st;
+    float u[3], Ac[3][3];
+    p2g_front(k, env, g, gp, true, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, vt_svd_i != 0, st, u, Ac);
+    const WarpGroup wg = warp_group(k, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base, live_, seg);
+    float4* genv = grid + (size_t)env * k.G * (DET ? 2 : 1);   // DET: the int64 accumulator array (32 B per cell)
+    float4* myrow = tile + wg.row * WARP_TILE_NODES;
+    const float lw = live_ ? 1.f : 0.f;
+    __syncwarp();   // (persistent kernel: every lane has left the previous tile's flush)
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      if ((a * 9 + 8) / WN < win || (a * 9) / WN > win) continue;   // no node of this a in the window (compile time)
       const float wa = st.w[a][0] * lw;
       const float ua[3] = {u[0] + (float)a * Ac[0][0], u[1] + (float)a * Ac[0][1], u[2] + (float)a * Ac[0][2]};
 #pragma unroll
@@ -871,98 +884,78 @@ k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
         const float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const int j = a * 9 + b * 3 + c;
-          if (j / WN != win) continue;   // compile time after unrolling
           const float wt = wab * st.w[c][2];
-          myrow[j - win * WN] =
-              make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
-                          wt * (uab[2] + (float)c * Ac[2][2]), wt);
+          myrow[a * 9 + b * 3 + c] = make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
+                                                 wt * (uab[2] + (float)c * Ac[2][2]), wt);   // .w: bare weight
         }
       }
     }
     __syncwarp();
-    warp_flush<NW, false, DET>(k, tile, wg, st.base, live_, win * WN, genv, env, k.p_mass);
+    warp_flush<false, DET>(k, tile, seg, wg, st.base, genv, k.p_mass);
+    warp_mark_blocks(k, wg, st.base, live_, bl, env);
   }
-  warp_mark_blocks(k, wg, st.base, live_, bl, env);
 }
 
 // Persistent variant: one CTA slot per resident CTA, every warp walks the tiles w, w + W, w + 2W, ... and issues the
 // loads of its NEXT tile before it starts computing the current one, so a tile's DRAM latency (12 % of the one-tile
 // kernel's stall samples sat on the first use of x) is hidden behind a whole tile of arithmetic.
-template <int NW, bool DET>
-__global__ void __launch_bounds__(P2GW_BLOCK, p2gw_min_blocks<NW>())
+template <bool DET>
+__global__ void __launch_bounds__(P2GW_BLOCK, P2GW_MIN_BLOCKS)
 k_p2g_pers(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
            const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
            const float* __restrict__ h_s, const float* __restrict__ vt_in, float* __restrict__ vt_out,
            float* __restrict__ svd_out, int vt_svd_i, BlkList bl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int WN = warp_tile_nodes<NW>(), WS = warp_tile_stride<NW>();
-  float4* tile = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * warp_tile_bytes<NW>());   // [32][WS]
-  const int lane = threadIdx.x & 31;
-  const int nwarps = gridDim.x * (P2GW_BLOCK / 32);
-  const int tpe = k.n_pad >> 5, ntiles = k.B * tpe;   // tiles per env, tiles in all
-  int t = blockIdx.x * (P2GW_BLOCK / 32) + (threadIdx.x >> 5);
-  if (t >= ntiles) return;
-  auto locate = [&](int tt, int& env, int& g, int& gp, bool& live) {
-    env = tt / tpe;
-    const int slot = (tt - env * tpe) * 32 + lane;
-    live = slot < k.n;
-    g = env * k.n + (live ? slot : 0);
-    gp = env * k.n_pad + slot;
-  };
+  unsigned char* wmem = smem_raw + (threadIdx.x >> 5) * WARP_TILE_BYTES;
+  float4* tile = reinterpret_cast<float4*>(wmem);                                                  // [32][27]
+  int2* seg = reinterpret_cast<int2*>(wmem + sizeof(float4) * 32 * WARP_TILE_NODES);               // segment table
+  const TileWalk w = tile_walk(k);
+  if (w.t >= w.ntiles) return;
   const bool warm = vt_in != nullptr, vt_svd = vt_svd_i != 0;
   P2gIn nx;
   {
     int env, g, gp;
     bool live;
-    locate(t, env, g, gp, live);
+    tile_locate(k, w, w.t, env, g, gp, live);
     p2g_issue_loads(env, g, gp, ps_in, mu_s, la_s, mat_s, h_s, vt_in, vt_svd, nx);
   }
-  for (; t < ntiles; t += nwarps) {
+  for (int t = w.t; t < w.ntiles; t += w.nwarps) {
     int env, g, gp;
     bool live_;
-    locate(t, env, g, gp, live_);
+    tile_locate(k, w, t, env, g, gp, live_);
     const P2gIn cur = nx;
-    if (t + nwarps < ntiles) {
+    if (t + w.nwarps < w.ntiles) {
       int e2, g2, gp2;
       bool l2;
-      locate(t + nwarps, e2, g2, gp2, l2);
+      tile_locate(k, w, t + w.nwarps, e2, g2, gp2, l2);
       p2g_issue_loads(e2, g2, gp2, ps_in, mu_s, la_s, mat_s, h_s, vt_in, vt_svd, nx);
     }
     Stencil st;
     float u[3], Ac[3][3];
     p2g_front_loaded(k, gp, true, cur, warm, ps_out, vt_out, svd_out, st, u, Ac);
-    const WarpGroup wg = warp_group(live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY);
+    const WarpGroup wg = warp_group(k, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base, live_, seg);
     float4* genv = grid + (size_t)env * k.G * (DET ? 2 : 1);   // DET: the int64 accumulator array (32 B per cell)
-    float4* myrow = tile + wg.row * WS;
+    float4* myrow = tile + wg.row * WARP_TILE_NODES;
     const float lw = live_ ? 1.f : 0.f;
-    __syncwarp();   // every lane has left the previous tile's flush
+    __syncwarp();   // (persistent kernel: every lane has left the previous tile's flush)
 #pragma unroll
-    for (int win = 0; win < NW; ++win) {
-      if (win) __syncwarp();   // the previous window has been flushed
+    for (int a = 0; a < 3; ++a) {
+      const float wa = st.w[a][0] * lw;
+      const float ua[3] = {u[0] + (float)a * Ac[0][0], u[1] + (float)a * Ac[0][1], u[2] + (float)a * Ac[0][2]};
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        if ((a * 9 + 8) / WN < win || (a * 9) / WN > win) continue;   // no node of this a in the window (compile time)
-        const float wa = st.w[a][0] * lw;
-        const float ua[3] = {u[0] + (float)a * Ac[0][0], u[1] + (float)a * Ac[0][1], u[2] + (float)a * Ac[0][2]};
+      for (int b = 0; b < 3; ++b) {
+        const float wab = wa * st.w[b][1];
+        const float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
 #pragma unroll
-        for (int b = 0; b < 3; ++b) {
-          const float wab = wa * st.w[b][1];
-          const float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int j = a * 9 + b * 3 + c;
-            if (j / WN != win) continue;   // compile time after unrolling
-            const float wt = wab * st.w[c][2];
-            myrow[j - win * WN] =
-                make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
-                            wt * (uab[2] + (float)c * Ac[2][2]), wt);
-          }
+        for (int c = 0; c < 3; ++c) {
+          const float wt = wab * st.w[c][2];
+          myrow[a * 9 + b * 3 + c] = make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
+                                                 wt * (uab[2] + (float)c * Ac[2][2]), wt);   // .w: bare weight
         }
       }
-      __syncwarp();
-      warp_flush<NW, false, DET>(k, tile, wg, st.base, live_, win * WN, genv, env, k.p_mass);
     }
+    __syncwarp();
+    warp_flush<false, DET>(k, tile, seg, wg, st.base, genv, k.p_mass);
     warp_mark_blocks(k, wg, st.base, live_, bl, env);
   }
 }
@@ -974,10 +967,10 @@ int tuning_pers(int v) {
   return o;
 }
 
-static int g_warp_nw = 1;   // staging windows of the warp-local kernels (1 or 3); 0 = the round-1 CTA-staged kernels
+static int g_warp_nw = 1;   // 1: warp-local staged-scatter kernels; 0 = the round-1 CTA-staged kernels (A/B partner)
 int tuning_warp(int v) {
   int o = g_warp_nw;
-  if (v >= 0 && v <= 3) g_warp_nw = v;
+  if (v == 0 || v == 1) g_warp_nw = v;
   return o;
 }
 
@@ -987,23 +980,21 @@ static BlkList blk_list_of(const MpmConst& k, const MpmWs& ws, int substep) {
   return bl;
 }
 
-template <int NW, bool DET>
+template <bool DET>
 static void launch_p2g_warp(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
                             const float* la_s, const float* vt_in, float* vt_out, float* svd_out, int substep,
                             const MpmWs& ws, cudaStream_t st, bool vt_svd) {
-  const size_t smem = warp_tile_bytes<NW>() * (P2GW_BLOCK / 32);
+  const size_t smem = WARP_TILE_BYTES * (P2GW_BLOCK / 32);
   // per-DEVICE attribute (one host thread per device under pmap): set on every launch
-  cudaFuncSetAttribute(k_p2g_warp<NW, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (g_pers) {
-    cudaFuncSetAttribute(k_p2g_pers<NW, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int ctas = std::min(num_sms() * p2gw_min_blocks<NW>(), cdiv((long long)k.B * (k.n_pad >> 5), P2GW_BLOCK / 32));
-    k_p2g_pers<NW, DET><<<ctas, P2GW_BLOCK, smem, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out,
-                                                        svd_out, (int)vt_svd, blk_list_of(k, ws, substep));
+    cudaFuncSetAttribute(k_p2g_pers<DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_p2g_pers<DET><<<persistent_ctas(k, P2GW_BLOCK / 32, P2GW_MIN_BLOCKS), P2GW_BLOCK, smem, st>>>(
+        k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out, (int)vt_svd, blk_list_of(k, ws, substep));
     return;
   }
-  k_p2g_warp<NW, DET><<<pgrid(k, P2GW_BLOCK), P2GW_BLOCK, smem, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s,
-                                                                     vt_in, vt_out, svd_out, (int)vt_svd,
-                                                                     blk_list_of(k, ws, substep));
+  cudaFuncSetAttribute(k_p2g_warp<DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_p2g_warp<DET><<<pgrid(k, P2GW_BLOCK), P2GW_BLOCK, smem, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in,
+                                                                  vt_out, svd_out, (int)vt_svd, blk_list_of(k, ws, substep));
 }
 
 // true: the P2G kernels in use append the touched blocks to the substep's list themselves (no k_blk_compact pass)
@@ -1016,16 +1007,8 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
   const bool vt_svd = svd_out != nullptr && !vt_in_is_vt;   // layout of vt_in: previous substep's SVD tile / V^T buffer
   if (tuning_stage() && g_warp_nw) {
     float4* fix = reinterpret_cast<float4*>(ws.grid_fix);
-    if (g_warp_nw == 1) {
-      if (fix) launch_p2g_warp<1, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
-      else launch_p2g_warp<1, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
-    } else if (g_warp_nw == 2) {
-      if (fix) launch_p2g_warp<2, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
-      else launch_p2g_warp<2, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
-    } else {
-      if (fix) launch_p2g_warp<3, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
-      else launch_p2g_warp<3, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
-    }
+    if (fix) launch_p2g_warp<true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
+    else launch_p2g_warp<false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
     return;
   }
   // the attribute is per DEVICE (a process may drive several, one host thread each: SURVEY 8b): set it on every launch
@@ -1459,17 +1442,16 @@ k_g2p_bwd(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict_
 // warp_flush() with clamped target indices (transpose of the clamping gather).  No block barrier.
 constexpr int G2PBW_BLOCK = 64;
 constexpr int G2PBW_CELLS = 4;   // distinct cells per warp whose grid velocities are tiled; more -> gather from L1/L2
-template <int NW> constexpr size_t g2pbw_warp_bytes() { return warp_tile_bytes<NW>() + sizeof(float4) * G2PBW_CELLS * 32; }
-template <int NW> constexpr int g2pbw_min_blocks() { return NW == 1 ? 7 : 10; }
-template <int NW>
-__global__ void __launch_bounds__(G2PBW_BLOCK, g2pbw_min_blocks<NW>())
+constexpr size_t G2PBW_WARP_BYTES = WARP_TILE_BYTES + sizeof(float4) * G2PBW_CELLS * 32;
+constexpr int G2PBW_MIN_BLOCKS = 7;   // resident 2-warp CTAs per SM that the staging tiles leave room for
+__global__ void __launch_bounds__(G2PBW_BLOCK, G2PBW_MIN_BLOCKS)
 k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __restrict__ grid_out,
                float* __restrict__ gs, float4* __restrict__ ggrid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int WN = warp_tile_nodes<NW>(), WS = warp_tile_stride<NW>();
-  unsigned char* wbase = smem_raw + (threadIdx.x >> 5) * g2pbw_warp_bytes<NW>();
-  float4* tile = reinterpret_cast<float4*>(wbase);                              // [32][WN] staged cotangents
-  float4* vtile = reinterpret_cast<float4*>(wbase + warp_tile_bytes<NW>());     // [G2PBW_CELLS][32] grid velocities
+  unsigned char* wbase = smem_raw + (threadIdx.x >> 5) * G2PBW_WARP_BYTES;
+  float4* tile = reinterpret_cast<float4*>(wbase);                                            // [32][27] staged cotangents
+  int2* seg = reinterpret_cast<int2*>(wbase + sizeof(float4) * 32 * WARP_TILE_NODES);        // segment table
+  float4* vtile = reinterpret_cast<float4*>(wbase + WARP_TILE_BYTES);                         // [G2PBW_CELLS][32] grid velocities
   UD_PARTICLE_INDEX(k, env, g);
   const int lane = threadIdx.x & 31;
   if (slot_ - lane >= k.n) return;   // warp-uniform
@@ -1478,7 +1460,7 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
   g2pb_load(k, ps_in, gs, gp, x, gxo, gvt, gC);
   Stencil st;
   make_stencil(x, k.inv_dx, st);
-  const WarpGroup wg = warp_group(live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY);
+  const WarpGroup wg = warp_group(k, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base, live_, seg);
   const float4* genv = grid_out + (size_t)env * k.G;
   const int nseg = __popc(wg.lb);
   const int leadlane = __ffs(wg.mm) - 1;
@@ -1517,7 +1499,7 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
     r0[i] = gvt[i] - (K[0][i] * st.fx[0] + K[1][i] * st.fx[1] + K[2][i] * st.fx[2]);
   }
   float Wg[3] = {0.f, 0.f, 0.f}, gfx[3] = {0.f, 0.f, 0.f};
-  float4* myrow = tile + wg.row * WS;
+  float4* myrow = tile + wg.row * WARP_TILE_NODES;
   float4* ggenv = ggrid + (size_t)env * k.G;
   auto nodes = [&](auto tiled_tag) {
     constexpr bool TILED = decltype(tiled_tag)::value;
@@ -1544,19 +1526,13 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
             gv = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
           }
           const float r[3] = {rab[0] + (float)c * K[2][0], rab[1] + (float)c * K[2][1], rab[2] + (float)c * K[2][2]};
-          const int j = a * 9 + b * 3 + c;          // compile time after unrolling
-          myrow[j % WN] = make_float4(wt * r[0], wt * r[1], wt * r[2], 0.f);
+          myrow[a * 9 + b * 3 + c] = make_float4(wt * r[0], wt * r[1], wt * r[2], 0.f);
           const float gwt = gv.x * r[0] + gv.y * r[1] + gv.z * r[2];
           Wg[0] += wt * gv.x;
           Wg[1] += wt * gv.y;
           Wg[2] += wt * gv.z;
           P += gwt * st.w[c][2];
           Q += gwt * st.dw[c][2];
-          if (NW > 1 && (j % WN == WN - 1 || j == 26)) {   // last node of a window: flush it (compile-time position)
-            __syncwarp();
-            warp_flush<NW, true, false>(k, tile, wg, st.base, live_, (j / WN) * WN, ggenv, env);
-            if (j != 26) __syncwarp();   // the next window overwrites the rows
-          }
         }
         P1 += P * st.w[b][1];
         P2 += P * st.dw[b][1];
@@ -1579,28 +1555,23 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
     }
     store_comps<PS_X, 3, PS_NQ>(gs, gp, ox);
   }
-  if (NW == 1) {
-    __syncwarp();
-    warp_flush<NW, true, false>(k, tile, wg, st.base, live_, 0, ggenv, env);
-  }
+  __syncwarp();
+  warp_flush<true, false>(k, tile, seg, wg, st.base, ggenv);
 }
 
 int tuning_warp(int v);
-template <int NW>
 static void launch_g2p_bwd_warp(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
                                 cudaStream_t st) {
-  const size_t smem = g2pbw_warp_bytes<NW>() * (G2PBW_BLOCK / 32);
-  cudaFuncSetAttribute(k_g2p_bwd_warp<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
-  k_g2p_bwd_warp<NW><<<pgrid(k, G2PBW_BLOCK), G2PBW_BLOCK, smem, st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
+  const size_t smem = G2PBW_WARP_BYTES * (G2PBW_BLOCK / 32);
+  cudaFuncSetAttribute(k_g2p_bwd_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
+  k_g2p_bwd_warp<<<pgrid(k, G2PBW_BLOCK), G2PBW_BLOCK, smem, st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
 }
 
 void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
                     cudaStream_t st) {
   KScope ks_(KC_G2P_BWD, st);
   const int nw = tuning_warp(-1);
-  if (nw == 1) return launch_g2p_bwd_warp<1>(k, ps_in, grid_out, ws, st);
-  if (nw == 2) return launch_g2p_bwd_warp<2>(k, ps_in, grid_out, ws, st);
-  if (nw == 3) return launch_g2p_bwd_warp<3>(k, ps_in, grid_out, ws, st);
+  if (nw == 1) return launch_g2p_bwd_warp(k, ps_in, grid_out, ws, st);
   cudaFuncSetAttribute(k_g2p_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2pb_smem_bytes());   // per device
   k_g2p_bwd<<<pgrid(k, G2PB_BLOCK), G2PB_BLOCK, g2pb_smem_bytes(), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
 }

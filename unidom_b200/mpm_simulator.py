@@ -173,11 +173,15 @@ class SimpleMPMSimulator:
     """B200 drop-in for SimpleMPMSimulator (mpm_simulator.py:27-63)."""
 
     def __init__(self, conf, batch_size, use_position_control=False, device="cuda", sdf_kind=None,
-                 p2g_mode=_lib.UD_P2G_ATOMIC, adjoint="recompute", tape_budget_bytes=None, ckpt_window=None):
+                 p2g_mode=_lib.UD_P2G_ATOMIC, adjoint="recompute", tape_budget_bytes=None, ckpt_window=None,
+                 env_groups=1):
         """adjoint: "recompute" (default) keeps only the step input and re-runs the S substeps in the backward;
         "tape" keeps every substep's residuals of a differentiated step in HBM until its backward (what jax.grad of
         the reference's lax.scan does: S times the memory, 0.71x the time); "auto" tapes while this process's allocated device memory plus
         the new tape stays within `tape_budget_bytes` (default: 70 % of the device's memory) and recomputes beyond.
+        env_groups: the envs of a call are independent (vmap over axis 0), so a call may run them as `env_groups`
+        sub-batches on that many CUDA streams: the latency-bound grid / binning kernels of one group overlap the
+        particle kernels of the others.  Results are those of env_groups=1 (every env is computed by the same kernels).
         ckpt_window: K-spaced substep checkpoints inside the recompute adjoint (ud_mpm_step_bwd_windowed): the backward
         keeps the state entering every K-th substep and recomputes K substeps at a time, so its workspace holds K instead
         of conf.steps substeps (long steps: whip_rope's 70 substeps) for one extra forward sweep; None = conf.steps."""
@@ -196,8 +200,11 @@ class SimpleMPMSimulator:
             sdf_kind = getattr(conf, "sdf_kind", _lib.UD_SDF_BOX)
         self.sdf_kind = int(sdf_kind)
         self.p2g_mode = int(p2g_mode)
-        self._ws_fwd = _Workspace(self.device)
-        self._ws_bwd = _Workspace(self.device)
+        self.env_groups = max(1, int(env_groups))
+        self._ws_fwd_g = [_Workspace(self.device) for _ in range(self.env_groups)]
+        self._ws_bwd_g = [_Workspace(self.device) for _ in range(self.env_groups)]
+        self._ws_fwd, self._ws_bwd = self._ws_fwd_g[0], self._ws_bwd_g[0]
+        self._group_streams = None
         if adjoint not in ("auto", "tape", "recompute"):
             raise ValueError(f"adjoint={adjoint!r}: expected 'auto', 'tape' or 'recompute'")
         self.adjoint = adjoint
@@ -333,10 +340,40 @@ class SimpleMPMSimulator:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _groups(self, B):
+        """[(first env, envs, stream, group index)] of a call over B envs; one group on the current stream unless
+        env_groups > 1 divides the batch."""
+        G = self.env_groups
+        if G <= 1 or B % G or B < G:
+            return None
+        if self._group_streams is None:
+            self._group_streams = [torch.cuda.Stream(self.device) for _ in range(G)]
+        per = B // G
+        return [(g * per, per, self._group_streams[g], g) for g in range(G)]
+
     def _call_fwd(self, leaves, softness_list, action, want_tape=False):
         p = self.params(B=leaves[0].shape[0], n=leaves[0].shape[1])
         out = [torch.empty_like(t) for t in leaves]
         soft_out = [torch.empty_like(t) for t in softness_list]
+        groups = self._groups(leaves[0].shape[0])
+        if groups is not None and not (want_tape and self.adjoint != "recompute"):
+            if want_tape:
+                self.last_adjoint = "recompute"
+            cur = torch.cuda.current_stream(self.device)
+            for e0, ne, sg, g in groups:
+                sg.wait_stream(cur)
+                with torch.cuda.stream(sg):
+                    pg = self.params(B=ne, n=leaves[0].shape[1])
+                    sl = lambda ts: [t[e0:e0 + ne] for t in ts]      # noqa: E731 -- batch is the leading axis of every leaf
+                    sin, sout = self._pack(sl(leaves), sl(softness_list)), self._pack(sl(out), sl(soft_out))
+                    ws, nbytes = self._ws_fwd_g[g].get(self._L.ud_mpm_fwd_workspace_bytes(C.byref(pg)))
+                    rc = self._L.ud_mpm_step_fwd(C.byref(pg), C.byref(sin), _ptr(self._material_dev), _ptr(self._h_dev),
+                                                 _ptr(action[e0:e0 + ne]), C.byref(sout), ws, nbytes,
+                                                 C.c_void_p(sg.cuda_stream))
+                    _lib.check(rc, "ud_mpm_step_fwd")
+            for _, _, sg, _ in groups:
+                cur.wait_stream(sg)
+            return out, None
         sin, sout = self._pack(leaves, softness_list), self._pack(out, soft_out)
         if want_tape and self.adjoint != "recompute":
             need = self._L.ud_mpm_tape_bytes(C.byref(p))
@@ -369,6 +406,25 @@ class SimpleMPMSimulator:
             rc = self._L.ud_mpm_step_bwd_taped(C.byref(p), C.byref(sin), _ptr(action), C.byref(sgo), C.byref(sgi),
                                                _ptr(gaction), _aligned(tape.buf), tape.nbytes, self._stream())
             _lib.check(rc, "ud_mpm_step_bwd_taped")
+            return gin, gaction
+        groups = self._groups(leaves[0].shape[0])
+        if groups is not None:
+            cur = torch.cuda.current_stream(self.device)
+            K = self.ckpt_window if (self.ckpt_window is not None and self.ckpt_window < int(self.conf.steps)) else int(self.conf.steps)
+            for e0, ne, sg, g in groups:
+                sg.wait_stream(cur)
+                with torch.cuda.stream(sg):
+                    pg = self.params(B=ne, n=leaves[0].shape[1])
+                    sl = lambda ts: [(t[e0:e0 + ne] if t is not None else None) for t in ts]      # noqa: E731
+                    s_in, s_go, s_gi = self._pack(sl(leaves), sl(softness_list)), self._pack(sl(gout), None), self._pack(sl(gin), None)
+                    ws, nbytes = self._ws_bwd_g[g].get(self._L.ud_mpm_bwd_windowed_workspace_bytes(C.byref(pg), K))
+                    rc = self._L.ud_mpm_step_bwd_windowed(C.byref(pg), C.byref(s_in), _ptr(self._material_dev),
+                                                          _ptr(self._h_dev), _ptr(action[e0:e0 + ne]), C.byref(s_go),
+                                                          C.byref(s_gi), _ptr(gaction[e0:e0 + ne]), K, ws, nbytes,
+                                                          C.c_void_p(sg.cuda_stream))
+                    _lib.check(rc, "ud_mpm_step_bwd_windowed")
+            for _, _, sg, _ in groups:
+                cur.wait_stream(sg)
             return gin, gaction
         if self.ckpt_window is not None and self.ckpt_window < int(self.conf.steps):
             K = self.ckpt_window
