@@ -782,6 +782,7 @@ __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __re
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* p = tile + r_begin * WS + j;
     int left = cnt;
+#ifndef UD_FLUSH4
     for (; left >= 8; left -= 8) {
       const float4 q0 = p[0], q1 = p[WS], q2 = p[2 * WS], q3 = p[3 * WS];
       const float4 q4 = p[4 * WS], q5 = p[5 * WS], q6 = p[6 * WS], q7 = p[7 * WS];
@@ -804,6 +805,16 @@ __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __re
       acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
       acc2.x += q3.x; acc2.y += q3.y; acc2.z += q3.z; acc2.w += q3.w;
     }
+#else
+    for (; left >= 4; left -= 4) {
+      const float4 q0 = p[0], q1 = p[WS], q2 = p[2 * WS], q3 = p[3 * WS];
+      p += 4 * WS;
+      acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
+      acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
+      acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
+      acc.x += q3.x; acc.y += q3.y; acc.z += q3.z; acc.w += q3.w;
+    }
+#endif
     for (; left > 0; --left) {
       const float4 q0 = *p;
       p += WS;
