@@ -687,10 +687,10 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
 //           (segments in leader-lane order, rows in lane order), so the reduction order is fixed
 //   stage : every lane writes its node values as float4 {px,py,pz,m} at tile[row][node] (one STS.128 per node; the
 //           432-byte row stride is conflict-free for 16-byte accesses)
-//   flush : lane = (node, row group) sums its node's float4 column over the rows of each segment (LDS.128 + 4 FADD per
-//           row) and issues ONE 16-byte vector RED per (segment, node)
-// NW = 1: one window of all 27 nodes (13.8 KB per warp); NW = 3: three windows of 9 nodes (one per x offset, 4.6 KB
-// per warp), each flushed by 9 nodes x 3 row groups.
+//   flush : lane = node sums its node's float4 column over the rows of each segment (LDS.128 + 4 FADD per row) and
+//           issues ONE 16-byte vector RED per (segment, node)
+// One window of all 27 nodes (13.8 KB per warp).  Two windows of 14 / 13 nodes and three of 9 (more resident warps, one
+// flush pass per window) were measured and lost: 13.76 / 16.34 vs 12.79 ms per step (profiles/r02_summary.md).
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;
 // The 4x4x4 grid blocks a substep's P2G scatters into, listed by the scatter itself: the first warp to touch a block
@@ -782,7 +782,6 @@ __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __re
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* p = tile + r_begin * WS + j;
     int left = cnt;
-#ifndef UD_FLUSH4
     for (; left >= 8; left -= 8) {
       const float4 q0 = p[0], q1 = p[WS], q2 = p[2 * WS], q3 = p[3 * WS];
       const float4 q4 = p[4 * WS], q5 = p[5 * WS], q6 = p[6 * WS], q7 = p[7 * WS];
@@ -805,16 +804,6 @@ __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __re
       acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
       acc2.x += q3.x; acc2.y += q3.y; acc2.z += q3.z; acc2.w += q3.w;
     }
-#else
-    for (; left >= 4; left -= 4) {
-      const float4 q0 = p[0], q1 = p[WS], q2 = p[2 * WS], q3 = p[3 * WS];
-      p += 4 * WS;
-      acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
-      acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
-      acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
-      acc.x += q3.x; acc.y += q3.y; acc.z += q3.z; acc.w += q3.w;
-    }
-#endif
     for (; left > 0; --left) {
       const float4 q0 = *p;
       p += WS;
@@ -1041,15 +1030,12 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
 // G2P (g2p_micro, :196-221) + advection (:326).  Out-of-range nodes clamp (JAX gather rule).
 // Rows of C' of original particles 0..2 are kept for the J update quirk (:327).
 // ------------------------------------------------------------------------------------------------
-// The 27-node gather of G2P for one warp: nv = sum wt g, nC = 4 inv_dx sum wt g (x) d.  The 32 particles of a warp
-// sit in a few cells (sorted order), so the warp fetches the 27 grid velocities of each DISTINCT base cell once
-// (<= G2P_TILE_CELLS cells, all loads issued before the first is consumed, no block barrier) into `tile` and every
-// lane reads its stencil from shared memory; warps spanning more cells gather from L1/L2.
-// All lanes of the warp must call it.  `tile` [G2P_TILE_CELLS*27] and `cb` [G2P_TILE_CELLS] are per-warp shared memory.
-// Fills this warp's node tile with the 27 grid values of each distinct base cell of the warp (<= G2P_TILE_CELLS cells;
-// all loads are issued before the first one is consumed: one L2 round trip).  CLAMP: gather rule (clamped indices);
-// otherwise the scatter rule's transpose (dropped nodes read as zero).  Returns false (warp-uniform) when the warp
-// spans more cells than the tile holds; *gid = index of my cell in the tile.  All lanes of the warp must call it.
+// Per-warp node tile.  The 32 particles of a warp sit in a few cells (sorted order), so the warp fetches the 27 grid
+// values of each DISTINCT base cell once (<= G2P_TILE_CELLS cells; all loads are issued before the first one is
+// consumed: one L2 round trip, no block barrier) into `tile` [G2P_TILE_CELLS][32] and every lane reads its stencil from
+// shared memory; warps spanning more cells gather from L1/L2.  CLAMP: gather rule (clamped indices); otherwise the
+// scatter rule's transpose (dropped nodes read as zero).  Returns false (warp-uniform) when the warp spans more cells
+// than the tile holds; *gid = index of my cell in the tile.  All lanes of the warp must call it.
 template <bool CLAMP>
 __device__ __forceinline__ bool warp_tile_fill(const MpmConst& k, const float4* __restrict__ genv, const int base[3], bool live,
                                                float4* __restrict__ tile, int* gid_out) {
