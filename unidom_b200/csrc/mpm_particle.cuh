@@ -100,10 +100,37 @@ UD_DEV void constitutive_pre(const MpmConst& k, const Mat3& C, const Mat3& F, fl
 }
 
 // mpm_simulator.py:249-268 given the SVD (o.U, o.s, o.Vt) of o.F1: plastic clip, J, F2, stress, affine
-UD_DEV void constitutive_post(const MpmConst& k, const Mat3& C, Consti& o) {
+// all_plastic (warp-uniform in the kernels): every lane's particle is plastic, so the stress is formed in the frame of
+// the SVD, M = (F2 - R) F2^T = U diag((sc - 1) sc) U^T (the formula plastic_affine and the adjoint already use): two
+// 3x3 products fewer, and neither R nor D is formed (o.D is left unset).
+UD_DEV void constitutive_post(const MpmConst& k, const Mat3& C, Consti& o, bool all_plastic = false) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) o.sc[i] = o.plastic ? fminf(fmaxf(o.s[i], k.sig_lo), k.sig_hi) : o.s[i];
   o.J = o.sc[0] * o.sc[1] * o.sc[2];
+  if (all_plastic) {
+    Mat3 Us, Um;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        Us(i, j) = o.U(i, j) * o.sc[j];
+        Um(i, j) = Us(i, j) * (o.sc[j] - 1.f);
+      }
+    o.F2 = mat_mul(Us, o.Vt);
+    const float iso = o.la * o.J * (o.J - 1.f);
+    const float cs = k.c_stress_mul / k.c_stress_div;
+    const float tm = 2.f * o.mu;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i; j < 3; ++j) {
+        const float Mij = Um(i, 0) * o.U(j, 0) + Um(i, 1) * o.U(j, 1) + Um(i, 2) * o.U(j, 2);
+        const float st = tm * Mij + (i == j ? iso : 0.f);
+        o.affine(i, j) = cs * st + k.p_mass * C(i, j);
+        if (i != j) o.affine(j, i) = cs * st + k.p_mass * C(j, i);
+      }
+    return;
+  }
   Mat3 R = mat_mul(o.U, o.Vt);
   if (o.plastic) {
     Mat3 Us;

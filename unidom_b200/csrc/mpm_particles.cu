@@ -561,7 +561,11 @@ __device__ __forceinline__ void p2g_front_loaded(const MpmConst& k, int gp, bool
   Consti o;
   constitutive_pre(k, C, F, in.mu, in.la, in.h, in.mat, o);
   svd3_ws(o.F1, o.U, o.s, o.Vt, warm, vt0);
+#ifdef UD_NO_PLASTIC_FAST
   constitutive_post(k, C, o);
+#else
+  constitutive_post(k, C, o, __all_sync(0xffffffffu, o.plastic));   // every caller runs whole warps through here
+#endif
   if (wr) {   // padding lanes of an env's last tile write too: the next substep's dead lanes read initialised memory
     store_comps<PS_F, 9, PS_NQ>(ps_out, gp, o.F2.m);
     if (vt_out) {
@@ -779,37 +783,34 @@ __device__ __forceinline__ void warp_flush(const MpmConst& k, const float4* __re
       cell = (ix * k.ry + iy) * k.rz + iz;
     }
     if (!ok) continue;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // packed fp32 adds (FADD2, sm_100): the column sum is 2 issue slots per row instead of 4; same order, same
+    // rounding as the scalar form
+    float2 aL = make_float2(0.f, 0.f), aH = aL, bL = aL, bH = aL;
     const float4* p = tile + r_begin * WS + j;
     int left = cnt;
+#define UD_ACC(L_, H_, q_) { L_ = __fadd2_rn(L_, make_float2(q_.x, q_.y)); H_ = __fadd2_rn(H_, make_float2(q_.z, q_.w)); }
     for (; left >= 8; left -= 8) {
       const float4 q0 = p[0], q1 = p[WS], q2 = p[2 * WS], q3 = p[3 * WS];
       const float4 q4 = p[4 * WS], q5 = p[5 * WS], q6 = p[6 * WS], q7 = p[7 * WS];
       p += 8 * WS;
-      acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
-      acc2.x += q4.x; acc2.y += q4.y; acc2.z += q4.z; acc2.w += q4.w;
-      acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
-      acc2.x += q5.x; acc2.y += q5.y; acc2.z += q5.z; acc2.w += q5.w;
-      acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
-      acc2.x += q6.x; acc2.y += q6.y; acc2.z += q6.z; acc2.w += q6.w;
-      acc.x += q3.x; acc.y += q3.y; acc.z += q3.z; acc.w += q3.w;
-      acc2.x += q7.x; acc2.y += q7.y; acc2.z += q7.z; acc2.w += q7.w;
+      UD_ACC(aL, aH, q0) UD_ACC(bL, bH, q4) UD_ACC(aL, aH, q1) UD_ACC(bL, bH, q5)
+      UD_ACC(aL, aH, q2) UD_ACC(bL, bH, q6) UD_ACC(aL, aH, q3) UD_ACC(bL, bH, q7)
     }
     if (left >= 4) {
       const float4 q0 = p[0], q1 = p[WS], q2 = p[2 * WS], q3 = p[3 * WS];
       p += 4 * WS;
       left -= 4;
-      acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
-      acc2.x += q1.x; acc2.y += q1.y; acc2.z += q1.z; acc2.w += q1.w;
-      acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
-      acc2.x += q3.x; acc2.y += q3.y; acc2.z += q3.z; acc2.w += q3.w;
+      UD_ACC(aL, aH, q0) UD_ACC(bL, bH, q1) UD_ACC(aL, aH, q2) UD_ACC(bL, bH, q3)
     }
     for (; left > 0; --left) {
       const float4 q0 = *p;
       p += WS;
-      acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
+      UD_ACC(aL, aH, q0)
     }
-    acc.x += acc2.x; acc.y += acc2.y; acc.z += acc2.z; acc.w += acc2.w;
+#undef UD_ACC
+    aL = __fadd2_rn(aL, bL);
+    aH = __fadd2_rn(aH, bH);
+    float4 acc = make_float4(aL.x, aL.y, aH.x, aH.y);
     acc.w *= wscale;   // P2G stages the bare weight in .w: p_mass is applied once per (segment, node), not per particle
     if (DET) {  // UD_P2G_DETERMINISTIC: 4 integer REDs on 64-bit fixed point (associative => order-independent)
       unsigned long long* acc64 = reinterpret_cast<unsigned long long*>(genv) + 4 * (size_t)cell;
