@@ -466,7 +466,15 @@ constexpr int P2G_BLOCK = 64;    // threads (= particles) per CTA of k_p2g: with
 constexpr int G2PB_BLOCK = UD_BLOCK;  // k_g2p_bwd: one window of 27 nodes, 108 flush lanes of 128 (two windows cost it registers)
 constexpr int P2G_NPH = 14;      // nodes per staging window of k_p2g (27 nodes -> 2 windows)
 constexpr int G2PB_NPH = 27;
-constexpr int G2P_TILE_CELLS = 4;    // distinct base cells per warp whose stencils k_g2p keeps in shared memory
+// float4 slots between the cells of a node tile: 33 (528 B), not 32, so that lanes in DIFFERENT cells reading the same
+// node hit different banks (32 puts node j of every cell in the same four banks: an nseg-way conflict on each of the 27
+// stencil loads; measured k_g2p 50.4 -> 46.0 us).  Only slots 0..26 of a cell are used, so 4 cells still fit in 4 * 32.
+#ifndef UD_NT_STRIDE
+#define UD_NT_STRIDE 33
+#endif
+constexpr int NT_STRIDE = UD_NT_STRIDE;
+constexpr int G2P_TILE_CELLS = 4;
+static_assert((G2P_TILE_CELLS - 1) * NT_STRIDE + 27 <= G2P_TILE_CELLS * 32, "node tile: the padded cells must fit");    // distinct base cells per warp whose stencils k_g2p keeps in shared memory
 constexpr int G2PB_TILE_RUNS = 12;  // segments whose 27 grid velocities k_g2p_bwd keeps in shared memory (5.2 KB: the CTA
                                     // stays at 4 per SM); CTAs with more distinct cells gather from L1/L2 as before
 constexpr size_t g2pb_tile_offset() { return (stage_smem_bytes<G2PB_BLOCK>(3, G2PB_NPH) + 15) & ~(size_t)15; }
@@ -1078,7 +1086,7 @@ __device__ __forceinline__ bool warp_tile_fill(const MpmConst& k, const float4* 
     }
 #pragma unroll
     for (int ge = 0; ge < G2P_TILE_CELLS; ++ge)
-      if (ge < ngroups) tile[ge * 32 + lane] = tmp[ge];
+      if (ge < ngroups && lane < 27) tile[ge * NT_STRIDE + lane] = tmp[ge];
     __syncwarp();
   }
   return tiled;
@@ -1096,7 +1104,7 @@ __device__ __forceinline__ void g2p_gather(const MpmConst& k, const float4* __re
   for (int c = 0; c < 3; ++c) nv[c] = 0.f;
   nC = mat_zero();
   if (!live) return;
-  const float4* my_tile = tile + gid * 32;
+  const float4* my_tile = tile + gid * NT_STRIDE;
   float Xa[3] = {0.f, 0.f, 0.f}, Xb[3] = {0.f, 0.f, 0.f}, Xc[3] = {0.f, 0.f, 0.f};
   auto nodes = [&](auto tiled_tag) {
     constexpr bool TILED = decltype(tiled_tag)::value;
@@ -1482,10 +1490,10 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
     }
 #pragma unroll
     for (int ge = 0; ge < G2PBW_CELLS; ++ge)
-      if (ge < nseg) vtile[ge * 32 + lane] = tmp[ge];
+      if (ge < nseg && lane < 27) vtile[ge * NT_STRIDE + lane] = tmp[ge];
     __syncwarp();
   }
-  const float4* my_tile = vtile + my_seg * 32;
+  const float4* my_tile = vtile + my_seg * NT_STRIDE;
   const float lw = live_ ? 1.f : 0.f;
   const float c4 = 4.f * k.inv_dx;
   // r(a,b,c) = gv' + 4 inv_dx gC' (off - fx) = r0 + a K0 + b K1 + c K2   (K_j = 4 inv_dx * column j of gC')
@@ -1630,7 +1638,7 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     __syncwarp();   // every lane is done with the previous tile's node tile
     tiled = warp_tile_fill<false>(k, ggrid + (size_t)env * k.G, s0.base, live_, wtile[threadIdx.x >> 5], &tile_gid);
   }
-  const float4* my_tile = wtile[threadIdx.x >> 5] + tile_gid * 32;
+  const float4* my_tile = wtile[threadIdx.x >> 5] + tile_gid * NT_STRIDE;
   if (live_) {
     // Phase 1: everything the 27-node gather needs is the stencil, A = dx * affine and u0.  The matrices that
     // produce them (C, F, U, s, Vt, F1, F2, D: ~80 registers) die here and are loaded again (L2 hits) for the
