@@ -474,6 +474,19 @@ constexpr int G2PB_NPH = 27;
 #endif
 constexpr int NT_STRIDE = UD_NT_STRIDE;
 constexpr int G2P_TILE_CELLS = 4;
+// One-tile-per-warp kernels: every warp asks L2 for the quads a warp one wave of CTAs later will load first (the CTAs
+// are dispatched in tile order), so that warp's first dependent load is an L2 hit instead of a DRAM round trip.
+// Measured: k_g2p_bwd_warp 113.5 -> 110.5 us; nothing for k_g2p (45.8 / 45.9), where it is not used.
+#ifndef UD_AHEAD_TILES
+#define UD_AHEAD_TILES (148 * 32)
+#endif
+template <int Q0, int Q1, int NQ>
+__device__ __forceinline__ void ahead_prefetch(const MpmConst& k, const float* __restrict__ base, int gp) {
+  if (UD_AHEAD_TILES > 0) {
+    const int gpa = gp + UD_AHEAD_TILES * 32;
+    if (gpa < k.N_pad) prefetch_quads<Q0, Q1, NQ>(base, gpa);
+  }
+}
 static_assert((G2P_TILE_CELLS - 1) * NT_STRIDE + 27 <= G2P_TILE_CELLS * 32, "node tile: the padded cells must fit");    // distinct base cells per warp whose stencils k_g2p keeps in shared memory
 constexpr int G2PB_TILE_RUNS = 12;  // segments whose 27 grid velocities k_g2p_bwd keeps in shared memory (5.2 KB: the CTA
                                     // stays at 4 per SM); CTAs with more distinct cells gather from L1/L2 as before
@@ -859,6 +872,29 @@ __device__ __forceinline__ void warp_mark_blocks(const MpmConst& k, const WarpGr
   }
 }
 
+// Stages one particle's 27 node values {wt (u + a Ac0 + b Ac1 + c Ac2), wt} (.w: the bare weight) into its tile row.
+// (Carrying the value as the fp32x2 pairs (x, y), (z, 1) -- FMUL2 / FFMA2 -- was measured slower: the register-pair moves
+// eat the saved issue slots, 128.1 vs 126.0 us per launch, profiles/r02_run22.sh.)
+__device__ __forceinline__ void p2g_stage_row(const Stencil& st, const float u[3], const float Ac[3][3], float lw,
+                                              float4* __restrict__ myrow) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float wa = st.w[a][0] * lw;
+    const float ua[3] = {u[0] + (float)a * Ac[0][0], u[1] + (float)a * Ac[0][1], u[2] + (float)a * Ac[0][2]};
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const float wab = wa * st.w[b][1];
+      const float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float wt = wab * st.w[c][2];
+        myrow[a * 9 + b * 3 + c] = make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
+                                               wt * (uab[2] + (float)c * Ac[2][2]), wt);   // .w: bare weight
+      }
+    }
+  }
+}
+
 constexpr int P2GW_BLOCK = 128;   // 4 independent warps per CTA (the CTA is only the unit shared memory is carved in)
 constexpr int P2GW_MIN_BLOCKS = 4;  // resident CTAs per SM = what the 14 KB staging tile per warp leaves room for
 // One tile (32 particles) per warp, one CTA per 4 tiles: the A/B partner of k_p2g_pers (ud_tuning_set("pers", 0)).
@@ -883,22 +919,7 @@ k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
     float4* myrow = tile + wg.row * WARP_TILE_NODES;
     const float lw = live_ ? 1.f : 0.f;
     __syncwarp();   // (persistent kernel: every lane has left the previous tile's flush)
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float wa = st.w[a][0] * lw;
-      const float ua[3] = {u[0] + (float)a * Ac[0][0], u[1] + (float)a * Ac[0][1], u[2] + (float)a * Ac[0][2]};
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        const float wab = wa * st.w[b][1];
-        const float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float wt = wab * st.w[c][2];
-          myrow[a * 9 + b * 3 + c] = make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
-                                                 wt * (uab[2] + (float)c * Ac[2][2]), wt);   // .w: bare weight
-        }
-      }
-    }
+    p2g_stage_row(st, u, Ac, lw, myrow);
     __syncwarp();
     warp_flush<false, DET>(k, tile, seg, wg, st.base, genv, k.p_mass);
     warp_mark_blocks(k, wg, st.base, live_, bl, env);
@@ -947,22 +968,7 @@ k_p2g_pers(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
     float4* myrow = tile + wg.row * WARP_TILE_NODES;
     const float lw = live_ ? 1.f : 0.f;
     __syncwarp();   // (persistent kernel: every lane has left the previous tile's flush)
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float wa = st.w[a][0] * lw;
-      const float ua[3] = {u[0] + (float)a * Ac[0][0], u[1] + (float)a * Ac[0][1], u[2] + (float)a * Ac[0][2]};
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        const float wab = wa * st.w[b][1];
-        const float uab[3] = {ua[0] + (float)b * Ac[1][0], ua[1] + (float)b * Ac[1][1], ua[2] + (float)b * Ac[1][2]};
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float wt = wab * st.w[c][2];
-          myrow[a * 9 + b * 3 + c] = make_float4(wt * (uab[0] + (float)c * Ac[2][0]), wt * (uab[1] + (float)c * Ac[2][1]),
-                                                 wt * (uab[2] + (float)c * Ac[2][2]), wt);   // .w: bare weight
-        }
-      }
-    }
+    p2g_stage_row(st, u, Ac, lw, myrow);
     __syncwarp();
     warp_flush<false, DET>(k, tile, seg, wg, st.base, genv, k.p_mass);
     warp_mark_blocks(k, wg, st.base, live_, bl, env);
@@ -1464,6 +1470,8 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
   float x[3], gxo[3], gvt[3];
   Mat3 gC;
   g2pb_load(k, ps_in, gs, gp, x, gxo, gvt, gC);
+  ahead_prefetch<0, 0, PS_NQ>(k, ps_in, gp);
+  ahead_prefetch<0, 3, PS_NQ>(k, gs, gp);
   Stencil st;
   make_stencil(x, k.inv_dx, st);
   const WarpGroup wg = warp_group(k, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base, live_, seg);
