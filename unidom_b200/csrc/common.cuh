@@ -430,8 +430,11 @@ UD_DEV Mat3 svd3_bwd_rotated(const Mat3& U, const float s[3], const Mat3& Vt, co
       if (i == j) {
         M(i, j) = dS[i];
       } else {
-        float Fij = safe_inv(s2[j] - s2[i]);
-        float Fji = safe_inv(s2[i] - s2[j]);
+        // safe_inv is odd and fp subtraction anti-commutes exactly: F_ji = -F_ij bit for bit, so each of the three
+        // index pairs costs ONE IEEE division (the two calls as written are 6 distinct divisions after CSE)
+        const int lo = i < j ? i : j, hi = i < j ? j : i;
+        const float f = safe_inv(s2[hi] - s2[lo]);   // F_{lo,hi}
+        const float Fij = i < j ? f : -f, Fji = -Fij;
         float Jsym = Fij * UtdU(i, j) + Fji * UtdU(j, i);
         float Ksym = Fij * VdV(i, j) + Fji * VdV(j, i);
         // (J+J^T)*S broadcasts S over the last axis (column j); (U*S) scales column i of U,

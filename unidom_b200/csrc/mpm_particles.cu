@@ -34,6 +34,12 @@ static inline dim3 pgrid(const MpmConst& k, int block) { return dim3(cdiv(k.n, b
 // tiles w, w + W, w + 2W, ... (W = warps in the grid), prefetching its next tile while it computes the current one.
 struct TileWalk {
   int lane, nwarps, tpe, ntiles, t;   // tpe = tiles per env; t = current tile (global over envs)
+  int dq, dr;                         // nwarps = dq * tpe + dr: the walk's stride in (env, tile of env) coordinates
+};
+// a tile as (env, tile of the env): the walk advances it by additions (an integer division per tile and per lookahead
+// was 4 % of k_p2g_pers' instructions and of its stall samples)
+struct TilePos {
+  int t, env, rem;
 };
 __device__ __forceinline__ TileWalk tile_walk(const MpmConst& k) {
   TileWalk w;
@@ -42,12 +48,32 @@ __device__ __forceinline__ TileWalk tile_walk(const MpmConst& k) {
   w.tpe = k.n_pad >> 5;
   w.ntiles = k.B * w.tpe;
   w.t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  w.dq = w.nwarps / w.tpe;
+  w.dr = w.nwarps - w.dq * w.tpe;
   return w;
 }
-// particle of this lane in tile t: env, g = index into per-particle arrays, gp = index into the sorted tile arrays
-__device__ __forceinline__ void tile_locate(const MpmConst& k, const TileWalk& w, int t, int& env, int& g, int& gp, bool& live) {
-  env = t / w.tpe;
-  const int slot = (t - env * w.tpe) * 32 + w.lane;
+__device__ __forceinline__ TilePos tile_first(const TileWalk& w) {
+  TilePos p;
+  p.t = w.t;
+  p.env = w.t / w.tpe;
+  p.rem = w.t - p.env * w.tpe;
+  return p;
+}
+__device__ __forceinline__ TilePos tile_next(const TileWalk& w, TilePos p) {
+  p.t += w.nwarps;
+  p.env += w.dq;
+  p.rem += w.dr;
+  if (p.rem >= w.tpe) {
+    p.rem -= w.tpe;
+    ++p.env;
+  }
+  return p;
+}
+// particle of this lane in tile p: env, g = index into per-particle arrays, gp = index into the sorted tile arrays
+__device__ __forceinline__ void tile_locate(const MpmConst& k, const TileWalk& w, const TilePos& p, int& env, int& g, int& gp,
+                                            bool& live) {
+  env = p.env;
+  const int slot = p.rem * 32 + w.lane;
   live = slot < k.n;
   g = env * k.n + (live ? slot : 0);
   gp = env * k.n_pad + slot;
@@ -943,21 +969,23 @@ k_p2g_pers(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
   if (w.t >= w.ntiles) return;
   const bool warm = vt_in != nullptr, vt_svd = vt_svd_i != 0;
   P2gIn nx;
+  TilePos pos = tile_first(w);
   {
     int env, g, gp;
     bool live;
-    tile_locate(k, w, w.t, env, g, gp, live);
+    tile_locate(k, w, pos, env, g, gp, live);
     p2g_issue_loads(env, g, gp, ps_in, mu_s, la_s, mat_s, h_s, vt_in, vt_svd, nx);
   }
-  for (int t = w.t; t < w.ntiles; t += w.nwarps) {
+  for (; pos.t < w.ntiles;) {
     int env, g, gp;
     bool live_;
-    tile_locate(k, w, t, env, g, gp, live_);
+    tile_locate(k, w, pos, env, g, gp, live_);
     const P2gIn cur = nx;
-    if (t + w.nwarps < w.ntiles) {
+    pos = tile_next(w, pos);
+    if (pos.t < w.ntiles) {
       int e2, g2, gp2;
       bool l2;
-      tile_locate(k, w, t + w.nwarps, e2, g2, gp2, l2);
+      tile_locate(k, w, pos, e2, g2, gp2, l2);
       p2g_issue_loads(e2, g2, gp2, ps_in, mu_s, la_s, mat_s, h_s, vt_in, vt_svd, nx);
     }
     Stencil st;
@@ -1048,7 +1076,8 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
 // Per-warp node tile.  The 32 particles of a warp sit in a few cells (sorted order), so the warp fetches the 27 grid
 // values of each DISTINCT base cell once (<= G2P_TILE_CELLS cells; all loads are issued before the first one is
 // consumed: one L2 round trip, no block barrier) into `tile` [G2P_TILE_CELLS][32] and every lane reads its stencil from
-// shared memory; warps spanning more cells gather from L1/L2.  CLAMP: gather rule (clamped indices); otherwise the
+// shared memory; warps spanning more cells gather from L1/L2.  (Sending an interior cell as one shuffle of its linear
+// index instead of three + the index rules was measured slower in k_g2p, 46.0 -> 49.5 us: spills at its 64 registers.)  CLAMP: gather rule (clamped indices); otherwise the
 // scatter rule's transpose (dropped nodes read as zero).  Returns false (warp-uniform) when the warp spans more cells
 // than the tile holds; *gid = index of my cell in the tile.  All lanes of the warp must call it.
 template <bool CLAMP>
@@ -1615,28 +1644,32 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
   float4 nxq;
   int nmat;
   float nh;
-  auto issue = [&](int t) {
+  auto issue = [&](const TilePos& tp) {
     int e2, g2, gp2;
     bool l2;
-    tile_locate(k, w, t, e2, g2, gp2, l2);
+    tile_locate(k, w, tp, e2, g2, gp2, l2);
     nxq = reinterpret_cast<const float4*>(ps_in)[quad_index(gp2, 0, PS_NQ)];
     nmat = mat_s[g2];
     nh = h_s[g2];
+    // (one cp.async.bulk.prefetch.L2 per contiguous range from one lane instead of these 15 per-lane prefetches was
+    // measured slower: 143.6 vs 141.3 us per launch)
     prefetch_quads<1, 5, PS_NQ>(ps_in, gp2);
     prefetch_quads<0, 5, SV_NQ>(svd_in, gp2);
     prefetch_quads<0, 0, PS_NQ>(gs, gp2);
     prefetch_quads<3, 5, PS_NQ>(gs, gp2);
   };
-  issue(w.t);
-  for (int t = w.t; t < w.ntiles; t += w.nwarps) {
+  TilePos pos = tile_first(w);
+  issue(pos);
+  for (; pos.t < w.ntiles;) {
   int env, g, gp;
   bool live_;
-  tile_locate(k, w, t, env, g, gp, live_);
+  tile_locate(k, w, pos, env, g, gp, live_);
   float gmu = 0.f, gla = 0.f, gn2 = 0.f;
   const int mat_p = nmat;
   const float h_p = nh, mu_e = mu_s[env], la_e = la_s[env];
   const float x0[3] = {nxq.x, nxq.y, nxq.z};
-  if (t + w.nwarps < w.ntiles) issue(t + w.nwarps);
+  pos = tile_next(w, pos);
+  if (pos.t < w.ntiles) issue(pos);
   // the cotangents of the 27 nodes of each distinct base cell of the warp, fetched once per warp (dropped nodes = 0)
   int tile_gid = 0;
   bool tiled;
