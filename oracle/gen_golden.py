@@ -425,6 +425,24 @@ def cloth_env_para_case(name, B, seed, it):
           f"g_stiffness={out['g_stiffness']}")
 
 
+F64 = False   # --f64: the env cases once more in float64 FROM THE FIXTURE'S INPUTS -> ref_mpmenv_<name>_f64.npz.  The gap
+              # between the fp32 fixture and this run is the fp32 noise of the UNMODIFIED reference itself on that rollout:
+              # the floor the env-level GPU tests print and scale their bars with (tests/util.py::env_floor).
+
+
+def _f64_override(name, st, jnp):
+    """fp64 run: start from exactly the state the fp32 fixture started from."""
+    import torch
+    d = np.load(os.path.join(GOLD, f"ref_mpmenv_{name}.npz"))
+    rep = {k: jnp.array(torch.from_numpy(d["in_" + k]).double()) for k in ("x", "v", "C", "F", "J") if "in_" + k in d}
+    prims = list(st.primitives)
+    for q in range(len(prims)):
+        if f"in_prim{q}_pos" in d:
+            prims[q] = prims[q]._replace(position=jnp.array(torch.from_numpy(d[f"in_prim{q}_pos"]).double()),
+                                         rotation=jnp.array(torch.from_numpy(d[f"in_prim{q}_rot"]).double()))
+    return st._replace(primitives=prims, **rep), d["actions"].astype(np.float64)
+
+
 def mpm_env_case(name, B, density, seed):
     """Env level for MPM: the reference's push task (envs/shape_elasto_plastic.py: ShapeRopeEnv.step_diff = focus
     shift, get_primitive_actions, 20 sub-actions x 16 substeps, reward e^(-10 l2) + e^(-contact)) on a reduced
@@ -435,6 +453,8 @@ def mpm_env_case(name, B, density, seed):
     import torch
     import jax
     import jax.numpy as jnp
+    if F64:
+        jax.set_float(torch.float64)
     from daxbench.core.envs import shape_elasto_plastic as sep
     from daxbench.core.engine.primitives.primitives import set_sdf
     from daxbench.core.engine.primitives.box import _sdf_batch as box_sdf
@@ -459,6 +479,10 @@ def mpm_env_case(name, B, density, seed):
                      for b in range(B)]).astype(np.float32)
     out = {"goal": goal, "actions": acts, "density": np.array(density), "in_x": x0,
            "material": np.asarray(env.simulator.material).astype(np.int32), "h": np.asarray(env.simulator.h).astype(np.float32)}
+    if F64:
+        st, acts = _f64_override(name, st, jnp)
+        env.goal = jnp.array(torch.from_numpy(np.load(os.path.join(GOLD, f"ref_mpmenv_{name}.npz"))["goal"]).double())
+        out = {}
     a = torch.from_numpy(acts).requires_grad_(True)
     obs, reward, done, info = env.step_diff(jax.Array(a), st)
     ns = info["state"]
@@ -466,7 +490,7 @@ def mpm_env_case(name, B, density, seed):
     out.update({"reward": reward.t.detach().numpy(), "g_actions": ga.numpy(), "out_x": np.asarray(ns.x.t.detach()),
                 "out_v": np.asarray(ns.v.t.detach()), "out_F": np.asarray(ns.F.t.detach()),
                 "out_prim_pos": np.asarray(ns.primitives[0].position.t.detach()), "obs": np.asarray(obs.t.detach())})
-    path = os.path.join(GOLD, f"ref_mpmenv_{name}.npz")
+    path = os.path.join(GOLD, f"ref_mpmenv_{name}{'_f64' if F64 else ''}.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: n={n} B={B} reward={out['reward']} |g_actions|max={np.abs(out['g_actions']).max():.3e}")
 
@@ -486,6 +510,9 @@ def task_env_case(name, B, seed, steps=2):  # noqa: C901
     stubs.install()
     import torch
     import jax
+    import jax.numpy as jnp
+    if F64:
+        jax.set_float(torch.float64)
     rng = np.random.RandomState(seed)
     if name == "rope":
         from daxbench.core.envs import shape_rope_env as mod
@@ -515,6 +542,9 @@ def task_env_case(name, B, seed, steps=2):  # noqa: C901
     for q, prim in enumerate(st.primitives):
         out[f"in_prim{q}_pos"] = np.asarray(prim.position)
         out[f"in_prim{q}_rot"] = np.asarray(prim.rotation)
+    if F64:
+        st, acts = _f64_override(name, st, jnp)
+        out = {}
     a = torch.from_numpy(acts).requires_grad_(True)
     total, s = 0, st
     for t in range(steps):
@@ -530,7 +560,7 @@ def task_env_case(name, B, seed, steps=2):  # noqa: C901
     (ga,) = torch.autograd.grad(total, [a])
     out["g_actions"] = ga.numpy()
     out["obs"] = np.asarray(obs.t.detach())
-    path = os.path.join(GOLD, f"ref_mpmenv_{name}.npz")
+    path = os.path.join(GOLD, f"ref_mpmenv_{name}{'_f64' if F64 else ''}.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: n={st.x.shape[1]} B={B} rewards={[out[f'reward{t}'] for t in range(steps)]} "
           f"|g_actions|max={np.abs(out['g_actions']).max():.3e}")
@@ -540,7 +570,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--real-jax", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--f64", action="store_true", help="mpmenv_* cases only: the fp64 floor files (see F64 above)")
     args = ap.parse_args()
+    global F64
+    F64 = args.f64
     mods = load_reference(args.real_jax)
     os.makedirs(GOLD, exist_ok=True)
     cases = {
@@ -573,6 +606,8 @@ def main():
     cases["clothenv_ep3"] = lambda: cloth_env_case("ep3", 3, 4, 0)
     for name, fn in cases.items():
         if args.only and args.only not in name:
+            continue
+        if F64 and not name.startswith("mpmenv_"):
             continue
         fn()
 

@@ -30,11 +30,16 @@ def test_mpm_cuda_matches_reference_golden(built_lib, name):
                                          lambda t: t.to(dev))
     else:
         out, _ = sim.step_jax(st, act)
-    bowl = conf.sdf_kind == 1
+    # north_star bars: state rtol 1e-4; gradients rtol 1e-3 and cosine >= 0.999.  A looser bound is only ever K x the
+    # MEASURED fp32-vs-fp64 floor of the reference arithmetic on this very case (util.golden_mpm_floor; e.g. the two
+    # bowls' finite-difference normals flip a collider branch in fp32: floor 1.3e-3 on v, up to 1.3e-2 on gradients)
+    fl_state, fl_grad = util.golden_mpm_floor(name)
+    K_FLOOR = 4.0
     for k in ("x", "v", "C", "F", "J"):
         e = util.rel_err(getattr(out, k), d["out_" + k])
-        print(f"{name} state {k}: cuda-vs-reference rel {e:.3e}")
-        assert e < (2e-3 if bowl else 1e-4), (k, e)      # north_star: state rtol 1e-4 (bowl: see test_oracle_golden)
+        bar = max(1e-4, K_FLOOR * fl_state[k])
+        print(f"{name} state {k}: cuda-vs-reference rel {e:.3e}  fp32 floor {fl_state[k]:.1e}  bar {bar:.1e}")
+        assert e < bar, (k, e, bar)
     for q in range(conf.n_primitive):
         for k in ("position", "rotation", "v", "w", "action_buffer"):
             e = util.rel_err(getattr(out.primitives[q], k), d[f"out_p{q}_{k}"])
@@ -49,9 +54,11 @@ def test_mpm_cuda_matches_reference_golden(built_lib, name):
             assert float(g.abs().max()) < 1e-10, k
             continue
         e, cs = util.rel_err(g, ref), util.cosine(g, ref)
-        print(f"{name} grad {k:16s}: rel {e:.3e} cos {cs:.8f} max|ref| {float(ref.abs().max()):.3e}")
-        assert cs >= 0.999, (k, cs)                       # north_star: gradients rtol 1e-3, cosine >= 0.999
-        assert e < (1e-2 if bowl else 3e-3), (k, e)
+        bar = max(1e-3, K_FLOOR * fl_grad.get(k, 0.0))
+        print(f"{name} grad {k:16s}: rel {e:.3e} cos {cs:.8f} max|ref| {float(ref.abs().max()):.3e}  fp32 floor "
+              f"{fl_grad.get(k, 0.0):.1e}  bar {bar:.1e}")
+        assert cs >= 0.999, (k, cs)
+        assert e < bar, (k, e, bar)
 
 
 @pytest.mark.parametrize("name", CLOTH_CASES)

@@ -93,17 +93,19 @@ def test_multi_step_episode_parity(built_lib):
     n = st.x.shape[1]
     st = st._replace(C=torch.zeros_like(st.C), F=torch.eye(3, device=st.x.device).expand(B, n, 3, 3).contiguous())
     act = torch.tensor([[0.0, 0.0, 0.6, 0, 0, 0], [0.3, 0.0, 0.5, 0, 0, 0.2]], device=st.x.device)
-    s_gpu, s_ref = st, util.to_oracle_state(st)
+    s_gpu, s_ref, s_ref64 = st, util.to_oracle_state(st), util.to_oracle_state(st, torch.float64)
     osim = omp.Simulator(util.oracle_conf(conf), sim.material.clone(), sim.h.clone())
+    osim64 = omp.Simulator(util.oracle_conf(conf), sim.material.clone(), sim.h.clone().double(), dtype=torch.float64)
     for it in range(6):
         s_gpu, _ = sim.step_jax(s_gpu, act)
         s_ref = omp.step_batch(osim, s_ref, act.cpu())
+        s_ref64 = omp.step_batch(osim64, s_ref64, act.cpu().double())
     for k in ("x", "v", "C", "F"):
         e = util.rel_err(getattr(s_gpu, k), getattr(s_ref, k))
-        print(f"episode {k}: {e:.3e}")
-    assert util.rel_err(s_gpu.x, s_ref.x) < 1e-4
-    assert util.rel_err(s_gpu.F, s_ref.F) < 1e-4
-    assert util.rel_err(s_gpu.v, s_ref.v) < 2e-3   # velocities: see DESIGN.md (noise floor printed above)
+        fl = util.rel_err(getattr(s_ref, k), getattr(s_ref64, k))   # fp32 noise of the reference arithmetic over the episode
+        bar = util.floor_bar(1e-4, fl)
+        print(f"episode {k}: cuda-vs-oracle32 {e:.3e}   oracle32-vs-oracle64 (floor) {fl:.3e}   bar {bar:.1e}")
+        assert e < bar, (k, e, bar)                                   # north_star: state rtol 1e-4
 
 
 def _leaf_list(state, n_prim):

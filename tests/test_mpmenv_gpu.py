@@ -24,10 +24,13 @@ def test_push_env_step_and_action_gradient_vs_reference(built_lib):
     obs, reward, done, info = env.step_diff(a, st)
     ns = info["state"]
     (ga,) = torch.autograd.grad(reward.sum(), [a])
+    # Bars: north_star's (state rtol 1e-4, gradients rtol 1e-3 / cosine 0.999), or K x the fp32 noise of the unmodified
+    # reference on this very rollout (fp32 fixture vs the same run in fp64, util.env_floor) where that is higher.
+    fl = util.env_floor("push")
     for k, ref in (("x", d["out_x"]), ("v", d["out_v"]), ("F", d["out_F"])):
-        e = util.rel_err(getattr(ns, k), ref)
-        print(f"mpm env push {k}: cuda-vs-reference rel {e:.3e}")
-        assert e < (1e-4 if k != "v" else 2e-3), (k, e)                 # 320 substeps; v: see test_multi_step_episode_parity
+        e, bar = util.rel_err(getattr(ns, k), ref), util.floor_bar(1e-4, fl("out_" + k))
+        print(f"mpm env push {k}: cuda-vs-reference rel {e:.3e}  reference fp32-vs-fp64 floor {fl('out_' + k):.1e}  bar {bar:.1e}")
+        assert e < bar, (k, e, bar)
     assert util.rel_err(ns.primitives[0].position, d["out_prim_pos"]) < 1e-5
     er = util.rel_err(reward, d["reward"])
     print(f"mpm env push reward {reward.tolist()} ref {d['reward'].tolist()} rel {er:.3e}")
@@ -52,7 +55,9 @@ def test_push_env_step_and_action_gradient_vs_reference(built_lib):
         assert cs >= 0.999 and eg < 1e-3, (b, cs, eg)                      # north_star bar
         compared += 1
     assert compared >= 1
-    assert util.rel_err(obs, d["obs"]) < 2e-3
+    eo = util.rel_err(obs, d["obs"])                                      # obs carries the velocities
+    print(f"mpm env push obs: rel {eo:.3e}  floor {fl('obs'):.1e}")
+    assert eo < util.floor_bar(1e-4, fl("obs"))
 
 
 def test_whip_rope_env_two_steps_vs_reference(built_lib):
@@ -73,6 +78,7 @@ def test_whip_rope_env_two_steps_vs_reference(built_lib):
     assert float(base.abs().max()) < 1e-6                               # same rope lattice up to the shift
     st = st._replace(x=d["in_x"].to(env.device), primitives=[p])
     a = d["actions"].to(env.device).requires_grad_(True)
+    fl = util.env_floor("whip")      # fp32 noise of the unmodified reference on this rollout (fp32 fixture vs fp64 run)
     total, s = 0, st
     for t in range(2):
         obs, reward, done, info = env.step_diff(a[t], s)
@@ -80,14 +86,15 @@ def test_whip_rope_env_two_steps_vs_reference(built_lib):
         total = total + reward.sum()
         ex, ev = util.rel_err(s.x, d[f"x{t}"]), util.rel_err(s.v, d[f"v{t}"])
         er = util.rel_err(reward, d[f"reward{t}"])
-        print(f"whip env step {t}: x rel {ex:.3e} v rel {ev:.3e} reward {reward.tolist()} ref {d[f'reward{t}'].tolist()} rel {er:.3e}")
-        assert ex < 1e-4 and ev < 2e-3 and er < 1e-4
+        print(f"whip env step {t}: x rel {ex:.3e} (floor {fl(f'x{t}'):.1e}) v rel {ev:.3e} (floor {fl(f'v{t}'):.1e}) "
+              f"reward {reward.tolist()} ref {d[f'reward{t}'].tolist()} rel {er:.3e}")
+        assert ex < util.floor_bar(1e-4, fl(f"x{t}")) and ev < util.floor_bar(1e-4, fl(f"v{t}")) and er < 1e-4
         assert util.rel_err(s.primitives[0].position, d[f"prim0_pos{t}"]) < 1e-5
     (ga,) = torch.autograd.grad(total, [a])
     cs, eg = util.cosine(ga, d["g_actions"]), util.rel_err(ga, d["g_actions"])
-    print(f"whip env action gradient cos {cs:.6f} rel {eg:.3e}")
+    print(f"whip env action gradient cos {cs:.6f} rel {eg:.3e}  floor {fl('g_actions'):.1e}")
     assert cs >= 0.999 and eg < 1e-3
-    assert util.rel_err(obs, d["obs"]) < 2e-3
+    assert util.rel_err(obs, d["obs"]) < util.floor_bar(1e-4, fl("obs"))
 
 
 def test_pour_water_env_two_steps_vs_reference(built_lib):
@@ -104,6 +111,7 @@ def test_pour_water_env_two_steps_vs_reference(built_lib):
              for q, p in enumerate(st.primitives)]
     st = st._replace(x=d["in_x"].to(env.device), primitives=prims)
     a = d["actions"].to(env.device).requires_grad_(True)
+    fl = util.env_floor("pour")      # fp32 noise of the unmodified reference on this rollout (fp32 fixture vs fp64 run)
     total, s = 0, st
     for t in range(2):
         obs, reward, done, info = env.step_diff(a[t], s)
@@ -111,21 +119,23 @@ def test_pour_water_env_two_steps_vs_reference(built_lib):
         total = total + reward.sum()
         ex, ev = util.rel_err(s.x, d[f"x{t}"]), util.rel_err(s.v, d[f"v{t}"])
         er = util.rel_err(reward, d[f"reward{t}"])
-        print(f"pour env step {t}: x rel {ex:.3e} v rel {ev:.3e} reward {reward.tolist()} ref {d[f'reward{t}'].tolist()} rel {er:.3e}")
+        print(f"pour env step {t}: x rel {ex:.3e} (floor {fl(f'x{t}'):.1e}) v rel {ev:.3e} (floor {fl(f'v{t}'):.1e}) "
+              f"reward {reward.tolist()} ref {d[f'reward{t}'].tolist()} rel {er:.3e}")
         # v: the bowl's finite-difference normals (d = 1e-6 in fp32, primitives.py:129-143) quantise to a few ulps of
-        # the SDF, so particles touching the bowl carry that noise in v (the oracle-vs-reference golden shows the same)
-        assert ex < 1e-4 and ev < 1e-2 and er < 1e-4
+        # the SDF, so particles touching the bowl carry that noise in v -- in the reference's own fp32 run as well:
+        # the bar is K x the measured fp32-vs-fp64 gap of the reference
+        assert ex < util.floor_bar(1e-4, fl(f"x{t}")) and ev < util.floor_bar(1e-4, fl(f"v{t}")) and er < 1e-4
         for q in range(2):
             assert util.rel_err(s.primitives[q].position, d[f"prim{q}_pos{t}"]) < 1e-5
             assert util.rel_err(s.primitives[q].rotation, d[f"prim{q}_rot{t}"]) < 1e-5
     (ga,) = torch.autograd.grad(total, [a])
     cs, eg = util.cosine(ga, d["g_actions"]), util.rel_err(ga, d["g_actions"])
     print(f"pour env action gradient cos {cs:.6f} rel {eg:.3e}  max|ref| {float(d['g_actions'].abs().max()):.3e}")
-    # cosine meets the north_star bar; the max-norm error is 2-3e-3: the action gradient reaches the liquid only
-    # through the bowl collider, whose normals are fp32 central differences with d = 1e-6 (a few ulps of the SDF), so
-    # two correct fp32 evaluations of the same formulas differ at this level ("Numerics")
-    assert cs >= 0.999 and eg < 5e-3
-    assert util.rel_err(obs, d["obs"]) < 2e-3
+    # the action gradient reaches the liquid only through the bowl collider, whose normals are fp32 central differences
+    # with d = 1e-6 (a few ulps of the SDF): two fp32 evaluations of the same formulas differ at the printed floor
+    print(f"pour env action gradient: reference fp32-vs-fp64 floor {fl('g_actions'):.1e}  bar {util.floor_bar(1e-3, fl('g_actions')):.1e}")
+    assert cs >= 0.999 and eg < util.floor_bar(1e-3, fl("g_actions"))
+    assert util.rel_err(obs, d["obs"]) < util.floor_bar(1e-4, fl("obs"))
 
 
 def test_shape_rope_env_step_vs_reference(built_lib):
@@ -149,13 +159,15 @@ def test_shape_rope_env_step_vs_reference(built_lib):
     obs, reward, done, info = env.step_diff(a[0], st)
     s = info["state"]
     (ga,) = torch.autograd.grad(reward.sum(), [a])
+    fl = util.env_floor("rope")      # fp32 noise of the unmodified reference over these 3 990 substeps (fp32 fixture vs fp64 run)
     ex, er = util.rel_err(s.x, d["x0"]), util.rel_err(reward, d["reward0"])
-    print(f"rope env: x rel {ex:.3e} reward {reward.tolist()} ref {d['reward0'].tolist()} rel {er:.3e}")
-    assert ex < 1e-3 and er < 1e-3          # 3 990 substeps of a pushed plastic rope: fp32 drift of two correct runs
+    print(f"rope env: x rel {ex:.3e} (floor {fl('x0'):.1e}) reward {reward.tolist()} ref {d['reward0'].tolist()} rel {er:.3e} "
+          f"(floor {fl('reward0'):.1e})")
+    assert ex < util.floor_bar(1e-4, fl("x0")) and er < util.floor_bar(1e-4, fl("reward0"))
     assert util.rel_err(s.primitives[0].position, d["prim0_pos0"]) < 1e-5
     cs, eg = util.cosine(ga, d["g_actions"]), util.rel_err(ga, d["g_actions"])
-    print(f"rope env action gradient cos {cs:.6f} rel {eg:.3e}  ours {ga.tolist()} ref {d['g_actions'].tolist()}")
-    assert cs >= 0.999 and eg < 1e-2       # cosine bar met; max-norm 3.5e-3 after 3 990 substeps
+    print(f"rope env action gradient cos {cs:.6f} rel {eg:.3e} (floor {fl('g_actions'):.1e})  ours {ga.tolist()} ref {d['g_actions'].tolist()}")
+    assert cs >= 0.999 and eg < util.floor_bar(1e-3, fl("g_actions"))
     # the reference's own reset continues with random pushes: they run and keep the rope on the table
     env.state = s
     s2 = env.random_push(step=1, rng=np.random.RandomState(0))

@@ -141,3 +141,51 @@ def golden_mpm_grads(step_fn, state, action, d, n_prim, to_dev):
     res = {k: (g if g is not None else torch.zeros_like(req[k])) for k, g in zip(names, grads[:-1])}
     res["action"] = grads[-1]
     return res, out
+
+
+_FLOORS = {}
+
+
+def golden_mpm_floor(name):
+    """fp32 noise floor of the REFERENCE ARITHMETIC on golden case `name`: the oracle restatement (pinned to the reference
+    sources by tests/test_oracle_golden.py) run in fp32 and in fp64 from the fixture's inputs and cotangents.
+    -> ({state leaf: rel}, {gradient leaf: rel}); a tolerance above north_star's bar is only ever asserted as a multiple
+    of these measured numbers."""
+    if name in _FLOORS:
+        return _FLOORS[name]
+    conf, d = golden_mpm(name)
+    res = {}
+    for dtype in (torch.float32, torch.float64):
+        osim = omp.Simulator(oracle_conf(conf), d["material"].to(torch.int32), d["h"].to(dtype), dtype=dtype)
+        st = golden_oracle_state(conf, d, dtype=dtype)
+        act = d["action"].to(dtype)
+        if "g_x" in d:
+            got, out = golden_mpm_grads(lambda s, a: omp.step_batch(osim, s, a), st, act, d, conf.n_primitive, lambda t: t)
+        else:
+            with torch.no_grad():
+                got, out = {}, omp.step_batch(osim, st, act)
+        res[dtype] = (out, got)
+    (o32, g32), (o64, g64) = res[torch.float32], res[torch.float64]
+    fs = {k: rel_err(getattr(o32, k), getattr(o64, k)) for k in ("x", "v", "C", "F", "J")}
+    fg = {k: rel_err(g32[k], g64[k]) for k in g32 if g32[k] is not None and float(g64[k].abs().max()) > 1e-20}
+    _FLOORS[name] = (fs, fg)
+    return fs, fg
+
+
+def env_floor(name):
+    """fp32 noise of the UNMODIFIED reference on env fixture `name`: tests/golden/ref_mpmenv_<name>_f64.npz holds the same
+    rollout of the same reference env classes, from the fixture's own inputs, with the shim's float type switched to
+    float64 (oracle/gen_golden.py --f64).  -> f(key) = rel_err(fp32 fixture[key], fp64 run[key])."""
+    a = np.load(os.path.join(GOLD, f"ref_mpmenv_{name}.npz"))
+    b = np.load(os.path.join(GOLD, f"ref_mpmenv_{name}_f64.npz"))
+
+    def floor(key):
+        return rel_err(torch.from_numpy(a[key]).double(), torch.from_numpy(b[key]).double())
+    return floor
+
+
+K_FLOOR = 4.0      # bars above north_star's are K_FLOOR x a measured floor, never a hand-picked constant
+
+
+def floor_bar(bar, floor):
+    return max(bar, K_FLOOR * floor)

@@ -134,7 +134,7 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
   w.blk_flag = (int32_t*)take(4 * (size_t)k.B * k.nbx * k.nby * k.nbz);
   w.blk_nbuf = bwd ? k.S : 2;
   w.blk_list = (int32_t*)take(4 * (size_t)w.blk_nbuf * k.B * k.nbx * k.nby * k.nbz);
-  w.blk_count = (int32_t*)take(4 * S);
+  w.blk_count = (int32_t*)take(4 * 2 * S);   // [S][2]: {listed blocks, shell job needed}
   if (!bwd) {
     w.ps = (float*)take(4 * (size_t)PS_NCOMP * NP);
     w.vt_roll = (float*)take(4 * (size_t)VT_NCOMP * NP);
@@ -156,7 +156,7 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
     }
     w.act_count = (int32_t*)take(4 * S);
     w.gs = (float*)take(4 * (size_t)PS_NCOMP * NP);
-    w.ggrid = (float4*)take(16 * BG);
+    w.ggrid = (float4*)take(16 * BG * 2);
     w.g_fk_pos = (float*)take(4 * (size_t)k.B * P * (S + 1) * 3);
     w.g_fk_rot = (float*)take(4 * (size_t)k.B * P * (S + 1) * 4);
     w.g_fk_v = (float*)take(4 * (size_t)k.B * P * S * 3);
@@ -283,7 +283,7 @@ int ud_mpm_step_fwd(const ud_mpm_params* p, const ud_mpm_state* in, const int32_
   zero_async(ws.jrows, 4 * (size_t)k.B * k.S * 9, st);
   // the grids are zeroed in full once per call; between substeps only the 4x4x4 blocks P2G marked are re-zeroed
   zero_async(ws.blk_flag, 4 * (size_t)k.B * k.nbx * k.nby * k.nbz, st);
-  zero_async(ws.blk_count, 4 * (size_t)k.S, st);
+  zero_async(ws.blk_count, 8 * (size_t)k.S, st);
   const size_t BG = (size_t)k.B * k.G;
   zero_async(ws.grid_raw, 16 * BG * 2, st);
   if (ws.grid_fix) zero_async(ws.grid_fix, 32 * BG, st);
@@ -325,7 +325,7 @@ static void mpm_record_range(const MpmConst& k, const ud_mpm_state* in, MpmWs& w
   zero_async(ws.grid_raw, 16 * BG * nf, st);
   if (ws.grid_fix) zero_async(ws.grid_fix, 32 * BG, st);   // consumed (re-zeroed) cell by cell by k_grid_fwd
   zero_async(ws.blk_flag, 4 * (size_t)k.B * k.nbx * k.nby * k.nbz, st);
-  zero_async(ws.blk_count + f0, 4 * (size_t)nf, st);
+  zero_async(ws.blk_count + 2 * f0, 8 * (size_t)nf, st);
   zero_async(ws.act_count + f0, 4 * (size_t)nf, st);
   auto sv = [&](int f) { return ws.svd_s + (size_t)SV_NCOMP * k.N_pad * (f - f0); };
   auto ps_rd = [&](int f) { return (f == f0 && start) ? start : ws.ps + slot * (f - f0); };
@@ -358,23 +358,26 @@ static void mpm_reverse_begin(const MpmConst& k, const ud_mpm_state* gout, MpmWs
   zero_async(ws.g_scal, 4 * (size_t)k.B * GS_STRIDE, st);
   zero_async(ws.g_prim_in, 4 * (size_t)k.B * P * 16, st);
   zero_async(ws.g_act, 4 * (size_t)k.B * P * 6, st);
-  zero_async(ws.ggrid, 16 * BG, st);
+  zero_async(ws.ggrid, 16 * BG * 2, st);
 }
 // Reverses substeps f1-1 .. f0 recorded in slots 0.. (ws.sub0 == f0).  start = state at f0 when it is not in slot 0.
-// first_of_call: no G2P^T has scattered into ws.ggrid yet.  Otherwise the grid still holds the cotangents of substep
-// f1, whose block list belongs to a window that is gone: it is re-zeroed in full.
+// Two cotangent grids, used alternately: G2P^T of substep f scatters into slot f & 1, the grid adjoint reverses it in
+// place and, in the same launch, re-zeroes the OTHER slot from the block list of substep f + 1 (whose P2G^T has
+// finished), so that G2P^T(f - 1) finds it empty -- G2P^T(f + 1) scattered into the blocks P2G(f + 1) marked (+ face
+// cells through clamped indices, when that substep's shell flag is up).
+// first_of_call: both slots are still as mpm_reverse_begin zeroed them.  Otherwise they hold cotangents of substeps
+// whose block lists belong to a window that is gone: both are re-zeroed in full.
 static void mpm_reverse_range(const MpmConst& k, const ud_mpm_state* in, MpmWs& ws, int f0, int f1, const float* start,
                               bool first_of_call, cudaStream_t st) {
   const size_t slot = (size_t)PS_NCOMP * k.N_pad, BG = (size_t)k.B * k.G;
+  if (!first_of_call) zero_async(ws.ggrid, 16 * BG * 2, st);
   for (int f = f1 - 1; f >= f0; --f) {
     const float* s_in = (f == f0 && start) ? start : ws.ps + slot * (f - f0);
-    // G2P^T of substep f scatters into the blocks P2G(f) marked (+ face cells through clamped indices): only those
-    // are re-zeroed before the next (earlier) substep scatters
-    if (f < f1 - 1) launch_grid_clear(k, ws.ggrid, f + 1, ws, st);
-    else if (!first_of_call) zero_async(ws.ggrid, 16 * BG, st);
-    launch_g2p_bwd(k, s_in, ws.grid_out + BG * (f - f0), ws, st);
-    launch_grid_bwd(k, ws.grid_raw + BG * (f - f0), f, in, ws, st);
-    launch_p2g_bwd(k, s_in, ws.svd_s + (size_t)SV_NCOMP * k.N_pad * (f - f0), in->mu, in->lamda, f == 0, ws, st);
+    float4* gg = ws.ggrid + BG * (f & 1);
+    float4* other = ws.ggrid + BG * ((f + 1) & 1);
+    launch_g2p_bwd(k, s_in, ws.grid_out + BG * (f - f0), ws, st, gg);
+    launch_grid_bwd(k, ws.grid_raw + BG * (f - f0), f, in, ws, st, gg, f < f1 - 1 ? other : nullptr, f + 1);
+    launch_p2g_bwd(k, s_in, ws.svd_s + (size_t)SV_NCOMP * k.N_pad * (f - f0), in->mu, in->lamda, f == 0, ws, st, gg);
   }
 }
 static void mpm_reverse_end(const MpmConst& k, const ud_mpm_state* in, const float* action, const ud_mpm_state* gout,
@@ -435,7 +438,7 @@ int ud_mpm_step_bwd_windowed(const ud_mpm_params* p, const ud_mpm_state* in, con
   mpm_prepare(k, in, material, h, action, nullptr, ws, ws.ckpt_ps, st);
   cudaMemcpyAsync(ws.run_ps, ws.ckpt_ps, 4 * slot, cudaMemcpyDeviceToDevice, st);
   zero_async(ws.blk_flag, 4 * (size_t)k.B * k.nbx * k.nby * k.nbz, st);
-  zero_async(ws.blk_count, 4 * (size_t)S, st);
+  zero_async(ws.blk_count, 8 * (size_t)S, st);
   zero_async(ws.run_grid, 16 * BG * 2, st);
   if (ws.grid_fix) zero_async(ws.grid_fix, 32 * BG, st);
   {

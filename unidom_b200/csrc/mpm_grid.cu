@@ -155,6 +155,7 @@ k_blk_compact(int total, int32_t* __restrict__ blk_flag, int32_t* __restrict__ l
   const int lane = threadIdx.x & 31;
   const bool marked = i < total && blk_flag[i] == BLK_MARK_CTA;
   if (marked) blk_flag[i] = stamp;   // same state the self-listing warp kernels leave: flag == substep + 1 <=> listed
+  if (i == 0) count[1] = 1;           // the CTA-staged kernels do not look for stencils that leave the grid: shell job on
   const unsigned m = __ballot_sync(0xffffffffu, marked);
   if (!m) return;
   int base = 0;
@@ -197,7 +198,7 @@ grid_fwd_body(const MpmConst& k, float4* grid_in, float4* grid_out, long long* _
   const int w = blk_list[li];
   const int env = w / nblk, bid = w - env * nblk;
   const int bz = bid % k.nbz, by = (bid / k.nbz) % k.nby, bx = bid / (k.nbz * k.nby);
-#pragma unroll
+#pragma unroll 1
   for (int it = 0; it < 2; ++it) {
     const int lc = lane + 32 * it;
     const int ci = bx * 4 + (lc >> 4), cj = by * 4 + ((lc >> 2) & 3), ck = bz * 4 + (lc & 3);
@@ -228,24 +229,30 @@ grid_fwd_body(const MpmConst& k, float4* grid_in, float4* grid_out, long long* _
       }
     }
     if (!in_range) continue;
-    if (!has_mass) {  // empty cell: interior ones are never gathered with a non-zero weight
-      const bool on_shell = ci == 0 || cj == 0 || ck == 0 || ci == k.rx - 1 || cj == k.ry - 1 || ck == k.rz - 1;
-      if (on_shell)  // every cell of a listed block is this job's, its empty boundary cells included (the shell job
-        empty_shell_cell(k, ci, cj, ck, idx, env, g, grid_out, f, in, fk_pos, fk_rot, fk_vw, act_list, act_count);  // skips listed blocks)
-      else if (grid_out != grid_in || grid_fix)
-        grid_out[idx] = g;
+    const bool on_shell = ci == 0 || cj == 0 || ck == 0 || ci == k.rx - 1 || cj == k.ry - 1 || ck == k.rz - 1;
+    if (!has_mass && !on_shell) {  // empty interior cell: never gathered with a non-zero weight
+      if (grid_out != grid_in || grid_fix) grid_out[idx] = g;
       continue;
     }
+    // ONE inlined copy of the cell update for both kinds of cell (the kernel's code size is what bounds it, see
+    // k_grid_fwd).  A cell with mass evaluates every primitive, as in the reference.  (Skipping primitives whose
+    // influence is below 1e-12 was measured: in the plasticine scene half of the cells with mass are within reach of
+    // the pusher, nearly every 4x4x4 block has an active lane, and the extra test made the kernel 25 % longer.)
+    // Every cell of a listed block is this job's, its EMPTY boundary cells included (the shell job skips listed
+    // blocks): those skip primitives without influence and are listed for k_grid_bwd when one acts on them.
+    const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
     float p[3] = {g.x, g.y, g.z}, v[3];
+    bool any_active = false;
     auto prim_of = [&](int q, PrimIn<float>& pr) {
       load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
-      // every primitive acts on every cell with mass, as in the reference.  (Skipping primitives whose influence is
-      // below 1e-12 was measured: in the plasticine scene half of the cells with mass are within reach of the pusher,
-      // nearly every 4x4x4 block has an active lane, and the extra test made the kernel 25 % longer.)
-      return true;
+      if (has_mass) return true;
+      const bool a = prim_active(k, gpos, pr);
+      any_active |= a;
+      return a;
     };
     cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
     grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
+    if (!has_mass && act_list && any_active) act_list[atomicAdd(act_count, 1)] = (int32_t)idx;
   }
   }  // listed blocks of this warp
 }
@@ -276,14 +283,16 @@ __device__ __forceinline__ bool shell_cell(const MpmConst& k, int t, int& ci, in
   return true;
 }
 
-// In-place forward only, between substeps, instead of a memset of the whole grid: re-zero (a) the empty face cells
-// k_grid_shell wrote velocities into -- CTAs [0, shell_ctas) -- and (b) the blocks the previous substep's P2G touched
-// -- the remaining CTAs, persistent warps over the block list.
+// Between substeps, instead of a memset of the whole grid (the forward's raw grids and the adjoint's cotangent grids
+// are both used alternately, and the grid-side launch of a substep re-zeroes the slot the next one scatters into):
+// re-zero (a) the face cells written outside the listed blocks -- CTAs [0, shell_ctas), only in substeps whose shell
+// flag is up -- and (b) the blocks that substep's P2G touched -- the remaining CTAs, persistent warps over the list.
 __device__ __forceinline__ void
 grid_clear_body(const MpmConst& k, float4* __restrict__ grid, const int32_t* __restrict__ blk_list,
                 const int32_t* __restrict__ blk_count, int shell_ctas_per_env, int vblock, int nblocks) {
   const int shell_ctas = shell_ctas_per_env * k.B;
   if (vblock < shell_ctas) {
+    if (blk_count[1] == 0) return;   // no stencil left the grid in that substep: no face cell outside the listed blocks was written
     const int env = vblock / shell_ctas_per_env;
     int ci, cj, ck;
     if (!shell_cell(k, (vblock - env * shell_ctas_per_env) * blockDim.x + threadIdx.x, ci, cj, ck)) return;
@@ -347,12 +356,20 @@ struct GridClearArgs {
   int ctas;                 // shell_ctas_per_env * B + persistent CTAs
   int shell_ctas_per_env;
 };
+// KIND / PC: the collider's SDF (UD_SDF_*) and position control as COMPILE-TIME constants.  Both are call parameters, and
+// with both variants inlined at each of the 7 SDF evaluations per primitive the kernel was 9 768 (k_grid_bwd: 13 088)
+// instructions = 156 KB (209 KB) of code that every warp walks through exactly once: ncu showed "no instruction"
+// (instruction-cache misses) as the top stall of both kernels, 4.9 cycles per issue in k_grid_bwd.
+template <int KIND, int PC>
 __global__ void __launch_bounds__(128)
-k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, long long* __restrict__ grid_fix, int f,
+k_grid_fwd(MpmConst k_, float4* grid_in, float4* grid_out, long long* __restrict__ grid_fix, int f,
            ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
            const float* __restrict__ fk_vw, const int32_t* __restrict__ blk_list, const int32_t* __restrict__ blk_count,
            int32_t* __restrict__ act_list, int32_t* __restrict__ act_count, const int32_t* __restrict__ blk_flag,
            int shell_ctas_per_env, GridClearArgs clr) {
+  MpmConst k = k_;
+  k.sdf_kind = KIND;
+  k.pos_control = PC;
   int vb = blockIdx.x;
   if (vb < GRID_FWD_CTAS) {
     grid_fwd_body(k, grid_in, grid_out, grid_fix, f, in, fk_pos, fk_rot, fk_vw, blk_list, blk_count, act_list, act_count, vb,
@@ -361,6 +378,10 @@ k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, long long* __restrict_
   }
   vb -= GRID_FWD_CTAS;
   if (vb < shell_ctas_per_env * k.B) {
+    // Face cells of unlisted blocks are gathered only by particles whose stencil leaves the grid (clamped / wrapped
+    // indices); P2G raises blk_count[1] when it meets one.  An in-range stencil reads only nodes its own P2G scattered
+    // into, i.e. cells of listed blocks (block job).
+    if (blk_count[1] == 0) return;
     const int env = vb / shell_ctas_per_env;
     grid_shell_body(k, grid_in, grid_out, f, in, fk_pos, fk_rot, fk_vw, act_list, act_count, blk_flag, env,
                     vb - env * shell_ctas_per_env);
@@ -369,12 +390,6 @@ k_grid_fwd(MpmConst k, float4* grid_in, float4* grid_out, long long* __restrict_
   vb -= shell_ctas_per_env * k.B;
   grid_clear_body(k, clr.grid, clr.blk_list, clr.blk_count, clr.shell_ctas_per_env, vb, clr.ctas);
 }
-__global__ void __launch_bounds__(128)
-k_grid_clear(MpmConst k, float4* __restrict__ grid, const int32_t* __restrict__ blk_list,
-             const int32_t* __restrict__ blk_count, int shell_ctas_per_env) {
-  grid_clear_body(k, grid, blk_list, blk_count, shell_ctas_per_env, blockIdx.x, gridDim.x);
-}
-
 static inline int shell_ctas_of(const MpmConst& k) { return cdiv(2 * (k.rx * k.ry + k.rx * k.rz + k.ry * k.rz), 128); }
 
 // clear_grid != null: additionally re-zero `clear_grid` from the block list of substep `clear_substep` (same launch).
@@ -388,28 +403,21 @@ void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const
   int32_t* ac = al ? ws.act_count + substep : nullptr;
   const int total = k.B * k.nbx * k.nby * k.nbz;
   int32_t* bl = ws.blk_list + (size_t)(substep % ws.blk_nbuf) * total;
-  int32_t* bc = ws.blk_count + substep;
+  int32_t* bc = ws.blk_count + 2 * substep;
   if (!lists_ready) k_blk_compact<<<cdiv(total, 128), 128, 0, st>>>(total, ws.blk_flag, bl, bc, substep + 1);
   const int sc = shell_ctas_of(k);
   GridClearArgs clr = {nullptr, nullptr, nullptr, 0, sc};
   if (clear_grid) {
     clr.grid = clear_grid;
     clr.blk_list = ws.blk_list + (size_t)(clear_substep % ws.blk_nbuf) * total;
-    clr.blk_count = ws.blk_count + clear_substep;
+    clr.blk_count = ws.blk_count + 2 * clear_substep;
     clr.ctas = sc * k.B + 148 * 2;
   }
   // in-place (forward) mode the raw value of an empty cell is still there when the shell job reads it
-  k_grid_fwd<<<GRID_FWD_CTAS + sc * k.B + clr.ctas, 128, 0, st>>>(k, grid_in, grid_out, const_cast<long long*>(grid_fix),
-                                                                substep, *in, ws.fk_pos, ws.fk_rot, ws.fk_vw, bl, bc, al, ac,
-                                                                ws.blk_flag, sc, clr);
-}
-
-void launch_grid_clear(const MpmConst& k, float4* grid, int prev_substep, const MpmWs& ws, cudaStream_t st) {
-  KScope ks_(KC_GRID, st);
-  const int total = k.B * k.nbx * k.nby * k.nbz;
-  const int sc = shell_ctas_of(k);
-  k_grid_clear<<<sc * k.B + 148 * 4, 128, 0, st>>>(k, grid, ws.blk_list + (size_t)(prev_substep % ws.blk_nbuf) * total,
-                                                   ws.blk_count + prev_substep, sc);
+  auto kern = k.sdf_kind == UD_SDF_BOX ? (k.pos_control ? k_grid_fwd<UD_SDF_BOX, 1> : k_grid_fwd<UD_SDF_BOX, 0>)
+                                       : (k.pos_control ? k_grid_fwd<UD_SDF_CONTAINER, 1> : k_grid_fwd<UD_SDF_CONTAINER, 0>);
+  kern<<<GRID_FWD_CTAS + sc * k.B + clr.ctas, 128, 0, st>>>(k, grid_in, grid_out, const_cast<long long*>(grid_fix), substep, *in,
+                                                          ws.fk_pos, ws.fk_rot, ws.fk_vw, bl, bc, al, ac, ws.blk_flag, sc, clr);
 }
 
 // ================================================================================================
@@ -428,18 +436,51 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Sums each of v[0..N) over the 32 lanes; lane j < N returns the total of v[j] (lanes >= N: 0).  A transposed butterfly:
+// every step halves the values a lane carries, 31 shuffles in all instead of 5 per value, and the totals end up one per
+// lane, so the N accumulations that follow are ONE atomic instruction of N lanes instead of N by lane 0.
+template <int N>
+__device__ __forceinline__ float warp_sum_transposed(const float (&vin)[N]) {
+  static_assert(N <= 32, "one value per lane");
+  const int lane = threadIdx.x & 31;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = i < N ? vin[i] : 0.f;
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float keep = up ? v[i + h] : v[i], send = up ? v[i] : v[i + h];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
+}
+
+constexpr int GRID_BWD_CTAS = 148 * 8;
+template <int KIND, int PC>   // compile-time SDF kind / position control: see k_grid_fwd
 __global__ void __launch_bounds__(128)
-k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__ ggrid, int f,
+k_grid_bwd(MpmConst k_, const float4* __restrict__ grid_raw, float4* __restrict__ ggrid, int f,
            ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
            const float* __restrict__ fk_vw, float* __restrict__ g_fk_pos, float* __restrict__ g_fk_rot,
            float* __restrict__ g_fk_v, float* __restrict__ g_scal, const int32_t* __restrict__ act_list,
-           const int32_t* __restrict__ act_count) {
+           const int32_t* __restrict__ act_count, GridClearArgs clr) {
+  MpmConst k = k_;
+  k.sdf_kind = KIND;
+  k.pos_control = PC;
+  // CTAs beyond the persistent ones re-zero the OTHER cotangent grid (the one G2P^T of the next, earlier substep
+  // scatters into) from the block list of substep f + 1, whose P2G^T has finished: no separate clear launch.
+  if (blockIdx.x >= GRID_BWD_CTAS) {
+    grid_clear_body(k, clr.grid, clr.blk_list, clr.blk_count, clr.shell_ctas_per_env, blockIdx.x - GRID_BWD_CTAS, clr.ctas);
+    return;
+  }
   // Persistent grid-stride loop over the cells the recompute pass listed (cells with mass + empty shell cells under
   // a primitive): ~5 % of the grid.  Every other cell keeps the zero the memset gave it.  Whole warps iterate
   // together (the warp reductions below need all lanes).
   const int count = *act_count;
   const int lane = threadIdx.x & 31;
-  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (GRID_BWD_CTAS * blockDim.x) >> 5;
   for (int wbase = warp0 * 32; wbase < count; wbase += nwarps * 32) {
   const bool live = wbase + lane < count;
   const size_t idx = live ? (size_t)act_list[wbase + lane] : 0;
@@ -472,7 +513,7 @@ k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__
     v[0] = (has_mass ? g.x / g.w : g.x) + k.gdt[0];
     v[1] = (has_mass ? g.y / g.w : g.y) + k.gdt[1];
     v[2] = (has_mass ? g.z / g.w : g.z) + k.gdt[2];
-#pragma unroll
+#pragma unroll 1   // one copy of the collider code (vin goes to local memory: 3 stores per primitive)
     for (int q = 0; q < UD_MAX_PRIM; ++q) {
       if (q >= k.n_prim) break;
       PrimIn<float> pf;
@@ -529,17 +570,22 @@ k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__
     size_t t = (size_t)env * k.n_prim + q;
     float* tp = g_fk_pos + t * (k.S + 1) * 3;
     float* tr = g_fk_rot + t * (k.S + 1) * 4;
+    auto dst_of = [&](int j) -> float* {   // accumulator of cotangent j of primitive q (PRIM_NIN order)
+      if (j < 3) return &tp[f * 3 + j];
+      if (j < 7) return &tr[f * 4 + (j - 3)];
+      if (j < 10) return &tp[(f + 1) * 3 + (j - 7)];
+      if (j < 14) return &tr[(f + 1) * 4 + (j - 10)];
+      if (j < 17) return &g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + (j - 14)];
+      if (j < 18) return &g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + 3];
+      return &g_fk_v[(t * k.S + f) * 3 + (j - 18)];
+    };
+    if (uniform) {   // one env in the warp: lane j ends up with the warp total of cotangent j and adds it
+      const float tot = warp_sum_transposed<PRIM_NIN>(pg.g);
+      if (lane < PRIM_NIN && tot != 0.f) atomicAdd(dst_of(lane), tot);
+    } else {
 #pragma unroll
-    for (int j = 0; j < PRIM_NIN; ++j) {
-      float* dst;
-      if (j < 3) dst = &tp[f * 3 + j];
-      else if (j < 7) dst = &tr[f * 4 + (j - 3)];
-      else if (j < 10) dst = &tp[(f + 1) * 3 + (j - 7)];
-      else if (j < 14) dst = &tr[(f + 1) * 4 + (j - 10)];
-      else if (j < 17) dst = &g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + (j - 14)];
-      else if (j < 18) dst = &g_scal[env * GS_STRIDE + GS_PRIM + q * GS_PRIM_STRIDE + 3];
-      else dst = &g_fk_v[(t * k.S + f) * 3 + (j - 18)];
-      reduce_add(pg.g[j], dst);
+      for (int j = 0; j < PRIM_NIN; ++j)
+        if (pg.g[j] != 0.f) atomicAdd(dst_of(j), pg.g[j]);
     }
   }
   // ---- reverse of v = p / m + dt g
@@ -551,12 +597,25 @@ k_grid_bwd(MpmConst k, const float4* __restrict__ grid_raw, float4* __restrict__
   }  // listed cells
 }
 
+// ggrid: the cotangent grid G2P^T(substep) scattered into, reversed in place.  clear_grid != null: additionally
+// re-zero `clear_grid` from the block list of `clear_substep` in the same launch.
 void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,
-                     const MpmWs& ws, cudaStream_t st) {
+                     const MpmWs& ws, cudaStream_t st, float4* ggrid, float4* clear_grid, int clear_substep) {
   KScope ks_(KC_GRID_BWD, st);
-  k_grid_bwd<<<148 * 8, 128, 0, st>>>(k, grid_raw, ws.ggrid, substep, *in, ws.fk_pos, ws.fk_rot, ws.fk_vw,
-                                      ws.g_fk_pos, ws.g_fk_rot, ws.g_fk_v, ws.g_scal,
-                                      ws.act_list + (size_t)(substep - ws.sub0) * k.B * k.G, ws.act_count + substep);
+  const int total = k.B * k.nbx * k.nby * k.nbz;
+  const int sc = shell_ctas_of(k);
+  GridClearArgs clr = {nullptr, nullptr, nullptr, 0, sc};
+  if (clear_grid) {
+    clr.grid = clear_grid;
+    clr.blk_list = ws.blk_list + (size_t)(clear_substep % ws.blk_nbuf) * total;
+    clr.blk_count = ws.blk_count + 2 * clear_substep;
+    clr.ctas = sc * k.B + 148 * 2;
+  }
+  auto kern = k.sdf_kind == UD_SDF_BOX ? (k.pos_control ? k_grid_bwd<UD_SDF_BOX, 1> : k_grid_bwd<UD_SDF_BOX, 0>)
+                                       : (k.pos_control ? k_grid_bwd<UD_SDF_CONTAINER, 1> : k_grid_bwd<UD_SDF_CONTAINER, 0>);
+  kern<<<GRID_BWD_CTAS + clr.ctas, 128, 0, st>>>(k, grid_raw, ggrid, substep, *in, ws.fk_pos, ws.fk_rot, ws.fk_vw, ws.g_fk_pos,
+                                                 ws.g_fk_rot, ws.g_fk_v, ws.g_scal,
+                                                 ws.act_list + (size_t)(substep - ws.sub0) * k.B * k.G, ws.act_count + substep, clr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -568,7 +627,8 @@ void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, con
 // memory with parallel loads (the per-row output-table cotangents are added on the way, the (v, w) row cotangents are
 // warp-reduced), then lane 0 walks the short sequential chain on shared memory.  The previous one-thread version did
 // ~400 dependent global read-modify-writes (117 us for S = 16).
-__global__ void __launch_bounds__(32)
+constexpr int FKB_BLOCK = 128;
+__global__ void __launch_bounds__(FKB_BLOCK)
 k_fk_bwd(MpmConst k, ud_mpm_state in, const float* __restrict__ action, ud_mpm_state gout,
          const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
          const float* __restrict__ fk_vw, const float* __restrict__ fk_act,
@@ -581,11 +641,40 @@ k_fk_bwd(MpmConst k, ud_mpm_state in, const float* __restrict__ action, ud_mpm_s
   const int S = k.S;
   float* gtp = fksm;                  // [(S+1)*3]
   float* gtr = fksm + (S + 1) * 3;    // [(S+1)*4]
+  float* jac = fksm + (S + 1) * 7;    // [S-1][4][8]: d qmul(dq, rot[f]) / d(dq, rot[f]) of every row
   const ud_primitive& go = gout.prim[q];
   const float* tp = fk_pos + (size_t)t * (S + 1) * 3;
   const float* tr = fk_rot + (size_t)t * (S + 1) * 4;
   const float* gp_in = g_fk_pos + (size_t)t * (S + 1) * 3;
   const float* gr_in = g_fk_rot + (size_t)t * (S + 1) * 4;
+  // The Jacobians of the rotation chain's rows (forward mode over the 8 inputs of qmul: ~1 500 dependent instructions
+  // each, IEEE divisions) do not depend on each other: one row per thread, all of them at once.  The sequential part
+  // that is left for thread 0 is a 4x8 matrix-vector product per row.  (Round 2 until its last session evaluated them
+  // inside the sequential loop: 80 us per call at S = 16 and ~4 us for every further row.)
+  {
+    float vwr[3], dq0[4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) vwr[j] = fk_vw[(size_t)t * 6 + 3 + j];
+    w2quat(vwr, dq0);
+    for (int f = threadIdx.x; f < S - 1; f += FKB_BLOCK) {
+      Dual<8> dqd[4], rd[4], out[4];
+      for (int j = 0; j < 4; ++j) {
+        dqd[j].v = dq0[j];
+        rd[j].v = tr[f * 4 + j];
+        for (int i = 0; i < 8; ++i) {
+          dqd[j].d[i] = (i == j) ? 1.f : 0.f;
+          rd[j].d[i] = (i == 4 + j) ? 1.f : 0.f;
+        }
+      }
+      qmul(dqd, rd, out);
+      for (int o = 0; o < 4; ++o)
+        for (int i = 0; i < 8; ++i) jac[(f * 4 + o) * 8 + i] = out[o].d[i];
+    }
+  }
+  if (threadIdx.x >= 32) {   // warps 1.. only computed Jacobians
+    __syncthreads();
+    return;
+  }
   // rows 1..S-1 of the output tables are internal rows 1..S-1; output row 0 = internal row S-1 (copy_frame)
   for (int e = lane; e < (S + 1) * 3; e += 32) {
     const int r = e / 3;
@@ -612,7 +701,7 @@ k_fk_bwd(MpmConst k, ud_mpm_state in, const float* __restrict__ action, ud_mpm_s
   for (int j = 0; j < 6; ++j)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) gvw[j] += __shfl_xor_sync(0xffffffffu, gvw[j], off);
-  __syncwarp();
+  __syncthreads();   // the staged tables and every row's Jacobian are in shared memory
   if (lane != 0) return;
   // row S is the clamped alias of row S-1; output row 0 lands on internal row S-1
   for (int j = 0; j < 3; ++j) gtp[(S - 1) * 3 + j] += gtp[S * 3 + j] + (go.position ? go.position[(size_t)env * S * 3 + j] : 0.f);
@@ -631,22 +720,12 @@ k_fk_bwd(MpmConst k, ud_mpm_state in, const float* __restrict__ action, ud_mpm_s
       gtp[f * 3 + j] += gnext;
       gvw[j] += gnext;
     }
-    // rot[f+1] = qmul(dq, rot[f]) : Jacobian by forward mode over the 8 inputs
-    Dual<8> dqd[4], rd[4], out[4];
-    for (int j = 0; j < 4; ++j) {
-      dqd[j].v = dq[j];
-      rd[j].v = tr[f * 4 + j];
-      for (int i = 0; i < 8; ++i) {
-        dqd[j].d[i] = (i == j) ? 1.f : 0.f;
-        rd[j].d[i] = (i == 4 + j) ? 1.f : 0.f;
-      }
-    }
-    qmul(dqd, rd, out);
+    // rot[f+1] = qmul(dq, rot[f]): transposed Jacobian (computed above) times the cotangent of row f+1
     for (int i = 0; i < 4; ++i) {
       float a = 0.f, b = 0.f;
       for (int o = 0; o < 4; ++o) {
-        a += gtr[(f + 1) * 4 + o] * out[o].d[i];
-        b += gtr[(f + 1) * 4 + o] * out[o].d[4 + i];
+        a += gtr[(f + 1) * 4 + o] * jac[(f * 4 + o) * 8 + i];
+        b += gtr[(f + 1) * 4 + o] * jac[(f * 4 + o) * 8 + 4 + i];
       }
       gdq[i] += a;
       gtr[f * 4 + i] += b;
@@ -682,8 +761,10 @@ void launch_fk_bwd(const MpmConst& k, const ud_mpm_state* in, const float* actio
   int n = k.B * k.n_prim;
   if (n == 0) return;
   KScope ks_(KC_FK, st);
-  k_fk_bwd<<<n, 32, sizeof(float) * 7 * (k.S + 1), st>>>(k, *in, action, *gout, ws.fk_pos, ws.fk_rot, ws.fk_vw, ws.fk_act,
-                                                         ws.g_fk_pos, ws.g_fk_rot, ws.g_fk_v, ws.g_prim_in, ws.g_act);
+  const size_t smem = sizeof(float) * (7 * (size_t)(k.S + 1) + 32 * (size_t)(k.S > 1 ? k.S - 1 : 0));   // 20.6 KB at S = 133
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_fk_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
+  k_fk_bwd<<<n, FKB_BLOCK, smem, st>>>(k, *in, action, *gout, ws.fk_pos, ws.fk_rot, ws.fk_vw, ws.fk_act, ws.g_fk_pos,
+                                       ws.g_fk_rot, ws.g_fk_v, ws.g_prim_in, ws.g_act);
 }
 
 }  // namespace ud

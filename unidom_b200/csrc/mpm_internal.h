@@ -100,7 +100,9 @@ struct MpmWs {
   int32_t* blk_list;    // [blk_nbuf][B*nbx*nby*nbz] the marked blocks, compacted; slot = substep % blk_nbuf
   int blk_nbuf;         // fwd: 2 (k_grid_clear reads the previous substep's list); bwd: S (the reverse pass re-zeroes
                         // the cotangent grid block by block)
-  int32_t* blk_count;   // [S] number of listed blocks per substep
+  int32_t* blk_count;   // [S][2] per substep: number of listed blocks; 1 when some particle's stencil leaves the grid
+                        // (only then does anything gather a face cell of a block nobody scattered into: the shell
+                        // job of the grid update and the face-cell re-zeroing run only for such substeps)
   float* vt_roll;       // fwd only: [12*N_pad] V^T of the previous substep's SVD (warm start)
   int32_t* act_list;    // bwd only: [S][B*G] cells listed by the recompute pass for the grid adjoint
   // windowed adjoint only (ud_mpm_step_bwd_windowed): K-spaced checkpoints and the checkpoint pass's scratch
@@ -119,7 +121,8 @@ struct MpmWs {
   float* jrows;         // [B*S*9] rows i<3 of C' of original particles 0..2 (J update, :327)
   // adjoint
   float* gs;            // [24*N_pad] cotangent tiles (sorted order)
-  float4* ggrid;        // [B*G]
+  float4* ggrid;        // [2][B*G] cotangent grids, used alternately: substep f scatters into / gathers from slot f & 1
+                        // while the grid adjoint's launch re-zeroes the other one block by block
   float* g_fk_pos;      // [B*P*(S+1)*3]
   float* g_fk_rot;      // [B*P*(S+1)*4]
   float* g_fk_v;        // [B*P*S*3] (position-control rows)
@@ -167,9 +170,9 @@ void launch_unsort_state(const MpmConst& k, const float* ps_slot, const float* J
                          ud_mpm_state* out, cudaStream_t st);
 void launch_gather_cot(const MpmConst& k, const ud_mpm_state* gout, const MpmWs& ws, cudaStream_t st);
 void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
-                    cudaStream_t st);
+                    cudaStream_t st, float4* ggrid);
 void launch_p2g_bwd(const MpmConst& k, const float* ps_in, const float* svd_in, const float* mu_s,
-                    const float* la_s, bool first_substep, const MpmWs& ws, cudaStream_t st);
+                    const float* la_s, bool first_substep, const MpmWs& ws, cudaStream_t st, const float4* ggrid);
 void launch_finish_bwd(const MpmConst& k, const ud_mpm_state* in, const ud_mpm_state* gout,
                        ud_mpm_state* gin, const float* action, float* gaction, const MpmWs& ws,
                        cudaStream_t st);
@@ -179,12 +182,11 @@ void launch_fk_fwd(const MpmConst& k, const ud_mpm_state* in, const float* actio
                    const MpmWs& ws, cudaStream_t st);
 // grid_fix != null (deterministic P2G): the raw {p,m} is first converted from the fixed-point accumulators
 // into grid_in (which the adjoint reads later), then updated into grid_out.
-void launch_grid_clear(const MpmConst& k, float4* grid, int prev_substep, const MpmWs& ws, cudaStream_t st);
 void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const long long* grid_fix, int substep,
                      const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st, float4* clear_grid = nullptr,
                      int clear_substep = 0, bool lists_ready = false);
 void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,
-                     const MpmWs& ws, cudaStream_t st);
+                     const MpmWs& ws, cudaStream_t st, float4* ggrid, float4* clear_grid, int clear_substep);
 void launch_fk_bwd(const MpmConst& k, const ud_mpm_state* in, const float* action,
                    const ud_mpm_state* gout, const MpmWs& ws, cudaStream_t st);
 

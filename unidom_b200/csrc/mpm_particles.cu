@@ -30,6 +30,17 @@ static inline dim3 pgrid(const MpmConst& k, int block) { return dim3(cdiv(k.n, b
   int g = env * (k).n + (live_ ? slot_ : 0);                 \
   int gp = env * (k).n_pad + (slot_ < (k).n_pad ? slot_ : 0);
 
+// The same with the CTAs walking the tiles from the LAST one down (k_g2p): the persistent P2G of the next substep walks
+// upwards and reads x, v, C of the tiles G2P wrote LAST first, while they are still in L2.  Measured on the plasticine
+// scene: k_p2g_pers 123.2 -> 121.2 us per launch, k_g2p unchanged (profiles/r02_run25.sh).  The same reversal of G2P^T
+// (after the upward P2G^T) cost it more than it gained: 110.9 -> 115.8 us, not kept.
+#define UD_PARTICLE_INDEX_REV(k, env, g)                                              \
+  int env = gridDim.y - 1 - blockIdx.y;                                               \
+  int slot_ = (gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x;                \
+  bool live_ = slot_ < (k).n;                                                         \
+  int g = env * (k).n + (live_ ? slot_ : 0);                                          \
+  int gp = env * (k).n_pad + (slot_ < (k).n_pad ? slot_ : 0);
+
 // Persistent particle kernels (round 2): the grid is one CTA per resident CTA slot and every WARP walks the 32-particle
 // tiles w, w + W, w + 2W, ... (W = warps in the grid), prefetching its next tile while it computes the current one.
 struct TileWalk {
@@ -751,7 +762,7 @@ constexpr unsigned FULL = 0xffffffffu;
 struct BlkList {
   int32_t* flag;    // [B * nblk]
   int32_t* list;    // this substep's list
-  int32_t* count;   // this substep's counter
+  int32_t* count;   // this substep's counter; count[1]: set when a particle's stencil leaves the grid (mpm_internal.h)
   int stamp;
 };
 struct WarpGroup {
@@ -882,6 +893,11 @@ __device__ __forceinline__ void warp_mark_blocks(const MpmConst& k, const WarpGr
                                                  const BlkList& bl, int env) {
   if (k.mark == 0) return;
   const int lane = threadIdx.x & 31;
+  // a stencil that leaves the grid reads (G2P, clamped / wrapped indices) face cells of blocks nobody scattered into:
+  // tell the grid update that its shell job is needed this substep (rare: a plain idempotent store)
+  const bool outside = live && !(base[0] >= 0 && base[0] + 2 < k.rx && base[1] >= 0 && base[1] + 2 < k.ry && base[2] >= 0 &&
+                                 base[2] + 2 < k.rz);
+  if (__any_sync(FULL, outside) && lane == 0) bl.count[1] = 1;
   const int a = (lane & 4) ? 2 : 0, b = (lane & 2) ? 2 : 0, c = (lane & 1) ? 2 : 0;
   const int nseg = __popc(g.lb);
   for (int s0 = 0; s0 < nseg; s0 += 4) {   // warp-uniform; warps spanning more than four cells are rare
@@ -1019,7 +1035,7 @@ int tuning_warp(int v) {
 
 static BlkList blk_list_of(const MpmConst& k, const MpmWs& ws, int substep) {
   const size_t total = (size_t)k.B * k.nbx * k.nby * k.nbz;
-  BlkList bl = {ws.blk_flag, ws.blk_list + (size_t)(substep % ws.blk_nbuf) * total, ws.blk_count + substep, substep + 1};
+  BlkList bl = {ws.blk_flag, ws.blk_list + (size_t)(substep % ws.blk_nbuf) * total, ws.blk_count + 2 * substep, substep + 1};
   return bl;
 }
 
@@ -1205,7 +1221,7 @@ __global__ void __launch_bounds__(UD_BLOCK, UD_G2P_MINB)
 k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ grid,
       const int32_t* __restrict__ perm, float* __restrict__ jrows, int substep) {
   __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_CELLS * 32];
-  UD_PARTICLE_INDEX(k, env, g);
+  UD_PARTICLE_INDEX_REV(k, env, g);
   if (slot_ - (int)(threadIdx.x & 31) >= k.n) return;   // warp-uniform
   const int p = perm[g];   // needed only at the end: issued with the first load
   float x[3];
@@ -1604,19 +1620,19 @@ k_g2p_bwd_warp(MpmConst k, const float* __restrict__ ps_in, const float4* __rest
 
 int tuning_warp(int v);
 static void launch_g2p_bwd_warp(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
-                                cudaStream_t st) {
+                                cudaStream_t st, float4* ggrid) {
   const size_t smem = G2PBW_WARP_BYTES * (G2PBW_BLOCK / 32);
   cudaFuncSetAttribute(k_g2p_bwd_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
-  k_g2p_bwd_warp<<<pgrid(k, G2PBW_BLOCK), G2PBW_BLOCK, smem, st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
+  k_g2p_bwd_warp<<<pgrid(k, G2PBW_BLOCK), G2PBW_BLOCK, smem, st>>>(k, ps_in, grid_out, ws.gs, ggrid);
 }
 
 void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_out, const MpmWs& ws,
-                    cudaStream_t st) {
+                    cudaStream_t st, float4* ggrid) {
   KScope ks_(KC_G2P_BWD, st);
   const int nw = tuning_warp(-1);
-  if (nw == 1) return launch_g2p_bwd_warp(k, ps_in, grid_out, ws, st);
+  if (nw == 1) return launch_g2p_bwd_warp(k, ps_in, grid_out, ws, st, ggrid);
   cudaFuncSetAttribute(k_g2p_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2pb_smem_bytes());   // per device
-  k_g2p_bwd<<<pgrid(k, G2PB_BLOCK), G2PB_BLOCK, g2pb_smem_bytes(), st>>>(k, ps_in, grid_out, ws.gs, ws.ggrid);
+  k_g2p_bwd<<<pgrid(k, G2PB_BLOCK), G2PB_BLOCK, g2pb_smem_bytes(), st>>>(k, ps_in, grid_out, ws.gs, ggrid);
 }
 
 // P2G^T (gather of the cotangents of scattered momentum/mass; dropped nodes contribute nothing),
@@ -1868,10 +1884,10 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
 }
 
 void launch_p2g_bwd(const MpmConst& k, const float* ps_in, const float* svd_in, const float* mu_s,
-                    const float* la_s, bool first_substep, const MpmWs& ws, cudaStream_t st) {
+                    const float* la_s, bool first_substep, const MpmWs& ws, cudaStream_t st, const float4* ggrid) {
   KScope ks_(KC_P2G_BWD, st);
   if (first_substep) cudaMemsetAsync(ws.norm2, 0, 4 * (size_t)k.B * 2, st);
-  k_p2g_bwd<<<persistent_ctas(k, UD_BLOCK / 32, 4), UD_BLOCK, 0, st>>>(k, ps_in, svd_in, ws.ggrid, ws.gs, mu_s, la_s, ws.mat_s,
+  k_p2g_bwd<<<persistent_ctas(k, UD_BLOCK / 32, 4), UD_BLOCK, 0, st>>>(k, ps_in, svd_in, ggrid, ws.gs, mu_s, la_s, ws.mat_s,
                                                      ws.h_s, ws.g_scal, first_substep ? ws.norm2 : nullptr);
 }
 
