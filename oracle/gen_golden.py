@@ -425,6 +425,48 @@ def cloth_env_para_case(name, B, seed, it):
           f"g_stiffness={out['g_stiffness']}")
 
 
+def cloth_unfold_case(name, B, seed, key_seed=1):
+    """The unfold tasks' reset (envs/unfold_cloth1_env.py:56-82): lattice + threefry normal noise * 1e-4, then ONE
+    pick-and-place fold between two nodes drawn from np.random (2 000 substeps through step_diff), run from the
+    reference's own UnfoldCloth1Env under the shim with np.random seeded.  Also the same reset of the unmodified
+    reference from lattice positions perturbed by 1e-7 (about one fp32 ulp): the chaotic rollout's own sensitivity,
+    the floor the GPU test scales its bar with."""
+    sys.path.insert(0, os.path.join(HERE, "jaxshim"))
+    import stubs
+    stubs.install()
+    import torch
+    import jax
+    import jax.numpy as jnp
+    from jax import random
+    from daxbench.core.envs import unfold_cloth1_env as mod
+    env = mod.UnfoldCloth1Env(batch_size=B, seed=1)
+    np.random.seed(seed)
+    obs, st = env.reset(jax.random.PRNGKey(key_seed))
+    # what reset() drew, recomputed the same way for the fixture
+    init = env.simulator.reset_jax()
+    k, _ = random.split(jax.random.PRNGKey(key_seed))
+    noisy = init.x + random.normal(k, init.x.shape) * 0.0001
+    np.random.seed(seed)
+    st_point = np.random.randint(0, init.x.shape[1], size=(B,))
+    ed_point = np.random.randint(0, init.x.shape[1], size=(B,))
+    out = {"lattice_x": np.asarray(init.x), "noisy_x": np.asarray(noisy), "st_point": st_point, "ed_point": ed_point,
+           "x": np.asarray(st.x), "v": np.asarray(st.v), "primitive0": np.asarray(st.primitive0), "obs": np.asarray(obs),
+           "mu": np.asarray(st.mu), "seed": np.array(seed), "key_seed": np.array(key_seed), "goal": np.asarray(env.goal)}
+    # sensitivity of the reference itself: the same fold from positions perturbed by 1e-7
+    prng = np.random.RandomState(seed + 1000)
+    xp = (np.asarray(noisy) + 1e-7 * prng.randn(*noisy.shape)).astype(np.float32)
+    bidx = jnp.arange(B)
+    s0 = init._replace(x=jnp.array(xp))
+    actions = jnp.concatenate((s0.x[bidx, st_point], s0.x[bidx, ed_point]), axis=-1)
+    _, _, _, info = env.step_diff(actions, s0)
+    out["pert_x"] = np.asarray(info["state"].x)
+    path = os.path.join(GOLD, f"ref_clothenv_{name}.npz")
+    np.savez_compressed(path, **out)
+    d = np.abs(out["pert_x"] - out["x"]).max()
+    print(f"wrote {path}: B={B} fold {st_point}->{ed_point}, |x - lattice|max={np.abs(out['x'] - out['lattice_x']).max():.3f}, "
+          f"reference vs 1e-7-perturbed reference |dx|max={d:.3e}")
+
+
 F64 = False   # --f64: the env cases once more in float64 FROM THE FIXTURE'S INPUTS -> ref_mpmenv_<name>_f64.npz.  The gap
               # between the fp32 fixture and this run is the fp32 noise of the UNMODIFIED reference itself on that rollout:
               # the floor the env-level GPU tests print and scale their bars with (tests/util.py::env_floor).
@@ -599,6 +641,7 @@ def main():
     cases["mpmenv_whip"] = lambda: task_env_case("whip", 2, 43)
     cases["mpmenv_pour"] = lambda: task_env_case("pour", 2, 44)
     cases["mpmenv_rope"] = lambda: task_env_case("rope", 1, 45, steps=1)      # 3 990 substeps per env step: ~30 min here
+    cases["clothenv_unfold1"] = lambda: cloth_unfold_case("unfold1", 2, 51)
     cases["clothenv_ep1"] = lambda: cloth_env_case("ep1", 1, 2, 31)
     # BASELINE.json configs[3]: fold_cloth1_para, stiffness of training iteration 3 (apg_para.py:326-329)
     cases["clothenv_para"] = lambda: cloth_env_para_case("para", 2, 33, 3)

@@ -246,3 +246,28 @@ def test_unfold_task_reset_by_random_folds(built_lib):
     assert float((folded.x - st.x).abs().max()) > 0.02                    # the cloth was folded
     # x' = clip(x, 0, 1) + dt * clip(v, +-max_v) (cloth_simulator.py:328-329): at most dt * max_v = 0.004 outside the box
     assert float(folded.x[..., 1].min()) >= -0.0041 and float(folded.x.max()) <= 1.0041
+
+
+@pytest.mark.gpu
+def test_unfold_cloth1_reset_vs_reference(built_lib):
+    """The unfold tasks' reset as the reference runs it (envs/unfold_cloth1_env.py:56-82 under oracle/jaxshim,
+    gen_golden.py::cloth_unfold_case): lattice + threefry normal noise * 1e-4 (bit for bit), then one pick-and-place fold
+    between the nodes np.random draws -- 2 000 chaotic substeps, compared against a floor: the same fold of the
+    unmodified reference from positions perturbed by 1e-7."""
+    from unidom_b200 import envs
+    path = os.path.join(util.GOLD, "ref_clothenv_unfold1.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in np.load(path).items()}
+    B = d["x"].shape[0]
+    env = envs.UnfoldClothEnv(B, n_folds=1, goal=d["goal"].numpy())
+    obs, st = env.reset(key=int(d["key_seed"]), rng=np.random.RandomState(int(d["seed"])))
+    assert float(st.mu[0]) == 3.0 and int(st.cur_step[0]) == 1
+    e0 = float((env.reset_noisy_x.cpu() - d["noisy_x"]).abs().max())
+    print(f"unfold1 reset: lattice + threefry noise max|d| {e0:.2e}")
+    assert e0 == 0.0                                                       # same lattice, same threefry stream, same roundings
+    ex, fl = util.rel_err(st.x, d["x"]), util.rel_err(d["pert_x"], d["x"])
+    print(f"unfold1 after the fold: x cuda-vs-reference rel {ex:.3e}; reference vs 1e-7-perturbed reference (floor) {fl:.3e}")
+    assert ex < util.floor_bar(1e-4, fl)
+    assert util.rel_err(obs, d["obs"]) < util.floor_bar(1e-4, fl)
+    assert float((st.x.cpu() - d["lattice_x"]).abs().max()) > 0.02            # the cloth was folded

@@ -142,7 +142,8 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
     w.grid_out = w.grid_raw;
   } else {
     w.ps = (float*)take(4 * (size_t)PS_NCOMP * NP * (W + 1));
-    w.grid_raw = (float4*)take(16 * BG * W);
+    w.grid_raw = (float4*)take(16 * BG * 2);
+    w.act_raw = (float4*)take(16 * BG * W);
     w.grid_out = (float4*)take(16 * BG * W);
     w.svd_s = (float*)take(4 * (size_t)SV_NCOMP * NP * W);
     w.act_list = (int32_t*)take(4 * BG * W);
@@ -318,11 +319,14 @@ static void mpm_prepare(const MpmConst& k, const ud_mpm_state* in, const int32_t
 }
 // Records substeps [f0, f1) into slots 0.. of the per-substep arrays (ws.sub0 must be f0).  start = state at f0
 // (null: ws.ps slot 0 already holds it); vt0 = V^T entering f0 in the forward's buffer layout (windowed adjoint).
+// need_end_state: the state after substep f1 - 1 is wanted (the taped forward un-sorts it into the output).  The adjoint
+// never reads it -- it needs the substep's grids, not what G2P makes of them -- so its recompute pass skips that G2P.
 static void mpm_record_range(const MpmConst& k, const ud_mpm_state* in, MpmWs& ws, int f0, int f1, const float* start,
-                             const float* vt0, cudaStream_t st) {
+                             const float* vt0, cudaStream_t st, bool need_end_state) {
   const size_t slot = (size_t)PS_NCOMP * k.N_pad, BG = (size_t)k.B * k.G;
   const int nf = f1 - f0;
-  zero_async(ws.grid_raw, 16 * BG * nf, st);
+  zero_async(ws.grid_raw, 16 * BG * 2, st);   // two raw grids, used alternately as in the forward (round 2 until its last
+                                             // session kept one per substep: a 600 MB memset per call at S = 16, B = 32)
   if (ws.grid_fix) zero_async(ws.grid_fix, 32 * BG, st);   // consumed (re-zeroed) cell by cell by k_grid_fwd
   zero_async(ws.blk_flag, 4 * (size_t)k.B * k.nbx * k.nby * k.nbz, st);
   zero_async(ws.blk_count + 2 * f0, 8 * (size_t)nf, st);
@@ -335,17 +339,21 @@ static void mpm_record_range(const MpmConst& k, const ud_mpm_state* in, MpmWs& w
     const bool warm = g_svd_warm && (f % SVD_RESTART);
     const bool from_ckpt = warm && f == f0 && vt0;
     const float* vt_in = !warm ? nullptr : (from_ckpt ? vt0 : sv(f - 1));
-    launch_p2g(k, ps_rd(f), ps_wr(f + 1), ws.grid_raw + BG * (f - f0), in->mu, in->lamda, vt_in, nullptr, sv(f), f, ws, st,
-               from_ckpt);
-    launch_grid_fwd(k, ws.grid_raw + BG * (f - f0), ws.grid_out + BG * (f - f0), ws.grid_fix, f, in, ws, st, nullptr, 0, lists);
-    launch_g2p(k, ps_rd(f), ps_wr(f + 1), ws.grid_out + BG * (f - f0), f, ws, st);
+    float4* gf = ws.grid_raw + BG * (f & 1);
+    float4* gn = ws.grid_raw + BG * ((f + 1) & 1);
+    launch_p2g(k, ps_rd(f), ps_wr(f + 1), gf, in->mu, in->lamda, vt_in, nullptr, sv(f), f, ws, st, from_ckpt);
+    // the raw {p, m} of the listed cells is kept in list order (ws.act_raw) for the grid adjoint; the other raw grid
+    // (substep f - 1's, read for the last time by that substep's grid launch) is re-zeroed block by block here
+    const bool clear = f > f0 && f + 1 < f1;
+    launch_grid_fwd(k, gf, ws.grid_out + BG * (f - f0), ws.grid_fix, f, in, ws, st, clear ? gn : nullptr, f - 1, lists);
+    if (f + 1 < f1 || need_end_state) launch_g2p(k, ps_rd(f), ps_wr(f + 1), ws.grid_out + BG * (f - f0), f, ws, st);
   }
 }
 static void mpm_record_pass(const MpmConst& k, const ud_mpm_state* in, const int32_t* material, const float* h,
                             const float* action, ud_mpm_state* out, MpmWs& ws, cudaStream_t st) {
   mpm_prepare(k, in, material, h, action, out, ws, ws.ps, st);
   ws.sub0 = 0;
-  mpm_record_range(k, in, ws, 0, k.S, nullptr, nullptr, st);
+  mpm_record_range(k, in, ws, 0, k.S, nullptr, nullptr, st, out != nullptr);
 }
 
 static void mpm_reverse_begin(const MpmConst& k, const ud_mpm_state* gout, MpmWs& ws, cudaStream_t st) {
@@ -376,7 +384,7 @@ static void mpm_reverse_range(const MpmConst& k, const ud_mpm_state* in, MpmWs& 
     float4* gg = ws.ggrid + BG * (f & 1);
     float4* other = ws.ggrid + BG * ((f + 1) & 1);
     launch_g2p_bwd(k, s_in, ws.grid_out + BG * (f - f0), ws, st, gg);
-    launch_grid_bwd(k, ws.grid_raw + BG * (f - f0), f, in, ws, st, gg, f < f1 - 1 ? other : nullptr, f + 1);
+    launch_grid_bwd(k, f, in, ws, st, gg, f < f1 - 1 ? other : nullptr, f + 1);
     launch_p2g_bwd(k, s_in, ws.svd_s + (size_t)SV_NCOMP * k.N_pad * (f - f0), in->mu, in->lamda, f == 0, ws, st, gg);
   }
 }
@@ -463,7 +471,7 @@ int ud_mpm_step_bwd_windowed(const ud_mpm_params* p, const ud_mpm_state* in, con
   for (int w = n_win - 1; w >= 0; --w) {
     const int f0 = w * W, f1 = f0 + W < S ? f0 + W : S;
     ws.sub0 = f0;
-    mpm_record_range(k, in, ws, f0, f1, ws.ckpt_ps + slot * w, w ? ws.ckpt_vt + vslot * w : nullptr, st);
+    mpm_record_range(k, in, ws, f0, f1, ws.ckpt_ps + slot * w, w ? ws.ckpt_vt + vslot * w : nullptr, st, false);
     mpm_reverse_range(k, in, ws, f0, f1, ws.ckpt_ps + slot * w, w == n_win - 1, st);
   }
   mpm_reverse_end(k, in, action, gout, gin, gaction, ws, st);

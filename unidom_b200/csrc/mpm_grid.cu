@@ -168,7 +168,8 @@ k_blk_compact(int total, int32_t* __restrict__ blk_flag, int32_t* __restrict__ l
 __device__ __forceinline__ void
 empty_shell_cell(const MpmConst& k, int ci, int cj, int ck, size_t idx, int env, const float4& g, float4* grid_out, int f,
                  const ud_mpm_state& in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
-                 const float* __restrict__ fk_vw, int32_t* __restrict__ act_list, int32_t* __restrict__ act_count) {
+                 const float* __restrict__ fk_vw, int32_t* __restrict__ act_list, int32_t* __restrict__ act_count,
+                 float4* __restrict__ act_raw) {
   const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
   float p[3] = {g.x, g.y, g.z}, v[3];
   bool any_active = false;
@@ -181,7 +182,11 @@ empty_shell_cell(const MpmConst& k, int ci, int cj, int ck, size_t idx, int env,
   cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
   grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
   // an empty shell cell under a primitive's influence can carry a cotangent to that primitive: list it for k_grid_bwd
-  if (act_list && any_active) act_list[atomicAdd(act_count, 1)] = (int32_t)idx;
+  if (act_list && any_active) {
+    const int at = atomicAdd(act_count, 1);
+    act_list[at] = (int32_t)idx;
+    act_raw[at] = g;
+  }
 }
 
 // Grid update over the listed 4x4x4 blocks: persistent warps, one block (64 cells, 2 per lane) per iteration.
@@ -189,7 +194,8 @@ __device__ __forceinline__ void
 grid_fwd_body(const MpmConst& k, float4* grid_in, float4* grid_out, long long* __restrict__ grid_fix, int f,
               const ud_mpm_state& in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
               const float* __restrict__ fk_vw, const int32_t* __restrict__ blk_list, const int32_t* __restrict__ blk_count,
-              int32_t* __restrict__ act_list, int32_t* __restrict__ act_count, int vblock, int nblocks) {
+              int32_t* __restrict__ act_list, int32_t* __restrict__ act_count, float4* __restrict__ act_raw, int vblock,
+              int nblocks) {
   const int nblk = k.nbx * k.nby * k.nbz;
   const int lane = threadIdx.x & 31;
   const int warp0 = (int)((vblock * (size_t)blockDim.x + threadIdx.x) >> 5), nwarps = (nblocks * blockDim.x) >> 5;
@@ -213,7 +219,6 @@ grid_fwd_body(const MpmConst& k, float4* grid_in, float4* grid_out, long long* _
         fx[1] = make_longlong2(0, 0);
         g = make_float4((float)((double)a.x * FIX_INV), (float)((double)a.y * FIX_INV), (float)((double)b.x * FIX_INV),
                         (float)((double)b.y * FIX_INV));
-        if (grid_out != grid_in) grid_in[idx] = g;  // the adjoint reads the raw grid
       } else {
         g = grid_in[idx];
       }
@@ -225,7 +230,11 @@ grid_fwd_body(const MpmConst& k, float4* grid_in, float4* grid_out, long long* _
         int base = 0;
         if (lane == __ffs(m) - 1) base = atomicAdd(act_count, __popc(m));
         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (has_mass) act_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)idx;
+        if (has_mass) {   // the raw {p, m} travels with the list: the raw grids themselves are re-used every other substep
+          const int at = base + __popc(m & ((1u << lane) - 1u));
+          act_list[at] = (int32_t)idx;
+          act_raw[at] = g;
+        }
       }
     }
     if (!in_range) continue;
@@ -252,7 +261,11 @@ grid_fwd_body(const MpmConst& k, float4* grid_in, float4* grid_out, long long* _
     };
     cell_update<float>(k, ci, cj, ck, p, g.w, in.friction[env], prim_of, v);
     grid_out[idx] = make_float4(v[0], v[1], v[2], g.w);
-    if (!has_mass && act_list && any_active) act_list[atomicAdd(act_count, 1)] = (int32_t)idx;
+    if (!has_mass && act_list && any_active) {
+      const int at = atomicAdd(act_count, 1);
+      act_list[at] = (int32_t)idx;
+      act_raw[at] = g;
+    }
   }
   }  // listed blocks of this warp
 }
@@ -326,8 +339,8 @@ grid_clear_body(const MpmConst& k, float4* __restrict__ grid, const int32_t* __r
 __device__ __forceinline__ void
 grid_shell_body(const MpmConst& k, const float4* grid_raw, float4* grid_out, int f, const ud_mpm_state& in,
                 const float* __restrict__ fk_pos, const float* __restrict__ fk_rot, const float* __restrict__ fk_vw,
-                int32_t* __restrict__ act_list, int32_t* __restrict__ act_count, const int32_t* __restrict__ blk_flag,
-                int env, int vblock) {
+                int32_t* __restrict__ act_list, int32_t* __restrict__ act_count, float4* __restrict__ act_raw,
+                const int32_t* __restrict__ blk_flag, int env, int vblock) {
   const int t0 = vblock * blockDim.x + threadIdx.x;
   const int nxy = k.rx * k.ry, nxz = k.rx * k.rz;
   int ci, cj, ck;
@@ -341,7 +354,7 @@ grid_shell_body(const MpmConst& k, const float4* grid_raw, float4* grid_out, int
   const size_t idx = (size_t)env * k.G + (size_t)(ci * k.ry + cj) * k.rz + ck;
   // nobody scattered into this block: the cell is empty, and grid_raw holds what the call's memset / the re-zeroing
   // left there (zero)
-  empty_shell_cell(k, ci, cj, ck, idx, env, grid_raw[idx], grid_out, f, in, fk_pos, fk_rot, fk_vw, act_list, act_count);
+  empty_shell_cell(k, ci, cj, ck, idx, env, grid_raw[idx], grid_out, f, in, fk_pos, fk_rot, fk_vw, act_list, act_count, act_raw);
 }
 
 // ONE launch per substep for the whole grid side: CTAs [0, NF) update the listed 4x4x4 blocks (persistent warps),
@@ -365,15 +378,15 @@ __global__ void __launch_bounds__(128)
 k_grid_fwd(MpmConst k_, float4* grid_in, float4* grid_out, long long* __restrict__ grid_fix, int f,
            ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
            const float* __restrict__ fk_vw, const int32_t* __restrict__ blk_list, const int32_t* __restrict__ blk_count,
-           int32_t* __restrict__ act_list, int32_t* __restrict__ act_count, const int32_t* __restrict__ blk_flag,
-           int shell_ctas_per_env, GridClearArgs clr) {
+           int32_t* __restrict__ act_list, int32_t* __restrict__ act_count, float4* __restrict__ act_raw,
+           const int32_t* __restrict__ blk_flag, int shell_ctas_per_env, GridClearArgs clr) {
   MpmConst k = k_;
   k.sdf_kind = KIND;
   k.pos_control = PC;
   int vb = blockIdx.x;
   if (vb < GRID_FWD_CTAS) {
-    grid_fwd_body(k, grid_in, grid_out, grid_fix, f, in, fk_pos, fk_rot, fk_vw, blk_list, blk_count, act_list, act_count, vb,
-                  GRID_FWD_CTAS);
+    grid_fwd_body(k, grid_in, grid_out, grid_fix, f, in, fk_pos, fk_rot, fk_vw, blk_list, blk_count, act_list, act_count, act_raw,
+                  vb, GRID_FWD_CTAS);
     return;
   }
   vb -= GRID_FWD_CTAS;
@@ -383,7 +396,7 @@ k_grid_fwd(MpmConst k_, float4* grid_in, float4* grid_out, long long* __restrict
     // into, i.e. cells of listed blocks (block job).
     if (blk_count[1] == 0) return;
     const int env = vb / shell_ctas_per_env;
-    grid_shell_body(k, grid_in, grid_out, f, in, fk_pos, fk_rot, fk_vw, act_list, act_count, blk_flag, env,
+    grid_shell_body(k, grid_in, grid_out, f, in, fk_pos, fk_rot, fk_vw, act_list, act_count, act_raw, blk_flag, env,
                     vb - env * shell_ctas_per_env);
     return;
   }
@@ -401,6 +414,7 @@ void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const
   KScope ks_(KC_GRID, st, lists_ready ? 1 : 2);
   int32_t* al = (grid_out != grid_in && ws.act_list) ? ws.act_list + (size_t)(substep - ws.sub0) * k.B * k.G : nullptr;
   int32_t* ac = al ? ws.act_count + substep : nullptr;
+  float4* ar = al ? ws.act_raw + (size_t)(substep - ws.sub0) * k.B * k.G : nullptr;
   const int total = k.B * k.nbx * k.nby * k.nbz;
   int32_t* bl = ws.blk_list + (size_t)(substep % ws.blk_nbuf) * total;
   int32_t* bc = ws.blk_count + 2 * substep;
@@ -417,7 +431,7 @@ void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const
   auto kern = k.sdf_kind == UD_SDF_BOX ? (k.pos_control ? k_grid_fwd<UD_SDF_BOX, 1> : k_grid_fwd<UD_SDF_BOX, 0>)
                                        : (k.pos_control ? k_grid_fwd<UD_SDF_CONTAINER, 1> : k_grid_fwd<UD_SDF_CONTAINER, 0>);
   kern<<<GRID_FWD_CTAS + sc * k.B + clr.ctas, 128, 0, st>>>(k, grid_in, grid_out, const_cast<long long*>(grid_fix), substep, *in,
-                                                          ws.fk_pos, ws.fk_rot, ws.fk_vw, bl, bc, al, ac, ws.blk_flag, sc, clr);
+                                                          ws.fk_pos, ws.fk_rot, ws.fk_vw, bl, bc, al, ac, ar, ws.blk_flag, sc, clr);
 }
 
 // ================================================================================================
@@ -461,7 +475,7 @@ __device__ __forceinline__ float warp_sum_transposed(const float (&vin)[N]) {
 constexpr int GRID_BWD_CTAS = 148 * 8;
 template <int KIND, int PC>   // compile-time SDF kind / position control: see k_grid_fwd
 __global__ void __launch_bounds__(128)
-k_grid_bwd(MpmConst k_, const float4* __restrict__ grid_raw, float4* __restrict__ ggrid, int f,
+k_grid_bwd(MpmConst k_, const float4* __restrict__ act_raw, float4* __restrict__ ggrid, int f,
            ud_mpm_state in, const float* __restrict__ fk_pos, const float* __restrict__ fk_rot,
            const float* __restrict__ fk_vw, float* __restrict__ g_fk_pos, float* __restrict__ g_fk_rot,
            float* __restrict__ g_fk_v, float* __restrict__ g_scal, const int32_t* __restrict__ act_list,
@@ -486,7 +500,7 @@ k_grid_bwd(MpmConst k_, const float4* __restrict__ grid_raw, float4* __restrict_
   const size_t idx = live ? (size_t)act_list[wbase + lane] : 0;
   const int env = (int)(idx / k.G);
   const int c = (int)(idx - (size_t)env * k.G);
-  float4 g = grid_raw[idx];
+  float4 g = live ? act_raw[wbase + lane] : make_float4(0.f, 0.f, 0.f, 0.f);   // raw {p, m} of the listed cell (coalesced)
   float4 gv4 = ggrid[idx];
   int ck = c % k.rz, cj = (c / k.rz) % k.ry, ci = c / (k.rz * k.ry);
   bool work = live && (gv4.x != 0.f || gv4.y != 0.f || gv4.z != 0.f);
@@ -599,8 +613,8 @@ k_grid_bwd(MpmConst k_, const float4* __restrict__ grid_raw, float4* __restrict_
 
 // ggrid: the cotangent grid G2P^T(substep) scattered into, reversed in place.  clear_grid != null: additionally
 // re-zero `clear_grid` from the block list of `clear_substep` in the same launch.
-void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,
-                     const MpmWs& ws, cudaStream_t st, float4* ggrid, float4* clear_grid, int clear_substep) {
+void launch_grid_bwd(const MpmConst& k, int substep, const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st, float4* ggrid,
+                     float4* clear_grid, int clear_substep) {
   KScope ks_(KC_GRID_BWD, st);
   const int total = k.B * k.nbx * k.nby * k.nbz;
   const int sc = shell_ctas_of(k);
@@ -613,7 +627,7 @@ void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, con
   }
   auto kern = k.sdf_kind == UD_SDF_BOX ? (k.pos_control ? k_grid_bwd<UD_SDF_BOX, 1> : k_grid_bwd<UD_SDF_BOX, 0>)
                                        : (k.pos_control ? k_grid_bwd<UD_SDF_CONTAINER, 1> : k_grid_bwd<UD_SDF_CONTAINER, 0>);
-  kern<<<GRID_BWD_CTAS + clr.ctas, 128, 0, st>>>(k, grid_raw, ggrid, substep, *in, ws.fk_pos, ws.fk_rot, ws.fk_vw, ws.g_fk_pos,
+  kern<<<GRID_BWD_CTAS + clr.ctas, 128, 0, st>>>(k, ws.act_raw + (size_t)(substep - ws.sub0) * k.B * k.G, ggrid, substep, *in, ws.fk_pos, ws.fk_rot, ws.fk_vw, ws.g_fk_pos,
                                                  ws.g_fk_rot, ws.g_fk_v, ws.g_scal,
                                                  ws.act_list + (size_t)(substep - ws.sub0) * k.B * k.G, ws.act_count + substep, clr);
 }

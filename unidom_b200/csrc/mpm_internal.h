@@ -92,8 +92,7 @@ struct MpmWs {
   float* h_s;           // [N] hardness in sorted order
   // state
   float* ps;            // fwd: [24*N_pad]; bwd: [(S+1)*24*N_pad] start-of-substep states (tiles, see above)
-  float4* grid_raw;     // fwd: [2][B*G] (used alternately: the grid launch of substep f re-zeroes the other one);
-                        // bwd: [S*B*G] scattered (p,m)
+  float4* grid_raw;     // [2][B*G] scattered (p, m), used alternately: the grid launch of substep f re-zeroes the other one
   float4* grid_out;     // fwd: == grid_raw; bwd: [S*B*G] updated velocities
   long long* grid_fix;  // deterministic P2G only: [B*G*4] 64-bit fixed-point accumulators of one substep
   int32_t* blk_flag;    // [B*nbx*nby*nbz] 4x4x4 grid blocks that P2G scattered into this substep
@@ -105,6 +104,7 @@ struct MpmWs {
                         // job of the grid update and the face-cell re-zeroing run only for such substeps)
   float* vt_roll;       // fwd only: [12*N_pad] V^T of the previous substep's SVD (warm start)
   int32_t* act_list;    // bwd only: [S][B*G] cells listed by the recompute pass for the grid adjoint
+  float4* act_raw;      // bwd only: [S][B*G] their raw (p, m), in list order (the raw grids do not outlive their substep)
   // windowed adjoint only (ud_mpm_step_bwd_windowed): K-spaced checkpoints and the checkpoint pass's scratch
   float* ckpt_ps;       // [n_win][24*N_pad] start state of substep w*window (slot 0 = the gathered step input)
   float* ckpt_vt;       // [n_win][12*N_pad] V^T entering that substep (SVD warm start)
@@ -185,8 +185,8 @@ void launch_fk_fwd(const MpmConst& k, const ud_mpm_state* in, const float* actio
 void launch_grid_fwd(const MpmConst& k, float4* grid_in, float4* grid_out, const long long* grid_fix, int substep,
                      const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st, float4* clear_grid = nullptr,
                      int clear_substep = 0, bool lists_ready = false);
-void launch_grid_bwd(const MpmConst& k, const float4* grid_raw, int substep, const ud_mpm_state* in,
-                     const MpmWs& ws, cudaStream_t st, float4* ggrid, float4* clear_grid, int clear_substep);
+void launch_grid_bwd(const MpmConst& k, int substep, const ud_mpm_state* in, const MpmWs& ws, cudaStream_t st, float4* ggrid,
+                     float4* clear_grid, int clear_substep);
 void launch_fk_bwd(const MpmConst& k, const ud_mpm_state* in, const float* action,
                    const ud_mpm_state* gout, const MpmWs& ws, cudaStream_t st);
 

@@ -207,6 +207,34 @@ class FoldCloth1ParaEnv(ClothEnv):
         assert self.observation_size == 1545
 
 
+class UnfoldClothEnv(ClothEnv):
+    """core/envs/unfold_cloth1_env.py:40-82 / unfold_cloth3_env.py:40-83: the fold_cloth scene with friction mu = 3,
+    max_steps = 15, observation_size 1544, whose reset is
+        key, _ = split(key); x = lattice + normal(key, x.shape) * 1e-4; state = random_fold(state, step=n_folds)
+    with n_folds = 1 (unfold_cloth1) or 3 (unfold_cloth3).  The noise comes from the reference's own threefry stream
+    (unidom_b200.jaxrng), the fold end points from `rng` (the reference draws them from the global np.random state:
+    pass np.random, or a RandomState seeded like it)."""
+
+    def __init__(self, batch_size, conf=None, aux_reward=False, seed=1, n_folds=3, goal=None, device="cuda", fused=True):
+        from . import confs
+        conf = confs.UnfoldClothConf() if conf is None else conf
+        super().__init__(conf, batch_size, 15, confs.fold_cloth_mask(conf), goal=goal, aux_reward=aux_reward,
+                         device=device, fused=fused)
+        self.n_folds = n_folds
+        assert self.observation_size == 1544
+
+    def reset(self, key=None, rng=None):
+        from . import jaxrng
+        st = self.simulator.reset_jax()
+        k = jaxrng.PRNGKey(0 if key is None else key) if (key is None or np.isscalar(key)) else np.asarray(key, np.uint32)
+        k = jaxrng.split(k)[0]
+        noise = jaxrng.normal(k, tuple(st.x.shape)) * np.float32(0.0001)
+        st = st._replace(x=st.x + torch.as_tensor(noise, dtype=st.x.dtype, device=self.device))
+        self.reset_noisy_x = st.x.clone()                   # the state before the folds (tests compare it bit for bit)
+        st = self.random_fold(st, step=self.n_folds, rng=rng)
+        return self.get_obs(st), st
+
+
 # -------------------------------------------------------------------------------------------------------------------
 # MPM env (core/envs/basic/mpm_env.py) with the push task of core/envs/shape_elasto_plastic.py ("push_plasticine")
 # -------------------------------------------------------------------------------------------------------------------
