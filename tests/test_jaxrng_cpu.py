@@ -37,3 +37,18 @@ def test_cloth_reset_shift_is_the_reference_stream():
     shift = R.normal(key, (2,)) * np.float32(0.05)
     assert key.tolist() == [4146024105, 967050713]
     assert shift.dtype == np.float32 and np.all(np.abs(shift) < 0.25)
+
+
+def test_unfold_reset_noise_and_fold_points_are_the_reference_draws():
+    """unfold_cloth1_env.py:74-79: key, _ = split(PRNGKey(1)); x = lattice + normal(key, x.shape) * 1e-4, then the fold end
+    points from np.random -- against what the reference's own UnfoldCloth1Env.reset drew under the shim
+    (tests/golden/ref_clothenv_unfold1.npz, gen_golden.py::cloth_unfold_case), bit for bit."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_clothenv_unfold1.npz"))
+    k = R.split(R.PRNGKey(int(d["key_seed"])))[0]
+    noise = R.normal(k, d["lattice_x"].shape) * np.float32(0.0001)
+    assert noise.dtype == np.float32
+    assert np.array_equal((d["lattice_x"] + noise).astype(np.float32), d["noisy_x"])
+    rs = np.random.RandomState(int(d["seed"]))
+    P = d["lattice_x"].shape[1]
+    assert np.array_equal(rs.randint(0, P, size=(2,)), d["st_point"]) and np.array_equal(rs.randint(0, P, size=(2,)), d["ed_point"])
