@@ -39,6 +39,10 @@ extern "C" {
 #define UD_SDF_CONTAINER 1  /* core/engine/primitives/container.py:8-16 */
 
 #define UD_P2G_ATOMIC 0        /* vector RED per touched cell (fast, order-nondeterministic)   */
+#define UD_P2G_LIQUID_FAST 0x100 /* flag, OR-ed into p2g_mode: the scene holds material-0 (liquid) particles; they
+                                   then skip the SVD in both passes (J = |det F1|; mpm_simulator.py:241-242 make mu 0).
+                                   Without the flag liquid particles take the general SVD path: same results to
+                                   rounding, only slower.  The kernels of scenes without liquid stay free of the branch. */
 #define UD_P2G_DETERMINISTIC 1 /* same sorted in-CTA segment sums, combined across CTAs with 64-bit
                                   fixed-point integer REDs (associative): bit-reproducible run to run and
                                   between the forward and the adjoint's recompute pass            */

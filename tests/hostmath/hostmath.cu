@@ -124,6 +124,31 @@ void hm_constitutive_plastic(int n, const double* consts, const float* C, const 
   }
 }
 
+// The liquid fast path of P2G / P2G^T (constitutive_post_liquid + constitutive_bwd_liquid: no SVD, J = |det F1|)
+void hm_constitutive_liquid(int n, const double* consts, const float* C, const float* F, const float* gA, const float* gF2,
+                            float* F2, float* affine, float* gC, float* gF) {
+  MpmConst k = make_k(consts);
+  for (int i = 0; i < n; ++i) {
+    Mat3 c, f, ga, gf2, gc, gf;
+    for (int j = 0; j < 9; ++j) {
+      c.m[j] = C[9 * i + j];
+      f.m[j] = F[9 * i + j];
+      ga.m[j] = gA[9 * i + j];
+      gf2.m[j] = gF2[9 * i + j];
+    }
+    Consti o;
+    constitutive_pre(k, c, f, 0.83f, 0.55f, 1.f, 0, o);
+    constitutive_post_liquid(k, c, o);
+    constitutive_bwd_liquid(k, c, f, ga, gf2, gc, gf);
+    for (int j = 0; j < 9; ++j) {
+      F2[9 * i + j] = o.F2.m[j];
+      affine[9 * i + j] = o.affine.m[j];
+      gC[9 * i + j] = gc.m[j];
+      gF[9 * i + j] = gf.m[j];
+    }
+  }
+}
+
 // forward collide / position control on one cell
 void hm_prim_fwd(int pos_control, int kind, float dt, const float* gpos, const float* prim, float softness,
                  const float* vin, float* vout) {

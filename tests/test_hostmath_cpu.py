@@ -95,6 +95,8 @@ def test_constitutive_forward_and_reverse_vs_oracle(hm, material):
     consts = np.array([conf.dt, conf.dx, conf.inv_dx, conf.p_mass, conf.p_vol], np.float64)
     Cm = (rng.randn(n, 3, 3) * 3).astype(np.float32)
     F = (np.eye(3)[None] + 0.25 * rng.randn(n, 3, 3)).astype(np.float32)   # spread sigmas across the clip range
+    if material == 0:
+        F[:40, 0] *= -1                                                   # reflections: det F < 0, J = |det|
     h = rng.uniform(0.05, 6.0, n).astype(np.float32)
     mat = np.full(n, material, np.int32)
     gA = rng.randn(n, 3, 3).astype(np.float32)
@@ -128,6 +130,20 @@ def test_constitutive_forward_and_reverse_vs_oracle(hm, material):
     assert cosF > 0.99999
     assert abs(gmu.astype(np.float64).sum() - float(rmu)) < 1e-4 * (abs(float(rmu)) + 1e-6)
     assert abs(gla.astype(np.float64).sum() - float(rla)) < 1e-4 * (abs(float(rla)) + 1e-6)
+    if material == 0:
+        # the liquid fast path of P2G / P2G^T: no SVD at all, J = |det F1| by pivoted elimination and
+        # dF1 = gJ sign(det) cof(F1) -- against the generic SVD path above and the fp64 oracle.  Some of the random F1
+        # have a negative determinant (reflections), which the sign covers.
+        fast = {k: np.empty((n, 3, 3), np.float32) for k in ("F2", "affine", "gC", "gF")}
+        hm.hm_constitutive_liquid(n, fp(consts), fp(Cm), fp(F), fp(gA), fp(gF2), fp(fast["F2"]), fp(fast["affine"]),
+                                  fp(fast["gC"]), fp(fast["gF"]))
+        assert (np.linalg.det(F.astype(np.float64)) < 0).sum() > 0
+        assert rel(fast["F2"], F2) < 5e-6
+        assert rel(fast["affine"], aff) < 2e-5
+        assert rel(fast["gC"], rC) < 1e-4
+        assert rel(fast["gF"], rF) < 1e-4          # no SVD-VJP conditioning on this path
+        assert np.abs(fast["gF"] - outs["gF"]).max() < 2e-4 * np.abs(outs["gF"]).max()
+        assert np.abs(fast["affine"] - outs["affine"]).max() < 2e-5 * np.abs(outs["affine"]).max()
     if material == 2:
         # the adjoint kernel's plastic fast path: the same chain carried out in the frame of the SVD
         # (plastic_affine + constitutive_bwd_plastic, 8 matrix products instead of 21) against the generic path

@@ -60,6 +60,45 @@ def test_sort_bins_bit_exact(built_lib):
     assert np.array_equal(perm.cpu().numpy(), ref_perm)
 
 
+def test_sort_bins_crowded_cells_bit_exact(built_lib):
+    """Cells holding thousands of particles (whip_rope at density 25: 2 025 per cell) are ranked by k_rank_big (bitmap +
+    popcount scan) instead of the per-particle counting loop: same stable argsort, bit for bit.  Three layouts: particle
+    indices of a cell contiguous (a lattice, like add_box), interleaved over the whole index range (spread beyond
+    the bitmap -> the cooperative fallback) and a mix with ordinary sparse cells."""
+    conf = _conf()
+    B = 2
+    rng = np.random.RandomState(11)
+    n = 150000
+    sim = _sim(conf, B)
+    sim.n_particles = n
+    dx = 1.0 / conf.inv_dx
+    x = np.empty((B, n, 3), np.float32)
+    # env 0: 40 crowded cells, each a contiguous index range; the rest spread thinly over the grid
+    cells = rng.randint(4, 28, size=(60, 3))
+    owner = np.minimum(np.arange(n) // 3000, 59)
+    x[0] = (cells[owner] + 0.5 + rng.uniform(0.01, 0.98, (n, 3))) * dx
+    thin = rng.rand(n) < 0.2
+    x[0][thin] = rng.uniform(0.05, 0.6, (int(thin.sum()), 3))
+    # env 1: the same cells but every cell's particles interleaved over the whole index range
+    owner1 = rng.randint(0, 12, n)
+    x[1] = (cells[owner1] + 0.5 + rng.uniform(0.01, 0.98, (n, 3))) * dx
+    xt = torch.from_numpy(x).cuda()
+    base, key, perm = sim.sort_bins(xt)
+    inv_dx = np.float32(conf.inv_dx)
+    ref_base = (x * inv_dx - np.float32(0.5)).astype(np.int32)
+    assert np.array_equal(base.cpu().numpy(), ref_base)
+    res = np.array(conf.res)
+    cb = np.clip(ref_base, 0, res - 1)
+    nb = (res + 3) // 4
+    blk = ((cb[..., 0] >> 2) * nb[1] + (cb[..., 1] >> 2)) * nb[2] + (cb[..., 2] >> 2)
+    ref_key = (blk << 6) | ((cb[..., 0] & 3) << 4) | ((cb[..., 1] & 3) << 2) | (cb[..., 2] & 3)
+    assert np.array_equal(key.cpu().numpy(), ref_key.astype(np.int32))
+    occ = np.bincount(ref_key[1])
+    assert occ.max() > 5000                                                       # crowded for real
+    ref_perm = np.stack([np.argsort(ref_key[b], kind="stable") for b in range(B)]).astype(np.int32)
+    assert np.array_equal(perm.cpu().numpy(), ref_perm)
+
+
 @pytest.mark.parametrize("material,n_prim,pos_control", [(2, 1, False), (1, 2, False), (0, 1, False), (1, 1, True)])
 def test_step_forward_parity(built_lib, material, n_prim, pos_control):
     conf = _conf(steps=8, n_primitive=n_prim, use_position_control=pos_control)
@@ -143,15 +182,23 @@ def _run_grad(step_fn, state, action, cot, n_prim, to_dev):
 
 @pytest.mark.parametrize("material,n_prim,pos_control,cot_scale",
                          [(2, 1, False, 1e-3), (1, 2, False, 1e-3), (0, 1, False, 1e-3), (1, 1, True, 1e-3),
-                          (2, 1, False, 10.0)])
+                          (2, 1, False, 10.0), (-1, 1, False, 1e-3)])
 def test_step_backward_parity(built_lib, material, n_prim, pos_control, cot_scale):
     """Adjoint of one step (4 substeps) against torch autograd of the oracle.  cot_scale=1e-3 keeps
-    the per-env gradient norm < 1 (norm_grad is a pass-through), 10.0 exercises the renormalisation."""
+    the per-env gradient norm < 1 (norm_grad is a pass-through), 10.0 exercises the renormalisation.
+    material -1: liquid, elastic and plastic particles interleaved at random, so that nearly every warp mixes the
+    SVD-free liquid path (UD_P2G_LIQUID_FAST) with the two SVD paths."""
     conf = _conf(steps=4, n_primitive=n_prim, use_position_control=pos_control)
     B = 2
     sim = _sim(conf, B)
     kw = dict(v_scale=0.05, c_scale=1.0, f_scale=0.02, ylow=0.045) if material == 0 else {}
-    st = util.mini_plasticine(sim, B, seed=10 + material, material=material, **kw)
+    st = util.mini_plasticine(sim, B, seed=10 + material, material=2 if material < 0 else material, **kw)
+    if material < 0:
+        rs = np.random.RandomState(3)
+        sim.material = torch.from_numpy(rs.randint(0, 3, sim.material.shape[0]).astype(np.int32))
+        sim._material_dev = sim.material.to(st.x.device).contiguous()
+        from unidom_b200 import _lib
+        assert sim.params().p2g_mode & _lib.UD_P2G_LIQUID_FAST
     dev = st.x.device
     act = (_actions(B, n_prim, seed=4) * 0.8).to(dev)
     g = torch.Generator().manual_seed(7)

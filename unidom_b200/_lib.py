@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libunidom_b200.so")
 UD_MAX_PRIM = 4
 UD_SDF_BOX, UD_SDF_CONTAINER = 0, 1
 UD_P2G_ATOMIC, UD_P2G_DETERMINISTIC = 0, 1
+UD_P2G_LIQUID_FAST = 0x100
 
 _fp = C.c_void_p  # device pointers travel as integers
 

@@ -58,7 +58,8 @@ bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k) {
   if (p->res[0] < 1 || p->res[1] < 1 || p->res[2] < 1 || p->n_grid < 1) return false;
   if (p->n_primitive < 0 || p->n_primitive > UD_MAX_PRIM) return false;
   if (p->sdf_kind != UD_SDF_BOX && p->sdf_kind != UD_SDF_CONTAINER) return false;
-  if (p->p2g_mode != UD_P2G_ATOMIC && p->p2g_mode != UD_P2G_DETERMINISTIC) return false;
+  const int p2g_mode = p->p2g_mode & ~UD_P2G_LIQUID_FAST;
+  if (p2g_mode != UD_P2G_ATOMIC && p2g_mode != UD_P2G_DETERMINISTIC) return false;
   if (!(p->dt > 0) || !(p->dx > 0) || !(p->inv_dx > 0) || !(p->p_mass > 0) || !(p->p_vol > 0)) return false;
   long long N = (long long)p->num_envs * p->n_particles;
   long long G = (long long)p->res[0] * p->res[1] * p->res[2];
@@ -91,7 +92,8 @@ bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k) {
   k->n_prim = p->n_primitive;
   k->sdf_kind = p->sdf_kind;
   k->pos_control = p->use_position_control ? 1 : 0;
-  k->p2g_mode = p->p2g_mode;
+  k->p2g_mode = p2g_mode;
+  k->liquid_fast = (p->p2g_mode & UD_P2G_LIQUID_FAST) ? 1 : 0;
   k->mark = g_mark;
   return true;
 }
@@ -122,7 +124,8 @@ size_t mpm_carve(const ud_mpm_params*, const MpmConst& k, bool bwd, void* base, 
   w.perm = (int32_t*)take(4 * N);
   w.inv_perm = (int32_t*)take(4 * N);
   w.cell_start = (int32_t*)take(4 * (size_t)k.B * (k.NK + 1));
-  w.cursor = (int32_t*)take(4 * (size_t)k.B * k.NK);
+  w.cursor = (int32_t*)take(4 * ((size_t)k.B * k.NK + 1));   // [B*NK] + the crowded-cell counter of k_rank
+  w.big_list = (int32_t*)take(4 * 2 * (N / 160 + 1));        // (env, key) of the cells k_rank leaves to k_rank_big
   w.chunk_sum = (int32_t*)take(4 * (size_t)k.B * ((k.NK + 1023) / 1024));
   w.mat_s = (int32_t*)take(4 * N);
   w.h_s = (float*)take(4 * N);

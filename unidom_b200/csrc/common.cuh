@@ -54,6 +54,41 @@ UD_DEV Mat3 mat_zero() {
   return r;
 }
 
+// Cofactor matrix cof(A)_ij = d det(A) / d A_ij (= det(A) A^-T).
+UD_DEV Mat3 mat_cofactor(const Mat3& a) {
+  Mat3 r;
+  r(0, 0) = a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1);
+  r(0, 1) = a(1, 2) * a(2, 0) - a(1, 0) * a(2, 2);
+  r(0, 2) = a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0);
+  r(1, 0) = a(0, 2) * a(2, 1) - a(0, 1) * a(2, 2);
+  r(1, 1) = a(0, 0) * a(2, 2) - a(0, 2) * a(2, 0);
+  r(1, 2) = a(0, 1) * a(2, 0) - a(0, 0) * a(2, 1);
+  r(2, 0) = a(0, 1) * a(1, 2) - a(0, 2) * a(1, 1);
+  r(2, 1) = a(0, 2) * a(1, 0) - a(0, 0) * a(1, 2);
+  r(2, 2) = a(0, 0) * a(1, 1) - a(0, 1) * a(1, 0);
+  return r;
+}
+// det(A) by one elimination step with partial pivoting on column 0 and the 2x2 determinant of the rest: relative error
+// ~ eps * cond(A) like an SVD's product of singular values (a plain cofactor expansion loses cond(A)^2).
+UD_DEV float det3_pivoted(const Mat3& a) {
+  float r0[3] = {a.m[0], a.m[1], a.m[2]}, r1[3] = {a.m[3], a.m[4], a.m[5]}, r2[3] = {a.m[6], a.m[7], a.m[8]};
+  float sg = 1.f;
+  if (fabsf(r1[0]) > fabsf(r0[0])) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const float t = r0[i]; r0[i] = r1[i]; r1[i] = t; }
+    sg = -sg;
+  }
+  if (fabsf(r2[0]) > fabsf(r0[0])) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const float t = r0[i]; r0[i] = r2[i]; r2[i] = t; }
+    sg = -sg;
+  }
+  const float inv = r0[0] != 0.f ? 1.f / r0[0] : 0.f;
+  const float m1 = r1[0] * inv, m2 = r2[0] * inv;
+  const float b11 = r1[1] - m1 * r0[1], b12 = r1[2] - m1 * r0[2], b21 = r2[1] - m2 * r0[1], b22 = r2[2] - m2 * r0[2];
+  return sg * r0[0] * (b11 * b22 - b12 * b21);
+}
+
 // ---------------------------------------------------------------------------------------------
 // 3x3 SVD  A = U diag(s) V^T,  s descending >= 0  (replaces jnp.linalg.svd, svd_safe_batch.py:51).
 // One-sided (Hestenes) Jacobi: rotate column pairs of B = A V until orthogonal.  Fixed sweep count,

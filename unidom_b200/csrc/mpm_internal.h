@@ -87,7 +87,8 @@ struct MpmWs {
   int32_t* tmp_idx;     // [N]
   int32_t* perm;        // [N] sorted slot -> original particle index (per env)
   int32_t* cell_start;  // [B*(NK+1)]
-  int32_t* cursor;      // [B*NK]
+  int32_t* cursor;      // [B*NK + 1]
+  int32_t* big_list;    // [2 * (N / RANK_BIG + 1)]
   int32_t* mat_s;       // [N] material in sorted order
   float* h_s;           // [N] hardness in sorted order
   // state

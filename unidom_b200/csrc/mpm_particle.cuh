@@ -18,6 +18,7 @@ struct MpmConst {
   float gdt[3];              // float(dt)*float(gravity)     (:285)
   float sig_lo, sig_hi;      // float(1-2.5e-2*10), float(1+4.5e-3*100)  (:250)
   int n_prim, sdf_kind, pos_control, p2g_mode;
+  int liquid_fast;           // UD_P2G_LIQUID_FAST: kernels with the SVD-free liquid path (template LIQ)
   int mark;  // development switch: 0 no block marks (timing only, wrong results), 1 every (segment,node), 2 corner nodes
 };
 
@@ -154,6 +155,53 @@ UD_DEV void constitutive_post(const MpmConst& k, const Mat3& C, Consti& o, bool 
       float st = 2.f * o.mu * M(i, j) + (i == j ? iso : 0.f);
       o.affine(i, j) = cs * st + k.p_mass * C(i, j);
     }
+}
+
+// Liquid particle (material 0: mu = 0, la = 1, no clip, F2 = F1; mpm_simulator.py:241-242): the deviatoric term is
+// 2 * 0 * M = 0 and the only thing left of the SVD is J = prod(sig) = |det F1|, so neither pass factorises F1.
+// Cotangents: dU = dV = 0 and d sig_i = gJ prod_{j != i} sig_j, for which the reference's SVD VJP
+// (svd_safe_batch.py:95-100) reduces to U diag(d sig) Vt = gJ sign(det F1) cof(F1).
+UD_DEV void constitutive_post_liquid(const MpmConst& k, const Mat3& C, Consti& o) {
+  o.J = fabsf(det3_pivoted(o.F1));
+  o.F2 = o.F1;
+  const float iso = o.la * o.J * (o.J - 1.f);
+  const float cs = k.c_stress_mul / k.c_stress_div;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) o.affine(i, j) = cs * (i == j ? iso : 0.f) + k.p_mass * C(i, j);
+}
+// affine of a liquid particle from its input state (the adjoint's gather phase)
+UD_DEV void liquid_affine(const MpmConst& k, const Mat3& C, const Mat3& F, Mat3& affine) {
+  Consti o;
+  constitutive_pre(k, C, F, 0.f, 0.f, 1.f, 0, o);
+  constitutive_post_liquid(k, C, o);
+  affine = o.affine;
+}
+// Reverse of the liquid constitutive step; d/d(state.mu), d/d(state.lamda) are zero (both are overwritten by constants).
+UD_DEV void constitutive_bwd_liquid(const MpmConst& k, const Mat3& C, const Mat3& F, const Mat3& gA, const Mat3& gF2out,
+                                    Mat3& gC, Mat3& gF) {
+  Mat3 A;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A.m[i] = k.dt * C.m[i];
+  A.m[0] += 1.f;
+  A.m[4] += 1.f;
+  A.m[8] += 1.f;
+  const Mat3 F1 = mat_mul(A, F);
+  const float det = det3_pivoted(F1);
+  const float J = fabsf(det);
+  const float cs = k.c_stress_mul / k.c_stress_div;
+  const float trS = gA.m[0] * cs + gA.m[4] * cs + gA.m[8] * cs;
+  const float gJ = (2.f * J - 1.f) * trS;   // la = 1
+  const float gd = det < 0.f ? -gJ : gJ;
+  const Mat3 cof = mat_cofactor(F1);
+  Mat3 gF1;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) gF1.m[i] = gF2out.m[i] + gd * cof.m[i];
+  const Mat3 gCf = mat_mul_nt(gF1, F);
+  gF = mat_mul_tn(A, gF1);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) gC.m[i] = k.p_mass * gA.m[i] + k.dt * gCf.m[i];
 }
 
 // mpm_simulator.py:238-268

@@ -1,6 +1,7 @@
 // Particle-side kernels of the MLS-MPM step: per-frame binning, P2G scatter, G2P gather and their
 // adjoints.  sm_100a.  Reference: DaXBench/daxbench/core/engine/mpm_simulator.py:178-330.
 #include <algorithm>
+#include <climits>
 #include <type_traits>
 
 #include "mpm_internal.h"
@@ -193,8 +194,12 @@ __global__ void k_place(MpmConst k, const int32_t* __restrict__ keys, const int3
   tmp_idx[(size_t)env * k.n + slot] = g - env * k.n;
 }
 
+constexpr int RANK_BIG = 160;          // occupancy above which a cell is ranked by k_rank_big
+constexpr int RANK_BIG_BLOCK = 256;
+constexpr int RANK_BIG_WORDS = 4096;   // bitmap words per CTA: index spread up to 131 072 inside one cell
 __global__ void k_rank(MpmConst k, const int32_t* __restrict__ keys, const int32_t* __restrict__ cell_start,
-                       const int32_t* __restrict__ tmp_idx, int32_t* __restrict__ perm, int32_t* __restrict__ inv_perm) {
+                       const int32_t* __restrict__ tmp_idx, int32_t* __restrict__ perm, int32_t* __restrict__ inv_perm,
+                       int32_t* __restrict__ big_list, int32_t* __restrict__ big_count) {
   UD_PARTICLE_INDEX(k, env, g);
   if (!live_) return;
   int p = tmp_idx[g];
@@ -202,10 +207,117 @@ __global__ void k_rank(MpmConst k, const int32_t* __restrict__ keys, const int32
   const int32_t* cs = cell_start + (size_t)env * (k.NK + 1);
   int lo = cs[key], hi = cs[key + 1];
   const int32_t* seg = tmp_idx + (size_t)env * k.n;
+  if (hi - lo > RANK_BIG) {   // a crowded cell: the count below is quadratic in the occupancy -> k_rank_big
+    if (g - env * k.n == lo) {
+      const int e = atomicAdd(big_count, 1);
+      big_list[2 * e] = env;
+      big_list[2 * e + 1] = key;
+    }
+    return;
+  }
   int rank = 0;
   for (int j = lo; j < hi; ++j) rank += seg[j] < p;
   perm[(size_t)env * k.n + lo + rank] = p;
   inv_perm[(size_t)env * k.n + p] = lo + rank;   // sorted slot of original particle p (the un-sort gathers by it)
+}
+
+// Stable ranks inside the crowded cells k_rank listed (a rope or a settled pile puts thousands of particles into one
+// cell: whip_rope at add_box density 25 has 2 025 per cell, where the per-particle count took 1.2 ms per sort).  One CTA
+// per listed cell: the cell's particle indices set bits in a shared-memory bitmap over [min index, max index], a
+// popcount scan of the bitmap words gives every index its rank among the cell's indices: O(occupancy + index spread / 32).
+// A cell whose indices spread over more than 32 * RANK_BIG_WORDS falls back to the counting loop, spread over the CTA.
+__global__ void __launch_bounds__(RANK_BIG_BLOCK)
+k_rank_big(MpmConst k, const int32_t* __restrict__ cell_start, const int32_t* __restrict__ tmp_idx,
+           const int32_t* __restrict__ big_list, const int32_t* __restrict__ big_count, int32_t* __restrict__ perm,
+           int32_t* __restrict__ inv_perm) {
+  __shared__ unsigned bits[RANK_BIG_WORDS];
+  __shared__ int before[RANK_BIG_WORDS];
+  __shared__ int red[2][RANK_BIG_BLOCK / 32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nbig = *big_count;
+  for (int e = blockIdx.x; e < nbig; e += gridDim.x) {
+    const int env = big_list[2 * e], key = big_list[2 * e + 1];
+    const int32_t* cs = cell_start + (size_t)env * (k.NK + 1);
+    const int lo = cs[key], hi = cs[key + 1];
+    const int32_t* seg = tmp_idx + (size_t)env * k.n;
+    int32_t* pm = perm + (size_t)env * k.n;
+    int32_t* ip = inv_perm + (size_t)env * k.n;
+    int mn = INT_MAX, mx = -1;
+    for (int j = lo + tid; j < hi; j += RANK_BIG_BLOCK) {
+      const int p = seg[j];
+      mn = min(mn, p);
+      mx = max(mx, p);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    __syncthreads();   // the previous cell's readers of bits / before / red are done
+    if (lane == 0) {
+      red[0][wid] = mn;
+      red[1][wid] = mx;
+    }
+    __syncthreads();
+    mn = red[0][0];
+    mx = red[1][0];
+#pragma unroll
+    for (int i = 1; i < RANK_BIG_BLOCK / 32; ++i) {
+      mn = min(mn, red[0][i]);
+      mx = max(mx, red[1][i]);
+    }
+    const int w0 = mn >> 5, nw = (mx >> 5) - w0 + 1;
+    if (nw > RANK_BIG_WORDS) {   // CTA-uniform
+      for (int j = lo + tid; j < hi; j += RANK_BIG_BLOCK) {
+        const int p = seg[j];
+        int rank = 0;
+        for (int i = lo; i < hi; ++i) rank += seg[i] < p;
+        pm[lo + rank] = p;
+        ip[p] = lo + rank;
+      }
+      continue;
+    }
+    for (int i = tid; i < nw; i += RANK_BIG_BLOCK) bits[i] = 0u;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int j = lo + tid; j < hi; j += RANK_BIG_BLOCK) {
+      const int p = seg[j];
+      atomicOr(&bits[(p >> 5) - w0], 1u << (p & 31));
+    }
+    __syncthreads();
+    for (int base = 0; base < nw; base += RANK_BIG_BLOCK) {   // exclusive popcount scan, RANK_BIG_BLOCK words per round
+      const int i = base + tid;
+      const int v = i < nw ? __popc(bits[i]) : 0;
+      int incl = v;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        incl += lane >= off ? t : 0;
+      }
+      if (lane == 31) red[0][wid] = incl;
+      __syncthreads();
+      int wb = 0, tot = 0;
+#pragma unroll
+      for (int q = 0; q < RANK_BIG_BLOCK / 32; ++q) {
+        const int t = red[0][q];
+        wb += q < wid ? t : 0;
+        tot += t;
+      }
+      const int carry = carry_s;
+      if (i < nw) before[i] = carry + wb + incl - v;
+      __syncthreads();
+      if (tid == 0) carry_s = carry + tot;
+      __syncthreads();
+    }
+    for (int j = lo + tid; j < hi; j += RANK_BIG_BLOCK) {
+      const int p = seg[j];
+      const int wi = (p >> 5) - w0;
+      const int rank = before[wi] + __popc(bits[wi] & ((1u << (p & 31)) - 1u));
+      pm[lo + rank] = p;
+      ip[p] = lo + rank;
+    }
+  }
 }
 
 __global__ void k_identity_perm(MpmConst k, int32_t* __restrict__ perm, int32_t* __restrict__ inv_perm) {
@@ -219,15 +331,18 @@ void launch_sort(const MpmConst& k, const float* x_aos, const MpmWs& ws, int32_t
     k_identity_perm<<<pgrid(k, 256), 256, 0, st>>>(k, ws.perm, ws.inv_perm);
     return;
   }
-  KScope ks_(KC_SORT, st, 7);
+  KScope ks_(KC_SORT, st, 8);
   cudaMemsetAsync(ws.cell_start, 0, sizeof(int32_t) * (size_t)k.B * (k.NK + 1), st);
-  cudaMemsetAsync(ws.cursor, 0, sizeof(int32_t) * (size_t)k.B * k.NK, st);
+  cudaMemsetAsync(ws.cursor, 0, sizeof(int32_t) * ((size_t)k.B * k.NK + 1), st);   // + the crowded-cell counter
   k_keys<<<pgrid(k, 256), 256, 0, st>>>(k, x_aos, ws.keys, ws.cell_start, out_base);
   const dim3 sg(cdiv(k.NK, SCAN_CHUNK), k.B);
   k_scan_sums<<<sg, SCAN_CHUNK, 0, st>>>(k, ws.cell_start, ws.chunk_sum);
   k_scan_chunks<<<sg, SCAN_CHUNK, 0, st>>>(k, ws.cell_start, ws.chunk_sum);
   k_place<<<pgrid(k, 256), 256, 0, st>>>(k, ws.keys, ws.cell_start, ws.cursor, ws.tmp_idx);
-  k_rank<<<pgrid(k, 256), 256, 0, st>>>(k, ws.keys, ws.cell_start, ws.tmp_idx, ws.perm, ws.inv_perm);
+  int32_t* big_count = ws.cursor + (size_t)k.B * k.NK;
+  k_rank<<<pgrid(k, 256), 256, 0, st>>>(k, ws.keys, ws.cell_start, ws.tmp_idx, ws.perm, ws.inv_perm, ws.big_list, big_count);
+  k_rank_big<<<2 * num_sms(), RANK_BIG_BLOCK, 0, st>>>(k, ws.cell_start, ws.tmp_idx, ws.big_list, big_count, ws.perm,
+                                                       ws.inv_perm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -592,7 +707,8 @@ static_assert(SV_VT == 12 && PS_NQ == 6, "p2g_issue_loads reads V^T as whole qua
 // substep's V^T), plastic clip, stress; stores F' (+ V^T for the next warm start, or the whole SVD in the recompute
 // pass).  Returns the stencil and the affine scatter value at node (a,b,c):
 //   wt * (u + a*Ac[0] + b*Ac[1] + c*Ac[2]),  u = p_mass v - dx A fx,  Ac[j] = dx * column j of A
-__device__ __forceinline__ void p2g_front_loaded(const MpmConst& k, int gp, bool wr, const P2gIn& in, bool warm,
+template <bool LIQ>
+__device__ __forceinline__ void p2g_front_loaded(const MpmConst& k, int gp, bool wr, bool live, const P2gIn& in, bool warm,
                                                  float* __restrict__ ps_out, float* __restrict__ vt_out,
                                                  float* __restrict__ svd_out, Stencil& st, float u[3], float Ac[3][3]) {
   const float sq[PS_NCOMP] = {in.q[0].x, in.q[0].y, in.q[0].z, in.q[0].w, in.q[1].x, in.q[1].y, in.q[1].z, in.q[1].w,
@@ -618,12 +734,38 @@ __device__ __forceinline__ void p2g_front_loaded(const MpmConst& k, int gp, bool
   make_stencil(x, k.inv_dx, st);
   Consti o;
   constitutive_pre(k, C, F, in.mu, in.la, in.h, in.mat, o);
-  svd3_ws(o.F1, o.U, o.s, o.Vt, warm, vt0);
+  // A liquid particle needs no factorisation (constitutive_post_liquid).  A warp of liquid particles skips the SVD and
+  // the V^T / SVD stores (every caller runs whole warps through here); in a mixed warp the liquid lanes ride along
+  // and ignore the result.  P2G^T decides per particle the same way and never reads a liquid particle's SVD.
+  const bool liq = LIQ && o.liquid;
+  const bool no_svd = LIQ && __all_sync(0xffffffffu, liq || !live);
+  if (!no_svd) svd3_ws(o.F1, o.U, o.s, o.Vt, warm, vt0);
 #ifdef UD_NO_PLASTIC_FAST
-  constitutive_post(k, C, o);
+  const bool all_plastic = false;
 #else
-  constitutive_post(k, C, o, __all_sync(0xffffffffu, o.plastic));   // every caller runs whole warps through here
+  const bool all_plastic = __all_sync(0xffffffffu, o.plastic);
 #endif
+  // Only warp-uniform branches here: a per-lane branch on `liq` ended with nvcc 12.9 re-materialising the vote of
+  // `all_plastic` inside the non-liquid side (VOTE.ALL behind WARPSYNC.COLLECTIVE in divergent code: a warp mixing liquid
+  // with other particles deadlocked).  A mixed warp therefore runs the general path on every lane and the liquid lanes
+  // then take their own J = |det F1| through selects, so that forward and P2G^T agree on it bit for bit.
+  if (no_svd) {
+    constitutive_post_liquid(k, C, o);
+    vt_out = svd_out = nullptr;
+  } else {
+    constitutive_post(k, C, o, all_plastic);
+    if (LIQ) {
+      Consti ol;
+      ol.F1 = o.F1;
+      ol.la = 1.f;
+      constitutive_post_liquid(k, C, ol);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        o.affine.m[c] = liq ? ol.affine.m[c] : o.affine.m[c];
+        o.F2.m[c] = liq ? ol.F2.m[c] : o.F2.m[c];
+      }
+    }
+  }
   if (wr) {   // padding lanes of an env's last tile write too: the next substep's dead lanes read initialised memory
     store_comps<PS_F, 9, PS_NQ>(ps_out, gp, o.F2.m);
     if (vt_out) {
@@ -653,7 +795,8 @@ __device__ __forceinline__ void p2g_front_loaded(const MpmConst& k, int gp, bool
 }
 // load + front half (the one-tile-per-warp kernels): every global load of the particle is issued before the first one
 // is consumed (one DRAM round trip per warp, not three)
-__device__ __forceinline__ void p2g_front(const MpmConst& k, int env, int g, int gp, bool wr, const float* __restrict__ ps_in,
+template <bool LIQ>
+__device__ __forceinline__ void p2g_front(const MpmConst& k, int env, int g, int gp, bool wr, bool live, const float* __restrict__ ps_in,
                                           float* __restrict__ ps_out, const float* __restrict__ mu_s,
                                           const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
                                           const float* __restrict__ h_s, const float* __restrict__ vt_in,
@@ -661,7 +804,7 @@ __device__ __forceinline__ void p2g_front(const MpmConst& k, int env, int g, int
                                           Stencil& st, float u[3], float Ac[3][3]) {
   P2gIn in;
   p2g_issue_loads(env, g, gp, ps_in, mu_s, la_s, mat_s, h_s, vt_in, vt_svd, in);
-  p2g_front_loaded(k, gp, wr, in, vt_in != nullptr, ps_out, vt_out, svd_out, st, u, Ac);
+  p2g_front_loaded<LIQ>(k, gp, wr, live, in, vt_in != nullptr, ps_out, vt_out, svd_out, st, u, Ac);
 }
 
 // MODE 0: CTA-staged scatter + fp32 vector REDs; 1: staged + 64-bit fixed-point REDs (deterministic);
@@ -680,7 +823,7 @@ k_p2g(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
   UD_PARTICLE_INDEX(k, env, g);
   Stencil st;
   float u[3], Ac[3][3];
-  p2g_front(k, env, g, gp, slot_ < k.n_pad, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, vt_svd != 0, st, u, Ac);
+  p2g_front<false>(k, env, g, gp, slot_ < k.n_pad, live_, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, vt_svd != 0, st, u, Ac);
   constexpr bool DET = MODE == 1;
   int row = 0;
   if (MODE != 2)
@@ -940,7 +1083,7 @@ __device__ __forceinline__ void p2g_stage_row(const Stencil& st, const float u[3
 constexpr int P2GW_BLOCK = 128;   // 4 independent warps per CTA (the CTA is only the unit shared memory is carved in)
 constexpr int P2GW_MIN_BLOCKS = 4;  // resident CTAs per SM = what the 14 KB staging tile per warp leaves room for
 // One tile (32 particles) per warp, one CTA per 4 tiles: the A/B partner of k_p2g_pers (ud_tuning_set("pers", 0)).
-template <bool DET>
+template <bool DET, bool LIQ>
 __global__ void __launch_bounds__(P2GW_BLOCK, P2GW_MIN_BLOCKS)
 k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
            const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
@@ -955,7 +1098,7 @@ k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
   {
     Stencil st;
     float u[3], Ac[3][3];
-    p2g_front(k, env, g, gp, true, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, vt_svd_i != 0, st, u, Ac);
+    p2g_front<LIQ>(k, env, g, gp, true, live_, ps_in, ps_out, mu_s, la_s, mat_s, h_s, vt_in, vt_out, svd_out, vt_svd_i != 0, st, u, Ac);
     const WarpGroup wg = warp_group(k, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base, live_, seg);
     float4* genv = grid + (size_t)env * k.G * (DET ? 2 : 1);   // DET: the int64 accumulator array (32 B per cell)
     float4* myrow = tile + wg.row * WARP_TILE_NODES;
@@ -971,7 +1114,7 @@ k_p2g_warp(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
 // Persistent variant: one CTA slot per resident CTA, every warp walks the tiles w, w + W, w + 2W, ... and issues the
 // loads of its NEXT tile before it starts computing the current one, so a tile's DRAM latency (12 % of the one-tile
 // kernel's stall samples sat on the first use of x) is hidden behind a whole tile of arithmetic.
-template <bool DET>
+template <bool DET, bool LIQ>
 __global__ void __launch_bounds__(P2GW_BLOCK, P2GW_MIN_BLOCKS)
 k_p2g_pers(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ grid,
            const float* __restrict__ mu_s, const float* __restrict__ la_s, const int32_t* __restrict__ mat_s,
@@ -1006,7 +1149,7 @@ k_p2g_pers(MpmConst k, const float* ps_in, float* ps_out, float4* __restrict__ g
     }
     Stencil st;
     float u[3], Ac[3][3];
-    p2g_front_loaded(k, gp, true, cur, warm, ps_out, vt_out, svd_out, st, u, Ac);
+    p2g_front_loaded<LIQ>(k, gp, true, live_, cur, warm, ps_out, vt_out, svd_out, st, u, Ac);
     const WarpGroup wg = warp_group(k, live_ ? (base_key(st.base) & ~DEAD_KEY) : DEAD_KEY, st.base, live_, seg);
     float4* genv = grid + (size_t)env * k.G * (DET ? 2 : 1);   // DET: the int64 accumulator array (32 B per cell)
     float4* myrow = tile + wg.row * WARP_TILE_NODES;
@@ -1039,20 +1182,20 @@ static BlkList blk_list_of(const MpmConst& k, const MpmWs& ws, int substep) {
   return bl;
 }
 
-template <bool DET>
+template <bool DET, bool LIQ>
 static void launch_p2g_warp(const MpmConst& k, const float* ps_in, float* ps_out, float4* grid, const float* mu_s,
                             const float* la_s, const float* vt_in, float* vt_out, float* svd_out, int substep,
                             const MpmWs& ws, cudaStream_t st, bool vt_svd) {
   const size_t smem = WARP_TILE_BYTES * (P2GW_BLOCK / 32);
   // per-DEVICE attribute (one host thread per device under pmap): set on every launch
   if (g_pers) {
-    cudaFuncSetAttribute(k_p2g_pers<DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_p2g_pers<DET><<<persistent_ctas(k, P2GW_BLOCK / 32, P2GW_MIN_BLOCKS), P2GW_BLOCK, smem, st>>>(
+    cudaFuncSetAttribute(k_p2g_pers<DET, LIQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_p2g_pers<DET, LIQ><<<persistent_ctas(k, P2GW_BLOCK / 32, P2GW_MIN_BLOCKS), P2GW_BLOCK, smem, st>>>(
         k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in, vt_out, svd_out, (int)vt_svd, blk_list_of(k, ws, substep));
     return;
   }
-  cudaFuncSetAttribute(k_p2g_warp<DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_p2g_warp<DET><<<pgrid(k, P2GW_BLOCK), P2GW_BLOCK, smem, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in,
+  cudaFuncSetAttribute(k_p2g_warp<DET, LIQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_p2g_warp<DET, LIQ><<<pgrid(k, P2GW_BLOCK), P2GW_BLOCK, smem, st>>>(k, ps_in, ps_out, grid, mu_s, la_s, ws.mat_s, ws.h_s, vt_in,
                                                                   vt_out, svd_out, (int)vt_svd, blk_list_of(k, ws, substep));
 }
 
@@ -1066,8 +1209,10 @@ void launch_p2g(const MpmConst& k, const float* ps_in, float* ps_out, float4* gr
   const bool vt_svd = svd_out != nullptr && !vt_in_is_vt;   // layout of vt_in: previous substep's SVD tile / V^T buffer
   if (tuning_stage() && g_warp_nw) {
     float4* fix = reinterpret_cast<float4*>(ws.grid_fix);
-    if (fix) launch_p2g_warp<true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
-    else launch_p2g_warp<false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
+    if (fix && k.liquid_fast) launch_p2g_warp<true, true>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
+    else if (fix) launch_p2g_warp<true, false>(k, ps_in, ps_out, fix, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
+    else if (k.liquid_fast) launch_p2g_warp<false, true>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
+    else launch_p2g_warp<false, false>(k, ps_in, ps_out, grid, mu_s, la_s, vt_in, vt_out, svd_out, substep, ws, st, vt_svd);
     return;
   }
   // the attribute is per DEVICE (a process may drive several, one host thread each: SURVEY 8b): set it on every launch
@@ -1644,6 +1789,7 @@ void launch_g2p_bwd(const MpmConst& k, const float* ps_in, const float4* grid_ou
 //   gv = p_mass S            S = sum q            T_j = sum off_j q
 //   gA_ij = dx (T_ij - S_i fx_j)                  gfx(direct) = -dx A^T S
 //   gwt = p_mass g_m + g_p . (p_mass v + A dpos)  contracted hierarchically with (w, dw) over c, b, a
+template <bool LIQ>
 __global__ void __launch_bounds__(UD_BLOCK, 4)
 k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__ svd_in,
           const float4* __restrict__ ggrid, float* __restrict__ gs, const float* __restrict__ mu_s,
@@ -1660,7 +1806,7 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
   float4 nxq;
   int nmat;
   float nh;
-  auto issue = [&](const TilePos& tp) {
+  auto issue = [&](const TilePos& tp, int prev_mat) {
     int e2, g2, gp2;
     bool l2;
     tile_locate(k, w, tp, e2, g2, gp2, l2);
@@ -1670,12 +1816,12 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     // (one cp.async.bulk.prefetch.L2 per contiguous range from one lane instead of these 15 per-lane prefetches was
     // measured slower: 143.6 vs 141.3 us per launch)
     prefetch_quads<1, 5, PS_NQ>(ps_in, gp2);
-    prefetch_quads<0, 5, SV_NQ>(svd_in, gp2);
+    if (!LIQ || prev_mat != 0) prefetch_quads<0, 5, SV_NQ>(svd_in, gp2);   // (neighbouring tiles: same material, nearly always)
     prefetch_quads<0, 0, PS_NQ>(gs, gp2);
     prefetch_quads<3, 5, PS_NQ>(gs, gp2);
   };
   TilePos pos = tile_first(w);
-  issue(pos);
+  issue(pos, 1);
   for (; pos.t < w.ntiles;) {
   int env, g, gp;
   bool live_;
@@ -1685,7 +1831,7 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
   const float h_p = nh, mu_e = mu_s[env], la_e = la_s[env];
   const float x0[3] = {nxq.x, nxq.y, nxq.z};
   pos = tile_next(w, pos);
-  if (pos.t < w.ntiles) issue(pos);
+  if (pos.t < w.ntiles) issue(pos, mat_p);
   // the cotangents of the 27 nodes of each distinct base cell of the warp, fetched once per warp (dropped nodes = 0)
   int tile_gid = 0;
   bool tiled;
@@ -1703,6 +1849,7 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     Stencil st;
     float Ac[3][3], u0[3];
     const bool plastic = mat_p == 2;
+    const bool liquid = LIQ && mat_p == 0;
     {
       float xvc[15], us[12];
       Mat3 C, F;
@@ -1711,18 +1858,23 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
 #pragma unroll
       for (int c = 0; c < 9; ++c) C.m[c] = xvc[PS_C + c];
       make_stencil(xvc + PS_X, k.inv_dx, st);
-      load_comps<SV_U, 12, SV_NQ>(svd_in, gp, us);
-#pragma unroll
-      for (int c = 0; c < 9; ++c) o.U.m[c] = us[c];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) o.s[c] = us[9 + c];
-      if (plastic) {  // the stress of a plastic particle is a function of (U, clip(s)) alone
-        plastic_affine(k, C, o.U, o.s, mu_e, la_e, h_p, o.affine);
-      } else {
+      if (liquid) {   // no SVD was kept for a liquid particle (constitutive_post_liquid): J = |det F1|
         load_comps<PS_F, 9, PS_NQ>(ps_in, gp, F.m);
-        load_comps<SV_VT, 9, SV_NQ>(svd_in, gp, o.Vt.m);
-        constitutive_pre(k, C, F, mu_e, la_e, h_p, mat_p, o);
-        constitutive_post(k, C, o);
+        liquid_affine(k, C, F, o.affine);
+      } else {
+        load_comps<SV_U, 12, SV_NQ>(svd_in, gp, us);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) o.U.m[c] = us[c];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o.s[c] = us[9 + c];
+        if (plastic) {  // the stress of a plastic particle is a function of (U, clip(s)) alone
+          plastic_affine(k, C, o.U, o.s, mu_e, la_e, h_p, o.affine);
+        } else {
+          load_comps<PS_F, 9, PS_NQ>(ps_in, gp, F.m);
+          load_comps<SV_VT, 9, SV_NQ>(svd_in, gp, o.Vt.m);
+          constitutive_pre(k, C, F, mu_e, la_e, h_p, mat_p, o);
+          constitutive_post(k, C, o);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -1811,13 +1963,21 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     Consti o;
     float gx_in[3];
     {
-      float cf[18], sv[21];
+      float cf[18];
       load_comps<PS_C, 18, PS_NQ, true>(ps_in, gp, cf);
-      load_comps<0, 21, SV_NQ, true>(svd_in, gp, sv);
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
         C.m[c] = cf[c];
         F.m[c] = cf[9 + c];
+      }
+    }
+    {
+      // (a liquid particle has no SVD and ignores what it loads here -- its lanes read the first tile's lines, L1 hits;
+      // predicating the load instead costs the other materials' path 88 bytes of spills at the kernel's 128-register cap)
+      float sv[21];
+      load_comps<0, 21, SV_NQ, true>(svd_in, liquid ? (int)(threadIdx.x & 31) : gp, sv);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
         o.U.m[c] = sv[SV_U + c];
         o.Vt.m[c] = sv[SV_VT + c];
       }
@@ -1826,7 +1986,9 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
     }
     load_comps<PS_X, 3, PS_NQ>(gs, gp, gx_in);
     load_comps<PS_F, 9, PS_NQ>(gs, gp, gF2out.m);
-    if (plastic) {
+    if (liquid) {
+      constitutive_bwd_liquid(k, C, F, gA, gF2out, gC, gF);
+    } else if (plastic) {
       constitutive_bwd_plastic(k, C, F, o.U, o.s, o.Vt, mu_e, la_e, h_p, gA, gF2out, gC, gF, gmu, gla);
     } else {
       constitutive_pre(k, C, F, mu_e, la_e, h_p, mat_p, o);
@@ -1887,8 +2049,9 @@ void launch_p2g_bwd(const MpmConst& k, const float* ps_in, const float* svd_in, 
                     const float* la_s, bool first_substep, const MpmWs& ws, cudaStream_t st, const float4* ggrid) {
   KScope ks_(KC_P2G_BWD, st);
   if (first_substep) cudaMemsetAsync(ws.norm2, 0, 4 * (size_t)k.B * 2, st);
-  k_p2g_bwd<<<persistent_ctas(k, UD_BLOCK / 32, 4), UD_BLOCK, 0, st>>>(k, ps_in, svd_in, ggrid, ws.gs, mu_s, la_s, ws.mat_s,
-                                                     ws.h_s, ws.g_scal, first_substep ? ws.norm2 : nullptr);
+  auto kern = k.liquid_fast ? k_p2g_bwd<true> : k_p2g_bwd<false>;
+  kern<<<persistent_ctas(k, UD_BLOCK / 32, 4), UD_BLOCK, 0, st>>>(k, ps_in, svd_in, ggrid, ws.gs, mu_s, la_s, ws.mat_s, ws.h_s,
+                                                                 ws.g_scal, first_substep ? ws.norm2 : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

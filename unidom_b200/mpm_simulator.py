@@ -194,6 +194,7 @@ class SimpleMPMSimulator:
         self.device = torch.device(device)
         self.n_particles = 0
         self.material = None  # host int32 [n]   (mpm_simulator.py:57,117)
+        self._liq_cache = (None, False)
         self.h = None         # host float32 [n] (mpm_simulator.py:58,118)
         self.key_global = None
         if sdf_kind is None:
@@ -306,6 +307,16 @@ class SimpleMPMSimulator:
         return torch.from_numpy(jaxrng.split(kg, B).view(np.int32).copy())
 
     # ------------------------------------------------------------------------ the step
+    def _has_liquid(self):
+        """Material-0 particles in the scene -> UD_P2G_LIQUID_FAST (kernels with the SVD-free liquid path).  Only a
+        speed hint: without the flag liquid particles take the general path, with it other scenes pay a branch."""
+        m = self.material
+        if m is None:
+            return False
+        if self._liq_cache[0] != id(m):
+            self._liq_cache = (id(m), bool((torch.as_tensor(m).cpu() == 0).any()))
+        return self._liq_cache[1]
+
     def params(self, B=None, n=None):
         conf = self.conf
         p = _lib.MpmParams()
@@ -320,7 +331,7 @@ class SimpleMPMSimulator:
         p.n_primitive = int(conf.n_primitive)
         p.sdf_kind = self.sdf_kind
         p.use_position_control = int(bool(self.use_position_control))
-        p.p2g_mode = self.p2g_mode
+        p.p2g_mode = self.p2g_mode | (_lib.UD_P2G_LIQUID_FAST if self._has_liquid() else 0)
         return p
 
     def _pack(self, leaves, softness_list):
