@@ -166,7 +166,11 @@ def apg_update_leg(dev, dist, world, iters=20):
     for label, fused in (("nccl", False), ("fused", True)):
         if fused and not apg.fused_update_available(dev):
             continue
-        upd = apg.FusedUpdate(n, 1e-4, dev) if fused else None
+        try:
+            upd = apg.FusedUpdate(n, 1e-4, dev) if fused else None
+        except Exception as e:      # noqa: BLE001 -- e.g. no peer mapping between some pair of GPUs: keep the NCCL number
+            out["fused_error"] = repr(e)[:160]
+            continue
         p = params.clone()
         for _ in range(3):
             p = upd.step(p, grad, 0.3) if fused else opt.step(p, apg.reduce_policy_gradient(grad, 0.3)[0])
@@ -643,9 +647,6 @@ def main():
     e2e_value = world * units_per_step * args.steps / (e2e_ms * 1e-3)
     del dev_in, dev_out
 
-    # ---------------- the path's one collective, timed in the same run (N > 1)
-    apg_leg = apg_update_leg(dev, dist, world) if dist is not None else None
-
     # ---------------- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -676,7 +677,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "copies_per_step": 2, "host_gbs_per_rank": (h2d + d2h) / (e2e_ms / args.steps * 1e-3) / 1e9,
                     "host_gbs_all_ranks": world * (h2d + d2h) / (e2e_ms / args.steps * 1e-3) / 1e9, "numa": numa},
-            "apg_update": apg_leg,
+            "apg_update": None,
             "peak_hbm_bytes": peak_hbm,
             "gpu_launches": launches,
             "roofline": roofline,
@@ -685,9 +686,43 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+    else:
+        line = None
+
+    # ---------------- the path's one collective, timed in the same run (N > 1), AFTER every other number is in `line`:
+    # a watchdog prints the line without it if the leg (symmetric-memory rendezvous, flag barrier in peer memory) does
+    # not come back, so that a multi-GPU run can never end without its JSON line
+    emitted = threading.Event()
+
+    def emit(apg):
+        if not emitted.is_set():
+            emitted.set()
+            if line is not None:
+                line["apg_update"] = apg
+                print(json.dumps(line), flush=True)
+
     if dist is not None:
-        dist.destroy_process_group()
+        finished = threading.Event()
+
+        def watchdog():
+            if not finished.wait(180):
+                emit({"error": "apg_update leg did not finish within 180 s"})
+                os._exit(0)
+        threading.Thread(target=watchdog, daemon=True).start()
+        try:
+            apg_leg = apg_update_leg(dev, dist, world)
+        except Exception as e:      # noqa: BLE001
+            apg_leg = {"error": repr(e)[:200]}
+        emit(apg_leg)
+        threading.Timer(60, lambda: os._exit(0)).start()      # (a process group that cannot be torn down)
+        try:
+            dist.destroy_process_group()
+        except Exception:           # noqa: BLE001
+            pass
+        finished.set()
+        sys.stdout.flush()
+        os._exit(0)
+    emit(None)
 
 
 if __name__ == "__main__":
