@@ -163,9 +163,13 @@ def apg_update_leg(dev, dist, world, iters=20):
     params = torch.randn(n, generator=g).to(dev)
     opt = apg.Adam(n, 1e-4, dev)
     out = {}
-    for label, fused in (("nccl", False), ("fused", True)):
+    from unidom_b200 import _lib
+    # fused: all-read form (every rank reads all N staged gradients) and reduce-scatter + broadcast form, both timed;
+    # `fused_us` = the form the library uses by default (reduce-scatter)
+    for label, fused, rs in (("nccl", False, -1), ("fused_allread", True, 0), ("fused_rs", True, 1)):
         if fused and not apg.fused_update_available(dev):
             continue
+        _lib.lib().ud_tuning_set(b"apg_rs", rs)
         try:
             upd = apg.FusedUpdate(n, 1e-4, dev) if fused else None
         except Exception as e:      # noqa: BLE001 -- e.g. no peer mapping between some pair of GPUs: keep the NCCL number
@@ -186,6 +190,10 @@ def apg_update_leg(dev, dist, world, iters=20):
         t = torch.tensor([e0.elapsed_time(e1) / iters * 1e3], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[label + "_us"] = float(t.item())
+    _lib.lib().ud_tuning_set(b"apg_rs", -1)
+    pick = "fused_rs_us"
+    if pick in out:
+        out["fused_us"] = out[pick]
     out.update({"elements": n, "bytes_reduced_per_rank": 4 * n, "ranks": world,
                 "what": "scrub + per-rank global-norm clip -> mean over ranks -> Adam, per update, max over ranks"})
     return out

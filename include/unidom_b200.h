@@ -249,10 +249,12 @@ int ud_adam_step(float* params, const float* grad, float* m, float* v, int64_t n
  * per-rank global-norm clip, mean over the ranks, optax.adam -- identical arithmetic and order of operations to
  * ud_apg_scrub_clip -> all-reduce(sum) -> ud_adam_step(world_size).  The ranks exchange the clipped gradient through
  * peer-mapped device memory (NVLink): peer_stage[r] / peer_flags[r] are DEVICE arrays of `world` device pointers, one
- * per rank, to that rank's staging buffer (float[2 * n]) and flag array (int32[>= world], zeroed once before the first
- * call), valid in the calling process (cudaIpc / cuMem fabric handles / torch symmetric memory -- obtaining the mapping
+ * per rank, to that rank's staging buffer (float[4 * n]: two staging slots + two slots of the reduced gradient) and flag
+ * array (int32[64], zeroed once before the first call), valid in the calling process (cudaIpc / cuMem fabric handles / torch symmetric memory -- obtaining the mapping
  * is the caller's business).  t = 1, 2, ... must advance by one per call on every rank.  scratch: 8 floats.
- * Every rank sums the staged gradients in rank order, so replicas stay bit-identical.  world == 1 degenerates to
+ * Every rank sums the staged gradients in rank order, so replicas stay bit-identical.  A rank sums only
+ * its slice and stores the mean into every peer's reduced slot (reduce-scatter + broadcast over peer memory, a second
+ * flag barrier): 2 n instead of world * n elements over NVLink per rank, same bits.  world == 1 degenerates to
  * scrub + clip + Adam in one launch. */
 int ud_apg_fused_update(float* params, const float* grad, float* m, float* v, int64_t n, float max_grad_norm,
                         double lr, double b1, double b2, double eps, int32_t t, int32_t rank, int32_t world,

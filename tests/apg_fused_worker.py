@@ -21,6 +21,7 @@ def main():
     opt = apg.Adam(n, 1e-3, dev)
     upd = apg.FusedUpdate(n, 1e-3, dev)
     p_ref, p_fused = params.clone(), params.clone()
+    history = []
     for t in range(1, 6):
         gt = (torch.randn(n, generator=torch.Generator().manual_seed(100 * t + rank)) * (1e-3 if t < 4 else 1.0)).to(dev)
         red, _ = apg.reduce_policy_gradient(gt, 0.3)
@@ -39,6 +40,29 @@ def main():
         # a few ulp).  Where the two ranks' clipped gradients cancel to |g| ~ eps = 1e-8, Adam's g / (|g| + eps) turns
         # those ulps into a visible fraction of ONE step (lr = 1e-3): a handful of entries, bounded by 2 % of a step.
         assert err <= 0.02 * 1e-3 and frac < 1e-4, (err, frac)
+        history.append(p_fused.clone())
+    # the all-read form (every rank reads all N staged gradients; the A/B partner of the default reduce-scatter +
+    # broadcast form above): same sums in the same order
+    from unidom_b200 import _lib
+    assert _lib.lib().ud_tuning_set(b"apg_rs", 0) >= 0
+    upd_rs = apg.FusedUpdate(n, 1e-3, dev)
+    p_rs = params.clone()
+    for t in range(1, 6):
+        gt = (torch.randn(n, generator=torch.Generator().manual_seed(100 * t + rank)) * (1e-3 if t < 4 else 1.0)).to(dev)
+        p_rs = upd_rs.step(p_rs, gt, 0.3)
+        torch.cuda.synchronize()
+        # the per-rank sum of squares is accumulated with fp32 atomics (order-dependent), so the clip factor of the
+        # large-gradient iterations may differ by an ulp between two runs: compare to the same tolerance as above and
+        # demand identical replicas
+        dp = (p_rs - history[t - 1]).abs()
+        other = p_rs.clone()
+        dist.broadcast(other, 0)
+        print(f"[rank {rank}] t={t}: all-read form vs reduce-scatter form max |dp| {float(dp.max()):.3e}; "
+              f"bit-identical to the reduce-scatter form: {bool(torch.equal(p_rs, history[t - 1]))}; replicas identical: "
+              f"{bool(torch.equal(other, p_rs))}", flush=True)
+        assert torch.equal(other, p_rs), "replicas diverged (all-read form)"
+        assert float(dp.max()) <= 0.02 * 1e-3
+    _lib.lib().ud_tuning_set(b"apg_rs", -1)
     dist.barrier()
     if rank == 0:
         print("fused update ok")

@@ -174,7 +174,8 @@ class FusedUpdate:
         self.t = 0
         self._L = _lib.lib()
         # two staging slots (iteration parity): a rank may start staging iteration t+1 while a peer still reads t
-        self.stage = symm_mem.empty(2 * n, dtype=torch.float32, device=self.device)
+        # + two slots of the reduced gradient (reduce-scatter + broadcast form)
+        self.stage = symm_mem.empty(4 * n, dtype=torch.float32, device=self.device)
         self.flags = symm_mem.empty(64, dtype=torch.int32, device=self.device)
         self.flags.zero_()
         h_stage = symm_mem.rendezvous(self.stage, self.group.group_name)

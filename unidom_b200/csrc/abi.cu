@@ -51,6 +51,7 @@ int tuning_sort() { return g_sort; }
 int tuning_stage() { return g_stage; }
 int tuning_warp(int v);   // mpm_particles.cu
 int tuning_pers(int v);
+int tuning_apg_rs(int v);
 
 bool mpm_fold_constants(const ud_mpm_params* p, MpmConst* k) {
   if (!p) return false;
@@ -208,6 +209,7 @@ int ud_tuning_set(const char* name, int value) {
   if (name && !strcmp(name, "warp")) return tuning_warp(value);
   if (name && !strcmp(name, "pers")) return tuning_pers(value);
   if (name && !strcmp(name, "cloth_cta_nodes")) return cloth_tuning_cta_nodes(value);
+  if (name && !strcmp(name, "apg_rs")) return tuning_apg_rs(value) + 1;   // (old value + 1: the old value may be -1 = auto)
   return -1;
 }
 int ud_timing_num_classes(void) { return KC_COUNT; }
