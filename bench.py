@@ -165,7 +165,7 @@ def apg_update_leg(dev, dist, world, iters=20):
     out = {}
     from unidom_b200 import _lib
     # fused: all-read form (every rank reads all N staged gradients) and reduce-scatter + broadcast form, both timed;
-    # `fused_us` = the form the library uses by default (reduce-scatter)
+    # `fused_us` = the form the library picks for this world size (reduce-scatter from 4 ranks up)
     for label, fused, rs in (("nccl", False, -1), ("fused_allread", True, 0), ("fused_rs", True, 1)):
         if fused and not apg.fused_update_available(dev):
             continue
@@ -191,7 +191,7 @@ def apg_update_leg(dev, dist, world, iters=20):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[label + "_us"] = float(t.item())
     _lib.lib().ud_tuning_set(b"apg_rs", -1)
-    pick = "fused_rs_us"
+    pick = "fused_rs_us" if world >= 4 else "fused_allread_us"
     if pick in out:
         out["fused_us"] = out[pick]
     out.update({"elements": n, "bytes_reduced_per_rank": 4 * n, "ranks": world,

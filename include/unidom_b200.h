@@ -252,7 +252,7 @@ int ud_adam_step(float* params, const float* grad, float* m, float* v, int64_t n
  * per rank, to that rank's staging buffer (float[4 * n]: two staging slots + two slots of the reduced gradient) and flag
  * array (int32[64], zeroed once before the first call), valid in the calling process (cudaIpc / cuMem fabric handles / torch symmetric memory -- obtaining the mapping
  * is the caller's business).  t = 1, 2, ... must advance by one per call on every rank.  scratch: 8 floats.
- * Every rank sums the staged gradients in rank order, so replicas stay bit-identical.  A rank sums only
+ * Every rank sums the staged gradients in rank order, so replicas stay bit-identical.  From 4 ranks up a rank sums only
  * its slice and stores the mean into every peer's reduced slot (reduce-scatter + broadcast over peer memory, a second
  * flag barrier): 2 n instead of world * n elements over NVLink per rank, same bits.  world == 1 degenerates to
  * scrub + clip + Adam in one launch. */

@@ -11,12 +11,12 @@
 //      replicas stay bit-identical without a broadcast --, divides by N and applies Adam to its replica.
 // Staging is double-buffered by iteration parity: a rank may stage iteration t+1 while a peer still reads t; it can
 // only reach t+2 after every peer has signalled t+1, i.e. has finished reading t.
-// By default (ud_tuning_set("apg_rs", 0) keeps the all-read form as the A/B partner) step 4 is reduce-scatter +
+// From UD_APG_RS_MIN_WORLD ranks up (ud_tuning_set("apg_rs", 0 / 1) forces either form) step 4 is reduce-scatter +
 // broadcast (RS): a rank sums only ITS slice of the staged
 // gradients (rank order again), stores the mean of the slice into every peer's `reduced` buffer (P2P stores), the ranks
 // meet at a second flag barrier and Adam then reads local memory only: 2 n instead of N n elements over NVLink per rank
-// (at N = 8 the all-read form tied with NCCL: 124 vs 118 us per update; at N = 2 the two forms move the same bytes and RS
-// still wins, 58 vs 67 us, through its 16-byte accesses).  Same sums in the same order as the all-read form.
+// (at N = 8 the scalar all-read form tied with NCCL: 124 vs 118 us per update; at N = 2 the two forms move the same bytes
+// and the all-read form wins by its one barrier less, 48 vs 54 us).  Same sums in the same order as the all-read form.
 // Arithmetic and rounding are those of k_apg_clip / k_adam_step (csrc/reward.cu): op-by-op, no FMA contraction.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -65,17 +65,30 @@ __global__ void __launch_bounds__(FB)
 k_apg_fused(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, long long n,
             float max_norm, float lr, float b1, float b2, float omb1, float omb2, float eps, float c1, float c2, int t,
             int rank, int world, const unsigned long long* __restrict__ peer_stage,
-            const unsigned long long* __restrict__ peer_flags, float* __restrict__ scratch) {
+            const unsigned long long* __restrict__ peer_flags, float* __restrict__ scratch, bool vec) {
   __shared__ float red[FB / 32];
   unsigned* ctr = reinterpret_cast<unsigned*>(scratch) + 1;
   const long long tid = (long long)blockIdx.x * FB + threadIdx.x, nthr = (long long)gridDim.x * FB;
   const size_t slot = (size_t)(t & 1) * (size_t)n;
   float* my_stage = reinterpret_cast<float*>(peer_stage[rank]) + slot;
   // ---- 1. per-rank squared norm of the scrubbed gradient
+  // vec (launcher: n % 4 == 0 and 16-byte aligned arrays): every pass moves float4; per element the same operations
+  const long long n4 = n >> 2;
   float acc = 0.f;
-  for (long long i = tid; i < n; i += nthr) {
-    const float g = scrub(grad[i]);
-    acc += g * g;
+  if (vec) {
+    for (long long q = tid; q < n4; q += nthr) {
+      const float4 g4 = reinterpret_cast<const float4*>(grad)[q];
+      const float g0 = scrub(g4.x), g1 = scrub(g4.y), g2 = scrub(g4.z), g3 = scrub(g4.w);
+      acc += g0 * g0;
+      acc += g1 * g1;
+      acc += g2 * g2;
+      acc += g3 * g3;
+    }
+  } else {
+    for (long long i = tid; i < n; i += nthr) {
+      const float g = scrub(grad[i]);
+      acc += g * g;
+    }
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
@@ -90,9 +103,19 @@ k_apg_fused(float* __restrict__ p, const float* __restrict__ grad, float* __rest
   // ---- 2. clip (apg.py:264-266, evaluated as written) and stage for the peers
   const float norm = sqrtf(__ldcg(scratch));
   const bool clip = !(norm < max_norm);
-  for (long long i = tid; i < n; i += nthr) {
-    const float g = scrub(grad[i]);
-    my_stage[i] = clip ? (g / norm) * max_norm : g;
+  if (vec) {
+    for (long long q = tid; q < n4; q += nthr) {
+      const float4 g4 = reinterpret_cast<const float4*>(grad)[q];
+      const float g0 = scrub(g4.x), g1 = scrub(g4.y), g2 = scrub(g4.z), g3 = scrub(g4.w);
+      reinterpret_cast<float4*>(my_stage)[q] =
+          clip ? make_float4((g0 / norm) * max_norm, (g1 / norm) * max_norm, (g2 / norm) * max_norm, (g3 / norm) * max_norm)
+               : make_float4(g0, g1, g2, g3);
+    }
+  } else {
+    for (long long i = tid; i < n; i += nthr) {
+      const float g = scrub(grad[i]);
+      my_stage[i] = clip ? (g / norm) * max_norm : g;
+    }
   }
   __threadfence_system();
   grid_barrier(ctr + 1, gridDim.x);
@@ -110,8 +133,8 @@ k_apg_fused(float* __restrict__ p, const float* __restrict__ grad, float* __rest
   const float fw = (float)world;
   const float* reduced = nullptr;
   if (RS) {
-    // my slice, in whole float4 (n4 = n / 4 quads; the last rank also takes the n % 4 tail as scalars)
-    const long long n4 = n >> 2, per = (n4 + world - 1) / world;
+    // my slice, in whole float4 (the launcher picks this form only when vec holds, so there is no tail)
+    const long long per = (n4 + world - 1) / world;
     const long long q0 = per * rank < n4 ? per * rank : n4, q1 = q0 + per < n4 ? q0 + per : n4;
     const size_t rslot = (size_t)(2 + (t & 1)) * (size_t)n;   // `reduced` lives behind the two staging slots
     for (long long q = q0 + tid; q < q1; q += nthr) {
@@ -125,16 +148,6 @@ k_apg_fused(float* __restrict__ p, const float* __restrict__ grad, float* __rest
       for (int r = 0; r < world; ++r)
         __stcg(reinterpret_cast<float4*>(reinterpret_cast<float*>(peer_stage[r]) + rslot) + q, acc);
     }
-    if (rank == world - 1)
-      for (long long i = (n4 << 2) + tid; i < n; i += nthr) {
-        float acc = 0.f;
-        for (int r = 0; r < world; ++r) {
-          const float a = __ldcg(reinterpret_cast<const float*>(peer_stage[r]) + slot + i);
-          acc = r == 0 ? a : __fadd_rn(acc, a);
-        }
-        acc = acc / fw;
-        for (int r = 0; r < world; ++r) __stcg(reinterpret_cast<float*>(peer_stage[r]) + rslot + i, acc);
-      }
     __threadfence_system();
     grid_barrier(ctr + 2, gridDim.x);
     // second flag barrier: every rank's slice has landed in my `reduced` buffer
@@ -148,6 +161,38 @@ k_apg_fused(float* __restrict__ p, const float* __restrict__ grad, float* __rest
     __syncthreads();
     reduced = reinterpret_cast<const float*>(peer_stage[rank]) + rslot;
   }
+  auto adam = [&](float gi, float mo, float vo, float po, float& mn, float& vn, float& pn) {
+    mn = __fadd_rn(__fmul_rn(b1, mo), __fmul_rn(omb1, gi));
+    vn = __fadd_rn(__fmul_rn(b2, vo), __fmul_rn(__fmul_rn(omb2, gi), gi));
+    const float mhat = __fdiv_rn(mn, c1), vhat = __fdiv_rn(vn, c2);
+    pn = __fsub_rn(po, __fdiv_rn(__fmul_rn(lr, mhat), __fadd_rn(__fsqrt_rn(vhat), eps)));
+  };
+  if (vec) {
+    for (long long q = tid; q < n4; q += nthr) {
+      float4 g4;
+      if (RS) {
+        g4 = __ldcg(reinterpret_cast<const float4*>(reduced) + q);
+      } else {
+        for (int r = 0; r < world; ++r) {
+          const float4 a = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(peer_stage[r]) + slot) + q);
+          if (r == 0) g4 = a;
+          else g4 = make_float4(__fadd_rn(g4.x, a.x), __fadd_rn(g4.y, a.y), __fadd_rn(g4.z, a.z), __fadd_rn(g4.w, a.w));
+        }
+        if (world > 1) g4 = make_float4(g4.x / fw, g4.y / fw, g4.z / fw, g4.w / fw);
+      }
+      const float4 m4 = reinterpret_cast<const float4*>(m)[q], v4 = reinterpret_cast<const float4*>(v)[q],
+                   p4 = reinterpret_cast<const float4*>(p)[q];
+      float4 mn, vn, pn;
+      adam(g4.x, m4.x, v4.x, p4.x, mn.x, vn.x, pn.x);
+      adam(g4.y, m4.y, v4.y, p4.y, mn.y, vn.y, pn.y);
+      adam(g4.z, m4.z, v4.z, p4.z, mn.z, vn.z, pn.z);
+      adam(g4.w, m4.w, v4.w, p4.w, mn.w, vn.w, pn.w);
+      reinterpret_cast<float4*>(m)[q] = mn;
+      reinterpret_cast<float4*>(v)[q] = vn;
+      reinterpret_cast<float4*>(p)[q] = pn;
+    }
+    return;
+  }
   for (long long i = tid; i < n; i += nthr) {
     float gi;
     if (RS) {
@@ -160,12 +205,11 @@ k_apg_fused(float* __restrict__ p, const float* __restrict__ grad, float* __rest
       }
       gi = world == 1 ? s : s / fw;
     }
-    const float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(omb1, gi));
-    const float vi = __fadd_rn(__fmul_rn(b2, v[i]), __fmul_rn(__fmul_rn(omb2, gi), gi));
+    float mi, vi, pi;
+    adam(gi, m[i], v[i], p[i], mi, vi, pi);
     m[i] = mi;
     v[i] = vi;
-    const float mhat = __fdiv_rn(mi, c1), vhat = __fdiv_rn(vi, c2);
-    p[i] = __fsub_rn(p[i], __fdiv_rn(__fmul_rn(lr, mhat), __fadd_rn(__fsqrt_rn(vhat), eps)));
+    p[i] = pi;
   }
 }
 
@@ -173,7 +217,7 @@ k_apg_fused(float* __restrict__ p, const float* __restrict__ grad, float* __rest
 
 // ud_tuning_set("apg_rs", v): -1 = reduce-scatter form from UD_APG_RS_MIN_WORLD ranks up (default), 0 = never, 1 = always
 #ifndef UD_APG_RS_MIN_WORLD
-#define UD_APG_RS_MIN_WORLD 2
+#define UD_APG_RS_MIN_WORLD 4
 #endif
 static int g_apg_rs = -1;
 int tuning_apg_rs(int v) {
@@ -199,11 +243,13 @@ extern "C" int ud_apg_fused_update(float* params, const float* grad, float* m, f
   long long want = (n + FB - 1) / FB;
   const int blocks = (int)(want < 2LL * sms ? want : 2LL * sms);   // resident by construction: 2 x 256 threads per SM
   const float c1 = (float)(1.0 - pow(b1, (double)t)), c2 = (float)(1.0 - pow(b2, (double)t));
-  const bool rs = world > 1 && (g_apg_rs == 1 || (g_apg_rs < 0 && world >= UD_APG_RS_MIN_WORLD));
+  const bool vec = n % 4 == 0 && (((uintptr_t)params | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0;   // (the
+  // staging buffers are the caller's symmetric allocations: 16-byte aligned by contract, their slots by n % 4 == 0)
+  const bool rs = vec && world > 1 && (g_apg_rs == 1 || (g_apg_rs < 0 && world >= UD_APG_RS_MIN_WORLD));
   auto kern = rs ? k_apg_fused<true> : k_apg_fused<false>;
   kern<<<blocks, FB, 0, st>>>(params, grad, m, v, (long long)n, max_grad_norm, (float)lr, (float)b1, (float)b2,
                                      (float)(1.0 - b1), (float)(1.0 - b2), (float)eps, c1, c2, (int)t, (int)rank, (int)world,
                                      reinterpret_cast<const unsigned long long*>(peer_stage),
-                                     reinterpret_cast<const unsigned long long*>(peer_flags), scratch);
+                                     reinterpret_cast<const unsigned long long*>(peer_flags), scratch, vec);
   return cudaGetLastError() == cudaSuccess ? UD_OK : set_error(UD_E_CUDA, "ud_apg_fused_update: launch failed");
 }
