@@ -755,15 +755,13 @@ __device__ __forceinline__ void p2g_front_loaded(const MpmConst& k, int gp, bool
   } else {
     constitutive_post(k, C, o, all_plastic);
     if (LIQ) {
-      Consti ol;
-      ol.F1 = o.F1;
-      ol.la = 1.f;
-      constitutive_post_liquid(k, C, ol);
+      // the general path already gave a liquid lane F2 = F1 and affine = p_mass C off the diagonal (mu = 0); only the
+      // isotropic term changes with J (constitutive_post_liquid's expression)
+      const float Jd = fabsf(det3_pivoted(o.F1));
+      const float iso_l = o.la * Jd * (Jd - 1.f);
+      const float cs = k.c_stress_mul / k.c_stress_div;
 #pragma unroll
-      for (int c = 0; c < 9; ++c) {
-        o.affine.m[c] = liq ? ol.affine.m[c] : o.affine.m[c];
-        o.F2.m[c] = liq ? ol.F2.m[c] : o.F2.m[c];
-      }
+      for (int i = 0; i < 3; ++i) o.affine(i, i) = liq ? cs * iso_l + k.p_mass * C(i, i) : o.affine(i, i);
     }
   }
   if (wr) {   // padding lanes of an env's last tile write too: the next substep's dead lanes read initialised memory
