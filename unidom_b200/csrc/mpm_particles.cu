@@ -625,11 +625,7 @@ constexpr int G2PB_NPH = 27;
 #define UD_NT_STRIDE 33
 #endif
 constexpr int NT_STRIDE = UD_NT_STRIDE;
-#ifndef UD_G2P_TILE_CELLS
-#define UD_G2P_TILE_CELLS 4
-#endif
-constexpr int G2P_TILE_CELLS = UD_G2P_TILE_CELLS;   // (a multiple of 4: the tile is filled four cells at a time)
-constexpr int G2P_TILE_SLOTS = G2P_TILE_CELLS * NT_STRIDE;   // float4 slots of a warp's node tile
+constexpr int G2P_TILE_CELLS = 4;
 // One-tile-per-warp kernels: every warp asks L2 for the quads a warp one wave of CTAs later will load first (the CTAs
 // are dispatched in tile order), so that warp's first dependent load is an L2 hit instead of a DRAM round trip.
 // Measured: k_g2p_bwd_warp 113.5 -> 110.5 us; nothing for k_g2p (45.8 / 45.9), where it is not used.
@@ -643,7 +639,7 @@ __device__ __forceinline__ void ahead_prefetch(const MpmConst& k, const float* _
     if (gpa < k.N_pad) prefetch_quads<Q0, Q1, NQ>(base, gpa);
   }
 }
-static_assert(G2P_TILE_CELLS % 4 == 0 && NT_STRIDE >= 27, "node tile: whole batches of four cells, 27 nodes per cell");    // distinct base cells per warp whose stencils k_g2p keeps in shared memory
+static_assert((G2P_TILE_CELLS - 1) * NT_STRIDE + 27 <= G2P_TILE_CELLS * 32, "node tile: the padded cells must fit");    // distinct base cells per warp whose stencils k_g2p keeps in shared memory
 constexpr int G2PB_TILE_RUNS = 12;  // segments whose 27 grid velocities k_g2p_bwd keeps in shared memory (5.2 KB: the CTA
                                     // stays at 4 per SM); CTAs with more distinct cells gather from L1/L2 as before
 constexpr size_t g2pb_tile_offset() { return (stage_smem_bytes<G2PB_BLOCK>(3, G2PB_NPH) + 15) & ~(size_t)15; }
@@ -1259,15 +1255,11 @@ __device__ __forceinline__ bool warp_tile_fill(const MpmConst& k, const float4* 
   if (tiled) {
     const int jn = lane < 27 ? lane : 0;
     const int a = jn / 9, b = (jn / 3) % 3, c = jn % 3;
+    float4 tmp[G2P_TILE_CELLS];
     unsigned bits = lb;
 #pragma unroll
-    for (int ge0 = 0; ge0 < G2P_TILE_CELLS; ge0 += 4) {   // four cells' loads in flight at a time (registers)
-    if (ge0 >= ngroups) break;   // warp-uniform
-    float4 tmp[4];
-#pragma unroll
-    for (int gi = 0; gi < 4; ++gi) {
-      const int ge = ge0 + gi;
-      tmp[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ge = 0; ge < G2P_TILE_CELLS; ++ge) {
+      tmp[ge] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ge < ngroups) {   // warp-uniform
         const int L = __ffs(bits) - 1;
         bits &= bits - 1;
@@ -1283,13 +1275,12 @@ __device__ __forceinline__ bool warp_tile_fill(const MpmConst& k, const float4* 
           iy = idx_scatter(by + b, k.ry);
           iz = idx_scatter(bz + c, k.rz);
         }
-        if (lane < 27 && (CLAMP || (ix | iy | iz) >= 0)) tmp[gi] = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
+        if (lane < 27 && (CLAMP || (ix | iy | iz) >= 0)) tmp[ge] = __ldg(&genv[(ix * k.ry + iy) * k.rz + iz]);
       }
     }
 #pragma unroll
-    for (int gi = 0; gi < 4; ++gi)
-      if (ge0 + gi < ngroups && lane < 27) tile[(ge0 + gi) * NT_STRIDE + lane] = tmp[gi];
-    }
+    for (int ge = 0; ge < G2P_TILE_CELLS; ++ge)
+      if (ge < ngroups && lane < 27) tile[ge * NT_STRIDE + lane] = tmp[ge];
     __syncwarp();
   }
   return tiled;
@@ -1372,7 +1363,7 @@ __device__ __forceinline__ void g2p_gather(const MpmConst& k, const float4* __re
 __global__ void __launch_bounds__(UD_BLOCK, UD_G2P_MINB)
 k_g2p(MpmConst k, const float* ps_in, float* ps_out, const float4* __restrict__ grid,
       const int32_t* __restrict__ perm, float* __restrict__ jrows, int substep) {
-  __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_SLOTS];
+  __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_CELLS * 32];
   UD_PARTICLE_INDEX_REV(k, env, g);
   if (slot_ - (int)(threadIdx.x & 31) >= k.n) return;   // warp-uniform
   const int p = perm[g];   // needed only at the end: issued with the first load
@@ -1805,7 +1796,7 @@ k_p2g_bwd(MpmConst k, const float* __restrict__ ps_in, const float* __restrict__
   // norm2 != nullptr on the step's first substep (the last one reversed): the cotangents written here are the
   // step's input cotangents, so norm_grad_state's nan_to_num + per-env sum of squares (mpm_simulator.py:389-408)
   // happen on the way out instead of in a separate pass over the 24 components
-  __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_SLOTS];
+  __shared__ float4 wtile[UD_BLOCK / 32][G2P_TILE_CELLS * 32];
   const TileWalk w = tile_walk(k);
   if (w.t >= w.ntiles) return;
   // Persistent: what the tile fill needs first (x quad, material, hardness) is loaded one tile ahead into registers;
