@@ -240,8 +240,25 @@ grid_fwd_body(const MpmConst& k, float4* grid_in, float4* grid_out, long long* _
         }
       }
     }
-    if (!in_range) continue;
     const bool on_shell = ci == 0 || cj == 0 || ck == 0 || ci == k.rx - 1 || cj == k.ry - 1 || ck == k.rz - 1;
+    const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
+    // Scenes with several primitives (pour_water: two bowls, each out of reach of the other's liquid): a primitive that
+    // no cell of this half-block is within reach of (influence below 1e-12, i.e. 1 - influence rounds to 1; the same
+    // test the empty cells and the adjoint use) is skipped for the whole warp -- a warp-uniform decision, no divergence.
+    // With ONE primitive the test does not pay (see below) and every cell with mass evaluates it, as in the reference.
+    unsigned reach = 0xffffffffu;
+    if (k.n_prim >= 2) {   // kernel-uniform; all 32 lanes are here (branch-free per lane: votes with the full mask)
+      reach = 0u;
+      const bool work = in_range && (has_mass || on_shell);
+#pragma unroll 1
+      for (int q = 0; q < k.n_prim; ++q) {
+        PrimIn<float> pr;
+        load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
+        const bool a = prim_active(k, gpos, pr) && work;
+        if (__any_sync(0xffffffffu, a)) reach |= 1u << q;
+      }
+    }
+    if (!in_range) continue;
     if (!has_mass && !on_shell) {  // empty interior cell: never gathered with a non-zero weight
       if (grid_out != grid_in || grid_fix) grid_out[idx] = g;
       continue;
@@ -252,10 +269,10 @@ grid_fwd_body(const MpmConst& k, float4* grid_in, float4* grid_out, long long* _
     // the pusher, nearly every 4x4x4 block has an active lane, and the extra test made the kernel 25 % longer.)
     // Every cell of a listed block is this job's, its EMPTY boundary cells included (the shell job skips listed
     // blocks): those skip primitives without influence and are listed for k_grid_bwd when one acts on them.
-    const float gpos[3] = {(float)ci * k.dx, (float)cj * k.dx, (float)ck * k.dx};
     float p[3] = {g.x, g.y, g.z}, v[3];
     bool any_active = false;
     auto prim_of = [&](int q, PrimIn<float>& pr) {
+      if (!((reach >> q) & 1u)) return false;   // warp-uniform
       load_prim_f<float>(k, in, fk_pos, fk_rot, fk_vw, env, q, f, pr);
       if (has_mass) return true;
       const bool a = prim_active(k, gpos, pr);
