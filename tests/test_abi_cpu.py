@@ -35,8 +35,14 @@ def test_workspace_query_and_validation_without_gpu(built_lib):
     assert L.ud_mpm_num_keys(ctypes.byref(p)) == 12 * 8 * 12 * 64
     p.n_primitive = 9          # invalid
     assert L.ud_mpm_fwd_workspace_bytes(ctypes.byref(p)) == 0
-    # null pointers are rejected before anything is enqueued
+    # p2g_mode: UD_P2G_ATOMIC / UD_P2G_DETERMINISTIC, optionally OR-ed with the UD_P2G_LIQUID_FAST flag; nothing else
     p.n_primitive = 1
+    for mode, ok in ((0, True), (1, True), (_lib.UD_P2G_LIQUID_FAST, True), (1 | _lib.UD_P2G_LIQUID_FAST, True),
+                     (2, False), (7, False), (2 | _lib.UD_P2G_LIQUID_FAST, False), (0x200, False)):
+        p.p2g_mode = mode
+        assert (L.ud_mpm_fwd_workspace_bytes(ctypes.byref(p)) > 0) == ok, mode
+    p.p2g_mode = 0
+    # null pointers are rejected before anything is enqueued
     rc = L.ud_mpm_step_fwd(ctypes.byref(p), None, None, None, None, None, None, 0, None)
     assert rc == -1
 
