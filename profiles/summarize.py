@@ -19,6 +19,10 @@ WANT = [
     "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_sector_hit_rate.pct", "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum",
     "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum", "smsp__inst_executed_op_global_red.sum",
+    "lts__t_requests_srcunit_tex_op_red.sum", "lts__t_sectors_srcunit_tex_op_red.sum",
+    "lts__t_sectors_srcunit_tex_op_red_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_red.avg.per_cycle_elapsed",
+    "lts__t_sectors_srcunit_tex_op_red.avg.peak_sustained", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sector_hit_rate.pct",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
