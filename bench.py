@@ -314,13 +314,81 @@ def cpu_oracle_rate(conf, n_envs, density, substeps, repeat, threads):
     return n_envs * n * substeps / best, n, best
 
 
+def shim_reference_rate(density, substeps, repeat, threads):
+    """particle-substeps/s (fwd+bwd) of the UNMODIFIED reference sources -- daxbench.core.engine.mpm_simulator.
+    SimpleMPMSimulator.step_jax and jax.grad through its own custom_vjp rules -- executed under oracle/jaxshim (a
+    torch-CPU stand-in for the jax API the path uses; JAX itself is not installable here), on the same bounded sample as
+    cpu_oracle_rate.  Only where the reference tree exists (this container: /root/reference does not travel to the
+    GPU box).  Returns (rate, n, seconds) or None."""
+    ref = os.environ.get("UNIDOM_REFERENCE", "/root/reference/DaXBench")
+    if not os.path.isdir(ref):
+        return None
+    import numpy as np
+    torch.set_num_threads(threads)
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "oracle"))
+    import gen_golden as gg
+    mods = gg.load_reference(False)
+    import jax
+    import jax.numpy as jnp
+    mpm, _, prim, box, _ = mods
+    conf = gg.MPMConf(jnp, jax.random.PRNGKey(0), n_grid=96, res=(48, 32, 48), dt=2e-4, steps=substeps, E=2, nu=0.2,
+                      ground_friction=2, n_primitive=1)
+    prim.set_sdf(box._sdf_batch)
+    sim = mpm.SimpleMPMSimulator(conf, 1, use_position_control=False)
+    sim.key_global = jax.random.PRNGKey(1)
+    state = sim.add_box(conf=conf, state=None, hardness=1.0, size=[0.2, 0.06, 0.12], init_pos=[0.25, 0.07, 0.25],
+                        z_rotation_angle=0, material=2, density=density)
+    p = prim.create_primitive(conf, friction=0.1, softness=666, color=[0.5] * 3, size=[0.015, 0.06, 0.015],
+                              init_pos=[0.25, 0.01, 0.20])
+    state = sim.reset_jax(state._replace(primitives=[p]))
+    n = state.x.shape[1]
+    action = jnp.array(np.array([[0.003, 0.0, 0.004, 0.0, 0.0, 0.0]], np.float32))
+    cx = jnp.array((np.random.RandomState(0).randn(1, n, 3) * 1e-3).astype(np.float32))
+
+    def loss(inp):
+        st, act = inp
+        ns, _ = sim.step_jax(st, act)
+        return (ns.x * cx).sum()
+    best = None
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        jax.grad(loss, allow_int=True)((state, action))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n * substeps / best, n, best
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path.  The reference itself (JAX) cannot
     be installed in this image (no jax/jaxlib wheel, no network), so this times the oracle PORT
-    (oracle/, a torch-CPU restatement of the same arithmetic) with all host threads."""
+    (oracle/, a torch-CPU restatement of the same arithmetic) with all host threads.  `--ref-kind shim` (only where
+    /root/reference exists, i.e. in the build container, not on the GPU box) times the unmodified reference sources
+    under oracle/jaxshim instead and reports the port beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.ref_kind == "shim":
+        threads = os.cpu_count() or 1
+        sub = 2
+        got = shim_reference_rate(DENSITY, sub, max(args.steps, 1), threads)
+        if got is not None:
+            rate, n, secs = got
+            from unidom_b200 import confs
+            port, _, _ = cpu_oracle_rate(confs.shape_elasto_plastic_conf(), 1, DENSITY, sub, 2, threads)
+            line = {
+                "impl": "reference", "metric": "particle-substeps/s fwd+bwd", "value": rate, "unit": "particle-substeps/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(n), "sample": f"1 env x {n} particles x {sub} substeps fwd+bwd per step"},
+                "cpu_baseline": {"value": rate, "unit": "particle-substeps/s", "cores": threads, "kind": "shim",
+                                 "sample": f"1 env x {n} particles x {sub} substeps fwd+bwd (best of {max(args.steps, 1)}), the "
+                                           "unmodified reference SimpleMPMSimulator.step_jax + jax.grad under oracle/jaxshim "
+                                           "(torch-CPU)", "port_value": port},
+                "e2e": {"value": rate, "unit": "particle-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            }
+            print(json.dumps(line))
+            return
     from unidom_b200 import confs
     conf = confs.shape_elasto_plastic_conf()
     threads = os.cpu_count() or 1
@@ -418,6 +486,9 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-kind", default="port", choices=["port", "shim"],
+                    help="--impl reference: the oracle port (default; the only one available on the GPU box) or the "
+                         "unmodified reference sources under oracle/jaxshim (where /root/reference exists)")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--density", type=float, default=DENSITY)
     ap.add_argument("--no-cpu-baseline", action="store_true")
